@@ -1,0 +1,534 @@
+/*
+ * ldu_oracle_gamg.c -- CPU restatement of the RapidCFD-dev GAMG solver (pair
+ * agglomeration, coarse addressing, Galerkin-by-summation coarse matrices, V-cycle).
+ * TEST INFRASTRUCTURE ONLY (see ldu_oracle.h).  PARITY UNPINNED by reference tests.
+ *
+ * Paths relative to /root/reference/src/OpenFOAM/matrices/lduMatrix/solvers/GAMG/
+ * (abbreviated GAMG/).  Serial (single-domain) only in this round: coupled-patch
+ * agglomeration (processorGAMGInterface.C:93-137) is not restated yet.
+ */
+#include "ldu_oracle_internal.h"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_MAX_LEVELS 50 /* GAMGAgglomeration.C:94 maxLevels_(50) */
+
+struct orc_gamg {
+    int nLevels;                       /* coarse levels created */
+    orc_addr *addr[ORC_MAX_LEVELS];    /* coarse level addressing, [0] = first coarse */
+    int *restrictAddr[ORC_MAX_LEVELS]; /* cells of level k (0 = finest) -> cells of coarse k */
+    int *faceRestrict[ORC_MAX_LEVELS]; /* faces of level k -> coarse face or -(cell+1) */
+    unsigned char *faceFlip[ORC_MAX_LEVELS];
+    int nFineCells[ORC_MAX_LEVELS], nFineFaces[ORC_MAX_LEVELS];
+    const orc_addr *finest;
+};
+
+/* pairGAMGAgglomeration::agglomerate(nCoarseCells, addr, faceWeights):
+ * GAMGAgglomerations/pairGAMGAgglomeration/pairGAMGAgglomerate.C:135-313 */
+static int *pair_agglomerate(const orc_addr *a, const double *w, int *nCoarseOut, int *forward)
+{
+    int n = a->nCells, nf = a->nFaces;
+    const int *up = a->u, *lo = a->l;
+    int *off = (int *)calloc((size_t)n + 1, sizeof(int));
+    int *cnt = (int *)calloc((size_t)n + 1, sizeof(int));
+    int *cf = (int *)malloc(sizeof(int) * (size_t)(2 * nf + 1));
+    for (int f = 0; f < nf; f++) cnt[up[f]]++;
+    for (int f = 0; f < nf; f++) cnt[lo[f]]++;
+    for (int c = 0; c < n; c++) off[c + 1] = off[c] + cnt[c];
+    memset(cnt, 0, sizeof(int) * ((size_t)n + 1));
+    /* per cell: first the faces where it is neighbour (upperAddr hits), then the
+     * faces it owns (:172-192) */
+    for (int f = 0; f < nf; f++) cf[off[up[f]] + cnt[up[f]]++] = f;
+    for (int f = 0; f < nf; f++) cf[off[lo[f]] + cnt[lo[f]]++] = f;
+
+    int *map = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    for (int c = 0; c < n; c++) map[c] = -1;
+    int nCoarse = 0;
+    const double GREAT = 1e20;
+    for (int ci = 0; ci < n; ci++) {
+        int c = *forward ? ci : n - ci - 1;
+        if (map[c] >= 0) continue;
+        int match = -1;
+        double maxW = -GREAT;
+        for (int k = off[c]; k < off[c + 1]; k++) {
+            int f = cf[k];
+            if (map[up[f]] < 0 && map[lo[f]] < 0 && w[f] > maxW) {
+                match = f;
+                maxW = w[f];
+            }
+        }
+        if (match >= 0) {
+            map[up[match]] = nCoarse;
+            map[lo[match]] = nCoarse;
+            nCoarse++;
+        } else {
+            int cm = -1;
+            double cmax = -GREAT;
+            for (int k = off[c]; k < off[c + 1]; k++) {
+                int f = cf[k];
+                if (w[f] > cmax) {
+                    cm = f;
+                    cmax = w[f];
+                }
+            }
+            if (cm >= 0) {
+                int a1 = map[up[cm]], a2 = map[lo[cm]];
+                map[c] = a1 > a2 ? a1 : a2;
+            }
+        }
+    }
+    for (int ci = 0; ci < n; ci++) { /* leftover singletons :276-286 */
+        int c = *forward ? ci : n - ci - 1;
+        if (map[c] < 0) map[c] = nCoarse++;
+    }
+    if (!*forward) { /* :288-298 */
+        nCoarse--;
+        for (int c = 0; c < n; c++) map[c] = nCoarse - map[c];
+        nCoarse++;
+    }
+    *forward = !*forward; /* :302-304 static direction flag */
+    free(off);
+    free(cnt);
+    free(cf);
+    *nCoarseOut = nCoarse;
+    return map;
+}
+
+/* GAMGAgglomeration::agglomerateLduAddressing:
+ * GAMGAgglomerations/GAMGAgglomeration/GAMGAgglomerateLduAddressing.C:245-461 */
+static orc_addr *coarse_addressing(const orc_addr *fine, const int *rmap, int nCoarse,
+                                   int **faceRestrictOut, unsigned char **flipOut)
+{
+    int nff = fine->nFaces;
+    int maxN = 10;
+    int *ccn = (int *)calloc((size_t)nCoarse, sizeof(int));
+    int *ccf = (int *)malloc(sizeof(int) * (size_t)maxN * (size_t)nCoarse);
+    int *fr = (int *)malloc(sizeof(int) * (size_t)(nff > 0 ? nff : 1));
+    int *initNei = (int *)malloc(sizeof(int) * (size_t)(nff > 0 ? nff : 1));
+    int nCF = 0;
+    for (int f = 0; f < nff; f++) {
+        int ru = rmap[fine->u[f]], rl = rmap[fine->l[f]];
+        if (ru == rl) {
+            fr[f] = -(ru + 1);
+            continue;
+        }
+        int cOwn = ru, cNei = rl;
+        if (ru > rl) {
+            cOwn = rl;
+            cNei = ru;
+        }
+        int found = 0;
+        for (int i = 0; i < ccn[cOwn]; i++) {
+            int cfi = ccf[(size_t)maxN * cOwn + i];
+            if (initNei[cfi] == cNei) {
+                found = 1;
+                fr[f] = cfi;
+                break;
+            }
+        }
+        if (!found) {
+            if (ccn[cOwn] >= maxN) {
+                int oldN = maxN;
+                maxN *= 2;
+                ccf = (int *)realloc(ccf, sizeof(int) * (size_t)maxN * (size_t)nCoarse);
+                for (int i = nCoarse - 1; i >= 0; i--)
+                    for (int j = ccn[i] - 1; j >= 0; j--)
+                        ccf[(size_t)maxN * i + j] = ccf[(size_t)oldN * i + j];
+            }
+            ccf[(size_t)maxN * cOwn + ccn[cOwn]] = nCF;
+            initNei[nCF] = cNei;
+            fr[f] = nCF;
+            ccn[cOwn]++;
+            nCF++;
+        }
+    }
+    /* renumber grouped by coarse owner, discovery order within an owner (:381-402) */
+    int *cOwner = (int *)malloc(sizeof(int) * (size_t)(nCF > 0 ? nCF : 1));
+    int *cNeigh = (int *)malloc(sizeof(int) * (size_t)(nCF > 0 ? nCF : 1));
+    int *cMap = (int *)malloc(sizeof(int) * (size_t)(nCF > 0 ? nCF : 1));
+    int k = 0;
+    for (int cc = 0; cc < nCoarse; cc++)
+        for (int i = 0; i < ccn[cc]; i++) {
+            int cfi = ccf[(size_t)maxN * cc + i];
+            cOwner[k] = cc;
+            cNeigh[k] = initNei[cfi];
+            cMap[cfi] = k;
+            k++;
+        }
+    for (int f = 0; f < nff; f++)
+        if (fr[f] >= 0) fr[f] = cMap[fr[f]];
+    unsigned char *flip = (unsigned char *)calloc((size_t)(nff > 0 ? nff : 1), 1);
+    for (int f = 0; f < nff; f++) { /* :413-446 */
+        if (fr[f] >= 0) {
+            int ru = rmap[fine->u[f]], rl = rmap[fine->l[f]];
+            if (cOwner[fr[f]] == ru && cNeigh[fr[f]] == rl) flip[f] = 1;
+        }
+    }
+    orc_addr *ca = orc_addr_create(nCoarse, nCF, cOwner, cNeigh, 0, NULL, NULL);
+    free(ccn);
+    free(ccf);
+    free(initNei);
+    free(cOwner);
+    free(cNeigh);
+    free(cMap);
+    *faceRestrictOut = fr;
+    *flipOut = flip;
+    return ca;
+}
+
+/* level loop: pairGAMGAgglomerate.C:31-130 (mergeLevels 1 only) */
+orc_gamg *orc_gamg_create(const orc_addr *a, const double *faceWeights,
+                          int nCellsInCoarsestLevel, int mergeLevels, int *forwardFlag)
+{
+    if (mergeLevels != 1) return NULL;
+    orc_gamg *g = (orc_gamg *)calloc(1, sizeof(orc_gamg));
+    g->finest = a;
+    int fwd_local = 1; /* pairGAMGAgglomeration.C:33 initial forward_ = true */
+    int *fwd = forwardFlag ? forwardFlag : &fwd_local;
+    const orc_addr *fine = a;
+    double *w = (double *)malloc(sizeof(double) * (size_t)(a->nFaces > 0 ? a->nFaces : 1));
+    memcpy(w, faceWeights, sizeof(double) * (size_t)a->nFaces);
+    while (g->nLevels < ORC_MAX_LEVELS - 1) {
+        int nCoarse = -1;
+        int *map = pair_agglomerate(fine, w, &nCoarse, fwd);
+        /* continueAgglomerating: GAMGAgglomeration.C:72-84 */
+        if (!(nCoarse >= nCellsInCoarsestLevel)) {
+            free(map);
+            break;
+        }
+        int lev = g->nLevels;
+        g->restrictAddr[lev] = map;
+        g->nFineCells[lev] = fine->nCells;
+        g->nFineFaces[lev] = fine->nFaces;
+        g->addr[lev] = coarse_addressing(fine, map, nCoarse, &g->faceRestrict[lev], &g->faceFlip[lev]);
+        /* restrictFaceField of the weights (:86-107; GAMGAgglomerationTemplates.C:155-271) */
+        double *cw = (double *)calloc((size_t)(g->addr[lev]->nFaces > 0 ? g->addr[lev]->nFaces : 1),
+                                      sizeof(double));
+        for (int f = 0; f < fine->nFaces; f++)
+            if (g->faceRestrict[lev][f] >= 0) cw[g->faceRestrict[lev][f]] += w[f];
+        free(w);
+        w = cw;
+        fine = g->addr[lev];
+        g->nLevels++;
+    }
+    free(w);
+    return g;
+}
+
+void orc_gamg_free(orc_gamg *g)
+{
+    if (!g) return;
+    for (int i = 0; i < g->nLevels; i++) {
+        orc_addr_free(g->addr[i]);
+        free(g->restrictAddr[i]);
+        free(g->faceRestrict[i]);
+        free(g->faceFlip[i]);
+    }
+    free(g);
+}
+
+int orc_gamg_nlevels(const orc_gamg *g) { return g->nLevels; }
+int orc_gamg_ncells(const orc_gamg *g, int lev) { return g->addr[lev]->nCells; }
+int orc_gamg_nfaces(const orc_gamg *g, int lev) { return g->addr[lev]->nFaces; }
+const int *orc_gamg_restrict_addr(const orc_gamg *g, int lev) { return g->restrictAddr[lev]; }
+const int *orc_gamg_face_restrict_addr(const orc_gamg *g, int lev) { return g->faceRestrict[lev]; }
+const unsigned char *orc_gamg_face_flip(const orc_gamg *g, int lev) { return g->faceFlip[lev]; }
+const orc_addr *orc_gamg_addr(const orc_gamg *g, int lev) { return g->addr[lev]; }
+
+/* restrictField: GAMGAgglomerationTemplates.C:35-61, GAMGAgglomerationF.H:10-40.
+ * Segments come from a stable sort, so each coarse value is the sum of its fine
+ * values in ascending fine index starting from zero. */
+static void restrict_field(const int *map, int nFine, int nCoarse, const double *ff, double *cf)
+{
+    for (int i = 0; i < nCoarse; i++) cf[i] = 0.0;
+    for (int i = 0; i < nFine; i++) cf[map[i]] = cf[map[i]] + ff[i];
+}
+
+/* prolongField: GAMGAgglomerationTemplates.C:273-308 */
+static void prolong_field(const int *map, int nFine, const double *cf, double *ff)
+{
+    for (int i = 0; i < nFine; i++) ff[i] = cf[map[i]];
+}
+
+typedef struct {
+    int n, nf;
+    double *diag, *upper, *lower; /* lower == NULL when symmetric */
+    orc_matrix *m;
+} lev_matrix;
+
+/* agglomerateMatrix: GAMGSolverAgglomerateMatrix.C:37-322 with the sorted
+ * (non-atomic) functors GAMGSolverAgglomerateMatrixF.H:9-160 */
+static void agglomerate_matrix(const orc_gamg *g, int lev, const double *fd, const double *fu,
+                               const double *fl, lev_matrix *cm)
+{
+    const orc_addr *ca = g->addr[lev];
+    int nFine = g->nFineCells[lev], nFF = g->nFineFaces[lev];
+    cm->n = ca->nCells;
+    cm->nf = ca->nFaces;
+    cm->diag = (double *)calloc((size_t)cm->n, sizeof(double));
+    cm->upper = (double *)calloc((size_t)(cm->nf > 0 ? cm->nf : 1), sizeof(double));
+    cm->lower = fl ? (double *)calloc((size_t)(cm->nf > 0 ? cm->nf : 1), sizeof(double)) : NULL;
+    restrict_field(g->restrictAddr[lev], nFine, cm->n, fd, cm->diag); /* :59-71 */
+    const int *fr = g->faceRestrict[lev];
+    const unsigned char *flip = g->faceFlip[lev];
+    for (int f = 0; f < nFF; f++) {
+        if (fr[f] >= 0) {
+            if (!fl) {
+                cm->upper[fr[f]] = cm->upper[fr[f]] + fu[f];
+            } else if (!flip[f]) {
+                cm->upper[fr[f]] = cm->upper[fr[f]] + fu[f];
+                cm->lower[fr[f]] = cm->lower[fr[f]] + fl[f];
+            } else {
+                cm->upper[fr[f]] = cm->upper[fr[f]] + fl[f];
+                cm->lower[fr[f]] = cm->lower[fr[f]] + fu[f];
+            }
+        } else {
+            int c = -1 - fr[f];
+            if (!fl)
+                cm->diag[c] = cm->diag[c] + 2 * fu[f];
+            else
+                cm->diag[c] = cm->diag[c] + (fu[f] + fl[f]);
+        }
+    }
+    cm->m = orc_matrix_create(ca, cm->diag, cm->upper, cm->lower, NULL, NULL);
+}
+
+/* scale: GAMGSolverScale.C:59-171 */
+static void gamg_scale(const orc_matrix *A, double *field, double *Acf, const double *source)
+{
+    int n = A->a->nCells;
+    orc_amul(A, field, Acf, NULL);
+    double num = 0, den = 0;
+    for (int i = 0; i < n; i++) num += source[i] * field[i];
+    for (int i = 0; i < n; i++) den += Acf[i] * field[i];
+    /* stabilise(y, VSMALL): y >= 0 ? y + VSMALL : y - VSMALL */
+    double sden = den >= 0 ? den + 1e-300 : den - 1e-300;
+    double sf = num / sden;
+    for (int i = 0; i < n; i++) {
+        double t1 = sf * field[i];
+        double t2 = sf * Acf[i];
+        field[i] = t1 + (source[i] - t2) / A->diag[i];
+    }
+}
+
+/* interpolate (first overload): GAMGSolverInterpolate.C:45-110 */
+static void gamg_interpolate(const orc_matrix *A, double *psi, double *Apsi)
+{
+    const orc_addr *a = A->a;
+    for (int c = 0; c < a->nCells; c++) {
+        double out = 0.0;
+        for (int f = a->ownerStart[c]; f < a->ownerStart[c + 1]; f++)
+            out = out + A->upper[f] * psi[a->u[f]];
+        for (int k = a->losortStart[c]; k < a->losortStart[c + 1]; k++) {
+            int f = a->losort[k];
+            out = out + A->lower[f] * psi[a->l[f]];
+        }
+        Apsi[c] = out;
+    }
+    for (int c = 0; c < a->nCells; c++) psi[c] = -Apsi[c] / A->diag[c];
+}
+
+/* dense LU with partial pivoting of the coarsest matrix, standing in for
+ * matrices/LUscalarMatrix (GAMGSolver.C:144-172, GAMGSolverSolve.C:564-569) */
+typedef struct {
+    int n;
+    double *lu;
+    int *piv;
+} dense_lu;
+
+static dense_lu *lu_factor(const orc_matrix *A)
+{
+    const orc_addr *a = A->a;
+    int n = a->nCells;
+    dense_lu *d = (dense_lu *)malloc(sizeof(dense_lu));
+    d->n = n;
+    d->lu = (double *)calloc((size_t)n * n, sizeof(double));
+    d->piv = (int *)malloc(sizeof(int) * (size_t)n);
+    for (int c = 0; c < n; c++) d->lu[(size_t)c * n + c] = A->diag[c];
+    for (int f = 0; f < a->nFaces; f++) {
+        d->lu[(size_t)a->l[f] * n + a->u[f]] += A->upper[f];
+        d->lu[(size_t)a->u[f] * n + a->l[f]] += A->lower[f];
+    }
+    for (int k = 0; k < n; k++) {
+        int p = k;
+        double mx = fabs(d->lu[(size_t)k * n + k]);
+        for (int i = k + 1; i < n; i++)
+            if (fabs(d->lu[(size_t)i * n + k]) > mx) {
+                mx = fabs(d->lu[(size_t)i * n + k]);
+                p = i;
+            }
+        d->piv[k] = p;
+        if (p != k)
+            for (int j = 0; j < n; j++) {
+                double t = d->lu[(size_t)k * n + j];
+                d->lu[(size_t)k * n + j] = d->lu[(size_t)p * n + j];
+                d->lu[(size_t)p * n + j] = t;
+            }
+        for (int i = k + 1; i < n; i++) {
+            double fct = d->lu[(size_t)i * n + k] / d->lu[(size_t)k * n + k];
+            d->lu[(size_t)i * n + k] = fct;
+            for (int j = k + 1; j < n; j++) d->lu[(size_t)i * n + j] -= fct * d->lu[(size_t)k * n + j];
+        }
+    }
+    return d;
+}
+
+static void lu_solve(const dense_lu *d, double *b)
+{
+    int n = d->n;
+    for (int k = 0; k < n; k++) {
+        if (d->piv[k] != k) {
+            double t = b[k];
+            b[k] = b[d->piv[k]];
+            b[d->piv[k]] = t;
+        }
+        for (int i = k + 1; i < n; i++) b[i] -= d->lu[(size_t)i * n + k] * b[k];
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        for (int j = i + 1; j < n; j++) b[i] -= d->lu[(size_t)i * n + j] * b[j];
+        b[i] /= d->lu[(size_t)i * n + i];
+    }
+}
+
+static int imin(int a, int b) { return a < b ? a : b; }
+
+/* GAMGSolver::solve + Vcycle: GAMGSolverSolve.C:59-474 */
+int orc_gamg_solve(const orc_matrix *m, orc_gamg *g, const char *smoother, const orc_controls *c,
+                   double *psi, const double *source, orc_perf *perf, double *hist, int histCap)
+{
+    memset(perf, 0, sizeof(*perf));
+    strcpy(perf->solverName, "GAMG");
+    if (smoother && *smoother && strcmp(smoother, "Jacobi") && strcmp(smoother, "GaussSeidel"))
+        return -2; /* GaussSeidel aliases to Jacobi: GaussSeidelSmoother.C:43-69 */
+    int nL = g->nLevels;
+    if (nL == 0) return -4; /* GAMGSolver.C:174-192 "No coarse levels created" */
+    int n = m->a->nCells;
+    int scaleCorrection = c->scaleCorrection < 0 ? m->symmetric : c->scaleCorrection;
+    double tol = c->tolerance, relTol = c->relTol;
+
+    /* constructor: coarse matrices for every level (GAMGSolver.C:85-96) */
+    lev_matrix *lm = (lev_matrix *)calloc((size_t)nL, sizeof(lev_matrix));
+    for (int lev = 0; lev < nL; lev++) {
+        const double *fd = lev ? lm[lev - 1].diag : m->diag;
+        const double *fu = lev ? lm[lev - 1].upper : m->upper;
+        const double *fl = lev ? lm[lev - 1].lower : (m->symmetric ? NULL : m->lower);
+        agglomerate_matrix(g, lev, fd, fu, fl, &lm[lev]);
+    }
+    int coarsest = nL - 1;
+    dense_lu *lu = c->directSolveCoarsest ? lu_factor(lm[coarsest].m) : NULL;
+
+    double *Apsi = (double *)calloc((size_t)n, sizeof(double));
+    double *finestCorr = (double *)calloc((size_t)n, sizeof(double));
+    double *finestRes = (double *)calloc((size_t)n, sizeof(double));
+    orc_amul(m, psi, Apsi, NULL);
+    double normFactor = orc_normFactor(m, psi, source, Apsi, finestCorr, NULL);
+    perf->normFactor = normFactor;
+    for (int i = 0; i < n; i++) finestRes[i] = source[i] - Apsi[i];
+    perf->initialResidual = orc_gsummag(finestRes, n, NULL) / normFactor;
+    perf->finalResidual = perf->initialResidual;
+    if (hist && histCap > 0) hist[0] = perf->finalResidual;
+
+#define CONVERGED()                                                                        \
+    (perf->converged = (perf->finalResidual < tol ||                                       \
+                        (relTol > 1e-20 && perf->finalResidual < relTol * perf->initialResidual)))
+
+    if (c->minIter > 0 || !CONVERGED()) {
+        double **corr = (double **)calloc((size_t)nL, sizeof(double *));
+        double **src = (double **)calloc((size_t)nL, sizeof(double *));
+        int maxSize = n;
+        for (int lev = 0; lev < nL; lev++) {
+            corr[lev] = (double *)calloc((size_t)lm[lev].n, sizeof(double));
+            src[lev] = (double *)calloc((size_t)lm[lev].n, sizeof(double));
+            if (lm[lev].n > maxSize) maxSize = lm[lev].n;
+        }
+        double *scratch1 = (double *)calloc((size_t)maxSize, sizeof(double));
+        double *scratch2 = (double *)calloc((size_t)maxSize, sizeof(double));
+        do {
+            /* ---- Vcycle :181-474 ---- */
+            restrict_field(g->restrictAddr[0], n, lm[0].n, finestRes, src[0]);
+            for (int lev = 0; lev < coarsest; lev++) {
+                if (c->nPreSweeps) {
+                    memset(corr[lev], 0, sizeof(double) * (size_t)lm[lev].n);
+                    orc_jacobi_smooth(lm[lev].m, c->omega, corr[lev], src[lev],
+                                      imin(c->nPreSweeps + c->preSweepsLevelMultiplier * lev,
+                                           c->maxPreSweeps),
+                                      NULL);
+                    double *ACf = scratch1;
+                    if (scaleCorrection && lev < coarsest - 1)
+                        gamg_scale(lm[lev].m, corr[lev], ACf, src[lev]);
+                    orc_amul(lm[lev].m, corr[lev], ACf, NULL);
+                    for (int i = 0; i < lm[lev].n; i++) src[lev][i] -= ACf[i];
+                }
+                restrict_field(g->restrictAddr[lev + 1], lm[lev].n, lm[lev + 1].n, src[lev],
+                               src[lev + 1]);
+            }
+            /* solveCoarsestLevel :552-619 */
+            if (c->directSolveCoarsest) {
+                memcpy(corr[coarsest], src[coarsest], sizeof(double) * (size_t)lm[coarsest].n);
+                lu_solve(lu, corr[coarsest]);
+            } else {
+                orc_controls cc;
+                orc_controls_default(&cc);
+                cc.tolerance = tol;
+                cc.relTol = relTol;
+                orc_perf cp;
+                memset(corr[coarsest], 0, sizeof(double) * (size_t)lm[coarsest].n);
+                orc_solve(lm[coarsest].m, lm[coarsest].lower ? "BICCG" : "ICCG", NULL, &cc,
+                          corr[coarsest], src[coarsest], NULL, &cp, NULL, 0);
+            }
+            for (int lev = coarsest - 1; lev >= 0; lev--) {
+                double *pre = scratch2;
+                if (c->nPreSweeps) memcpy(pre, corr[lev], sizeof(double) * (size_t)lm[lev].n);
+                prolong_field(g->restrictAddr[lev + 1], lm[lev].n, corr[lev + 1], corr[lev]);
+                double *ACf = scratch1;
+                if (c->interpolateCorrection) gamg_interpolate(lm[lev].m, corr[lev], ACf);
+                if (scaleCorrection && (c->interpolateCorrection || lev < coarsest - 1))
+                    gamg_scale(lm[lev].m, corr[lev], ACf, src[lev]);
+                if (c->nPreSweeps)
+                    for (int i = 0; i < lm[lev].n; i++) corr[lev][i] += pre[i];
+                orc_jacobi_smooth(lm[lev].m, c->omega, corr[lev], src[lev],
+                                  imin(c->nPostSweeps + c->postSweepsLevelMultiplier * lev,
+                                       c->maxPostSweeps),
+                                  NULL);
+            }
+            prolong_field(g->restrictAddr[0], n, corr[0], finestCorr);
+            if (c->interpolateCorrection) gamg_interpolate(m, finestCorr, Apsi);
+            if (scaleCorrection) gamg_scale(m, finestCorr, Apsi, finestRes);
+            for (int i = 0; i < n; i++) psi[i] = psi[i] + finestCorr[i];
+            orc_jacobi_smooth(m, c->omega, psi, source, c->nFinestSweeps, NULL);
+            /* ---- end Vcycle ---- */
+            orc_amul(m, psi, Apsi, NULL);
+            for (int i = 0; i < n; i++) finestRes[i] = source[i] - Apsi[i];
+            perf->finalResidual = orc_gsummag(finestRes, n, NULL) / normFactor;
+            if (hist && perf->nIterations + 1 < histCap) hist[perf->nIterations + 1] = perf->finalResidual;
+        } while ((++perf->nIterations < c->maxIter && !CONVERGED()) ||
+                 perf->nIterations < c->minIter);
+        for (int lev = 0; lev < nL; lev++) {
+            free(corr[lev]);
+            free(src[lev]);
+        }
+        free(corr);
+        free(src);
+        free(scratch1);
+        free(scratch2);
+    }
+#undef CONVERGED
+    if (lu) {
+        free(lu->lu);
+        free(lu->piv);
+        free(lu);
+    }
+    for (int lev = 0; lev < nL; lev++) {
+        free(lm[lev].diag);
+        free(lm[lev].upper);
+        free(lm[lev].lower);
+        orc_matrix_free(lm[lev].m);
+    }
+    free(lm);
+    free(Apsi);
+    free(finestCorr);
+    free(finestRes);
+    return 0;
+}

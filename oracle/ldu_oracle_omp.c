@@ -1,0 +1,135 @@
+/*
+ * ldu_oracle_omp.c -- all-core (OpenMP, rows in parallel) variant of the oracle's PCG
+ * for the CPU baseline / bench.py --impl reference.  TEST INFRASTRUCTURE ONLY.
+ * Same numerics as orc_pcg (PCG.C:69-208 with none/diagonal/AINV) except that global
+ * sums are per-thread partial sums combined in thread order.
+ */
+#include "ldu_oracle_internal.h"
+#include <math.h>
+#include <omp.h>
+#include <stdlib.h>
+#include <string.h>
+
+int orc_max_threads(void) { return omp_get_max_threads(); }
+
+static inline double row_sum(const orc_addr *a, int c, double init, const double *U,
+                             const double *L, const double *x)
+{
+    double out = init;
+    for (int f = a->ownerStart[c]; f < a->ownerStart[c + 1]; f++) out = out + U[f] * x[a->u[f]];
+    for (int k = a->losortStart[c]; k < a->losortStart[c + 1]; k++) {
+        int f = a->losort[k];
+        out = out + L[f] * x[a->l[f]];
+    }
+    return out;
+}
+
+void orc_amul_omp(const orc_matrix *m, const double *psi, double *Apsi, int nThreads)
+{
+    const orc_addr *a = m->a;
+#pragma omp parallel for num_threads(nThreads) schedule(static)
+    for (int c = 0; c < a->nCells; c++)
+        Apsi[c] = row_sum(a, c, m->diag[c] * psi[c], m->upper, m->lower, psi);
+}
+
+int orc_pcg_omp(const orc_matrix *m, int pk, const orc_controls *c, double *psi,
+                const double *source, orc_perf *perf, int nT)
+{
+    const orc_addr *a = m->a;
+    int n = a->nCells;
+    memset(perf, 0, sizeof(*perf));
+    double *pA = (double *)calloc((size_t)n, sizeof(double));
+    double *wA = (double *)calloc((size_t)n, sizeof(double));
+    double *rA = (double *)calloc((size_t)n, sizeof(double));
+    double *rD = (double *)calloc((size_t)n, sizeof(double));
+    double *tmp = (double *)calloc((size_t)n, sizeof(double));
+    double wArA = 1e20, wArAold;
+
+    orc_amul_omp(m, psi, wA, nT);
+    double s0 = 0, sp = 0;
+#pragma omp parallel for num_threads(nT) schedule(static) reduction(+ : sp)
+    for (int i = 0; i < n; i++) {
+        rA[i] = source[i] - wA[i];
+        rD[i] = 1.0 / m->diag[i];
+        sp += psi[i];
+    }
+    orc_sumA(m, tmp);
+    double avg = sp / (double)n, nf = 0;
+#pragma omp parallel for num_threads(nT) schedule(static) reduction(+ : nf, s0)
+    for (int i = 0; i < n; i++) {
+        double t = avg * tmp[i];
+        nf += fabs(wA[i] - t) + fabs(source[i] - t);
+        s0 += fabs(rA[i]);
+    }
+    nf += 1e-20;
+    perf->normFactor = nf;
+    perf->initialResidual = perf->finalResidual = s0 / nf;
+    const double *U = m->upper, *L = m->lower;
+
+    int conv = perf->finalResidual < c->tolerance ||
+               (c->relTol > 1e-20 && perf->finalResidual < c->relTol * perf->initialResidual);
+    if (c->minIter > 0 || !conv) {
+        do {
+            wArAold = wArA;
+            double dot = 0;
+            if (pk == 2) {
+#pragma omp parallel for num_threads(nT) schedule(static) reduction(+ : dot)
+                for (int i = 0; i < n; i++) {
+                    double out = 0.0;
+                    for (int f = a->ownerStart[i]; f < a->ownerStart[i + 1]; f++) {
+                        int nb = a->u[f];
+                        out = out + (U[f] * rD[nb]) * rA[nb];
+                    }
+                    for (int k = a->losortStart[i]; k < a->losortStart[i + 1]; k++) {
+                        int f = a->losort[k];
+                        int nb = a->l[f];
+                        out = out + (L[f] * rD[nb]) * rA[nb];
+                    }
+                    wA[i] = rD[i] * (rA[i] - out);
+                    dot += wA[i] * rA[i];
+                }
+            } else {
+#pragma omp parallel for num_threads(nT) schedule(static) reduction(+ : dot)
+                for (int i = 0; i < n; i++) {
+                    wA[i] = pk == 1 ? rD[i] * rA[i] : rA[i];
+                    dot += wA[i] * rA[i];
+                }
+            }
+            wArA = dot;
+            if (perf->nIterations == 0) {
+                memcpy(pA, wA, sizeof(double) * (size_t)n);
+            } else {
+                double beta = wArA / wArAold;
+#pragma omp parallel for num_threads(nT) schedule(static)
+                for (int i = 0; i < n; i++) pA[i] = fma(beta, pA[i], wA[i]);
+            }
+            double wApA = 0;
+#pragma omp parallel for num_threads(nT) schedule(static) reduction(+ : wApA)
+            for (int i = 0; i < n; i++) {
+                wA[i] = row_sum(a, i, m->diag[i] * pA[i], U, L, pA);
+                wApA += wA[i] * pA[i];
+            }
+            if (fabs(wApA) / nf < 1e-300) {
+                perf->singular = 1;
+                break;
+            }
+            double alpha = wArA / wApA, sm = 0;
+#pragma omp parallel for num_threads(nT) schedule(static) reduction(+ : sm)
+            for (int i = 0; i < n; i++) {
+                psi[i] = fma(alpha, pA[i], psi[i]);
+                rA[i] = fma(-alpha, wA[i], rA[i]);
+                sm += fabs(rA[i]);
+            }
+            perf->finalResidual = sm / nf;
+            conv = perf->finalResidual < c->tolerance ||
+                   (c->relTol > 1e-20 && perf->finalResidual < c->relTol * perf->initialResidual);
+        } while ((perf->nIterations++ < c->maxIter && !conv) || perf->nIterations < c->minIter);
+        perf->converged = conv;
+    }
+    free(pA);
+    free(wA);
+    free(rA);
+    free(rD);
+    free(tmp);
+    return 0;
+}
