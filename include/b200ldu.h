@@ -1,0 +1,212 @@
+/*
+ * b200ldu.h -- C ABI of the Blackwell-native lduMatrix linear-solver core.
+ *
+ * Drop-in boundary for the RapidCFD-dev (OpenFOAM-2.3.x) hot path: a reference-side
+ * lduMatrix::solver / preconditioner / smoother registered in the run-time selection
+ * tables (LDU/lduMatrix/lduMatrix.H:141-185,297-341,438-460) forwards to these entry
+ * points; INTEGRATION.md shows the binding.  "LDU/" = src/OpenFOAM/matrices/lduMatrix/,
+ * "FV/" = src/finiteVolume/ of the reference tree.
+ *
+ * Conventions
+ *  - scalar = double, label = int32 (reference etc/bashrc:76, label.H:46-67).
+ *  - Every pointer named *_d is DEVICE memory on the context's GPU, in the caller's
+ *    OpenFOAM ordering (cells 0..nCells-1, faces sorted by owner then neighbour).
+ *    Pointers named *_h are HOST memory.  The caller keeps ownership of everything it
+ *    passes in; the library owns handles, derived addressing, renumbering permutations,
+ *    banded coefficient copies and all workspace (no cudaMalloc inside ldu_solve after
+ *    the first call on a handle).
+ *  - Face f: owner lower[f] < neighbour upper[f]; upper[f] = A(owner, neighbour),
+ *    lower[f] = A(neighbour, owner); lower == NULL means symmetric
+ *    (LDU/lduMatrix/lduMatrix.C:328-345).
+ *  - Every function returns 0 on success or a negative B200LDU_E* code; nothing throws
+ *    across the ABI; b200ldu_last_error() gives the message for the calling thread.
+ *  - No CPU fallback: a missing GPU or a CUDA error is an error return, never a silent
+ *    host computation.
+ */
+#ifndef B200LDU_H
+#define B200LDU_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200LDU_OK 0
+#define B200LDU_EINVAL -1     /* bad argument */
+#define B200LDU_ECUDA -2      /* CUDA runtime / launch failure */
+#define B200LDU_ENOSOLVER -3  /* unknown solver name (lduMatrixSolver.C:76-84 prints the table) */
+#define B200LDU_ENOPRECOND -4 /* unknown preconditioner / smoother name */
+#define B200LDU_EMATRIX -5    /* solver not registered for this matrix kind (sym/asym tables) */
+#define B200LDU_ELAYOUT -6    /* mesh cannot be banded (more than 65535 columns in one band) */
+#define B200LDU_ENCCL -7
+#define B200LDU_ENOLEVELS -8  /* GAMG: no coarse levels created (GAMGSolver.C:174-192) */
+
+typedef struct b200ldu_ctx b200ldu_ctx;       /* one per device (+ NCCL communicator) */
+typedef struct b200ldu_addr b200ldu_addr;     /* lduAddressing + banded layout */
+typedef struct b200ldu_matrix b200ldu_matrix; /* lduMatrix coefficients in banded form */
+typedef struct b200ldu_gamg b200ldu_gamg;     /* cached GAMGAgglomeration (MeshObject) */
+
+/* solver controls: LDU/lduMatrix/lduMatrixSolver.C:167-173, smoothSolver.C:80,
+ * JacobiSmoother.C:34-36, GAMGSolver.C:67-77,209-249, GAMGAgglomeration.C:96-128 */
+typedef struct b200ldu_controls {
+    double tolerance; /* 1e-6 */
+    double relTol;    /* 0 */
+    int maxIter;      /* 1000 */
+    int minIter;      /* 0 */
+    int nSweeps;      /* smoothSolver: 1 */
+    double omega;     /* Jacobi damping 0.9 */
+    int bicgstabRefQuirk; /* 1: mirror PBiCGStab.C:263-270 (second update uses yA) */
+    int nCellsInCoarsestLevel, mergeLevels;
+    int nPreSweeps, preSweepsLevelMultiplier, maxPreSweeps;
+    int nPostSweeps, postSweepsLevelMultiplier, maxPostSweeps;
+    int nFinestSweeps;
+    int interpolateCorrection;
+    int scaleCorrection; /* -1 = matrix.symmetric() */
+    int directSolveCoarsest;
+    int checkEvery; /* host polls the device convergence flag every k iterations (0 = default 8);
+                       the iteration count is decided on the device and is exact */
+} b200ldu_controls;
+
+/* solverPerformance: src/OpenFOAM/matrices/LduMatrix/LduMatrix/SolverPerformance.H */
+typedef struct b200ldu_perf {
+    double initialResidual, finalResidual, normFactor;
+    int nIterations, converged, singular;
+    char solverName[64]; /* preconditionerName + typeName, DIC/DILU printed as AINV */
+} b200ldu_perf;
+
+const char *b200ldu_last_error(void);
+void b200ldu_controls_default(b200ldu_controls *c);
+
+/* ---- context ---- */
+/* Replaces argList's device selection (src/OpenFOAM/global/argList/argList.C:775-831). */
+int b200ldu_ctx_create(int device, b200ldu_ctx **out);
+int b200ldu_ctx_destroy(b200ldu_ctx *ctx);
+/* Replaces Pstream over MPI (src/Pstream/mpi/UPstream.C:64-79): one NCCL communicator
+ * per context.  nccl_unique_id_128 is the 128-byte ncclUniqueId created on rank 0 and
+ * broadcast by the host program. */
+int b200ldu_comm_unique_id(void *out128);
+int b200ldu_comm_init(b200ldu_ctx *ctx, const void *nccl_unique_id_128, int rank, int nRanks);
+/* stream all work of this context is enqueued on (a cudaStream_t); NULL out => legacy stream */
+int b200ldu_ctx_set_stream(b200ldu_ctx *ctx, void *cudaStream);
+int b200ldu_ctx_sync(b200ldu_ctx *ctx);
+
+/* ---- lduAddressing (LDU/lduAddressing/lduAddressing.H:119-256) ----
+ * lower_h/upper_h: HOST int32[nFaces].  Coupled patches (processor / cyclic interfaces,
+ * LDU/lduAddressing/lduInterface): patchStart_h[nPatches+1] offsets into faceCells_h,
+ * neighbRank_h[nPatches] (rank owning the other side; == own rank for cyclic).
+ * cellCentres_h: optional HOST double[3*nCells] (fvMesh::C()) used only to choose the
+ * band renumbering; NULL => graph-distance embedding of the addressing itself. */
+int b200ldu_addr_create(b200ldu_ctx *ctx, int nCells, int nFaces, const int *lower_h,
+                        const int *upper_h, int nPatches, const int *patchStart_h,
+                        const int *faceCells_h, const int *neighbRank_h,
+                        const double *cellCentres_h, b200ldu_addr **out);
+int b200ldu_addr_destroy(b200ldu_addr *a);
+/* introspection (tests, DESIGN.md numbers) */
+int b200ldu_addr_info(const b200ldu_addr *a, long long *nPadRows, long long *nEntries,
+                      long long *nHalo, int *bandRows, int *nBands);
+/* cell renumbering: perm_h[c] = banded row of caller cell c (HOST int32[nCells]) */
+int b200ldu_addr_perm(const b200ldu_addr *a, int *perm_h);
+
+/* ---- lduMatrix coefficients (LDU/lduMatrix/lduMatrix.H:78-96, lduMatrix.C:221-471) ----
+ * Copies diag/upper/lower (+ interfaceBouCoeffs/interfaceIntCoeffs, flat over coupled
+ * patches in patch order) into the banded layout; replaces calcSortCoeffs/lowerSort. */
+int b200ldu_matrix_create(b200ldu_addr *a, b200ldu_matrix **out);
+int b200ldu_matrix_set(b200ldu_matrix *m, const double *diag_d, const double *upper_d,
+                       const double *lower_d /* NULL => symmetric */,
+                       const double *bouCoeffs_d, const double *intCoeffs_d);
+int b200ldu_matrix_destroy(b200ldu_matrix *m);
+
+/* lduMatrix::Amul / Tmul (LDU/lduMatrix/lduMatrixATmul.C:183-261, :264-342) incl. the
+ * coupled-interface update; sumA (:345-395); residual (:428-496); H
+ * (lduMatrixOperations.C:131-155); H1 (lduMatrixATmul.C:533-554); faceH
+ * (lduMatrixTemplates.C:108-149).  Caller-order device vectors. */
+int b200ldu_amul(b200ldu_matrix *m, const double *psi_d, double *Apsi_d);
+int b200ldu_tmul(b200ldu_matrix *m, const double *psi_d, double *Tpsi_d);
+int b200ldu_sumA(b200ldu_matrix *m, double *sumA_d);
+int b200ldu_residual(b200ldu_matrix *m, const double *psi_d, const double *source_d, double *rA_d);
+int b200ldu_H(b200ldu_matrix *m, const double *psi_d, double *Hpsi_d);
+int b200ldu_H1(b200ldu_matrix *m, double *H1_d);
+int b200ldu_faceH(b200ldu_matrix *m, const double *psi_d, double *faceHpsi_d);
+/* preconditioner::precondition / preconditionT (lduMatrix.H:497-520): name in
+ * {none, diagonal, AINV, DIC, DILU} with the reference's aliasing
+ * (lduMatrixPreconditioner.C:58-61) */
+int b200ldu_precondition(b200ldu_matrix *m, const char *name, int transpose, const double *rA_d,
+                         double *wA_d);
+/* smoother::smooth (lduMatrix.H:406-412): name in {Jacobi, GaussSeidel(alias)} */
+int b200ldu_smooth(b200ldu_matrix *m, const char *name, double omega, double *psi_d,
+                   const double *source_d, int nSweeps);
+
+/* banded-order views for benchmarking the kernels exactly as the solvers run them:
+ * vectors of b200ldu_vec_len() doubles in banded row order (+ halo tail). */
+long long b200ldu_vec_len(const b200ldu_addr *a);
+int b200ldu_to_banded(b200ldu_addr *a, const double *x_d, double *xb_d);
+int b200ldu_from_banded(b200ldu_addr *a, const double *xb_d, double *x_d);
+int b200ldu_amul_banded(b200ldu_matrix *m, const double *psib_d, double *Apsib_d);
+
+/* ---- lduMatrix::solver::New(...)->solve(psi, source, cmpt)
+ * (LDU/lduMatrix/lduMatrixSolver.C:43-140; lduMatrix.H:253-258) ----
+ * solver in {PCG, PBiCG, PBiCGStab, smoothSolver, diagonal, ICCG, BICCG, GAMG};
+ * precondOrSmoother: preconditioner name for the Krylov solvers, smoother for
+ * smoothSolver/GAMG.  hist_h (HOST, may be NULL) receives the normalised residual after
+ * every iteration (hist[0] = initial).  gamg may be NULL unless solver == GAMG. */
+int b200ldu_solve(b200ldu_matrix *m, const char *solver, const char *precondOrSmoother,
+                  const b200ldu_controls *controls, b200ldu_gamg *gamg, double *psi_d,
+                  const double *source_d, b200ldu_perf *perf, double *hist_h, int histCap);
+/* same, HOST psi/source through pinned staging (the "e2e" path: H2D + solve + D2H) */
+int b200ldu_solve_host(b200ldu_matrix *m, const char *solver, const char *precondOrSmoother,
+                       const b200ldu_controls *controls, b200ldu_gamg *gamg, double *psi_h,
+                       const double *source_h, b200ldu_perf *perf, double *hist_h, int histCap);
+/* number of library kernels launched on this context since creation */
+long long b200ldu_launch_count(const b200ldu_ctx *ctx);
+
+/* ---- GAMGAgglomeration (pair agglomeration, cached on the mesh:
+ * LDU/solvers/GAMG/GAMGAgglomerations/..., GAMGAgglomeration.C:132-233) ----
+ * faceWeights_h: HOST double[nFaces] (faceAreaPairGAMGAgglomeration.C:56-78).
+ * forward: in/out pairGAMGAgglomeration::forward_ (static in the reference). */
+int b200ldu_gamg_create(b200ldu_addr *a, const double *faceWeights_h, int nCellsInCoarsestLevel,
+                        int mergeLevels, int *forward, b200ldu_gamg **out);
+int b200ldu_gamg_destroy(b200ldu_gamg *g);
+int b200ldu_gamg_nlevels(const b200ldu_gamg *g);
+int b200ldu_gamg_level_size(const b200ldu_gamg *g, int lev, int *nCells, int *nFaces);
+/* HOST copies of the level maps (parity tests): restrictAddressing of level lev */
+int b200ldu_gamg_restrict_addr(const b200ldu_gamg *g, int lev, int *out_h);
+
+/* ---- finiteVolume face-sum loops (caller-order device fields) ----
+ * nComp = 1 or 3, AoS.  Boundary faces of all patches concatenated in patch order.
+ * fvc::surfaceIntegrate / surfaceSum: FV/finiteVolume/fvc/fvcSurfaceIntegrate.C:138-203,
+ * :264-360 ; gaussGrad::gradf: FV/finiteVolume/gradSchemes/gaussGrad/gaussGrad.C:143-242 ;
+ * fvmLaplacianUncorrected fill: gaussLaplacianScheme.C:63-64 ; fvmDiv fill:
+ * gaussConvectionScheme.C:95-97 ; linear interpolate: surfaceInterpolationScheme.C:159-240 ;
+ * addBoundaryDiag/Source: FV/fvMatrices/fvMatrix/fvMatrix.C:209-226,290-312. */
+int b200ldu_fv_boundary_set(b200ldu_addr *a, int nBFaces, const int *bFaceCells_h);
+int b200ldu_fv_surface_integrate(b200ldu_addr *a, int nComp, const double *ssf_d,
+                                 const double *bssf_d, const double *V_d, double *out_d,
+                                 int divideByV, int neiSign);
+int b200ldu_fv_gauss_grad(b200ldu_addr *a, int nComp, const double *Sf_d, const double *ssf_d,
+                          const double *bSf_d, const double *bssf_d, const double *V_d,
+                          double *out_d);
+int b200ldu_fv_laplacian_fill(b200ldu_addr *a, const double *deltaCoeffs_d,
+                              const double *gammaMagSf_d, double *upper_d, double *diag_d);
+int b200ldu_fv_convection_fill(b200ldu_addr *a, const double *weights_d, const double *phi_d,
+                               double *lower_d, double *upper_d, double *diag_d);
+int b200ldu_fv_interpolate_linear(b200ldu_addr *a, int nComp, const double *w_d,
+                                  const double *vf_d, double *sf_d);
+int b200ldu_fv_add_boundary_diag(b200ldu_addr *a, const double *internalCoeffs_d, double *diag_d);
+int b200ldu_fv_add_boundary_source(b200ldu_addr *a, const double *boundaryCoeffs_d,
+                                   double *source_d);
+
+/* ---- structural self-check of the banded layout (host only, no GPU, no arithmetic);
+ * used by the CPU test-suite.  what: 0 perm 1 iperm 2 sliceStart(int64) 3 sliceW(u16)
+ * 4 sliceWL(u16) 5 col(u16) 6 code(int32) 7 haloStart 8 haloIdx 9 dims{nPad,nBands,bandRows,
+ * nRecv,maxHalo}.  Returns the element count. */
+int b200ldu_layout_debug_create(int nCells, int nFaces, const int *lower_h, const int *upper_h,
+                                int nPatches, const int *patchStart_h, const int *faceCells_h,
+                                const double *cellCentres_h, b200ldu_addr **out);
+long long b200ldu_layout_debug_get(const b200ldu_addr *a, int what, void *out, long long cap);
+int b200ldu_layout_debug_destroy(b200ldu_addr *a);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,377 @@
+"""ctypes binding of include/b200ldu.h (lib/libb200ldu.so) plus thin Python mirrors of the
+reference's lduAddressing / lduMatrix / lduMatrix::solver interface.
+
+PyTorch is used only for device memory (torch.Tensor on cuda) and streams; every compute
+call goes through the C ABI.  There is no CPU fallback: a missing library or GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200ldu.so")
+
+
+class B200LduError(RuntimeError):
+    def __init__(self, rc, msg):
+        super().__init__(f"b200ldu error {rc}: {msg}")
+        self.rc = rc
+
+
+class Controls(C.Structure):
+    _fields_ = [
+        ("tolerance", C.c_double), ("relTol", C.c_double),
+        ("maxIter", C.c_int), ("minIter", C.c_int), ("nSweeps", C.c_int),
+        ("omega", C.c_double), ("bicgstabRefQuirk", C.c_int),
+        ("nCellsInCoarsestLevel", C.c_int), ("mergeLevels", C.c_int),
+        ("nPreSweeps", C.c_int), ("preSweepsLevelMultiplier", C.c_int), ("maxPreSweeps", C.c_int),
+        ("nPostSweeps", C.c_int), ("postSweepsLevelMultiplier", C.c_int), ("maxPostSweeps", C.c_int),
+        ("nFinestSweeps", C.c_int), ("interpolateCorrection", C.c_int),
+        ("scaleCorrection", C.c_int), ("directSolveCoarsest", C.c_int), ("checkEvery", C.c_int),
+    ]
+
+
+class Perf(C.Structure):
+    _fields_ = [
+        ("initialResidual", C.c_double), ("finalResidual", C.c_double), ("normFactor", C.c_double),
+        ("nIterations", C.c_int), ("converged", C.c_int), ("singular", C.c_int),
+        ("solverName", C.c_char * 64),
+    ]
+
+    def line(self, fieldName="p"):
+        """The reference's solverPerformance::print line (SolverPerformance.C:96-123)."""
+        nm = self.solverName.decode()
+        if self.singular:
+            return f"{nm}:  Solving for {fieldName}:  solution singularity"
+        return (f"{nm}:  Solving for {fieldName}, Initial residual = {self.initialResidual:g}, "
+                f"Final residual = {self.finalResidual:g}, No Iterations {self.nIterations}")
+
+
+EXPORTS = [
+    "b200ldu_last_error", "b200ldu_controls_default", "b200ldu_ctx_create", "b200ldu_ctx_destroy",
+    "b200ldu_comm_unique_id", "b200ldu_comm_init", "b200ldu_ctx_set_stream", "b200ldu_ctx_sync",
+    "b200ldu_addr_create", "b200ldu_addr_destroy", "b200ldu_addr_info", "b200ldu_addr_perm",
+    "b200ldu_matrix_create", "b200ldu_matrix_set", "b200ldu_matrix_destroy",
+    "b200ldu_amul", "b200ldu_tmul", "b200ldu_sumA", "b200ldu_residual", "b200ldu_H", "b200ldu_H1",
+    "b200ldu_faceH", "b200ldu_precondition", "b200ldu_smooth",
+    "b200ldu_vec_len", "b200ldu_to_banded", "b200ldu_from_banded", "b200ldu_amul_banded",
+    "b200ldu_solve", "b200ldu_solve_host", "b200ldu_launch_count",
+    "b200ldu_gamg_create", "b200ldu_gamg_destroy", "b200ldu_gamg_nlevels", "b200ldu_gamg_level_size",
+    "b200ldu_gamg_restrict_addr",
+    "b200ldu_fv_boundary_set", "b200ldu_fv_surface_integrate", "b200ldu_fv_gauss_grad",
+    "b200ldu_fv_laplacian_fill", "b200ldu_fv_convection_fill", "b200ldu_fv_interpolate_linear",
+    "b200ldu_fv_add_boundary_diag", "b200ldu_fv_add_boundary_source",
+]
+
+_lib = None
+vp = C.c_void_p
+
+
+def lib():
+    """Load libb200ldu.so; raise loudly if it has not been built (no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). This package has no CPU or PyTorch fallback.")
+    # torch bundles its own libnccl.so.2 (newer than the system one); load torch first so
+    # both torch and this library resolve the same NCCL
+    import torch  # noqa: F401
+    L = C.CDLL(LIB_PATH)
+    L.b200ldu_last_error.restype = C.c_char_p
+    L.b200ldu_vec_len.restype = C.c_longlong
+    L.b200ldu_vec_len.argtypes = [vp]
+    L.b200ldu_launch_count.restype = C.c_longlong
+    L.b200ldu_launch_count.argtypes = [vp]
+    L.b200ldu_controls_default.argtypes = [C.POINTER(Controls)]
+    L.b200ldu_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.b200ldu_ctx_destroy.argtypes = [vp]
+    L.b200ldu_comm_unique_id.argtypes = [vp]
+    L.b200ldu_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.b200ldu_ctx_set_stream.argtypes = [vp, vp]
+    L.b200ldu_ctx_sync.argtypes = [vp]
+    L.b200ldu_addr_create.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, C.POINTER(vp)]
+    L.b200ldu_addr_destroy.argtypes = [vp]
+    L.b200ldu_addr_info.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
+                                    C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.b200ldu_addr_perm.argtypes = [vp, vp]
+    L.b200ldu_matrix_create.argtypes = [vp, C.POINTER(vp)]
+    L.b200ldu_matrix_set.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.b200ldu_matrix_destroy.argtypes = [vp]
+    for nm in ("b200ldu_amul", "b200ldu_tmul", "b200ldu_H", "b200ldu_faceH", "b200ldu_amul_banded",
+               "b200ldu_to_banded", "b200ldu_from_banded"):
+        getattr(L, nm).argtypes = [vp, vp, vp]
+    L.b200ldu_sumA.argtypes = [vp, vp]
+    L.b200ldu_H1.argtypes = [vp, vp]
+    L.b200ldu_residual.argtypes = [vp, vp, vp, vp]
+    L.b200ldu_precondition.argtypes = [vp, C.c_char_p, C.c_int, vp, vp]
+    L.b200ldu_smooth.argtypes = [vp, C.c_char_p, C.c_double, vp, vp, C.c_int]
+    L.b200ldu_solve.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(Controls), vp, vp, vp,
+                                C.POINTER(Perf), vp, C.c_int]
+    L.b200ldu_solve_host.argtypes = L.b200ldu_solve.argtypes
+    L.b200ldu_gamg_create.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
+    L.b200ldu_gamg_destroy.argtypes = [vp]
+    L.b200ldu_gamg_nlevels.argtypes = [vp]
+    L.b200ldu_gamg_level_size.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.b200ldu_gamg_restrict_addr.argtypes = [vp, C.c_int, vp]
+    L.b200ldu_fv_boundary_set.argtypes = [vp, C.c_int, vp]
+    L.b200ldu_fv_surface_integrate.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int]
+    L.b200ldu_fv_gauss_grad.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
+    L.b200ldu_fv_laplacian_fill.argtypes = [vp, vp, vp, vp, vp]
+    L.b200ldu_fv_convection_fill.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.b200ldu_fv_interpolate_linear.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.b200ldu_fv_add_boundary_diag.argtypes = [vp, vp, vp]
+    L.b200ldu_fv_add_boundary_source.argtypes = [vp, vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise B200LduError(rc, lib().b200ldu_last_error().decode(errors="replace"))
+
+
+def controls(**kw):
+    c = Controls()
+    lib().b200ldu_controls_default(C.byref(c))
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise KeyError(k)
+        setattr(c, k, v)
+    return c
+
+
+def _np_i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _np_f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _hp(a):
+    return None if a is None else a.ctypes.data_as(vp)
+
+
+def _dp(t):
+    """device pointer of a torch cuda float64/int32 tensor (or None)"""
+    if t is None:
+        return None
+    if not t.is_cuda or not t.is_contiguous():
+        raise ValueError("device pointers must come from contiguous CUDA tensors")
+    return vp(t.data_ptr())
+
+
+class Context:
+    """One per GPU (replaces argList's device selection and the Pstream communicator)."""
+
+    def __init__(self, device=0, use_torch_stream=True):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("b200ldu needs a CUDA device; there is no CPU fallback")
+        self.h = vp()
+        check(lib().b200ldu_ctx_create(device, C.byref(self.h)))
+        self.device = torch.device("cuda", device)
+        if use_torch_stream:
+            check(lib().b200ldu_ctx_set_stream(self.h, vp(torch.cuda.current_stream(self.device).cuda_stream)))
+        self.rank, self.nRanks = 0, 1
+
+    def comm_init_from_torch(self):
+        """Create the NCCL communicator; the unique id travels over torch.distributed."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = (C.c_char * 128)()
+        if rank == 0:
+            check(lib().b200ldu_comm_unique_id(C.cast(buf, vp)))
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            t = t.to(self.device)
+        dist.broadcast(t, 0)
+        raw = bytes(t.cpu().numpy().tobytes())
+        idbuf = C.create_string_buffer(raw, 128)
+        check(lib().b200ldu_comm_init(self.h, C.cast(idbuf, vp), rank, world))
+        self.rank, self.nRanks = rank, world
+
+    def sync(self):
+        check(lib().b200ldu_ctx_sync(self.h))
+
+    @property
+    def launches(self):
+        return lib().b200ldu_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().b200ldu_ctx_destroy(self.h)
+            self.h = vp()
+
+
+class LduAddressing:
+    """lduAddressing (+ coupled patches) -> banded device layout."""
+
+    def __init__(self, ctx, nCells, lower, upper, patchStart=None, faceCells=None, neighbRank=None,
+                 cellCentres=None):
+        self.ctx = ctx
+        self.nCells = int(nCells)
+        l, u = _np_i32(lower), _np_i32(upper)
+        self.nFaces = len(l)
+        ps, fc, nr = _np_i32(patchStart), _np_i32(faceCells), _np_i32(neighbRank)
+        nP = 0 if ps is None else len(ps) - 1
+        self.nPatchFaces = 0 if ps is None else int(ps[-1])
+        cc = _np_f64(cellCentres)
+        self.h = vp()
+        check(lib().b200ldu_addr_create(ctx.h, self.nCells, self.nFaces, _hp(l), _hp(u), nP, _hp(ps), _hp(fc),
+                                        _hp(nr), _hp(cc), C.byref(self.h)))
+
+    def info(self):
+        a, b, c = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        d, e = C.c_int(), C.c_int()
+        check(lib().b200ldu_addr_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e)))
+        return dict(nPadRows=a.value, nEntries=b.value, nHalo=c.value, bandRows=d.value, nBands=e.value)
+
+    def perm(self):
+        p = np.zeros(self.nCells, dtype=np.int32)
+        check(lib().b200ldu_addr_perm(self.h, _hp(p)))
+        return p
+
+    @property
+    def vec_len(self):
+        return lib().b200ldu_vec_len(self.h)
+
+    def close(self):
+        if self.h:
+            lib().b200ldu_addr_destroy(self.h)
+            self.h = vp()
+
+
+class LduMatrix:
+    """lduMatrix: coefficients in banded form + the operations the solvers consume."""
+
+    def __init__(self, addr):
+        self.addr = addr
+        self.h = vp()
+        check(lib().b200ldu_matrix_create(addr.h, C.byref(self.h)))
+        self._keep = None
+
+    def set(self, diag, upper, lower=None, bouCoeffs=None, intCoeffs=None):
+        self._keep = (diag, upper, lower, bouCoeffs, intCoeffs)  # faceH reads upper/lower later
+        check(lib().b200ldu_matrix_set(self.h, _dp(diag), _dp(upper), _dp(lower), _dp(bouCoeffs), _dp(intCoeffs)))
+        return self
+
+    def _new(self, like, n=None):
+        import torch
+        return torch.empty(like.shape[0] if n is None else n, dtype=torch.float64, device=like.device)
+
+    def Amul(self, psi):
+        out = self._new(psi)
+        check(lib().b200ldu_amul(self.h, _dp(psi), _dp(out)))
+        return out
+
+    def Tmul(self, psi):
+        out = self._new(psi)
+        check(lib().b200ldu_tmul(self.h, _dp(psi), _dp(out)))
+        return out
+
+    def sumA(self, like):
+        out = self._new(like)
+        check(lib().b200ldu_sumA(self.h, _dp(out)))
+        return out
+
+    def residual(self, psi, source):
+        out = self._new(psi)
+        check(lib().b200ldu_residual(self.h, _dp(psi), _dp(source), _dp(out)))
+        return out
+
+    def H(self, psi):
+        out = self._new(psi)
+        check(lib().b200ldu_H(self.h, _dp(psi), _dp(out)))
+        return out
+
+    def H1(self, like):
+        out = self._new(like)
+        check(lib().b200ldu_H1(self.h, _dp(out)))
+        return out
+
+    def faceH(self, psi):
+        out = self._new(psi, self.addr.nFaces)
+        check(lib().b200ldu_faceH(self.h, _dp(psi), _dp(out)))
+        return out
+
+    def precondition(self, name, rA, transpose=False):
+        out = self._new(rA)
+        check(lib().b200ldu_precondition(self.h, name.encode(), int(transpose), _dp(rA), _dp(out)))
+        return out
+
+    def smooth(self, name, psi, source, nSweeps, omega=0.9):
+        p = psi.clone()
+        check(lib().b200ldu_smooth(self.h, name.encode(), omega, _dp(p), _dp(source), nSweeps))
+        return p
+
+    def solve(self, solver, pre, psi, source, gamg=None, histCap=0, **ctl):
+        """lduMatrix::solver::New(...)->solve(psi, source): psi updated in place.
+        Returns (Perf, history ndarray)."""
+        c = controls(**ctl)
+        perf = Perf()
+        hist = np.full(max(histCap, 1), np.nan)
+        check(lib().b200ldu_solve(self.h, solver.encode(), (pre or "").encode(), C.byref(c),
+                                  gamg.h if gamg is not None else None, _dp(psi), _dp(source),
+                                  C.byref(perf), _hp(hist) if histCap else None, histCap))
+        return perf, hist[~np.isnan(hist)] if histCap else hist[:0]
+
+    def solve_host(self, solver, pre, psi_h, source_h, gamg=None, **ctl):
+        """End-to-end entry: HOST numpy psi/source, H2D + solve + D2H inside the call."""
+        c = controls(**ctl)
+        perf = Perf()
+        assert psi_h.dtype == np.float64 and source_h.dtype == np.float64
+        check(lib().b200ldu_solve_host(self.h, solver.encode(), (pre or "").encode(), C.byref(c),
+                                       gamg.h if gamg is not None else None, _hp(psi_h), _hp(source_h),
+                                       C.byref(perf), None, 0))
+        return perf
+
+    def close(self):
+        if self.h:
+            lib().b200ldu_matrix_destroy(self.h)
+            self.h = vp()
+
+
+class GamgAgglomeration:
+    def __init__(self, addr, faceWeights, nCellsInCoarsestLevel=10, mergeLevels=1, forward=1):
+        self.addr = addr
+        self.h = vp()
+        self._fw = C.c_int(int(forward))
+        w = _np_f64(faceWeights)
+        check(lib().b200ldu_gamg_create(addr.h, _hp(w), nCellsInCoarsestLevel, mergeLevels, C.byref(self._fw),
+                                        C.byref(self.h)))
+        self.nLevels = lib().b200ldu_gamg_nlevels(self.h)
+
+    @property
+    def forward(self):
+        return self._fw.value
+
+    def level_size(self, lev):
+        a, b = C.c_int(), C.c_int()
+        check(lib().b200ldu_gamg_level_size(self.h, lev, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def restrict_addr(self, lev):
+        n = self.addr.nCells if lev == 0 else self.level_size(lev - 1)[0]
+        out = np.zeros(n, dtype=np.int32)
+        check(lib().b200ldu_gamg_restrict_addr(self.h, lev, _hp(out)))
+        return out
+
+    def close(self):
+        if self.h:
+            lib().b200ldu_gamg_destroy(self.h)
+            self.h = vp()
+
+
+def mesh_to_device(ctx, mesh, with_centres=True):
+    """LduAddressing for a rapidcfd-dev_b200.mesh.HexMesh (processor patches included)."""
+    ps, fc = mesh.patch_start_facecells()
+    nr = np.array([p.neighbRank for p in mesh.coupled_patches()], dtype=np.int32)
+    if len(nr) == 0:
+        ps = fc = nr = None
+    return LduAddressing(ctx, mesh.nCells, mesh.lower, mesh.upper, ps, fc, nr,
+                         mesh.cell_centres() if with_centres else None)

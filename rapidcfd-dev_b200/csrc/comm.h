@@ -1,0 +1,6 @@
+// comm.h -- internal interface of comm.cu
+#pragma once
+#include "internal.h"
+int comm_destroy(b200ldu_ctx *ctx);
+int comm_allreduce_sum(b200ldu_ctx *ctx, double *d_buf, int n);
+int comm_halo_exchange(b200ldu_addr *a, double *x, double *sendBuf, const int *stop);

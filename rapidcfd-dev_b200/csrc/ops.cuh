@@ -1,0 +1,272 @@
+// ops.cuh -- engine operators (row-gather family) and generic elementwise / scalar
+// kernels used by the solvers.  See engine.cuh for the Op concept.
+#pragma once
+#include "engine.cuh"
+
+// device-resident solver state: alpha/beta and the convergence decision never leave
+// the GPU inside the iteration loop (the reference synchronises the host three times
+// per PCG iteration: PCG.C:142,166,195).
+struct SolverScalars {
+    double sum[8];  // latest (all-reduced) sums
+    double wArA, wArAold, wApA, alpha, beta, omega;
+    double rA0rA, rA0rAold, tAtA, tAsA;
+    double normFactor, initialResidual, finalResidual, average, sumMag0;
+    double tolerance, relTol, nCellsGlobal;
+    int nIterations, converged, singular, stop;
+    int maxIter, minIter, histCap, nSweeps;
+};
+
+struct OpBase {
+    const int *stop = nullptr;
+    double *partials = nullptr;
+};
+
+// ---- Amul / Tmul: out = diag*x + sum v*x[c]  (lduMatrixATmul.C:78-137) ----
+// MODE 0 plain; 1: sum(out*x) [PCG wApA];  2: sum(aux*x), sum(out*x) [GAMG scale: num =
+// <source,field>, den = <Acf,field>, GAMGSolverScale.C:80-125];  3: sum(out*aux) [PBiCG
+// wApT, PBiCGStab rA0AyA];  4: sum(out*out), sum(out*aux) [PBiCGStab tAtA, tAsA]
+template <int MODE>
+struct AmulOp : OpBase {
+    static constexpr int NVEC = 1;
+    static constexpr int NRED = (MODE == 0) ? 0 : ((MODE == 1 || MODE == 3) ? 1 : 2);
+    static constexpr bool LOCAL = false;
+    const double *x, *diag, *aux;
+    double *out;
+    __device__ __forceinline__ void stage(int g, double &a, double &) const { a = x[g]; }
+    __device__ __forceinline__ void stage_own(int r, double2 &a, double2 &) const
+    {
+        a = *reinterpret_cast<const double2 *>(x + r);
+    }
+    __device__ __forceinline__ double init(int r, double a, double) const
+    {
+        return __dmul_rn(diag[r], a);
+    }
+    __device__ __forceinline__ double term(double acc, double v, double a, double) const
+    {
+        return __dadd_rn(acc, __dmul_rn(v, a));
+    }
+    __device__ __forceinline__ void finish(int r, double acc0, double acc1, double a0, double,
+                                           double a1, double, double *red) const
+    {
+        *reinterpret_cast<double2 *>(out + r) = make_double2(acc0, acc1);
+        if (MODE == 1) red[0] += acc0 * a0 + acc1 * a1;
+        if (MODE == 2) {
+            red[0] += aux[r] * a0 + aux[r + 1] * a1;
+            red[1] += acc0 * a0 + acc1 * a1;
+        }
+        if (MODE == 3) red[0] += acc0 * aux[r] + acc1 * aux[r + 1];
+        if (MODE == 4) {
+            red[0] += acc0 * acc0 + acc1 * acc1;
+            red[1] += acc0 * aux[r] + acc1 * aux[r + 1];
+        }
+    }
+};
+
+// ---- AINV ("DIC"/"DILU"): w = rD*(r - sum (v*rD[c])*r[c])  (AINVPreconditionerF.H:42-99)
+// optional fused dot <w, dotv> (wArA with dotv = r; wArT with dotv = rT)
+template <int NRED_>
+struct AinvOp : OpBase {
+    static constexpr int NVEC = 2, NRED = NRED_;
+    static constexpr bool LOCAL = true;
+    const double *r, *rD, *dotv;
+    double *out;
+    __device__ __forceinline__ void stage(int g, double &a, double &b) const
+    {
+        a = r[g];
+        b = rD[g];
+    }
+    __device__ __forceinline__ void stage_own(int row, double2 &a, double2 &b) const
+    {
+        a = *reinterpret_cast<const double2 *>(r + row);
+        b = *reinterpret_cast<const double2 *>(rD + row);
+    }
+    __device__ __forceinline__ double init(int, double, double) const { return 0.0; }
+    __device__ __forceinline__ double term(double acc, double v, double a, double b) const
+    {
+        return __dadd_rn(acc, __dmul_rn(__dmul_rn(v, b), a));
+    }
+    __device__ __forceinline__ void finish(int row, double acc0, double acc1, double a0, double b0,
+                                           double a1, double b1, double *red) const
+    {
+        double w0 = __dmul_rn(b0, __dsub_rn(a0, acc0));
+        double w1 = __dmul_rn(b1, __dsub_rn(a1, acc1));
+        *reinterpret_cast<double2 *>(out + row) = make_double2(w0, w1);
+        if (NRED == 1) {
+            double d0 = dotv ? dotv[row] : a0, d1 = dotv ? dotv[row + 1] : a1;
+            red[0] += w0 * d0 + w1 * d1;
+        }
+    }
+};
+
+// ---- Jacobi sweep (JacobiSmootherF.H:51-109; omega-damped, old psi everywhere) ----
+struct JacobiOp : OpBase {
+    static constexpr int NVEC = 1, NRED = 0;
+    static constexpr bool LOCAL = false;
+    const double *x, *diag, *b;
+    double *out;
+    double omega;
+    int nCells;
+    __device__ __forceinline__ void stage(int g, double &a, double &) const { a = x[g]; }
+    __device__ __forceinline__ void stage_own(int r, double2 &a, double2 &) const
+    {
+        a = *reinterpret_cast<const double2 *>(x + r);
+    }
+    __device__ __forceinline__ double init(int, double, double) const { return 0.0; }
+    __device__ __forceinline__ double term(double acc, double v, double a, double) const
+    {
+        return __dadd_rn(acc, __dmul_rn(v, a));
+    }
+    __device__ __forceinline__ double row(int r, double acc, double a) const
+    {
+        double rD = __ddiv_rn(1.0, diag[r]);
+        double w = __dmul_rn(omega, rD);
+        double extra = __dadd_rn(__dmul_rn(1 - omega, a), __dmul_rn(w, b[r]));
+        return __dsub_rn(extra, __dmul_rn(w, acc));
+    }
+    __device__ __forceinline__ void finish(int r, double acc0, double acc1, double a0, double,
+                                           double a1, double, double *) const
+    {
+        *reinterpret_cast<double2 *>(out + r) = make_double2(row(r, acc0, a0), row(r + 1, acc1, a1));
+    }
+};
+
+// ---- residual: rA = (b - diag*x) - sum v*x ; fused sum|rA|  (lduMatrixATmul.C:397-496)
+template <int NRED_>
+struct ResidualOp : OpBase {
+    static constexpr int NVEC = 1, NRED = NRED_;
+    static constexpr bool LOCAL = false;
+    const double *x, *diag, *b;
+    double *out;
+    __device__ __forceinline__ void stage(int g, double &a, double &) const { a = x[g]; }
+    __device__ __forceinline__ void stage_own(int r, double2 &a, double2 &) const
+    {
+        a = *reinterpret_cast<const double2 *>(x + r);
+    }
+    __device__ __forceinline__ double init(int r, double a, double) const
+    {
+        return __dsub_rn(b[r], __dmul_rn(diag[r], a));
+    }
+    __device__ __forceinline__ double term(double acc, double v, double a, double) const
+    {
+        return __dsub_rn(acc, __dmul_rn(v, a));
+    }
+    __device__ __forceinline__ void finish(int r, double acc0, double acc1, double, double, double,
+                                           double, double *red) const
+    {
+        *reinterpret_cast<double2 *>(out + r) = make_double2(acc0, acc1);
+        if (NRED == 1) red[0] += fabs(acc0) + fabs(acc1);
+    }
+};
+
+// ---- coefficient-only row sums: sumA (all entries, + diag), H1 (local, negated) ----
+template <bool LOCAL_, bool NEG_>
+struct CoeffSumOp : OpBase {
+    static constexpr int NVEC = 0, NRED = 0;
+    static constexpr bool LOCAL = LOCAL_;
+    const double *diag; // nullptr => start from 0
+    double *out;
+    __device__ __forceinline__ void stage(int, double &, double &) const {}
+    __device__ __forceinline__ void stage_own(int, double2 &, double2 &) const {}
+    __device__ __forceinline__ double init(int r, double, double) const
+    {
+        return diag ? diag[r] : 0.0;
+    }
+    __device__ __forceinline__ double term(double acc, double v, double, double) const
+    {
+        return NEG_ ? __dsub_rn(acc, v) : __dadd_rn(acc, v);
+    }
+    __device__ __forceinline__ void finish(int r, double acc0, double acc1, double, double, double,
+                                           double, double *) const
+    {
+        *reinterpret_cast<double2 *>(out + r) = make_double2(acc0, acc1);
+    }
+};
+
+// ---- off-diagonal product sums: H = -(sum v*x) local only (lduMatrixOperations.C:107-155);
+// GAMG interpolate: psi' = -(sum v*x)/diag over all entries (GAMGSolverInterpolate.C:45-110)
+template <bool LOCAL_, bool DIVDIAG_>
+struct OffDiagOp : OpBase {
+    static constexpr int NVEC = 1, NRED = 0;
+    static constexpr bool LOCAL = LOCAL_;
+    const double *x, *diag;
+    double *out;
+    __device__ __forceinline__ void stage(int g, double &a, double &) const { a = x[g]; }
+    __device__ __forceinline__ void stage_own(int r, double2 &a, double2 &) const
+    {
+        a = *reinterpret_cast<const double2 *>(x + r);
+    }
+    __device__ __forceinline__ double init(int, double, double) const { return 0.0; }
+    __device__ __forceinline__ double term(double acc, double v, double a, double) const
+    {
+        return DIVDIAG_ ? __dadd_rn(acc, __dmul_rn(v, a)) : __dsub_rn(acc, __dmul_rn(v, a));
+    }
+    __device__ __forceinline__ void finish(int r, double acc0, double acc1, double, double, double,
+                                           double, double *) const
+    {
+        if (DIVDIAG_) {
+            acc0 = __ddiv_rn(-acc0, diag[r]);
+            acc1 = __ddiv_rn(-acc1, diag[r + 1]);
+        }
+        *reinterpret_cast<double2 *>(out + r) = make_double2(acc0, acc1);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// elementwise kernels with fused reductions.  f(i2, red) handles elements 2*i2, 2*i2+1
+// (vectors are 16-byte aligned and of even length => 128-bit loads/stores).
+// ---------------------------------------------------------------------------
+constexpr int EW_THREADS = 256;
+
+template <int NRED, class F>
+__global__ void __launch_bounds__(EW_THREADS) ew_kernel(int n2, const int *stop, double *partials, F f)
+{
+    if (stop && *stop) return;
+    double red[NRED > 0 ? NRED : 1];
+#pragma unroll
+    for (int k = 0; k < (NRED > 0 ? NRED : 1); k++) red[k] = 0;
+    for (int i = blockIdx.x * EW_THREADS + threadIdx.x; i < n2; i += gridDim.x * EW_THREADS) f(i, red);
+    if (NRED > 0) block_reduce_store<(NRED > 0 ? NRED : 1), EW_THREADS>(red, partials, blockIdx.x);
+}
+
+inline int ew_grid(const b200ldu_ctx *ctx, int n2)
+{
+    int want = (n2 + EW_THREADS - 1) / EW_THREADS;
+    int cap = ctx->smCount * 8;
+    return want < 1 ? 1 : (want < cap ? want : cap);
+}
+
+template <int NRED, class F>
+int ew_launch(b200ldu_ctx *ctx, int n2, const int *stop, double *partials, int *nPartialsOut, F f)
+{
+    int g = ew_grid(ctx, n2);
+    ew_kernel<NRED, F><<<g, EW_THREADS, 0, ctx->stream>>>(n2, stop, partials, f);
+    ctx->launches++;
+    if (nPartialsOut) *nPartialsOut = g;
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}
+
+// sums NRED interleaved partial streams in fixed order, then thread 0 runs the scalar
+// logic g(sc).  One CTA.  With more than one rank the sums go through an all-reduce
+// between the two halves (see scalar_step in solvers.cu).
+template <int NRED, bool RUN_LOGIC, class G>
+__global__ void __launch_bounds__(256) scalar_kernel(const double *partials, int nPartials,
+                                                     SolverScalars *sc, G g)
+{
+    if (sc->stop) return;
+    if (NRED > 0) {
+        double red[NRED > 0 ? NRED : 1];
+#pragma unroll
+        for (int k = 0; k < (NRED > 0 ? NRED : 1); k++) {
+            double s = 0;
+            for (int i = threadIdx.x; i < nPartials; i += 256) s += partials[(size_t)i * NRED + k];
+            red[k] = s;
+        }
+        __shared__ double tot[NRED > 0 ? NRED : 1];
+        block_reduce_store<(NRED > 0 ? NRED : 1), 256>(red, tot, 0);
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int k = 0; k < NRED; k++) sc->sum[k] = tot[k];
+    }
+    if (RUN_LOGIC && threadIdx.x == 0) g(sc);
+}
