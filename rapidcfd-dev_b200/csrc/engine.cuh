@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) engine_kernel(const LayoutDev 
     if (op.stop && *op.stop) return;
     const int band = blockIdx.x;
     const int rowBase = band * L.bandRows;
-    const int stride = L.bandRows + L.maxHalo;
+    const int stride = (L.bandRows + L.maxHalo + 1) & ~1; // keep the second tile 16-byte aligned
     double *xs = smem;
     double *ys = smem + ((Op::NVEC > 1) ? stride : 0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -166,9 +166,11 @@ template <class Op>
 int engine_launch(b200ldu_addr *a, const double *val, const Op &op)
 {
     const LayoutDev &L = a->L;
-    size_t smem = sizeof(double) * (size_t)(L.bandRows + L.maxHalo) * Op::NVEC;
+    size_t smem = sizeof(double) * (size_t)((L.bandRows + L.maxHalo + 1) & ~1) * Op::NVEC;
     static size_t configured = 0; // per Op instantiation
-    if (smem > 48 * 1024 && smem > configured) {
+    // the kernel also owns a little static shared memory (reduction scratch): opt in to
+    // large dynamic shared memory well before the 48 KB default limit
+    if (smem > 40 * 1024 && smem > configured) {
         CUDA_TRY(cudaFuncSetAttribute(engine_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
         configured = smem;

@@ -117,6 +117,8 @@ struct b200ldu_matrix {
     bool haveT = false;
     double *d_val = nullptr;  // banded coefficients for Amul   [nEntries]
     double *d_valT = nullptr; // banded coefficients for Tmul   (aliases d_val when symmetric)
+    double *d_valS = nullptr, *d_valST = nullptr; // val * rD[column] for the AINV sweep (lazy)
+    bool valSValid = false, valSTValid = false;
     double *d_diag = nullptr; // banded diagonal [nPad] (padding rows = 1)
     double *d_rD = nullptr;   // 1/diag, built lazily per matrix_set
     bool rDValid = false;

@@ -287,7 +287,8 @@ extern "C" int b200ldu_matrix_destroy(b200ldu_matrix *m)
     cudaSetDevice(m->a->ctx->device);
     cudaStreamSynchronize(m->a->ctx->stream);
     if (m->d_valT && m->d_valT != m->d_val) cudaFree(m->d_valT);
-    void *ptrs[] = {m->d_val, m->d_diag, m->d_rD, m->d_partials, m->d_scal, m->d_hist, m->d_sendBuf};
+    void *ptrs[] = {m->d_val, m->d_diag, m->d_rD, m->d_partials, m->d_scal, m->d_hist, m->d_sendBuf,
+                    m->d_valS, m->d_valST};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (double *p : m->work)
@@ -372,6 +373,7 @@ extern "C" int b200ldu_matrix_set(b200ldu_matrix *m, const double *diag_d, const
     a->ctx->launches++;
     KERNEL_CHECK();
     m->haveT = needT;
+    m->valSValid = m->valSTValid = false; // AINV-scaled copies follow the coefficients
     m->upper_ext = upper_d;
     m->lower_ext = lo;
     return B200LDU_OK;
@@ -412,10 +414,35 @@ int mat_amul(b200ldu_matrix *m, bool transpose, double *x, double *out, int mode
     return B200LDU_EINVAL;
 }
 
+static int ainv_prepare(b200ldu_matrix *m, bool transpose)
+{
+    b200ldu_addr *a = m->a;
+    bool useT = transpose && m->d_valT != m->d_val;
+    double **dst = useT ? &m->d_valST : &m->d_valS;
+    bool *valid = useT ? &m->valSTValid : &m->valSValid;
+    if (*valid) return B200LDU_OK;
+    size_t ne = (size_t)(a->nEntries > 0 ? a->nEntries : 1);
+    if (!*dst) CUDA_TRY(cudaMalloc((void **)dst, sizeof(double) * ne));
+    const LayoutDev &L = a->L;
+    size_t smem = sizeof(double) * (size_t)(L.bandRows + L.maxHalo);
+    static size_t configured = 0;
+    if (smem > 40 * 1024 && smem > configured) {
+        CUDA_TRY(cudaFuncSetAttribute(ainv_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    ainv_scale_kernel<<<L.nBands, ENGINE_THREADS, smem, a->ctx->stream>>>(L, useT ? m->d_valT : m->d_val, m->d_rD,
+                                                                           *dst);
+    a->ctx->launches++;
+    KERNEL_CHECK();
+    *valid = true;
+    return B200LDU_OK;
+}
+
 int mat_ainv(b200ldu_matrix *m, bool transpose, const double *r, double *w, bool fuseDot,
              const double *dotv, double *partials, const int *stop)
 {
-    const double *val = transpose ? m->d_valT : m->d_val;
+    TRY(ainv_prepare(m, transpose));
+    const double *val = (transpose && m->d_valT != m->d_val) ? m->d_valST : m->d_valS;
     if (fuseDot) {
         AinvOp<1> op;
         op.stop = stop;

@@ -63,33 +63,32 @@ struct AmulOp : OpBase {
 };
 
 // ---- AINV ("DIC"/"DILU"): w = rD*(r - sum (v*rD[c])*r[c])  (AINVPreconditionerF.H:42-99)
-// optional fused dot <w, dotv> (wArA with dotv = r; wArT with dotv = rT)
+// The first product v*rD[c] does not depend on r: it is formed once per matrix
+// (ainv_scale_kernel below, same rounding) so the sweep stages a single vector and
+// streams exactly the bytes of an Amul.  Optional fused dot <w, dotv> (wArA with
+// dotv = r; wArT with dotv = rT).
 template <int NRED_>
 struct AinvOp : OpBase {
-    static constexpr int NVEC = 2, NRED = NRED_;
+    static constexpr int NVEC = 1, NRED = NRED_;
     static constexpr bool LOCAL = true;
     const double *r, *rD, *dotv;
     double *out;
-    __device__ __forceinline__ void stage(int g, double &a, double &b) const
-    {
-        a = r[g];
-        b = rD[g];
-    }
-    __device__ __forceinline__ void stage_own(int row, double2 &a, double2 &b) const
+    __device__ __forceinline__ void stage(int g, double &a, double &) const { a = r[g]; }
+    __device__ __forceinline__ void stage_own(int row, double2 &a, double2 &) const
     {
         a = *reinterpret_cast<const double2 *>(r + row);
-        b = *reinterpret_cast<const double2 *>(rD + row);
     }
     __device__ __forceinline__ double init(int, double, double) const { return 0.0; }
-    __device__ __forceinline__ double term(double acc, double v, double a, double b) const
+    __device__ __forceinline__ double term(double acc, double vs, double a, double) const
     {
-        return __dadd_rn(acc, __dmul_rn(__dmul_rn(v, b), a));
+        return __dadd_rn(acc, __dmul_rn(vs, a));
     }
-    __device__ __forceinline__ void finish(int row, double acc0, double acc1, double a0, double b0,
-                                           double a1, double b1, double *red) const
+    __device__ __forceinline__ void finish(int row, double acc0, double acc1, double a0, double,
+                                           double a1, double, double *red) const
     {
-        double w0 = __dmul_rn(b0, __dsub_rn(a0, acc0));
-        double w1 = __dmul_rn(b1, __dsub_rn(a1, acc1));
+        double2 d = *reinterpret_cast<const double2 *>(rD + row);
+        double w0 = __dmul_rn(d.x, __dsub_rn(a0, acc0));
+        double w1 = __dmul_rn(d.y, __dsub_rn(a1, acc1));
         *reinterpret_cast<double2 *>(out + row) = make_double2(w0, w1);
         if (NRED == 1) {
             double d0 = dotv ? dotv[row] : a0, d1 = dotv ? dotv[row + 1] : a1;
@@ -97,6 +96,38 @@ struct AinvOp : OpBase {
         }
     }
 };
+
+// valS[e] = val[e] * rD[column(e)] for the owner/neighbour entries (interface slots are
+// never read by the LOCAL sweep and are zeroed).  Same band/slice walk as the engine.
+static __global__ void __launch_bounds__(ENGINE_THREADS) ainv_scale_kernel(const LayoutDev L,
+                                                                    const double *__restrict__ val,
+                                                                    const double *__restrict__ rD,
+                                                                    double *__restrict__ valS)
+{
+    extern __shared__ double smem[];
+    const int band = blockIdx.x, rowBase = band * L.bandRows;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < L.bandRows; i += ENGINE_THREADS) smem[i] = rD[rowBase + i];
+    const int hs = L.haloStart[band], hn = L.haloStart[band + 1] - hs;
+    for (int i = tid; i < hn; i += ENGINE_THREADS) {
+        int g = L.haloIdx[hs + i];
+        smem[L.bandRows + i] = g < L.nPad ? rD[g] : 0.0;
+    }
+    __syncthreads();
+    for (int sl = warp; sl < L.slicesPerBand; sl += ENGINE_THREADS / 32) {
+        const int s = band * L.slicesPerBand + sl;
+        const long long base = L.sliceStart[s];
+        const int W = L.sliceW[s], WL = L.sliceWL[s];
+        for (int j = 0; j < W; j++) {
+            size_t e = (size_t)base + (size_t)j * SLICE_ROWS + 2 * lane;
+            double2 v = *reinterpret_cast<const double2 *>(val + e);
+            uint32_t c = *reinterpret_cast<const uint32_t *>(L.col + e);
+            double2 o = make_double2(0, 0);
+            if (j < WL) o = make_double2(__dmul_rn(v.x, smem[c & 0xffffu]), __dmul_rn(v.y, smem[c >> 16]));
+            *reinterpret_cast<double2 *>(valS + e) = o;
+        }
+    }
+}
 
 // ---- Jacobi sweep (JacobiSmootherF.H:51-109; omega-damped, old psi everywhere) ----
 struct JacobiOp : OpBase {

@@ -97,7 +97,8 @@ def test_pcg_history(gpu, meshmod, orc, pre, dims):
     _cmp_hist(hist, href)
     assert abs(perf.initialResidual - pr.initialResidual) <= 1e-12 * pr.initialResidual
     assert abs(perf.normFactor - pr.normFactor) <= 1e-12 * pr.normFactor
-    np.testing.assert_allclose(psi.cpu().numpy(), psi_ref, atol=1e-7)
+    np.testing.assert_allclose(psi.cpu().numpy(), psi_ref, rtol=0, atol=2e-6)  # both stop at 1e-7 residual
+    np.testing.assert_allclose(psi.cpu().numpy(), xs, rtol=0, atol=1e-4)
     assert perf.converged == 1 and perf.singular == 0
     cs.close()
 
