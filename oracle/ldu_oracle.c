@@ -768,3 +768,7 @@ int orc_solve(const orc_matrix *m, const char *solver, const char *pre, const or
     }
     return -1;
 }
+
+/* accessors for tests */
+const int *orc_addr_lower(const orc_addr *a) { return a->l; }
+const int *orc_addr_upper(const orc_addr *a) { return a->u; }

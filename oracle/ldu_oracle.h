@@ -78,6 +78,8 @@ void orc_addr_free(orc_addr *a);
 const int *orc_addr_owner_start(const orc_addr *a);
 const int *orc_addr_losort(const orc_addr *a);
 const int *orc_addr_losort_start(const orc_addr *a);
+const int *orc_addr_lower(const orc_addr *a);
+const int *orc_addr_upper(const orc_addr *a);
 
 /* ---- matrix ---- */
 orc_matrix *orc_matrix_create(const orc_addr *a, const double *diag, const double *upper,

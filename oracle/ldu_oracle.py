@@ -68,7 +68,8 @@ def lib():
         L.orc_addr_create.restype = C.c_void_p
         L.orc_addr_create.argtypes = [C.c_int, C.c_int, c_ip, c_ip, C.c_int, c_ip, c_ip]
         L.orc_addr_free.argtypes = [C.c_void_p]
-        for nm in ("orc_addr_owner_start", "orc_addr_losort", "orc_addr_losort_start"):
+        for nm in ("orc_addr_owner_start", "orc_addr_losort", "orc_addr_losort_start", "orc_addr_lower",
+                   "orc_addr_upper"):
             getattr(L, nm).restype = c_ip
             getattr(L, nm).argtypes = [C.c_void_p]
         L.orc_matrix_create.restype = C.c_void_p
@@ -169,6 +170,12 @@ class Addr:
         self.nPatches = nP
         self.h = lib().orc_addr_create(self.nCells, self.nFaces, _i(self.l), _i(self.u), nP,
                                        _i(self.patchStart), _i(self.faceCells))
+
+    def lower(self):
+        return np.ctypeslib.as_array(lib().orc_addr_lower(self.h), (max(self.nFaces, 1),))[: self.nFaces].copy()
+
+    def upper(self):
+        return np.ctypeslib.as_array(lib().orc_addr_upper(self.h), (max(self.nFaces, 1),))[: self.nFaces].copy()
 
     def owner_start(self):
         return np.ctypeslib.as_array(lib().orc_addr_owner_start(self.h), (self.nCells + 1,)).copy()

@@ -88,6 +88,7 @@ struct b200ldu_addr {
     long long nEntries = 0;
     long long nHaloTotal = 0;
     std::vector<int> perm_h, iperm_h;
+    std::vector<double> centres_h; // optional cell centres (kept for GAMG coarse-level banding)
     // device arrays owned
     long long *d_sliceStart = nullptr;
     uint16_t *d_sliceW = nullptr, *d_sliceWL = nullptr, *d_col = nullptr;
@@ -123,7 +124,7 @@ struct b200ldu_matrix {
     double *d_rD = nullptr;   // 1/diag, built lazily per matrix_set
     bool rDValid = false;
     // caller-order pointers kept for faceH (caller owns)
-    const double *upper_ext = nullptr, *lower_ext = nullptr;
+    const double *upper_ext = nullptr, *lower_ext = nullptr, *diag_ext = nullptr;
     // solver workspace (allocated once, reused across solves -- PCGCache.H:9-58)
     std::vector<double *> work;
     double *d_partials = nullptr; // reduction partials

@@ -148,6 +148,7 @@ extern "C" int b200ldu_addr_create(b200ldu_ctx *ctx, int nCells, int nFaces, con
                 return B200LDU_EINVAL;
             }
     }
+    if (cellCentres_h) a->centres_h.assign(cellCentres_h, cellCentres_h + 3 * (size_t)nCells);
     int rc = layout_build(a, cellCentres_h);
     if (rc != B200LDU_OK) {
         b200ldu_addr_destroy(a);
@@ -375,6 +376,7 @@ extern "C" int b200ldu_matrix_set(b200ldu_matrix *m, const double *diag_d, const
     m->haveT = needT;
     m->valSValid = m->valSTValid = false; // AINV-scaled copies follow the coefficients
     m->upper_ext = upper_d;
+    m->diag_ext = diag_d;
     m->lower_ext = lo;
     return B200LDU_OK;
 }

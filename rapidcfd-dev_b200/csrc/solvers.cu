@@ -9,62 +9,9 @@
 // LDU/solvers/PCG/PCG.C:69-208, PBiCG/PBiCG.C:68-246, PBiCGStab/PBiCGStab.C:66-300,
 // smoothSolver/smoothSolver.C:77-193, diagonalSolver/diagonalSolver.C:62-81,
 // LduMatrix/LduMatrix/SolverPerformance.C:32-92.
-#include "comm.h"
 #include "ldu.h"
-#include "ops.cuh"
-#include "solvers.h"
 
-constexpr double GREAT_ = 1e20;   // SolverPerformance.H:269-275
-constexpr double SMALL_ = 1e-20;
-constexpr double VSMALL_ = 1e-300;
-
-// ---- scalar step: sum partials (fixed order) [+ all-reduce] + scalar logic -------
-template <int NRED, class G>
-int scalar_step(Solve &S, int nPartials, G g)
-{
-    b200ldu_ctx *ctx = S.ctx;
-    if (ctx->nRanks == 1 || NRED == 0) {
-        scalar_kernel<NRED, true, G><<<1, 256, 0, ctx->stream>>>(S.partials, nPartials, S.sc, g);
-        ctx->launches++;
-    } else {
-        scalar_kernel<NRED, false, G><<<1, 256, 0, ctx->stream>>>(S.partials, nPartials, S.sc, g);
-        ctx->launches++;
-        TRY(comm_allreduce_sum(ctx, S.sc->sum, NRED)); // device pointer arithmetic only
-        scalar_kernel<0, true, G><<<1, 256, 0, ctx->stream>>>(S.partials, 0, S.sc, g);
-        ctx->launches++;
-    }
-    KERNEL_CHECK();
-    return B200LDU_OK;
-}
-
-__device__ __forceinline__ bool check_convergence(SolverScalars *sc)
-{
-    // SolverPerformance.C:74-85
-    bool c = sc->finalResidual < sc->tolerance ||
-             (sc->relTol > SMALL_ && sc->finalResidual < sc->relTol * sc->initialResidual);
-    sc->converged = c ? 1 : 0;
-    return c;
-}
-
-__device__ __forceinline__ void hist_put(SolverScalars *sc, double *hist, int i, double v)
-{
-    if (hist && i < sc->histCap) hist[i] = v;
-}
-
-// end of a Krylov iteration body: (nIterations++ < maxIter && !converged) || nIterations < minIter
-__device__ __forceinline__ void end_of_body(SolverScalars *sc, double *hist, double sumMag)
-{
-    sc->finalResidual = sumMag / sc->normFactor;
-    hist_put(sc, hist, sc->nIterations + 1, sc->finalResidual);
-    bool conv = check_convergence(sc);
-    int n = sc->nIterations;
-    sc->nIterations = n + 1;
-    bool cont = (n < sc->maxIter && !conv) || (n + 1 < sc->minIter);
-    if (!cont) sc->stop = 1;
-}
-
-#define V2(p) reinterpret_cast<double2 *>(p)
-#define CV2(p) reinterpret_cast<const double2 *>(p)
+#include "solver_steps.cuh"
 
 // initial residual, normFactor and the first convergence test, common to all solvers
 // (PCG.C:92-128; lduMatrixSolver.C:205-236).  wA must hold A.psi; tmp receives sumA.
@@ -454,6 +401,11 @@ int solve_diagonal(Solve &S)
     });
 }
 
+int gamg_run_cycles(Solve &S, long long maxBodies, int (*body)(void *), void *arg)
+{
+    return run_iterations(S, maxBodies, [&](long long) -> int { return body(arg); });
+}
+
 double *Solve::vec(int k)
 {
     while ((int)m->work.size() <= k) m->work.push_back(nullptr);
@@ -603,7 +555,8 @@ int solve_banded(b200ldu_matrix *m, const char *solver, const char *pre, const b
         }
         if (S.fixedSweeps) perf->nIterations = S.fixedSweeps;
         if (S.sweepParityUnknown) {
-            long long sweeps = perf->nIterations; // nIterations counts sweeps
+            long long sweeps = perf->nIterations; // smoothSolver: nIterations counts sweeps
+            if (S.gamgFinestSweeps) sweeps = (long long)perf->nIterations * S.gamgFinestSweeps;
             S.resultBuf = S.smoothBuf[sweeps & 1];
         }
         if (S.resultBuf) *resultBuf = S.resultBuf;

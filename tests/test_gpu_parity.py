@@ -228,7 +228,11 @@ def test_fv_face_sums_bit_exact(gpu, meshmod, orc):
     addr = capi.mesh_to_device(ctx, mesh)
     L = capi.lib()
     dev = ctx.device
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    keep = []  # device inputs must outlive the asynchronous launches that read them
+
+    def t(a):
+        keep.append(torch.from_numpy(np.ascontiguousarray(a)).to(dev))
+        return keep[-1]
     rng = np.random.default_rng(5)
     bfc = np.concatenate([p.faceCells for p in mesh.patches]).astype(np.int32)
     bSf = np.concatenate([p.Sf for p in mesh.patches])
