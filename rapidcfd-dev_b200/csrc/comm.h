@@ -3,4 +3,6 @@
 #include "internal.h"
 int comm_destroy(b200ldu_ctx *ctx);
 int comm_allreduce_sum(b200ldu_ctx *ctx, double *d_buf, int n);
-int comm_halo_exchange(b200ldu_addr *a, double *x, double *sendBuf, const int *stop);
+int comm_halo_exchange(b200ldu_addr *a, double *x, double *sendBuf, const int *stop, int *usedP2P);
+int comm_addr_setup(b200ldu_addr *a);
+P2PRed comm_p2p_red(b200ldu_ctx *ctx);

@@ -88,7 +88,39 @@ __global__ void __launch_bounds__(ENGINE_THREADS) engine_kernel(const LayoutDev 
 {
     extern __shared__ double smem[];
     if (op.stop && *op.stop) return;
-    const int band = blockIdx.x;
+    // Fused halo send (peer-memory path): the first nPackChunks CTAs of the grid gather psi
+    // at the processor-patch face cells, store it straight into the neighbours' receive
+    // buffers over NVLink and release their arrival flags; all other CTAs are SpMV bands
+    // (those that reference received values wait for the neighbours' flags below).
+    const bool fusedPack = op.waitHalo && L.nPackChunks > 0;
+    unsigned long long haloSeqNow = 0;
+    if (fusedPack) {
+        haloSeqNow = L.seqs[1] + 1; // seqs[1] only advances when the whole grid has finished
+        if ((int)blockIdx.x < L.nPackChunks) {
+            const PackChunk c = L.packChunks[blockIdx.x];
+            const PackPatch P = L.packPatches[c.patch];
+            const double *src = op.pack_src();
+            double *dst = P.dst[haloSeqNow & 1];
+            for (int i = c.begin + threadIdx.x; i < c.end; i += ENGINE_THREADS)
+                dst[i - P.start] = src[__ldg(L.sendRows + i)];
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long done = atomicAdd(&L.seqs[8 + c.patch], 1ull) + 1;
+                if (done == (unsigned long long)P.nChunks) {
+                    L.seqs[8 + c.patch] = 0;
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.flag), "l"(haloSeqNow) : "memory");
+                }
+                if (atomicAdd(&L.seqs[6], 1ull) + 1 == (unsigned long long)gridDim.x) {
+                    L.seqs[6] = 0;
+                    __threadfence();
+                    L.seqs[1] = haloSeqNow;
+                }
+            }
+            return;
+        }
+    }
+    const int band = blockIdx.x - (fusedPack ? L.nPackChunks : 0);
     const int rowBase = band * L.bandRows;
     const int stride = (L.bandRows + L.maxHalo + 1) & ~1; // keep the second tile 16-byte aligned
     double *xs = smem;
@@ -106,10 +138,30 @@ __global__ void __launch_bounds__(ENGINE_THREADS) engine_kernel(const LayoutDev 
     }
     {
         const int hs = L.haloStart[band], hn = L.haloStart[band + 1] - hs;
+        // peer-memory halo: bands that reference received values wait for the neighbours'
+        // arrival flags here, so interior bands overlap with the exchange
+        const double *remoteTail = nullptr;
+        if (op.waitHalo && L.haloFlags) {
+            const unsigned long long seq = fusedPack ? haloSeqNow : *L.haloSeq;
+            remoteTail = (seq & 1) ? L.tail1 : L.tail0;
+            if (hn > 0 && __ldg(L.haloIdx + hs + hn - 1) >= L.nPad) {
+                if (tid < L.nNbr) {
+                    const unsigned long long *f = L.haloFlags + L.nbr[tid];
+                    unsigned long long v;
+                    do {
+                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+                    } while (v < seq);
+                }
+                __syncthreads();
+            }
+        }
         for (int i = tid; i < hn; i += ENGINE_THREADS) {
             int g = __ldg(L.haloIdx + hs + i);
             double a, b = 0;
-            op.stage(g, a, b);
+            if (remoteTail && g >= L.nPad)
+                a = __ldcg(remoteTail + (g - L.nPad));
+            else
+                op.stage(g, a, b);
             xs[L.bandRows + i] = a;
             if (Op::NVEC > 1) ys[L.bandRows + i] = b;
         }
@@ -160,6 +212,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS) engine_kernel(const LayoutDev 
         op.finish(rowBase + lr, acc0, acc1, a0, b0, a1, b1, red);
     }
     if (Op::NRED > 0) block_reduce_store<(Op::NRED > 0 ? Op::NRED : 1), ENGINE_THREADS>(red, op.partials, band);
+    if (fusedPack && threadIdx.x == 0) {
+        if (atomicAdd(&L.seqs[6], 1ull) + 1 == (unsigned long long)gridDim.x) {
+            L.seqs[6] = 0;
+            __threadfence();
+            L.seqs[1] = haloSeqNow;
+        }
+    }
 }
 
 template <class Op>
@@ -175,7 +234,8 @@ int engine_launch(b200ldu_addr *a, const double *val, const Op &op)
                                       (int)smem));
         configured = smem;
     }
-    engine_kernel<Op><<<L.nBands, ENGINE_THREADS, smem, a->ctx->stream>>>(L, val, op);
+    int grid = L.nBands + ((op.waitHalo && L.nPackChunks > 0) ? L.nPackChunks : 0);
+    engine_kernel<Op><<<grid, ENGINE_THREADS, smem, a->ctx->stream>>>(L, val, op);
     a->ctx->launches++;
     KERNEL_CHECK();
     return B200LDU_OK;

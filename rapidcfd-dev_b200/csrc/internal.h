@@ -56,6 +56,37 @@ struct b200ldu_ctx {
     // pinned staging for *_host entry points and scalar read-back
     void *pinned = nullptr;
     size_t pinnedBytes = 0;
+    // peer-memory (CUDA IPC over NVLink) collectives, see comm.cu
+    bool p2p = false;
+    char *region = nullptr;          // this rank's shared region
+    char *peerRegion[8] = {nullptr}; // every rank's region mapped here (own included)
+    unsigned long long *d_seq = nullptr; // local device counters: [0] reduction seq, [1] halo seq, [2..] scratch
+};
+
+// layout of the IPC-shared region of every rank
+constexpr int P2P_MAXR = 8;
+constexpr size_t P2P_MAIL_OFF = 0;        // double mail[2][P2P_MAXR][8]
+constexpr size_t P2P_MAILFLAG_OFF = 2048; // u64 mailFlag[2][P2P_MAXR]
+constexpr size_t P2P_HALOFLAG_OFF = 4096; // u64 haloFlag[P2P_MAXR]   (indexed by source rank)
+constexpr size_t P2P_RECV_OFF = 8192;     // double recv[2][P2P_RECV_CAP]
+constexpr size_t P2P_RECV_CAP = 1u << 20; // doubles per parity
+constexpr size_t P2P_REGION_BYTES = P2P_RECV_OFF + 2 * P2P_RECV_CAP * sizeof(double);
+
+struct P2PRed { // passed by value to scalar_kernel
+    int rank = 0, nRanks = 1;
+    double *mail[P2P_MAXR] = {nullptr};
+    unsigned long long *flag[P2P_MAXR] = {nullptr};
+    unsigned long long *seq = nullptr;
+};
+
+// peer-memory halo send descriptors (comm.cu builds them, engine.cuh executes them)
+struct PackPatch {
+    double *dst[2];            // neighbour's receive buffer (parity 0/1) + this patch's offset there
+    unsigned long long *flag;  // neighbour's arrival flag for this rank
+    int start, n, nChunks;
+};
+struct PackChunk {
+    int patch, begin, end;
 };
 
 // device view of the banded addressing, passed by value to kernels
@@ -75,6 +106,17 @@ struct LayoutDev {
     const int *haloIdx;          // banded extended index: < nPad local row, else nPad + recv slot
     const int *perm;             // [nCells] caller cell -> banded row
     const int *iperm;            // [nPad]  banded row -> caller cell, -1 padding
+    // peer-memory halo (null/0 when the exchange goes through NCCL into the vector's own tail)
+    const unsigned long long *haloFlags; // this rank's arrival flags, indexed by source rank
+    const unsigned long long *haloSeq;   // device counter of completed exchanges
+    const double *tail0, *tail1;         // receive buffers by exchange parity
+    int nNbr;
+    int nbr[8];
+    const PackChunk *packChunks;   // fused halo send: first nPackChunks CTAs of a consuming kernel
+    const PackPatch *packPatches;
+    const int *sendRows;           // banded row of every coupled-patch face cell
+    unsigned long long *seqs;      // device counters: [1] halo sequence, [6] CTAs done, [8+p] chunks done
+    int nPackChunks;
 };
 
 struct b200ldu_addr {
@@ -95,6 +137,10 @@ struct b200ldu_addr {
     int *d_code = nullptr; // [nEntries] value source: 2f+side | -1 pad | -2-pf interface
     int *d_haloStart = nullptr, *d_haloIdx = nullptr, *d_perm = nullptr, *d_iperm = nullptr;
     int *d_sendRows = nullptr; // [nRecv] banded row of faceCells (pack kernel)
+    bool p2pHalo = false;      // peer-store halo usable for this addressing
+    void *d_packPatches = nullptr, *d_packChunks = nullptr; // PackPatch[], PackChunk[] (comm.cu)
+    int nPackChunks = 0;
+    double nCellsGlobal = 0;
     // caller-order CSR views for the FV face-sum kernels and faceH
     int *d_l = nullptr, *d_u = nullptr, *d_ownerStart = nullptr, *d_losort = nullptr,
         *d_losortStart = nullptr;

@@ -108,7 +108,9 @@ int pick_band_rows(int nCells)
         int v = atoi(e);
         if (v >= SLICE_ROWS && v % SLICE_ROWS == 0 && v <= 16384) return v;
     }
-    long long target = nCells / 512;
+    // at least ~4 waves of CTAs on a 148-SM part (6 CTAs/SM) so that small per-rank meshes
+    // (strong scaling) are not quantised into one or two waves; large meshes get 2048 rows
+    long long target = nCells / 3552;
     int b = SLICE_ROWS;
     while (b * 2 <= target && b < 2048) b *= 2;
     return b;

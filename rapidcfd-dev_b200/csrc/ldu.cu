@@ -154,6 +154,11 @@ extern "C" int b200ldu_addr_create(b200ldu_ctx *ctx, int nCells, int nFaces, con
         b200ldu_addr_destroy(a);
         return rc;
     }
+    rc = comm_addr_setup(a);
+    if (rc != B200LDU_OK) {
+        b200ldu_addr_destroy(a);
+        return rc;
+    }
     *out = a;
     return B200LDU_OK;
 }
@@ -166,7 +171,7 @@ extern "C" int b200ldu_addr_destroy(b200ldu_addr *a)
     void *ptrs[] = {a->d_sliceStart, a->d_sliceW, a->d_sliceWL, a->d_col, a->d_code, a->d_haloStart,
                     a->d_haloIdx, a->d_perm, a->d_iperm, a->d_sendRows, a->d_l, a->d_u,
                     a->d_ownerStart, a->d_losort, a->d_losortStart, a->d_bFaceCells,
-                    a->d_bCellStart, a->d_bCellFaces, a->d_bCells};
+                    a->d_bCellStart, a->d_bCellFaces, a->d_bCells, a->d_packPatches, a->d_packChunks};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (double *p : a->pool)
@@ -384,20 +389,22 @@ extern "C" int b200ldu_matrix_set(b200ldu_matrix *m, const double *diag_d, const
 // ---------------------------------------------------------------------------
 // banded-order operations used by the solvers
 // ---------------------------------------------------------------------------
-int mat_halo(b200ldu_matrix *m, double *x, const int *stop)
+int mat_halo(b200ldu_matrix *m, double *x, const int *stop, int *usedP2P)
 {
-    return comm_halo_exchange(m->a, x, m->d_sendBuf, stop);
+    return comm_halo_exchange(m->a, x, m->d_sendBuf, stop, usedP2P);
 }
 
 int mat_amul(b200ldu_matrix *m, bool transpose, double *x, double *out, int mode, const double *aux,
              double *partials, const int *stop)
 {
-    TRY(mat_halo(m, x, stop));
+    int wait = 0;
+    TRY(mat_halo(m, x, stop, &wait));
     const double *val = transpose ? m->d_valT : m->d_val;
 #define LAUNCH_AMUL(MODE)                  \
     {                                      \
         AmulOp<MODE> op;                   \
         op.stop = stop;                    \
+        op.waitHalo = wait;                \
         op.partials = partials;            \
         op.x = x;                          \
         op.diag = m->d_diag;               \
@@ -467,9 +474,11 @@ int mat_ainv(b200ldu_matrix *m, bool transpose, const double *r, double *w, bool
 
 int mat_jacobi(b200ldu_matrix *m, double omega, double *x, const double *b, double *out, const int *stop)
 {
-    TRY(mat_halo(m, x, stop));
+    int wait = 0;
+    TRY(mat_halo(m, x, stop, &wait));
     JacobiOp op;
     op.stop = stop;
+    op.waitHalo = wait;
     op.x = x;
     op.diag = m->d_diag;
     op.b = b;
@@ -482,10 +491,12 @@ int mat_jacobi(b200ldu_matrix *m, double omega, double *x, const double *b, doub
 int mat_residual(b200ldu_matrix *m, double *x, const double *b, double *out, bool fuseSumMag,
                  double *partials, const int *stop)
 {
-    TRY(mat_halo(m, x, stop));
+    int wait = 0;
+    TRY(mat_halo(m, x, stop, &wait));
     if (fuseSumMag) {
         ResidualOp<1> op;
         op.stop = stop;
+        op.waitHalo = wait;
         op.partials = partials;
         op.x = x;
         op.diag = m->d_diag;
@@ -495,6 +506,7 @@ int mat_residual(b200ldu_matrix *m, double *x, const double *b, double *out, boo
     }
     ResidualOp<0> op;
     op.stop = stop;
+    op.waitHalo = wait;
     op.x = x;
     op.diag = m->d_diag;
     op.b = b;
@@ -530,9 +542,11 @@ int mat_H(b200ldu_matrix *m, const double *x, double *out)
 
 int mat_interpolate(b200ldu_matrix *m, double *x, double *out, const int *stop)
 {
-    TRY(mat_halo(m, x, stop));
+    int wait = 0;
+    TRY(mat_halo(m, x, stop, &wait));
     OffDiagOp<false, true> op;
     op.stop = stop;
+    op.waitHalo = wait;
     op.x = x;
     op.diag = m->d_diag;
     op.out = out;

@@ -5,7 +5,7 @@
 int ctx_pinned(b200ldu_ctx *c, size_t bytes, void **out);
 int to_banded(b200ldu_addr *a, const double *x, double *xb);
 int from_banded(b200ldu_addr *a, const double *xb, double *x);
-int mat_halo(b200ldu_matrix *m, double *x, const int *stop);
+int mat_halo(b200ldu_matrix *m, double *x, const int *stop, int *usedP2P);
 // mode: see AmulOp in ops.cuh
 int mat_amul(b200ldu_matrix *m, bool transpose, double *x, double *out, int mode, const double *aux,
              double *partials, const int *stop);

@@ -19,6 +19,7 @@ struct SolverScalars {
 struct OpBase {
     const int *stop = nullptr;
     double *partials = nullptr;
+    int waitHalo = 0; // 1: a peer-memory halo exchange of the staged vector is in flight
 };
 
 // ---- Amul / Tmul: out = diag*x + sum v*x[c]  (lduMatrixATmul.C:78-137) ----
@@ -33,6 +34,7 @@ struct AmulOp : OpBase {
     const double *x, *diag, *aux;
     double *out;
     __device__ __forceinline__ void stage(int g, double &a, double &) const { a = x[g]; }
+    __device__ __forceinline__ const double *pack_src() const { return x; }
     __device__ __forceinline__ void stage_own(int r, double2 &a, double2 &) const
     {
         a = *reinterpret_cast<const double2 *>(x + r);
@@ -74,6 +76,7 @@ struct AinvOp : OpBase {
     const double *r, *rD, *dotv;
     double *out;
     __device__ __forceinline__ void stage(int g, double &a, double &) const { a = r[g]; }
+    __device__ __forceinline__ const double *pack_src() const { return r; }
     __device__ __forceinline__ void stage_own(int row, double2 &a, double2 &) const
     {
         a = *reinterpret_cast<const double2 *>(r + row);
@@ -138,6 +141,7 @@ struct JacobiOp : OpBase {
     double omega;
     int nCells;
     __device__ __forceinline__ void stage(int g, double &a, double &) const { a = x[g]; }
+    __device__ __forceinline__ const double *pack_src() const { return x; }
     __device__ __forceinline__ void stage_own(int r, double2 &a, double2 &) const
     {
         a = *reinterpret_cast<const double2 *>(x + r);
@@ -169,6 +173,7 @@ struct ResidualOp : OpBase {
     const double *x, *diag, *b;
     double *out;
     __device__ __forceinline__ void stage(int g, double &a, double &) const { a = x[g]; }
+    __device__ __forceinline__ const double *pack_src() const { return x; }
     __device__ __forceinline__ void stage_own(int r, double2 &a, double2 &) const
     {
         a = *reinterpret_cast<const double2 *>(x + r);
@@ -197,6 +202,7 @@ struct CoeffSumOp : OpBase {
     const double *diag; // nullptr => start from 0
     double *out;
     __device__ __forceinline__ void stage(int, double &, double &) const {}
+    __device__ __forceinline__ const double *pack_src() const { return nullptr; }
     __device__ __forceinline__ void stage_own(int, double2 &, double2 &) const {}
     __device__ __forceinline__ double init(int r, double, double) const
     {
@@ -222,6 +228,7 @@ struct OffDiagOp : OpBase {
     const double *x, *diag;
     double *out;
     __device__ __forceinline__ void stage(int g, double &a, double &) const { a = x[g]; }
+    __device__ __forceinline__ const double *pack_src() const { return x; }
     __device__ __forceinline__ void stage_own(int r, double2 &a, double2 &) const
     {
         a = *reinterpret_cast<const double2 *>(x + r);
@@ -278,11 +285,15 @@ int ew_launch(b200ldu_ctx *ctx, int n2, const int *stop, double *partials, int *
 }
 
 // sums NRED interleaved partial streams in fixed order, then thread 0 runs the scalar
-// logic g(sc).  One CTA.  With more than one rank the sums go through an all-reduce
-// between the two halves (see scalar_step in solvers.cu).
+// logic g(sc).  One CTA.  With more than one rank the per-rank sums are combined either
+//  * over peer memory (p2p.nRanks > 1): thread 0 stores its sums + a sequence flag into
+//    every rank's mailbox (NVLink peer stores), waits until every rank's flag for this
+//    sequence number has arrived in its own mailbox and adds the contributions in rank
+//    order -- one kernel, no NCCL call, bit-identical result on every rank; or
+//  * through ncclAllReduce between a sum-only and a logic-only launch (scalar_step_on).
 template <int NRED, bool RUN_LOGIC, class G>
 __global__ void __launch_bounds__(256) scalar_kernel(const double *partials, int nPartials,
-                                                     SolverScalars *sc, G g)
+                                                     SolverScalars *sc, G g, P2PRed p2p)
 {
     if (sc->stop) return;
     if (NRED > 0) {
@@ -296,8 +307,36 @@ __global__ void __launch_bounds__(256) scalar_kernel(const double *partials, int
         __shared__ double tot[NRED > 0 ? NRED : 1];
         block_reduce_store<(NRED > 0 ? NRED : 1), 256>(red, tot, 0);
         __syncthreads();
-        if (threadIdx.x == 0)
-            for (int k = 0; k < NRED; k++) sc->sum[k] = tot[k];
+        if (threadIdx.x == 0) {
+            if (p2p.nRanks > 1) {
+                const unsigned long long seq = *p2p.seq + 1;
+                const int par = (int)(seq & 1);
+                for (int r = 0; r < p2p.nRanks; r++) {
+                    double *dst = p2p.mail[r] + ((size_t)(par * P2P_MAXR + p2p.rank) * 8);
+                    for (int k = 0; k < NRED; k++) dst[k] = tot[k];
+                }
+                __threadfence_system();
+                for (int r = 0; r < p2p.nRanks; r++) {
+                    unsigned long long *f = p2p.flag[r] + (par * P2P_MAXR + p2p.rank);
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(seq) : "memory");
+                }
+                double acc[NRED > 0 ? NRED : 1];
+                for (int k = 0; k < NRED; k++) acc[k] = 0;
+                for (int r = 0; r < p2p.nRanks; r++) { // rank order => same bits everywhere
+                    const unsigned long long *f = p2p.flag[p2p.rank] + (par * P2P_MAXR + r);
+                    unsigned long long v;
+                    do {
+                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+                    } while (v < seq);
+                    const double *src = p2p.mail[p2p.rank] + ((size_t)(par * P2P_MAXR + r) * 8);
+                    for (int k = 0; k < NRED; k++) acc[k] += __ldcg(src + k);
+                }
+                for (int k = 0; k < NRED; k++) sc->sum[k] = acc[k];
+                *p2p.seq = seq;
+            } else {
+                for (int k = 0; k < NRED; k++) sc->sum[k] = tot[k];
+            }
+        }
     }
     if (RUN_LOGIC && threadIdx.x == 0) g(sc);
 }

@@ -9,18 +9,21 @@ static constexpr double SMALL_ = 1e-20;
 static constexpr double VSMALL_ = 1e-300;
 
 // ---- scalar step: sum partials (fixed order) [+ all-reduce] + scalar logic -------
+P2PRed comm_p2p_red(b200ldu_ctx *ctx); // comm.cu
+
 template <int NRED, class G>
 int scalar_step_on(Solve &S, double *partials, int nPartials, G g)
 {
     b200ldu_ctx *ctx = S.ctx;
-    if (ctx->nRanks == 1 || NRED == 0) {
-        scalar_kernel<NRED, true, G><<<1, 256, 0, ctx->stream>>>(partials, nPartials, S.sc, g);
+    if (ctx->nRanks == 1 || NRED == 0 || ctx->p2p) {
+        P2PRed p = (ctx->nRanks > 1 && NRED > 0) ? comm_p2p_red(ctx) : P2PRed();
+        scalar_kernel<NRED, true, G><<<1, 256, 0, ctx->stream>>>(partials, nPartials, S.sc, g, p);
         ctx->launches++;
     } else {
-        scalar_kernel<NRED, false, G><<<1, 256, 0, ctx->stream>>>(partials, nPartials, S.sc, g);
+        scalar_kernel<NRED, false, G><<<1, 256, 0, ctx->stream>>>(partials, nPartials, S.sc, g, P2PRed());
         ctx->launches++;
         TRY(comm_allreduce_sum(ctx, S.sc->sum, NRED)); // device pointer arithmetic only
-        scalar_kernel<0, true, G><<<1, 256, 0, ctx->stream>>>(partials, 0, S.sc, g);
+        scalar_kernel<0, true, G><<<1, 256, 0, ctx->stream>>>(partials, 0, S.sc, g, P2PRed());
         ctx->launches++;
     }
     KERNEL_CHECK();

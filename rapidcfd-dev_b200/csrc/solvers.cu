@@ -466,16 +466,8 @@ int solve_banded(b200ldu_matrix *m, const char *solver, const char *pre, const b
     h.minIter = S.c.minIter;
     h.histCap = S.hist ? histCap : 0;
     h.nSweeps = S.c.nSweeps;
-    h.nCellsGlobal = (double)a->nCells;
+    h.nCellsGlobal = a->nCellsGlobal > 0 ? a->nCellsGlobal : (double)a->nCells; // all-reduced at addr_create
     CUDA_TRY(cudaMemcpyAsync(S.sc, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
-    if (ctx->nRanks > 1) { // global cell count for gAverage
-        // sum[] is scratch here
-        double nc = (double)a->nCells;
-        CUDA_TRY(cudaMemcpyAsync(&S.sc->sum[7], &nc, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        TRY(comm_allreduce_sum(ctx, &S.sc->sum[7], 1));
-        CUDA_TRY(cudaMemcpyAsync(&S.sc->nCellsGlobal, &S.sc->sum[7], sizeof(double), cudaMemcpyDeviceToDevice,
-                                 ctx->stream));
-    }
 
     int rc = B200LDU_OK;
     bool diagonalOnly = (a->nFaces == 0 && a->L.nRecv == 0);
