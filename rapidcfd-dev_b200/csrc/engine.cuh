@@ -99,10 +99,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS) engine_kernel(const LayoutDev 
         if ((int)blockIdx.x < L.nPackChunks) {
             const PackChunk c = L.packChunks[blockIdx.x];
             const PackPatch P = L.packPatches[c.patch];
-            const double *src = op.pack_src();
             double *dst = P.dst[haloSeqNow & 1];
             for (int i = c.begin + threadIdx.x; i < c.end; i += ENGINE_THREADS)
-                dst[i - P.start] = src[__ldg(L.sendRows + i)];
+                dst[i - P.start] = op.pack_val(__ldg(L.sendRows + i));
             __threadfence_system();
             __syncthreads();
             if (threadIdx.x == 0) {

@@ -11,6 +11,8 @@
 // LduMatrix/LduMatrix/SolverPerformance.C:32-92.
 #include "ldu.h"
 
+#include <cstdlib>
+
 #include "solver_steps.cuh"
 
 // initial residual, normFactor and the first convergence test, common to all solvers
@@ -164,6 +166,82 @@ int solve_pcg(Solve &S, int pk)
     };
     return run_iterations(S, (long long)S.c.maxIter + 1 > S.c.minIter ? (long long)S.c.maxIter + 1 : S.c.minIter,
                           body);
+}
+
+// ---------------------------------------------------------------------------
+// PCG, fused form: two matrix sweeps + two scalar steps per iteration (4 launches, 2 global
+// sums) instead of 7 launches / 3 sums.  Same recurrences and the same per-row arithmetic as
+// solve_pcg; the psi/r update of body k is applied while body k+1 stages r, and the
+// convergence decision of body k is taken in the first scalar step of body k+1 (the extra
+// preconditioner sweep that has then already run only overwrote scratch).
+// ---------------------------------------------------------------------------
+int solve_pcg_fused(Solve &S, int pk)
+{
+    b200ldu_matrix *m = S.m;
+    b200ldu_addr *a = m->a;
+    SolverScalars *sc = S.sc;
+    double *hist = S.hist;
+    const int *stop = &sc->stop;
+    const int n2 = a->L.nPad / 2;
+    double *psi = S.psi, *b = S.src;
+    double *pb[2] = {S.vec(0), S.vec(4)}, *w = S.vec(1), *rb[2] = {S.vec(2), S.vec(3)}, *z = S.vec(5);
+    if (!pb[0] || !pb[1] || !w || !rb[0] || !rb[1] || !z) return B200LDU_ECUDA;
+    const double *rD = m->d_rD;
+
+    TRY(mat_amul(m, false, psi, w, 0, nullptr, nullptr, nullptr));
+    TRY(init_residual(S, psi, b, w, rb[0], pb[0]));
+
+    auto body = [&](long long k) -> int {
+        const double *rOld = rb[k & 1], *pPrev = pb[k & 1];
+        double *rNew = rb[(k + 1) & 1], *pNew = pb[(k + 1) & 1];
+        int np = a->L.nBands;
+        if (pk == 2) {
+            TRY(mat_pcg_ka(m, rOld, rNew, w, pPrev, psi, z, sc, S.partials, stop));
+        } else {
+            TRY(ew_launch<2>(S.ctx, n2, stop, S.partials, &np, [=] __device__(int i, double *red) {
+                double2 r = CV2(rOld)[i];
+                if (sc->bodies > 0) {
+                    const double alpha = sc->alpha;
+                    double2 ww = CV2(w)[i], pp = CV2(pPrev)[i], x = CV2(psi)[i];
+                    r.x = fma(-alpha, ww.x, r.x);
+                    r.y = fma(-alpha, ww.y, r.y);
+                    V2(psi)[i] = make_double2(fma(alpha, pp.x, x.x), fma(alpha, pp.y, x.y));
+                }
+                V2(rNew)[i] = r;
+                double2 zz = r;
+                if (pk == 1) {
+                    double2 d = CV2(rD)[i];
+                    zz = make_double2(__dmul_rn(d.x, r.x), __dmul_rn(d.y, r.y));
+                }
+                V2(z)[i] = zz;
+                red[0] += zz.x * r.x + zz.y * r.y;
+                red[1] += fabs(r.x) + fabs(r.y);
+            }));
+        }
+        TRY(scalar_step<2>(S, np, [=] __device__(SolverScalars *s) {
+            if (s->bodies > 0) {
+                end_of_body(s, hist, s->sum[1]);
+                if (s->stop) return;
+            }
+            s->wArAold = s->wArA;
+            s->wArA = s->sum[0];
+            s->beta = s->wArA / s->wArAold;
+        }));
+        TRY(mat_pcg_kb(m, z, pPrev, pNew, w, sc, S.partials, stop));
+        TRY(scalar_step<1>(S, a->L.nBands, [=] __device__(SolverScalars *s) {
+            s->wApA = s->sum[0];
+            if (fabs(s->wApA) / s->normFactor < VSMALL_) { // checkSingularity PCG.C:170
+                s->singular = 1;
+                s->stop = 1;
+                return;
+            }
+            s->alpha = s->wArA / s->wApA;
+            s->bodies++;
+        }));
+        return B200LDU_OK;
+    };
+    long long mb = (long long)S.c.maxIter + 1 > S.c.minIter ? (long long)S.c.maxIter + 1 : S.c.minIter;
+    return run_iterations(S, mb + 1, body); // +1: the last body's update is applied by the next sweep
 }
 
 // ---------------------------------------------------------------------------
@@ -497,8 +575,13 @@ int solve_banded(b200ldu_matrix *m, const char *solver, const char *pre, const b
                     if (!m->symmetric) {
                         b200_set_error("PCG is registered for symmetric matrices only (PCG.C:36-37)");
                         rc = B200LDU_EMATRIX;
-                    } else
-                        rc = solve_pcg(S, pk);
+                    } else {
+                        // the fused form needs the peer-memory halo (or no halo); B200LDU_PCG_FUSED=0 keeps
+                        // the reference's 7-kernel op list
+                        const char *ev = getenv("B200LDU_PCG_FUSED");
+                        bool fused = !(ev && atoi(ev) == 0) && (a->L.nRecv == 0 || a->p2pHalo);
+                        rc = fused ? solve_pcg_fused(S, pk) : solve_pcg(S, pk);
+                    }
                 } else if (!strcmp(sv, "PBiCG")) {
                     if (m->symmetric) {
                         b200_set_error("PBiCG is registered for asymmetric matrices only (PBiCG.C:36-37)");
