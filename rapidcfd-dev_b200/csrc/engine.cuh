@@ -37,6 +37,12 @@ __device__ __forceinline__ uint32_t ldg_stream_u32(const void *p)
     return r;
 }
 
+__device__ __forceinline__ void cp_async16(void *smemDst, const void *gsrc)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -81,8 +87,8 @@ __device__ __forceinline__ void block_reduce_store(double (&red)[NRED], double *
 //   void   finish(int r, double acc0, double acc1, a0,b0,a1,b1, double *red)
 //                                                    writes rows r, r+1; adds reductions
 // ---------------------------------------------------------------------------
-template <class Op>
-__global__ void __launch_bounds__(ENGINE_THREADS) engine_kernel(const LayoutDev L,
+template <class Op, bool SHARED>
+__global__ void __launch_bounds__(ENGINE_THREADS, SHARED ? 3 : 1) engine_kernel(const LayoutDev L,
                                                                 const double *__restrict__ val,
                                                                 Op op)
 {
@@ -173,6 +179,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) engine_kernel(const LayoutDev 
 #pragma unroll
     for (int k = 0; k < (Op::NRED > 0 ? Op::NRED : 1); k++) red[k] = 0;
 
+    if constexpr (!SHARED) {
     for (int sl = warp; sl < L.slicesPerBand; sl += NW) {
         const int s = band * L.slicesPerBand + sl;
         const long long base = L.sliceStart[s];
@@ -210,6 +217,72 @@ __global__ void __launch_bounds__(ENGINE_THREADS) engine_kernel(const LayoutDev 
         }
         op.finish(rowBase + lr, acc0, acc1, a0, b0, a1, b1, red);
     }
+    } else {
+    // ---- shared-coefficient layout (symmetric matrices, layout_shared.cu) ----
+    // Each warp streams its slices through a private double buffer in shared memory with
+    // cp.async (LDGSTS, 16-byte, L2-only): the value stream (owner + interface coefficients,
+    // then the "extras": coefficients of faces owned outside the slice), the 16-bit columns
+    // of the value slots and the (column, ref) pairs of the neighbour slots.  The copies of
+    // slice i+1 are in flight while slice i is reduced, and no register is spent on staging.
+    // Owner/interface slots read their own position back; neighbour slots pick the
+    // coefficient of the same face through the 16-bit ref.
+    {
+    char *wb0 = reinterpret_cast<char *>(smem + stride) + (size_t)warp * 2 * L.sh_bufBytes;
+    auto issue = [&](int sl, char *buf) {
+        const int s = band * L.slicesPerBand + sl;
+        const long long vb = L.sh_vStart[s];
+        const int nV2 = (int)((L.sh_vStart[s + 1] - vb) >> 1);
+        const int nC = L.sh_VS[s] * 8, nN = L.sh_WN[s] * 16; // 16-byte chunks
+        const char *gv = reinterpret_cast<const char *>(val + vb);
+        const char *gc = reinterpret_cast<const char *>(L.sh_colV + vb);
+        const char *gn = reinterpret_cast<const char *>(L.sh_nbr + L.sh_nStart[s]);
+        for (int i = lane; i < nV2; i += 32) cp_async16(buf + 16 * i, gv + 16 * (size_t)i);
+        for (int i = lane; i < nC; i += 32) cp_async16(buf + L.sh_colOff + 16 * i, gc + 16 * (size_t)i);
+        for (int i = lane; i < nN; i += 32) cp_async16(buf + L.sh_nbrOff + 16 * i, gn + 16 * (size_t)i);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int cur = 0;
+    if (warp < L.slicesPerBand) issue(warp, wb0);
+    for (int sl = warp; sl < L.slicesPerBand; sl += NW) {
+        char *buf = wb0 + (size_t)cur * L.sh_bufBytes;
+        if (sl + NW < L.slicesPerBand) {
+            issue(sl + NW, wb0 + (size_t)(cur ^ 1) * L.sh_bufBytes);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+        const int s = band * L.slicesPerBand + sl;
+        const int VS = L.sh_VS[s], WO = L.sh_WO[s], WN = L.sh_WN[s];
+        const double *wbuf = reinterpret_cast<const double *>(buf);
+        const uint32_t *cbuf = reinterpret_cast<const uint32_t *>(buf + L.sh_colOff);
+        const uint2 *nbuf = reinterpret_cast<const uint2 *>(buf + L.sh_nbrOff);
+        const int lr = sl * SLICE_ROWS + 2 * lane;
+        const double a0 = (Op::NVEC > 0) ? xs[lr] : 0, a1 = (Op::NVEC > 0) ? xs[lr + 1] : 0;
+        double acc0 = op.init(rowBase + lr, a0, 0);
+        double acc1 = op.init(rowBase + lr + 1, a1, 0);
+#define VALUE_SLOT(J)                                                                      \
+    {                                                                                      \
+        const uint32_t c_ = cbuf[(J) * 32 + lane];                                         \
+        const double2 v_ = reinterpret_cast<const double2 *>(wbuf)[(J) * 32 + lane];       \
+        acc0 = op.term(acc0, v_.x, (Op::NVEC > 0) ? xs[c_ & 0xffffu] : 0, 0);              \
+        acc1 = op.term(acc1, v_.y, (Op::NVEC > 0) ? xs[c_ >> 16] : 0, 0);                  \
+    }
+        for (int j = 0; j < WO; j++) VALUE_SLOT(j) // owner faces, ascending face index
+        for (int j = 0; j < WN; j++) {             // neighbour faces, losort order
+            const uint2 e = nbuf[j * 32 + lane];
+            acc0 = op.term(acc0, wbuf[e.x >> 16], (Op::NVEC > 0) ? xs[e.x & 0xffffu] : 0, 0);
+            acc1 = op.term(acc1, wbuf[e.y >> 16], (Op::NVEC > 0) ? xs[e.y & 0xffffu] : 0, 0);
+        }
+        if (!Op::LOCAL)
+            for (int j = WO; j < VS; j++) VALUE_SLOT(j) // coupled-patch faces, patch order
+#undef VALUE_SLOT
+        op.finish(rowBase + lr, acc0, acc1, a0, 0, a1, 0, red);
+        __syncwarp(); // the buffer is overwritten by the copies issued in the next iteration
+        cur ^= 1;
+    }
+    }
+    }
     if (Op::NRED > 0) block_reduce_store<(Op::NRED > 0 ? Op::NRED : 1), ENGINE_THREADS>(red, op.partials, band);
     if (fusedPack && threadIdx.x == 0) {
         if (atomicAdd(&L.seqs[6], 1ull) + 1 == (unsigned long long)gridDim.x) {
@@ -220,22 +293,39 @@ __global__ void __launch_bounds__(ENGINE_THREADS) engine_kernel(const LayoutDev 
     }
 }
 
-template <class Op>
-int engine_launch(b200ldu_addr *a, const double *val, const Op &op)
+template <class Op, bool SHARED>
+int engine_launch_impl(b200ldu_addr *a, const double *val, const Op &op)
 {
     const LayoutDev &L = a->L;
-    size_t smem = sizeof(double) * (size_t)((L.bandRows + L.maxHalo + 1) & ~1) * Op::NVEC;
-    static size_t configured = 0; // per Op instantiation
+    size_t smem = sizeof(double) * (size_t)((L.bandRows + L.maxHalo + 1) & ~1) * (Op::NVEC > 0 ? Op::NVEC : (SHARED ? 1 : 0));
+    if (SHARED) smem += (size_t)(ENGINE_THREADS / 32) * 2 * L.sh_bufBytes;
+    static size_t configured = 0; // per instantiation
     // the kernel also owns a little static shared memory (reduction scratch): opt in to
     // large dynamic shared memory well before the 48 KB default limit
     if (smem > 40 * 1024 && smem > configured) {
-        CUDA_TRY(cudaFuncSetAttribute(engine_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(engine_kernel<Op, SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
         configured = smem;
     }
     int grid = L.nBands + ((op.waitHalo && L.nPackChunks > 0) ? L.nPackChunks : 0);
-    engine_kernel<Op><<<grid, ENGINE_THREADS, smem, a->ctx->stream>>>(L, val, op);
+    engine_kernel<Op, SHARED><<<grid, ENGINE_THREADS, smem, a->ctx->stream>>>(L, val, op);
     a->ctx->launches++;
     KERNEL_CHECK();
     return B200LDU_OK;
+}
+
+// general per-entry layout
+template <class Op>
+int engine_launch(b200ldu_addr *a, const double *val, const Op &op)
+{
+    return engine_launch_impl<Op, false>(a, val, op);
+}
+
+// matrix sweep: shared-coefficient layout when the matrix uses it (symmetric, not transposed
+// with distinct interface coefficients), else the general layout
+template <class Op>
+int engine_launch_m(b200ldu_matrix *m, bool transpose, const Op &op)
+{
+    if (m->shared && !(transpose && m->haveT)) return engine_launch_impl<Op, true>(m->a, m->d_valSh, op);
+    return engine_launch_impl<Op, false>(m->a, transpose ? m->d_valT : m->d_val, op);
 }

@@ -117,6 +117,16 @@ struct LayoutDev {
     const int *sendRows;           // banded row of every coupled-patch face cell
     unsigned long long *seqs;      // device counters: [1] halo sequence, [6] CTAs done, [8+p] chunks done
     int nPackChunks;
+    // shared-coefficient layout for symmetric matrices (layout_shared.cu); null when unused
+    const long long *sh_vStart;  // [nSlices+1] offsets into the value stream (doubles)
+    const long long *sh_nStart;  // [nSlices+1] offsets into the neighbour stream (entries)
+    const uint16_t *sh_VS;       // value slots per row (owner + interface)
+    const uint16_t *sh_WO;       // owner slots per row
+    const uint16_t *sh_WN;       // neighbour slots per row
+    const uint16_t *sh_colV;     // column of every value-stream element (extras: unused)
+    const uint32_t *sh_nbr;      // neighbour entries: column | ref << 16
+    int sh_warpDoubles;          // doubles of the longest per-slice value stream
+    int sh_bufBytes, sh_colOff, sh_nbrOff; // per-warp stream buffer: values | columns | neighbour entries
 };
 
 struct b200ldu_addr {
@@ -153,6 +163,18 @@ struct b200ldu_addr {
     std::vector<long long> dbg_sliceStart;
     std::vector<uint16_t> dbg_sliceW, dbg_sliceWL, dbg_col;
     std::vector<int> dbg_code, dbg_haloStart, dbg_haloIdx;
+    // shared-coefficient layout (built lazily at the first symmetric matrix_set)
+    bool sharedBuilt = false, sharedOk = false;
+    long long sh_nV = 0, sh_nN = 0;
+    int sh_warpDoubles = 0;
+    long long *d_shVStart = nullptr, *d_shNStart = nullptr;
+    uint16_t *d_shVS = nullptr, *d_shWO = nullptr, *d_shWN = nullptr, *d_shColV = nullptr;
+    int *d_shCodeV = nullptr;
+    uint32_t *d_shNbr = nullptr;
+    std::vector<long long> dbg_shVStart, dbg_shNStart;
+    std::vector<uint16_t> dbg_shVS, dbg_shWO, dbg_shWN, dbg_shColV;
+    std::vector<int> dbg_shCodeV;
+    std::vector<uint32_t> dbg_shNbr;
     // workspace pool for caller-order entry points (banded vectors)
     std::vector<double *> pool;
     long long vecLen = 0; // nPad + nRecv (padded to even)
@@ -164,8 +186,9 @@ struct b200ldu_matrix {
     bool haveT = false;
     double *d_val = nullptr;  // banded coefficients for Amul   [nEntries]
     double *d_valT = nullptr; // banded coefficients for Tmul   (aliases d_val when symmetric)
-    double *d_valS = nullptr, *d_valST = nullptr; // val * rD[column] for the AINV sweep (lazy)
-    bool valSValid = false, valSTValid = false;
+    double *d_valSh = nullptr; // shared-coefficient value stream (symmetric matrices)
+    bool shared = false;       // Amul-type sweeps run on the shared-coefficient layout
+    bool valValid = false;     // general per-entry stream filled for the current coefficients
     double *d_diag = nullptr; // banded diagonal [nPad] (padding rows = 1)
     double *d_rD = nullptr;   // 1/diag, built lazily per matrix_set
     bool rDValid = false;
@@ -184,6 +207,7 @@ struct b200ldu_matrix {
 // cross-file helpers
 // ---------------------------------------------------------------------------
 int layout_build(b200ldu_addr *a, const double *centres);
+int layout_build_shared(b200ldu_addr *a);
 int addr_alloc_vec(b200ldu_addr *a, double **out); // banded vector of vecLen doubles, zeroed
 double *addr_pool_vec(b200ldu_addr *a, int slot);  // reusable scratch (grows on demand)
 

@@ -177,7 +177,10 @@ int layout_build(b200ldu_addr *a, const double *centres)
     int bits[3] = {0, 0, 0};
     {
         long long tiles = 1;
-        while ((double)nCells / (double)tiles > (double)bandRows && bits[0] + bits[1] + bits[2] < 45) {
+        // tiles of ~one slice (64 rows): slices become small cubes (most of a row's faces stay inside
+        // its slice: that is what the shared-coefficient layout exploits) and Morton order keeps
+        // every run of bandRows/64 consecutive tiles a compact brick
+        while ((double)nCells / (double)tiles > (double)SLICE_ROWS && bits[0] + bits[1] + bits[2] < 45) {
             int best = 2; // ties go to the last axis so x keeps the longest runs
             double bestExt = -1;
             for (int k = 2; k >= 0; k--) {
@@ -434,6 +437,7 @@ extern "C" int b200ldu_layout_debug_create(int nCells, int nFaces, const int *lo
         a->faceCells.assign(faceCells_h, faceCells_h + a->patchStart[nPatches]);
     }
     int rc = layout_build(a, cellCentres_h);
+    if (rc == B200LDU_OK) rc = layout_build_shared(a);
     if (rc != B200LDU_OK) {
         delete a;
         return rc;
@@ -464,6 +468,14 @@ extern "C" long long b200ldu_layout_debug_get(const b200ldu_addr *a, int what, v
     case 7: return give(a->dbg_haloStart.data(), 4, (long long)a->dbg_haloStart.size());
     case 8: return give(a->dbg_haloIdx.data(), 4, a->nHaloTotal);
     case 9: return give(dims, 4, 5);
+    case 10: return give(a->dbg_shVStart.data(), 8, (long long)a->dbg_shVStart.size());
+    case 11: return give(a->dbg_shNStart.data(), 8, (long long)a->dbg_shNStart.size());
+    case 12: return give(a->dbg_shVS.data(), 2, (long long)a->dbg_shVS.size());
+    case 13: return give(a->dbg_shWO.data(), 2, (long long)a->dbg_shWO.size());
+    case 14: return give(a->dbg_shWN.data(), 2, (long long)a->dbg_shWN.size());
+    case 15: return give(a->dbg_shColV.data(), 2, a->sh_nV);
+    case 16: return give(a->dbg_shCodeV.data(), 4, a->sh_nV);
+    case 17: return give(a->dbg_shNbr.data(), 4, a->sh_nN);
     }
     return -1;
 }

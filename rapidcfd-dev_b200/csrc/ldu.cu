@@ -2,6 +2,8 @@
 // operations of the C ABI (include/b200ldu.h).
 #include <stdarg.h>
 
+#include <cstdlib>
+
 #include "comm.h"
 #include "ldu.h"
 #include "ops.cuh"
@@ -171,7 +173,9 @@ extern "C" int b200ldu_addr_destroy(b200ldu_addr *a)
     void *ptrs[] = {a->d_sliceStart, a->d_sliceW, a->d_sliceWL, a->d_col, a->d_code, a->d_haloStart,
                     a->d_haloIdx, a->d_perm, a->d_iperm, a->d_sendRows, a->d_l, a->d_u,
                     a->d_ownerStart, a->d_losort, a->d_losortStart, a->d_bFaceCells,
-                    a->d_bCellStart, a->d_bCellFaces, a->d_bCells, a->d_packPatches, a->d_packChunks};
+                    a->d_bCellStart, a->d_bCellFaces, a->d_bCells, a->d_packPatches, a->d_packChunks,
+                    a->d_shVStart, a->d_shNStart, a->d_shVS, a->d_shWO, a->d_shWN, a->d_shColV, a->d_shCodeV,
+                    a->d_shNbr};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (double *p : a->pool)
@@ -273,11 +277,9 @@ extern "C" int b200ldu_matrix_create(b200ldu_addr *a, b200ldu_matrix **out)
     CUDA_TRY(cudaSetDevice(a->ctx->device));
     b200ldu_matrix *m = new b200ldu_matrix();
     m->a = a;
-    size_t ne = (size_t)(a->nEntries > 0 ? a->nEntries : 1);
-    CUDA_TRY(cudaMalloc((void **)&m->d_val, sizeof(double) * ne));
+    // coefficient streams are allocated by matrix_set (which layout is used depends on symmetry)
     CUDA_TRY(cudaMalloc((void **)&m->d_diag, sizeof(double) * (size_t)a->vecLen));
     CUDA_TRY(cudaMalloc((void **)&m->d_rD, sizeof(double) * (size_t)a->vecLen));
-    m->d_valT = m->d_val;
     int np = a->L.nBands > a->ctx->smCount * 8 ? a->L.nBands : a->ctx->smCount * 8;
     CUDA_TRY(cudaMalloc((void **)&m->d_partials, sizeof(double) * 4 * (size_t)np));
     CUDA_TRY(cudaMalloc((void **)&m->d_scal, sizeof(SolverScalars)));
@@ -294,7 +296,7 @@ extern "C" int b200ldu_matrix_destroy(b200ldu_matrix *m)
     cudaStreamSynchronize(m->a->ctx->stream);
     if (m->d_valT && m->d_valT != m->d_val) cudaFree(m->d_valT);
     void *ptrs[] = {m->d_val, m->d_diag, m->d_rD, m->d_partials, m->d_scal, m->d_hist, m->d_sendBuf,
-                    m->d_valS, m->d_valST};
+                    m->d_valSh};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (double *p : m->work)
@@ -361,25 +363,54 @@ extern "C" int b200ldu_matrix_set(b200ldu_matrix *m, const double *diag_d, const
     // Tmul needs its own coefficient stream when A != A^T (asymmetric coefficients or
     // interfaceIntCoeffs != interfaceBouCoeffs)
     bool needT = !m->symmetric || (a->L.nRecv && bou_d != int_d);
-    if (needT && m->d_valT == m->d_val) {
-        m->d_valT = nullptr;
-        CUDA_TRY(cudaMalloc((void **)&m->d_valT, sizeof(double) * (size_t)(ne > 0 ? ne : 1)));
-    }
-    if (ne > 0) {
-        unsigned g = (unsigned)((ne + 255) / 256);
-        fill_val_kernel<<<g, 256, 0, st>>>(ne, a->d_code, upper_d, lo, bou_d, m->d_val, 0);
-        a->ctx->launches++;
-        if (needT) {
-            fill_val_kernel<<<g, 256, 0, st>>>(ne, a->d_code, upper_d, lo, int_d, m->d_valT, 1);
-            a->ctx->launches++;
+    // Optional shared-coefficient layout for symmetric matrices (one value per face, 16 B/face
+    // instead of 20).  Measured on B200 (profiles/r01_ncu_shared_layout.txt) it moves 14 % fewer
+    // bytes but is bound by shared-memory wavefronts (fp64 gathers of coefficients AND psi), 265 us
+    // vs 223 us per 256^3 Amul, so the per-entry layout stays the default; B200LDU_SHARED=1 opts in.
+    bool useShared = false;
+    if (m->symmetric && a->nFaces > 0) {
+        const char *ev = getenv("B200LDU_SHARED");
+        if (ev && atoi(ev) == 1) {
+            TRY(layout_build_shared(a));
+            useShared = a->sharedOk;
         }
+    }
+    m->shared = useShared;
+    if (useShared) {
+        if (!m->d_valSh) CUDA_TRY(cudaMalloc((void **)&m->d_valSh, sizeof(double) * (size_t)(a->sh_nV > 0 ? a->sh_nV : 1)));
+        fill_val_kernel<<<(unsigned)((a->sh_nV + 255) / 256), 256, 0, st>>>(a->sh_nV, a->d_shCodeV, upper_d, lo, bou_d,
+                                                                            m->d_valSh, 0);
+        a->ctx->launches++;
+    }
+    const bool needGeneral = !useShared;
+    if (needGeneral || needT) {
+        size_t nb = sizeof(double) * (size_t)(ne > 0 ? ne : 1);
+        if (needGeneral && !m->d_val) CUDA_TRY(cudaMalloc((void **)&m->d_val, nb));
+        if (needT && (!m->d_valT || m->d_valT == m->d_val)) {
+            m->d_valT = nullptr;
+            CUDA_TRY(cudaMalloc((void **)&m->d_valT, nb));
+        }
+        if (ne > 0) {
+            unsigned g = (unsigned)((ne + 255) / 256);
+            if (needGeneral) {
+                fill_val_kernel<<<g, 256, 0, st>>>(ne, a->d_code, upper_d, lo, bou_d, m->d_val, 0);
+                a->ctx->launches++;
+            }
+            if (needT) {
+                fill_val_kernel<<<g, 256, 0, st>>>(ne, a->d_code, upper_d, lo, int_d, m->d_valT, 1);
+                a->ctx->launches++;
+            }
+        }
+    }
+    if (!needT) {
+        if (m->d_valT && m->d_valT != m->d_val) cudaFree(m->d_valT);
+        m->d_valT = m->d_val; // A^T == A
     }
     fill_diag_kernel<<<(unsigned)((a->vecLen + 255) / 256), 256, 0, st>>>(a->vecLen, a->L.nPad, a->d_iperm,
                                                                           diag_d, m->d_diag, m->d_rD);
     a->ctx->launches++;
     KERNEL_CHECK();
     m->haveT = needT;
-    m->valSValid = m->valSTValid = false; // AINV-scaled copies follow the coefficients
     m->upper_ext = upper_d;
     m->diag_ext = diag_d;
     m->lower_ext = lo;
@@ -399,7 +430,6 @@ int mat_amul(b200ldu_matrix *m, bool transpose, double *x, double *out, int mode
 {
     int wait = 0;
     TRY(mat_halo(m, x, stop, &wait));
-    const double *val = transpose ? m->d_valT : m->d_val;
 #define LAUNCH_AMUL(MODE)                  \
     {                                      \
         AmulOp<MODE> op;                   \
@@ -410,7 +440,7 @@ int mat_amul(b200ldu_matrix *m, bool transpose, double *x, double *out, int mode
         op.diag = m->d_diag;               \
         op.aux = aux;                      \
         op.out = out;                      \
-        return engine_launch(m->a, val, op); \
+        return engine_launch_m(m, transpose, op); \
     }
     switch (mode) {
     case 0: LAUNCH_AMUL(0)
@@ -423,35 +453,9 @@ int mat_amul(b200ldu_matrix *m, bool transpose, double *x, double *out, int mode
     return B200LDU_EINVAL;
 }
 
-static int ainv_prepare(b200ldu_matrix *m, bool transpose)
-{
-    b200ldu_addr *a = m->a;
-    bool useT = transpose && m->d_valT != m->d_val;
-    double **dst = useT ? &m->d_valST : &m->d_valS;
-    bool *valid = useT ? &m->valSTValid : &m->valSValid;
-    if (*valid) return B200LDU_OK;
-    size_t ne = (size_t)(a->nEntries > 0 ? a->nEntries : 1);
-    if (!*dst) CUDA_TRY(cudaMalloc((void **)dst, sizeof(double) * ne));
-    const LayoutDev &L = a->L;
-    size_t smem = sizeof(double) * (size_t)(L.bandRows + L.maxHalo);
-    static size_t configured = 0;
-    if (smem > 40 * 1024 && smem > configured) {
-        CUDA_TRY(cudaFuncSetAttribute(ainv_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    ainv_scale_kernel<<<L.nBands, ENGINE_THREADS, smem, a->ctx->stream>>>(L, useT ? m->d_valT : m->d_val, m->d_rD,
-                                                                           *dst);
-    a->ctx->launches++;
-    KERNEL_CHECK();
-    *valid = true;
-    return B200LDU_OK;
-}
-
 int mat_ainv(b200ldu_matrix *m, bool transpose, const double *r, double *w, bool fuseDot,
              const double *dotv, double *partials, const int *stop)
 {
-    TRY(ainv_prepare(m, transpose));
-    const double *val = (transpose && m->d_valT != m->d_val) ? m->d_valST : m->d_valS;
     if (fuseDot) {
         AinvOp<1> op;
         op.stop = stop;
@@ -460,7 +464,7 @@ int mat_ainv(b200ldu_matrix *m, bool transpose, const double *r, double *w, bool
         op.rD = m->d_rD;
         op.dotv = dotv;
         op.out = w;
-        return engine_launch(m->a, val, op);
+        return engine_launch_m(m, transpose, op);
     }
     AinvOp<0> op;
     op.stop = stop;
@@ -469,14 +473,13 @@ int mat_ainv(b200ldu_matrix *m, bool transpose, const double *r, double *w, bool
     op.rD = m->d_rD;
     op.dotv = nullptr;
     op.out = w;
-    return engine_launch(m->a, val, op);
+    return engine_launch_m(m, transpose, op);
 }
 
 // fused PCG sweeps (ops.cuh PcgAinvOp / PcgAmulOp)
 int mat_pcg_ka(b200ldu_matrix *m, const double *rOld, double *rNew, const double *w, const double *p,
                double *psi, double *z, const void *sc, double *partials, const int *stop)
 {
-    TRY(ainv_prepare(m, false));
     PcgAinvOp op;
     op.stop = stop;
     op.partials = partials;
@@ -488,7 +491,7 @@ int mat_pcg_ka(b200ldu_matrix *m, const double *rOld, double *rNew, const double
     op.z = z;
     op.rD = m->d_rD;
     op.sc = (const SolverScalars *)sc;
-    return engine_launch(m->a, m->d_valS, op);
+    return engine_launch_m(m, false, op);
 }
 
 int mat_pcg_kb(b200ldu_matrix *m, const double *z, const double *pOld, double *pNew, double *w, const void *sc,
@@ -506,7 +509,7 @@ int mat_pcg_kb(b200ldu_matrix *m, const double *z, const double *pOld, double *p
     op.out = w;
     op.diag = m->d_diag;
     op.sc = (const SolverScalars *)sc;
-    return engine_launch(m->a, m->d_val, op);
+    return engine_launch_m(m, false, op);
 }
 
 int mat_jacobi(b200ldu_matrix *m, double omega, double *x, const double *b, double *out, const int *stop)
@@ -522,7 +525,7 @@ int mat_jacobi(b200ldu_matrix *m, double omega, double *x, const double *b, doub
     op.out = out;
     op.omega = omega;
     op.nCells = m->a->nCells;
-    return engine_launch(m->a, m->d_val, op);
+    return engine_launch_m(m, false, op);
 }
 
 int mat_residual(b200ldu_matrix *m, double *x, const double *b, double *out, bool fuseSumMag,
@@ -539,7 +542,7 @@ int mat_residual(b200ldu_matrix *m, double *x, const double *b, double *out, boo
         op.diag = m->d_diag;
         op.b = b;
         op.out = out;
-        return engine_launch(m->a, m->d_val, op);
+        return engine_launch_m(m, false, op);
     }
     ResidualOp<0> op;
     op.stop = stop;
@@ -548,7 +551,7 @@ int mat_residual(b200ldu_matrix *m, double *x, const double *b, double *out, boo
     op.diag = m->d_diag;
     op.b = b;
     op.out = out;
-    return engine_launch(m->a, m->d_val, op);
+    return engine_launch_m(m, false, op);
 }
 
 int mat_sumA(b200ldu_matrix *m, double *out, const int *stop)
@@ -557,7 +560,7 @@ int mat_sumA(b200ldu_matrix *m, double *out, const int *stop)
     op.stop = stop;
     op.diag = m->d_diag;
     op.out = out;
-    return engine_launch(m->a, m->d_val, op);
+    return engine_launch_m(m, false, op);
 }
 
 int mat_H1(b200ldu_matrix *m, double *out)
@@ -565,7 +568,7 @@ int mat_H1(b200ldu_matrix *m, double *out)
     CoeffSumOp<true, true> op;
     op.diag = nullptr;
     op.out = out;
-    return engine_launch(m->a, m->d_val, op);
+    return engine_launch_m(m, false, op);
 }
 
 int mat_H(b200ldu_matrix *m, const double *x, double *out)
@@ -574,7 +577,7 @@ int mat_H(b200ldu_matrix *m, const double *x, double *out)
     op.x = x;
     op.diag = m->d_diag;
     op.out = out;
-    return engine_launch(m->a, m->d_val, op);
+    return engine_launch_m(m, false, op);
 }
 
 int mat_interpolate(b200ldu_matrix *m, double *x, double *out, const int *stop)
@@ -587,7 +590,7 @@ int mat_interpolate(b200ldu_matrix *m, double *x, double *out, const int *stop)
     op.x = x;
     op.diag = m->d_diag;
     op.out = out;
-    return engine_launch(m->a, m->d_val, op);
+    return engine_launch_m(m, false, op);
 }
 
 // ---------------------------------------------------------------------------
@@ -604,7 +607,6 @@ static int amul_ext(b200ldu_matrix *m, bool T, const double *psi, double *out)
 {
     CHECK_M(m);
     if (!psi || !out) return B200LDU_EINVAL;
-    if (T && !m->d_valT) return B200LDU_EINVAL;
     b200ldu_addr *a = m->a;
     double *xb = addr_pool_vec(a, 0), *yb = addr_pool_vec(a, 1);
     if (!xb || !yb) return B200LDU_ECUDA;

@@ -70,7 +70,13 @@ def test_matrix_ops_bit_exact(gpu, meshmod, orc, dims, kind, centres, band):
     for pre in ("none", "diagonal", "DIC"):
         for T in (False, True):
             got = mat.precondition(pre, xd, T).cpu().numpy()
-            assert np.array_equal(got, om.precondition(pre, x, T)), (pre, T)
+            ref = om.precondition(pre, x, T)
+            if pre == "DIC":
+                # AINV stages t = rD*r: one rounding per term apart from the reference's
+                # (upper*rD)*r association (ops.cuh AinvOp) -> stated tolerance 1e-13
+                np.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-13 * np.abs(ref).max())
+            else:
+                assert np.array_equal(got, ref), (pre, T)
     for ns in (1, 2, 3):
         assert np.array_equal(mat.smooth("GaussSeidel", xd, bd, ns).cpu().numpy(), om.jacobi(x, b, ns))
     cs.close()

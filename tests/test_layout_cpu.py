@@ -170,3 +170,103 @@ def test_layout_rejects_bad_addressing(capi):
                                               C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
     rc = L.b200ldu_layout_debug_create(3, 2, l.ctypes.data, u.ctypes.data, 0, None, None, None, C.byref(h))
     assert rc == -1
+
+
+def _shared(capi, lay_handle_getter):
+    pass
+
+
+def _layout_shared(capi, mesh, centres=True, band=None):
+    """general + shared-coefficient layout arrays (host-only debug build)"""
+    L = capi.lib()
+    L.b200ldu_layout_debug_get.restype = C.c_longlong
+    L.b200ldu_layout_debug_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong]
+    L.b200ldu_layout_debug_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.b200ldu_layout_debug_destroy.argtypes = [C.c_void_p]
+    if band:
+        os.environ["B200LDU_BAND_ROWS"] = str(band)
+    ps, fc = mesh.patch_start_facecells()
+    nP = len(ps) - 1
+    l = np.ascontiguousarray(mesh.lower, np.int32)
+    u = np.ascontiguousarray(mesh.upper, np.int32)
+    cc = np.ascontiguousarray(mesh.cell_centres()) if centres else None
+    h = C.c_void_p()
+    rc = L.b200ldu_layout_debug_create(mesh.nCells, mesh.nFaces, l.ctypes.data, u.ctypes.data, nP,
+                                       ps.ctypes.data if nP else None, fc.ctypes.data if nP else None,
+                                       cc.ctypes.data if cc is not None else None, C.byref(h))
+    os.environ.pop("B200LDU_BAND_ROWS", None)
+    assert rc == 0
+    names = {0: ("perm", np.int32), 1: ("iperm", np.int32), 7: ("haloStart", np.int32), 8: ("haloIdx", np.int32),
+             9: ("dims", np.int32), 10: ("vStart", np.int64), 11: ("nStart", np.int64), 12: ("VS", np.uint16),
+             13: ("WO", np.uint16), 14: ("WN", np.uint16), 15: ("colV", np.uint16), 16: ("codeV", np.int32),
+             17: ("nbr", np.uint32)}
+    out = {}
+    for what, (name, dt) in names.items():
+        n = L.b200ldu_layout_debug_get(h, what, None, 0)
+        a = np.zeros(max(n, 1), dtype=dt)
+        L.b200ldu_layout_debug_get(h, what, a.ctypes.data, n)
+        out[name] = a[:n]
+    L.b200ldu_layout_debug_destroy(h)
+    return out
+
+
+@pytest.mark.parametrize("dims,centres,band,nR", [((8, 8, 8), True, None, 1), ((9, 6, 5), False, 128, 1),
+                                                  ((12, 12, 12), True, 256, 1), ((8, 8, 8), True, 64, 4),
+                                                  ((3, 2, 1), True, None, 1)])
+def test_shared_layout_structure(capi, meshmod, dims, centres, band, nR):
+    """The shared-coefficient layout reproduces every row in reference order: owner faces
+    (own value slot), neighbour faces (ref to the owner's slot in the same slice, or to the
+    slice's extras), interface faces; each face's coefficient is stored once per slice."""
+    mesh = meshmod.hex_mesh(*dims) if nR == 1 else meshmod.decompose(dims[0], nR, 1)
+    lay = _layout_shared(capi, mesh, centres, band)
+    nPad, nBands, bandRows, nRecv, maxHalo = [int(x) for x in lay["dims"]]
+    perm, iperm = lay["perm"], lay["iperm"]
+    assert len(lay["vStart"]) == nPad // 64 + 1
+    n = mesh.nCells
+    own = [[] for _ in range(n)]
+    nei = [[] for _ in range(n)]
+    for f in range(mesh.nFaces):
+        own[mesh.lower[f]].append(f)
+        nei[mesh.upper[f]].append(f)
+    ps, fc = mesh.patch_start_facecells()
+    ifc = [[] for _ in range(n)]
+    for i, c in enumerate(fc):
+        ifc[c].append(i)
+    stored = 0
+    for s in range(nPad // 64):
+        vb, nb = int(lay["vStart"][s]), int(lay["nStart"][s])
+        nV = int(lay["vStart"][s + 1]) - vb
+        VS, WO, WN = int(lay["VS"][s]), int(lay["WO"][s]), int(lay["WN"][s])
+        band = (s * 64) // bandRows
+        halo = lay["haloIdx"][lay["haloStart"][band]:lay["haloStart"][band + 1]]
+        codes = lay["codeV"][vb:vb + nV]
+        assert nV % 2 == 0 and nV >= VS * 64 + 1
+        stored += int((codes >= 0).sum())
+
+        def target(cv):
+            return band * bandRows + cv if cv < bandRows else int(halo[cv - bandRows])
+        for q in range(64):
+            r = s * 64 + q
+            c = iperm[r]
+            colv = [int(lay["colV"][vb + j * 64 + q]) for j in range(VS)]
+            codv = [int(codes[j * 64 + q]) for j in range(VS)]
+            nbrs = [int(lay["nbr"][nb + j * 64 + q]) for j in range(WN)]
+            if c < 0:
+                assert all(x == -1 for x in codv)
+                assert all(codes[e >> 16] == -1 for e in nbrs)
+                continue
+            got_o = [(codv[j], target(colv[j])) for j in range(WO) if codv[j] != -1]
+            assert got_o == [(2 * f, int(perm[mesh.upper[f]])) for f in own[c]]
+            got_n = [(int(codes[e >> 16]), target(e & 0xffff)) for e in nbrs if codes[e >> 16] != -1]
+            assert got_n == [(2 * f, int(perm[mesh.lower[f]])) for f in nei[c]]
+            for e in nbrs:  # refs into owner slots must point at the owner's row inside this slice
+                ref = e >> 16
+                if ref < VS * 64 and codes[ref] != -1:
+                    assert s * 64 + ref % 64 == perm[mesh.lower[codes[ref] // 2]]
+            got_i = [(codv[j], target(colv[j])) for j in range(WO, VS) if codv[j] != -1]
+            assert got_i == [(-2 - i, nPad + i) for i in ifc[c]]
+    # every face stored once as an owner value, plus once per slice that only sees its neighbour side
+    assert stored >= mesh.nFaces
+    if dims == (12, 12, 12):
+        assert stored < 1.45 * mesh.nFaces  # cube-shaped slices: most faces are slice-internal
