@@ -38,6 +38,24 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the Amul engine kernel from the
+    committed `ncu --set full` capture (profiles/r01_ncu_full_engine_raw.csv), or None."""
+    import csv
+    p = os.path.join(ROOT, "profiles", "r01_ncu_full_engine_raw.csv")
+    try:
+        rows = list(csv.reader(open(p)))
+        hdr, units = rows[0], rows[1]
+        kn, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            if "AmulOp" in r[kn]:
+                return float(r[rd]) * mult[units[rd]] + float(r[wr]) * mult[units[wr]]
+    except Exception:
+        return None
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -238,14 +256,20 @@ def main():
         psi_np[:] = 0
         mat.solve_host("PCG", "DIC", psi_np, src_np, **kw)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    # each step = one b200ldu_solve_host call (H2D psi+source, solve, D2H psi), bracketed by CUDA
+    # events; the harness's host-side reset of the initial guess between steps is not solver work
+    e2e_local = 0.0
     for _ in range(args.steps):
         psi_np[:] = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
         mat.solve_host("PCG", "DIC", psi_np, src_np, **kw)
-    e1.record()
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_local += e0.elapsed_time(e1)
     barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_ms = max_over_ranks(e2e_local)
     e2e_val = nGlobal * iters * args.steps / (e2e_ms * 1e-3) / 1e6
 
     # ---------------- CPU baseline (rank 0, N=1 only, bounded sample) ----------------
@@ -277,7 +301,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "engine_kernel<AmulOp<0>> (Amul SpMV, banded)",
                          "achieved": amul_gbs, "peak": peak, "unit": "GB/s", "frac": amul_gbs / peak,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": amul_bytes,
-                         "ms_per_launch": amul_ms, "traffic": None,
+                         "ms_per_launch": amul_ms, "traffic": ncu_traffic(),
                          "pcg_iteration_gbs_unfused_model": pcg_gbs, "pcg_iteration_frac": pcg_gbs / peak},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "Mcell-iters/s", "h2d_bytes_per_step": 16 * nGlobal,

@@ -1,0 +1,148 @@
+#!/usr/bin/env python
+"""Per-kernel roofline table (not the driver's bench contract -- that is bench.py):
+times every hot-path kernel alone on the 256^3 cavity with CUDA events and reports achieved
+ALGORITHMIC GB/s (SURVEY.md section 8d byte counts) against the measured HBM peak.
+  python bench_kernels.py [--n 256] [--reps 20] > gpurun_out/kernels.json
+Run it under `ncu --metrics gpu__time_duration.sum` for the matching launch list."""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--reps", type=int, default=20)
+    args = ap.parse_args()
+    import torch
+    capi = importlib.import_module("rapidcfd-dev_b200.capi")
+    meshmod = importlib.import_module("rapidcfd-dev_b200.mesh")
+    from bench import peaks
+    peak, peak_src = peaks()
+    L = capi.lib()
+    n = args.n
+    mesh = meshmod.hex_mesh(n)
+    N, F = mesh.nCells, mesh.nFaces
+    ctx = capi.Context(0)
+    dev = ctx.device
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    addr = capi.mesh_to_device(ctx, mesh)
+    dp = capi._dp
+    rows = []
+
+    def timeit(name, nbytes, fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.reps
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        rows.append({"kernel": name, "algorithmic_bytes": int(nbytes), "ms": ms, "GBps": gbs, "frac": gbs / peak})
+        print(f"{name:34s} {ms*1e3:9.1f} us  {gbs:8.1f} GB/s  {gbs/peak:5.2f}", file=sys.stderr)
+
+    vl = addr.vec_len
+    xb = torch.rand(vl, dtype=torch.float64, device=dev)
+    yb = torch.zeros(vl, dtype=torch.float64, device=dev)
+    bb = torch.rand(vl, dtype=torch.float64, device=dev)
+    xb[N:] = 0
+    # ---- symmetric matrix ----
+    cp = meshmod.pressure_laplacian(mesh)
+    mat = capi.LduMatrix(addr)
+    dg, up = tt(cp["diag"]), tt(cp["upper"])
+    mat.set(dg, up)
+    op = lambda nm: (lambda: capi.check(L.b200ldu_bench_op(mat.h, nm.encode(), dp(xb), dp(yb), dp(bb))))
+    timeit("Amul symmetric", 24 * N + 16 * F, op("amul"))
+    timeit("Amul + fused <Ap,p>", 24 * N + 16 * F, op("amul_dot"))
+    timeit("AINV precondition", 24 * N + 16 * F, op("ainv"))
+    timeit("AINV + fused <w,r>", 24 * N + 16 * F, op("ainv_dot"))
+    timeit("Jacobi sweep", 40 * N + 16 * F, op("jacobi"))
+    timeit("residual + fused sum|r|", 32 * N + 16 * F, op("residual"))
+    timeit("sumA", 16 * N + 8 * F, op("sumA"))
+    mat.close()
+    # ---- asymmetric matrix ----
+    cu = meshmod.momentum_matrix(mesh)
+    matU = capi.LduMatrix(addr)
+    dgu, upu, lou = tt(cu["diag"]), tt(cu["upper"]), tt(cu["lower"])
+    matU.set(dgu, upu, lou)
+    opu = lambda nm: (lambda: capi.check(L.b200ldu_bench_op(matU.h, nm.encode(), dp(xb), dp(yb), dp(bb))))
+    timeit("Amul asymmetric", 24 * N + 24 * F, opu("amul"))
+    timeit("Tmul asymmetric", 24 * N + 24 * F, opu("tmul"))
+    psi, src = torch.rand(N, dtype=torch.float64, device=dev), torch.rand(N, dtype=torch.float64, device=dev)
+    timeit("faceH (flux)", 24 * F + 8 * N, lambda: matU.faceH(psi))
+    matU.close()
+    del dgu, upu, lou
+    # ---- vector kernels through a short PCG (fused op list): whole-iteration rate ----
+    # ---- finite-volume face sums ----
+    bfc = np.concatenate([p.faceCells for p in mesh.patches]).astype(np.int32)
+    capi.check(L.b200ldu_fv_boundary_set(addr.h, len(bfc), bfc.ctypes.data))
+    nB = len(bfc)
+    V = tt(mesh.volumes())
+    for nc in (1, 3):
+        ssf = torch.rand(F * nc, dtype=torch.float64, device=dev)
+        bssf = torch.rand(nB * nc, dtype=torch.float64, device=dev)
+        out = torch.empty(N * nc, dtype=torch.float64, device=dev)
+        timeit(f"fvc::surfaceIntegrate nComp={nc}", 8 * nc * F + 8 * F + 8 * N + 8 * nc * N,
+               lambda: capi.check(L.b200ldu_fv_surface_integrate(addr.h, nc, dp(ssf), dp(bssf), dp(V), dp(out), 1, -1)))
+        Sf = torch.rand(F * 3, dtype=torch.float64, device=dev)
+        bSf = torch.rand(nB * 3, dtype=torch.float64, device=dev)
+        g = torch.empty(N * 3 * nc, dtype=torch.float64, device=dev)
+        timeit(f"gaussGrad::gradf nComp={nc}", 8 * nc * F + 24 * F + 8 * F + 8 * N + 24 * nc * N,
+               lambda: capi.check(L.b200ldu_fv_gauss_grad(addr.h, nc, dp(Sf), dp(ssf), dp(bSf), dp(bssf), dp(V), dp(g))))
+        vf = torch.rand(N * nc, dtype=torch.float64, device=dev)
+        w = torch.rand(F, dtype=torch.float64, device=dev)
+        sf = torch.empty(F * nc, dtype=torch.float64, device=dev)
+        timeit(f"linear interpolate nComp={nc}", 8 * F + 8 * F + 8 * nc * N + 8 * nc * F,
+               lambda: capi.check(L.b200ldu_fv_interpolate_linear(addr.h, nc, dp(w), dp(vf), dp(sf))))
+        del ssf, bssf, out, Sf, bSf, g, vf, w, sf
+    dc, gm = torch.rand(F, dtype=torch.float64, device=dev), torch.rand(F, dtype=torch.float64, device=dev)
+    upp, low = torch.empty(F, dtype=torch.float64, device=dev), torch.empty(F, dtype=torch.float64, device=dev)
+    dgo = torch.empty(N, dtype=torch.float64, device=dev)
+    timeit("fvm::laplacian fill (+negSumDiag)", 24 * F + 8 * F + 8 * N,
+           lambda: capi.check(L.b200ldu_fv_laplacian_fill(addr.h, dp(dc), dp(gm), dp(upp), dp(dgo))))
+    timeit("fvm::div fill (+negSumDiag)", 32 * F + 8 * F + 8 * N,
+           lambda: capi.check(L.b200ldu_fv_convection_fill(addr.h, dp(dc), dp(gm), dp(low), dp(upp), dp(dgo))))
+    # ---- time to solution: GAMG vs PCG on the pressure matrix (tolerance 1e-6, relTol 0) ----
+    import time
+    del dc, gm, upp, low, dgo
+    solves = {}
+    mat = capi.LduMatrix(addr)
+    mat.set(dg, up)
+    b = tt(meshmod.cell_field_global(mesh, 9))
+    t0 = time.perf_counter()
+    gg = capi.GamgAgglomeration(addr, meshmod.face_area_pair_weights(mesh), 10)
+    t_agg = time.perf_counter() - t0
+    for name, solver, second, kw in (("GAMG", "GAMG", "GaussSeidel", dict(tolerance=1e-6, maxIter=200)),
+                                     ("PCG+DIC", "PCG", "DIC", dict(tolerance=1e-6, maxIter=5000))):
+        for rep in range(2):
+            psi = torch.zeros(N, dtype=torch.float64, device=dev)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            perf, _ = mat.solve(solver, second, psi, b, gamg=gg if solver == "GAMG" else None, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        solves[name] = {"ms": ms, "iterations": perf.nIterations, "final_residual": perf.finalResidual,
+                        "Mcell_iters_per_s": N * perf.nIterations / (ms * 1e-3) / 1e6, "line": perf.line("p")}
+        print(name, solves[name], file=sys.stderr)
+    solves["GAMG"]["levels"] = gg.nLevels
+    solves["GAMG"]["agglomeration_host_s"] = t_agg
+    print(json.dumps({"n": n, "peak_gbs": peak, "peak_source": peak_src, "kernels": rows, "solves": solves}))
+    addr.close()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -143,6 +143,9 @@ long long b200ldu_vec_len(const b200ldu_addr *a);
 int b200ldu_to_banded(b200ldu_addr *a, const double *x_d, double *xb_d);
 int b200ldu_from_banded(b200ldu_addr *a, const double *xb_d, double *x_d);
 int b200ldu_amul_banded(b200ldu_matrix *m, const double *psib_d, double *Apsib_d);
+/* one banded kernel by name (amul, tmul, amul_dot, ainv, ainv_dot, jacobi, residual, sumA, H):
+ * the per-kernel roofline table of bench.py --kernels */
+int b200ldu_bench_op(b200ldu_matrix *m, const char *op, double *xb_d, double *yb_d, const double *bb_d);
 
 /* ---- lduMatrix::solver::New(...)->solve(psi, source, cmpt)
  * (LDU/lduMatrix/lduMatrixSolver.C:43-140; lduMatrix.H:253-258) ----

@@ -56,7 +56,7 @@ EXPORTS = [
     "b200ldu_amul", "b200ldu_tmul", "b200ldu_sumA", "b200ldu_residual", "b200ldu_H", "b200ldu_H1",
     "b200ldu_faceH", "b200ldu_precondition", "b200ldu_smooth",
     "b200ldu_vec_len", "b200ldu_to_banded", "b200ldu_from_banded", "b200ldu_amul_banded",
-    "b200ldu_solve", "b200ldu_solve_host", "b200ldu_launch_count",
+    "b200ldu_solve", "b200ldu_solve_host", "b200ldu_launch_count", "b200ldu_bench_op",
     "b200ldu_gamg_create", "b200ldu_gamg_destroy", "b200ldu_gamg_nlevels", "b200ldu_gamg_level_size",
     "b200ldu_gamg_restrict_addr",
     "b200ldu_fv_boundary_set", "b200ldu_fv_surface_integrate", "b200ldu_fv_gauss_grad",
@@ -111,6 +111,7 @@ def lib():
     L.b200ldu_solve.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(Controls), vp, vp, vp,
                                 C.POINTER(Perf), vp, C.c_int]
     L.b200ldu_solve_host.argtypes = L.b200ldu_solve.argtypes
+    L.b200ldu_bench_op.argtypes = [vp, C.c_char_p, vp, vp, vp]
     L.b200ldu_gamg_create.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
     L.b200ldu_gamg_destroy.argtypes = [vp]
     L.b200ldu_gamg_nlevels.argtypes = [vp]

@@ -88,7 +88,7 @@ __device__ __forceinline__ void block_reduce_store(double (&red)[NRED], double *
 //                                                    writes rows r, r+1; adds reductions
 // ---------------------------------------------------------------------------
 template <class Op, bool SHARED>
-__global__ void __launch_bounds__(ENGINE_THREADS, SHARED ? 3 : 1) engine_kernel(const LayoutDev L,
+__global__ void __launch_bounds__(ENGINE_THREADS, SHARED ? 3 : 6) engine_kernel(const LayoutDev L,
                                                                 const double *__restrict__ val,
                                                                 Op op)
 {

@@ -800,3 +800,22 @@ extern "C" int b200ldu_smooth(b200ldu_matrix *m, const char *name, double omega,
     }
     return from_banded(a, cur, psi_d);
 }
+
+// banded-order single-kernel entry for the kernel table of bench.py (--kernels): vectors are
+// b200ldu_vec_len() doubles in banded order, exactly as the solvers hold them
+extern "C" int b200ldu_bench_op(b200ldu_matrix *m, const char *op, double *xb, double *yb, const double *bb)
+{
+    CHECK_M(m);
+    if (!op || !xb || !yb) return B200LDU_EINVAL;
+    if (!strcmp(op, "amul")) return mat_amul(m, false, xb, yb, 0, nullptr, nullptr, nullptr);
+    if (!strcmp(op, "tmul")) return mat_amul(m, true, xb, yb, 0, nullptr, nullptr, nullptr);
+    if (!strcmp(op, "amul_dot")) return mat_amul(m, false, xb, yb, 1, nullptr, m->d_partials, nullptr);
+    if (!strcmp(op, "ainv")) return mat_ainv(m, false, xb, yb, false, nullptr, nullptr, nullptr);
+    if (!strcmp(op, "ainv_dot")) return mat_ainv(m, false, xb, yb, true, nullptr, m->d_partials, nullptr);
+    if (!strcmp(op, "jacobi")) return bb ? mat_jacobi(m, 0.9, xb, bb, yb, nullptr) : B200LDU_EINVAL;
+    if (!strcmp(op, "residual")) return bb ? mat_residual(m, xb, bb, yb, true, m->d_partials, nullptr) : B200LDU_EINVAL;
+    if (!strcmp(op, "sumA")) return mat_sumA(m, yb, nullptr);
+    if (!strcmp(op, "H")) return mat_H(m, xb, yb);
+    b200_set_error("bench_op: unknown op %s", op);
+    return B200LDU_EINVAL;
+}
