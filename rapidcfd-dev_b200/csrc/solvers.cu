@@ -73,6 +73,15 @@ int run_iterations(Solve &S, long long maxBodies, Body body)
     long long enq = 0;
     int chunk = 0;
     bool pending[2] = {false, false};
+    cudaGraphExec_t graphExec = nullptr;
+    long long launchesPerGraph = 0;
+    struct GraphGuard {
+        cudaGraphExec_t &g;
+        ~GraphGuard()
+        {
+            if (g) cudaGraphExecDestroy(g);
+        }
+    } guard{graphExec};
     for (;;) {
         int slot = chunk & 1;
         // before reusing a slot, consume its previous result
@@ -90,7 +99,34 @@ int run_iterations(Solve &S, long long maxBodies, Body body)
             }
             break;
         }
-        for (int k = 0; k < every && enq < maxBodies; k++, enq++) TRY(body(enq));
+        // CUDA graph: after one chunk launched kernel by kernel (attribute set-up, warm caches) a full
+        // chunk of `every` bodies (even, so every ping-pong returns to its starting buffers) is captured
+        // once and replayed -- the device-side stop flag makes replayed bodies after convergence no-ops.
+        const bool fullChunk = (enq + every <= maxBodies) && (every % 2 == 0) && (enq % 2 == 0);
+        if (S.useGraph && fullChunk && chunk >= 1) {
+            if (!graphExec) {
+                long long l0 = ctx->launches;
+                cudaGraph_t g = nullptr;
+                CUDA_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+                int rcb = B200LDU_OK;
+                for (int k = 0; k < every && rcb == B200LDU_OK; k++) rcb = body(enq + k);
+                cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+                if (rcb != B200LDU_OK) return rcb;
+                if (ce != cudaSuccess || !g) {
+                    b200_set_error("CUDA graph capture failed: %s", cudaGetErrorString(ce));
+                    return B200LDU_ECUDA;
+                }
+                launchesPerGraph = ctx->launches - l0;
+                ctx->launches = l0;
+                CUDA_TRY(cudaGraphInstantiate(&graphExec, g, 0));
+                cudaGraphDestroy(g);
+            }
+            CUDA_TRY(cudaGraphLaunch(graphExec, ctx->stream));
+            ctx->launches += launchesPerGraph;
+            enq += every;
+        } else {
+            for (int k = 0; k < every && enq < maxBodies; k++, enq++) TRY(body(enq));
+        }
         CUDA_TRY(cudaMemcpyAsync((void *)&flags[slot], &S.sc->stop, sizeof(int), cudaMemcpyDeviceToHost,
                                  ctx->stream));
         CUDA_TRY(cudaEventRecord(ev[slot], ctx->stream));
@@ -533,6 +569,36 @@ int solve_banded(b200ldu_matrix *m, const char *solver, const char *pre, const b
     S.pinnedFlags[0] = S.pinnedFlags[1] = 0;
     CUDA_TRY(cudaEventCreateWithFlags(&S.ev[0], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&S.ev[1], cudaEventDisableTiming));
+
+    // CUDA graphs need a capturable stream: if the context runs on the legacy default stream the
+    // solve moves to the context's own stream, ordered against the caller's stream by events
+    {
+        const char *ev = getenv("B200LDU_GRAPH");
+        S.useGraph = !(ev && atoi(ev) == 0) && (ctx->nRanks == 1 || ctx->p2p);
+    }
+    cudaStream_t userStream = ctx->stream;
+    const bool swapStream = S.useGraph && ctx->ownStream && userStream != ctx->ownStream;
+    if (swapStream) {
+        CUDA_TRY(cudaEventRecord(S.ev[0], userStream));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->ownStream, S.ev[0], 0));
+        ctx->stream = ctx->ownStream;
+    }
+    struct StreamRestore {
+        b200ldu_ctx *c;
+        cudaStream_t user;
+        bool on;
+        ~StreamRestore()
+        {
+            if (!on) return;
+            cudaEvent_t e;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess) {
+                cudaEventRecord(e, c->ownStream);
+                cudaStreamWaitEvent(user, e, 0);
+                cudaEventDestroy(e);
+            }
+            c->stream = user;
+        }
+    } restore{ctx, userStream, swapStream};
 
     SolverScalars h;
     memset(&h, 0, sizeof(h));

@@ -19,6 +19,7 @@ struct Solve {
     bool sweepParityUnknown = false;
     double *smoothBuf[2] = {nullptr, nullptr};
     bool noScalars = false;
+    bool useGraph = false; // replay iteration chunks as a CUDA graph
     int gamgFinestSweeps = 0; // GAMG: finest-level sweeps per cycle (result-buffer parity)
     double *vec(int k); // workspace vector k of the matrix (allocated once, reused)
 };
