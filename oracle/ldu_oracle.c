@@ -98,7 +98,15 @@ void orc_addr_free(orc_addr *a)
     free(a->losortStart);
     free(a->patchStart);
     free(a->faceCells);
+    free(a->neighbRank);
     free(a);
+}
+
+void orc_addr_set_neighb_ranks(orc_addr *a, const int *neighbRank)
+{
+    free(a->neighbRank);
+    a->neighbRank = (int *)malloc(sizeof(int) * (size_t)(a->nPatches > 0 ? a->nPatches : 1));
+    memcpy(a->neighbRank, neighbRank, sizeof(int) * (size_t)a->nPatches);
 }
 
 const int *orc_addr_owner_start(const orc_addr *a) { return a->ownerStart; }
@@ -128,14 +136,14 @@ void orc_matrix_free(orc_matrix *m) { free(m); }
 /* processorFvPatchScalarField.C:37-172                                       */
 /* ------------------------------------------------------------------------- */
 
-static double *orc_halo_exchange(const orc_addr *a, const double *psi, const orc_comm *comm)
+double *orc_halo_exchange(const orc_addr *a, const double *psi, const orc_comm *comm)
 {
     int tot = a->nPatches ? a->patchStart[a->nPatches] : 0;
     if (tot == 0) return NULL;
     double *send = (double *)malloc(sizeof(double) * (size_t)tot);
     double *recv = (double *)calloc((size_t)tot, sizeof(double));
     for (int i = 0; i < tot; i++) send[i] = psi[a->faceCells[i]]; /* patchInternalField */
-    if (comm && comm->halo) comm->halo(comm->ctx, send, recv, tot);
+    if (comm && comm->halo) comm->halo(comm->ctx, send, recv, tot, a->nPatches, a->patchStart);
     free(send);
     return recv;
 }

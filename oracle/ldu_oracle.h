@@ -41,9 +41,14 @@ typedef struct orc_matrix orc_matrix;
  * doubles in place (rank-ordered sum for reproducibility). */
 typedef struct orc_comm {
     void *ctx;
-    void (*halo)(void *ctx, const double *send, double *recv, int n);
+    /* patchStart[nPatches+1] gives the slice of every coupled patch in send/recv (coarse GAMG
+     * levels have their own patch sizes; the neighbour ranks are those of the finest level) */
+    void (*halo)(void *ctx, const double *send, double *recv, int n, int nPatches, const int *patchStart);
     void (*sum)(void *ctx, double *vals, int n);
     long long nCellsGlobal; /* for gAverage; 0 => local nCells */
+    /* all-gather of fixed-size records: every rank contributes n doubles, all[r*n + i] */
+    void (*gather)(void *ctx, const double *mine, int n, double *all);
+    int rank, nRanks;
 } orc_comm;
 
 typedef struct orc_controls {
@@ -74,6 +79,8 @@ void orc_controls_default(orc_controls *c);
 /* ---- addressing (lduAddressing.C:169-344) ---- */
 orc_addr *orc_addr_create(int nCells, int nFaces, const int *l, const int *u,
                           int nPatches, const int *patchStart, const int *faceCells);
+/* neighbour rank of every coupled patch (needed by the multi-rank GAMG agglomeration only) */
+void orc_addr_set_neighb_ranks(orc_addr *a, const int *neighbRank);
 void orc_addr_free(orc_addr *a);
 const int *orc_addr_owner_start(const orc_addr *a);
 const int *orc_addr_losort(const orc_addr *a);
@@ -117,7 +124,8 @@ int orc_solve(const orc_matrix *m, const char *solver, const char *precondOrSmoo
 /* ---- GAMG building blocks (exposed for parity tests) ---- */
 typedef struct orc_gamg orc_gamg;
 orc_gamg *orc_gamg_create(const orc_addr *a, const double *faceWeights /* finest level */,
-                          int nCellsInCoarsestLevel, int mergeLevels, int *forwardFlag);
+                          int nCellsInCoarsestLevel, int mergeLevels, int *forwardFlag,
+                          const orc_comm *comm /* NULL: single domain */);
 void orc_gamg_free(orc_gamg *g);
 int orc_gamg_nlevels(const orc_gamg *g);                 /* number of coarse levels */
 int orc_gamg_ncells(const orc_gamg *g, int lev);        /* cells of coarse level lev */
@@ -127,7 +135,9 @@ const int *orc_gamg_face_restrict_addr(const orc_gamg *g, int lev);
 const unsigned char *orc_gamg_face_flip(const orc_gamg *g, int lev);
 const orc_addr *orc_gamg_addr(const orc_gamg *g, int lev);     /* coarse level addressing */
 int orc_gamg_solve(const orc_matrix *m, orc_gamg *g, const char *smoother, const orc_controls *c,
-                   double *psi, const double *source, orc_perf *perf, double *hist, int histCap);
+                   double *psi, const double *source, const orc_comm *comm, orc_perf *perf, double *hist,
+                   int histCap);
+int orc_gamg_npatchfaces(const orc_gamg *g, int lev); /* coupled-patch faces of coarse level lev */
 
 /* ---- finite-volume face-sum loops (Appendix A.11) ---- */
 /* nComp = 1 (scalar) or 3 (vector); fields are AoS: x[c*nComp + k]. */

@@ -49,12 +49,14 @@ class Perf(C.Structure):
     ]
 
 
-HALO_CB = C.CFUNCTYPE(None, C.c_void_p, c_dp, c_dp, C.c_int)
+HALO_CB = C.CFUNCTYPE(None, C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, c_ip)
 SUM_CB = C.CFUNCTYPE(None, C.c_void_p, c_dp, C.c_int)
+GATHER_CB = C.CFUNCTYPE(None, C.c_void_p, c_dp, C.c_int, c_dp)
 
 
 class Comm(C.Structure):
-    _fields_ = [("ctx", C.c_void_p), ("halo", HALO_CB), ("sum", SUM_CB), ("nCellsGlobal", C.c_longlong)]
+    _fields_ = [("ctx", C.c_void_p), ("halo", HALO_CB), ("sum", SUM_CB), ("nCellsGlobal", C.c_longlong),
+                ("gather", GATHER_CB), ("rank", C.c_int), ("nRanks", C.c_int)]
 
 
 _lib = None
@@ -93,7 +95,9 @@ def lib():
         L.orc_solve.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(Controls), c_dp, c_dp,
                                 C.c_void_p, C.POINTER(Perf), c_dp, C.c_int]
         L.orc_gamg_create.restype = C.c_void_p
-        L.orc_gamg_create.argtypes = [C.c_void_p, c_dp, C.c_int, C.c_int, c_ip]
+        L.orc_gamg_create.argtypes = [C.c_void_p, c_dp, C.c_int, C.c_int, c_ip, C.c_void_p]
+        L.orc_addr_set_neighb_ranks.argtypes = [C.c_void_p, c_ip]
+        L.orc_gamg_npatchfaces.argtypes = [C.c_void_p, C.c_int]
         L.orc_gamg_free.argtypes = [C.c_void_p]
         L.orc_gamg_nlevels.argtypes = [C.c_void_p]
         L.orc_gamg_ncells.argtypes = [C.c_void_p, C.c_int]
@@ -108,7 +112,7 @@ def lib():
         L.orc_gamg_addr.argtypes = [C.c_void_p, C.c_int]
         L.orc_gamg_solve.restype = C.c_int
         L.orc_gamg_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.POINTER(Controls), c_dp, c_dp,
-                                     C.POINTER(Perf), c_dp, C.c_int]
+                                     C.c_void_p, C.POINTER(Perf), c_dp, C.c_int]
         L.orc_surface_integrate.argtypes = [C.c_void_p, C.c_int, c_dp, C.c_int, c_ip, c_dp, c_dp, c_dp,
                                             C.c_int, C.c_int]
         L.orc_gauss_grad.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp, C.c_int, c_ip, c_dp, c_dp, c_dp, c_dp]
@@ -154,7 +158,7 @@ def controls(**kw):
 class Addr:
     """lduAddressing (owner/neighbour + derived arrays + coupled patches)."""
 
-    def __init__(self, nCells, lower, upper, patchStart=None, faceCells=None, _handle=None):
+    def __init__(self, nCells, lower, upper, patchStart=None, faceCells=None, _handle=None, neighbRank=None):
         self.nCells = int(nCells)
         self._own = _handle is None
         if _handle is not None:
@@ -170,6 +174,9 @@ class Addr:
         self.nPatches = nP
         self.h = lib().orc_addr_create(self.nCells, self.nFaces, _i(self.l), _i(self.u), nP,
                                        _i(self.patchStart), _i(self.faceCells))
+        if neighbRank is not None and nP:
+            self.neighbRank = i32(neighbRank)
+            lib().orc_addr_set_neighb_ranks(self.h, _i(self.neighbRank))
 
     def lower(self):
         return np.ctypeslib.as_array(lib().orc_addr_lower(self.h), (max(self.nFaces, 1),))[: self.nFaces].copy()
@@ -193,21 +200,29 @@ class Addr:
 
 
 class PyComm:
-    """Wraps python callables halo(send)->recv and allsum(vals)->vals as an orc_comm."""
+    """Wraps python callables as an orc_comm:
+    halo(send, patchStart) -> recv ; allsum(vals) -> vals ; gather(mine) -> (nRanks, n) array."""
 
-    def __init__(self, halo=None, allsum=None, nCellsGlobal=0):
-        def _halo(ctx, send, recv, n):
+    def __init__(self, halo=None, allsum=None, nCellsGlobal=0, gather=None, rank=0, nRanks=1):
+        def _halo(ctx, send, recv, n, nP, pstart):
             s = np.ctypeslib.as_array(send, (n,))
             r = np.ctypeslib.as_array(recv, (n,))
-            r[:] = halo(s.copy())
+            ps = np.ctypeslib.as_array(pstart, (nP + 1,)).copy()
+            r[:] = halo(s.copy(), ps)
 
         def _sum(ctx, vals, n):
             v = np.ctypeslib.as_array(vals, (n,))
             v[:] = allsum(v.copy())
 
+        def _gather(ctx, mine, n, allp):
+            m = np.ctypeslib.as_array(mine, (n,))
+            a = np.ctypeslib.as_array(allp, (nRanks * n,))
+            a[:] = np.asarray(gather(m.copy())).reshape(-1)
+
         self._h = HALO_CB(_halo) if halo else HALO_CB()
         self._s = SUM_CB(_sum) if allsum else SUM_CB()
-        self.c = Comm(None, self._h, self._s, int(nCellsGlobal))
+        self._g = GATHER_CB(_gather) if gather else GATHER_CB()
+        self.c = Comm(None, self._h, self._s, int(nCellsGlobal), self._g, int(rank), int(nRanks))
 
     def ptr(self):
         return C.cast(C.byref(self.c), C.c_void_p)
@@ -314,11 +329,12 @@ class Matrix:
 class Gamg:
     """Pair agglomeration hierarchy (cached like the reference's MeshObject)."""
 
-    def __init__(self, addr, faceWeights, nCellsInCoarsestLevel=10, mergeLevels=1, forward=None):
+    def __init__(self, addr, faceWeights, nCellsInCoarsestLevel=10, mergeLevels=1, forward=None, comm=None):
         self.addr = addr
         self._fw = C.c_int(1 if forward is None else int(forward))
         w = f64(faceWeights)
-        self.h = lib().orc_gamg_create(addr.h, _d(w), nCellsInCoarsestLevel, mergeLevels, C.byref(self._fw))
+        self.h = lib().orc_gamg_create(addr.h, _d(w), nCellsInCoarsestLevel, mergeLevels, C.byref(self._fw),
+                                       _commp(comm))
         if not self.h:
             raise RuntimeError("orc_gamg_create failed (mergeLevels != 1?)")
         self.nLevels = lib().orc_gamg_nlevels(self.h)
@@ -332,6 +348,9 @@ class Gamg:
 
     def nfaces(self, lev):
         return lib().orc_gamg_nfaces(self.h, lev)
+
+    def npatchfaces(self, lev):
+        return lib().orc_gamg_npatchfaces(self.h, lev)
 
     def restrict_addr(self, lev):
         n = self.addr.nCells if lev == 0 else self.ncells(lev - 1)
@@ -350,13 +369,13 @@ class Gamg:
         a.nFaces = self.nfaces(lev)
         return a
 
-    def solve(self, matrix, smoother, psi0, source, histCap=2048, **ctl):
+    def solve(self, matrix, smoother, psi0, source, histCap=2048, comm=None, **ctl):
         c = controls(**ctl)
         psi = f64(psi0).copy()
         hist = np.full(histCap, np.nan)
         perf = Perf()
         rc = lib().orc_gamg_solve(matrix.h, self.h, (smoother or "").encode(), C.byref(c), _d(psi),
-                                  _d(f64(source)), C.byref(perf), _d(hist), histCap)
+                                  _d(f64(source)), _commp(comm), C.byref(perf), _d(hist), histCap)
         if rc != 0:
             raise RuntimeError(f"orc_gamg_solve failed rc={rc}")
         return psi, perf, hist[~np.isnan(hist)]

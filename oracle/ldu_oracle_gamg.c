@@ -4,8 +4,12 @@
  * TEST INFRASTRUCTURE ONLY (see ldu_oracle.h).  PARITY UNPINNED by reference tests.
  *
  * Paths relative to /root/reference/src/OpenFOAM/matrices/lduMatrix/solvers/GAMG/
- * (abbreviated GAMG/).  Serial (single-domain) only in this round: coupled-patch
- * agglomeration (processorGAMGInterface.C:93-137) is not restated yet.
+ * (abbreviated GAMG/).  Multi-rank: processor interfaces are agglomerated as in
+ * interfaces/processorGAMGInterface/processorGAMGInterface.C:60-140 (unique (master cell,
+ * slave cell) pairs in order of first appearance along the fine patch), their coefficients
+ * are restricted by summation (GAMGSolverAgglomerateMatrix.C:325-447) and the coarsest
+ * level is solved directly on the matrix assembled from all ranks (LUscalarMatrix.C:60-160;
+ * here every rank assembles and factorises the same global matrix instead of the master).
  */
 #include "ldu_oracle_internal.h"
 #include <math.h>
@@ -22,6 +26,8 @@ struct orc_gamg {
     int *faceRestrict[ORC_MAX_LEVELS]; /* faces of level k -> coarse face or -(cell+1) */
     unsigned char *faceFlip[ORC_MAX_LEVELS];
     int nFineCells[ORC_MAX_LEVELS], nFineFaces[ORC_MAX_LEVELS];
+    int *patchFaceRestrict[ORC_MAX_LEVELS]; /* fine patch face (flat) -> coarse patch face (flat) */
+    int nFinePatchFaces[ORC_MAX_LEVELS];
     const orc_addr *finest;
 };
 
@@ -178,9 +184,58 @@ static orc_addr *coarse_addressing(const orc_addr *fine, const int *rmap, int nC
     return ca;
 }
 
+/* processorGAMGInterface: coarse patch faces of every coupled patch
+ * (interfaces/processorGAMGInterface/processorGAMGInterface.C:60-140).  nbrMap holds the
+ * neighbour side's restrict-map values per fine patch face (internalFieldTransfer). */
+static void coarse_interfaces(const orc_addr *fine, const int *rmap, const double *nbrMap, int myRank,
+                              int **cPatchStartOut, int **cFaceCellsOut, int **pfRestrictOut)
+{
+    int nP = fine->nPatches;
+    int tot = nP ? fine->patchStart[nP] : 0;
+    int *cStart = (int *)calloc((size_t)nP + 1, sizeof(int));
+    int *cCells = (int *)malloc(sizeof(int) * (size_t)(tot > 0 ? tot : 1));
+    int *pfr = (int *)malloc(sizeof(int) * (size_t)(tot > 0 ? tot : 1));
+    int nC = 0;
+    for (int p = 0; p < nP; p++) {
+        int s0 = fine->patchStart[p], s1 = fine->patchStart[p + 1];
+        int nb = fine->neighbRank ? fine->neighbRank[p] : -1;
+        cStart[p] = nC;
+        /* pairs (master cell, slave cell); linear search keeps first-appearance order */
+        int *pa = (int *)malloc(sizeof(int) * (size_t)(s1 - s0 + 1));
+        int *pb = (int *)malloc(sizeof(int) * (size_t)(s1 - s0 + 1));
+        int np = 0;
+        for (int i = s0; i < s1; i++) {
+            int mine = rmap[fine->faceCells[i]], theirs = (int)nbrMap[i];
+            int a = myRank < nb ? mine : theirs, b = myRank < nb ? theirs : mine;
+            int found = -1;
+            for (int k = np - 1; k >= 0; k--) /* recent pairs first: patches are locally ordered */
+                if (pa[k] == a && pb[k] == b) {
+                    found = k;
+                    break;
+                }
+            if (found < 0) {
+                found = np;
+                pa[np] = a;
+                pb[np] = b;
+                cCells[nC + np] = mine;
+                np++;
+            }
+            pfr[i] = nC + found;
+        }
+        nC += np;
+        free(pa);
+        free(pb);
+    }
+    cStart[nP] = nC;
+    *cPatchStartOut = cStart;
+    *cFaceCellsOut = cCells;
+    *pfRestrictOut = pfr;
+}
+
 /* level loop: pairGAMGAgglomerate.C:31-130 (mergeLevels 1 only) */
 orc_gamg *orc_gamg_create(const orc_addr *a, const double *faceWeights,
-                          int nCellsInCoarsestLevel, int mergeLevels, int *forwardFlag)
+                          int nCellsInCoarsestLevel, int mergeLevels, int *forwardFlag,
+                          const orc_comm *comm)
 {
     if (mergeLevels != 1) return NULL;
     orc_gamg *g = (orc_gamg *)calloc(1, sizeof(orc_gamg));
@@ -193,8 +248,10 @@ orc_gamg *orc_gamg_create(const orc_addr *a, const double *faceWeights,
     while (g->nLevels < ORC_MAX_LEVELS - 1) {
         int nCoarse = -1;
         int *map = pair_agglomerate(fine, w, &nCoarse, fwd);
-        /* continueAgglomerating: GAMGAgglomeration.C:72-84 */
-        if (!(nCoarse >= nCellsInCoarsestLevel)) {
+        /* continueAgglomerating: GAMGAgglomeration.C:72-84 (and-reduced over the ranks) */
+        double stopVotes = (nCoarse >= nCellsInCoarsestLevel) ? 0.0 : 1.0;
+        if (comm && comm->sum) comm->sum(comm->ctx, &stopVotes, 1);
+        if (stopVotes > 0) {
             free(map);
             break;
         }
@@ -203,6 +260,27 @@ orc_gamg *orc_gamg_create(const orc_addr *a, const double *faceWeights,
         g->nFineCells[lev] = fine->nCells;
         g->nFineFaces[lev] = fine->nFaces;
         g->addr[lev] = coarse_addressing(fine, map, nCoarse, &g->faceRestrict[lev], &g->faceFlip[lev]);
+        g->nFinePatchFaces[lev] = fine->nPatches ? fine->patchStart[fine->nPatches] : 0;
+        if (fine->nPatches) { /* GAMGAgglomerateLduAddressing.C:470-560 */
+            int tot = fine->patchStart[fine->nPatches];
+            double *mapD = (double *)malloc(sizeof(double) * (size_t)fine->nCells);
+            for (int c = 0; c < fine->nCells; c++) mapD[c] = (double)map[c];
+            double *nbrMap = orc_halo_exchange(fine, mapD, comm);
+            free(mapD);
+            int *cStart, *cCells;
+            coarse_interfaces(fine, map, nbrMap, comm ? comm->rank : 0, &cStart, &cCells,
+                              &g->patchFaceRestrict[lev]);
+            free(nbrMap);
+            /* rebuild the coarse addressing with its coupled patches */
+            orc_addr *ca = g->addr[lev];
+            orc_addr *withP = orc_addr_create(ca->nCells, ca->nFaces, ca->l, ca->u, fine->nPatches, cStart, cCells);
+            if (fine->neighbRank) orc_addr_set_neighb_ranks(withP, fine->neighbRank);
+            orc_addr_free(ca);
+            g->addr[lev] = withP;
+            free(cStart);
+            free(cCells);
+            (void)tot;
+        }
         /* restrictFaceField of the weights (:86-107; GAMGAgglomerationTemplates.C:155-271) */
         double *cw = (double *)calloc((size_t)(g->addr[lev]->nFaces > 0 ? g->addr[lev]->nFaces : 1),
                                       sizeof(double));
@@ -225,6 +303,7 @@ void orc_gamg_free(orc_gamg *g)
         free(g->restrictAddr[i]);
         free(g->faceRestrict[i]);
         free(g->faceFlip[i]);
+        free(g->patchFaceRestrict[i]);
     }
     free(g);
 }
@@ -232,6 +311,11 @@ void orc_gamg_free(orc_gamg *g)
 int orc_gamg_nlevels(const orc_gamg *g) { return g->nLevels; }
 int orc_gamg_ncells(const orc_gamg *g, int lev) { return g->addr[lev]->nCells; }
 int orc_gamg_nfaces(const orc_gamg *g, int lev) { return g->addr[lev]->nFaces; }
+int orc_gamg_npatchfaces(const orc_gamg *g, int lev)
+{
+    const orc_addr *a = g->addr[lev];
+    return a->nPatches ? a->patchStart[a->nPatches] : 0;
+}
 const int *orc_gamg_restrict_addr(const orc_gamg *g, int lev) { return g->restrictAddr[lev]; }
 const int *orc_gamg_face_restrict_addr(const orc_gamg *g, int lev) { return g->faceRestrict[lev]; }
 const unsigned char *orc_gamg_face_flip(const orc_gamg *g, int lev) { return g->faceFlip[lev]; }
@@ -255,13 +339,14 @@ static void prolong_field(const int *map, int nFine, const double *cf, double *f
 typedef struct {
     int n, nf;
     double *diag, *upper, *lower; /* lower == NULL when symmetric */
+    double *bou, *intc;           /* coupled-patch coefficients of this level */
     orc_matrix *m;
 } lev_matrix;
 
 /* agglomerateMatrix: GAMGSolverAgglomerateMatrix.C:37-322 with the sorted
  * (non-atomic) functors GAMGSolverAgglomerateMatrixF.H:9-160 */
 static void agglomerate_matrix(const orc_gamg *g, int lev, const double *fd, const double *fu,
-                               const double *fl, lev_matrix *cm)
+                               const double *fl, const double *fbou, const double *fint, lev_matrix *cm)
 {
     const orc_addr *ca = g->addr[lev];
     int nFine = g->nFineCells[lev], nFF = g->nFineFaces[lev];
@@ -292,17 +377,33 @@ static void agglomerate_matrix(const orc_gamg *g, int lev, const double *fd, con
                 cm->diag[c] = cm->diag[c] + (fu[f] + fl[f]);
         }
     }
-    cm->m = orc_matrix_create(ca, cm->diag, cm->upper, cm->lower, NULL, NULL);
+    /* agglomerateInterfaceCoefficients (:325-447): sums over the patch face map */
+    int nCP = ca->nPatches ? ca->patchStart[ca->nPatches] : 0;
+    cm->bou = (double *)calloc((size_t)(nCP > 0 ? nCP : 1), sizeof(double));
+    cm->intc = (double *)calloc((size_t)(nCP > 0 ? nCP : 1), sizeof(double));
+    for (int i = 0; i < g->nFinePatchFaces[lev]; i++) {
+        int cpf = g->patchFaceRestrict[lev][i];
+        cm->bou[cpf] = cm->bou[cpf] + fbou[i];
+        cm->intc[cpf] = cm->intc[cpf] + fint[i];
+    }
+    cm->m = orc_matrix_create(ca, cm->diag, cm->upper, cm->lower, nCP ? cm->bou : NULL, nCP ? cm->intc : NULL);
 }
 
 /* scale: GAMGSolverScale.C:59-171 */
-static void gamg_scale(const orc_matrix *A, double *field, double *Acf, const double *source)
+static void gamg_scale(const orc_matrix *A, double *field, double *Acf, const double *source,
+                       const orc_comm *comm)
 {
     int n = A->a->nCells;
-    orc_amul(A, field, Acf, NULL);
+    orc_amul(A, field, Acf, comm);
     double num = 0, den = 0;
     for (int i = 0; i < n; i++) num += source[i] * field[i];
     for (int i = 0; i < n; i++) den += Acf[i] * field[i];
+    if (comm && comm->sum) { /* vector2D all-reduce: GAMGSolverScale.C:139-140 */
+        double v[2] = {num, den};
+        comm->sum(comm->ctx, v, 2);
+        num = v[0];
+        den = v[1];
+    }
     /* stabilise(y, VSMALL): y >= 0 ? y + VSMALL : y - VSMALL */
     double sden = den >= 0 ? den + 1e-300 : den - 1e-300;
     double sf = num / sden;
@@ -314,9 +415,10 @@ static void gamg_scale(const orc_matrix *A, double *field, double *Acf, const do
 }
 
 /* interpolate (first overload): GAMGSolverInterpolate.C:45-110 */
-static void gamg_interpolate(const orc_matrix *A, double *psi, double *Apsi)
+static void gamg_interpolate(const orc_matrix *A, double *psi, double *Apsi, const orc_comm *comm)
 {
     const orc_addr *a = A->a;
+    double *pnf = orc_halo_exchange(a, psi, comm);
     for (int c = 0; c < a->nCells; c++) {
         double out = 0.0;
         for (int f = a->ownerStart[c]; f < a->ownerStart[c + 1]; f++)
@@ -327,30 +429,32 @@ static void gamg_interpolate(const orc_matrix *A, double *psi, double *Apsi)
         }
         Apsi[c] = out;
     }
+    if (pnf) { /* updateMatrixInterfaces: Apsi[cell] -= bou*psiNbr */
+        int tot = a->patchStart[a->nPatches];
+        for (int i = 0; i < tot; i++) {
+            double v = A->bou[i] * pnf[i];
+            Apsi[a->faceCells[i]] = Apsi[a->faceCells[i]] + (-v);
+        }
+        free(pnf);
+    }
     for (int c = 0; c < a->nCells; c++) psi[c] = -Apsi[c] / A->diag[c];
 }
 
 /* dense LU with partial pivoting of the coarsest matrix, standing in for
- * matrices/LUscalarMatrix (GAMGSolver.C:144-172, GAMGSolverSolve.C:564-569) */
+ * matrices/LUscalarMatrix (GAMGSolver.C:144-172, GAMGSolverSolve.C:564-569).  With more
+ * than one rank the coarsest matrices of all ranks (and their processor-interface
+ * coefficients, LUscalarMatrix.C:201-270: A[row][col of the neighbour cell] -= coeff) are
+ * assembled into one global matrix; every rank factorises the same matrix. */
 typedef struct {
-    int n;
+    int n;        /* global size */
+    int nLocal, offset, nMax, nRanks;
     double *lu;
     int *piv;
 } dense_lu;
 
-static dense_lu *lu_factor(const orc_matrix *A)
+static void lu_factor_inplace(dense_lu *d)
 {
-    const orc_addr *a = A->a;
-    int n = a->nCells;
-    dense_lu *d = (dense_lu *)malloc(sizeof(dense_lu));
-    d->n = n;
-    d->lu = (double *)calloc((size_t)n * n, sizeof(double));
-    d->piv = (int *)malloc(sizeof(int) * (size_t)n);
-    for (int c = 0; c < n; c++) d->lu[(size_t)c * n + c] = A->diag[c];
-    for (int f = 0; f < a->nFaces; f++) {
-        d->lu[(size_t)a->l[f] * n + a->u[f]] += A->upper[f];
-        d->lu[(size_t)a->u[f] * n + a->l[f]] += A->lower[f];
-    }
+    int n = d->n;
     for (int k = 0; k < n; k++) {
         int p = k;
         double mx = fabs(d->lu[(size_t)k * n + k]);
@@ -372,12 +476,90 @@ static dense_lu *lu_factor(const orc_matrix *A)
             for (int j = k + 1; j < n; j++) d->lu[(size_t)i * n + j] -= fct * d->lu[(size_t)k * n + j];
         }
     }
+}
+
+static dense_lu *lu_factor(const orc_matrix *A, const orc_comm *comm)
+{
+    const orc_addr *a = A->a;
+    int nl = a->nCells;
+    dense_lu *d = (dense_lu *)calloc(1, sizeof(dense_lu));
+    int R = (comm && comm->gather && comm->nRanks > 1) ? comm->nRanks : 1;
+    d->nRanks = R;
+    d->nLocal = nl;
+    int *counts = (int *)calloc((size_t)R, sizeof(int));
+    if (R > 1) {
+        double mine = nl;
+        double *all = (double *)calloc((size_t)R, sizeof(double));
+        comm->gather(comm->ctx, &mine, 1, all);
+        for (int r = 0; r < R; r++) counts[r] = (int)all[r];
+        free(all);
+    } else
+        counts[0] = nl;
+    int N = 0, nMax = 0, *offs = (int *)calloc((size_t)R + 1, sizeof(int));
+    for (int r = 0; r < R; r++) {
+        offs[r] = N;
+        N += counts[r];
+        if (counts[r] > nMax) nMax = counts[r];
+    }
+    int me = R > 1 ? comm->rank : 0;
+    d->n = N;
+    d->offset = offs[me];
+    d->nMax = nMax;
+    /* local rows of the global matrix */
+    double *rows = (double *)calloc((size_t)nMax * N, sizeof(double));
+    for (int c = 0; c < nl; c++) rows[(size_t)c * N + offs[me] + c] = A->diag[c];
+    for (int f = 0; f < a->nFaces; f++) {
+        rows[(size_t)a->l[f] * N + offs[me] + a->u[f]] += A->upper[f];
+        rows[(size_t)a->u[f] * N + offs[me] + a->l[f]] += A->lower[f];
+    }
+    if (R > 1 && a->nPatches) {
+        double *ids = (double *)malloc(sizeof(double) * (size_t)nl);
+        for (int c = 0; c < nl; c++) ids[c] = (double)c;
+        double *nbrCell = orc_halo_exchange(a, ids, comm);
+        free(ids);
+        for (int p = 0; p < a->nPatches; p++)
+            for (int i = a->patchStart[p]; i < a->patchStart[p + 1]; i++)
+                rows[(size_t)a->faceCells[i] * N + offs[a->neighbRank[p]] + (int)nbrCell[i]] -= A->bou[i];
+        free(nbrCell);
+    }
+    d->lu = (double *)calloc((size_t)N * N, sizeof(double));
+    if (R > 1) {
+        double *all = (double *)calloc((size_t)R * nMax * N, sizeof(double));
+        comm->gather(comm->ctx, rows, nMax * N, all);
+        for (int r = 0; r < R; r++)
+            for (int i = 0; i < counts[r]; i++)
+                memcpy(d->lu + (size_t)(offs[r] + i) * N, all + ((size_t)r * nMax + i) * N, sizeof(double) * (size_t)N);
+        free(all);
+    } else
+        memcpy(d->lu, rows, sizeof(double) * (size_t)N * N);
+    free(rows);
+    d->piv = (int *)malloc(sizeof(int) * (size_t)N);
+    /* keep counts/offs for the per-cycle gather */
+    d->piv = (int *)realloc(d->piv, sizeof(int) * ((size_t)N + 2 * (size_t)R + 2));
+    memcpy(d->piv + N, counts, sizeof(int) * (size_t)R);
+    memcpy(d->piv + N + R, offs, sizeof(int) * ((size_t)R + 1));
+    free(counts);
+    free(offs);
+    lu_factor_inplace(d);
     return d;
 }
 
-static void lu_solve(const dense_lu *d, double *b)
+/* x (local part) = (A_global^-1 b_global)(local part) */
+static void lu_solve(const dense_lu *d, const double *bLocal, double *xLocal, const orc_comm *comm)
 {
-    int n = d->n;
+    int n = d->n, R = d->nRanks;
+    const int *counts = d->piv + n, *offs = d->piv + n + R;
+    double *b = (double *)calloc((size_t)n, sizeof(double));
+    if (R > 1) {
+        double *mine = (double *)calloc((size_t)d->nMax, sizeof(double));
+        double *all = (double *)calloc((size_t)R * d->nMax, sizeof(double));
+        memcpy(mine, bLocal, sizeof(double) * (size_t)d->nLocal);
+        comm->gather(comm->ctx, mine, d->nMax, all);
+        for (int r = 0; r < R; r++) memcpy(b + offs[r], all + (size_t)r * d->nMax, sizeof(double) * (size_t)counts[r]);
+        free(mine);
+        free(all);
+    } else
+        memcpy(b, bLocal, sizeof(double) * (size_t)n);
     for (int k = 0; k < n; k++) {
         if (d->piv[k] != k) {
             double t = b[k];
@@ -390,13 +572,16 @@ static void lu_solve(const dense_lu *d, double *b)
         for (int j = i + 1; j < n; j++) b[i] -= d->lu[(size_t)i * n + j] * b[j];
         b[i] /= d->lu[(size_t)i * n + i];
     }
+    memcpy(xLocal, b + d->offset, sizeof(double) * (size_t)d->nLocal);
+    free(b);
 }
 
 static int imin(int a, int b) { return a < b ? a : b; }
 
 /* GAMGSolver::solve + Vcycle: GAMGSolverSolve.C:59-474 */
 int orc_gamg_solve(const orc_matrix *m, orc_gamg *g, const char *smoother, const orc_controls *c,
-                   double *psi, const double *source, orc_perf *perf, double *hist, int histCap)
+                   double *psi, const double *source, const orc_comm *comm, orc_perf *perf, double *hist,
+                   int histCap)
 {
     memset(perf, 0, sizeof(*perf));
     strcpy(perf->solverName, "GAMG");
@@ -414,19 +599,21 @@ int orc_gamg_solve(const orc_matrix *m, orc_gamg *g, const char *smoother, const
         const double *fd = lev ? lm[lev - 1].diag : m->diag;
         const double *fu = lev ? lm[lev - 1].upper : m->upper;
         const double *fl = lev ? lm[lev - 1].lower : (m->symmetric ? NULL : m->lower);
-        agglomerate_matrix(g, lev, fd, fu, fl, &lm[lev]);
+        const double *fb = lev ? lm[lev - 1].bou : m->bou;
+        const double *fi = lev ? lm[lev - 1].intc : m->intc;
+        agglomerate_matrix(g, lev, fd, fu, fl, fb, fi, &lm[lev]);
     }
     int coarsest = nL - 1;
-    dense_lu *lu = c->directSolveCoarsest ? lu_factor(lm[coarsest].m) : NULL;
+    dense_lu *lu = c->directSolveCoarsest ? lu_factor(lm[coarsest].m, comm) : NULL;
 
     double *Apsi = (double *)calloc((size_t)n, sizeof(double));
     double *finestCorr = (double *)calloc((size_t)n, sizeof(double));
     double *finestRes = (double *)calloc((size_t)n, sizeof(double));
-    orc_amul(m, psi, Apsi, NULL);
-    double normFactor = orc_normFactor(m, psi, source, Apsi, finestCorr, NULL);
+    orc_amul(m, psi, Apsi, comm);
+    double normFactor = orc_normFactor(m, psi, source, Apsi, finestCorr, comm);
     perf->normFactor = normFactor;
     for (int i = 0; i < n; i++) finestRes[i] = source[i] - Apsi[i];
-    perf->initialResidual = orc_gsummag(finestRes, n, NULL) / normFactor;
+    perf->initialResidual = orc_gsummag(finestRes, n, comm) / normFactor;
     perf->finalResidual = perf->initialResidual;
     if (hist && histCap > 0) hist[0] = perf->finalResidual;
 
@@ -439,8 +626,8 @@ int orc_gamg_solve(const orc_matrix *m, orc_gamg *g, const char *smoother, const
         double **src = (double **)calloc((size_t)nL, sizeof(double *));
         int maxSize = n;
         for (int lev = 0; lev < nL; lev++) {
-            corr[lev] = (double *)calloc((size_t)lm[lev].n, sizeof(double));
-            src[lev] = (double *)calloc((size_t)lm[lev].n, sizeof(double));
+            corr[lev] = (double *)calloc((size_t)(lm[lev].n > 0 ? lm[lev].n : 1), sizeof(double));
+            src[lev] = (double *)calloc((size_t)(lm[lev].n > 0 ? lm[lev].n : 1), sizeof(double));
             if (lm[lev].n > maxSize) maxSize = lm[lev].n;
         }
         double *scratch1 = (double *)calloc((size_t)maxSize, sizeof(double));
@@ -454,11 +641,11 @@ int orc_gamg_solve(const orc_matrix *m, orc_gamg *g, const char *smoother, const
                     orc_jacobi_smooth(lm[lev].m, c->omega, corr[lev], src[lev],
                                       imin(c->nPreSweeps + c->preSweepsLevelMultiplier * lev,
                                            c->maxPreSweeps),
-                                      NULL);
+                                      comm);
                     double *ACf = scratch1;
                     if (scaleCorrection && lev < coarsest - 1)
-                        gamg_scale(lm[lev].m, corr[lev], ACf, src[lev]);
-                    orc_amul(lm[lev].m, corr[lev], ACf, NULL);
+                        gamg_scale(lm[lev].m, corr[lev], ACf, src[lev], comm);
+                    orc_amul(lm[lev].m, corr[lev], ACf, comm);
                     for (int i = 0; i < lm[lev].n; i++) src[lev][i] -= ACf[i];
                 }
                 restrict_field(g->restrictAddr[lev + 1], lm[lev].n, lm[lev + 1].n, src[lev],
@@ -466,8 +653,7 @@ int orc_gamg_solve(const orc_matrix *m, orc_gamg *g, const char *smoother, const
             }
             /* solveCoarsestLevel :552-619 */
             if (c->directSolveCoarsest) {
-                memcpy(corr[coarsest], src[coarsest], sizeof(double) * (size_t)lm[coarsest].n);
-                lu_solve(lu, corr[coarsest]);
+                lu_solve(lu, src[coarsest], corr[coarsest], comm);
             } else {
                 orc_controls cc;
                 orc_controls_default(&cc);
@@ -476,32 +662,32 @@ int orc_gamg_solve(const orc_matrix *m, orc_gamg *g, const char *smoother, const
                 orc_perf cp;
                 memset(corr[coarsest], 0, sizeof(double) * (size_t)lm[coarsest].n);
                 orc_solve(lm[coarsest].m, lm[coarsest].lower ? "BICCG" : "ICCG", NULL, &cc,
-                          corr[coarsest], src[coarsest], NULL, &cp, NULL, 0);
+                          corr[coarsest], src[coarsest], comm, &cp, NULL, 0);
             }
             for (int lev = coarsest - 1; lev >= 0; lev--) {
                 double *pre = scratch2;
                 if (c->nPreSweeps) memcpy(pre, corr[lev], sizeof(double) * (size_t)lm[lev].n);
                 prolong_field(g->restrictAddr[lev + 1], lm[lev].n, corr[lev + 1], corr[lev]);
                 double *ACf = scratch1;
-                if (c->interpolateCorrection) gamg_interpolate(lm[lev].m, corr[lev], ACf);
+                if (c->interpolateCorrection) gamg_interpolate(lm[lev].m, corr[lev], ACf, comm);
                 if (scaleCorrection && (c->interpolateCorrection || lev < coarsest - 1))
-                    gamg_scale(lm[lev].m, corr[lev], ACf, src[lev]);
+                    gamg_scale(lm[lev].m, corr[lev], ACf, src[lev], comm);
                 if (c->nPreSweeps)
                     for (int i = 0; i < lm[lev].n; i++) corr[lev][i] += pre[i];
                 orc_jacobi_smooth(lm[lev].m, c->omega, corr[lev], src[lev],
                                   imin(c->nPostSweeps + c->postSweepsLevelMultiplier * lev,
                                        c->maxPostSweeps),
-                                  NULL);
+                                  comm);
             }
             prolong_field(g->restrictAddr[0], n, corr[0], finestCorr);
-            if (c->interpolateCorrection) gamg_interpolate(m, finestCorr, Apsi);
-            if (scaleCorrection) gamg_scale(m, finestCorr, Apsi, finestRes);
+            if (c->interpolateCorrection) gamg_interpolate(m, finestCorr, Apsi, comm);
+            if (scaleCorrection) gamg_scale(m, finestCorr, Apsi, finestRes, comm);
             for (int i = 0; i < n; i++) psi[i] = psi[i] + finestCorr[i];
-            orc_jacobi_smooth(m, c->omega, psi, source, c->nFinestSweeps, NULL);
+            orc_jacobi_smooth(m, c->omega, psi, source, c->nFinestSweeps, comm);
             /* ---- end Vcycle ---- */
-            orc_amul(m, psi, Apsi, NULL);
+            orc_amul(m, psi, Apsi, comm);
             for (int i = 0; i < n; i++) finestRes[i] = source[i] - Apsi[i];
-            perf->finalResidual = orc_gsummag(finestRes, n, NULL) / normFactor;
+            perf->finalResidual = orc_gsummag(finestRes, n, comm) / normFactor;
             if (hist && perf->nIterations + 1 < histCap) hist[perf->nIterations + 1] = perf->finalResidual;
         } while ((++perf->nIterations < c->maxIter && !CONVERGED()) ||
                  perf->nIterations < c->minIter);
@@ -524,6 +710,8 @@ int orc_gamg_solve(const orc_matrix *m, orc_gamg *g, const char *smoother, const
         free(lm[lev].diag);
         free(lm[lev].upper);
         free(lm[lev].lower);
+        free(lm[lev].bou);
+        free(lm[lev].intc);
         orc_matrix_free(lm[lev].m);
     }
     free(lm);

@@ -12,6 +12,7 @@ struct orc_addr {
     int nPatches;      /* coupled (processor / cyclic) patches only */
     int *patchStart;   /* [nPatches+1] offsets into the flat patch arrays */
     int *faceCells;    /* flat */
+    int *neighbRank;   /* [nPatches] or NULL */
 };
 
 struct orc_matrix {
@@ -25,5 +26,6 @@ double orc_gsum(const double *x, int n, const orc_comm *comm);
 double orc_gsumprod(const double *x, const double *y, int n, const orc_comm *comm);
 double orc_gsummag(const double *x, int n, const orc_comm *comm);
 int orc_precond_kind(const char *name, char *printed);
+double *orc_halo_exchange(const orc_addr *a, const double *psi, const orc_comm *comm);
 
 #endif

@@ -22,7 +22,8 @@ def global_case(meshmod, n, kind="P", dims=None):
 
 def oracle_matrix(orc, mesh, coef):
     ps, fc = mesh.patch_start_facecells()
-    a = orc.Addr(mesh.nCells, mesh.lower, mesh.upper, ps, fc)
+    nr = [p.neighbRank for p in mesh.coupled_patches()]
+    a = orc.Addr(mesh.nCells, mesh.lower, mesh.upper, ps, fc, neighbRank=nr if nr else None)
     m = orc.Matrix(a, coef["diag"], coef["upper"], coef["lower"], coef["bou"], coef["int"])
     return a, m
 
@@ -38,15 +39,14 @@ class ThreadExchange:
         self.sums = [None] * nRanks
 
     def comm(self, orc, rank, mesh, nCellsGlobal):
-        patches = mesh.coupled_patches()
-        starts, _ = mesh.patch_start_facecells()
+        nbrs = [p.neighbRank for p in mesh.coupled_patches()]
 
-        def halo(send):
-            self.box[rank] = {p.neighbRank: send[starts[i]:starts[i + 1]].copy() for i, p in enumerate(patches)}
+        def halo(send, starts):
+            self.box[rank] = {nb: send[starts[i]:starts[i + 1]].copy() for i, nb in enumerate(nbrs)}
             self.bar.wait()
             recv = np.empty_like(send)
-            for i, p in enumerate(patches):
-                recv[starts[i]:starts[i + 1]] = self.box[p.neighbRank][rank]
+            for i, nb in enumerate(nbrs):
+                recv[starts[i]:starts[i + 1]] = self.box[nb][rank]
             self.bar.wait()
             return recv
 
@@ -58,7 +58,14 @@ class ThreadExchange:
                 tot = tot + self.sums[r]
             self.bar.wait()
             return tot
-        return orc.PyComm(halo, allsum, nCellsGlobal)
+
+        def gather(mine):
+            self.sums[rank] = mine.copy()
+            self.bar.wait()
+            out = np.stack([self.sums[r] for r in range(self.n)])
+            self.bar.wait()
+            return out
+        return orc.PyComm(halo, allsum, nCellsGlobal, gather, rank, self.n)
 
 
 def run_threads(nRanks, fn):
@@ -87,17 +94,17 @@ def torch_comm(orc, mesh, nCellsGlobal, device="cpu"):
     import torch
     import torch.distributed as dist
     rank = dist.get_rank()
-    patches = mesh.coupled_patches()
-    starts, _ = mesh.patch_start_facecells()
+    world = dist.get_world_size()
+    nbrs = [p.neighbRank for p in mesh.coupled_patches()]
 
-    def halo(send):
+    def halo(send, starts):
         recv = np.empty_like(send)
         reqs, bufs = [], []
-        for i, p in enumerate(patches):
+        for i, nb in enumerate(nbrs):
             s = torch.from_numpy(send[starts[i]:starts[i + 1]].copy())
-            r = torch.empty(starts[i + 1] - starts[i], dtype=torch.float64)
-            reqs.append(dist.isend(s, p.neighbRank, tag=rank))
-            reqs.append(dist.irecv(r, p.neighbRank, tag=p.neighbRank))
+            r = torch.empty(int(starts[i + 1] - starts[i]), dtype=torch.float64)
+            reqs.append(dist.isend(s, nb, tag=rank))
+            reqs.append(dist.irecv(r, nb, tag=nb))
             bufs.append((i, r, s))
         for q in reqs:
             q.wait()
@@ -105,13 +112,18 @@ def torch_comm(orc, mesh, nCellsGlobal, device="cpu"):
             recv[starts[i]:starts[i + 1]] = r.numpy()
         return recv
 
-    def allsum(v):
-        world = dist.get_world_size()
-        t = torch.from_numpy(v.copy())
+    def _allgather(v):
+        t = torch.from_numpy(np.ascontiguousarray(v).copy())
         parts = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(parts, t)
+        return [p.numpy() for p in parts]
+
+    def allsum(v):
         tot = np.zeros_like(v)
-        for p in parts:  # rank-ordered sum
-            tot = tot + p.numpy()
+        for p in _allgather(v):  # rank-ordered sum
+            tot = tot + p
         return tot
-    return orc.PyComm(halo, allsum, nCellsGlobal)
+
+    def gather(mine):
+        return np.stack(_allgather(mine))
+    return orc.PyComm(halo, allsum, nCellsGlobal, gather, rank, world)

@@ -109,3 +109,38 @@ def test_gloo_two_process_pcg():
     p = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
     assert "GLOO-PCG-OK" in p.stdout
+
+
+@pytest.mark.parametrize("nR,kind", [(2, "P"), (4, "P"), (8, "P"), (2, "U")])
+def test_gamg_multi_rank_oracle(meshmod, orc, nR, kind):
+    """Multi-rank GAMG (processor-interface agglomeration, restricted interface coefficients,
+    global coarsest solve): same level count on every rank, matching coarse patch sizes on the
+    two sides of every processor patch, monotone convergence to the single-domain solution."""
+    n = 12
+    gm, gc = dh.global_case(meshmod, n, kind)
+    ga, gM = dh.oracle_matrix(orc, gm, gc)
+    xs = meshmod.cell_field_global(gm, 42)
+    b = gM.amul(xs)
+    ex = dh.ThreadExchange(nR)
+
+    def rank_fn(r):
+        m, c = dh.local_case(meshmod, n, nR, r, kind)
+        a, M = dh.oracle_matrix(orc, m, c)
+        comm = ex.comm(orc, r, m, n ** 3)
+        g = orc.Gamg(a, meshmod.face_area_pair_weights(m), 10, comm=comm)
+        sizes = [(g.ncells(k), g.npatchfaces(k)) for k in range(g.nLevels)]
+        psi, perf, hist = g.solve(M, "GaussSeidel", np.zeros(m.nCells), b[m.cellGlobal], comm=comm,
+                                  tolerance=1e-8, maxIter=100)
+        return m.cellGlobal, psi, perf.nIterations, hist, g.nLevels, sizes, perf.converged
+    res = dh.run_threads(nR, rank_fn)
+    assert len({r[4] for r in res}) == 1 and res[0][4] >= 2      # same number of levels everywhere
+    assert len({r[2] for r in res}) == 1                         # same number of cycles
+    for cg, psi, nit, hist, nl, sizes, conv in res:
+        assert conv and nit < 60
+        assert np.all(np.diff(hist) < 0)
+        np.testing.assert_allclose(psi, xs[cg], atol=1e-5)
+        assert all(nc >= 10 for nc, _ in sizes)
+    # coarse patch faces are created pairwise: totals over the ranks are even on every level
+    for k in range(res[0][4]):
+        assert sum(r[5][k][1] for r in res) % 2 == 0
+    np.testing.assert_allclose(res[0][3], res[-1][3], rtol=0, atol=0)  # identical history on all ranks
