@@ -308,3 +308,66 @@ int comm_halo_exchange(b200ldu_addr *a, double *x, double *sendBuf, const int *s
     if (remote) NCCL_TRY(ncclGroupEnd());
     return B200LDU_OK;
 }
+
+// ---------------------------------------------------------------------------
+// setup-time helpers for the multi-rank GAMG agglomeration (host data, collective calls)
+// ---------------------------------------------------------------------------
+// exchange one int per coupled-patch face with the neighbour rank of each patch
+// (the reference's internalFieldTransfer of the restrict map,
+// GAMGAgglomerateLduAddressing.C:487-500)
+int comm_exchange_patch_ints(b200ldu_ctx *ctx, int nPatches, const int *patchStart, const int *neighbRank,
+                             const int *send, int *recv)
+{
+    int tot = nPatches ? patchStart[nPatches] : 0;
+    if (tot == 0) return B200LDU_OK;
+    if (!ctx->nccl) {
+        b200_set_error("processor patches present but no communicator (b200ldu_comm_init)");
+        return B200LDU_ENCCL;
+    }
+    int *d_s = nullptr, *d_r = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&d_s, sizeof(int) * (size_t)tot));
+    CUDA_TRY(cudaMalloc((void **)&d_r, sizeof(int) * (size_t)tot));
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(d_s, send, sizeof(int) * (size_t)tot, cudaMemcpyHostToDevice, st));
+    NCCL_TRY(ncclGroupStart());
+    for (int p = 0; p < nPatches; p++) {
+        int s = patchStart[p], n = patchStart[p + 1] - s;
+        NCCL_TRY(ncclSend(d_s + s, n, ncclInt, neighbRank[p], (ncclComm_t)ctx->nccl, st));
+        NCCL_TRY(ncclRecv(d_r + s, n, ncclInt, neighbRank[p], (ncclComm_t)ctx->nccl, st));
+    }
+    NCCL_TRY(ncclGroupEnd());
+    CUDA_TRY(cudaMemcpyAsync(recv, d_r, sizeof(int) * (size_t)tot, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(d_s);
+    cudaFree(d_r);
+    return B200LDU_OK;
+}
+
+// all-gather of n doubles per rank (host in, host out: all[r*n + i])
+int comm_allgather_host(b200ldu_ctx *ctx, const double *mine, int n, double *all)
+{
+    if (ctx->nRanks == 1) {
+        memcpy(all, mine, sizeof(double) * (size_t)n);
+        return B200LDU_OK;
+    }
+    double *d_s = nullptr, *d_a = nullptr;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(cudaMalloc((void **)&d_s, sizeof(double) * (size_t)n));
+    CUDA_TRY(cudaMalloc((void **)&d_a, sizeof(double) * (size_t)n * ctx->nRanks));
+    CUDA_TRY(cudaMemcpyAsync(d_s, mine, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    NCCL_TRY(ncclAllGather(d_s, d_a, n, ncclDouble, (ncclComm_t)ctx->nccl, st));
+    CUDA_TRY(cudaMemcpyAsync(all, d_a, sizeof(double) * (size_t)n * ctx->nRanks, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(d_s);
+    cudaFree(d_a);
+    return B200LDU_OK;
+}
+
+// in-stream all-gather of GMAX doubles per rank (device buffers), NCCL fallback of the
+// peer-memory gather used by the coarsest-level solve
+int comm_allgather_dev(b200ldu_ctx *ctx, const double *d_mine, int n, double *d_all)
+{
+    if (ctx->nRanks == 1) return B200LDU_OK;
+    NCCL_TRY(ncclAllGather(d_mine, d_all, n, ncclDouble, (ncclComm_t)ctx->nccl, ctx->stream));
+    return B200LDU_OK;
+}

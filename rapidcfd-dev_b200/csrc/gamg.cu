@@ -17,11 +17,17 @@
 //    convergence decision stay on the device; the coarsest level is solved on the device
 //    with the inverse of the (tiny) coarsest matrix computed once per solve on the host,
 //    instead of a D2H/host-LU/H2D round trip in every cycle (GAMGSolverSolve.C:564-569).
-// Serial (single-rank) only in this round: coupled-patch agglomeration
-// (processorGAMGInterface.C:93-137) is not built yet.
+// Multi-rank: processor interfaces are agglomerated level by level like
+// processorGAMGInterface.C:60-140 (the neighbour side's restrict map is exchanged over NCCL at
+// set-up), interface coefficients are restricted by deterministic segmented sums, every coarse
+// level gets its own peer-memory halo descriptors, and the coarsest level is solved against
+// the inverse of the matrix assembled from ALL ranks (LUscalarMatrix.C:60-160 gathers it on the
+// master; here every rank holds its own rows of the inverse and the right-hand sides are
+// all-gathered through peer memory inside the solve kernel).
 #include <algorithm>
 #include <cmath>
 
+#include "comm.h"
 #include "ldu.h"
 #include "solver_steps.cuh"
 
@@ -42,6 +48,11 @@ struct GamgLevel {
     int *d_faceChildStart = nullptr, *d_faceChild = nullptr; // coarse face -> (fine face << 1 | flip) ascending
     int *d_diagFaceStart = nullptr, *d_diagFace = nullptr;   // coarse cell -> collapsed fine faces ascending
     double *d_diag = nullptr, *d_upper = nullptr, *d_lower = nullptr; // caller-order coarse coefficients
+    // coupled patches of the coarse level
+    int nFinePF = 0, nCoarsePF = 0;
+    std::vector<int> cPatchStart, cFaceCells;
+    int *d_pfChildStart = nullptr, *d_pfChild = nullptr; // coarse patch face -> fine patch faces ascending
+    double *d_bou = nullptr, *d_int = nullptr;
     // level vectors (banded, vecLen of the coarse level)
     double *corr = nullptr, *src = nullptr, *tmp = nullptr, *acf = nullptr, *pre = nullptr;
 };
@@ -50,8 +61,13 @@ struct b200ldu_gamg {
     b200ldu_addr *finest = nullptr;
     int nLevels = 0;
     std::vector<GamgLevel> lev;
-    double *d_inv = nullptr; // inverse of the coarsest matrix (banded order), n x n
-    int invN = 0;
+    double *d_inv = nullptr; // this rank's rows of the inverse of the (global) coarsest matrix
+    int invN = 0;            // global size of the coarsest system
+    // multi-rank coarsest solve
+    std::vector<int> coarsestCounts, coarsestOffs, coarsestNbrCell;
+    int nMaxCoarsest = 0;
+    double *d_gatherAll = nullptr; // NCCL fallback of the peer-memory gather
+    bool metaUploaded = false;
 };
 
 // ---------------------------------------------------------------------------
@@ -178,7 +194,7 @@ static void level_free(GamgLevel &L)
 {
     void *ptrs[] = {L.d_childStart, L.d_child, L.d_pmap, L.d_cellChildStart, L.d_cellChild, L.d_faceChildStart,
                     L.d_faceChild, L.d_diagFaceStart, L.d_diagFace, L.d_diag, L.d_upper, L.d_lower,
-                    L.corr, L.src, L.tmp, L.acf, L.pre};
+                    L.corr, L.src, L.tmp, L.acf, L.pre, L.d_pfChildStart, L.d_pfChild, L.d_bou, L.d_int};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (L.mat) b200ldu_matrix_destroy(L.mat);
@@ -192,6 +208,7 @@ extern "C" int b200ldu_gamg_destroy(b200ldu_gamg *g)
     cudaStreamSynchronize(g->finest->ctx->stream);
     for (auto &L : g->lev) level_free(L);
     if (g->d_inv) cudaFree(g->d_inv);
+    if (g->d_gatherAll) cudaFree(g->d_gatherAll);
     delete g;
     return B200LDU_OK;
 }
@@ -204,15 +221,18 @@ extern "C" int b200ldu_gamg_create(b200ldu_addr *a, const double *faceWeights_h,
         b200_set_error("GAMG: mergeLevels != 1 is not supported yet");
         return B200LDU_EINVAL;
     }
-    if (a->nPatches) {
-        b200_set_error("GAMG: coupled-patch (processor) agglomeration is not built yet; single rank only");
-        return B200LDU_EINVAL;
-    }
+    for (int p = 0; p < a->nPatches; p++)
+        if (a->neighbRank[p] == a->ctx->rank) {
+            b200_set_error("GAMG: cyclic (same-rank) interfaces are not supported");
+            return B200LDU_EINVAL;
+        }
     CUDA_TRY(cudaSetDevice(a->ctx->device));
     b200ldu_gamg *g = new b200ldu_gamg();
     g->finest = a;
     bool forward = forwardInOut ? (*forwardInOut != 0) : true; // pairGAMGAgglomeration.C:33
     std::vector<int> lo = a->l, up = a->u;
+    std::vector<int> fPatchStart = a->patchStart, fFaceCells = a->faceCells; // coupled patches of the fine level
+    const int nPatches = a->nPatches;
     std::vector<double> w(faceWeights_h, faceWeights_h + a->nFaces);
     std::vector<double> centres = a->centres_h;
     const std::vector<int> *finePerm = &a->perm_h;
@@ -222,7 +242,16 @@ extern "C" int b200ldu_gamg_create(b200ldu_addr *a, const double *faceWeights_h,
         std::vector<int> map;
         int nCoarse = -1;
         pair_agglomerate(nFine, lo, up, w, forward, map, nCoarse);
-        if (!(nCoarse >= nCellsInCoarsestLevel)) break; // continueAgglomerating GAMGAgglomeration.C:72-84
+        // continueAgglomerating (GAMGAgglomeration.C:72-84): and-reduced over the ranks
+        {
+            double votes = (nCoarse >= nCellsInCoarsestLevel) ? 0.0 : 1.0;
+            std::vector<double> all((size_t)a->ctx->nRanks, 0.0);
+            rc = comm_allgather_host(a->ctx, &votes, 1, all.data());
+            if (rc != B200LDU_OK) break;
+            double stopVotes = 0;
+            for (double v : all) stopVotes += v;
+            if (stopVotes > 0) break;
+        }
         g->lev.emplace_back();
         GamgLevel &L = g->lev.back();
         L.nFine = nFine;
@@ -244,9 +273,60 @@ extern "C" int b200ldu_gamg_create(b200ldu_addr *a, const double *faceWeights_h,
             for (int C = 0; C < nCoarse; C++)
                 for (int k = 0; k < 3; k++) cc[3 * (size_t)C + k] /= cn[C];
         }
-        rc = b200ldu_addr_create(a->ctx, nCoarse, L.nCoarseFaces, cOwner.data(), cNeigh.data(), 0, nullptr, nullptr,
-                                 nullptr, cc.empty() ? nullptr : cc.data(), &L.addr);
+        // processor interfaces of the coarse level (processorGAMGInterface.C:60-140): unique
+        // (master cell, slave cell) pairs in order of first appearance along every fine patch
+        L.nFinePF = nPatches ? fPatchStart[nPatches] : 0;
+        std::vector<int> pfRestrict(std::max(L.nFinePF, 1));
+        L.cPatchStart.assign((size_t)nPatches + 1, 0);
+        if (nPatches) {
+            std::vector<int> sendMap(L.nFinePF), nbrMap(L.nFinePF);
+            for (int i = 0; i < L.nFinePF; i++) sendMap[i] = map[fFaceCells[i]];
+            rc = comm_exchange_patch_ints(a->ctx, nPatches, fPatchStart.data(), a->neighbRank.data(), sendMap.data(),
+                                          nbrMap.data());
+            if (rc != B200LDU_OK) break;
+            int nC = 0;
+            for (int p = 0; p < nPatches; p++) {
+                const int nb = a->neighbRank[p], me = a->ctx->rank;
+                L.cPatchStart[p] = nC;
+                std::vector<std::pair<int, int>> pairs;
+                for (int i = fPatchStart[p]; i < fPatchStart[p + 1]; i++) {
+                    std::pair<int, int> pr = me < nb ? std::make_pair(sendMap[i], nbrMap[i])
+                                                     : std::make_pair(nbrMap[i], sendMap[i]);
+                    int found = -1;
+                    for (int k = (int)pairs.size() - 1; k >= 0; k--)
+                        if (pairs[k] == pr) {
+                            found = k;
+                            break;
+                        }
+                    if (found < 0) {
+                        found = (int)pairs.size();
+                        pairs.push_back(pr);
+                        L.cFaceCells.push_back(sendMap[i]);
+                    }
+                    pfRestrict[i] = nC + found;
+                }
+                nC += (int)pairs.size();
+            }
+            L.cPatchStart[nPatches] = nC;
+            L.nCoarsePF = nC;
+        }
+        rc = b200ldu_addr_create(a->ctx, nCoarse, L.nCoarseFaces, cOwner.data(), cNeigh.data(), nPatches,
+                                 nPatches ? L.cPatchStart.data() : nullptr, nPatches ? L.cFaceCells.data() : nullptr,
+                                 nPatches ? a->neighbRank.data() : nullptr, cc.empty() ? nullptr : cc.data(), &L.addr);
         if (rc != B200LDU_OK) break;
+        if (nPatches) {
+            std::vector<int> ps, pi;
+            csr_from_map(pfRestrict, L.nCoarsePF, ps, pi);
+            rc = dev_upload(&L.d_pfChildStart, ps);
+            if (rc == B200LDU_OK) rc = dev_upload(&L.d_pfChild, pi);
+            if (rc != B200LDU_OK) break;
+            if (cudaMalloc((void **)&L.d_bou, sizeof(double) * (size_t)std::max(L.nCoarsePF, 1)) != cudaSuccess ||
+                cudaMalloc((void **)&L.d_int, sizeof(double) * (size_t)std::max(L.nCoarsePF, 1)) != cudaSuccess) {
+                b200_set_error("GAMG: out of device memory");
+                rc = B200LDU_ECUDA;
+                break;
+            }
+        }
         rc = b200ldu_matrix_create(L.addr, &L.mat);
         if (rc != B200LDU_OK) break;
         // ---- device maps ----
@@ -310,6 +390,8 @@ extern "C" int b200ldu_gamg_create(b200ldu_addr *a, const double *faceWeights_h,
         w.swap(cw);
         lo.swap(cOwner);
         up.swap(cNeigh);
+        fPatchStart = L.cPatchStart;
+        fFaceCells = L.cFaceCells;
         centres.swap(cc);
         finePerm = &L.addr->perm_h;
         nFine = nCoarse;
@@ -320,6 +402,39 @@ extern "C" int b200ldu_gamg_create(b200ldu_addr *a, const double *faceWeights_h,
         return rc;
     }
     g->nLevels = (int)g->lev.size();
+    // coarsest level across the ranks: sizes, offsets and the neighbour-side cell of every
+    // coarsest processor-patch face (columns of the global matrix, LUscalarMatrix.C:201-270)
+    if (g->nLevels > 0 && a->ctx->nRanks > 1) {
+        GamgLevel &LC = g->lev[g->nLevels - 1];
+        const int R = a->ctx->nRanks;
+        double mine = LC.nCoarse;
+        std::vector<double> all(R);
+        rc = comm_allgather_host(a->ctx, &mine, 1, all.data());
+        if (rc == B200LDU_OK) {
+            g->coarsestCounts.resize(R);
+            g->coarsestOffs.assign(R + 1, 0);
+            g->nMaxCoarsest = 0;
+            for (int r = 0; r < R; r++) {
+                g->coarsestCounts[r] = (int)all[r];
+                g->coarsestOffs[r + 1] = g->coarsestOffs[r] + g->coarsestCounts[r];
+                g->nMaxCoarsest = std::max(g->nMaxCoarsest, g->coarsestCounts[r]);
+            }
+            if (g->nMaxCoarsest > P2P_GMAX) {
+                b200_set_error("GAMG: coarsest level has %d cells on one rank; the multi-rank direct solve "
+                               "supports up to %d (lower nCellsInCoarsestLevel)", g->nMaxCoarsest, P2P_GMAX);
+                rc = B200LDU_EINVAL;
+            }
+        }
+        if (rc == B200LDU_OK && nPatches) {
+            g->coarsestNbrCell.resize(std::max(LC.nCoarsePF, 1));
+            rc = comm_exchange_patch_ints(a->ctx, nPatches, LC.cPatchStart.data(), a->neighbRank.data(),
+                                          LC.cFaceCells.data(), g->coarsestNbrCell.data());
+        }
+        if (rc != B200LDU_OK) {
+            b200ldu_gamg_destroy(g);
+            return rc;
+        }
+    }
     *out = g;
     return B200LDU_OK;
 }
@@ -412,6 +527,87 @@ __global__ void agg_faces_kernel(int nCF, const int *__restrict__ fStart, const 
     if (fLower) cLower[F] = l;
 }
 
+// coarse interface coefficients: sums over the patch face map, ascending fine patch face
+// (agglomerateInterfaceCoefficients, GAMGSolverAgglomerateMatrix.C:325-447)
+__global__ void agg_patch_kernel(int nCPF, const int *__restrict__ start, const int *__restrict__ child,
+                                 const double *__restrict__ fBou, const double *__restrict__ fInt,
+                                 double *__restrict__ cBou, double *__restrict__ cInt)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nCPF) return;
+    double b = 0.0, c = 0.0;
+    for (int k = start[i]; k < start[i + 1]; k++) {
+        b = __dadd_rn(b, fBou[child[k]]);
+        c = __dadd_rn(c, fInt[child[k]]);
+    }
+    cBou[i] = b;
+    cInt[i] = c;
+}
+
+// multi-rank coarsest solve: all-gather the (tiny) coarsest right-hand sides through peer
+// memory -- every rank stores its part + a sequence flag into every rank's gather area -- then
+// apply this rank's rows of the global inverse.  One CTA.  seqs[2] = gather sequence.
+struct P2PGather {
+    int rank = 0, nRanks = 1;
+    double *area[P2P_MAXR] = {nullptr};
+    unsigned long long *flag[P2P_MAXR] = {nullptr};
+    unsigned long long *seq = nullptr;
+    int counts[P2P_MAXR] = {0}, offs[P2P_MAXR + 1] = {0};
+};
+
+__global__ void dense_apply_p2p_kernel(int nLocal, int nGlobal, const double *__restrict__ invRows,
+                                       const double *__restrict__ b, double *__restrict__ x, P2PGather G,
+                                       const int *stop)
+{
+    if (stop && *stop) return;
+    __shared__ double bg[P2P_MAXR * P2P_GMAX];
+    const unsigned long long seq = *G.seq + 1;
+    const int par = (int)(seq & 1);
+    for (int i = threadIdx.x; i < nLocal * G.nRanks; i += blockDim.x) {
+        int r = i / nLocal, k = i % nLocal;
+        G.area[r][(size_t)(par * P2P_MAXR + G.rank) * P2P_GMAX + k] = b[k];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < G.nRanks) {
+        unsigned long long *f = G.flag[threadIdx.x] + (par * P2P_MAXR + G.rank);
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(seq) : "memory");
+        const unsigned long long *w = G.flag[G.rank] + (par * P2P_MAXR + threadIdx.x);
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
+        } while (v < seq);
+    }
+    __syncthreads();
+    for (int r = 0; r < G.nRanks; r++)
+        for (int k = threadIdx.x; k < G.counts[r]; k += blockDim.x)
+            bg[G.offs[r] + k] = __ldcg(G.area[G.rank] + (size_t)(par * P2P_MAXR + r) * P2P_GMAX + k);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nLocal; i += blockDim.x) {
+        double s = 0.0;
+        for (int j = 0; j < nGlobal; j++) s += invRows[(size_t)i * nGlobal + j] * bg[j];
+        x[i] = s;
+    }
+    if (threadIdx.x == 0) *G.seq = seq;
+}
+
+// NCCL fallback: gathered right-hand sides arrive padded to P2P_GMAX per rank
+__global__ void dense_apply_gathered_kernel(int nLocal, int nGlobal, int nRanks, const double *__restrict__ invRows,
+                                            const double *__restrict__ gathered, const int *__restrict__ offs,
+                                            const int *__restrict__ counts, double *__restrict__ x, const int *stop)
+{
+    if (stop && *stop) return;
+    __shared__ double bg[P2P_MAXR * P2P_GMAX];
+    for (int r = 0; r < nRanks; r++)
+        for (int k = threadIdx.x; k < counts[r]; k += blockDim.x) bg[offs[r] + k] = gathered[(size_t)r * P2P_GMAX + k];
+    __syncthreads();
+    for (int i = threadIdx.x; i < nLocal; i += blockDim.x) {
+        double s = 0.0;
+        for (int j = 0; j < nGlobal; j++) s += invRows[(size_t)i * nGlobal + j] * bg[j];
+        x[i] = s;
+    }
+}
+
 // x = Ainv * b for the coarsest level (one CTA; row-major inverse, fixed order)
 __global__ void dense_apply_kernel(int n, const double *__restrict__ inv, const double *__restrict__ b,
                                    double *__restrict__ x, const int *stop)
@@ -480,6 +676,7 @@ static int gamg_build_matrices(Solve &S, b200ldu_gamg *g)
     b200ldu_matrix *fm = S.m;
     cudaStream_t st = S.ctx->stream;
     const double *fd = fm->diag_ext, *fu = fm->upper_ext, *fl = fm->symmetric ? nullptr : fm->lower_ext;
+    const double *fb = fm->bou_ext, *fi = fm->int_ext;
     if (!fd || !fu) {
         b200_set_error("GAMG: matrix coefficients not set");
         return B200LDU_EINVAL;
@@ -490,8 +687,17 @@ static int gamg_build_matrices(Solve &S, b200ldu_gamg *g)
                  L.d_diagFace, fd, fu, fl, L.d_diag);
         LAUNCH1D(agg_faces_kernel, L.nCoarseFaces, st, L.nCoarseFaces, L.d_faceChildStart, L.d_faceChild, fu, fl,
                  L.d_upper, L.d_lower);
+        if (L.nCoarsePF > 0) {
+            LAUNCH1D(agg_patch_kernel, L.nCoarsePF, st, L.nCoarsePF, L.d_pfChildStart, L.d_pfChild, fb, fi, L.d_bou,
+                     L.d_int);
+        }
         KERNEL_CHECK();
-        TRY(b200ldu_matrix_set(L.mat, L.d_diag, L.d_upper, fl ? L.d_lower : nullptr, nullptr, nullptr));
+        // identical boundary/internal interface coefficients on the finest level stay identical
+        const double *cInt = (fm->bou_ext == fm->int_ext) ? L.d_bou : L.d_int;
+        TRY(b200ldu_matrix_set(L.mat, L.d_diag, L.d_upper, fl ? L.d_lower : nullptr, L.nCoarsePF > 0 ? L.d_bou : nullptr,
+                               L.nCoarsePF > 0 ? cInt : nullptr));
+        fb = L.d_bou;
+        fi = L.d_int;
         fd = L.d_diag;
         fu = L.d_upper;
         fl = fl ? L.d_lower : nullptr;
@@ -499,37 +705,70 @@ static int gamg_build_matrices(Solve &S, b200ldu_gamg *g)
     return B200LDU_OK;
 }
 
-// inverse of the coarsest matrix on the host (partial-pivot Gauss-Jordan), uploaded in
-// banded order; stands in for LUscalarMatrix (GAMGSolver.C:144-172)
+// Inverse of the coarsest matrix on the host (partial-pivot Gauss-Jordan), standing in for
+// LUscalarMatrix (GAMGSolver.C:144-172).  Single rank: the local matrix in banded order.
+// Multi rank: every rank contributes its rows of the global matrix (local coefficients +
+// processor-interface coefficients at the neighbour's global column, LUscalarMatrix.C:201-270),
+// all rows are all-gathered, every rank inverts the same matrix and keeps its own rows.
 static int gamg_coarsest_inverse(Solve &S, b200ldu_gamg *g)
 {
     GamgLevel &L = g->lev[g->nLevels - 1];
-    int n = L.nCoarse, nf = L.nCoarseFaces;
+    b200ldu_ctx *ctx = S.ctx;
+    const int R = ctx->nRanks;
+    int n = L.nCoarse, nf = L.nCoarseFaces, npf = L.nCoarsePF;
     bool asym = !S.m->symmetric;
-    std::vector<double> d(n), u(std::max(nf, 1)), l(std::max(nf, 1));
-    cudaStream_t st = S.ctx->stream;
+    std::vector<double> d(std::max(n, 1)), u(std::max(nf, 1)), l(std::max(nf, 1)), bou(std::max(npf, 1));
+    cudaStream_t st = ctx->stream;
     CUDA_TRY(cudaMemcpyAsync(d.data(), L.d_diag, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     if (nf) CUDA_TRY(cudaMemcpyAsync(u.data(), L.d_upper, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
     if (nf && asym) CUDA_TRY(cudaMemcpyAsync(l.data(), L.d_lower, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
+    if (npf) CUDA_TRY(cudaMemcpyAsync(bou.data(), L.d_bou, sizeof(double) * npf, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (!asym) l = u;
     const std::vector<int> &perm = L.addr->perm_h;
-    std::vector<double> A((size_t)n * n, 0.0), I((size_t)n * n, 0.0);
-    for (int c = 0; c < n; c++) {
-        A[(size_t)perm[c] * n + perm[c]] = d[c];
-        I[(size_t)c * n + c] = 1.0;
-    }
+    // global numbering: rank offset + banded row (the solve kernel works on banded vectors)
+    const int me = ctx->rank;
+    const int N = R > 1 ? g->coarsestOffs[R] : n;
+    const int off = R > 1 ? g->coarsestOffs[me] : 0;
+    const int nMax = R > 1 ? g->nMaxCoarsest : n;
+    std::vector<double> rows((size_t)std::max(nMax, 1) * N, 0.0);
+    for (int c = 0; c < n; c++) rows[(size_t)perm[c] * N + off + perm[c]] = d[c];
     for (int f = 0; f < nf; f++) {
         int o = perm[L.addr->l[f]], nb = perm[L.addr->u[f]];
-        A[(size_t)o * n + nb] += u[f];
-        A[(size_t)nb * n + o] += l[f];
+        rows[(size_t)o * N + off + nb] += u[f];
+        rows[(size_t)nb * N + off + o] += l[f];
     }
-    for (int k = 0; k < n; k++) {
+    std::vector<double> A;
+    if (R > 1) {
+        // the neighbour's banded numbering is not known here: the neighbour-side cell index was
+        // exchanged in caller order, so all ranks also gather their perm to translate columns
+        std::vector<double> permD((size_t)nMax, -1.0), permAll((size_t)nMax * R);
+        for (int c = 0; c < n; c++) permD[c] = perm[c];
+        TRY(comm_allgather_host(ctx, permD.data(), nMax, permAll.data()));
+        for (int p = 0; p < L.addr->nPatches; p++) {
+            int nbr = L.addr->neighbRank[p];
+            for (int i = L.cPatchStart[p]; i < L.cPatchStart[p + 1]; i++) {
+                int row = perm[L.cFaceCells[i]];
+                int col = g->coarsestOffs[nbr] + (int)permAll[(size_t)nbr * nMax + g->coarsestNbrCell[i]];
+                rows[(size_t)row * N + col] -= bou[i];
+            }
+        }
+        std::vector<double> all((size_t)R * nMax * N);
+        TRY(comm_allgather_host(ctx, rows.data(), nMax * N, all.data()));
+        A.assign((size_t)N * N, 0.0);
+        for (int r = 0; r < R; r++)
+            for (int i = 0; i < g->coarsestCounts[r]; i++)
+                memcpy(&A[(size_t)(g->coarsestOffs[r] + i) * N], &all[((size_t)r * nMax + i) * N], sizeof(double) * N);
+    } else
+        A = rows;
+    std::vector<double> I((size_t)N * N, 0.0);
+    for (int c = 0; c < N; c++) I[(size_t)c * N + c] = 1.0;
+    for (int k = 0; k < N; k++) {
         int p = k;
-        double mx = fabs(A[(size_t)k * n + k]);
-        for (int i = k + 1; i < n; i++)
-            if (fabs(A[(size_t)i * n + k]) > mx) {
-                mx = fabs(A[(size_t)i * n + k]);
+        double mx = fabs(A[(size_t)k * N + k]);
+        for (int i = k + 1; i < N; i++)
+            if (fabs(A[(size_t)i * N + k]) > mx) {
+                mx = fabs(A[(size_t)i * N + k]);
                 p = i;
             }
         if (mx == 0.0) {
@@ -537,32 +776,35 @@ static int gamg_coarsest_inverse(Solve &S, b200ldu_gamg *g)
             return B200LDU_EINVAL;
         }
         if (p != k)
-            for (int j = 0; j < n; j++) {
-                std::swap(A[(size_t)k * n + j], A[(size_t)p * n + j]);
-                std::swap(I[(size_t)k * n + j], I[(size_t)p * n + j]);
+            for (int j = 0; j < N; j++) {
+                std::swap(A[(size_t)k * N + j], A[(size_t)p * N + j]);
+                std::swap(I[(size_t)k * N + j], I[(size_t)p * N + j]);
             }
-        double piv = 1.0 / A[(size_t)k * n + k];
-        for (int j = 0; j < n; j++) {
-            A[(size_t)k * n + j] *= piv;
-            I[(size_t)k * n + j] *= piv;
+        double piv = 1.0 / A[(size_t)k * N + k];
+        for (int j = 0; j < N; j++) {
+            A[(size_t)k * N + j] *= piv;
+            I[(size_t)k * N + j] *= piv;
         }
-        for (int i = 0; i < n; i++) {
+        for (int i = 0; i < N; i++) {
             if (i == k) continue;
-            double fct = A[(size_t)i * n + k];
+            double fct = A[(size_t)i * N + k];
             if (fct == 0.0) continue;
-            for (int j = 0; j < n; j++) {
-                A[(size_t)i * n + j] -= fct * A[(size_t)k * n + j];
-                I[(size_t)i * n + j] -= fct * I[(size_t)k * n + j];
+            for (int j = 0; j < N; j++) {
+                A[(size_t)i * N + j] -= fct * A[(size_t)k * N + j];
+                I[(size_t)i * N + j] -= fct * I[(size_t)k * N + j];
             }
         }
     }
-    if (g->invN < n) {
+    size_t need = (size_t)std::max(n, 1) * N;
+    if ((size_t)g->invN * g->invN < need || !g->d_inv) {
         if (g->d_inv) cudaFree(g->d_inv);
         g->d_inv = nullptr;
-        CUDA_TRY(cudaMalloc((void **)&g->d_inv, sizeof(double) * (size_t)n * n));
-        g->invN = n;
+        CUDA_TRY(cudaMalloc((void **)&g->d_inv, sizeof(double) * need));
     }
-    CUDA_TRY(cudaMemcpyAsync(g->d_inv, I.data(), sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, st));
+    g->invN = N;
+    CUDA_TRY(cudaMemcpyAsync(g->d_inv, &I[(size_t)off * N], sizeof(double) * (size_t)n * N, cudaMemcpyHostToDevice, st));
+    if (R > 1 && !ctx->p2p && !g->d_gatherAll)
+        CUDA_TRY(cudaMalloc((void **)&g->d_gatherAll, sizeof(double) * (size_t)(R + 1) * P2P_GMAX + sizeof(int) * 64));
     CUDA_TRY(cudaStreamSynchronize(st)); // I goes out of scope
     return B200LDU_OK;
 }
@@ -621,7 +863,39 @@ static int gamg_cycle(void *vp)
     { // solveCoarsestLevel :552-619
         GamgLevel &L = g->lev[coarsest];
         if (c.directSolveCoarsest) {
-            dense_apply_kernel<<<1, 256, 0, st>>>(L.nCoarse, g->d_inv, L.src, L.corr, stop);
+            if (S.ctx->nRanks == 1) {
+                dense_apply_kernel<<<1, 256, 0, st>>>(L.nCoarse, g->d_inv, L.src, L.corr, stop);
+            } else if (S.ctx->p2p) {
+                P2PGather G;
+                G.rank = S.ctx->rank;
+                G.nRanks = S.ctx->nRanks;
+                for (int r = 0; r < G.nRanks; r++) {
+                    G.area[r] = (double *)(S.ctx->peerRegion[r] + P2P_GATHER_OFF);
+                    G.flag[r] = (unsigned long long *)(S.ctx->peerRegion[r] + P2P_GFLAG_OFF);
+                    G.counts[r] = g->coarsestCounts[r];
+                    G.offs[r] = g->coarsestOffs[r];
+                }
+                G.offs[G.nRanks] = g->coarsestOffs[G.nRanks];
+                G.seq = S.ctx->d_seq + 2;
+                dense_apply_p2p_kernel<<<1, 256, 0, st>>>(L.nCoarse, g->invN, g->d_inv, L.src, L.corr, G, stop);
+            } else {
+                // NCCL fallback: pad to P2P_GMAX per rank, all-gather, apply
+                double *mine = g->d_gatherAll + (size_t)S.ctx->nRanks * P2P_GMAX;
+                CUDA_TRY(cudaMemsetAsync(mine, 0, sizeof(double) * P2P_GMAX, st));
+                CUDA_TRY(cudaMemcpyAsync(mine, L.src, sizeof(double) * L.nCoarse, cudaMemcpyDeviceToDevice, st));
+                TRY(comm_allgather_dev(S.ctx, mine, P2P_GMAX, g->d_gatherAll));
+                int *meta = (int *)(g->d_gatherAll + (size_t)(S.ctx->nRanks + 1) * P2P_GMAX);
+                if (!g->metaUploaded) {
+                    std::vector<int> h(64, 0);
+                    for (int r = 0; r <= S.ctx->nRanks; r++) h[r] = g->coarsestOffs[r];
+                    for (int r = 0; r < S.ctx->nRanks; r++) h[32 + r] = g->coarsestCounts[r];
+                    CUDA_TRY(cudaMemcpyAsync(meta, h.data(), sizeof(int) * 64, cudaMemcpyHostToDevice, st));
+                    CUDA_TRY(cudaStreamSynchronize(st));
+                    g->metaUploaded = true;
+                }
+                dense_apply_gathered_kernel<<<1, 256, 0, st>>>(L.nCoarse, g->invN, S.ctx->nRanks, g->d_inv, g->d_gatherAll,
+                                                                meta, meta + 32, L.corr, stop);
+            }
             S.ctx->launches++;
         } else {
             b200_set_error("GAMG: directSolveCoarsest false is not supported yet");

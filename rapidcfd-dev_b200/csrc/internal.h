@@ -68,7 +68,10 @@ constexpr int P2P_MAXR = 8;
 constexpr size_t P2P_MAIL_OFF = 0;        // double mail[2][P2P_MAXR][8]
 constexpr size_t P2P_MAILFLAG_OFF = 2048; // u64 mailFlag[2][P2P_MAXR]
 constexpr size_t P2P_HALOFLAG_OFF = 4096; // u64 haloFlag[P2P_MAXR]   (indexed by source rank)
-constexpr size_t P2P_RECV_OFF = 8192;     // double recv[2][P2P_RECV_CAP]
+constexpr int P2P_GMAX = 64;              // doubles per rank in the coarsest-level gather
+constexpr size_t P2P_GATHER_OFF = 8192;   // double gather[2][P2P_MAXR][P2P_GMAX]
+constexpr size_t P2P_GFLAG_OFF = 8192 + 2 * P2P_MAXR * P2P_GMAX * sizeof(double); // u64 gflag[2][P2P_MAXR]
+constexpr size_t P2P_RECV_OFF = 32768;    // double recv[2][P2P_RECV_CAP]
 constexpr size_t P2P_RECV_CAP = 1u << 20; // doubles per parity
 constexpr size_t P2P_REGION_BYTES = P2P_RECV_OFF + 2 * P2P_RECV_CAP * sizeof(double);
 
@@ -193,7 +196,8 @@ struct b200ldu_matrix {
     double *d_rD = nullptr;   // 1/diag, built lazily per matrix_set
     bool rDValid = false;
     // caller-order pointers kept for faceH (caller owns)
-    const double *upper_ext = nullptr, *lower_ext = nullptr, *diag_ext = nullptr;
+    const double *upper_ext = nullptr, *lower_ext = nullptr, *diag_ext = nullptr, *bou_ext = nullptr,
+                 *int_ext = nullptr;
     // solver workspace (allocated once, reused across solves -- PCGCache.H:9-58)
     std::vector<double *> work;
     double *d_partials = nullptr; // reduction partials

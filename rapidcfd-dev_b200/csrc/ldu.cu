@@ -413,6 +413,8 @@ extern "C" int b200ldu_matrix_set(b200ldu_matrix *m, const double *diag_d, const
     m->haveT = needT;
     m->upper_ext = upper_d;
     m->diag_ext = diag_d;
+    m->bou_ext = bou_d;
+    m->int_ext = int_d;
     m->lower_ext = lo;
     return B200LDU_OK;
 }

@@ -69,6 +69,50 @@ def main():
         dist.barrier()
         if rank == 0:
             print(f"MULTI-GPU-OK {solver} {pre} ranks={world} iterations={perf.nIterations}", flush=True)
+    # ---- GAMG across the ranks: processor-interface agglomeration, restricted interface
+    # coefficients, peer-memory gather for the global coarsest solve ----
+    for kind, kw in (("P", {}), ("U", dict(nPreSweeps=1))):
+        n = 16
+        gm, gc = dh.global_case(meshmod, n, kind)
+        ga, gM = dh.oracle_matrix(orc, gm, gc)
+        xs = meshmod.cell_field_global(gm, 42)
+        b = gM.amul(xs)
+        ctl = dict(tolerance=1e-8, maxIter=60, **kw)
+        ex = dh.ThreadExchange(world)
+
+        def rank_fn(r):
+            m, c = dh.local_case(meshmod, n, world, r, kind)
+            a, M = dh.oracle_matrix(orc, m, c)
+            comm = ex.comm(orc, r, m, n ** 3)
+            g = orc.Gamg(a, meshmod.face_area_pair_weights(m), 10, comm=comm)
+            maps = [g.restrict_addr(k) for k in range(g.nLevels)]
+            sizes = [(g.ncells(k), g.nfaces(k)) for k in range(g.nLevels)]
+            psi, perf, hist = g.solve(M, "GaussSeidel", np.zeros(m.nCells), b[m.cellGlobal], comm=comm, **ctl)
+            return maps, sizes, psi, perf.nIterations, hist
+        omaps, osizes, opsi, onit, ohist = dh.run_threads(world, rank_fn)[rank]
+
+        mesh, coef = dh.local_case(meshmod, n, world, rank, kind)
+        addr = capi.mesh_to_device(ctx, mesh)
+        mat = capi.LduMatrix(addr)
+        d = {k: (t(v) if v is not None and len(v) else None) for k, v in coef.items()}
+        mat.set(d["diag"], d["upper"], d["lower"], d["bou"], d["int"])
+        gg = capi.GamgAgglomeration(addr, meshmod.face_area_pair_weights(mesh), 10)
+        assert gg.nLevels == len(omaps), (gg.nLevels, len(omaps))
+        for k in range(gg.nLevels):
+            assert gg.level_size(k) == osizes[k]
+            assert np.array_equal(gg.restrict_addr(k), omaps[k])
+        psi = torch.zeros(mesh.nCells, dtype=torch.float64, device=dev)
+        perf, hist = mat.solve("GAMG", "GaussSeidel", psi, t(b[mesh.cellGlobal]), gamg=gg, histCap=128, **ctl)
+        assert perf.nIterations == onit, (perf.nIterations, onit)
+        assert np.allclose(hist, ohist, rtol=1e-7, atol=0), (hist, ohist)
+        assert np.allclose(psi.cpu().numpy(), opsi, atol=1e-8)
+        assert np.allclose(psi.cpu().numpy(), xs[mesh.cellGlobal], atol=1e-5)
+        gg.close()
+        mat.close()
+        addr.close()
+        dist.barrier()
+        if rank == 0:
+            print(f"MULTI-GPU-OK GAMG {kind} ranks={world} cycles={perf.nIterations} levels={len(omaps)}", flush=True)
     ctx.close()
     dist.destroy_process_group()
 
