@@ -285,6 +285,13 @@ def main():
         cdt = time.perf_counter() - t0
         cpu = {"value": mesh.nCells * ci / cdt / 1e6, "unit": "Mcell-iters/s", "cores": nT, "kind": "port",
                "sample": f"{n}^3 cells x {ci} PCG(AINV) iterations, oracle OpenMP rows, {cdt:.1f} s"}
+        # stock CPU OpenFOAM numerics for context (true DIC + face-loop Amul, one core = one rank)
+        si = max(2, ci // 2)
+        t0 = time.perf_counter()
+        _, sperf = om.pcg_stock_dic(np.zeros(mesh.nCells), b, tolerance=0.0, maxIter=si - 1)
+        sdt = time.perf_counter() - t0
+        cpu["stock_dic_serial"] = {"value": mesh.nCells * si / sdt / 1e6, "unit": "Mcell-iters/s", "cores": 1,
+                                   "sample": f"{n}^3 cells x {si} PCG(true DIC) iterations, serial, {sdt:.1f} s"}
 
     if rank == 0:
         pcg_bytes = (160 * N + 32 * F)  # per iteration, reference op list with AINV

@@ -195,6 +195,15 @@ int b200ldu_fv_convection_fill(b200ldu_addr *a, const double *weights_d, const d
                                double *lower_d, double *upper_d, double *diag_d);
 int b200ldu_fv_interpolate_linear(b200ldu_addr *a, int nComp, const double *w_d,
                                   const double *vf_d, double *sf_d);
+/* linear surface interpolation fused into the face sums (no F-sized
+ * temporary).  grad_linear == gauss_grad(interpolate_linear(w, vf)) bit for bit, with bvf the
+ * boundary-face values of vf (gaussGrad::calcGrad, gaussGrad.C:256-271); flux_linear is
+ * phi = interpolate(U) & Sf per internal face (icoFoam.C:73-78). */
+int b200ldu_fv_grad_linear(b200ldu_addr *a, int nComp, const double *Sf_d, const double *w_d,
+                           const double *vf_d, const double *bSf_d, const double *bvf_d,
+                           const double *V_d, double *out_d);
+int b200ldu_fv_flux_linear(b200ldu_addr *a, const double *Sf_d, const double *w_d, const double *U_d,
+                           double *phi_d);
 int b200ldu_fv_add_boundary_diag(b200ldu_addr *a, const double *internalCoeffs_d, double *diag_d);
 int b200ldu_fv_add_boundary_source(b200ldu_addr *a, const double *boundaryCoeffs_d,
                                    double *source_d);

@@ -161,6 +161,9 @@ int orc_pcg_omp(const orc_matrix *m, int precondKind, const orc_controls *c, dou
                 const double *source, orc_perf *perf, int nThreads);
 void orc_amul_omp(const orc_matrix *m, const double *psi, double *Apsi, int nThreads);
 int orc_max_threads(void);
+/* stock OpenFOAM-2.3.x numerics (true DIC, face-loop Amul), serial: CPU baseline only */
+int orc_pcg_stock_dic(const orc_matrix *m, const orc_controls *c, double *psi, const double *source,
+                      orc_perf *perf);
 
 #ifdef __cplusplus
 }

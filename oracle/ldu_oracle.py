@@ -124,6 +124,8 @@ def lib():
         L.orc_pcg_omp.restype = C.c_int
         L.orc_pcg_omp.argtypes = [C.c_void_p, C.c_int, C.POINTER(Controls), c_dp, c_dp, C.POINTER(Perf), C.c_int]
         L.orc_amul_omp.argtypes = [C.c_void_p, c_dp, c_dp, C.c_int]
+        L.orc_pcg_stock_dic.restype = C.c_int
+        L.orc_pcg_stock_dic.argtypes = [C.c_void_p, C.POINTER(Controls), c_dp, c_dp, C.POINTER(Perf)]
         L.orc_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -318,6 +320,14 @@ class Matrix:
         k = {"none": 0, "diagonal": 1, "AINV": 2, "DIC": 2, "DILU": 2}[pre]
         nT = nThreads or lib().orc_max_threads()
         lib().orc_pcg_omp(self.h, k, C.byref(c), _d(psi), _d(f64(source)), C.byref(perf), nT)
+        return psi, perf
+
+    def pcg_stock_dic(self, psi0, source, **ctl):
+        """stock OpenFOAM numerics (true DIC + face-loop Amul), serial -- CPU baseline only"""
+        c = controls(**ctl)
+        psi = f64(psi0).copy()
+        perf = Perf()
+        lib().orc_pcg_stock_dic(self.h, C.byref(c), _d(psi), _d(f64(source)), C.byref(perf))
         return psi, perf
 
     def amul_omp(self, psi, nThreads=None):

@@ -61,7 +61,8 @@ EXPORTS = [
     "b200ldu_gamg_restrict_addr",
     "b200ldu_fv_boundary_set", "b200ldu_fv_surface_integrate", "b200ldu_fv_gauss_grad",
     "b200ldu_fv_laplacian_fill", "b200ldu_fv_convection_fill", "b200ldu_fv_interpolate_linear",
-    "b200ldu_fv_add_boundary_diag", "b200ldu_fv_add_boundary_source",
+    "b200ldu_fv_add_boundary_diag", "b200ldu_fv_add_boundary_source", "b200ldu_fv_grad_linear",
+    "b200ldu_fv_flux_linear",
 ]
 
 _lib = None
@@ -123,6 +124,8 @@ def lib():
     L.b200ldu_fv_laplacian_fill.argtypes = [vp, vp, vp, vp, vp]
     L.b200ldu_fv_convection_fill.argtypes = [vp, vp, vp, vp, vp, vp]
     L.b200ldu_fv_interpolate_linear.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.b200ldu_fv_grad_linear.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+    L.b200ldu_fv_flux_linear.argtypes = [vp, vp, vp, vp, vp]
     L.b200ldu_fv_add_boundary_diag.argtypes = [vp, vp, vp]
     L.b200ldu_fv_add_boundary_source.argtypes = [vp, vp, vp]
     _lib = L

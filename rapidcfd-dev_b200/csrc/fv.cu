@@ -300,3 +300,120 @@ extern "C" int b200ldu_fv_add_boundary_source(b200ldu_addr *a, const double *bou
 {
     return add_boundary(a, boundaryCoeffs_d, source_d);
 }
+
+// ---------------------------------------------------------------------------
+// surface interpolation fused into the face sums, so the
+// F-sized interpolated face field (401 MB - 1.2 GB at 256^3) is never written or re-read.
+// gaussGrad::calcGrad = gradf(interpolate(vsf)) (gaussGrad.C:256-271 with the linear scheme,
+// surfaceInterpolationScheme.C:159-240): the face value w*psi[own] + (1-w)*psi[nei] is
+// formed on the fly with the same two rounded products and one add as the unfused pipeline,
+// so the result equals b200ldu_fv_gauss_grad(b200ldu_fv_interpolate_linear(...)) bit for bit.
+// ---------------------------------------------------------------------------
+template <int NC>
+__global__ void grad_linear_kernel(int nCells, const int *__restrict__ ownerStart, const int *__restrict__ upper,
+                                   const int *__restrict__ losortStart, const int *__restrict__ losort,
+                                   const int *__restrict__ lower, const int *__restrict__ bStart,
+                                   const int *__restrict__ bFaces, const double *__restrict__ Sf,
+                                   const double *__restrict__ w, const double *__restrict__ vf,
+                                   const double *__restrict__ bSf, const double *__restrict__ bvf,
+                                   const double *__restrict__ V, double *__restrict__ out)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    double mine[NC];
+#pragma unroll
+    for (int j = 0; j < NC; j++) mine[j] = vf[(size_t)c * NC + j];
+    double acc[3 * NC];
+#pragma unroll
+    for (int k = 0; k < 3 * NC; k++) acc[k] = 0.0;
+    for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++) {
+        const int n = upper[f];
+        const double ww = w[f], w1 = 1 - ww;
+        const double s[3] = {Sf[(size_t)f * 3], Sf[(size_t)f * 3 + 1], Sf[(size_t)f * 3 + 2]};
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+            const double fv = __dadd_rn(__dmul_rn(ww, mine[j]), __dmul_rn(w1, vf[(size_t)n * NC + j]));
+#pragma unroll
+            for (int i = 0; i < 3; i++) acc[i * NC + j] = __dadd_rn(acc[i * NC + j], __dmul_rn(s[i], fv));
+        }
+    }
+    for (int q = losortStart[c]; q < losortStart[c + 1]; q++) {
+        const int f = losort[q], o = lower[f];
+        const double ww = w[f], w1 = 1 - ww;
+        const double s[3] = {Sf[(size_t)f * 3], Sf[(size_t)f * 3 + 1], Sf[(size_t)f * 3 + 2]};
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+            const double fv = __dadd_rn(__dmul_rn(ww, vf[(size_t)o * NC + j]), __dmul_rn(w1, mine[j]));
+#pragma unroll
+            for (int i = 0; i < 3; i++) acc[i * NC + j] = __dsub_rn(acc[i * NC + j], __dmul_rn(s[i], fv));
+        }
+    }
+    if (bStart)
+        for (int q = bStart[c]; q < bStart[c + 1]; q++) {
+            const int bf = bFaces[q];
+            const double s[3] = {bSf[(size_t)bf * 3], bSf[(size_t)bf * 3 + 1], bSf[(size_t)bf * 3 + 2]};
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < NC; j++)
+                    acc[i * NC + j] = __dadd_rn(acc[i * NC + j], __dmul_rn(s[i], bvf[(size_t)bf * NC + j]));
+        }
+    const double v = V[c];
+#pragma unroll
+    for (int k = 0; k < 3 * NC; k++) out[(size_t)c * 3 * NC + k] = __ddiv_rn(acc[k], v);
+}
+
+extern "C" int b200ldu_fv_grad_linear(b200ldu_addr *a, int nComp, const double *Sf_d, const double *w_d,
+                                      const double *vf_d, const double *bSf_d, const double *bvf_d,
+                                      const double *V_d, double *out_d)
+{
+    if (!a || !Sf_d || !w_d || !vf_d || !V_d || !out_d || (nComp != 1 && nComp != 3)) return B200LDU_EINVAL;
+    if (a->nBFaces && (!bSf_d || !bvf_d)) return B200LDU_EINVAL;
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    const int *bs = a->nBFaces ? a->d_bCellStart : nullptr;
+    dim3 g((a->nCells + 127) / 128), b(128);
+    if (nComp == 1)
+        grad_linear_kernel<1><<<g, b, 0, a->ctx->stream>>>(a->nCells, a->d_ownerStart, a->d_u, a->d_losortStart,
+                                                            a->d_losort, a->d_l, bs, a->d_bCellFaces, Sf_d, w_d, vf_d,
+                                                            bSf_d, bvf_d, V_d, out_d);
+    else
+        grad_linear_kernel<3><<<g, b, 0, a->ctx->stream>>>(a->nCells, a->d_ownerStart, a->d_u, a->d_losortStart,
+                                                            a->d_losort, a->d_l, bs, a->d_bCellFaces, Sf_d, w_d, vf_d,
+                                                            bSf_d, bvf_d, V_d, out_d);
+    a->ctx->launches++;
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}
+
+// phi = interpolate(U) & Sf per internal face (icoFoam.C:73-78 phiHbyA; face-parallel):
+// component-wise linear interpolation, then Sf.x*Ux + Sf.y*Uy + Sf.z*Uz added left to right
+__global__ void flux_linear_kernel(int nFaces, const int *__restrict__ l, const int *__restrict__ u,
+                                   const double *__restrict__ Sf, const double *__restrict__ w,
+                                   const double *__restrict__ U, double *__restrict__ phi)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nFaces) return;
+    const double ww = w[f], w1 = 1 - ww;
+    const int o = l[f], n = u[f];
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double fv = __dadd_rn(__dmul_rn(ww, U[(size_t)o * 3 + k]), __dmul_rn(w1, U[(size_t)n * 3 + k]));
+        const double p = __dmul_rn(Sf[(size_t)f * 3 + k], fv);
+        acc = k == 0 ? p : __dadd_rn(acc, p);
+    }
+    phi[f] = acc;
+}
+
+extern "C" int b200ldu_fv_flux_linear(b200ldu_addr *a, const double *Sf_d, const double *w_d, const double *U_d,
+                                      double *phi_d)
+{
+    if (!a || !Sf_d || !w_d || !U_d || !phi_d) return B200LDU_EINVAL;
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    if (a->nFaces == 0) return B200LDU_OK;
+    flux_linear_kernel<<<(a->nFaces + 255) / 256, 256, 0, a->ctx->stream>>>(a->nFaces, a->d_l, a->d_u, Sf_d, w_d, U_d,
+                                                                             phi_d);
+    a->ctx->launches++;
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}

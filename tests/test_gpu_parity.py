@@ -286,3 +286,43 @@ def test_fv_face_sums_bit_exact(gpu, meshmod, orc):
     capi.check(L.b200ldu_fv_add_boundary_source(addr.h, dp(t(ic)), dp(ss)))
     assert np.array_equal(ss.cpu().numpy(), orc.add_boundary_source(bfc, ic, d0))
     addr.close()
+
+
+def test_fv_fused_interpolation_bit_exact(gpu, meshmod, orc):
+    """grad / flux with the linear interpolation fused in give the same bits
+    as the unfused oracle pipeline (interpolate_linear, then gauss_grad / Sf & face value)."""
+    capi, ctx, torch = gpu
+    mesh = meshmod.hex_mesh(12, 10, 7)
+    oa = orc.Addr(mesh.nCells, mesh.lower, mesh.upper)
+    addr = capi.mesh_to_device(ctx, mesh)
+    L = capi.lib()
+    dev = ctx.device
+    keep = []
+
+    def t(a):
+        keep.append(torch.from_numpy(np.ascontiguousarray(a)).to(dev))
+        return keep[-1]
+    rng = np.random.default_rng(11)
+    bfc = np.concatenate([p.faceCells for p in mesh.patches]).astype(np.int32)
+    bSf = np.concatenate([p.Sf for p in mesh.patches])
+    capi.check(L.b200ldu_fv_boundary_set(addr.h, len(bfc), bfc.ctypes.data))
+    V = mesh.volumes() * rng.uniform(0.9, 1.1, mesh.nCells)
+    Sf = mesh.Sf() * rng.uniform(0.9, 1.1, (mesh.nFaces, 1)) + rng.uniform(-1e-3, 1e-3, (mesh.nFaces, 3))
+    w = rng.uniform(0.3, 0.7, mesh.nFaces)
+    dp = capi._dp
+    for nc in (1, 3):
+        vf = rng.uniform(-1, 1, (mesh.nCells, nc))
+        bvf = rng.uniform(-1, 1, (len(bfc), nc))
+        ssf = np.asarray(orc.interpolate_linear(oa, w, vf.ravel(), nc)).reshape(mesh.nFaces, nc)
+        ref = orc.gauss_grad(oa, Sf.ravel(), ssf.ravel(), bfc, bSf.ravel(), bvf.ravel(), V, nc)
+        out = torch.empty(mesh.nCells * 3 * nc, dtype=torch.float64, device=dev)
+        capi.check(L.b200ldu_fv_grad_linear(addr.h, nc, dp(t(Sf.ravel())), dp(t(w)), dp(t(vf.ravel())),
+                                            dp(t(bSf.ravel())), dp(t(bvf.ravel())), dp(t(V)), dp(out)))
+        assert np.array_equal(out.cpu().numpy(), ref.ravel())
+    U = rng.uniform(-1, 1, (mesh.nCells, 3))
+    Uf = np.asarray(orc.interpolate_linear(oa, w, U.ravel(), 3)).reshape(mesh.nFaces, 3)
+    phi_ref = (Sf[:, 0] * Uf[:, 0] + Sf[:, 1] * Uf[:, 1]) + Sf[:, 2] * Uf[:, 2]
+    phi = torch.empty(mesh.nFaces, dtype=torch.float64, device=dev)
+    capi.check(L.b200ldu_fv_flux_linear(addr.h, dp(t(Sf.ravel())), dp(t(w)), dp(t(U.ravel())), dp(phi)))
+    assert np.array_equal(phi.cpu().numpy(), phi_ref)
+    addr.close()

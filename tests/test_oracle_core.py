@@ -228,3 +228,16 @@ def test_pcg_omp_matches_serial(meshmod, orc):
     np.testing.assert_allclose(p1, p2, atol=1e-7)
     x = meshmod.cell_field_global(m, 12)
     assert np.array_equal(M.amul(x), M.amul_omp(x, 3))
+
+
+def test_stock_dic_pcg_baseline(meshmod, orc):
+    """The stock-OpenFOAM CPU baseline (true DIC) solves the same system (fewer iterations
+    than the reference's AINV stand-in)."""
+    m, c, a, M = _case(meshmod, orc, 10, "P")
+    A = dense_from_ldu(m.nCells, m.lower, m.upper, c["diag"], c["upper"])
+    xs = meshmod.cell_field_global(m, 42)
+    b = A @ xs
+    psi, perf = M.pcg_stock_dic(np.zeros(m.nCells), b, tolerance=1e-10, maxIter=500)
+    _, pa, _ = M.solve("PCG", "DIC", np.zeros(m.nCells), b, tolerance=1e-10, maxIter=500)
+    assert perf.converged and perf.nIterations <= pa.nIterations
+    np.testing.assert_allclose(psi, xs, atol=1e-6)
