@@ -376,35 +376,38 @@ __global__ void __launch_bounds__(256) scalar_kernel(const double *partials, int
         __shared__ double tot[NRED > 0 ? NRED : 1];
         block_reduce_store<(NRED > 0 ? NRED : 1), 256>(red, tot, 0);
         __syncthreads();
-        if (threadIdx.x == 0) {
-            if (p2p.nRanks > 1) {
-                const unsigned long long seq = *p2p.seq + 1;
-                const int par = (int)(seq & 1);
-                for (int r = 0; r < p2p.nRanks; r++) {
-                    double *dst = p2p.mail[r] + ((size_t)(par * P2P_MAXR + p2p.rank) * 8);
-                    for (int k = 0; k < NRED; k++) dst[k] = tot[k];
-                }
+        if (p2p.nRanks > 1) {
+            // one thread per peer: the R peer stores, flags and waits proceed concurrently, so the
+            // exchange costs one NVLink round trip instead of R
+            __shared__ double got[P2P_MAXR][NRED > 0 ? NRED : 1];
+            const unsigned long long seq = *p2p.seq + 1;
+            const int par = (int)(seq & 1);
+            if (threadIdx.x < p2p.nRanks) {
+                const int r = threadIdx.x;
+                double *dst = p2p.mail[r] + ((size_t)(par * P2P_MAXR + p2p.rank) * 8);
+                for (int k = 0; k < NRED; k++) dst[k] = tot[k];
                 __threadfence_system();
-                for (int r = 0; r < p2p.nRanks; r++) {
-                    unsigned long long *f = p2p.flag[r] + (par * P2P_MAXR + p2p.rank);
-                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(seq) : "memory");
-                }
-                double acc[NRED > 0 ? NRED : 1];
-                for (int k = 0; k < NRED; k++) acc[k] = 0;
-                for (int r = 0; r < p2p.nRanks; r++) { // rank order => same bits everywhere
-                    const unsigned long long *f = p2p.flag[p2p.rank] + (par * P2P_MAXR + r);
-                    unsigned long long v;
-                    do {
-                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-                    } while (v < seq);
-                    const double *src = p2p.mail[p2p.rank] + ((size_t)(par * P2P_MAXR + r) * 8);
-                    for (int k = 0; k < NRED; k++) acc[k] += __ldcg(src + k);
-                }
-                for (int k = 0; k < NRED; k++) sc->sum[k] = acc[k];
-                *p2p.seq = seq;
-            } else {
-                for (int k = 0; k < NRED; k++) sc->sum[k] = tot[k];
+                unsigned long long *f = p2p.flag[r] + (par * P2P_MAXR + p2p.rank);
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(seq) : "memory");
+                const unsigned long long *w = p2p.flag[p2p.rank] + (par * P2P_MAXR + r);
+                unsigned long long v;
+                do {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
+                } while (v < seq);
+                const double *src = p2p.mail[p2p.rank] + ((size_t)(par * P2P_MAXR + r) * 8);
+                for (int k = 0; k < NRED; k++) got[r][k] = __ldcg(src + k);
             }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int k = 0; k < NRED; k++) {
+                    double acc = 0;
+                    for (int r = 0; r < p2p.nRanks; r++) acc += got[r][k]; // rank order => same bits everywhere
+                    sc->sum[k] = acc;
+                }
+                *p2p.seq = seq;
+            }
+        } else if (threadIdx.x == 0) {
+            for (int k = 0; k < NRED; k++) sc->sum[k] = tot[k];
         }
     }
     if (RUN_LOGIC && threadIdx.x == 0) g(sc);
