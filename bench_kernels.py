@@ -105,7 +105,17 @@ def main():
         sf = torch.empty(F * nc, dtype=torch.float64, device=dev)
         timeit(f"linear interpolate nComp={nc}", 8 * F + 8 * F + 8 * nc * N + 8 * nc * F,
                lambda: capi.check(L.b200ldu_fv_interpolate_linear(addr.h, nc, dp(w), dp(vf), dp(sf))))
-        del ssf, bssf, out, Sf, bSf, g, vf, w, sf
+        # fused: grad(interpolate(vf)) without the F-sized face field (algorithmic bytes of the
+        # fused op: Sf + w + addressing once, vf read, grad written)
+        bvf = torch.rand(nB * nc, dtype=torch.float64, device=dev)
+        timeit(f"fused linear-interpolate + gaussGrad nComp={nc}", 24 * F + 8 * F + 8 * F + 8 * nc * N + 8 * N + 24 * nc * N,
+               lambda: capi.check(L.b200ldu_fv_grad_linear(addr.h, nc, dp(Sf), dp(w), dp(vf), dp(bSf), dp(bvf), dp(V), dp(g))))
+        if nc == 3:
+            phi = torch.empty(F, dtype=torch.float64, device=dev)
+            timeit("fused flux phi = interpolate(U) & Sf", 24 * F + 8 * F + 8 * F + 24 * N + 8 * F,
+                   lambda: capi.check(L.b200ldu_fv_flux_linear(addr.h, dp(Sf), dp(w), dp(vf), dp(phi))))
+            del phi
+        del ssf, bssf, out, Sf, bSf, g, vf, w, sf, bvf
     dc, gm = torch.rand(F, dtype=torch.float64, device=dev), torch.rand(F, dtype=torch.float64, device=dev)
     upp, low = torch.empty(F, dtype=torch.float64, device=dev), torch.empty(F, dtype=torch.float64, device=dev)
     dgo = torch.empty(N, dtype=torch.float64, device=dev)

@@ -233,11 +233,52 @@ static void coarse_interfaces(const orc_addr *fine, const int *rmap, const doubl
 }
 
 /* level loop: pairGAMGAgglomerate.C:31-130 (mergeLevels 1 only) */
+/* combineLevels: GAMGAgglomerateLduAddressing.C:606-765.  Level cur (built on the coarse
+ * addressing of level cur-1) is folded into level cur-1: cell, face and patch-face maps are
+ * composed and the coarser addressing replaces the intermediate one.  As in the reference the
+ * flip of a composed face is the flip of the SECOND step alone (:631), not the exclusive-or of
+ * the two; the flip of a face that collapses into a cell is never read (the reference indexes
+ * the face flip list with a cell label there, :637) and is stored as 0. */
+static void combine_levels(orc_gamg *g, int cur)
+{
+    int prev = cur - 1;
+    int *pr = g->restrictAddr[prev], *cr = g->restrictAddr[cur];
+    int *pf = g->faceRestrict[prev], *cf = g->faceRestrict[cur];
+    unsigned char *pflip = g->faceFlip[prev], *cflip = g->faceFlip[cur];
+    for (int i = 0; i < g->nFineFaces[prev]; i++) {
+        if (pf[i] >= 0) {
+            int mid = pf[i];
+            pf[i] = cf[mid];
+            pflip[i] = cflip[mid];
+        } else {
+            int midCell = -pf[i] - 1;
+            pf[i] = -cr[midCell] - 1;
+            pflip[i] = 0;
+        }
+    }
+    for (int i = 0; i < g->nFineCells[prev]; i++) pr[i] = cr[pr[i]];
+    if (g->patchFaceRestrict[prev] && g->patchFaceRestrict[cur])
+        for (int i = 0; i < g->nFinePatchFaces[prev]; i++)
+            g->patchFaceRestrict[prev][i] = g->patchFaceRestrict[cur][g->patchFaceRestrict[prev][i]];
+    orc_addr_free(g->addr[prev]);
+    g->addr[prev] = g->addr[cur];
+    g->addr[cur] = NULL;
+    free(cr);
+    free(cf);
+    free(cflip);
+    free(g->patchFaceRestrict[cur]);
+    g->restrictAddr[cur] = NULL;
+    g->faceRestrict[cur] = NULL;
+    g->faceFlip[cur] = NULL;
+    g->patchFaceRestrict[cur] = NULL;
+}
+
 orc_gamg *orc_gamg_create(const orc_addr *a, const double *faceWeights,
                           int nCellsInCoarsestLevel, int mergeLevels, int *forwardFlag,
                           const orc_comm *comm)
 {
-    if (mergeLevels != 1) return NULL;
+    if (mergeLevels < 1) return NULL;
+    int nPairLevels = 0;
     orc_gamg *g = (orc_gamg *)calloc(1, sizeof(orc_gamg));
     g->finest = a;
     int fwd_local = 1; /* pairGAMGAgglomeration.C:33 initial forward_ = true */
@@ -289,7 +330,11 @@ orc_gamg *orc_gamg_create(const orc_addr *a, const double *faceWeights,
         free(w);
         w = cw;
         fine = g->addr[lev];
-        g->nLevels++;
+        if (nPairLevels % mergeLevels) /* pairGAMGAgglomerate.C:110-117 */
+            combine_levels(g, lev);
+        else
+            g->nLevels++;
+        nPairLevels++;
     }
     free(w);
     return g;

@@ -87,10 +87,17 @@ __device__ __forceinline__ void block_reduce_store(double (&red)[NRED], double *
 //   void   finish(int r, double acc0, double acc1, a0,b0,a1,b1, double *red)
 //                                                    writes rows r, r+1; adds reductions
 // ---------------------------------------------------------------------------
-template <class Op, bool SHARED>
+// Optional tail: the CTA that finishes last (atomic ticket) runs tail.run(partials, nBands) --
+// the fixed-order sum of the per-band partials, the cross-rank exchange and the scalar logic
+// that would otherwise be a separate one-CTA launch (ops.cuh: ScalarTail).
+struct NoTail {
+    static constexpr bool ACTIVE = false;
+};
+
+template <class Op, bool SHARED, class Tail = NoTail>
 __global__ void __launch_bounds__(ENGINE_THREADS, SHARED ? 3 : 6) engine_kernel(const LayoutDev L,
                                                                 const double *__restrict__ val,
-                                                                Op op)
+                                                                Op op, Tail tail)
 {
     extern __shared__ double smem[];
     if (op.stop && *op.stop) return;
@@ -291,10 +298,27 @@ __global__ void __launch_bounds__(ENGINE_THREADS, SHARED ? 3 : 6) engine_kernel(
             L.seqs[1] = haloSeqNow;
         }
     }
+    if constexpr (Tail::ACTIVE) {
+        // ticket = one acq_rel atomic by thread 0 after the CTA barrier: the barrier orders the
+        // partial stores of threads 0..NRED-1 before it (cumulativity), so no per-thread fence
+        // -- a __threadfence() by all 256 threads would drain every vector store of the band.
+        __shared__ int amLast;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned *cnt = tail.counter();
+            unsigned prev;
+            asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(cnt) : "memory");
+            const bool last = prev + 1 == (unsigned)L.nBands;
+            if (last) *cnt = 0; // every band has drawn its ticket: ready for the next launch
+            amLast = last;
+        }
+        __syncthreads();
+        if (amLast) tail.run(op.partials, L.nBands);
+    }
 }
 
-template <class Op, bool SHARED>
-int engine_launch_impl(b200ldu_addr *a, const double *val, const Op &op)
+template <class Op, bool SHARED, class Tail = NoTail>
+int engine_launch_impl(b200ldu_addr *a, const double *val, const Op &op, const Tail &tail = Tail())
 {
     const LayoutDev &L = a->L;
     size_t smem = sizeof(double) * (size_t)((L.bandRows + L.maxHalo + 1) & ~1) * (Op::NVEC > 0 ? Op::NVEC : (SHARED ? 1 : 0));
@@ -303,12 +327,12 @@ int engine_launch_impl(b200ldu_addr *a, const double *val, const Op &op)
     // the kernel also owns a little static shared memory (reduction scratch): opt in to
     // large dynamic shared memory well before the 48 KB default limit
     if (smem > 40 * 1024 && smem > configured) {
-        CUDA_TRY(cudaFuncSetAttribute(engine_kernel<Op, SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(engine_kernel<Op, SHARED, Tail>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
         configured = smem;
     }
     int grid = L.nBands + ((op.waitHalo && L.nPackChunks > 0) ? L.nPackChunks : 0);
-    engine_kernel<Op, SHARED><<<grid, ENGINE_THREADS, smem, a->ctx->stream>>>(L, val, op);
+    engine_kernel<Op, SHARED, Tail><<<grid, ENGINE_THREADS, smem, a->ctx->stream>>>(L, val, op, tail);
     a->ctx->launches++;
     KERNEL_CHECK();
     return B200LDU_OK;
@@ -323,9 +347,10 @@ int engine_launch(b200ldu_addr *a, const double *val, const Op &op)
 
 // matrix sweep: shared-coefficient layout when the matrix uses it (symmetric, not transposed
 // with distinct interface coefficients), else the general layout
-template <class Op>
-int engine_launch_m(b200ldu_matrix *m, bool transpose, const Op &op)
+template <class Op, class Tail = NoTail>
+int engine_launch_m(b200ldu_matrix *m, bool transpose, const Op &op, const Tail &tail = Tail())
 {
-    if (m->shared && !(transpose && m->haveT)) return engine_launch_impl<Op, true>(m->a, m->d_valSh, op);
-    return engine_launch_impl<Op, false>(m->a, transpose ? m->d_valT : m->d_val, op);
+    if (m->shared && !(transpose && m->haveT))
+        return engine_launch_impl<Op, true, Tail>(m->a, m->d_valSh, op, tail);
+    return engine_launch_impl<Op, false, Tail>(m->a, transpose ? m->d_valT : m->d_val, op, tail);
 }

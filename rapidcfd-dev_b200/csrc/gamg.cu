@@ -217,8 +217,8 @@ extern "C" int b200ldu_gamg_create(b200ldu_addr *a, const double *faceWeights_h,
                                    int mergeLevels, int *forwardInOut, b200ldu_gamg **out)
 {
     if (!a || !faceWeights_h || !out) return B200LDU_EINVAL;
-    if (mergeLevels != 1) {
-        b200_set_error("GAMG: mergeLevels != 1 is not supported yet");
+    if (mergeLevels < 1) {
+        b200_set_error("GAMG: mergeLevels must be >= 1");
         return B200LDU_EINVAL;
     }
     for (int p = 0; p < a->nPatches; p++)
@@ -235,13 +235,136 @@ extern "C" int b200ldu_gamg_create(b200ldu_addr *a, const double *faceWeights_h,
     const int nPatches = a->nPatches;
     std::vector<double> w(faceWeights_h, faceWeights_h + a->nFaces);
     std::vector<double> centres = a->centres_h;
-    const std::vector<int> *finePerm = &a->perm_h;
     int nFine = a->nCells;
     int rc = B200LDU_OK;
-    while ((int)g->lev.size() < MAX_LEVELS - 1) {
-        std::vector<int> map;
+
+    // One pairing step on the host (pairGAMGAgglomerate.C:46-107): maps from the current fine
+    // level to the next coarser one.  With mergeLevels > 1 consecutive steps are composed
+    // (combineLevels) before the device structures of the level are built.
+    struct HostStep {
+        int nFine = 0, nFineFaces = 0, nCoarse = 0, nCoarseFaces = 0, nFinePF = 0, nCoarsePF = 0;
+        std::vector<int> map, faceRestrict, cOwner, cNeigh, pfRestrict, cPatchStart, cFaceCells;
+        std::vector<unsigned char> faceFlip;
+        std::vector<double> cc;
+    };
+
+    // build the device side of a finished level
+    auto finalize = [&](HostStep &H) -> int {
+        g->lev.emplace_back();
+        GamgLevel &L = g->lev.back();
+        b200ldu_addr *fineAddr = g->lev.size() >= 2 ? g->lev[g->lev.size() - 2].addr : a;
+        const std::vector<int> &finePerm = fineAddr->perm_h, &fiperm = fineAddr->iperm_h;
+        L.nFine = H.nFine;
+        L.nFineFaces = H.nFineFaces;
+        L.nCoarse = H.nCoarse;
+        L.nCoarseFaces = H.nCoarseFaces;
+        L.nFinePF = H.nFinePF;
+        L.nCoarsePF = H.nCoarsePF;
+        L.restrictAddr.swap(H.map);
+        L.faceRestrict.swap(H.faceRestrict);
+        L.faceFlip.swap(H.faceFlip);
+        L.cPatchStart.swap(H.cPatchStart);
+        L.cFaceCells.swap(H.cFaceCells);
+        const std::vector<int> &map = L.restrictAddr;
+        const int nCoarse = L.nCoarse, nFineL = L.nFine;
+        int r = b200ldu_addr_create(a->ctx, nCoarse, L.nCoarseFaces, H.cOwner.data(), H.cNeigh.data(), nPatches,
+                                    nPatches ? L.cPatchStart.data() : nullptr, nPatches ? L.cFaceCells.data() : nullptr,
+                                    nPatches ? a->neighbRank.data() : nullptr, H.cc.empty() ? nullptr : H.cc.data(),
+                                    &L.addr);
+        if (r != B200LDU_OK) return r;
+        if (nPatches) {
+            std::vector<int> ps, pi;
+            csr_from_map(H.pfRestrict, L.nCoarsePF, ps, pi);
+            TRY(dev_upload(&L.d_pfChildStart, ps));
+            TRY(dev_upload(&L.d_pfChild, pi));
+            if (cudaMalloc((void **)&L.d_bou, sizeof(double) * (size_t)std::max(L.nCoarsePF, 1)) != cudaSuccess ||
+                cudaMalloc((void **)&L.d_int, sizeof(double) * (size_t)std::max(L.nCoarsePF, 1)) != cudaSuccess) {
+                b200_set_error("GAMG: out of device memory");
+                return B200LDU_ECUDA;
+            }
+        }
+        TRY(b200ldu_matrix_create(L.addr, &L.mat));
+        // ---- device maps ----
+        {
+            std::vector<int> cs, ci;
+            csr_from_map(map, nCoarse, cs, ci); // coarse cell -> fine cells ascending
+            TRY(dev_upload(&L.d_cellChildStart, cs));
+            TRY(dev_upload(&L.d_cellChild, ci));
+            // banded versions
+            const std::vector<int> &cperm = L.addr->perm_h, &ciperm = L.addr->iperm_h;
+            const int nPadC = L.addr->L.nPad, nPadF = fineAddr->L.nPad;
+            std::vector<int> bs((size_t)nPadC + 1, 0), bi(std::max(nFineL, 1));
+            for (int R = 0; R < nPadC; R++) {
+                int C = ciperm[R];
+                int cntC = C >= 0 ? cs[C + 1] - cs[C] : 0;
+                bs[R + 1] = bs[R] + cntC;
+                for (int k = 0; k < cntC; k++) bi[bs[R] + k] = finePerm[ci[cs[C] + k]];
+            }
+            std::vector<int> pm(nPadF, -1);
+            for (int q = 0; q < nPadF; q++)
+                if (fiperm[q] >= 0) pm[q] = cperm[map[fiperm[q]]];
+            TRY(dev_upload(&L.d_childStart, bs));
+            TRY(dev_upload(&L.d_child, bi));
+            TRY(dev_upload(&L.d_pmap, pm));
+            // face maps (caller order)
+            std::vector<int> fmap(L.nFineFaces), dmap(L.nFineFaces);
+            for (int f = 0; f < L.nFineFaces; f++) {
+                fmap[f] = L.faceRestrict[f] >= 0 ? L.faceRestrict[f] : -1;
+                dmap[f] = L.faceRestrict[f] < 0 ? -1 - L.faceRestrict[f] : -1;
+            }
+            std::vector<int> fs, fi, ds, di;
+            csr_from_map(fmap, L.nCoarseFaces, fs, fi);
+            csr_from_map(dmap, nCoarse, ds, di);
+            for (int k = 0; k < fs[L.nCoarseFaces]; k++) fi[k] = (fi[k] << 1) | (L.faceFlip[fi[k]] ? 1 : 0);
+            TRY(dev_upload(&L.d_faceChildStart, fs));
+            TRY(dev_upload(&L.d_faceChild, fi));
+            TRY(dev_upload(&L.d_diagFaceStart, ds));
+            TRY(dev_upload(&L.d_diagFace, di));
+        }
+        size_t nf = (size_t)std::max(L.nCoarseFaces, 1);
+        if (cudaMalloc((void **)&L.d_diag, sizeof(double) * (size_t)nCoarse) != cudaSuccess ||
+            cudaMalloc((void **)&L.d_upper, sizeof(double) * nf) != cudaSuccess ||
+            cudaMalloc((void **)&L.d_lower, sizeof(double) * nf) != cudaSuccess) {
+            b200_set_error("GAMG: out of device memory");
+            return B200LDU_ECUDA;
+        }
+        for (double **v : {&L.corr, &L.src, &L.tmp, &L.acf, &L.pre}) TRY(addr_alloc_vec(L.addr, v));
+        return B200LDU_OK;
+    };
+
+    // combineLevels (GAMGAgglomerateLduAddressing.C:606-765): fold step N (built on the coarse side
+    // of P) into P.  The flip of a composed face is the flip of the second step alone, as in the
+    // reference (:631); a face that collapses into a cell carries no flip.
+    auto combine = [&](HostStep &P, HostStep &N) {
+        for (int f = 0; f < P.nFineFaces; f++) {
+            if (P.faceRestrict[f] >= 0) {
+                const int mid = P.faceRestrict[f];
+                P.faceRestrict[f] = N.faceRestrict[mid];
+                P.faceFlip[f] = N.faceFlip[mid];
+            } else {
+                P.faceRestrict[f] = -N.map[-P.faceRestrict[f] - 1] - 1;
+                P.faceFlip[f] = 0;
+            }
+        }
+        for (int c = 0; c < P.nFine; c++) P.map[c] = N.map[P.map[c]];
+        for (int i = 0; i < P.nFinePF; i++) P.pfRestrict[i] = N.pfRestrict[P.pfRestrict[i]];
+        P.nCoarse = N.nCoarse;
+        P.nCoarseFaces = N.nCoarseFaces;
+        P.nCoarsePF = N.nCoarsePF;
+        P.cOwner.swap(N.cOwner);
+        P.cNeigh.swap(N.cNeigh);
+        P.cPatchStart.swap(N.cPatchStart);
+        P.cFaceCells.swap(N.cFaceCells);
+        P.cc.swap(N.cc);
+    };
+
+    HostStep pend;
+    bool havePend = false;
+    int nPairLevels = 0;
+    while ((int)g->lev.size() + (havePend ? 1 : 0) < MAX_LEVELS - 1) {
+        HostStep H;
         int nCoarse = -1;
-        pair_agglomerate(nFine, lo, up, w, forward, map, nCoarse);
+        pair_agglomerate(nFine, lo, up, w, forward, H.map, nCoarse);
         // continueAgglomerating (GAMGAgglomeration.C:72-84): and-reduced over the ranks
         {
             double votes = (nCoarse >= nCellsInCoarsestLevel) ? 0.0 : 1.0;
@@ -252,42 +375,37 @@ extern "C" int b200ldu_gamg_create(b200ldu_addr *a, const double *faceWeights_h,
             for (double v : all) stopVotes += v;
             if (stopVotes > 0) break;
         }
-        g->lev.emplace_back();
-        GamgLevel &L = g->lev.back();
-        L.nFine = nFine;
-        L.nFineFaces = (int)lo.size();
-        L.nCoarse = nCoarse;
-        std::vector<int> cOwner, cNeigh;
-        coarse_addressing(lo, up, map, nCoarse, cOwner, cNeigh, L.faceRestrict, L.faceFlip);
-        L.nCoarseFaces = (int)cOwner.size();
-        L.restrictAddr = map;
+        H.nFine = nFine;
+        H.nFineFaces = (int)lo.size();
+        H.nCoarse = nCoarse;
+        coarse_addressing(lo, up, H.map, nCoarse, H.cOwner, H.cNeigh, H.faceRestrict, H.faceFlip);
+        H.nCoarseFaces = (int)H.cOwner.size();
         // coarse centres = mean of the children (only used to pick the band renumbering)
-        std::vector<double> cc;
         if (!centres.empty()) {
-            cc.assign((size_t)3 * nCoarse, 0.0);
+            H.cc.assign((size_t)3 * nCoarse, 0.0);
             std::vector<int> cn(nCoarse, 0);
             for (int c = 0; c < nFine; c++) {
-                for (int k = 0; k < 3; k++) cc[3 * (size_t)map[c] + k] += centres[3 * (size_t)c + k];
-                cn[map[c]]++;
+                for (int k = 0; k < 3; k++) H.cc[3 * (size_t)H.map[c] + k] += centres[3 * (size_t)c + k];
+                cn[H.map[c]]++;
             }
             for (int C = 0; C < nCoarse; C++)
-                for (int k = 0; k < 3; k++) cc[3 * (size_t)C + k] /= cn[C];
+                for (int k = 0; k < 3; k++) H.cc[3 * (size_t)C + k] /= cn[C];
         }
         // processor interfaces of the coarse level (processorGAMGInterface.C:60-140): unique
         // (master cell, slave cell) pairs in order of first appearance along every fine patch
-        L.nFinePF = nPatches ? fPatchStart[nPatches] : 0;
-        std::vector<int> pfRestrict(std::max(L.nFinePF, 1));
-        L.cPatchStart.assign((size_t)nPatches + 1, 0);
+        H.nFinePF = nPatches ? fPatchStart[nPatches] : 0;
+        H.pfRestrict.assign(std::max(H.nFinePF, 1), 0);
+        H.cPatchStart.assign((size_t)nPatches + 1, 0);
         if (nPatches) {
-            std::vector<int> sendMap(L.nFinePF), nbrMap(L.nFinePF);
-            for (int i = 0; i < L.nFinePF; i++) sendMap[i] = map[fFaceCells[i]];
+            std::vector<int> sendMap(H.nFinePF), nbrMap(H.nFinePF);
+            for (int i = 0; i < H.nFinePF; i++) sendMap[i] = H.map[fFaceCells[i]];
             rc = comm_exchange_patch_ints(a->ctx, nPatches, fPatchStart.data(), a->neighbRank.data(), sendMap.data(),
                                           nbrMap.data());
             if (rc != B200LDU_OK) break;
             int nC = 0;
             for (int p = 0; p < nPatches; p++) {
                 const int nb = a->neighbRank[p], me = a->ctx->rank;
-                L.cPatchStart[p] = nC;
+                H.cPatchStart[p] = nC;
                 std::vector<std::pair<int, int>> pairs;
                 for (int i = fPatchStart[p]; i < fPatchStart[p + 1]; i++) {
                     std::pair<int, int> pr = me < nb ? std::make_pair(sendMap[i], nbrMap[i])
@@ -301,101 +419,39 @@ extern "C" int b200ldu_gamg_create(b200ldu_addr *a, const double *faceWeights_h,
                     if (found < 0) {
                         found = (int)pairs.size();
                         pairs.push_back(pr);
-                        L.cFaceCells.push_back(sendMap[i]);
+                        H.cFaceCells.push_back(sendMap[i]);
                     }
-                    pfRestrict[i] = nC + found;
+                    H.pfRestrict[i] = nC + found;
                 }
                 nC += (int)pairs.size();
             }
-            L.cPatchStart[nPatches] = nC;
-            L.nCoarsePF = nC;
+            H.cPatchStart[nPatches] = nC;
+            H.nCoarsePF = nC;
         }
-        rc = b200ldu_addr_create(a->ctx, nCoarse, L.nCoarseFaces, cOwner.data(), cNeigh.data(), nPatches,
-                                 nPatches ? L.cPatchStart.data() : nullptr, nPatches ? L.cFaceCells.data() : nullptr,
-                                 nPatches ? a->neighbRank.data() : nullptr, cc.empty() ? nullptr : cc.data(), &L.addr);
-        if (rc != B200LDU_OK) break;
-        if (nPatches) {
-            std::vector<int> ps, pi;
-            csr_from_map(pfRestrict, L.nCoarsePF, ps, pi);
-            rc = dev_upload(&L.d_pfChildStart, ps);
-            if (rc == B200LDU_OK) rc = dev_upload(&L.d_pfChild, pi);
-            if (rc != B200LDU_OK) break;
-            if (cudaMalloc((void **)&L.d_bou, sizeof(double) * (size_t)std::max(L.nCoarsePF, 1)) != cudaSuccess ||
-                cudaMalloc((void **)&L.d_int, sizeof(double) * (size_t)std::max(L.nCoarsePF, 1)) != cudaSuccess) {
-                b200_set_error("GAMG: out of device memory");
-                rc = B200LDU_ECUDA;
-                break;
-            }
-        }
-        rc = b200ldu_matrix_create(L.addr, &L.mat);
-        if (rc != B200LDU_OK) break;
-        // ---- device maps ----
-        {
-            std::vector<int> cs, ci;
-            csr_from_map(map, nCoarse, cs, ci); // coarse cell -> fine cells ascending
-            rc = dev_upload(&L.d_cellChildStart, cs);
-            if (rc == B200LDU_OK) rc = dev_upload(&L.d_cellChild, ci);
-            if (rc != B200LDU_OK) break;
-            // banded versions
-            const std::vector<int> &cperm = L.addr->perm_h, &ciperm = L.addr->iperm_h;
-            int nPadC = L.addr->L.nPad, nPadF = (int)(finePerm == &a->perm_h ? a->L.nPad : g->lev[g->lev.size() - 2].addr->L.nPad);
-            std::vector<int> bs((size_t)nPadC + 1, 0), bi(std::max(nFine, 1));
-            for (int R = 0; R < nPadC; R++) {
-                int C = ciperm[R];
-                int cntC = C >= 0 ? cs[C + 1] - cs[C] : 0;
-                bs[R + 1] = bs[R] + cntC;
-                for (int k = 0; k < cntC; k++) bi[bs[R] + k] = (*finePerm)[ci[cs[C] + k]];
-            }
-            const std::vector<int> &fiperm = (finePerm == &a->perm_h) ? a->iperm_h : g->lev[g->lev.size() - 2].addr->iperm_h;
-            std::vector<int> pm(nPadF, -1);
-            for (int r = 0; r < nPadF; r++)
-                if (fiperm[r] >= 0) pm[r] = cperm[map[fiperm[r]]];
-            rc = dev_upload(&L.d_childStart, bs);
-            if (rc == B200LDU_OK) rc = dev_upload(&L.d_child, bi);
-            if (rc == B200LDU_OK) rc = dev_upload(&L.d_pmap, pm);
-            if (rc != B200LDU_OK) break;
-            // face maps (caller order)
-            std::vector<int> fmap(L.nFineFaces), dmap(L.nFineFaces);
-            for (int f = 0; f < L.nFineFaces; f++) {
-                fmap[f] = L.faceRestrict[f] >= 0 ? L.faceRestrict[f] : -1;
-                dmap[f] = L.faceRestrict[f] < 0 ? -1 - L.faceRestrict[f] : -1;
-            }
-            std::vector<int> fs, fi, ds, di;
-            csr_from_map(fmap, L.nCoarseFaces, fs, fi);
-            csr_from_map(dmap, nCoarse, ds, di);
-            for (int k = 0; k < fs[L.nCoarseFaces]; k++) fi[k] = (fi[k] << 1) | (L.faceFlip[fi[k]] ? 1 : 0);
-            rc = dev_upload(&L.d_faceChildStart, fs);
-            if (rc == B200LDU_OK) rc = dev_upload(&L.d_faceChild, fi);
-            if (rc == B200LDU_OK) rc = dev_upload(&L.d_diagFaceStart, ds);
-            if (rc == B200LDU_OK) rc = dev_upload(&L.d_diagFace, di);
-            if (rc != B200LDU_OK) break;
-        }
-        size_t nf = (size_t)std::max(L.nCoarseFaces, 1);
-        if (cudaMalloc((void **)&L.d_diag, sizeof(double) * (size_t)nCoarse) != cudaSuccess ||
-            cudaMalloc((void **)&L.d_upper, sizeof(double) * nf) != cudaSuccess ||
-            cudaMalloc((void **)&L.d_lower, sizeof(double) * nf) != cudaSuccess) {
-            b200_set_error("GAMG: out of device memory");
-            rc = B200LDU_ECUDA;
-            break;
-        }
-        for (double **v : {&L.corr, &L.src, &L.tmp, &L.acf, &L.pre}) {
-            rc = addr_alloc_vec(L.addr, v);
-            if (rc != B200LDU_OK) break;
-        }
-        if (rc != B200LDU_OK) break;
-        // restrictFaceField of the weights for the next level (pairGAMGAgglomerate.C:86-107)
-        std::vector<double> cw(L.nCoarseFaces, 0.0);
-        for (int f = 0; f < L.nFineFaces; f++)
-            if (L.faceRestrict[f] >= 0) cw[L.faceRestrict[f]] += w[f];
+        // restrictFaceField of the weights for the next step (pairGAMGAgglomerate.C:86-107)
+        std::vector<double> cw(H.nCoarseFaces, 0.0);
+        for (int f = 0; f < H.nFineFaces; f++)
+            if (H.faceRestrict[f] >= 0) cw[H.faceRestrict[f]] += w[f];
         w.swap(cw);
-        lo.swap(cOwner);
-        up.swap(cNeigh);
-        fPatchStart = L.cPatchStart;
-        fFaceCells = L.cFaceCells;
-        centres.swap(cc);
-        finePerm = &L.addr->perm_h;
+        lo = H.cOwner;
+        up = H.cNeigh;
+        fPatchStart = H.cPatchStart;
+        fFaceCells = H.cFaceCells;
+        centres = H.cc;
         nFine = nCoarse;
+        if (nPairLevels % mergeLevels) { // pairGAMGAgglomerate.C:110-117
+            combine(pend, H);
+        } else {
+            if (havePend) {
+                rc = finalize(pend);
+                if (rc != B200LDU_OK) break;
+            }
+            pend = std::move(H);
+            havePend = true;
+        }
+        nPairLevels++;
     }
+    if (rc == B200LDU_OK && havePend) rc = finalize(pend);
     if (forwardInOut) *forwardInOut = forward ? 1 : 0;
     if (rc != B200LDU_OK) {
         b200ldu_gamg_destroy(g);
@@ -898,8 +954,26 @@ static int gamg_cycle(void *vp)
             }
             S.ctx->launches++;
         } else {
-            b200_set_error("GAMG: directSolveCoarsest false is not supported yet");
-            return B200LDU_EINVAL;
+            // ICCG / BICCG to the GAMG tolerances, from a zero correction (:568-606).  The nested
+            // solve decides its own iteration count, so this mode runs cycle by cycle (no graph;
+            // gamg_solve sets checkEvery = 1): skip the work once the outer solve has stopped.
+            int stopped = 0;
+            CUDA_TRY(cudaMemcpyAsync(&stopped, stop, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (!stopped) {
+                CUDA_TRY(cudaMemsetAsync(L.corr, 0, sizeof(double) * (size_t)L.addr->vecLen, st));
+                b200ldu_controls cc;
+                b200ldu_controls_default(&cc);
+                cc.tolerance = c.tolerance;
+                cc.relTol = c.relTol;
+                b200ldu_perf cp;
+                double *res = nullptr;
+                TRY(solve_banded(L.mat, L.mat->symmetric ? "ICCG" : "BICCG", nullptr, &cc, nullptr, L.corr, L.src, &cp,
+                                 nullptr, 0, &res));
+                if (res != L.corr)
+                    CUDA_TRY(cudaMemcpyAsync(L.corr, res, sizeof(double) * (size_t)L.addr->vecLen,
+                                             cudaMemcpyDeviceToDevice, st));
+            }
         }
     }
     for (int k = coarsest - 1; k >= 0; k--) {
@@ -998,7 +1072,12 @@ int gamg_solve(Solve &S, b200ldu_gamg *g, const char *smoother)
     if (!A.psiBuf[1] || !A.Apsi || !A.finestCorr || !A.finestRes) return B200LDU_ECUDA;
 
     TRY(gamg_build_matrices(S, g));
-    if (S.c.directSolveCoarsest) TRY(gamg_coarsest_inverse(S, g));
+    if (S.c.directSolveCoarsest) {
+        TRY(gamg_coarsest_inverse(S, g));
+    } else {
+        S.useGraph = false; // the coarsest-level Krylov solve synchronises with the host
+        S.c.checkEvery = 1;
+    }
     TRY(mat_amul(fm, false, S.psi, A.Apsi, 0, nullptr, nullptr, nullptr));
     TRY(init_residual(S, S.psi, S.src, A.Apsi, A.finestRes, A.finestCorr, nullptr, nullptr));
     long long maxBodies = S.c.maxIter > S.c.minIter ? S.c.maxIter : S.c.minIter;

@@ -478,42 +478,6 @@ int mat_ainv(b200ldu_matrix *m, bool transpose, const double *r, double *w, bool
     return engine_launch_m(m, transpose, op);
 }
 
-// fused PCG sweeps (ops.cuh PcgAinvOp / PcgAmulOp)
-int mat_pcg_ka(b200ldu_matrix *m, const double *rOld, double *rNew, const double *w, const double *p,
-               double *psi, double *z, const void *sc, double *partials, const int *stop)
-{
-    PcgAinvOp op;
-    op.stop = stop;
-    op.partials = partials;
-    op.rOld = rOld;
-    op.rNew = rNew;
-    op.w = w;
-    op.p = p;
-    op.psi = psi;
-    op.z = z;
-    op.rD = m->d_rD;
-    op.sc = (const SolverScalars *)sc;
-    return engine_launch_m(m, false, op);
-}
-
-int mat_pcg_kb(b200ldu_matrix *m, const double *z, const double *pOld, double *pNew, double *w, const void *sc,
-               double *partials, const int *stop)
-{
-    int wait = 0;
-    TRY(mat_halo(m, pNew, stop, &wait)); // peer-memory path: nothing is launched, the send is fused
-    PcgAmulOp op;
-    op.stop = stop;
-    op.partials = partials;
-    op.waitHalo = wait;
-    op.z = z;
-    op.pOld = pOld;
-    op.pNew = pNew;
-    op.out = w;
-    op.diag = m->d_diag;
-    op.sc = (const SolverScalars *)sc;
-    return engine_launch_m(m, false, op);
-}
-
 int mat_jacobi(b200ldu_matrix *m, double omega, double *x, const double *b, double *out, const int *stop)
 {
     int wait = 0;

@@ -22,7 +22,3 @@ int mat_H(b200ldu_matrix *m, const double *x, double *out);
 int mat_interpolate(b200ldu_matrix *m, double *x, double *out, const int *stop);
 int precond_kind(const char *name, char *printed);
 int smoother_ok(const char *name);
-int mat_pcg_ka(b200ldu_matrix *m, const double *rOld, double *rNew, const double *w, const double *p,
-               double *psi, double *z, const void *sc, double *partials, const int *stop);
-int mat_pcg_kb(b200ldu_matrix *m, const double *z, const double *pOld, double *pNew, double *w, const void *sc,
-               double *partials, const int *stop);

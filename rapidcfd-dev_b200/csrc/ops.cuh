@@ -14,7 +14,8 @@ struct SolverScalars {
     double tolerance, relTol, nCellsGlobal;
     int nIterations, converged, singular, stop;
     int maxIter, minIter, histCap, nSweeps;
-    int bodies, pad_; // fused PCG: iteration bodies whose A.p product has been formed
+    int bodies; // fused PCG: iteration bodies whose A.p product has been formed
+    unsigned tailCount; // ticket counter of the fused scalar tail (engine.cuh)
 };
 
 struct OpBase {
@@ -361,16 +362,15 @@ int ew_launch(b200ldu_ctx *ctx, int n2, const int *stop, double *partials, int *
 //    order -- one kernel, no NCCL call, bit-identical result on every rank; or
 //  * through ncclAllReduce between a sum-only and a logic-only launch (scalar_step_on).
 template <int NRED, bool RUN_LOGIC, class G>
-__global__ void __launch_bounds__(256) scalar_kernel(const double *partials, int nPartials,
-                                                     SolverScalars *sc, G g, P2PRed p2p)
+__device__ __forceinline__ void scalar_body(const double *partials, int nPartials, SolverScalars *sc,
+                                            G &g, const P2PRed &p2p)
 {
-    if (sc->stop) return;
     if (NRED > 0) {
         double red[NRED > 0 ? NRED : 1];
 #pragma unroll
         for (int k = 0; k < (NRED > 0 ? NRED : 1); k++) {
             double s = 0;
-            for (int i = threadIdx.x; i < nPartials; i += 256) s += partials[(size_t)i * NRED + k];
+            for (int i = threadIdx.x; i < nPartials; i += 256) s += __ldcg(partials + (size_t)i * NRED + k);
             red[k] = s;
         }
         __shared__ double tot[NRED > 0 ? NRED : 1];
@@ -412,3 +412,25 @@ __global__ void __launch_bounds__(256) scalar_kernel(const double *partials, int
     }
     if (RUN_LOGIC && threadIdx.x == 0) g(sc);
 }
+
+template <int NRED, bool RUN_LOGIC, class G>
+__global__ void __launch_bounds__(256) scalar_kernel(const double *partials, int nPartials,
+                                                     SolverScalars *sc, G g, P2PRed p2p)
+{
+    if (sc->stop) return;
+    scalar_body<NRED, RUN_LOGIC>(partials, nPartials, sc, g, p2p);
+}
+
+// the same step as the tail of an engine kernel (run by the CTA that finishes last)
+template <int NRED, class G>
+struct ScalarTail {
+    static constexpr bool ACTIVE = true;
+    SolverScalars *sc;
+    G g;
+    P2PRed p2p;
+    __device__ __forceinline__ unsigned *counter() const { return &sc->tailCount; }
+    __device__ __forceinline__ void run(const double *partials, int nPartials)
+    {
+        scalar_body<NRED, true>(partials, nPartials, sc, g, p2p);
+    }
+};

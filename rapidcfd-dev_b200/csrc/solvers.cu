@@ -211,6 +211,45 @@ int solve_pcg(Solve &S, int pk)
 // convergence decision of body k is taken in the first scalar step of body k+1 (the extra
 // preconditioner sweep that has then already run only overwrote scratch).
 // ---------------------------------------------------------------------------
+// fused PCG sweeps (ops.cuh PcgAinvOp / PcgAmulOp), optionally with the scalar step as tail
+template <class Tail>
+static int pcg_ka(b200ldu_matrix *m, const double *rOld, double *rNew, const double *w, const double *p,
+                  double *psi, double *z, const SolverScalars *sc, double *partials, const int *stop,
+                  const Tail &tail)
+{
+    PcgAinvOp op;
+    op.stop = stop;
+    op.partials = partials;
+    op.rOld = rOld;
+    op.rNew = rNew;
+    op.w = w;
+    op.p = p;
+    op.psi = psi;
+    op.z = z;
+    op.rD = m->d_rD;
+    op.sc = sc;
+    return engine_launch_m(m, false, op, tail);
+}
+
+template <class Tail>
+static int pcg_kb(b200ldu_matrix *m, const double *z, const double *pOld, double *pNew, double *w,
+                  const SolverScalars *sc, double *partials, const int *stop, const Tail &tail)
+{
+    int wait = 0;
+    TRY(mat_halo(m, pNew, stop, &wait)); // peer-memory path: nothing is launched, the send is fused
+    PcgAmulOp op;
+    op.stop = stop;
+    op.partials = partials;
+    op.waitHalo = wait;
+    op.z = z;
+    op.pOld = pOld;
+    op.pNew = pNew;
+    op.out = w;
+    op.diag = m->d_diag;
+    op.sc = sc;
+    return engine_launch_m(m, false, op, tail);
+}
+
 int solve_pcg_fused(Solve &S, int pk)
 {
     b200ldu_matrix *m = S.m;
@@ -223,57 +262,78 @@ int solve_pcg_fused(Solve &S, int pk)
     double *pb[2] = {S.vec(0), S.vec(4)}, *w = S.vec(1), *rb[2] = {S.vec(2), S.vec(3)}, *z = S.vec(5);
     if (!pb[0] || !pb[1] || !w || !rb[0] || !rb[1] || !z) return B200LDU_ECUDA;
     const double *rD = m->d_rD;
+    // scalar steps as kernel tails (last-finishing CTA): needs the sums to be combinable inside a
+    // kernel, i.e. one rank or the peer-memory all-reduce.  Opt-in (B200LDU_TAIL=1): measured
+    // slower than the separate one-CTA launches on one GPU ("what did not pay").
+    const char *te = getenv("B200LDU_TAIL");
+    const bool tailOK = (S.ctx->nRanks == 1 || S.ctx->p2p) && (te && atoi(te) != 0);
+    const P2PRed pr = (S.ctx->nRanks > 1 && S.ctx->p2p) ? comm_p2p_red(S.ctx) : P2PRed();
 
     TRY(mat_amul(m, false, psi, w, 0, nullptr, nullptr, nullptr));
     TRY(init_residual(S, psi, b, w, rb[0], pb[0]));
+
+    // scalar step A: closes body k-1 (residual, convergence), then beta of body k
+    auto gA = [=] __device__(SolverScalars *s) {
+        if (s->bodies > 0) {
+            end_of_body(s, hist, s->sum[1]);
+            if (s->stop) return;
+        }
+        s->wArAold = s->wArA;
+        s->wArA = s->sum[0];
+        s->beta = s->wArA / s->wArAold;
+    };
+    // scalar step B: alpha of body k
+    auto gB = [=] __device__(SolverScalars *s) {
+        s->wApA = s->sum[0];
+        if (fabs(s->wApA) / s->normFactor < VSMALL_) { // checkSingularity PCG.C:170
+            s->singular = 1;
+            s->stop = 1;
+            return;
+        }
+        s->alpha = s->wArA / s->wApA;
+        s->bodies++;
+    };
+    const ScalarTail<2, decltype(gA)> tailA{sc, gA, pr};
+    const ScalarTail<1, decltype(gB)> tailB{sc, gB, pr};
 
     auto body = [&](long long k) -> int {
         const double *rOld = rb[k & 1], *pPrev = pb[k & 1];
         double *rNew = rb[(k + 1) & 1], *pNew = pb[(k + 1) & 1];
         int np = a->L.nBands;
-        if (pk == 2) {
-            TRY(mat_pcg_ka(m, rOld, rNew, w, pPrev, psi, z, sc, S.partials, stop));
+        if (pk == 2 && tailOK) {
+            TRY(pcg_ka(m, rOld, rNew, w, pPrev, psi, z, sc, S.partials, stop, tailA));
         } else {
-            TRY(ew_launch<2>(S.ctx, n2, stop, S.partials, &np, [=] __device__(int i, double *red) {
-                double2 r = CV2(rOld)[i];
-                if (sc->bodies > 0) {
-                    const double alpha = sc->alpha;
-                    double2 ww = CV2(w)[i], pp = CV2(pPrev)[i], x = CV2(psi)[i];
-                    r.x = fma(-alpha, ww.x, r.x);
-                    r.y = fma(-alpha, ww.y, r.y);
-                    V2(psi)[i] = make_double2(fma(alpha, pp.x, x.x), fma(alpha, pp.y, x.y));
-                }
-                V2(rNew)[i] = r;
-                double2 zz = r;
-                if (pk == 1) {
-                    double2 d = CV2(rD)[i];
-                    zz = make_double2(__dmul_rn(d.x, r.x), __dmul_rn(d.y, r.y));
-                }
-                V2(z)[i] = zz;
-                red[0] += zz.x * r.x + zz.y * r.y;
-                red[1] += fabs(r.x) + fabs(r.y);
-            }));
+            if (pk == 2) {
+                TRY(pcg_ka(m, rOld, rNew, w, pPrev, psi, z, sc, S.partials, stop, NoTail()));
+            } else {
+                TRY(ew_launch<2>(S.ctx, n2, stop, S.partials, &np, [=] __device__(int i, double *red) {
+                    double2 r = CV2(rOld)[i];
+                    if (sc->bodies > 0) {
+                        const double alpha = sc->alpha;
+                        double2 ww = CV2(w)[i], pp = CV2(pPrev)[i], x = CV2(psi)[i];
+                        r.x = fma(-alpha, ww.x, r.x);
+                        r.y = fma(-alpha, ww.y, r.y);
+                        V2(psi)[i] = make_double2(fma(alpha, pp.x, x.x), fma(alpha, pp.y, x.y));
+                    }
+                    V2(rNew)[i] = r;
+                    double2 zz = r;
+                    if (pk == 1) {
+                        double2 d = CV2(rD)[i];
+                        zz = make_double2(__dmul_rn(d.x, r.x), __dmul_rn(d.y, r.y));
+                    }
+                    V2(z)[i] = zz;
+                    red[0] += zz.x * r.x + zz.y * r.y;
+                    red[1] += fabs(r.x) + fabs(r.y);
+                }));
+            }
+            TRY(scalar_step<2>(S, np, gA));
         }
-        TRY(scalar_step<2>(S, np, [=] __device__(SolverScalars *s) {
-            if (s->bodies > 0) {
-                end_of_body(s, hist, s->sum[1]);
-                if (s->stop) return;
-            }
-            s->wArAold = s->wArA;
-            s->wArA = s->sum[0];
-            s->beta = s->wArA / s->wArAold;
-        }));
-        TRY(mat_pcg_kb(m, z, pPrev, pNew, w, sc, S.partials, stop));
-        TRY(scalar_step<1>(S, a->L.nBands, [=] __device__(SolverScalars *s) {
-            s->wApA = s->sum[0];
-            if (fabs(s->wApA) / s->normFactor < VSMALL_) { // checkSingularity PCG.C:170
-                s->singular = 1;
-                s->stop = 1;
-                return;
-            }
-            s->alpha = s->wArA / s->wApA;
-            s->bodies++;
-        }));
+        if (tailOK) {
+            TRY(pcg_kb(m, z, pPrev, pNew, w, sc, S.partials, stop, tailB));
+        } else {
+            TRY(pcg_kb(m, z, pPrev, pNew, w, sc, S.partials, stop, NoTail()));
+            TRY(scalar_step<1>(S, a->L.nBands, gB));
+        }
         return B200LDU_OK;
     };
     long long mb = (long long)S.c.maxIter + 1 > S.c.minIter ? (long long)S.c.maxIter + 1 : S.c.minIter;
@@ -565,7 +625,18 @@ int solve_banded(b200ldu_matrix *m, const char *solver, const char *pre, const b
     // pinned flags + events
     void *pin = nullptr;
     TRY(ctx_pinned(ctx, 4096, &pin));
-    S.pinnedFlags = (int *)pin;
+    // a solve nested in another one (GAMG coarsest level) polls its own pair of flags
+    static thread_local int depth = 0;
+    struct Depth {
+        int &d;
+        Depth(int &x) : d(x) { d++; }
+        ~Depth() { d--; }
+    } depthGuard(depth);
+    if (depth > 8) {
+        b200_set_error("solve: nesting too deep");
+        return B200LDU_EINVAL;
+    }
+    S.pinnedFlags = (int *)pin + 2 * (depth - 1);
     S.pinnedFlags[0] = S.pinnedFlags[1] = 0;
     CUDA_TRY(cudaEventCreateWithFlags(&S.ev[0], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&S.ev[1], cudaEventDisableTiming));

@@ -71,7 +71,9 @@ def main():
             print(f"MULTI-GPU-OK {solver} {pre} ranks={world} iterations={perf.nIterations}", flush=True)
     # ---- GAMG across the ranks: processor-interface agglomeration, restricted interface
     # coefficients, peer-memory gather for the global coarsest solve ----
-    for kind, kw in (("P", {}), ("U", dict(nPreSweeps=1))):
+    for kind, kw, merge, htol in (("P", {}, 1, 1e-7), ("U", dict(nPreSweeps=1), 1, 1e-7),
+                                  ("U", {}, 2, 1e-7),                        # combineLevels across processor patches
+                                  ("P", dict(directSolveCoarsest=0), 1, 1e-4)):  # ICCG on the coarsest level
         n = 16
         gm, gc = dh.global_case(meshmod, n, kind)
         ga, gM = dh.oracle_matrix(orc, gm, gc)
@@ -84,7 +86,7 @@ def main():
             m, c = dh.local_case(meshmod, n, world, r, kind)
             a, M = dh.oracle_matrix(orc, m, c)
             comm = ex.comm(orc, r, m, n ** 3)
-            g = orc.Gamg(a, meshmod.face_area_pair_weights(m), 10, comm=comm)
+            g = orc.Gamg(a, meshmod.face_area_pair_weights(m), 10, mergeLevels=merge, comm=comm)
             maps = [g.restrict_addr(k) for k in range(g.nLevels)]
             sizes = [(g.ncells(k), g.nfaces(k)) for k in range(g.nLevels)]
             psi, perf, hist = g.solve(M, "GaussSeidel", np.zeros(m.nCells), b[m.cellGlobal], comm=comm, **ctl)
@@ -96,7 +98,7 @@ def main():
         mat = capi.LduMatrix(addr)
         d = {k: (t(v) if v is not None and len(v) else None) for k, v in coef.items()}
         mat.set(d["diag"], d["upper"], d["lower"], d["bou"], d["int"])
-        gg = capi.GamgAgglomeration(addr, meshmod.face_area_pair_weights(mesh), 10)
+        gg = capi.GamgAgglomeration(addr, meshmod.face_area_pair_weights(mesh), 10, mergeLevels=merge)
         assert gg.nLevels == len(omaps), (gg.nLevels, len(omaps))
         for k in range(gg.nLevels):
             assert gg.level_size(k) == osizes[k]
@@ -104,15 +106,16 @@ def main():
         psi = torch.zeros(mesh.nCells, dtype=torch.float64, device=dev)
         perf, hist = mat.solve("GAMG", "GaussSeidel", psi, t(b[mesh.cellGlobal]), gamg=gg, histCap=128, **ctl)
         assert perf.nIterations == onit, (perf.nIterations, onit)
-        assert np.allclose(hist, ohist, rtol=1e-7, atol=0), (hist, ohist)
-        assert np.allclose(psi.cpu().numpy(), opsi, atol=1e-8)
+        assert np.allclose(hist, ohist, rtol=htol, atol=0), (hist, ohist)
+        assert np.allclose(psi.cpu().numpy(), opsi, atol=1e-8 if htol < 1e-6 else 1e-6)
         assert np.allclose(psi.cpu().numpy(), xs[mesh.cellGlobal], atol=1e-5)
         gg.close()
         mat.close()
         addr.close()
         dist.barrier()
         if rank == 0:
-            print(f"MULTI-GPU-OK GAMG {kind} ranks={world} cycles={perf.nIterations} levels={len(omaps)}", flush=True)
+            print(f"MULTI-GPU-OK GAMG {kind} ranks={world} cycles={perf.nIterations} levels={len(omaps)} "
+                  f"mergeLevels={merge} {kw}", flush=True)
     ctx.close()
     dist.destroy_process_group()
 

@@ -111,8 +111,10 @@ def test_gloo_two_process_pcg():
     assert "GLOO-PCG-OK" in p.stdout
 
 
-@pytest.mark.parametrize("nR,kind", [(2, "P"), (4, "P"), (8, "P"), (2, "U")])
-def test_gamg_multi_rank_oracle(meshmod, orc, nR, kind):
+@pytest.mark.parametrize("nR,kind,opts", [(2, "P", {}), (4, "P", {}), (8, "P", {}), (2, "U", {}),
+                                          (2, "P", dict(mergeLevels=2)), (4, "U", dict(mergeLevels=2)),
+                                          (2, "P", dict(directSolveCoarsest=0))])
+def test_gamg_multi_rank_oracle(meshmod, orc, nR, kind, opts):
     """Multi-rank GAMG (processor-interface agglomeration, restricted interface coefficients,
     global coarsest solve): same level count on every rank, matching coarse patch sizes on the
     two sides of every processor patch, monotone convergence to the single-domain solution."""
@@ -127,10 +129,11 @@ def test_gamg_multi_rank_oracle(meshmod, orc, nR, kind):
         m, c = dh.local_case(meshmod, n, nR, r, kind)
         a, M = dh.oracle_matrix(orc, m, c)
         comm = ex.comm(orc, r, m, n ** 3)
-        g = orc.Gamg(a, meshmod.face_area_pair_weights(m), 10, comm=comm)
+        g = orc.Gamg(a, meshmod.face_area_pair_weights(m), 10, mergeLevels=opts.get("mergeLevels", 1), comm=comm)
         sizes = [(g.ncells(k), g.npatchfaces(k)) for k in range(g.nLevels)]
+        kw = {k: v for k, v in opts.items() if k != "mergeLevels"}
         psi, perf, hist = g.solve(M, "GaussSeidel", np.zeros(m.nCells), b[m.cellGlobal], comm=comm,
-                                  tolerance=1e-8, maxIter=100)
+                                  tolerance=1e-8, maxIter=100, **kw)
         return m.cellGlobal, psi, perf.nIterations, hist, g.nLevels, sizes, perf.converged
     res = dh.run_threads(nR, rank_fn)
     assert len({r[4] for r in res}) == 1 and res[0][4] >= 2      # same number of levels everywhere

@@ -25,4 +25,4 @@ def test_multi_gpu_solvers(world):
     p = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), capture_output=True,
                        text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-4000:]
-    assert p.stdout.count("MULTI-GPU-OK") == 7
+    assert p.stdout.count("MULTI-GPU-OK") == 9

@@ -72,6 +72,64 @@ def test_gamg_converges(meshmod, orc, kind, kw):
     assert len(hist) == perf.nIterations + 1
 
 
+def test_merge_levels_compose_pair_steps(meshmod, orc):
+    """mergeLevels 2 (combineLevels, GAMGAgglomerateLduAddressing.C:606-765): level k is the
+    composition of pair steps 2k and 2k+1 of the mergeLevels-1 hierarchy (the pairing itself
+    sees the same addressing and weights in the same order)."""
+    m = meshmod.hex_mesh(12, 10, 8)
+    a = orc.Addr(m.nCells, m.lower, m.upper)
+    w = meshmod.face_area_pair_weights(m)
+    g1 = orc.Gamg(a, w, 10, mergeLevels=1)
+    g2 = orc.Gamg(a, w, 10, mergeLevels=2)
+    assert g2.nLevels == (g1.nLevels + 1) // 2
+    fine_l, fine_u = m.lower, m.upper
+    for k in range(g2.nLevels):
+        r = g1.restrict_addr(2 * k)
+        if 2 * k + 1 < g1.nLevels:
+            r = g1.restrict_addr(2 * k + 1)[r]
+            last = 2 * k + 1
+        else:
+            last = 2 * k
+        assert np.array_equal(g2.restrict_addr(k), r)
+        assert g2.ncells(k) == g1.ncells(last) and g2.nfaces(k) == g1.nfaces(last)
+        la2, la1 = g2.level_addr(k), g1.level_addr(last)
+        assert np.array_equal(la2.lower(), la1.lower()) and np.array_equal(la2.upper(), la1.upper())
+        # composed face map is consistent with the composed cell map
+        fr = g2.face_restrict_addr(k)
+        same = r[fine_l] == r[fine_u]
+        assert np.array_equal(fr < 0, same)
+        assert np.array_equal(-1 - fr[same], r[fine_l][same])
+        cl, cu = la2.lower(), la2.upper()
+        kk = ~same
+        assert np.array_equal(cl[fr[kk]], np.minimum(r[fine_l][kk], r[fine_u][kk]))
+        assert np.array_equal(cu[fr[kk]], np.maximum(r[fine_l][kk], r[fine_u][kk]))
+        fine_l, fine_u = cl, cu
+    assert g2.forward == g1.forward
+
+
+@pytest.mark.parametrize("kind", ["P", "U"])
+def test_gamg_merge_levels_and_krylov_coarsest_converge(meshmod, orc, kind):
+    m = meshmod.hex_mesh(12, 12, 12)
+    c = meshmod.pressure_laplacian(m) if kind == "P" else meshmod.momentum_matrix(m)
+    a = orc.Addr(m.nCells, m.lower, m.upper)
+    M = orc.Matrix(a, c["diag"], c["upper"], c["lower"])
+    A = dense_from_ldu(m.nCells, m.lower, m.upper, c["diag"], c["upper"], c["lower"])
+    xs = meshmod.cell_field_global(m, 42)
+    b = A @ xs
+    w = meshmod.face_area_pair_weights(m)
+    g1 = orc.Gamg(a, w, 10)
+    _, p_direct, _ = g1.solve(M, "GaussSeidel", np.zeros(m.nCells), b, tolerance=1e-8, maxIter=100)
+    # ICCG / BICCG on the coarsest level (GAMGSolverSolve.C:568-606) instead of the LU solve
+    psi, perf, hist = g1.solve(M, "GaussSeidel", np.zeros(m.nCells), b, tolerance=1e-8, maxIter=100,
+                               directSolveCoarsest=0)
+    assert perf.converged and abs(perf.nIterations - p_direct.nIterations) <= 2
+    np.testing.assert_allclose(psi, xs, atol=1e-5)
+    g2 = orc.Gamg(a, w, 10, mergeLevels=2)
+    psi, perf, hist = g2.solve(M, "GaussSeidel", np.zeros(m.nCells), b, tolerance=1e-8, maxIter=200)
+    assert perf.converged and np.all(np.diff(hist) < 0)
+    np.testing.assert_allclose(psi, xs, atol=1e-5)
+
+
 def test_gamg_no_levels_is_error(meshmod, orc):
     m = meshmod.hex_mesh(2)
     a = orc.Addr(m.nCells, m.lower, m.upper)
