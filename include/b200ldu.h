@@ -94,7 +94,10 @@ int b200ldu_ctx_sync(b200ldu_ctx *ctx);
 /* ---- lduAddressing (LDU/lduAddressing/lduAddressing.H:119-256) ----
  * lower_h/upper_h: HOST int32[nFaces].  Coupled patches (processor / cyclic interfaces,
  * LDU/lduAddressing/lduInterface): patchStart_h[nPatches+1] offsets into faceCells_h,
- * neighbRank_h[nPatches] (rank owning the other side; == own rank for cyclic).
+ * neighbRank_h[nPatches]: for a processor patch the rank owning the other side; for a cyclic
+ * patch -(q+1) where q is the partner patch of this same addressing (cyclicLduInterface::
+ * neighbPatchID, face i pairs with face i; scalar fields, no transform).  Cyclic patches are
+ * served by the Krylov and smooth solvers and all matrix operations; GAMG rejects them.
  * cellCentres_h: optional HOST double[3*nCells] (fvMesh::C()) used only to choose the
  * band renumbering; NULL => graph-distance embedding of the addressing itself. */
 int b200ldu_addr_create(b200ldu_ctx *ctx, int nCells, int nFaces, const int *lower_h,

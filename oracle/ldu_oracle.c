@@ -144,6 +144,16 @@ double *orc_halo_exchange(const orc_addr *a, const double *psi, const orc_comm *
     double *recv = (double *)calloc((size_t)tot, sizeof(double));
     for (int i = 0; i < tot; i++) send[i] = psi[a->faceCells[i]]; /* patchInternalField */
     if (comm && comm->halo) comm->halo(comm->ctx, send, recv, tot, a->nPatches, a->patchStart);
+    /* cyclic patches (neighbRank[p] = -(q+1): partner patch q of this addressing): the neighbour
+     * values are psi at the partner's face cells, cyclicFvPatchField.C:212-231 -- scalars are
+     * not transformed */
+    if (a->neighbRank)
+        for (int p = 0; p < a->nPatches; p++) {
+            if (a->neighbRank[p] >= 0) continue;
+            int q = -a->neighbRank[p] - 1;
+            int n = a->patchStart[p + 1] - a->patchStart[p];
+            for (int i = 0; i < n; i++) recv[a->patchStart[p] + i] = send[a->patchStart[q] + i];
+        }
     free(send);
     return recv;
 }

@@ -270,6 +270,14 @@ __global__ void pack_kernel(int n, const int *__restrict__ rows, const double *_
     if (i < n) send[i] = x[rows[i]];
 }
 
+__global__ void cyclic_fill_kernel(int n, const int *__restrict__ src, const double *__restrict__ x,
+                                   double *__restrict__ tail, const int *stop)
+{
+    if (stop && *stop) return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && src[i] >= 0) tail[i] = x[src[i]];
+}
+
 // x is a banded vector of vecLen doubles.  NCCL path: received neighbour values land in its
 // tail [nPad, nPad + nRecv) where the band halo lists point.  Peer-memory path: they land
 // in this rank's shared receive buffer (the engine reads it for columns >= nPad).
@@ -284,12 +292,18 @@ int comm_halo_exchange(b200ldu_addr *a, double *x, double *sendBuf, const int *s
         if (usedP2P) *usedP2P = 1;
         return B200LDU_OK;
     }
+    bool remote = false;
+    for (int p = 0; p < a->nPatches; p++)
+        if (a->neighbRank[p] >= 0) remote = true;
+    if (a->d_cyclicSrc) { // cyclic partners: x[nPad + face] = x[partner's face cell]
+        cyclic_fill_kernel<<<(nRecv + 255) / 256, 256, 0, ctx->stream>>>(nRecv, a->d_cyclicSrc, x, x + a->L.nPad, stop);
+        ctx->launches++;
+        KERNEL_CHECK();
+    }
+    if (!remote) return B200LDU_OK;
     pack_kernel<<<(nRecv + 255) / 256, 256, 0, ctx->stream>>>(nRecv, a->d_sendRows, x, sendBuf, stop);
     ctx->launches++;
     KERNEL_CHECK();
-    bool remote = false;
-    for (int p = 0; p < a->nPatches; p++)
-        if (a->neighbRank[p] != ctx->rank) remote = true;
     if (remote && !ctx->nccl) {
         b200_set_error("halo exchange: processor patches present but no communicator (b200ldu_comm_init)");
         return B200LDU_ENCCL;
@@ -298,8 +312,10 @@ int comm_halo_exchange(b200ldu_addr *a, double *x, double *sendBuf, const int *s
     for (int p = 0; p < a->nPatches; p++) {
         int s = a->patchStart[p], n = a->patchStart[p + 1] - s;
         int nb = a->neighbRank[p];
+        if (nb < 0) continue; // cyclic: filled above
         if (nb == ctx->rank) {
-            b200_set_error("halo exchange: cyclic (same-rank) interfaces are not supported yet");
+            b200_set_error("halo exchange: patch %d names this rank as its neighbour; cyclic patches are "
+                           "declared with neighbRank = -(partnerPatch + 1)", p);
             return B200LDU_EINVAL;
         }
         NCCL_TRY(ncclSend(sendBuf + s, n, ncclDouble, nb, (ncclComm_t)ctx->nccl, ctx->stream));

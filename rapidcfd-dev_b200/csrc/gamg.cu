@@ -222,8 +222,8 @@ extern "C" int b200ldu_gamg_create(b200ldu_addr *a, const double *faceWeights_h,
         return B200LDU_EINVAL;
     }
     for (int p = 0; p < a->nPatches; p++)
-        if (a->neighbRank[p] == a->ctx->rank) {
-            b200_set_error("GAMG: cyclic (same-rank) interfaces are not supported");
+        if (a->neighbRank[p] < 0 || a->neighbRank[p] == a->ctx->rank) {
+            b200_set_error("GAMG: cyclic interfaces are not supported (Krylov and smooth solvers are)");
             return B200LDU_EINVAL;
         }
     CUDA_TRY(cudaSetDevice(a->ctx->device));

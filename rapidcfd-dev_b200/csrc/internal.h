@@ -155,6 +155,7 @@ struct b200ldu_addr {
     int nPackChunks = 0;
     double nCellsGlobal = 0;
     // caller-order CSR views for the FV face-sum kernels and faceH
+    int *d_cyclicSrc = nullptr; // per coupled-patch face: banded row supplying it (cyclic partner) | -1
     int *d_l = nullptr, *d_u = nullptr, *d_ownerStart = nullptr, *d_losort = nullptr,
         *d_losortStart = nullptr;
     int nBFaces = 0;

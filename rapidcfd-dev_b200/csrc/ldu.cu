@@ -161,6 +161,35 @@ extern "C" int b200ldu_addr_create(b200ldu_ctx *ctx, int nCells, int nFaces, con
         b200ldu_addr_destroy(a);
         return rc;
     }
+    // cyclic patches: neighbRank[p] = -(q+1) pairs patch p with patch q of this addressing, face i
+    // with face i (cyclicLduInterface: neighbPatchID).  Their "received" values are psi at the
+    // partner's face cells, copied on the device (comm_halo_exchange).
+    {
+        bool any = false;
+        for (int p = 0; p < nPatches; p++) any = any || a->neighbRank[p] < 0;
+        if (any) {
+            std::vector<int> src((size_t)a->patchStart[nPatches], -1);
+            for (int p = 0; p < nPatches; p++) {
+                if (a->neighbRank[p] >= 0) continue;
+                const int q = -a->neighbRank[p] - 1;
+                const int n = a->patchStart[p + 1] - a->patchStart[p];
+                if (q < 0 || q >= nPatches || q == p || a->neighbRank[q] != -(p + 1) ||
+                    a->patchStart[q + 1] - a->patchStart[q] != n) {
+                    b200_set_error("addr_create: cyclic patch %d has no matching partner patch", p);
+                    b200ldu_addr_destroy(a);
+                    return B200LDU_EINVAL;
+                }
+                for (int i = 0; i < n; i++)
+                    src[(size_t)a->patchStart[p] + i] = a->perm_h[a->faceCells[(size_t)a->patchStart[q] + i]];
+            }
+            if (cudaMalloc((void **)&a->d_cyclicSrc, sizeof(int) * src.size()) != cudaSuccess ||
+                cudaMemcpy(a->d_cyclicSrc, src.data(), sizeof(int) * src.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+                b200_set_error("addr_create: out of device memory");
+                b200ldu_addr_destroy(a);
+                return B200LDU_ECUDA;
+            }
+        }
+    }
     *out = a;
     return B200LDU_OK;
 }
@@ -172,7 +201,7 @@ extern "C" int b200ldu_addr_destroy(b200ldu_addr *a)
     cudaStreamSynchronize(a->ctx->stream);
     void *ptrs[] = {a->d_sliceStart, a->d_sliceW, a->d_sliceWL, a->d_col, a->d_code, a->d_haloStart,
                     a->d_haloIdx, a->d_perm, a->d_iperm, a->d_sendRows, a->d_l, a->d_u,
-                    a->d_ownerStart, a->d_losort, a->d_losortStart, a->d_bFaceCells,
+                    a->d_ownerStart, a->d_losort, a->d_losortStart, a->d_bFaceCells, a->d_cyclicSrc,
                     a->d_bCellStart, a->d_bCellFaces, a->d_bCells, a->d_packPatches, a->d_packChunks,
                     a->d_shVStart, a->d_shNStart, a->d_shVS, a->d_shWO, a->d_shWN, a->d_shColV, a->d_shCodeV,
                     a->d_shNbr};

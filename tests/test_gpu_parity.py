@@ -326,3 +326,40 @@ def test_fv_fused_interpolation_bit_exact(gpu, meshmod, orc):
     capi.check(L.b200ldu_fv_flux_linear(addr.h, dp(t(Sf.ravel())), dp(t(w)), dp(t(U.ravel())), dp(phi)))
     assert np.array_equal(phi.cpu().numpy(), phi_ref)
     addr.close()
+
+
+@pytest.mark.parametrize("kind", ["P", "U"])
+def test_cyclic_interfaces(gpu, meshmod, orc, kind):
+    """Cyclic coupled patches (neighbRank = -(partner+1)): matrix operations bit-exact with the
+    oracle, Krylov and smooth solvers to the usual history tolerance, GAMG refuses them."""
+    from test_oracle_core import _cyclic_case
+    capi, ctx, torch = gpu
+    m, c, ps, fc, nr, lo, hi = _cyclic_case(meshmod, kind)
+    oa = orc.Addr(m.nCells, m.lower, m.upper, ps, fc, neighbRank=nr)
+    om = orc.Matrix(oa, c["diag"], c["upper"], c["lower"], c["bou"], c["int"])
+    addr = capi.LduAddressing(ctx, m.nCells, m.lower, m.upper, ps, fc, nr, m.cell_centres())
+    mat = capi.LduMatrix(addr)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(ctx.device)
+    mat.set(t(c["diag"]), t(c["upper"]), t(c["lower"]) if c["lower"] is not None else None, t(c["bou"]), t(c["int"]))
+    x, b = meshmod.cell_field_global(m, 3), meshmod.cell_field_global(m, 4)
+    xd, bd = t(x), t(b)
+    assert np.array_equal(mat.Amul(xd).cpu().numpy(), om.amul(x))
+    assert np.array_equal(mat.Tmul(xd).cpu().numpy(), om.tmul(x))
+    assert np.array_equal(mat.sumA(xd).cpu().numpy(), om.sumA())
+    assert np.array_equal(mat.residual(xd, bd).cpu().numpy(), om.residual(x, b))
+    for ns in (1, 2):
+        assert np.array_equal(mat.smooth("GaussSeidel", xd, bd, ns).cpu().numpy(), om.jacobi(x, b, ns))
+    rhs = om.amul(x)
+    solvers = (("PCG", "DIC"), ("PCG", "none")) if kind == "P" else (("PBiCG", "DILU"), ("PBiCGStab", "DILU"))
+    for solver, pre in solvers + (("smoothSolver", "GaussSeidel"),):
+        ctl = dict(tolerance=1e-10, maxIter=400)
+        psi_ref, pr, href = om.solve(solver, pre, np.zeros(m.nCells), rhs, **ctl)
+        psi = torch.zeros(m.nCells, dtype=torch.float64, device=ctx.device)
+        perf, hist = mat.solve(solver, pre, psi, t(rhs), histCap=512, **ctl)
+        assert abs(perf.nIterations - pr.nIterations) <= 1, (solver, perf.nIterations, pr.nIterations)
+        _cmp_hist(hist, href)
+        np.testing.assert_allclose(psi.cpu().numpy(), psi_ref, rtol=0, atol=1e-7)
+    with pytest.raises(Exception, match="cyclic"):
+        capi.GamgAgglomeration(addr, np.ones(m.nFaces), 4)
+    mat.close()
+    addr.close()

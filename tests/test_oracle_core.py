@@ -241,3 +241,63 @@ def test_stock_dic_pcg_baseline(meshmod, orc):
     _, pa, _ = M.solve("PCG", "DIC", np.zeros(m.nCells), b, tolerance=1e-10, maxIter=500)
     assert perf.converged and perf.nIterations <= pa.nIterations
     np.testing.assert_allclose(psi, xs, atol=1e-6)
+
+
+def _cyclic_case(meshmod, kind="P"):
+    """Hex box periodic in x: the x-min and x-max wall faces become a cyclic patch pair."""
+    m = meshmod.hex_mesh(6, 5, 4)
+    c = meshmod.pressure_laplacian(m, pin=False) if kind == "P" else meshmod.momentum_matrix(m)
+    nx, ny, nz = 6, 5, 4
+    jk = np.arange(ny * nz)
+    lo = (jk * nx).astype(np.int32)                # cells i = 0
+    hi = (jk * nx + nx - 1).astype(np.int32)       # cells i = nx-1
+    rng = np.random.default_rng(5)
+    coeff = rng.uniform(0.5, 1.5, ny * nz) * (1.0 if kind == "P" else 0.05)
+    diag = c["diag"].copy()
+    if kind == "P":
+        np.subtract.at(diag, lo, coeff)
+        np.subtract.at(diag, hi, coeff)
+        diag[0] *= 2                                # pin (setReference)
+        bou = np.concatenate([-coeff, -coeff])
+        intc = bou.copy()
+    else:
+        np.add.at(diag, lo, 1.5 * coeff)
+        np.add.at(diag, hi, 0.5 * coeff)
+        bou = np.concatenate([0.5 * coeff, 1.5 * coeff])   # distinct both ways: asymmetric coupling
+        intc = np.concatenate([1.5 * coeff, 0.5 * coeff])
+    ps = np.array([0, ny * nz, 2 * ny * nz], dtype=np.int32)
+    fc = np.concatenate([lo, hi]).astype(np.int32)
+    nr = np.array([-2, -1], dtype=np.int32)        # patch 0 <-> patch 1
+    return m, dict(diag=diag, upper=c["upper"], lower=c["lower"], bou=bou, int=intc), ps, fc, nr, lo, hi
+
+
+@pytest.mark.parametrize("kind", ["P", "U"])
+def test_cyclic_interfaces_vs_dense(meshmod, orc, kind):
+    """cyclic coupled patches (cyclicFvPatchField.C:212-231): Amul/Tmul/residual/sumA and the
+    solvers against a dense matrix that holds the periodic links explicitly."""
+    m, c, ps, fc, nr, lo, hi = _cyclic_case(meshmod, kind)
+    a = orc.Addr(m.nCells, m.lower, m.upper, ps, fc, neighbRank=nr)
+    M = orc.Matrix(a, c["diag"], c["upper"], c["lower"], c["bou"], c["int"])
+    A = dense_from_ldu(m.nCells, m.lower, m.upper, c["diag"], c["upper"], c["lower"])
+    n = len(lo)
+    A[lo, hi] -= c["bou"][:n]          # Apsi[faceCell] -= bou * psi[partner cell]
+    A[hi, lo] -= c["bou"][n:]
+    x = np.random.default_rng(1).standard_normal(m.nCells)
+    np.testing.assert_allclose(M.amul(x), A @ x, rtol=1e-13, atol=1e-13)
+    AT = dense_from_ldu(m.nCells, m.lower, m.upper, c["diag"],
+                        c["lower"] if c["lower"] is not None else c["upper"], c["upper"])
+    AT[lo, hi] -= c["int"][:n]
+    AT[hi, lo] -= c["int"][n:]
+    np.testing.assert_allclose(M.tmul(x), AT @ x, rtol=1e-13, atol=1e-13)
+    if kind == "P":
+        np.testing.assert_allclose(AT, A.T, atol=1e-15)
+    b = A @ x
+    np.testing.assert_allclose(M.residual(x, b), np.zeros(m.nCells), atol=1e-12)
+    np.testing.assert_allclose(M.sumA(), A.sum(axis=1), rtol=1e-12, atol=1e-12)
+    for solver, pre in ((("PCG", "DIC"),) if kind == "P" else (("PBiCG", "DILU"), ("PBiCGStab", "DILU"))):
+        psi, perf, _ = M.solve(solver, pre, np.zeros(m.nCells), b, tolerance=1e-11, maxIter=500)
+        assert perf.converged
+        np.testing.assert_allclose(psi, x, atol=1e-7)
+    psi, perf, _ = M.solve("smoothSolver", "GaussSeidel", np.zeros(m.nCells), b, tolerance=1e-9, maxIter=5000)
+    assert perf.converged
+    np.testing.assert_allclose(psi, x, atol=1e-5)
