@@ -109,6 +109,25 @@ def build_case(meshmod, n, nRanks, rank):
     return mesh, coef, b
 
 
+def host_threads(orc):
+    """Threads for the CPU arm: one per physical core the process may run on.  The row sweeps are
+    memory-bound; on the GPU boxes (2-way SMT) running one thread per logical CPU measured 3x
+    slower (31 vs 95 Mcell-iters/s at 256^3), so SMT siblings are left idle."""
+    n = orc.max_threads()
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False)
+        if phys:
+            n = min(n, phys)
+    except Exception:  # noqa: BLE001
+        pass
+    return max(1, n)
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle's OpenMP PCG (RapidCFD numerics: AINV for DIC) on all host threads."""
     if rank != 0:
@@ -119,7 +138,7 @@ def run_reference(args, rank, world):
     mesh, coef, b = build_case(meshmod, n, 1, 0)
     oa = orc.Addr(mesh.nCells, mesh.lower, mesh.upper)
     om = orc.Matrix(oa, coef["diag"], coef["upper"], None)
-    nT = orc.max_threads()
+    nT = host_threads(orc)
     iters = args.ref_iters
     kw = dict(tolerance=0.0, maxIter=iters - 1)
     for _ in range(args.warmup):
@@ -150,8 +169,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--n", type=int, default=256)
     ap.add_argument("--iters", type=int, default=50, help="PCG iterations per step")
-    ap.add_argument("--ref-iters", type=int, default=4, help="PCG iterations per step of the CPU arm")
-    ap.add_argument("--cpu-baseline-iters", type=int, default=8)
+    ap.add_argument("--ref-iters", type=int, default=50,
+                    help="PCG iterations per step of the CPU arm (same as --iters: per-solve set-up amortised alike)")
+    ap.add_argument("--cpu-baseline-iters", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -278,7 +298,7 @@ def main():
         from oracle import ldu_oracle as orc
         oa = orc.Addr(mesh.nCells, mesh.lower, mesh.upper)
         om = orc.Matrix(oa, coef["diag"], coef["upper"], None)
-        nT = orc.max_threads()
+        nT = host_threads(orc)
         ci = args.cpu_baseline_iters
         t0 = time.perf_counter()
         _, cperf = om.pcg_omp("DIC", np.zeros(mesh.nCells), b, nThreads=nT, tolerance=0.0, maxIter=ci - 1)
@@ -286,7 +306,7 @@ def main():
         cpu = {"value": mesh.nCells * ci / cdt / 1e6, "unit": "Mcell-iters/s", "cores": nT, "kind": "port",
                "sample": f"{n}^3 cells x {ci} PCG(AINV) iterations, oracle OpenMP rows, {cdt:.1f} s"}
         # stock CPU OpenFOAM numerics for context (true DIC + face-loop Amul, one core = one rank)
-        si = max(2, ci // 2)
+        si = max(2, min(8, ci // 2))
         t0 = time.perf_counter()
         _, sperf = om.pcg_stock_dic(np.zeros(mesh.nCells), b, tolerance=0.0, maxIter=si - 1)
         sdt = time.perf_counter() - t0
