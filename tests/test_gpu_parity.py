@@ -358,11 +358,13 @@ def test_cyclic_interfaces(gpu, meshmod, orc, kind):
     for solver, pre in solvers + (("smoothSolver", "GaussSeidel"),):
         # 120 cells: the recurrences reach rounding level within ~20 iterations, so the history is
         # compared over the first 10 at 1e-5 (a wrong or missing interface term shows at O(1))
-        ctl = dict(tolerance=1e-7, maxIter=400)
+        smooth = solver == "smoothSolver"  # damped Jacobi crawls on the Laplacian: fixed 60 sweeps there
+        ctl = dict(tolerance=1e-7, maxIter=60 if smooth else 400)
         psi_ref, pr, href = om.solve(solver, pre, np.zeros(m.nCells), rhs, **ctl)
         psi = torch.zeros(m.nCells, dtype=torch.float64, device=ctx.device)
         perf, hist = mat.solve(solver, pre, psi, t(rhs), histCap=512, **ctl)
-        assert perf.converged and abs(perf.nIterations - pr.nIterations) <= 2, (solver, perf.nIterations, pr.nIterations)
+        assert perf.converged == pr.converged and (smooth or perf.converged)
+        assert abs(perf.nIterations - pr.nIterations) <= 2, (solver, perf.nIterations, pr.nIterations)
         _cmp_hist(hist, href, first=10, rtol=1e-5)
         np.testing.assert_allclose(psi.cpu().numpy(), psi_ref, rtol=0, atol=1e-5)
     with pytest.raises(Exception, match="cyclic"):
