@@ -379,3 +379,12 @@ def mesh_to_device(ctx, mesh, with_centres=True):
         ps = fc = nr = None
     return LduAddressing(ctx, mesh.nCells, mesh.lower, mesh.upper, ps, fc, nr,
                          mesh.cell_centres() if with_centres else None)
+
+
+def polymesh_to_device(ctx, pm, cellCentres=None):
+    """LduAddressing for a foamfile.PolyMesh read from constant/polyMesh (processor and cyclic
+    patches included).  cellCentres: optional [nCells,3] (pm.fv_geometry()["C"]) for the renumbering."""
+    lo, up = pm.ldu()
+    ps, fc, nr = pm.coupled_interface_arrays()
+    return LduAddressing(ctx, pm.nCells, lo, up, ps, fc, nr, cellCentres)
+

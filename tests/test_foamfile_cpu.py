@@ -1,0 +1,312 @@
+"""OpenFOAM on-disk formats (rapidcfd-dev_b200/foamfile.py): dictionary
+syntax + look-up rules, fvSolution -> solver selection, polyMesh files (ascii / binary / gz,
+processor and cyclic patches), geometry against analytic values and the divergence theorem, and an
+unstructured-numbering case read from disk that drives the oracle and the banded-layout builder."""
+import gzip
+import importlib
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+from conftest import dense_from_ldu
+from test_layout_cpu import _check_layout, _layout, capi  # noqa: F401  (capi is a fixture)
+
+
+@pytest.fixture(scope="module")
+def ff():
+    return importlib.import_module("rapidcfd-dev_b200.foamfile")
+
+
+FVSOLUTION = r'''
+/*--------------------------------*- C++ -*----------------------------------*\
+| a typical system/fvSolution                                                 |
+\*---------------------------------------------------------------------------*/
+FoamFile
+{
+    version     2.0;
+    format      ascii;
+    class       dictionary;
+    location    "system";
+    object      fvSolution;
+}
+// * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * //
+
+tol 1e-06;
+
+solvers
+{
+    p
+    {
+        solver          PCG;
+        preconditioner  DIC;
+        tolerance       $tol;
+        relTol          0.05;   // trailing comment
+    }
+
+    pFinal
+    {
+        solver          GAMG;
+        smoother        GaussSeidel;
+        tolerance       1e-07;
+        relTol          0;
+        cacheAgglomeration on;
+        agglomerator    faceAreaPair;
+        nCellsInCoarsestLevel 20;
+        mergeLevels     2;
+        nPreSweeps      1;
+        directSolveCoarsest no;
+        scaleCorrection yes;
+    }
+
+    "(U|k|epsilon)"
+    {
+        solver          PBiCG;
+        preconditioner  { preconditioner DILU; }
+        tolerance       1e-05;
+        relTol          0;
+        maxIter         200;
+    }
+
+    "(U|k|epsilon)Final"
+    {
+        solver          smoothSolver;
+        smoother        { smoother GaussSeidel; }
+        nSweeps         2;
+        tolerance       1e-08;
+    }
+
+    ".*"
+    {
+        solver          PBiCGStab;
+        preconditioner  none;
+    }
+
+    T { solver ICCG; tolerance 1e-9; relTol 0; }
+}
+
+PISO
+{
+    nCorrectors     2;
+    nNonOrthogonalCorrectors 0;
+    pRefCell        0;
+    pRefValue       0;
+}
+
+nu              nu [ 0 2 -1 0 0 0 0 ] 0.01;
+vertices        ( (0 0 0) (1 0 0) (1 1 0) );
+blocks          ( hex (0 1 2 3 4 5 6 7) (20 20 1) simpleGrading (1 1 1) );
+'''
+
+
+def test_dictionary_syntax_and_lookup(ff):
+    d = ff.parse_dict(FVSOLUTION, "fvSolution")
+    assert d.toc()[:2] == ["FoamFile", "tol"]
+    assert d.subDict("FoamFile").lookup("class") == "dictionary"
+    piso = d.subDict("PISO")
+    assert piso.lookup("nCorrectors") == 2 and piso.lookupOrDefault("momentumPredictor", "on") == "on"
+    assert d.lookup("nu") == ["nu", [0, 2, -1, 0, 0, 0, 0], 0.01]
+    assert d.lookup("vertices") == [[0, 0, 0], [1, 0, 0], [1, 1, 0]]
+    assert d.lookup("blocks")[0] == "hex" and d.lookup("blocks")[2] == [20, 20, 1]
+    s = d.subDict("solvers")
+    assert s.subDict("p").lookup("tolerance") == 1e-06          # $tol expanded from the enclosing scope
+    # exact keyword wins over patterns; among patterns the most recently defined one wins (dictionary.C:313-316)
+    assert s.subDict("U").lookup("solver") == "PBiCGStab"       # ".*" was defined after "(U|k|epsilon)"
+    assert s.subDict("p").lookup("solver") == "PCG"
+    with pytest.raises(KeyError, match="undefined"):
+        piso.lookup("nOuterCorrectors")
+    with pytest.raises(KeyError, match="not a sub-dictionary"):
+        d.subDict("tol")
+    with pytest.raises(ValueError):
+        ff.parse_dict("a { b 1; ")
+    with pytest.raises(ValueError):
+        ff.parse_dict("a 1")
+    with pytest.raises(ValueError, match="not supported"):
+        ff.parse_dict('#include "other";')
+
+
+def test_fvsolution_solver_selection(ff):
+    text = FVSOLUTION.replace('    ".*"\n    {\n        solver          PBiCGStab;\n        preconditioner  none;\n    }\n', "")
+    d = ff.parse_dict(text)
+    assert ff.solver_controls(d, "p") == ("PCG", "DIC", dict(tolerance=1e-06, relTol=0.05))
+    sv, sm, c = ff.solver_controls(d, "pFinal")
+    assert (sv, sm) == ("GAMG", "GaussSeidel")
+    assert c == dict(tolerance=1e-07, relTol=0.0, nCellsInCoarsestLevel=20, mergeLevels=2, nPreSweeps=1,
+                     directSolveCoarsest=0, scaleCorrection=1)
+    for fld in ("U", "k", "epsilon"):
+        assert ff.solver_controls(d, fld) == ("PBiCG", "DILU", dict(tolerance=1e-05, relTol=0.0, maxIter=200))
+    assert ff.solver_controls(d, "UFinal") == ("smoothSolver", "GaussSeidel", dict(tolerance=1e-08, nSweeps=2))
+    assert ff.solver_controls(d, "T") == ("ICCG", "DIC", dict(tolerance=1e-9, relTol=0.0))
+    with pytest.raises(KeyError):
+        ff.solver_controls(d, "omega")
+
+
+def test_controls_feed_the_oracle(ff, meshmod, orc):
+    """the parsed controls select and drive a solve exactly like hand-written keyword arguments"""
+    d = ff.parse_dict(FVSOLUTION)
+    m = meshmod.hex_mesh(8, 8, 8)
+    c = meshmod.pressure_laplacian(m)
+    M = orc.Matrix(orc.Addr(m.nCells, m.lower, m.upper), c["diag"], c["upper"], None)
+    b = M.amul(meshmod.cell_field_global(m, 42))
+    sv, pre, ctl = ff.solver_controls(d, "p")
+    psi1, p1, h1 = M.solve(sv, pre, np.zeros(m.nCells), b, **ctl)
+    psi2, p2, h2 = M.solve("PCG", "DIC", np.zeros(m.nCells), b, tolerance=1e-6, relTol=0.05)
+    assert p1.nIterations == p2.nIterations and np.array_equal(psi1, psi2)
+    assert p1.solverName == b"AINVPCG"
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_polymesh_roundtrip_and_geometry(ff, meshmod, tmp_path, binary):
+    hm = meshmod.hex_mesh(5, 4, 3)
+    pm = ff.from_hex_mesh(hm)
+    d = str(tmp_path / "constant" / "polyMesh")
+    ff.write_poly_mesh(d, pm, binary)
+    # neighbour compressed: the reader falls back to <name>.gz like OpenFOAM does
+    with open(os.path.join(d, "neighbour"), "rb") as f, gzip.open(os.path.join(d, "neighbour.gz"), "wb") as g:
+        shutil.copyfileobj(f, g)
+    os.remove(os.path.join(d, "neighbour"))
+    r = ff.read_poly_mesh(d)
+    lo, up = r.ldu()
+    assert np.array_equal(lo, hm.lower) and np.array_equal(up, hm.upper) and r.nCells == hm.nCells
+    assert [(p.name, p.type, p.nFaces) for p in r.patches] == [(p.name, "wall", len(p.faceCells)) for p in hm.patches]
+    assert r.coupled_interface_arrays() == (None, None, None)
+    assert np.array_equal(r.boundary_face_cells(), np.concatenate([p.faceCells for p in hm.patches]))
+    g = r.fv_geometry()
+    np.testing.assert_allclose(g["C"], hm.cell_centres(), atol=1e-15)
+    np.testing.assert_allclose(g["V"], hm.volumes(), rtol=1e-14)
+    np.testing.assert_allclose(g["Sf"][:hm.nFaces], hm.Sf(), atol=1e-16)
+    np.testing.assert_allclose(g["weights"], 0.5, rtol=1e-14)
+    np.testing.assert_allclose(g["deltaCoeffs"], 1.0 / hm.h, rtol=1e-14)
+    for p, q in zip(hm.patches, r.patches):
+        np.testing.assert_allclose(g["Sf"][q.startFace:q.startFace + q.nFaces], p.Sf, atol=1e-16)
+
+
+def test_decomposed_case_processor_patches(ff, meshmod, tmp_path):
+    """processorN/constant/polyMesh of a 2x2x1 decomposition: the coupled-patch arrays handed to
+    b200ldu_addr_create equal those of the in-memory decomposition."""
+    for rank in range(4):
+        hm = meshmod.decompose(8, 4, rank)
+        d = str(tmp_path / f"processor{rank}" / "constant" / "polyMesh")
+        ff.write_poly_mesh(d, ff.from_hex_mesh(hm, rank))
+        r = ff.read_poly_mesh(d, geometry=False)
+        ps, fc, nr = r.coupled_interface_arrays()
+        eps, efc = hm.patch_start_facecells()
+        assert np.array_equal(ps, eps) and np.array_equal(fc, efc)
+        assert nr.tolist() == [p.neighbRank for p in hm.coupled_patches()]
+        assert all(p.myProcNo == rank for p in r.patches if p.type == "processor")
+        assert r.points is None
+
+
+def test_cyclic_patches_from_boundary_file(ff, meshmod, tmp_path):
+    hm = meshmod.hex_mesh(6, 5, 4)
+    pm = ff.from_hex_mesh(hm)
+    names = [p.name for p in pm.patches]
+    a, b = pm.patches[0], pm.patches[1]          # x-min / x-max walls become a cyclic pair
+    a.type = b.type = "cyclic"
+    a.neighbourPatch, b.neighbourPatch = b.name, a.name
+    d = str(tmp_path / "polyMesh")
+    ff.write_poly_mesh(d, pm)
+    r = ff.read_poly_mesh(d)
+    ps, fc, nr = r.coupled_interface_arrays()
+    assert nr.tolist() == [-2, -1] and ps.tolist() == [0, 20, 40]
+    assert np.array_equal(fc[:20], hm.patches[0].faceCells) and np.array_equal(fc[20:], hm.patches[1].faceCells)
+    assert [p.name for p in r.patches] == names
+    b.neighbourPatch = "nowhere"
+    ff.write_poly_mesh(d, pm)
+    with pytest.raises(ValueError, match="neighbourPatch"):
+        ff.read_poly_mesh(d).coupled_interface_arrays()
+
+
+def _scrambled(ff, meshmod, dims, seed, skew=0.25):
+    """hex cells renumbered at random (faces re-sorted into upper-triangular order) with skewed
+    points: an unstructured-numbering, non-orthogonal mesh as a mesher would write it."""
+    hm = meshmod.hex_mesh(*dims)
+    pm = ff.from_hex_mesh(hm)
+    rng = np.random.default_rng(seed)
+    new = rng.permutation(hm.nCells).astype(np.int32)       # old cell -> new cell
+    nI = pm.nInternalFaces
+    own, nei = new[pm.owner[:nI]], new[pm.neighbour]
+    flip = own > nei
+    o2, n2 = np.where(flip, nei, own), np.where(flip, own, nei)
+    order = np.lexsort((n2, o2))
+    quads = pm.faceLabels.reshape(-1, 4).copy()
+    qi = quads[:nI]
+    qi[flip] = qi[flip][:, ::-1]                               # keep the normal pointing owner -> neighbour
+    quads[:nI] = qi[order]
+    owner = np.concatenate([o2[order], new[pm.owner[nI:]]]).astype(np.int32)
+    pts = pm.points.copy()
+    interior = np.all((pts > 1e-12) & (pts < np.array([1.0, dims[1] / dims[0], dims[2] / dims[0]]) - 1e-12), axis=1)
+    pts[interior] += skew * hm.h * (rng.random((int(interior.sum()), 3)) - 0.5)
+    return ff.PolyMesh(owner, n2[order].astype(np.int32), pm.patches, pts, pm.faceOffsets,
+                       quads.reshape(-1).astype(np.int32)), hm
+
+
+def test_geometry_divergence_theorem_on_skewed_mesh(ff, meshmod):
+    pm, hm = _scrambled(ff, meshmod, (6, 5, 4), 3)
+    g = pm.fv_geometry()
+    nI = pm.nInternalFaces
+    closed = np.zeros((pm.nCells, 3))                          # sum of outward area vectors of every cell
+    np.add.at(closed, pm.owner, g["Sf"])
+    np.subtract.at(closed, pm.neighbour, g["Sf"][:nI])
+    np.testing.assert_allclose(closed, 0, atol=1e-15)
+    np.testing.assert_allclose(g["V"].sum(), hm.nCells * hm.h ** 3, rtol=1e-13)
+    vol = np.zeros(pm.nCells)                                  # V = 1/3 sum Cf.Sf (Gauss)
+    np.add.at(vol, pm.owner, np.einsum("ij,ij->i", g["Cf"], g["Sf"]) / 3)
+    np.subtract.at(vol, pm.neighbour, np.einsum("ij,ij->i", g["Cf"][:nI], g["Sf"][:nI]) / 3)
+    np.testing.assert_allclose(g["V"], vol, rtol=1e-12)
+    assert np.all(g["V"] > 0) and np.all((g["weights"] > 0.2) & (g["weights"] < 0.8))
+    d = g["C"][pm.neighbour] - g["C"][pm.owner[:nI]]
+    assert np.all(np.einsum("ij,ij->i", d, g["Sf"][:nI]) > 0)  # normals point owner -> neighbour
+
+
+class _AsMesh:
+    """adapter: PolyMesh -> what tests/test_layout_cpu.py expects of a mesh"""
+
+    def __init__(self, pm, centres):
+        self.lower, self.upper = pm.ldu()
+        self.nCells, self.nFaces = pm.nCells, len(self.lower)
+        self._c = centres
+        self._pm = pm
+
+    def cell_centres(self):
+        return self._c
+
+    def patch_start_facecells(self):
+        ps, fc, _ = self._pm.coupled_interface_arrays()
+        if ps is None:
+            return np.zeros(1, np.int32), np.zeros(0, np.int32)
+        return ps, fc
+
+
+@pytest.mark.parametrize("centres", [True, False])
+def test_unstructured_case_from_disk_drives_oracle_and_layout(ff, meshmod, orc, capi, tmp_path, centres):  # noqa: F811
+    """A randomly numbered, skewed mesh written to constant/polyMesh, read back, assembled into the
+    Laplacian from its own geometry (gaussLaplacianScheme: upper = deltaCoeffs*|Sf|), solved by the
+    oracle against a dense solve, and banded by the product's layout builder (with cell centres and
+    with the graph-distance embedding) -- structural check face for face."""
+    pm0, hm = _scrambled(ff, meshmod, (7, 6, 5), 11)
+    d = str(tmp_path / "constant" / "polyMesh")
+    ff.write_poly_mesh(d, pm0, binary=True)
+    pm = ff.read_poly_mesh(d)
+    g = pm.fv_geometry()
+    lo, up = pm.ldu()
+    upper = g["deltaCoeffs"] * g["magSf"][:len(lo)]
+    diag = np.zeros(pm.nCells)
+    np.subtract.at(diag, lo, upper)
+    np.subtract.at(diag, up, upper)
+    diag[0] *= 2
+    a = orc.Addr(pm.nCells, lo, up)
+    M = orc.Matrix(a, diag, upper, None)
+    A = dense_from_ldu(pm.nCells, lo, up, diag, upper)
+    xs = np.random.default_rng(2).standard_normal(pm.nCells)
+    b = A @ xs
+    np.testing.assert_allclose(M.amul(xs), b, rtol=1e-12, atol=1e-12)
+    psi, perf, _ = M.solve("PCG", "DIC", np.zeros(pm.nCells), b, tolerance=1e-10, maxIter=500)
+    assert perf.converged
+    np.testing.assert_allclose(psi, xs, atol=1e-6)
+    mesh = _AsMesh(pm, g["C"] if centres else None)
+    lay = _layout(capi, mesh, centres=centres, band=64)
+    _check_layout(mesh, lay)
+    nPad, nBands, bandRows, nRecv, maxHalo = [int(x) for x in lay["dims"]]
+    assert nBands >= 3 and maxHalo < 4 * bandRows      # the renumbering keeps the bands compact
