@@ -53,7 +53,14 @@ int orc_pcg_omp(const orc_matrix *m, int pk, const orc_controls *c, double *psi,
         rD[i] = 1.0 / m->diag[i];
         sp += psi[i];
     }
-    orc_sumA(m, tmp);
+    /* sumA (lduMatrixATmul.C:345-395), rows in parallel; single-domain matrices only (no interfaces) */
+#pragma omp parallel for num_threads(nT) schedule(static)
+    for (int i = 0; i < n; i++) {
+        double out = m->diag[i];
+        for (int f = a->ownerStart[i]; f < a->ownerStart[i + 1]; f++) out = out + m->upper[f];
+        for (int k = a->losortStart[i]; k < a->losortStart[i + 1]; k++) out = out + m->lower[a->losort[k]];
+        tmp[i] = out;
+    }
     double avg = sp / (double)n, nf = 0;
 #pragma omp parallel for num_threads(nT) schedule(static) reduction(+ : nf, s0)
     for (int i = 0; i < n; i++) {
@@ -97,7 +104,8 @@ int orc_pcg_omp(const orc_matrix *m, int pk, const orc_controls *c, double *psi,
             }
             wArA = dot;
             if (perf->nIterations == 0) {
-                memcpy(pA, wA, sizeof(double) * (size_t)n);
+#pragma omp parallel for num_threads(nT) schedule(static)
+                for (int i = 0; i < n; i++) pA[i] = wA[i];
             } else {
                 double beta = wArA / wArAold;
 #pragma omp parallel for num_threads(nT) schedule(static)
