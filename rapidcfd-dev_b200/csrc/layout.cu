@@ -102,8 +102,16 @@ uint64_t interleave(const uint32_t idx[3], const int bits[3])
     return code;
 }
 
+// set while layout_build retries with narrower bands (tile did not fit in shared memory)
+thread_local int g_bandRowsRetry = 0;
+
+// a band's tile is (bandRows + halo) doubles per staged vector, two vectors at most (engine.cuh);
+// B200 gives a CTA 227 KB, the kernel keeps a little static scratch
+constexpr size_t TILE_BYTES_MAX = 200 * 1024;
+
 int pick_band_rows(int nCells)
 {
+    if (g_bandRowsRetry) return g_bandRowsRetry;
     if (const char *e = getenv("B200LDU_BAND_ROWS")) {
         int v = atoi(e);
         if (v >= SLICE_ROWS && v % SLICE_ROWS == 0 && v <= 16384) return v;
@@ -338,8 +346,15 @@ int layout_build(b200ldu_addr *a, const double *centres)
         }
     }
     if (tooWide) {
-        b200_set_error("layout_build: %d band(s) reference more than 65535 distinct columns; "
-                       "set B200LDU_BAND_ROWS lower", tooWide);
+        if (bandRows > SLICE_ROWS) { // retry with narrower bands (see the tile check below)
+            const int saved = g_bandRowsRetry;
+            g_bandRowsRetry = bandRows / 2;
+            int rc = layout_build(a, centres);
+            g_bandRowsRetry = saved;
+            return rc;
+        }
+        b200_set_error("layout_build: %d band(s) of %d rows reference more than 65535 distinct columns",
+                       tooWide, bandRows);
         return B200LDU_ELAYOUT;
     }
     std::vector<int> haloStart((size_t)nBands + 1, 0);
@@ -347,6 +362,21 @@ int layout_build(b200ldu_addr *a, const double *centres)
     for (int b = 0; b < nBands; b++) {
         haloStart[b + 1] = haloStart[b] + (int)halo[b].size();
         maxHalo = std::max(maxHalo, (int)halo[b].size());
+    }
+    if ((size_t)(bandRows + maxHalo + 2) * 2 * sizeof(double) > TILE_BYTES_MAX) {
+        // poorly clustered numbering (no cell centres, high-degree graph): the halo of a band does not fit
+        // next to its rows in shared memory.  Narrower bands shrink both terms; the ordering is unchanged.
+        if (bandRows > SLICE_ROWS) {
+            const int saved = g_bandRowsRetry;
+            g_bandRowsRetry = bandRows / 2;
+            int rc = layout_build(a, centres);
+            g_bandRowsRetry = saved;
+            return rc;
+        }
+        b200_set_error("layout_build: a band of %d rows references %d outside columns: the tile does not fit in "
+                       "shared memory; pass cell centres (or renumber the mesh) so that neighbours are close",
+                       bandRows, maxHalo);
+        return B200LDU_ELAYOUT;
     }
     std::vector<int> haloIdx((size_t)std::max(haloStart[nBands], 1));
 #pragma omp parallel for schedule(static)

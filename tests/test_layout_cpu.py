@@ -270,3 +270,32 @@ def test_shared_layout_structure(capi, meshmod, dims, centres, band, nR):
     assert stored >= mesh.nFaces
     if dims == (12, 12, 12):
         assert stored < 1.45 * mesh.nFaces  # cube-shaped slices: most faces are slice-internal
+
+
+class _RandomGraph:
+    """LDU pattern of a random graph without any locality (worst case for the band tiles)."""
+
+    def __init__(self, n, k, seed):
+        rng = np.random.default_rng(seed)
+        a, b = rng.integers(0, n, size=n * k), rng.integers(0, n, size=n * k)
+        keep = a != b
+        pr = np.unique(np.stack([np.minimum(a, b)[keep], np.maximum(a, b)[keep]], 1), axis=0).astype(np.int32)
+        self.lower, self.upper = pr[:, 0].copy(), pr[:, 1].copy()
+        self.nCells, self.nFaces = n, len(pr)
+
+    def cell_centres(self):
+        return None
+
+    def patch_start_facecells(self):
+        return np.zeros(1, np.int32), np.zeros(0, np.int32)
+
+
+def test_layout_narrows_bands_until_the_tile_fits(capi):
+    """A band's rows + halo columns are staged in shared memory (two vectors at most): when a
+    numbering without locality makes that tile too large -- or needs more than 65535 columns -- the
+    builder halves bandRows until it fits instead of failing at launch time."""
+    g = _RandomGraph(30000, 6, 1)
+    lay = _layout(capi, g, centres=False, band=16384)
+    nPad, nBands, bandRows, nRecv, maxHalo = [int(x) for x in lay["dims"]]
+    assert bandRows < 16384 and (bandRows + maxHalo + 2) * 16 <= 200 * 1024
+    _check_layout(g, lay)
