@@ -1,0 +1,155 @@
+/*
+ * harness.cpp -- runs the REFERENCE'S OWN lduMatrix code on the CPU.  TEST INFRASTRUCTURE ONLY.
+ *
+ * The translation unit includes, by path from /root/reference (nothing is copied into this repo):
+ *   LDU/lduMatrix/lduMatrixATmul.C            lduMatrix::Amul, Tmul, sumA, residual, H1 and the
+ *                                             matrixMultiplyFunctor they launch            (:42-554)
+ *   LDU/lduAddressing/lduAddressingFunctors.H lduAddressingFunctor family, matrixOperation (:10-400)
+ *   LDU/lduMatrix/lduMatrixFunctors.H         lduMatrixDiagonalResidualFunctor, ...        (:6-301)
+ *   LDU/preconditioners/AINVPreconditioner/AINVPreconditionerF.H                           (:5-100)
+ *   LDU/smoothers/Jacobi/JacobiSmootherF.H                                                 (:8-110)
+ *   LDU/lduMatrix/lduMatrixSolverFunctors.H   the solvers' AXPY functors                   (:7-45)
+ * against oracle/ref_harness/shim/ (host-memory stand-ins for gpuList, tmp, textures, lduAddressing,
+ * lduMatrix's data members; thrust's host back end).  Built by `make -C oracle ref` with
+ * -ffp-contract=off into oracle/_ref/libref_ldu.so, where /root/reference exists.
+ *
+ * What a bit-exact match with the oracle then means: the oracle's row arithmetic (order of the
+ * products and sums) is the reference's, for the instructions a compiler emits WITHOUT fusing a*b+c.
+ * nvcc's device build of the reference does fuse where an expression allows it; DESIGN.md section 2
+ * lists where that applies (tails beyond three faces per side, the AXPY functors).
+ */
+#include "lduMatrix.H" /* the shim (first on the include path) */
+
+#include "lduMatrixATmul.C" /* reference, through oracle/_ref/inc/ */
+
+#include "AINVPreconditionerF.H"
+#include "JacobiSmootherF.H"
+#include "lduMatrixSolverFunctors.H"
+
+int Foam::lduMatrixSolutionCache::favourSpeed = 0;
+
+using namespace Foam;
+
+namespace
+{
+struct Case {
+    lduAddressing addr;
+    lduMatrix m;
+    scalargpuField lower, upper, diag, lowerSort, upperSort;
+    std::vector<label> ownerSort;
+    std::vector<scalar> ls, us;
+
+    Case(int n, int nF, const int *l, const int *u, const int *ownerStart, const int *losortStart, const int *losort,
+         const double *dg, const double *up, const double *lo)
+        : lower(lo ? lo : up, nF), upper(up, nF), diag(dg, n), ownerSort(nF), ls(nF), us(nF)
+    {
+        for (int k = 0; k < nF; k++) { // lduAddressing.C:373-400 ownerSortAddr; lduMatrix.C:404-436 sorted coefficients
+            ownerSort[k] = l[losort[k]];
+            ls[k] = (lo ? lo : up)[losort[k]];
+            us[k] = up[losort[k]];
+        }
+        addr.nCells_ = n;
+        addr.lower_.view(l, nF);
+        addr.upper_.view(u, nF);
+        addr.ownerStart_.view(ownerStart, n + 1);
+        addr.losortStart_.view(losortStart, n + 1);
+        addr.losort_.view(losort, nF);
+        addr.ownerSort_.view(ownerSort.data(), nF);
+        lowerSort.view(ls.data(), nF);
+        upperSort.view(us.data(), nF);
+        m.addr_ = &addr;
+        m.lowerPtr_ = &lower;
+        m.upperPtr_ = &upper;
+        m.diagPtr_ = &diag;
+        m.lowerSortPtr_ = &lowerSort;
+        m.upperSortPtr_ = &upperSort;
+        m.level_ = 0;
+        m.coarsest_ = false;
+    }
+};
+} // namespace
+
+#define CASE_ARGS int n, int nF, const int *l, const int *u, const int *ownerStart, const int *losortStart, \
+                  const int *losort, const double *dg, const double *up, const double *lo
+#define CASE_PASS n, nF, l, u, ownerStart, losortStart, losort, dg, up, lo
+
+extern "C" {
+
+/* op: 0 Amul, 1 Tmul, 2 sumA, 3 residual (x = psi, b = source), 4 H1.  favourSpeed selects the
+ * reference's path: 0 = losort indirection, 1/2 = pre-sorted coefficients ("fast"). */
+int ref_matrix_op(int op, int favourSpeed, CASE_ARGS, const double *x, const double *b, double *out)
+{
+    Case c(CASE_PASS);
+    lduMatrixSolutionCache::favourSpeed = favourSpeed;
+    scalargpuField o(out, n);
+    FieldField<gpuField, scalar> noCoeffs(0);
+    lduInterfaceFieldPtrsList noInterfaces;
+    switch (op) {
+    case 0: {
+        scalargpuField psi(x, n);
+        c.m.Amul(o, tmp<scalargpuField>(psi), noCoeffs, noInterfaces, 0);
+        return 0;
+    }
+    case 1: {
+        scalargpuField psi(x, n);
+        c.m.Tmul(o, tmp<scalargpuField>(psi), noCoeffs, noInterfaces, 0);
+        return 0;
+    }
+    case 2:
+        c.m.sumA(o, noCoeffs, noInterfaces);
+        return 0;
+    case 3: {
+        scalargpuField psi(x, n), src(b, n);
+        c.m.residual(o, psi, src, noCoeffs, noInterfaces, 0);
+        return 0;
+    }
+    case 4:
+        c.m.H1(o);
+        return 0;
+    }
+    return -1;
+}
+
+/* AINVPreconditionerFunctor<fast,3> exactly as AINVPreconditioner.C:78-117 launches it: transpose swaps
+ * the coefficient arrays (preconditionT, :119-160); rD = 1/diag (calcReciprocalD, :47-62). */
+int ref_ainv(int fast, int transpose, CASE_ARGS, const double *r, double *w)
+{
+    Case c(CASE_PASS);
+    std::vector<scalar> rD(n);
+    for (int i = 0; i < n; i++) rD[i] = 1.0 / dg[i];
+    const scalar *L = fast ? c.lowerSort.data() : c.lower.data();
+    const scalar *U = c.upper.data();
+    const scalar *Lt = c.lower.data(), *Ut = fast ? c.upperSort.data() : c.upper.data();
+    const label *own = fast ? c.addr.ownerSort_.data() : c.addr.lower_.data();
+    textures<scalar> rt(r), rDt(rD.data());
+    if (fast) {
+        AINVPreconditionerFunctor<true, 3> f(rt, rDt, transpose ? Ut : L, transpose ? Lt : U, own, c.addr.upper_.data(),
+                                             ownerStart, losortStart, losort);
+        for (label i = 0; i < n; i++) w[i] = f(i);
+    } else {
+        AINVPreconditionerFunctor<false, 3> f(rt, rDt, transpose ? Ut : L, transpose ? Lt : U, own, c.addr.upper_.data(),
+                                              ownerStart, losortStart, losort);
+        for (label i = 0; i < n; i++) w[i] = f(i);
+    }
+    return 0;
+}
+
+/* JacobiSmootherFunctor<fast,3>, one sweep without interfaces (JacobiSmoother.C:103-140) */
+int ref_jacobi(int fast, double omega, CASE_ARGS, const double *psi, const double *b, double *out)
+{
+    Case c(CASE_PASS);
+    textures<scalar> pt(psi);
+    const scalar *L = fast ? c.lowerSort.data() : c.lower.data();
+    const label *own = fast ? c.addr.ownerSort_.data() : c.addr.lower_.data();
+    if (fast) {
+        JacobiSmootherFunctor<true, 3> f(omega, pt, dg, b, L, c.upper.data(), own, c.addr.upper_.data(), ownerStart,
+                                         losortStart, losort);
+        for (label i = 0; i < n; i++) out[i] = f(i);
+    } else {
+        JacobiSmootherFunctor<false, 3> f(omega, pt, dg, b, L, c.upper.data(), own, c.addr.upper_.data(), ownerStart,
+                                          losortStart, losort);
+        for (label i = 0; i < n; i++) out[i] = f(i);
+    }
+    return 0;
+}
+}

@@ -1,0 +1,238 @@
+/*
+ * foam_shim.h -- the few OpenFOAM/RapidCFD types the reference's lduMatrix functor code is written
+ * against, re-declared over plain host memory so that the REFERENCE'S OWN SOURCE FILES (included by
+ * path from /root/reference, never copied) compile with g++ and run on the CPU.  TEST INFRASTRUCTURE
+ * ONLY (oracle/Makefile target `ref`): it lets tests compare the oracle's restatement with the code it
+ * restates.  Nothing here is an algorithm of the hot path; every loop that is executed comes from the
+ * reference file named in harness.cpp.
+ *
+ * Device qualifiers are defined away and thrust runs its host (CPP) back end, so `thrust::transform`
+ * over these containers is a serial loop calling the reference's functor once per cell.
+ */
+#ifndef FOAM_SHIM_H
+#define FOAM_SHIM_H
+
+#ifndef __CUDACC__
+#define __host__
+#define __device__
+#endif
+#define __HOST____DEVICE__
+
+#include <cstddef>
+#include <functional>
+#include <vector>
+
+#include <thrust/functional.h>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/permutation_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
+#include <thrust/iterator/zip_iterator.h>
+#include <thrust/transform.h>
+#include <thrust/tuple.h>
+
+#define forAll(list, i) for (Foam::label i = 0; i < (list).size(); i++)
+
+namespace Foam
+{
+typedef double scalar;       // etc/bashrc:76 WM_PRECISION_OPTION=DP
+typedef int label;           // label.H:46-67 (32-bit)
+typedef unsigned char direction;
+
+// ---- gpuList / gpuField: a non-owning or owning view of host memory ----
+template <class T> class gpuList
+{
+    std::vector<T> own_;
+    T *p_;
+    label n_;
+
+public:
+    typedef T *iterator;
+    typedef const T *const_iterator;
+    gpuList() : p_(nullptr), n_(0) {}
+    explicit gpuList(label n) : own_((size_t)n), p_(own_.data()), n_(n) {}
+    gpuList(label n, const T &v) : own_((size_t)n, v), p_(own_.data()), n_(n) {}
+    gpuList(T *p, label n) : p_(p), n_(n) {}
+    gpuList(const T *p, label n) : p_(const_cast<T *>(p)), n_(n) {}
+    gpuList(const gpuList &o) : own_(o.own_), p_(o.own_.empty() ? o.p_ : own_.data()), n_(o.n_) {}
+    gpuList &operator=(const gpuList &o)
+    {
+        for (label i = 0; i < n_ && i < o.n_; i++) p_[i] = o.p_[i];
+        return *this;
+    }
+    void operator=(const T &v)
+    {
+        for (label i = 0; i < n_; i++) p_[i] = v;
+    }
+    void view(const T *p, label n) // shim only: point this list at caller memory
+    {
+        own_.clear();
+        p_ = const_cast<T *>(p);
+        n_ = n;
+    }
+    label size() const { return n_; }
+    T *data() { return p_; }
+    const T *data() const { return p_; }
+    iterator begin() { return p_; }
+    iterator end() { return p_ + n_; }
+    const_iterator begin() const { return p_; }
+    const_iterator end() const { return p_ + n_; }
+};
+
+template <class T> class gpuField : public gpuList<T>
+{
+public:
+    using gpuList<T>::gpuList;
+    using gpuList<T>::operator=;
+};
+typedef gpuField<scalar> scalargpuField;
+typedef gpuList<label> labelgpuList;
+
+// ---- tmp<T>: reference or owned temporary ----
+template <class T> class tmp
+{
+    mutable T *owned_;
+    const T *ref_;
+
+public:
+    tmp(T *p) : owned_(p), ref_(p) {}
+    tmp(const T &r) : owned_(nullptr), ref_(&r) {}
+    tmp(const tmp &o) : owned_(o.owned_), ref_(o.ref_) { o.owned_ = nullptr; }
+    ~tmp() { delete owned_; }
+    const T &operator()() const { return *ref_; }
+    T &operator()() { return *const_cast<T *>(ref_); }
+    void clear() const
+    {
+        delete owned_;
+        owned_ = nullptr;
+    }
+};
+
+template <class T> tmp<gpuField<T>> operator-(const gpuField<T> &f)
+{
+    gpuField<T> *r = new gpuField<T>(f.size());
+    for (label i = 0; i < f.size(); i++) r->data()[i] = -f.data()[i];
+    return tmp<gpuField<T>>(r);
+}
+
+// ---- interface lists: the harness drives single-domain matrices, so no interface is ever set ----
+template <template <class> class Field, class T> class FieldField
+{
+    label n_;
+
+public:
+    explicit FieldField(label n = 0) : n_(n) {}
+    label size() const { return n_; }
+    const Field<T> &operator[](label) const
+    {
+        static Field<T> none;
+        return none;
+    }
+    void set(label, const tmp<Field<T>> &) {}
+};
+
+class lduInterfaceFieldPtrsList
+{
+public:
+    label size() const { return 0; }
+    bool set(label) const { return false; }
+};
+
+// ---- ops.H (src/OpenFOAM/primitives/ops/ops.H:227-238 and the unary-operator functor macro) ----
+template <class T> class unityOp
+{
+public:
+    T operator()(const T &x) const { return x; }
+};
+template <class T> class sumOp
+{
+public:
+    T operator()(const T &x, const T &y) const { return x + y; }
+};
+template <class R, class T> struct negateUnaryOperatorFunctor {
+    R operator()(const T &x) const { return -x; }
+};
+
+// ---- Textures.H (src/OpenFOAM/device/Textures.H): texture fetch == plain load ----
+template <class T> class textures
+{
+    const T *data_;
+
+public:
+    explicit textures(const T *d) : data_(d) {}
+    T operator[](const int &i) const { return data_[i]; }
+};
+template <class T> class textureBind
+{
+    const T *data_;
+
+public:
+    textureBind(const gpuList<T> &l) : data_(l.data()) {}
+    textures<T> operator()() const { return textures<T>(data_); }
+};
+
+// ---- lduMatrixSolutionCache::favourSpeed (selects the reference's "fast" sorted-coefficient path) ----
+struct lduMatrixSolutionCache {
+    static int favourSpeed;
+};
+
+// ---- lduAddressing: the arrays of LDU/lduAddressing/lduAddressing.H:200-255, supplied by the test ----
+class lduAddressing
+{
+public:
+    labelgpuList lower_, upper_, ownerStart_, losortStart_, losort_, ownerSort_;
+    label nCells_;
+    label size() const { return nCells_; }
+    const labelgpuList &lowerAddr() const { return lower_; }
+    const labelgpuList &upperAddr() const { return upper_; }
+    const labelgpuList &ownerStartAddr() const { return ownerStart_; }
+    const labelgpuList &losortStartAddr() const { return losortStart_; }
+    const labelgpuList &losortAddr() const { return losort_; }
+    const labelgpuList &ownerSortAddr() const { return ownerSort_; }
+    // coupled-patch sort addressing: never reached without interfaces
+    const labelgpuList &patchSortCells(label) const { return lower_; }
+    const labelgpuList &patchSortAddr(label) const { return lower_; }
+    const labelgpuList &patchSortStartAddr(label) const { return lower_; }
+};
+
+// ---- lduMatrix: declarations of the members defined in the reference's lduMatrixATmul.C ----
+class lduMatrix
+{
+public:
+    const lduAddressing *addr_;
+    scalargpuField *lowerPtr_, *upperPtr_, *diagPtr_, *lowerSortPtr_, *upperSortPtr_;
+    int level_;
+    bool coarsest_;
+
+    const lduAddressing &lduAddr() const { return *addr_; }
+    const scalargpuField &lower() const { return lowerPtr_ ? *lowerPtr_ : *upperPtr_; }
+    const scalargpuField &upper() const { return upperPtr_ ? *upperPtr_ : *lowerPtr_; }
+    const scalargpuField &diag() const { return *diagPtr_; }
+    const scalargpuField &lowerSort() const { return *lowerSortPtr_; }
+    const scalargpuField &upperSort() const { return *upperSortPtr_; }
+    bool coarsestLevel() const { return coarsest_; }
+    int level() const { return level_; }
+    void initMatrixInterfaces(const FieldField<gpuField, scalar> &, const lduInterfaceFieldPtrsList &,
+                              const scalargpuField &, scalargpuField &, const direction) const
+    {
+    }
+    void updateMatrixInterfaces(const FieldField<gpuField, scalar> &, const lduInterfaceFieldPtrsList &,
+                                const scalargpuField &, scalargpuField &, const direction) const
+    {
+    }
+
+    // defined by the reference (lduMatrixATmul.C:183-554)
+    void Amul(scalargpuField &, const tmp<scalargpuField> &, const FieldField<gpuField, scalar> &,
+              const lduInterfaceFieldPtrsList &, const direction) const;
+    void Tmul(scalargpuField &, const tmp<scalargpuField> &, const FieldField<gpuField, scalar> &,
+              const lduInterfaceFieldPtrsList &, const direction) const;
+    void sumA(scalargpuField &, const FieldField<gpuField, scalar> &, const lduInterfaceFieldPtrsList &) const;
+    void residual(scalargpuField &, const scalargpuField &, const scalargpuField &,
+                  const FieldField<gpuField, scalar> &, const lduInterfaceFieldPtrsList &, const direction) const;
+    tmp<scalargpuField> residual(const scalargpuField &, const scalargpuField &,
+                                 const FieldField<gpuField, scalar> &, const lduInterfaceFieldPtrsList &,
+                                 const direction) const;
+    void H1(scalargpuField &) const;
+    tmp<scalargpuField> H1() const;
+};
+} // namespace Foam
+#endif

@@ -1,0 +1,99 @@
+"""ctypes access to oracle/_ref/libref_ldu.so -- the REFERENCE'S OWN lduMatrix sources
+(lduMatrixATmul.C, lduAddressingFunctors.H, AINVPreconditionerF.H, JacobiSmootherF.H, ...) compiled
+for the host against the shims in oracle/ref_harness/ (see harness.cpp).  TEST INFRASTRUCTURE ONLY:
+used by tests/test_reference_functors.py to pin the oracle's row arithmetic to the code it restates.
+Built by `make -C oracle ref` where /root/reference exists; elsewhere the prebuilt library is used."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_ref", "libref_ldu.so")
+_lib = None
+
+
+def build():
+    """(Re)build where the reference tree is present; returns the library path or None."""
+    if os.path.isdir("/root/reference/src/OpenFOAM/matrices/lduMatrix"):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+    return _LIB if os.path.exists(_LIB) else None
+
+
+def available():
+    return build() is not None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError("oracle/_ref/libref_ldu.so is not built (needs /root/reference)")
+        _lib = C.CDLL(_LIB)
+    return _lib
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _d(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class RefMatrix:
+    """One single-domain LDU matrix handed to the reference code (no coupled interfaces)."""
+
+    def __init__(self, nCells, lower, upper, ownerStart, losortStart, losort, diag, upperC, lowerC=None):
+        self.n, self.nF = int(nCells), len(lower)
+        self.keep = [_i(lower), _i(upper), _i(ownerStart), _i(losortStart), _i(losort), _d(diag), _d(upperC), _d(lowerC)]
+
+    def _case(self):
+        l, u, os_, ls, lo, dg, up, low = self.keep
+        return [self.n, self.nF, _p(l), _p(u), _p(os_), _p(ls), _p(lo), _p(dg), _p(up), _p(low)]
+
+    def op(self, which, favourSpeed=0, x=None, b=None):
+        """which: amul | tmul | sumA | residual | H1 (lduMatrixATmul.C)."""
+        code = {"amul": 0, "tmul": 1, "sumA": 2, "residual": 3, "H1": 4}[which]
+        out = np.zeros(self.n)
+        x, b = _d(x), _d(b)
+        rc = lib().ref_matrix_op(code, int(favourSpeed), *self._case(), _p(x), _p(b), _p(out))
+        assert rc == 0
+        return out
+
+    def ainv(self, r, fast=False, transpose=False):
+        out = np.zeros(self.n)
+        r = _d(r)
+        assert lib().ref_ainv(int(fast), int(transpose), *self._case(), _p(r), _p(out)) == 0
+        return out
+
+    def jacobi(self, psi, b, omega=0.9, fast=False):
+        out = np.zeros(self.n)
+        psi, b = _d(psi), _d(b)
+        lib().ref_jacobi.argtypes = [C.c_int, C.c_double] + [C.c_int, C.c_int] + [C.c_void_p] * 11
+        assert lib().ref_jacobi(int(fast), float(omega), *self._case(), _p(psi), _p(b), _p(out)) == 0
+        return out
+
+
+_LIB_GAMG = os.path.join(_HERE, "_ref", "libref_gamg.so")
+_libg = None
+
+
+def pair_agglomerate(nCells, lower, upper, faceWeights, forward=1):
+    """The reference's pairGAMGAgglomeration::agglomerate (pairGAMGAgglomerate.C:135-313).
+    Returns (map int32[nCells], nCoarseCells, forward flag after the call)."""
+    global _libg
+    if _libg is None:
+        if not available() or not os.path.exists(_LIB_GAMG):
+            raise RuntimeError("oracle/_ref/libref_gamg.so is not built (needs /root/reference)")
+        _libg = C.CDLL(_LIB_GAMG)
+    l, u, w = _i(lower), _i(upper), _d(faceWeights)
+    fwd = C.c_int(int(forward))
+    out = np.zeros(int(nCells), dtype=np.int32)
+    nC = _libg.ref_pair_agglomerate(int(nCells), len(l), _p(l), _p(u), _p(w), C.byref(fwd), _p(out))
+    return out, nC, fwd.value

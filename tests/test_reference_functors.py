@@ -1,0 +1,103 @@
+"""Pins the oracle to the REFERENCE'S OWN SOURCE: oracle/_ref/libref_ldu.so and libref_gamg.so are
+the reference's lduMatrixATmul.C (Amul, Tmul, sumA, residual, H1 + matrixMultiplyFunctor),
+lduAddressingFunctors.H, AINVPreconditionerF.H, JacobiSmootherF.H and pairGAMGAgglomerate.C compiled
+for the host against type shims (oracle/ref_harness/, `make -C oracle ref`).  The oracle must agree
+with that code BIT FOR BIT on hex meshes (at most three faces per side of a cell, where the
+reference's unrolled row sum has no tail) and map for map in the pair agglomeration.
+
+Scope of the claim: host compilation with floating-point contraction off; the CUDA build of the
+reference may fuse a*b+c where the source allows it."""
+import importlib
+
+import numpy as np
+import pytest
+
+from oracle import ref_ldu
+
+pytestmark = pytest.mark.skipif(not ref_ldu.available(),
+                                reason="oracle/_ref not built and /root/reference absent")
+
+
+def _pair(meshmod, orc, dims, kind):
+    m = meshmod.hex_mesh(*dims)
+    c = meshmod.pressure_laplacian(m) if kind == "P" else meshmod.momentum_matrix(m)
+    a = orc.Addr(m.nCells, m.lower, m.upper)
+    M = orc.Matrix(a, c["diag"], c["upper"], c["lower"])
+    R = ref_ldu.RefMatrix(m.nCells, m.lower, m.upper, a.owner_start(), a.losort_start(), a.losort(),
+                          c["diag"], c["upper"], c["lower"])
+    return m, M, R
+
+
+@pytest.mark.parametrize("dims", [(7, 5, 4), (16, 16, 16), (13, 1, 1), (1, 1, 1)])
+@pytest.mark.parametrize("kind", ["P", "U"])
+def test_matrix_operations_match_reference_code(meshmod, orc, dims, kind):
+    m, M, R = _pair(meshmod, orc, dims, kind)
+    x, b = meshmod.cell_field_global(m, 3), meshmod.cell_field_global(m, 4)
+    for favourSpeed in (0, 1, 2):   # losort indirection / pre-sorted coefficients (lduMatrixATmul.C:191-192)
+        assert np.array_equal(R.op("amul", favourSpeed, x), M.amul(x))
+        assert np.array_equal(R.op("tmul", favourSpeed, x), M.tmul(x))
+        assert np.array_equal(R.op("sumA", favourSpeed), M.sumA())
+        assert np.array_equal(R.op("residual", favourSpeed, x, b), M.residual(x, b))
+        assert np.array_equal(R.op("H1", favourSpeed), M.H1())
+
+
+@pytest.mark.parametrize("kind", ["P", "U"])
+def test_ainv_and_jacobi_match_reference_functors(meshmod, orc, kind):
+    m, M, R = _pair(meshmod, orc, (9, 8, 7), kind)
+    x, b = meshmod.cell_field_global(m, 5), meshmod.cell_field_global(m, 6)
+    for fast in (False, True):
+        for T in (False, True):
+            assert np.array_equal(R.ainv(x, fast, T), M.precondition("DIC", x, T))
+        for omega in (0.9, 1.0, 0.5):
+            assert np.array_equal(R.jacobi(x, b, omega, fast), M.jacobi(x, b, 1, omega=omega))
+
+
+def test_rows_with_more_than_three_faces_per_side(meshmod, orc):
+    """Beyond the unrolled three faces per side the reference keeps a separate tail sum in Amul
+    (`return out + nExtra`, lduMatrixATmul.C:122-137) and -- in the `fast` variant of the generic
+    functor used by residual and H1 -- accumulates the neighbour tail in `nExtra` and then returns
+    `out` alone (lduAddressingFunctors.H:126-139), i.e. drops those terms.  The oracle sums every
+    term in row order: equal to the reference's general path up to rounding, and deliberately not
+    equal to the dropped-term result."""
+    rng = np.random.default_rng(0)
+    n = 400
+    a_, b_ = rng.integers(0, n, 6 * n), rng.integers(0, n, 6 * n)
+    keep = a_ != b_
+    pr = np.unique(np.stack([np.minimum(a_, b_)[keep], np.maximum(a_, b_)[keep]], 1), axis=0).astype(np.int32)
+    lo, up = pr[:, 0].copy(), pr[:, 1].copy()
+    U, L = rng.uniform(-1, 1, len(lo)), rng.uniform(-1, 1, len(lo))
+    D = rng.uniform(5, 6, n)
+    a = orc.Addr(n, lo, up)
+    M = orc.Matrix(a, D, U, L)
+    R = ref_ldu.RefMatrix(n, lo, up, a.owner_start(), a.losort_start(), a.losort(), D, U, L)
+    assert np.diff(a.losort_start()).max() > 3 and np.diff(a.owner_start()).max() > 3
+    x, b = rng.standard_normal(n), rng.standard_normal(n)
+    np.testing.assert_allclose(R.op("amul", 0, x), M.amul(x), rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(R.op("residual", 0, x, b), M.residual(x, b), rtol=1e-13, atol=1e-13)
+    assert np.array_equal(R.op("residual", 0, x, b), M.residual(x, b))       # general functor: plain row order
+    dropped = R.op("residual", 1, x, b)                                        # fast functor loses the tail
+    assert np.abs(dropped - M.residual(x, b)).max() > 1e-3
+
+
+@pytest.mark.parametrize("dims", [(12, 10, 8), (7, 5, 3), (16, 16, 16)])
+@pytest.mark.parametrize("forward0", [1, 0])
+def test_pair_agglomeration_matches_reference_code(meshmod, orc, dims, forward0):
+    """pairGAMGAgglomeration::agglomerate (pairGAMGAgglomerate.C:135-313), level by level: the
+    reference's code run on the oracle's coarse addressing and restricted weights gives the oracle's
+    fine->coarse map, coarse cell count and `forward_` flag on every level."""
+    m = meshmod.hex_mesh(*dims)
+    a = orc.Addr(m.nCells, m.lower, m.upper)
+    w = meshmod.face_area_pair_weights(m)
+    g = orc.Gamg(a, w, 10, forward=forward0)
+    lo, up, n, fwd = m.lower, m.upper, m.nCells, forward0
+    assert g.nLevels >= 3
+    for lev in range(g.nLevels):
+        rmap, nC, fwd = ref_ldu.pair_agglomerate(n, lo, up, w, fwd)
+        assert nC == g.ncells(lev)
+        assert np.array_equal(rmap, g.restrict_addr(lev))
+        fr, la = g.face_restrict_addr(lev), g.level_addr(lev)
+        cw = np.zeros(g.nfaces(lev))
+        np.add.at(cw, fr[fr >= 0], w[fr >= 0])   # restrictFaceField of the weights (pairGAMGAgglomerate.C:86-107)
+        lo, up, n, w = la.lower(), la.upper(), nC, cw
+    _, nC, fwd = ref_ldu.pair_agglomerate(n, lo, up, w, fwd)   # the step continueAgglomerating rejects
+    assert nC < 10 and fwd == g.forward
