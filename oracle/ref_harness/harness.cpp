@@ -58,7 +58,7 @@ struct Case {
         lowerSort.view(ls.data(), nF);
         upperSort.view(us.data(), nF);
         m.addr_ = &addr;
-        m.lowerPtr_ = &lower;
+        m.lowerPtr_ = lo ? &lower : nullptr; // symmetric matrices have no lower array (lduMatrix.C:328-345)
         m.upperPtr_ = &upper;
         m.diagPtr_ = &diag;
         m.lowerSortPtr_ = &lowerSort;

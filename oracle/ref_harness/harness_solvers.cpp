@@ -1,0 +1,123 @@
+/*
+ * harness_solvers.cpp -- runs the REFERENCE'S OWN Krylov solver loops on the CPU.  TEST
+ * INFRASTRUCTURE ONLY.  Included by path from /root/reference (symlinks in oracle/_ref/inc_solvers/):
+ *   LDU/solvers/PCG/PCG.C:69-208                 PCG::solve
+ *   LDU/solvers/PBiCG/PBiCG.C:68-246             PBiCG::solve
+ *   LDU/solvers/PBiCGStab/PBiCGStab.C:66-300     PBiCGStab::solve (with its yA/zA slip, :263-270)
+ *   LDU/preconditioners/AINVPreconditioner/AINVPreconditioner.C, AINVPreconditionerF.H
+ *   LDU/preconditioners/diagonalPreconditioner/diagonalPreconditioner.C
+ *   LDU/preconditioners/noPreconditioner/noPreconditioner.C
+ *   LDU/lduMatrix/lduMatrixATmul.C, lduMatrixFunctors.H, lduMatrixSolverFunctors.H,
+ *   LDU/lduAddressing/lduAddressingFunctors.H
+ * against oracle/ref_harness/shim_solvers/ (+ shim/).  What the shims restate instead of including is
+ * listed at the top of shim_solvers/solver_shim.h.
+ */
+#include "lduMatrix.H" /* shim_solvers */
+
+#include "lduMatrixATmul.C"
+#include "AINVPreconditioner.C"
+#include "diagonalPreconditioner.C"
+#include "noPreconditioner.C"
+#include "PCG.C"
+#include "PBiCG.C"
+#include "PBiCGStab.C"
+
+#include <cstring>
+
+namespace Foam
+{
+int lduMatrixSolutionCache::favourSpeed = 0;
+int lduMatrix::debug = 0;
+const gpuField<scalar> &lduMatrixSolutionCache::first(label size) { return ScratchPool::get("first", size); }
+
+// lduMatrixPreconditioner.C:38-62 (name as printed) and :65-140 (selection; DIC and DILU are registered
+// names of the AINV implementation in RapidCFD)
+word lduMatrix::preconditioner::getName(const dictionary &d)
+{
+    if (d.preconditioner == "DIC" || d.preconditioner == "DILU") return AINVPreconditioner::typeName;
+    return d.preconditioner;
+}
+autoPtr<lduMatrix::preconditioner> lduMatrix::preconditioner::New(const solver &sol, const dictionary &d)
+{
+    const word &n = d.preconditioner;
+    if (n == "DIC" || n == "DILU" || n == "AINV") return autoPtr<preconditioner>(new AINVPreconditioner(sol, d));
+    if (n == "diagonal") return autoPtr<preconditioner>(new diagonalPreconditioner(sol, d));
+    if (n == "none") return autoPtr<preconditioner>(new noPreconditioner(sol, d));
+    return autoPtr<preconditioner>(nullptr);
+}
+} // namespace Foam
+
+using namespace Foam;
+
+extern "C" {
+/* solver: "PCG" | "PBiCG" | "PBiCGStab"; returns 0, or -1 unknown solver, -2 unknown preconditioner.
+ * perf[0..4] = initialResidual, finalResidual, nIterations, converged, singular; name receives the
+ * printed solver name (preconditioner + typeName). */
+int ref_solve(const char *solverName, const char *precond, int favourSpeed, int n, int nF, const int *l, const int *u,
+              const int *ownerStart, const int *losortStart, const int *losort, const double *dg, const double *up,
+              const double *lo, double tolerance, double relTol, int maxIter, int minIter, double *psi_io,
+              const double *source, double *perf, char *name, int nameCap)
+{
+    lduAddressing addr;
+    std::vector<label> ownerSort(nF);
+    std::vector<scalar> ls(nF), us(nF);
+    for (int k = 0; k < nF; k++) {
+        ownerSort[k] = l[losort[k]];
+        ls[k] = (lo ? lo : up)[losort[k]];
+        us[k] = up[losort[k]];
+    }
+    addr.nCells_ = n;
+    addr.lower_.view(l, nF);
+    addr.upper_.view(u, nF);
+    addr.ownerStart_.view(ownerStart, n + 1);
+    addr.losortStart_.view(losortStart, n + 1);
+    addr.losort_.view(losort, nF);
+    addr.ownerSort_.view(ownerSort.data(), nF);
+    scalargpuField lower(lo ? lo : up, nF), upper(up, nF), diag(dg, n), lowerSort(ls.data(), nF), upperSort(us.data(), nF);
+    lduMatrix m;
+    m.addr_ = &addr;
+    m.lowerPtr_ = lo ? &lower : nullptr;
+    m.upperPtr_ = &upper;
+    m.diagPtr_ = &diag;
+    m.lowerSortPtr_ = &lowerSort;
+    m.upperSortPtr_ = &upperSort;
+    m.level_ = 0;
+    m.coarsest_ = false;
+    lduMatrixSolutionCache::favourSpeed = favourSpeed;
+
+    dictionary d;
+    d.preconditioner = precond;
+    d.tolerance = tolerance;
+    d.relTol = relTol;
+    d.maxIter = maxIter;
+    d.minIter = minIter;
+    FieldField<gpuField, scalar> noCoeffs(0);
+    lduInterfaceFieldPtrsList noInterfaces;
+    {
+        // unknown preconditioner: the reference aborts in preconditioner::New; report it instead
+        const word p(precond);
+        if (!(p == "DIC" || p == "DILU" || p == "AINV" || p == "diagonal" || p == "none")) return -2;
+    }
+    std::unique_ptr<lduMatrix::solver> s;
+    if (!strcmp(solverName, "PCG"))
+        s.reset(new PCG("psi", m, noCoeffs, noCoeffs, noInterfaces, d));
+    else if (!strcmp(solverName, "PBiCG"))
+        s.reset(new PBiCG("psi", m, noCoeffs, noCoeffs, noInterfaces, d));
+    else if (!strcmp(solverName, "PBiCGStab"))
+        s.reset(new PBiCGStab("psi", m, noCoeffs, noCoeffs, noInterfaces, d));
+    else
+        return -1;
+    scalargpuField psi(psi_io, n), src(source, n);
+    solverPerformance sp = s->solve(psi, src, 0);
+    perf[0] = sp.initialResidual();
+    perf[1] = sp.finalResidual();
+    perf[2] = sp.nIterations();
+    perf[3] = sp.converged();
+    perf[4] = sp.singular();
+    if (name && nameCap > 0) {
+        strncpy(name, sp.solverName().c_str(), (size_t)nameCap - 1);
+        name[nameCap - 1] = 0;
+    }
+    return 0;
+}
+}

@@ -15,8 +15,12 @@
 #ifndef __CUDACC__
 #define __host__
 #define __device__
-#endif
 #define __HOST____DEVICE__
+#define SHIM_HD
+#else /* device probe (ref_harness/device_probe.cu): keep the qualifiers so that nvcc emits the functors */
+#define __HOST____DEVICE__ __host__ __device__
+#define SHIM_HD __host__ __device__
+#endif
 
 #include <cstddef>
 #include <functional>
@@ -53,7 +57,8 @@ public:
     gpuList(label n, const T &v) : own_((size_t)n, v), p_(own_.data()), n_(n) {}
     gpuList(T *p, label n) : p_(p), n_(n) {}
     gpuList(const T *p, label n) : p_(const_cast<T *>(p)), n_(n) {}
-    gpuList(const gpuList &o) : own_(o.own_), p_(o.own_.empty() ? o.p_ : own_.data()), n_(o.n_) {}
+    gpuList(const gpuList &o) : own_(o.p_, o.p_ + o.n_), p_(own_.data()), n_(o.n_) {} // deep copy
+    gpuList(const gpuList &parent, label n) : p_(parent.p_), n_(n) {}                  // "delegate": a view
     gpuList &operator=(const gpuList &o)
     {
         for (label i = 0; i < n_ && i < o.n_; i++) p_[i] = o.p_[i];
@@ -141,15 +146,15 @@ public:
 template <class T> class unityOp
 {
 public:
-    T operator()(const T &x) const { return x; }
+    SHIM_HD T operator()(const T &x) const { return x; }
 };
 template <class T> class sumOp
 {
 public:
-    T operator()(const T &x, const T &y) const { return x + y; }
+    SHIM_HD T operator()(const T &x, const T &y) const { return x + y; }
 };
 template <class R, class T> struct negateUnaryOperatorFunctor {
-    R operator()(const T &x) const { return -x; }
+    SHIM_HD R operator()(const T &x) const { return -x; }
 };
 
 // ---- Textures.H (src/OpenFOAM/device/Textures.H): texture fetch == plain load ----
@@ -158,8 +163,8 @@ template <class T> class textures
     const T *data_;
 
 public:
-    explicit textures(const T *d) : data_(d) {}
-    T operator[](const int &i) const { return data_[i]; }
+    SHIM_HD explicit textures(const T *d) : data_(d) {}
+    SHIM_HD T operator[](const int &i) const { return data_[i]; }
 };
 template <class T> class textureBind
 {
@@ -173,6 +178,7 @@ public:
 // ---- lduMatrixSolutionCache::favourSpeed (selects the reference's "fast" sorted-coefficient path) ----
 struct lduMatrixSolutionCache {
     static int favourSpeed;
+    static const gpuField<scalar> &first(label size); // a scratch vector (defined by the solver harness)
 };
 
 // ---- lduAddressing: the arrays of LDU/lduAddressing/lduAddressing.H:200-255, supplied by the test ----
@@ -198,6 +204,17 @@ public:
 class lduMatrix
 {
 public:
+    class solver;         // defined in shim_solvers/solver_shim.h (only the solver harness needs them)
+    class preconditioner;
+    class smoother;
+    static int debug;
+    struct MeshStub {
+        int comm() const { return 0; }
+    };
+    MeshStub lduMesh_;
+    const MeshStub &mesh() const { return lduMesh_; }
+    bool symmetric() const { return lowerPtr_ == nullptr || lowerPtr_ == upperPtr_; }
+    bool asymmetric() const { return !symmetric(); }
     const lduAddressing *addr_;
     scalargpuField *lowerPtr_, *upperPtr_, *diagPtr_, *lowerSortPtr_, *upperSortPtr_;
     int level_;

@@ -97,3 +97,34 @@ def pair_agglomerate(nCells, lower, upper, faceWeights, forward=1):
     out = np.zeros(int(nCells), dtype=np.int32)
     nC = _libg.ref_pair_agglomerate(int(nCells), len(l), _p(l), _p(u), _p(w), C.byref(fwd), _p(out))
     return out, nC, fwd.value
+
+
+_LIB_SOLVERS = os.path.join(_HERE, "_ref", "libref_solvers.so")
+_libs = None
+
+
+def solve(solver, precond, nCells, lower, upper, ownerStart, losortStart, losort, diag, upperC, lowerC, psi0, source,
+          tolerance=1e-6, relTol=0.0, maxIter=1000, minIter=0, favourSpeed=0):
+    """The reference's PCG::solve / PBiCG::solve / PBiCGStab::solve (PCG.C:69-208, PBiCG.C:68-246,
+    PBiCGStab.C:66-300) with its own preconditioner classes.  Returns (psi, dict(initialResidual,
+    finalResidual, nIterations, converged, singular, solverName))."""
+    global _libs
+    if _libs is None:
+        if not available() or not os.path.exists(_LIB_SOLVERS):
+            raise RuntimeError("oracle/_ref/libref_solvers.so is not built (needs /root/reference)")
+        _libs = C.CDLL(_LIB_SOLVERS)
+        _libs.ref_solve.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8 + \
+            [C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+    l, u, os_, ls, lo = _i(lower), _i(upper), _i(ownerStart), _i(losortStart), _i(losort)
+    dg, up, low = _d(diag), _d(upperC), _d(lowerC)
+    psi = _d(psi0).copy()
+    src = _d(source)
+    perf = np.zeros(5)
+    name = C.create_string_buffer(64)
+    rc = _libs.ref_solve(solver.encode(), precond.encode(), int(favourSpeed), int(nCells), len(l), _p(l), _p(u), _p(os_),
+                         _p(ls), _p(lo), _p(dg), _p(up), _p(low), float(tolerance), float(relTol), int(maxIter),
+                         int(minIter), _p(psi), _p(src), _p(perf), name, 64)
+    if rc != 0:
+        raise ValueError({-1: "unknown solver", -2: "unknown preconditioner"}.get(rc, rc))
+    return psi, dict(initialResidual=perf[0], finalResidual=perf[1], nIterations=int(perf[2]), converged=bool(perf[3]),
+                     singular=bool(perf[4]), solverName=name.value.decode())
