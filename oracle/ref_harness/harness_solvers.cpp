@@ -4,6 +4,8 @@
  *   LDU/solvers/PCG/PCG.C:69-208                 PCG::solve
  *   LDU/solvers/PBiCG/PBiCG.C:68-246             PBiCG::solve
  *   LDU/solvers/PBiCGStab/PBiCGStab.C:66-300     PBiCGStab::solve (with its yA/zA slip, :263-270)
+ *   LDU/solvers/smoothSolver/smoothSolver.C:77-193   smoothSolver::solve
+ *   LDU/smoothers/Jacobi/JacobiSmoother.C:39-148, JacobiSmootherF.H
  *   LDU/preconditioners/AINVPreconditioner/AINVPreconditioner.C, AINVPreconditionerF.H
  *   LDU/preconditioners/diagonalPreconditioner/diagonalPreconditioner.C
  *   LDU/preconditioners/noPreconditioner/noPreconditioner.C
@@ -21,6 +23,8 @@
 #include "PCG.C"
 #include "PBiCG.C"
 #include "PBiCGStab.C"
+#include "JacobiSmoother.C"
+#include "smoothSolver.C"
 
 #include <cstring>
 
@@ -29,6 +33,19 @@ namespace Foam
 int lduMatrixSolutionCache::favourSpeed = 0;
 int lduMatrix::debug = 0;
 const gpuField<scalar> &lduMatrixSolutionCache::first(label size) { return ScratchPool::get("first", size); }
+const gpuField<scalar> &lduMatrixSolutionCache::second(label size) { return ScratchPool::get("second", size); }
+
+// lduMatrixSmoother.C: selection by the `smoother` word; GaussSeidel is a JacobiSmoother subclass in RapidCFD
+// (GaussSeidelSmoother.C:43-69)
+autoPtr<lduMatrix::smoother> lduMatrix::smoother::New(const word &fieldName, const lduMatrix &matrix,
+                                                      const FieldField<gpuField, scalar> &bou,
+                                                      const FieldField<gpuField, scalar> &intc,
+                                                      const lduInterfaceFieldPtrsList &ifs, const dictionary &d)
+{
+    if (d.smoother == "GaussSeidel" || d.smoother == "Jacobi")
+        return autoPtr<smoother>(new JacobiSmoother(fieldName, matrix, bou, intc, ifs, d));
+    return autoPtr<smoother>(nullptr);
+}
 
 // lduMatrixPreconditioner.C:38-62 (name as printed) and :65-140 (selection; DIC and DILU are registered
 // names of the AINV implementation in RapidCFD)
@@ -56,7 +73,7 @@ extern "C" {
 int ref_solve(const char *solverName, const char *precond, int favourSpeed, int n, int nF, const int *l, const int *u,
               const int *ownerStart, const int *losortStart, const int *losort, const double *dg, const double *up,
               const double *lo, double tolerance, double relTol, int maxIter, int minIter, double *psi_io,
-              const double *source, double *perf, char *name, int nameCap)
+              const double *source, double *perf, char *name, int nameCap, int nSweeps, double omega)
 {
     lduAddressing addr;
     std::vector<label> ownerSort(nF);
@@ -87,6 +104,9 @@ int ref_solve(const char *solverName, const char *precond, int favourSpeed, int 
 
     dictionary d;
     d.preconditioner = precond;
+    d.smoother = precond; // smoothSolver reads `smoother` where the Krylov solvers read `preconditioner`
+    d.nSweeps = nSweeps;
+    d.omega = omega;
     d.tolerance = tolerance;
     d.relTol = relTol;
     d.maxIter = maxIter;
@@ -96,7 +116,10 @@ int ref_solve(const char *solverName, const char *precond, int favourSpeed, int 
     {
         // unknown preconditioner: the reference aborts in preconditioner::New; report it instead
         const word p(precond);
-        if (!(p == "DIC" || p == "DILU" || p == "AINV" || p == "diagonal" || p == "none")) return -2;
+        const bool smooth = !strcmp(solverName, "smoothSolver");
+        if (smooth ? !(p == "GaussSeidel" || p == "Jacobi")
+                   : !(p == "DIC" || p == "DILU" || p == "AINV" || p == "diagonal" || p == "none"))
+            return -2;
     }
     std::unique_ptr<lduMatrix::solver> s;
     if (!strcmp(solverName, "PCG"))
@@ -105,6 +128,8 @@ int ref_solve(const char *solverName, const char *precond, int favourSpeed, int 
         s.reset(new PBiCG("psi", m, noCoeffs, noCoeffs, noInterfaces, d));
     else if (!strcmp(solverName, "PBiCGStab"))
         s.reset(new PBiCGStab("psi", m, noCoeffs, noCoeffs, noInterfaces, d));
+    else if (!strcmp(solverName, "smoothSolver"))
+        s.reset(new smoothSolver("psi", m, noCoeffs, noCoeffs, noInterfaces, d));
     else
         return -1;
     scalargpuField psi(psi_io, n), src(source, n);

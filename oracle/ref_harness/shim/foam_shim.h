@@ -112,6 +112,12 @@ public:
     }
 };
 
+template <class T> tmp<gpuField<T>> operator-(const gpuField<T> &a, const gpuField<T> &b)
+{
+    gpuField<T> *r = new gpuField<T>(a.size());
+    for (label i = 0; i < a.size(); i++) r->data()[i] = a.data()[i] - b.data()[i];
+    return tmp<gpuField<T>>(r);
+}
 template <class T> tmp<gpuField<T>> operator-(const gpuField<T> &f)
 {
     gpuField<T> *r = new gpuField<T>(f.size());
@@ -178,7 +184,8 @@ public:
 // ---- lduMatrixSolutionCache::favourSpeed (selects the reference's "fast" sorted-coefficient path) ----
 struct lduMatrixSolutionCache {
     static int favourSpeed;
-    static const gpuField<scalar> &first(label size); // a scratch vector (defined by the solver harness)
+    static const gpuField<scalar> &first(label size); // scratch vectors (defined by the solver harness)
+    static const gpuField<scalar> &second(label size);
 };
 
 // ---- lduAddressing: the arrays of LDU/lduAddressing/lduAddressing.H:200-255, supplied by the test ----
@@ -234,6 +241,15 @@ public:
     }
     void updateMatrixInterfaces(const FieldField<gpuField, scalar> &, const lduInterfaceFieldPtrsList &,
                                 const scalargpuField &, scalargpuField &, const direction) const
+    {
+    }
+    // the smoothers pass a sixth argument (negate): lduMatrixUpdateMatrixInterfaces.C:30-276
+    void initMatrixInterfaces(const FieldField<gpuField, scalar> &, const lduInterfaceFieldPtrsList &,
+                              const scalargpuField &, scalargpuField &, const direction, bool) const
+    {
+    }
+    void updateMatrixInterfaces(const FieldField<gpuField, scalar> &, const lduInterfaceFieldPtrsList &,
+                                const scalargpuField &, scalargpuField &, const direction, bool) const
     {
     }
 

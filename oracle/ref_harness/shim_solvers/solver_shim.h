@@ -32,10 +32,23 @@ public:
 };
 inline word operator+(const word &a, const word &b) { return word(static_cast<const std::string &>(a) + b); }
 
-struct dictionary { // the keys lduMatrix::solver::readControls reads (lduMatrixSolver.C:167-173)
-    word preconditioner;
-    scalar tolerance = 1e-6, relTol = 0;
-    label maxIter = 1000, minIter = 0;
+struct dictionary { // the keys lduMatrix::solver::readControls reads (lduMatrixSolver.C:167-173) + smoothers'
+    word preconditioner, smoother;
+    scalar tolerance = 1e-6, relTol = 0, omega = -1; // omega < 0: entry absent
+    label maxIter = 1000, minIter = 0, nSweeps = 1;
+    bool readIfPresent(const char *key, scalar &v) const
+    {
+        if (std::string(key) == "omega" && omega >= 0) {
+            v = omega;
+            return true;
+        }
+        return false;
+    }
+    template <class T> T lookupOrDefault(const char *key, const T &dflt) const
+    {
+        if (std::string(key) == "nSweeps") return (T)nSweeps;
+        return dflt;
+    }
 };
 
 #define defineTypeNameAndDebug(Type, DebugSwitch)         \
@@ -44,6 +57,7 @@ struct dictionary { // the keys lduMatrix::solver::readControls reads (lduMatrix
 
 struct NullStream {
     template <class T> NullStream &operator<<(const T &) { return *this; }
+    NullStream &masterStream(int) { return *this; }
 };
 static NullStream Info;
 static const char endl = '\n';
@@ -155,6 +169,13 @@ public:
     }
     virtual ~solver() {}
     const lduMatrix &matrix() const { return matrix_; }
+    void readControls() // lduMatrixSolver.C:167-173
+    {
+        maxIter_ = controlDict_.maxIter;
+        minIter_ = controlDict_.minIter;
+        tolerance_ = controlDict_.tolerance;
+        relTol_ = controlDict_.relTol;
+    }
     virtual solverPerformance solve(scalargpuField &psi, const scalargpuField &source, const direction cmpt = 0) const = 0;
     // lduMatrixSolver.C:205-236 -- sumA is the reference's (lduMatrixATmul.C:345-395)
     scalar normFactor(const scalargpuField &psi, const scalargpuField &source, const scalargpuField &Apsi,
@@ -190,6 +211,33 @@ public:
     }
     static word getName(const dictionary &solverControls);
     static autoPtr<preconditioner> New(const solver &sol, const dictionary &solverControls);
+};
+
+class lduMatrix::smoother // lduMatrix.H:262-414
+{
+protected:
+    word fieldName_;
+    const lduMatrix &matrix_;
+    const FieldField<gpuField, scalar> &interfaceBouCoeffs_;
+    const FieldField<gpuField, scalar> &interfaceIntCoeffs_;
+    lduInterfaceFieldPtrsList interfaces_;
+
+public:
+    template <class T> struct addsymMatrixConstructorToTable {
+    };
+    template <class T> struct addasymMatrixConstructorToTable {
+    };
+    smoother(const word &fieldName, const lduMatrix &matrix, const FieldField<gpuField, scalar> &bou,
+             const FieldField<gpuField, scalar> &intc, const lduInterfaceFieldPtrsList &ifs)
+        : fieldName_(fieldName), matrix_(matrix), interfaceBouCoeffs_(bou), interfaceIntCoeffs_(intc), interfaces_(ifs)
+    {
+    }
+    virtual ~smoother() {}
+    virtual void smooth(scalargpuField &psi, const scalargpuField &source, const direction cmpt,
+                        const label nSweeps) const = 0;
+    static autoPtr<smoother> New(const word &fieldName, const lduMatrix &matrix, const FieldField<gpuField, scalar> &bou,
+                                 const FieldField<gpuField, scalar> &intc, const lduInterfaceFieldPtrsList &ifs,
+                                 const dictionary &solverControls);
 };
 
 // ---- scratch vectors: PCGCache.H / lduMatrixSolutionCache.H hand out process-lifetime buffers ----

@@ -104,9 +104,10 @@ _libs = None
 
 
 def solve(solver, precond, nCells, lower, upper, ownerStart, losortStart, losort, diag, upperC, lowerC, psi0, source,
-          tolerance=1e-6, relTol=0.0, maxIter=1000, minIter=0, favourSpeed=0):
+          tolerance=1e-6, relTol=0.0, maxIter=1000, minIter=0, favourSpeed=0, nSweeps=1, omega=-1.0):
     """The reference's PCG::solve / PBiCG::solve / PBiCGStab::solve (PCG.C:69-208, PBiCG.C:68-246,
-    PBiCGStab.C:66-300) with its own preconditioner classes.  Returns (psi, dict(initialResidual,
+    PBiCGStab.C:66-300) with its own preconditioner classes, or smoothSolver::solve (smoothSolver.C:77-193,
+    `precond` = smoother word, nSweeps, omega < 0 = not in the dictionary) with its JacobiSmoother.  Returns (psi, dict(initialResidual,
     finalResidual, nIterations, converged, singular, solverName))."""
     global _libs
     if _libs is None:
@@ -114,7 +115,8 @@ def solve(solver, precond, nCells, lower, upper, ownerStart, losortStart, losort
             raise RuntimeError("oracle/_ref/libref_solvers.so is not built (needs /root/reference)")
         _libs = C.CDLL(_LIB_SOLVERS)
         _libs.ref_solve.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8 + \
-            [C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+            [C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int,
+             C.c_int, C.c_double]
     l, u, os_, ls, lo = _i(lower), _i(upper), _i(ownerStart), _i(losortStart), _i(losort)
     dg, up, low = _d(diag), _d(upperC), _d(lowerC)
     psi = _d(psi0).copy()
@@ -123,7 +125,7 @@ def solve(solver, precond, nCells, lower, upper, ownerStart, losortStart, losort
     name = C.create_string_buffer(64)
     rc = _libs.ref_solve(solver.encode(), precond.encode(), int(favourSpeed), int(nCells), len(l), _p(l), _p(u), _p(os_),
                          _p(ls), _p(lo), _p(dg), _p(up), _p(low), float(tolerance), float(relTol), int(maxIter),
-                         int(minIter), _p(psi), _p(src), _p(perf), name, 64)
+                         int(minIter), _p(psi), _p(src), _p(perf), name, 64, int(nSweeps), float(omega))
     if rc != 0:
         raise ValueError({-1: "unknown solver", -2: "unknown preconditioner"}.get(rc, rc))
     return psi, dict(initialResidual=perf[0], finalResidual=perf[1], nIterations=int(perf[2]), converged=bool(perf[3]),

@@ -161,3 +161,22 @@ def test_loop_semantics_match_reference_code(meshmod, orc):
         assert abs(pr["finalResidual"] - po.finalResidual) <= 1e-10 * max(po.finalResidual, 1e-300), kw
     with pytest.raises(ValueError):
         ref_ldu.solve("PCG", "FDIC", *args, z, b)
+
+
+@pytest.mark.parametrize("kind", ["P", "U"])
+def test_smooth_solver_matches_reference_code_bit_for_bit(meshmod, orc, kind):
+    """smoothSolver.C:77-193 + JacobiSmoother.C:39-148 (the reference's own loops): no vector update
+    outside the row functor, so solution and residuals are identical to the last bit, for positive
+    and negative nSweeps, a dictionary omega, and the `(nIterations += nSweeps) < maxIter` test."""
+    m, M, args, b = _solver_case(meshmod, orc, kind)
+    z = np.zeros(m.nCells)
+    for kw in (dict(tolerance=1e-6, maxIter=200, nSweeps=1), dict(tolerance=1e-6, maxIter=200, nSweeps=3),
+               dict(nSweeps=-4), dict(tolerance=1e-6, maxIter=50, nSweeps=2, omega=0.7),
+               dict(tolerance=0.0, maxIter=7, nSweeps=2), dict(tolerance=1e30, maxIter=9, nSweeps=2, minIter=5)):
+        for smoother in ("GaussSeidel", "Jacobi"):
+            psi_o, po, _ = M.solve("smoothSolver", smoother, z, b, **kw)
+            psi_r, pr = ref_ldu.solve("smoothSolver", smoother, *args, z, b, **kw)
+            assert pr["nIterations"] == po.nIterations and pr["converged"] == bool(po.converged), kw
+            assert np.array_equal(psi_r, psi_o), kw
+            assert pr["finalResidual"] == po.finalResidual and pr["initialResidual"] == po.initialResidual, kw
+            assert pr["solverName"] == po.solverName.decode() == "smoothSolver"
