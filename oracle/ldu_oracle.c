@@ -1,6 +1,6 @@
 /*
  * ldu_oracle.c -- CPU restatement of the RapidCFD-dev lduMatrix solver core.
- * TEST INFRASTRUCTURE ONLY (see ldu_oracle.h).  PARITY UNPINNED by reference tests.
+ * TEST INFRASTRUCTURE ONLY (see ldu_oracle.h for what is pinned to the reference's own code).
  *
  * Paths cited below are relative to /root/reference/src/OpenFOAM/matrices/lduMatrix/
  * (abbreviated LDU/) unless they start with another top-level directory.

@@ -5,13 +5,22 @@
  * call this.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs use it, and only as the checker or the CPU baseline.
  *
- * PARITY UNPINNED: the reference (SimFlowCFD/RapidCFD-dev @ 975bd36) ships no tests,
- * fixtures or golden vectors for this path and cannot be
- * built in this image (needs wmake + flex + MPI + all of libOpenFOAM).  This file is
- * an independent restatement of the algorithms, every function citing the reference
- * file:line it follows; it is validated by analytic properties (dense-matrix SpMV,
- * adjointness, CG exactness on tiny systems, eigenpairs of the 7-point Laplacian) in
- * tests/test_oracle_*.py.
+ * PARITY: the reference (SimFlowCFD/RapidCFD-dev @ 975bd36) ships no tests, fixtures or golden
+ * vectors for this path and cannot be built as a whole in this image
+ * (wmake + flex + MPI + all of libOpenFOAM).  Its hot-path SOURCE FILES, however, compile for the
+ * host against small type shims (oracle/ref_harness/, `make -C oracle ref` -> oracle/_ref/), and
+ * tests/test_reference_functors.py runs them beside this restatement:
+ *   PINNED to reference code, bit for bit on hex meshes: Amul, Tmul, sumA, residual, H1
+ *     (lduMatrixATmul.C), AINV precondition / preconditionT, the Jacobi sweep, smoothSolver,
+ *     the GAMG V-cycle with scaling and all sweep controls (GAMGSolverSolve.C, GAMGSolverScale.C),
+ *     the pair agglomeration maps (pairGAMGAgglomerate.C);
+ *   PINNED to rounding level (the reference's vector updates run unfused on the host, here they are
+ *     the FMAs nvcc emits): PCG, PBiCG, PBiCGStab loops incl. iteration counts, names, loop limits;
+ *   UNPINNED (restated from the source, checked by analytic properties only): coarse addressing and
+ *     coarse-matrix assembly, H, faceH, coupled interfaces (processor, cyclic), normFactor and the
+ *     convergence test (restated inside the shims too), the face-sum kernels' oracle, the dense LU.
+ * Analytic checks (dense-matrix SpMV, adjointness, CG exactness on tiny systems, eigenpairs of the
+ * 7-point Laplacian, decomposed vs single domain) are in tests/test_oracle_*.py.
  *
  * Conventions: scalar = double, label = int32 (reference: etc/bashrc:76, label.H:46).
  * Face f has owner l[f] < neighbour u[f]; upper[f] = A(l,u), lower[f] = A(u,l);

@@ -2,8 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs.  The product package (rapidcfd-dev_b200/) never
-imports this module.  Parity is unpinned by the reference's own tests (it has none);
-see oracle/ldu_oracle.h.
+imports this module.  The reference has no tests of its own; what is pinned to its source code
+(oracle/ref_ldu.py, tests/test_reference_functors.py) and what is not is listed in oracle/ldu_oracle.h.
 """
 import ctypes as C
 import os

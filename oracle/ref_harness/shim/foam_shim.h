@@ -75,6 +75,21 @@ public:
         n_ = n;
     }
     label size() const { return n_; }
+    label byteSize() const { return n_ * (label)sizeof(T); }
+    void setSize(label n)
+    {
+        own_.assign((size_t)n, T());
+        p_ = own_.data();
+        n_ = n;
+    }
+    void operator-=(const gpuList &o)
+    {
+        for (label i = 0; i < n_; i++) p_[i] -= o.p_[i];
+    }
+    void operator+=(const gpuList &o)
+    {
+        for (label i = 0; i < n_; i++) p_[i] += o.p_[i];
+    }
     T *data() { return p_; }
     const T *data() const { return p_; }
     iterator begin() { return p_; }
@@ -83,11 +98,20 @@ public:
     const_iterator end() const { return p_ + n_; }
 };
 
+template <class T> class tmp;
 template <class T> class gpuField : public gpuList<T>
 {
 public:
     using gpuList<T>::gpuList;
     using gpuList<T>::operator=;
+    gpuField() {}
+    gpuField(const gpuField &o) : gpuList<T>(o) {}
+    gpuField &operator=(const gpuField &o)
+    {
+        gpuList<T>::operator=(o);
+        return *this;
+    }
+    gpuField(const tmp<gpuField<T>> &t); // deep copy of a temporary (defined after tmp)
 };
 typedef gpuField<scalar> scalargpuField;
 typedef gpuList<label> labelgpuList;
@@ -111,6 +135,8 @@ public:
         owned_ = nullptr;
     }
 };
+
+template <class T> gpuField<T>::gpuField(const tmp<gpuField<T>> &t) : gpuList<T>(static_cast<const gpuList<T> &>(t())) {}
 
 template <class T> tmp<gpuField<T>> operator-(const gpuField<T> &a, const gpuField<T> &b)
 {
@@ -217,6 +243,7 @@ public:
     static int debug;
     struct MeshStub {
         int comm() const { return 0; }
+        template <class V, class Op> void reduce(V &, const Op &) const {} // one rank
     };
     MeshStub lduMesh_;
     const MeshStub &mesh() const { return lduMesh_; }

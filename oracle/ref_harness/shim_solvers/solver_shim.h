@@ -34,6 +34,7 @@ inline word operator+(const word &a, const word &b) { return word(static_cast<co
 
 struct dictionary { // the keys lduMatrix::solver::readControls reads (lduMatrixSolver.C:167-173) + smoothers'
     word preconditioner, smoother;
+    // GAMGSolver::readControls keys (GAMGSolver.C:209-249) are set on the solver object by the harness
     scalar tolerance = 1e-6, relTol = 0, omega = -1; // omega < 0: entry absent
     label maxIter = 1000, minIter = 0, nSweeps = 1;
     bool readIfPresent(const char *key, scalar &v) const
@@ -82,9 +83,24 @@ template <class T> class autoPtr
 public:
     autoPtr(T *p = nullptr) : p_(p) {}
     autoPtr(const autoPtr &o) : p_(o.p_) { o.p_ = nullptr; }
+    autoPtr &operator=(const autoPtr &o) // transfers ownership, like Foam::autoPtr
+    {
+        if (this != &o) {
+            delete p_;
+            p_ = o.p_;
+            o.p_ = nullptr;
+        }
+        return *this;
+    }
     ~autoPtr() { delete p_; }
     T *operator->() const { return p_; }
     T &operator()() const { return *p_; }
+    T *ptr() const
+    {
+        T *r = p_;
+        p_ = nullptr;
+        return r;
+    }
 };
 
 // global sums on one rank, in index order (the oracle's order; the reference's thrust::reduce order is
@@ -117,6 +133,7 @@ class solverPerformance // SolverPerformance.H/.C
 
 public:
     static constexpr scalar great_ = 1e20, small_ = 1e-20, vsmall_ = 1e-300; // SolverPerformance.H:269-275
+    solverPerformance() : initialResidual_(0), finalResidual_(0), noIterations_(0), converged_(false), singular_(false) {}
     solverPerformance(const word &s, const word &f)
         : solverName_(s), fieldName_(f), initialResidual_(0), finalResidual_(0), noIterations_(0), converged_(false),
           singular_(false)
@@ -136,6 +153,7 @@ public:
             converged_ = false;
         return converged_;
     }
+    template <class S> void print(S &) const {}
     bool checkSingularity(const scalar residual) // SolverPerformance.C:32-43
     {
         singular_ = residual < vsmall_;

@@ -130,3 +130,83 @@ def solve(solver, precond, nCells, lower, upper, ownerStart, losortStart, losort
         raise ValueError({-1: "unknown solver", -2: "unknown preconditioner"}.get(rc, rc))
     return psi, dict(initialResidual=perf[0], finalResidual=perf[1], nIterations=int(perf[2]), converged=bool(perf[3]),
                      singular=bool(perf[4]), solverName=name.value.decode())
+
+
+_LIB_GAMGSOLVE = os.path.join(_HERE, "_ref", "libref_gamgsolve.so")
+_libgs = None
+
+
+def coarse_matrix(r, fr, flip, nCoarse, nCoarseFaces, diag, upper, lower):
+    """Coarse-level coefficients by summation (GAMGSolverAgglomerateMatrix.C:37-322): restrict(diag), coarse
+    faces = sums of their fine faces (upper/lower swapped where the face is flipped), faces collapsed into
+    a coarse cell add 2*upper (symmetric) or upper+lower to its diagonal -- every sum in ascending fine
+    index.  Plain numpy (np.add.at is sequential), used to feed the reference's V-cycle."""
+    Dc = np.zeros(nCoarse)
+    np.add.at(Dc, r, diag)
+    Uc = np.zeros(nCoarseFaces)
+    Lc = None if lower is None else np.zeros(nCoarseFaces)
+    inside = fr < 0
+    keep = ~inside
+    if lower is None:
+        np.add.at(Uc, fr[keep], upper[keep])
+        np.add.at(Dc, -1 - fr[inside], 2 * upper[inside])
+    else:
+        fl = flip.astype(bool)
+        np.add.at(Uc, fr[keep], np.where(fl, lower, upper)[keep])
+        np.add.at(Lc, fr[keep], np.where(fl, upper, lower)[keep])
+        np.add.at(Dc, -1 - fr[inside], (upper + lower)[inside])
+    return Dc, Uc, Lc
+
+
+def gamg_solve(g, addr, diag, upper, lower, psi0, source, tolerance=1e-6, relTol=0.0, maxIter=1000, minIter=0,
+               nPreSweeps=0, preSweepsLevelMultiplier=1, maxPreSweeps=4, nPostSweeps=2, postSweepsLevelMultiplier=1,
+               maxPostSweeps=4, nFinestSweeps=2, interpolateCorrection=0, scaleCorrection=None,
+               directSolveCoarsest=1, omega=-1.0, favourSpeed=0):
+    """The reference's GAMGSolver::solve / Vcycle (GAMGSolverSolve.C) on the hierarchy of the oracle's Gamg
+    object `g` (maps + coarse addressing); coarse coefficients from coarse_matrix().  Defaults are
+    GAMGSolver.C:67-77's.  Returns (psi, dict) or raises NotImplementedError where the reference aborts."""
+    global _libgs
+    if _libgs is None:
+        if not available() or not os.path.exists(_LIB_GAMGSOLVE):
+            raise RuntimeError("oracle/_ref/libref_gamgsolve.so is not built (needs /root/reference)")
+        _libgs = C.CDLL(_LIB_GAMGSOLVE)
+    nL = g.nLevels
+    addrs = [addr] + [g.level_addr(k) for k in range(nL)]
+    coeffs = [(_d(diag), _d(upper), _d(lower))]
+    maps = []
+    for k in range(nL):
+        r, fr, fl = g.restrict_addr(k), g.face_restrict_addr(k), g.face_flip(k)
+        maps.append(_i(r))
+        d, u, lo = coeffs[-1]
+        coeffs.append(tuple(_d(x) for x in coarse_matrix(r, fr, fl, g.ncells(k), g.nfaces(k), d, u, lo)))
+    keep = []
+
+    def ptrs(arrs, ct):
+        arr = (C.c_void_p * len(arrs))(*[(a.ctypes.data if a is not None else None) for a in arrs])
+        keep.append((arrs, arr))
+        return arr
+    nC = _i([a.nCells for a in addrs])
+    nF = _i([len(a.lower()) for a in addrs])
+    L = [_i(a.lower()) for a in addrs]
+    U = [_i(a.upper()) for a in addrs]
+    OS = [_i(a.owner_start()) for a in addrs]
+    LS = [_i(a.losort_start()) for a in addrs]
+    LO = [_i(a.losort()) for a in addrs]
+    if scaleCorrection is None:
+        scaleCorrection = 1 if lower is None else 0   # GAMGSolver.C:73: matrix.symmetric()
+    ctl = _i([nPreSweeps, preSweepsLevelMultiplier, maxPreSweeps, nPostSweeps, postSweepsLevelMultiplier,
+              maxPostSweeps, nFinestSweeps, interpolateCorrection, scaleCorrection, directSolveCoarsest, maxIter,
+              minIter, favourSpeed])
+    psi = _d(psi0).copy()
+    src = _d(source)
+    perf = np.zeros(5)
+    _libgs.ref_gamg_solve.argtypes = [C.c_int] + [C.c_void_p] * 12 + [C.c_double, C.c_double, C.c_double] + [C.c_void_p] * 3
+    rc = _libgs.ref_gamg_solve(nL, _p(nC), _p(nF), ptrs(L, 0), ptrs(U, 0), ptrs(OS, 0), ptrs(LS, 0), ptrs(LO, 0),
+                               ptrs([c[0] for c in coeffs], 0), ptrs([c[1] for c in coeffs], 0),
+                               ptrs([c[2] for c in coeffs], 0), ptrs(maps, 0), _p(ctl), float(tolerance), float(relTol),
+                               float(omega), _p(psi), _p(src), _p(perf))
+    if rc == -3:
+        raise NotImplementedError("the reference aborts here: notImplemented(GAMGSolver::interpolate())")
+    assert rc == 0
+    return psi, dict(initialResidual=perf[0], finalResidual=perf[1], nIterations=int(perf[2]), converged=bool(perf[3]),
+                     singular=bool(perf[4]))

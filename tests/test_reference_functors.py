@@ -180,3 +180,38 @@ def test_smooth_solver_matches_reference_code_bit_for_bit(meshmod, orc, kind):
             assert np.array_equal(psi_r, psi_o), kw
             assert pr["finalResidual"] == po.finalResidual and pr["initialResidual"] == po.initialResidual, kw
             assert pr["solverName"] == po.solverName.decode() == "smoothSolver"
+
+
+@pytest.mark.parametrize("kind", ["P", "U"])
+def test_gamg_vcycle_matches_reference_code_bit_for_bit(meshmod, orc, kind):
+    """The reference's own GAMGSolver::solve / Vcycle / scale (GAMGSolverSolve.C, GAMGSolverScale.C) and
+    JacobiSmoother, run on the oracle's level hierarchy: identical cycle counts, solution and residuals
+    to the last bit for every combination of the sweep controls, the scaling switch and the loop limits
+    (`++nIterations < maxIter`, minIter).  With the Krylov coarsest solve only the fused vector updates
+    of that inner solve differ (rounding level).  interpolateCorrection: the reference itself ends in
+    notImplemented() (GAMGSolverInterpolate.C:171); this repo runs the part that exists."""
+    m = meshmod.hex_mesh(12, 10, 8)
+    c = meshmod.pressure_laplacian(m) if kind == "P" else meshmod.momentum_matrix(m)
+    a = orc.Addr(m.nCells, m.lower, m.upper)
+    M = orc.Matrix(a, c["diag"], c["upper"], c["lower"])
+    g = orc.Gamg(a, meshmod.face_area_pair_weights(m), 10)
+    b = M.amul(meshmod.cell_field_global(m, 42))
+    z = np.zeros(m.nCells)
+    for kw in (dict(), dict(nPreSweeps=1), dict(nPreSweeps=2, nFinestSweeps=1, scaleCorrection=1),
+               dict(nPostSweeps=1, maxPostSweeps=2, nFinestSweeps=3), dict(scaleCorrection=0),
+               dict(preSweepsLevelMultiplier=2, nPreSweeps=1, maxPreSweeps=3, postSweepsLevelMultiplier=0),
+               dict(maxIter=3, tolerance=0.0), dict(tolerance=1e30, minIter=2), dict(omega=0.8)):
+        okw = dict(tolerance=1e-8, maxIter=100)
+        okw.update(kw)
+        psi_o, po, ho = g.solve(M, "GaussSeidel", z, b, **okw)
+        psi_r, pr = ref_ldu.gamg_solve(g, a, c["diag"], c["upper"], c["lower"], z, b, **okw)
+        assert pr["nIterations"] == po.nIterations and pr["converged"] == bool(po.converged), kw
+        assert pr["initialResidual"] == po.initialResidual and pr["finalResidual"] == po.finalResidual, kw
+        assert np.array_equal(psi_r, psi_o), kw
+    okw = dict(tolerance=1e-8, maxIter=100, directSolveCoarsest=0)
+    psi_o, po, _ = g.solve(M, "GaussSeidel", z, b, **okw)
+    psi_r, pr = ref_ldu.gamg_solve(g, a, c["diag"], c["upper"], c["lower"], z, b, **okw)
+    assert pr["nIterations"] == po.nIterations
+    np.testing.assert_allclose(psi_r, psi_o, rtol=0, atol=1e-11)
+    with pytest.raises(NotImplementedError):
+        ref_ldu.gamg_solve(g, a, c["diag"], c["upper"], c["lower"], z, b, interpolateCorrection=1)
