@@ -4,6 +4,7 @@
  * The translation unit includes, by path from /root/reference (nothing is copied into this repo):
  *   LDU/lduMatrix/lduMatrixATmul.C            lduMatrix::Amul, Tmul, sumA, residual, H1 and the
  *                                             matrixMultiplyFunctor they launch            (:42-554)
+ *   LDU/lduMatrix/lduMatrixTemplates.C        lduMatrix::H, faceH                          (:50-160)
  *   LDU/lduAddressing/lduAddressingFunctors.H lduAddressingFunctor family, matrixOperation (:10-400)
  *   LDU/lduMatrix/lduMatrixFunctors.H         lduMatrixDiagonalResidualFunctor, ...        (:6-301)
  *   LDU/preconditioners/AINVPreconditioner/AINVPreconditionerF.H                           (:5-100)
@@ -20,7 +21,8 @@
  */
 #include "lduMatrix.H" /* the shim (first on the include path) */
 
-#include "lduMatrixATmul.C" /* reference, through oracle/_ref/inc/ */
+#include "lduMatrixATmul.C"     /* reference, through oracle/_ref/inc/ */
+#include "lduMatrixTemplates.C" /* reference: H, faceH */
 
 #include "AINVPreconditionerF.H"
 #include "JacobiSmootherF.H"
@@ -75,7 +77,9 @@ struct Case {
 
 extern "C" {
 
-/* op: 0 Amul, 1 Tmul, 2 sumA, 3 residual (x = psi, b = source), 4 H1.  favourSpeed selects the
+/* op: 0 Amul, 1 Tmul, 2 sumA, 3 residual (x = psi, b = source), 4 H1, 5 H, 6 faceH (out has nF entries),
+ * 7 negSumDiag, 8 sumDiag, 9 sumMagOffDiag (the compositions of lduMatrixOperations.C:36-104, which lives in a
+ * file with the matrix-algebra operators and is not included whole).  favourSpeed selects the
  * reference's path: 0 = losort indirection, 1/2 = pre-sorted coefficients ("fast"). */
 int ref_matrix_op(int op, int favourSpeed, CASE_ARGS, const double *x, const double *b, double *out)
 {
@@ -105,6 +109,35 @@ int ref_matrix_op(int op, int favourSpeed, CASE_ARGS, const double *x, const dou
     }
     case 4:
         c.m.H1(o);
+        return 0;
+    case 5: {
+        scalargpuField psi(x, n);
+        c.m.H(o, psi);
+        return 0;
+    }
+    case 6: {
+        scalargpuField psi(x, n), fo(out, nF);
+        c.m.faceH(fo, psi);
+        return 0;
+    }
+    case 7: // lduMatrixOperations.C:57-79 (diag starts from the values in `out`)
+        matrixOperation(o.begin(), o, c.addr,
+                        matrixCoeffsFunctor<scalar, negateUnaryOperatorFunctor<scalar, scalar>>(
+                            c.m.lower().data(), negateUnaryOperatorFunctor<scalar, scalar>()),
+                        matrixCoeffsFunctor<scalar, negateUnaryOperatorFunctor<scalar, scalar>>(
+                            c.m.upper().data(), negateUnaryOperatorFunctor<scalar, scalar>()));
+        return 0;
+    case 8: // :36-55
+        matrixOperation(o.begin(), o, c.addr,
+                        matrixCoeffsFunctor<scalar, unityOp<scalar>>(c.m.lower().data(), unityOp<scalar>()),
+                        matrixCoeffsFunctor<scalar, unityOp<scalar>>(c.m.upper().data(), unityOp<scalar>()));
+        return 0;
+    case 9: // :81-104
+        matrixOperation(o.begin(), o, c.addr,
+                        matrixCoeffsFunctor<scalar, magUnaryFunctionFunctor<scalar, scalar>>(
+                            c.m.upper().data(), magUnaryFunctionFunctor<scalar, scalar>()),
+                        matrixCoeffsFunctor<scalar, magUnaryFunctionFunctor<scalar, scalar>>(
+                            c.m.lower().data(), magUnaryFunctionFunctor<scalar, scalar>()));
         return 0;
     }
     return -1;

@@ -24,6 +24,7 @@
 
 #include <cstddef>
 #include <functional>
+#include <stdexcept>
 #include <vector>
 
 #include <thrust/functional.h>
@@ -293,6 +294,28 @@ public:
                                  const direction) const;
     void H1(scalargpuField &) const;
     tmp<scalargpuField> H1() const;
+    // defined by the reference (lduMatrixTemplates.C:50-160)
+    template <class Type> void H(gpuField<Type> &, const gpuField<Type> &) const;
+    template <class Type> tmp<gpuField<Type>> H(const gpuField<Type> &) const;
+    template <class Type> tmp<gpuField<Type>> H(const tmp<gpuField<Type>> &) const;
+    template <class Type> void faceH(gpuField<Type> &, const gpuField<Type> &) const;
+    template <class Type> tmp<gpuField<Type>> faceH(const gpuField<Type> &) const;
+    template <class Type> tmp<gpuField<Type>> faceH(const tmp<gpuField<Type>> &) const;
+    scalargpuField &diag() { return *diagPtr_; }
+};
+
+template <class T> struct pTraits;
+template <> struct pTraits<scalar> {
+    static constexpr scalar zero = 0.0;
+};
+struct FatalStream {
+    template <class T> FatalStream &operator<<(const T &) { return *this; }
+};
+static FatalStream FatalError;
+#define FatalErrorIn(where) ::Foam::FatalError
+inline int exit(FatalStream &) { throw std::runtime_error("FatalError"); }
+template <class R, class T> struct magUnaryFunctionFunctor {
+    SHIM_HD R operator()(const T &x) const { return x < 0 ? -x : x; }
 };
 } // namespace Foam
 #endif

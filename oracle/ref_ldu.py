@@ -58,9 +58,13 @@ class RefMatrix:
         return [self.n, self.nF, _p(l), _p(u), _p(os_), _p(ls), _p(lo), _p(dg), _p(up), _p(low)]
 
     def op(self, which, favourSpeed=0, x=None, b=None):
-        """which: amul | tmul | sumA | residual | H1 (lduMatrixATmul.C)."""
-        code = {"amul": 0, "tmul": 1, "sumA": 2, "residual": 3, "H1": 4}[which]
-        out = np.zeros(self.n)
+        """which: amul | tmul | sumA | residual | H1 (lduMatrixATmul.C) | H | faceH (lduMatrixTemplates.C) |
+        negSumDiag | sumDiag | sumMagOffDiag (lduMatrixOperations.C compositions; `b` = starting diagonal)."""
+        code = {"amul": 0, "tmul": 1, "sumA": 2, "residual": 3, "H1": 4, "H": 5, "faceH": 6, "negSumDiag": 7,
+                "sumDiag": 8, "sumMagOffDiag": 9}[which]
+        out = np.zeros(self.nF if which == "faceH" else self.n)
+        if code >= 7 and b is not None:
+            out[:] = b
         x, b = _d(x), _d(b)
         rc = lib().ref_matrix_op(code, int(favourSpeed), *self._case(), _p(x), _p(b), _p(out))
         assert rc == 0
