@@ -1,8 +1,8 @@
 /*
  * ldu_oracle_gamg.c -- CPU restatement of the RapidCFD-dev GAMG solver (pair
  * agglomeration, coarse addressing, Galerkin-by-summation coarse matrices, V-cycle).
- * TEST INFRASTRUCTURE ONLY (see ldu_oracle.h: V-cycle and pair agglomeration are pinned to the
- * reference's own code; coarse addressing / coarse matrices / interfaces are not).
+ * TEST INFRASTRUCTURE ONLY (see ldu_oracle.h: V-cycle, pair agglomeration, coarse addressing and
+ * combineLevels are pinned to the reference's own code; coarse matrices / interfaces are not).
  *
  * Paths relative to /root/reference/src/OpenFOAM/matrices/lduMatrix/solvers/GAMG/
  * (abbreviated GAMG/).  Multi-rank: processor interfaces are agglomerated as in

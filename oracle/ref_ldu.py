@@ -214,3 +214,35 @@ def gamg_solve(g, addr, diag, upper, lower, psi0, source, tolerance=1e-6, relTol
     assert rc == 0
     return psi, dict(initialResidual=perf[0], finalResidual=perf[1], nIterations=int(perf[2]), converged=bool(perf[3]),
                      singular=bool(perf[4]))
+
+
+_LIB_GAMGADDR = os.path.join(_HERE, "_ref", "libref_gamgaddr.so")
+_libga = None
+
+
+def coarse_levels(nCells, lower, upper, map0, nCoarse0, map1=None, nCoarse1=0):
+    """The reference's GAMGAgglomeration::agglomerateLduAddressing (GAMGAgglomerateLduAddressing.C:245-603)
+    for the restrict map `map0`; with `map1` (level 1 -> level 2) also the next level and then
+    combineLevels(1) (:606-765).  Returns dict(restrict, faceRestrict, flip, coarseOwner, coarseNeighbour,
+    nCoarseCells) describing level 0 afterwards."""
+    global _libga
+    if _libga is None:
+        if not available() or not os.path.exists(_LIB_GAMGADDR):
+            raise RuntimeError("oracle/_ref/libref_gamgaddr.so is not built (needs /root/reference)")
+        _libga = C.CDLL(_LIB_GAMGADDR)
+    l, u, m0 = _i(lower), _i(upper), _i(map0)
+    m1 = None if map1 is None else _i(map1)
+    nF = len(l)
+    r = np.zeros(int(nCells), np.int32)
+    fr = np.zeros(max(nF, 1), np.int32)
+    fl = np.zeros(max(nF, 1), np.uint8)
+    co = np.zeros(max(nF, 1), np.int32)
+    cn = np.zeros(max(nF, 1), np.int32)
+    ncf = C.c_int(0)
+    nc = _libga.ref_coarse_levels(2 if m1 is not None else 1, int(nCells), nF, _p(l), _p(u), _p(m0), int(nCoarse0),
+                                  _p(m1), int(nCoarse1), _p(r), _p(fr), _p(fl), C.byref(ncf), _p(co), _p(cn))
+    if nc < 0:
+        raise RuntimeError("the reference code raised a FatalError")
+    k = ncf.value
+    return dict(restrict=r, faceRestrict=fr[:nF], flip=fl[:nF], coarseOwner=co[:k], coarseNeighbour=cn[:k],
+                nCoarseCells=nc)

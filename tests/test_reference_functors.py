@@ -235,3 +235,42 @@ def test_H_faceH_and_diagonal_sums_match_reference_code(meshmod, orc, kind):
         d = d0.copy()
         fn(a.h, orc._d(upper), orc._d(lower), orc._d(d))
         assert np.array_equal(R.op(name, 0, None, d0), d), name   # all three add to the incoming field
+
+
+@pytest.mark.parametrize("dims", [(12, 10, 8), (7, 5, 3), (9, 9, 9)])
+def test_coarse_addressing_and_combine_levels_match_reference_code(meshmod, orc, dims):
+    """GAMGAgglomeration::agglomerateLduAddressing (GAMGAgglomerateLduAddressing.C:245-603, the reference's
+    own code): coarse owner/neighbour in its discovery + renumbering order, face restrict map and flip
+    map equal the oracle's on every level.  combineLevels (:606-765) applied by the reference to steps 0
+    and 1 gives level 0 of the oracle's mergeLevels-2 hierarchy -- including its rule that the flip of a
+    composed face is the flip of the second step alone (:631)."""
+    m = meshmod.hex_mesh(*dims)
+    a = orc.Addr(m.nCells, m.lower, m.upper)
+    w = meshmod.face_area_pair_weights(m)
+    g1, g2 = orc.Gamg(a, w, 10), orc.Gamg(a, w, 10, mergeLevels=2)
+    lo, up, n = m.lower, m.upper, m.nCells
+    for lev in range(g1.nLevels):
+        R = ref_ldu.coarse_levels(n, lo, up, g1.restrict_addr(lev), g1.ncells(lev))
+        la = g1.level_addr(lev)
+        assert R["nCoarseCells"] == g1.ncells(lev)
+        assert np.array_equal(R["coarseOwner"], la.lower()) and np.array_equal(R["coarseNeighbour"], la.upper())
+        assert np.array_equal(R["faceRestrict"], g1.face_restrict_addr(lev))
+        assert np.array_equal(R["flip"], g1.face_flip(lev))
+        lo, up, n = la.lower(), la.upper(), g1.ncells(lev)
+    R = ref_ldu.coarse_levels(m.nCells, m.lower, m.upper, g1.restrict_addr(0), g1.ncells(0), g1.restrict_addr(1),
+                              g1.ncells(1))
+    la = g2.level_addr(0)
+    assert R["nCoarseCells"] == g2.ncells(0)
+    assert np.array_equal(R["restrict"], g2.restrict_addr(0))
+    assert np.array_equal(R["faceRestrict"], g2.face_restrict_addr(0))
+    assert np.array_equal(R["coarseOwner"], la.lower()) and np.array_equal(R["coarseNeighbour"], la.upper())
+    kept = R["faceRestrict"] >= 0      # the flip of a face that collapses into a cell is never read
+    assert np.array_equal(R["flip"][kept], g2.face_flip(0)[kept])
+    # the rule differs from the exclusive-or of the two steps on some faces: the test would notice a "fixed" rule
+    f0, fr0, f1 = g1.face_flip(0).astype(bool), g1.face_restrict_addr(0), g1.face_flip(1).astype(bool)
+    both = (fr0 >= 0) & kept
+    xor = f0[both] ^ f1[fr0[both]]
+    if dims == (9, 9, 9):
+        assert f0[both].any()          # this mesh has faces flipped in step 0 that survive both steps
+    if f0[both].any():
+        assert np.any(xor != R["flip"][both].astype(bool))
