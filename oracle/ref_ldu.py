@@ -220,11 +220,13 @@ _LIB_GAMGADDR = os.path.join(_HERE, "_ref", "libref_gamgaddr.so")
 _libga = None
 
 
-def coarse_levels(nCells, lower, upper, map0, nCoarse0, map1=None, nCoarse1=0):
+def coarse_levels(nCells, lower, upper, map0, nCoarse0, map1=None, nCoarse1=0, diag=None, upperC=None, lowerC=None):
     """The reference's GAMGAgglomeration::agglomerateLduAddressing (GAMGAgglomerateLduAddressing.C:245-603)
     for the restrict map `map0`; with `map1` (level 1 -> level 2) also the next level and then
     combineLevels(1) (:606-765).  Returns dict(restrict, faceRestrict, flip, coarseOwner, coarseNeighbour,
-    nCoarseCells) describing level 0 afterwards."""
+    nCoarseCells) describing level 0 afterwards; with `diag`/`upperC`/`lowerC` (single step) also the coarse
+    coefficients assembled by GAMG::restrict / symAgglomerate / asymAgglomerate / diag*Agglomerate over the
+    reference-built sorted addressing (GAMGAgglomerationTemplates.C:35-61, GAMGSolverAgglomerateMatrix.C:183-320)."""
     global _libga
     if _libga is None:
         if not available() or not os.path.exists(_LIB_GAMGADDR):
@@ -239,10 +241,19 @@ def coarse_levels(nCells, lower, upper, map0, nCoarse0, map1=None, nCoarse1=0):
     co = np.zeros(max(nF, 1), np.int32)
     cn = np.zeros(max(nF, 1), np.int32)
     ncf = C.c_int(0)
+    dg, up, low = _d(diag), _d(upperC), _d(lowerC)
+    cD = np.zeros(max(int(nCoarse0), 1))
+    cU, cL = np.zeros(max(nF, 1)), np.zeros(max(nF, 1))
+    _libga.ref_coarse_levels.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_int] + \
+        [C.c_void_p] * 12
     nc = _libga.ref_coarse_levels(2 if m1 is not None else 1, int(nCells), nF, _p(l), _p(u), _p(m0), int(nCoarse0),
-                                  _p(m1), int(nCoarse1), _p(r), _p(fr), _p(fl), C.byref(ncf), _p(co), _p(cn))
+                                  _p(m1), int(nCoarse1), _p(r), _p(fr), _p(fl), C.byref(ncf), _p(co), _p(cn),
+                                  _p(dg), _p(up), _p(low), _p(cD), _p(cU), _p(cL))
     if nc < 0:
         raise RuntimeError("the reference code raised a FatalError")
     k = ncf.value
-    return dict(restrict=r, faceRestrict=fr[:nF], flip=fl[:nF], coarseOwner=co[:k], coarseNeighbour=cn[:k],
-                nCoarseCells=nc)
+    out = dict(restrict=r, faceRestrict=fr[:nF], flip=fl[:nF], coarseOwner=co[:k], coarseNeighbour=cn[:k],
+               nCoarseCells=nc)
+    if diag is not None:   # coarse coefficients assembled by the reference's functors (single step)
+        out.update(coarseDiag=cD[:nc], coarseUpper=cU[:k], coarseLower=None if lowerC is None else cL[:k])
+    return out
