@@ -18,7 +18,8 @@
  *     reference's restriction/agglomeration functors);
  *   PINNED to rounding level (the reference's vector updates run unfused on the host, here they are
  *     the FMAs nvcc emits): PCG, PBiCG, PBiCGStab loops incl. iteration counts, names, loop limits;
- *   UNPINNED (restated from the source, checked by analytic properties only): coupled interfaces (processor, cyclic), normFactor and the
+ *   UNPINNED (restated from the source, checked by analytic properties only): coupled interfaces'
+ *     exchange and coarse-level construction (the per-face update arithmetic IS pinned) (processor, cyclic), normFactor and the
  *     convergence test (restated inside the shims too), the face-sum kernels' oracle, the dense LU.
  * Analytic checks (dense-matrix SpMV, adjointness, CG exactness on tiny systems, eigenpairs of the
  * 7-point Laplacian, decomposed vs single domain) are in tests/test_oracle_*.py.

@@ -21,6 +21,8 @@
  */
 #include "lduMatrix.H" /* the shim (first on the include path) */
 
+#include <algorithm>
+
 #include "lduMatrixATmul.C"     /* reference, through oracle/_ref/inc/ */
 #include "lduMatrixTemplates.C" /* reference: H, faceH */
 
@@ -141,6 +143,37 @@ int ref_matrix_op(int op, int favourSpeed, CASE_ARGS, const double *x, const dou
         return 0;
     }
     return -1;
+}
+
+/* coupledFvPatchField::updateInterfaceMatrix (coupledFvPatchField.C:236-257): result[faceCells] (-/+)= coeffs*pnf
+ * through the reference's matrixPatchOperation + matrixInterfaceFunctor (lduAddressingFunctors.H:230-262,
+ * 340-400).  The per-patch sort addressing (unique cells, faces of a cell in ascending patch-face order,
+ * lduAddressing.C:38-130: stable sort by cell) is rebuilt here. */
+int ref_interface_update(int nCells, int nPatchFaces, const int *faceCells, const double *coeffs, const double *pnf,
+                         int negate, double *result_io)
+{
+    std::vector<label> order(nPatchFaces), cells, start;
+    for (int i = 0; i < nPatchFaces; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](label a, label b) { return faceCells[a] < faceCells[b]; });
+    for (int k = 0; k < nPatchFaces; k++) {
+        const label c = faceCells[order[k]];
+        if (cells.empty() || cells.back() != c) {
+            cells.push_back(c);
+            start.push_back(k);
+        }
+    }
+    start.push_back(nPatchFaces);
+    lduAddressing addr;
+    addr.nCells_ = nCells;
+    addr.patchCells_.view(cells.data(), (label)cells.size());
+    addr.patchSort_.view(order.data(), nPatchFaces);
+    addr.patchSortStart_.view(start.data(), (label)start.size());
+    scalargpuField result(result_io, nCells);
+    if (negate)
+        matrixPatchOperation(0, result, addr, matrixInterfaceFunctor<scalar, true>(coeffs, pnf));
+    else
+        matrixPatchOperation(0, result, addr, matrixInterfaceFunctor<scalar, false>(coeffs, pnf));
+    return 0;
 }
 
 /* AINVPreconditionerFunctor<fast,3> exactly as AINVPreconditioner.C:78-117 launches it: transpose swaps

@@ -228,10 +228,11 @@ public:
     const labelgpuList &losortStartAddr() const { return losortStart_; }
     const labelgpuList &losortAddr() const { return losort_; }
     const labelgpuList &ownerSortAddr() const { return ownerSort_; }
-    // coupled-patch sort addressing: never reached without interfaces
-    const labelgpuList &patchSortCells(label) const { return lower_; }
-    const labelgpuList &patchSortAddr(label) const { return lower_; }
-    const labelgpuList &patchSortStartAddr(label) const { return lower_; }
+    // coupled-patch sort addressing of ONE patch (lduAddressing.C:38-167), supplied by the harness
+    labelgpuList patchCells_, patchSort_, patchSortStart_;
+    const labelgpuList &patchSortCells(label) const { return patchCells_; }
+    const labelgpuList &patchSortAddr(label) const { return patchSort_; }
+    const labelgpuList &patchSortStartAddr(label) const { return patchSortStart_; }
 };
 
 // ---- lduMatrix: declarations of the members defined in the reference's lduMatrixATmul.C ----

@@ -46,6 +46,15 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def interface_update(nCells, faceCells, coeffs, pnf, result, negate=False):
+    """coupledFvPatchField::updateInterfaceMatrix through the reference's matrixPatchOperation /
+    matrixInterfaceFunctor: returns result with result[faceCells] -= coeffs*pnf (negate: +=)."""
+    fc, c, v = _i(faceCells), _d(coeffs), _d(pnf)
+    out = _d(result).copy()
+    assert lib().ref_interface_update(int(nCells), len(fc), _p(fc), _p(c), _p(v), int(bool(negate)), _p(out)) == 0
+    return out
+
+
 class RefMatrix:
     """One single-domain LDU matrix handed to the reference code (no coupled interfaces)."""
 

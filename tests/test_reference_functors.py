@@ -298,3 +298,40 @@ def test_coarse_matrix_assembly_matches_reference_functors(meshmod, orc, kind, d
         assert L is None or np.array_equal(R["coarseLower"], Ln), lev
         la = g.level_addr(lev)
         lo, up, n, D, U, L = la.lower(), la.upper(), g.ncells(lev), Dn, Un, Ln
+
+
+def test_interface_update_matches_reference_functor(meshmod, orc):
+    """Coupled-interface contribution (coupledFvPatchField.C:236-257) through the reference's
+    matrixPatchOperation + matrixInterfaceFunctor: the oracle's Amul / residual / Jacobi on a matrix
+    with coupled (cyclic) patches equal the reference's interior operator followed by the reference's
+    interface update, bit for bit -- several patch faces per cell included."""
+    from test_oracle_core import _cyclic_case
+    for kind in ("P", "U"):
+        m, c, ps, fc, nr, lo, hi = _cyclic_case(meshmod, kind)
+        a = orc.Addr(m.nCells, m.lower, m.upper, ps, fc, neighbRank=nr)
+        M = orc.Matrix(a, c["diag"], c["upper"], c["lower"], c["bou"], c["int"])
+        R = ref_ldu.RefMatrix(m.nCells, m.lower, m.upper, a.owner_start(), a.losort_start(), a.losort(),
+                              c["diag"], c["upper"], c["lower"])
+        x = meshmod.cell_field_global(m, 3)
+        n = len(lo)
+        pnf = np.concatenate([x[hi], x[lo]])                 # cyclic: psi at the partner's face cells
+        ref = R.op("amul", 0, x)
+        for p in range(2):                                   # updateMatrixInterfaces visits the patches in order
+            sl = slice(p * n, (p + 1) * n)
+            ref = ref_ldu.interface_update(m.nCells, fc[sl], c["bou"][sl], pnf[sl], ref)
+        assert np.array_equal(ref, M.amul(x))
+        reft = R.op("tmul", 0, x)
+        for p in range(2):
+            sl = slice(p * n, (p + 1) * n)
+            reft = ref_ldu.interface_update(m.nCells, fc[sl], c["int"][sl], pnf[sl], reft)
+        assert np.array_equal(reft, M.tmul(x))
+    # several faces of one patch on the same cell, both signs
+    rng = np.random.default_rng(4)
+    fcs = np.array([3, 1, 3, 0, 1, 3], dtype=np.int32)
+    co, v, r0 = rng.standard_normal(6), rng.standard_normal(6), rng.standard_normal(5)
+    for negate in (False, True):
+        exp = r0.copy()
+        for i in range(6):
+            t = co[i] * v[i]
+            exp[fcs[i]] = exp[fcs[i]] + (t if negate else -t)
+        assert np.array_equal(ref_ldu.interface_update(5, fcs, co, v, r0, negate), exp)
