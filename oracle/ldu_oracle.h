@@ -11,16 +11,19 @@
  * host against small type shims (oracle/ref_harness/, `make -C oracle ref` -> oracle/_ref/), and
  * tests/test_reference_functors.py runs them beside this restatement:
  *   PINNED to reference code, bit for bit on hex meshes: Amul, Tmul, sumA, residual, H1
- *     (lduMatrixATmul.C), H, faceH (lduMatrixTemplates.C), sumDiag/negSumDiag/sumMagOffDiag, AINV precondition / preconditionT, the Jacobi sweep, smoothSolver,
- *     the GAMG V-cycle with scaling and all sweep controls (GAMGSolverSolve.C, GAMGSolverScale.C),
- *     the pair agglomeration maps (pairGAMGAgglomerate.C), coarse addressing / face restrict / flip
- *     maps and combineLevels (GAMGAgglomerateLduAddressing.C), coarse-matrix assembly (the
- *     reference's restriction/agglomeration functors);
+ *     (lduMatrixATmul.C), H, faceH (lduMatrixTemplates.C), sumDiag / negSumDiag / sumMagOffDiag, the
+ *     coupled-interface update arithmetic (matrixPatchOperation + matrixInterfaceFunctor), AINV
+ *     precondition / preconditionT, the Jacobi sweep, smoothSolver, the GAMG V-cycle with scaling and
+ *     all sweep controls (GAMGSolverSolve.C, GAMGSolverScale.C), the pair agglomeration maps
+ *     (pairGAMGAgglomerate.C), coarse addressing / face restrict / flip maps and combineLevels
+ *     (GAMGAgglomerateLduAddressing.C), coarse-matrix assembly (the reference's restriction and
+ *     agglomeration functors);
  *   PINNED to rounding level (the reference's vector updates run unfused on the host, here they are
  *     the FMAs nvcc emits): PCG, PBiCG, PBiCGStab loops incl. iteration counts, names, loop limits;
- *   UNPINNED (restated from the source, checked by analytic properties only): coupled interfaces'
- *     exchange and coarse-level construction (the per-face update arithmetic IS pinned) (processor, cyclic), normFactor and the
- *     convergence test (restated inside the shims too), the face-sum kernels' oracle, the dense LU.
+ *   UNPINNED (restated from the source, checked by analytic properties only): the exchange side of
+ *     the coupled interfaces (processor send/receive, cyclic pairing) and their coarse-level
+ *     construction, normFactor and the convergence test (restated inside the shims too), the
+ *     face-sum kernels' oracle, the dense LU.
  * Analytic checks (dense-matrix SpMV, adjointness, CG exactness on tiny systems, eigenpairs of the
  * 7-point Laplacian, decomposed vs single domain) are in tests/test_oracle_*.py.
  *
