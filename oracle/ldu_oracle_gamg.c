@@ -498,30 +498,55 @@ typedef struct {
     int *piv;
 } dense_lu;
 
+/* LUDecompose: matrices/scalarMatrices/scalarMatrices.C:42-146 -- Crout's method with implicit
+ * (row-scaled) partial pivoting; a later row wins a tie (`>=`), a zero pivot becomes SMALL = 1e-15. */
 static void lu_factor_inplace(dense_lu *d)
 {
     int n = d->n;
-    for (int k = 0; k < n; k++) {
-        int p = k;
-        double mx = fabs(d->lu[(size_t)k * n + k]);
-        for (int i = k + 1; i < n; i++)
-            if (fabs(d->lu[(size_t)i * n + k]) > mx) {
-                mx = fabs(d->lu[(size_t)i * n + k]);
-                p = i;
+    double *A = d->lu;
+    double *vv = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) {
+        double largest = 0.0;
+        for (int j = 0; j < n; j++) {
+            double t = fabs(A[(size_t)i * n + j]);
+            if (t > largest) largest = t;
+        }
+        vv[i] = 1.0 / largest; /* the reference aborts on a zero row ("Singular matrix") */
+    }
+    for (int j = 0; j < n; j++) {
+        for (int i = 0; i < j; i++) {
+            double sum = A[(size_t)i * n + j];
+            for (int k = 0; k < i; k++) sum -= A[(size_t)i * n + k] * A[(size_t)k * n + j];
+            A[(size_t)i * n + j] = sum;
+        }
+        int iMax = 0;
+        double largest = 0.0;
+        for (int i = j; i < n; i++) {
+            double sum = A[(size_t)i * n + j];
+            for (int k = 0; k < j; k++) sum -= A[(size_t)i * n + k] * A[(size_t)k * n + j];
+            A[(size_t)i * n + j] = sum;
+            double t = vv[i] * fabs(sum);
+            if (t >= largest) {
+                largest = t;
+                iMax = i;
             }
-        d->piv[k] = p;
-        if (p != k)
-            for (int j = 0; j < n; j++) {
-                double t = d->lu[(size_t)k * n + j];
-                d->lu[(size_t)k * n + j] = d->lu[(size_t)p * n + j];
-                d->lu[(size_t)p * n + j] = t;
+        }
+        d->piv[j] = iMax;
+        if (j != iMax) {
+            for (int k = 0; k < n; k++) {
+                double t = A[(size_t)j * n + k];
+                A[(size_t)j * n + k] = A[(size_t)iMax * n + k];
+                A[(size_t)iMax * n + k] = t;
             }
-        for (int i = k + 1; i < n; i++) {
-            double fct = d->lu[(size_t)i * n + k] / d->lu[(size_t)k * n + k];
-            d->lu[(size_t)i * n + k] = fct;
-            for (int j = k + 1; j < n; j++) d->lu[(size_t)i * n + j] -= fct * d->lu[(size_t)k * n + j];
+            vv[iMax] = vv[j];
+        }
+        if (A[(size_t)j * n + j] == 0.0) A[(size_t)j * n + j] = 1.0e-15;
+        if (j != n - 1) {
+            double rDiag = 1.0 / A[(size_t)j * n + j];
+            for (int i = j + 1; i < n; i++) A[(size_t)i * n + j] *= rDiag;
         }
     }
+    free(vv);
 }
 
 static dense_lu *lu_factor(const orc_matrix *A, const orc_comm *comm)
@@ -606,17 +631,23 @@ static void lu_solve(const dense_lu *d, const double *bLocal, double *xLocal, co
         free(all);
     } else
         memcpy(b, bLocal, sizeof(double) * (size_t)n);
-    for (int k = 0; k < n; k++) {
-        if (d->piv[k] != k) {
-            double t = b[k];
-            b[k] = b[d->piv[k]];
-            b[d->piv[k]] = t;
+    /* LUBacksubstitute: scalarMatricesTemplates.C:119-164 (forward pass skips the leading zeros of b) */
+    int ii = 0;
+    for (int i = 0; i < n; i++) {
+        int ip = d->piv[i];
+        double sum = b[ip];
+        b[ip] = b[i];
+        if (ii != 0) {
+            for (int j = ii - 1; j < i; j++) sum -= d->lu[(size_t)i * n + j] * b[j];
+        } else if (sum != 0.0) {
+            ii = i + 1;
         }
-        for (int i = k + 1; i < n; i++) b[i] -= d->lu[(size_t)i * n + k] * b[k];
+        b[i] = sum;
     }
     for (int i = n - 1; i >= 0; i--) {
-        for (int j = i + 1; j < n; j++) b[i] -= d->lu[(size_t)i * n + j] * b[j];
-        b[i] /= d->lu[(size_t)i * n + i];
+        double sum = b[i];
+        for (int j = i + 1; j < n; j++) sum -= d->lu[(size_t)i * n + j] * b[j];
+        b[i] = sum / d->lu[(size_t)i * n + i];
     }
     memcpy(xLocal, b + d->offset, sizeof(double) * (size_t)d->nLocal);
     free(b);

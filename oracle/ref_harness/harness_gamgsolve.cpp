@@ -4,12 +4,42 @@
  *   GAMG/GAMGSolverSolve.C:59-619        GAMGSolver::solve, Vcycle, initVcycle, solveCoarsestLevel
  *   GAMG/GAMGSolverScale.C:59-171        GAMGSolver::scale
  *   GAMG/GAMGSolverInterpolate.C:45-110  GAMGSolver::interpolate
+ *   matrices/scalarMatrices/scalarMatrices.C:42-146, scalarMatricesTemplates.C:119-164   the coarsest-level LU
  *   + the smoother, Krylov solvers (coarsest level when directSolveCoarsest is off), preconditioners and
  *     lduMatrixATmul.C as in harness_solvers.cpp
  * against oracle/ref_harness/shim_gamgsolve/ (+ shim_solvers/, shim/).  The level hierarchy (restrict maps,
  * coarse addressing, coarse coefficients) is passed in by the test.
  */
-#include "GAMGSolver.H" /* shim */
+#include "GAMGSolver.H"     /* shim */
+#include "scalarMatrices.H" /* shim */
+
+#include "scalarMatrices.C"          /* reference: LUDecompose (Crout, implicit pivoting) */
+#include "scalarMatricesTemplates.C" /* reference: LUBacksubstitute */
+
+namespace Foam
+{
+// LUscalarMatrix.C:47-56 / LUscalarMatrixTemplates.C:110-126 on one rank: decompose once, back-substitute per solve
+class LUscalarMatrix
+{
+    scalarSquareMatrix lu_;
+    labelList piv_;
+
+public:
+    LUscalarMatrix(label n, const std::vector<scalar> &dense) : lu_(n), piv_(n)
+    {
+        for (label i = 0; i < n; i++)
+            for (label j = 0; j < n; j++) lu_[i][j] = dense[(size_t)i * n + j];
+        LUDecompose(lu_, piv_);
+    }
+    void solve(scalarField &x) const
+    {
+        List<scalar> b(x.size());
+        for (label i = 0; i < x.size(); i++) b[i] = x.data()[i];
+        LUBacksubstitute(lu_, piv_, b);
+        for (label i = 0; i < x.size(); i++) x.data()[i] = b[i];
+    }
+};
+} // namespace Foam
 
 #include "lduMatrixATmul.C"
 #include "AINVPreconditioner.C"
@@ -30,6 +60,7 @@ int lduMatrixSolutionCache::favourSpeed = 0;
 int lduMatrix::debug = 0;
 label UPstream::warnComm = -1;
 defineTypeNameAndDebug(GAMGSolver, 0); // GAMGSolver.C:35
+GAMGSolver::~GAMGSolver() { delete coarsestBufferPtr_; }
 const gpuField<scalar> &lduMatrixSolutionCache::first(label size) { return ScratchPool::get("first", size); }
 const gpuField<scalar> &lduMatrixSolutionCache::second(label size) { return ScratchPool::get("second", size); }
 
@@ -53,34 +84,6 @@ autoPtr<lduMatrix::smoother> lduMatrix::smoother::New(const word &fieldName, con
     return autoPtr<smoother>(new JacobiSmoother(fieldName, matrix, bou, intc, ifs, d)); // GaussSeidel == Jacobi here
 }
 
-// dense LU with partial pivoting (stands in for LUscalarMatrix / scalarMatrices.C LUDecompose)
-LUscalarMatrix::LUscalarMatrix(label n, const std::vector<scalar> &dense) : n_(n), lu_(dense), piv_((size_t)n)
-{
-    for (label k = 0; k < n; k++) {
-        label p = k;
-        for (label i = k + 1; i < n; i++)
-            if (std::fabs(lu_[(size_t)i * n + k]) > std::fabs(lu_[(size_t)p * n + k])) p = i;
-        piv_[(size_t)k] = p;
-        if (p != k)
-            for (label j = 0; j < n; j++) std::swap(lu_[(size_t)k * n + j], lu_[(size_t)p * n + j]);
-        for (label i = k + 1; i < n; i++) {
-            lu_[(size_t)i * n + k] /= lu_[(size_t)k * n + k];
-            for (label j = k + 1; j < n; j++) lu_[(size_t)i * n + j] -= lu_[(size_t)i * n + k] * lu_[(size_t)k * n + j];
-        }
-    }
-}
-void LUscalarMatrix::solve(scalarField &x) const
-{
-    scalar *b = x.data();
-    for (label k = 0; k < n_; k++) {
-        std::swap(b[k], b[piv_[(size_t)k]]);
-        for (label i = k + 1; i < n_; i++) b[i] -= lu_[(size_t)i * n_ + k] * b[k];
-    }
-    for (label i = n_ - 1; i >= 0; i--) {
-        for (label j = i + 1; j < n_; j++) b[i] -= lu_[(size_t)i * n_ + j] * b[j];
-        b[i] /= lu_[(size_t)i * n_ + i];
-    }
-}
 } // namespace Foam
 
 using namespace Foam;

@@ -171,40 +171,98 @@ def coarse_matrix(r, fr, flip, nCoarse, nCoarseFaces, diag, upper, lower):
     return Dc, Uc, Lc
 
 
-def gamg_solve(g, addr, diag, upper, lower, psi0, source, tolerance=1e-6, relTol=0.0, maxIter=1000, minIter=0,
-               nPreSweeps=0, preSweepsLevelMultiplier=1, maxPreSweeps=4, nPostSweeps=2, postSweepsLevelMultiplier=1,
-               maxPostSweeps=4, nFinestSweeps=2, interpolateCorrection=0, scaleCorrection=None,
-               directSolveCoarsest=1, omega=-1.0, favourSpeed=0):
-    """The reference's GAMGSolver::solve / Vcycle (GAMGSolverSolve.C) on the hierarchy of the oracle's Gamg
-    object `g` (maps + coarse addressing); coarse coefficients from coarse_matrix().  Defaults are
-    GAMGSolver.C:67-77's.  Returns (psi, dict) or raises NotImplementedError where the reference aborts."""
+def ldu_arrays(nCells, lower, upper):
+    """ownerStart, losortStart, losort of an LDU addressing (lduAddressing.C:169-344: faces are sorted by
+    owner already; losort = faces stably sorted by neighbour)."""
+    l, u = _i(lower), _i(upper)
+    ownerStart = np.zeros(int(nCells) + 1, np.int32)
+    np.add.at(ownerStart, l + 1, 1)
+    losortStart = np.zeros(int(nCells) + 1, np.int32)
+    np.add.at(losortStart, u + 1, 1)
+    return np.cumsum(ownerStart).astype(np.int32), np.cumsum(losortStart).astype(np.int32), \
+        np.argsort(u, kind="stable").astype(np.int32)
+
+
+def reference_hierarchy(nCells, lower, upper, faceWeights, nCellsInCoarsestLevel, diag, upperC, lowerC, forward=1,
+                        maxLevels=50):
+    """A GAMG hierarchy produced by REFERENCE CODE ONLY: pairGAMGAgglomeration::agglomerate for the maps,
+    GAMGAgglomeration::agglomerateLduAddressing for coarse addressing / face maps, the reference's functors
+    for the coarse coefficients; the level loop and the stop rule are pairGAMGAgglomerate.C:46-107 /
+    GAMGAgglomeration.C:72-84 (continue while nCoarseCells >= nCellsInCoarsestLevel), the face weights are
+    restricted by summation over the face map.  Returns a list of level dicts, finest first."""
+    levels = [dict(nCells=int(nCells), lower=_i(lower), upper=_i(upper), diag=_d(diag), upperC=_d(upperC),
+                   lowerC=_d(lowerC))]
+    w = _d(faceWeights)
+    fwd = forward
+    while len(levels) < maxLevels:
+        cur = levels[-1]
+        rmap, nC, fwd = pair_agglomerate(cur["nCells"], cur["lower"], cur["upper"], w, fwd)
+        if nC < nCellsInCoarsestLevel:
+            break
+        R = coarse_levels(cur["nCells"], cur["lower"], cur["upper"], rmap, nC, diag=cur["diag"], upperC=cur["upperC"],
+                          lowerC=cur["lowerC"])
+        cur["restrict"], cur["faceRestrict"], cur["flip"] = rmap, R["faceRestrict"], R["flip"]
+        cw = np.zeros(len(R["coarseOwner"]))
+        keep = R["faceRestrict"] >= 0
+        np.add.at(cw, R["faceRestrict"][keep], w[keep])
+        w = cw
+        levels.append(dict(nCells=nC, lower=R["coarseOwner"].copy(), upper=R["coarseNeighbour"].copy(),
+                           diag=R["coarseDiag"].copy(), upperC=R["coarseUpper"].copy(),
+                           lowerC=None if R["coarseLower"] is None else R["coarseLower"].copy()))
+    return levels, fwd
+
+
+def oracle_hierarchy(g, addr, diag, upperC, lowerC):
+    """The same level list built from the oracle's Gamg object `g` (maps + coarse addressing), coarse
+    coefficients from coarse_matrix()."""
+    levels = [dict(nCells=addr.nCells, lower=_i(addr.lower()), upper=_i(addr.upper()), diag=_d(diag), upperC=_d(upperC),
+                   lowerC=_d(lowerC))]
+    for k in range(g.nLevels):
+        cur = levels[-1]
+        r, fr, fl = g.restrict_addr(k), g.face_restrict_addr(k), g.face_flip(k)
+        cur["restrict"] = _i(r)
+        d, u, lo = coarse_matrix(r, fr, fl, g.ncells(k), g.nfaces(k), cur["diag"], cur["upperC"], cur["lowerC"])
+        la = g.level_addr(k)
+        levels.append(dict(nCells=g.ncells(k), lower=_i(la.lower()), upper=_i(la.upper()), diag=_d(d), upperC=_d(u),
+                           lowerC=_d(lo)))
+    return levels
+
+
+def gamg_solve(g, addr, diag, upper, lower, psi0, source, **kw):
+    """The reference's GAMGSolver::solve on the hierarchy of the oracle's Gamg object `g`."""
+    return gamg_solve_levels(oracle_hierarchy(g, addr, diag, upper, lower), psi0, source, **kw)
+
+
+def gamg_solve_levels(levels, psi0, source, tolerance=1e-6, relTol=0.0, maxIter=1000, minIter=0,
+                      nPreSweeps=0, preSweepsLevelMultiplier=1, maxPreSweeps=4, nPostSweeps=2,
+                      postSweepsLevelMultiplier=1, maxPostSweeps=4, nFinestSweeps=2, interpolateCorrection=0,
+                      scaleCorrection=None, directSolveCoarsest=1, omega=-1.0, favourSpeed=0):
+    """The reference's GAMGSolver::solve / Vcycle (GAMGSolverSolve.C) on a level list (finest first; every
+    level but the last carries `restrict`).  Defaults are GAMGSolver.C:67-77's.  Returns (psi, dict) or raises
+    NotImplementedError where the reference aborts."""
     global _libgs
     if _libgs is None:
         if not available() or not os.path.exists(_LIB_GAMGSOLVE):
             raise RuntimeError("oracle/_ref/libref_gamgsolve.so is not built (needs /root/reference)")
         _libgs = C.CDLL(_LIB_GAMGSOLVE)
-    nL = g.nLevels
-    addrs = [addr] + [g.level_addr(k) for k in range(nL)]
-    coeffs = [(_d(diag), _d(upper), _d(lower))]
-    maps = []
-    for k in range(nL):
-        r, fr, fl = g.restrict_addr(k), g.face_restrict_addr(k), g.face_flip(k)
-        maps.append(_i(r))
-        d, u, lo = coeffs[-1]
-        coeffs.append(tuple(_d(x) for x in coarse_matrix(r, fr, fl, g.ncells(k), g.nfaces(k), d, u, lo)))
+    nL = len(levels) - 1
+    lower = levels[0]["lowerC"]
+    maps = [_i(lv["restrict"]) for lv in levels[:-1]]
+    coeffs = [(lv["diag"], lv["upperC"], lv["lowerC"]) for lv in levels]
+    derived = [ldu_arrays(lv["nCells"], lv["lower"], lv["upper"]) for lv in levels]
     keep = []
 
     def ptrs(arrs, ct):
         arr = (C.c_void_p * len(arrs))(*[(a.ctypes.data if a is not None else None) for a in arrs])
         keep.append((arrs, arr))
         return arr
-    nC = _i([a.nCells for a in addrs])
-    nF = _i([len(a.lower()) for a in addrs])
-    L = [_i(a.lower()) for a in addrs]
-    U = [_i(a.upper()) for a in addrs]
-    OS = [_i(a.owner_start()) for a in addrs]
-    LS = [_i(a.losort_start()) for a in addrs]
-    LO = [_i(a.losort()) for a in addrs]
+    nC = _i([lv["nCells"] for lv in levels])
+    nF = _i([len(lv["lower"]) for lv in levels])
+    L = [lv["lower"] for lv in levels]
+    U = [lv["upper"] for lv in levels]
+    OS = [d[0] for d in derived]
+    LS = [d[1] for d in derived]
+    LO = [d[2] for d in derived]
     if scaleCorrection is None:
         scaleCorrection = 1 if lower is None else 0   # GAMGSolver.C:73: matrix.symmetric()
     ctl = _i([nPreSweeps, preSweepsLevelMultiplier, maxPreSweeps, nPostSweeps, postSweepsLevelMultiplier,
