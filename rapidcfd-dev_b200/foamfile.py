@@ -670,3 +670,77 @@ def from_hex_mesh(hm, rank=-1):
     offs = (4 * np.arange(len(allq) + 1)).astype(np.int32)
     return PolyMesh(np.concatenate(owner), hm.upper.astype(np.int32), patches, pts, offs,
                     allq.reshape(-1).astype(np.int32))
+
+
+# ---------------------------------------------------------------------------
+# decomposition (what decomposePar writes into processorN/constant/polyMesh)
+# ---------------------------------------------------------------------------
+def decompose_poly_mesh(pm, cellToProc):
+    """Split `pm` by the cell -> rank map, following domainDecomposition's ordering
+    (applications/utilities/parallelProcessing/decomposePar in OpenFOAM; not part of the reference
+    tree, its conventions are what processorLduInterface relies on):
+      * local cells and points keep their global relative order;
+      * internal faces = global internal faces with both cells on the rank, in global order (upper-
+        triangular order is preserved);
+      * then the physical patches in their order (faces in global order, empty patches kept);
+      * then one processor patch per neighbour rank in ascending rank order, its faces in global face
+        order on BOTH sides (so face i of procBoundaryAtoB is face i of procBoundaryBtoA); the face is
+        stored flipped where the local cell is the global neighbour.
+    A cyclic face stays in its cyclic patch on the rank that owns its cell; processorCyclic patches (a
+    cyclic pair split across ranks) are not produced -- keep both halves of a pair on one rank.
+    Returns a list of (PolyMesh, cellGlobal, faceGlobal) per rank; faceGlobal < 0 marks a flipped face
+    (-(f+1))."""
+    cellToProc = np.asarray(cellToProc, dtype=np.int64)
+    nP = int(cellToProc.max()) + 1 if len(cellToProc) else 1
+    nI = pm.nInternalFaces
+    own, nei = pm.owner.astype(np.int64), pm.neighbour.astype(np.int64)
+    po, pn = cellToProc[own[:nI]], cellToProc[nei]
+    out = []
+    for r in range(nP):
+        cells = np.nonzero(cellToProc == r)[0]
+        local = -np.ones(pm.nCells, dtype=np.int64)
+        local[cells] = np.arange(len(cells))
+        f_int = np.nonzero((po == r) & (pn == r))[0]
+        owner = [local[own[f_int]]]
+        neigh = local[nei[f_int]]
+        faceG = [f_int]
+        patches = []
+        start = len(f_int)
+        for p in pm.patches:                                   # physical (and cyclic) patches
+            if p.type in ("processor", "processorCyclic"):
+                continue
+            f = np.arange(p.startFace, p.startFace + p.nFaces)
+            f = f[cellToProc[own[f]] == r]
+            patches.append(PolyPatch(p.name, p.type, len(f), start, neighbourPatch=p.neighbourPatch))
+            owner.append(local[own[f]])
+            faceG.append(f)
+            start += len(f)
+        cut = np.nonzero(((po == r) | (pn == r)) & (po != pn))[0]   # internal faces cut by the decomposition
+        other = np.where(po[cut] == r, pn[cut], po[cut])
+        for nb in np.unique(other):
+            f = cut[other == nb]                                  # global face order
+            mine_is_owner = po[f] == r
+            owner.append(local[np.where(mine_is_owner, own[f], nei[f])])
+            faceG.append(np.where(mine_is_owner, f, -(f + 1)))
+            patches.append(PolyPatch(f"procBoundary{r}to{int(nb)}", "processor", len(f), start, r, int(nb)))
+            start += len(f)
+        faceG = np.concatenate(faceG)
+        sub = PolyMesh(np.concatenate(owner).astype(np.int32), neigh.astype(np.int32), patches)
+        if pm.points is not None:
+            gf = np.where(faceG >= 0, faceG, -faceG - 1)
+            sizes = (pm.faceOffsets[gf + 1] - pm.faceOffsets[gf]).astype(np.int64)
+            offs = np.zeros(len(gf) + 1, dtype=np.int64)
+            np.cumsum(sizes, out=offs[1:])
+            labels = np.empty(int(offs[-1]), dtype=np.int64)
+            for i, (g, fl) in enumerate(zip(gf, faceG < 0)):
+                pts = pm.faceLabels[pm.faceOffsets[g]:pm.faceOffsets[g + 1]]
+                # a flipped face keeps its first point and reverses the rest (face::reverseFace)
+                labels[offs[i]:offs[i + 1]] = pts if not fl else np.concatenate([pts[:1], pts[:0:-1]])
+            used = np.unique(labels)
+            pl = -np.ones(len(pm.points), dtype=np.int64)
+            pl[used] = np.arange(len(used))
+            sub.points = pm.points[used]
+            sub.faceOffsets = offs.astype(np.int32)
+            sub.faceLabels = pl[labels].astype(np.int32)
+        out.append((sub, cells, faceG))
+    return out

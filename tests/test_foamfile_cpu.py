@@ -310,3 +310,75 @@ def test_unstructured_case_from_disk_drives_oracle_and_layout(ff, meshmod, orc, 
     _check_layout(mesh, lay)
     nPad, nBands, bandRows, nRecv, maxHalo = [int(x) for x in lay["dims"]]
     assert nBands >= 3 and maxHalo < 4 * bandRows      # the renumbering keeps the bands compact
+
+
+def test_decompose_poly_mesh_matches_brick_decomposition(ff, meshmod, orc, tmp_path):
+    """decomposePar-style splitting of a polyMesh by a cell -> rank map: for the 2x2x1 brick map it gives
+    the in-memory decomposition of mesh.decompose (same local addressing, processor patches in the same
+    order with the same face order on both sides); geometry of the pieces is consistent (flipped faces
+    point out of their new owner); a decomposed PCG solve through files equals the single-domain one."""
+    import dist_helpers as dh
+    n, nR = 8, 4
+    g = meshmod.hex_mesh(n)
+    pm = ff.from_hex_mesh(g)
+    px, py, pz = meshmod.brick_split(nR)
+    c = np.arange(g.nCells)
+    i, j, k = c % n, (c // n) % n, c // (n * n)
+    proc = (i // (n // px)) + px * (j // (n // py)) + px * py * (k // (n // pz))
+    parts = ff.decompose_poly_mesh(pm, proc)
+    assert len(parts) == nR
+    for r, (sub, cells, faceG) in enumerate(parts):
+        hm = meshmod.decompose(n, nR, r)
+        assert np.array_equal(cells, hm.cellGlobal)
+        lo, up = sub.ldu()
+        assert np.array_equal(lo, hm.lower) and np.array_equal(up, hm.upper)
+        ps, fc, nr = sub.coupled_interface_arrays()
+        eps, efc = hm.patch_start_facecells()
+        assert np.array_equal(ps, eps) and np.array_equal(fc, efc)
+        assert nr.tolist() == [p.neighbRank for p in hm.coupled_patches()]
+        d = str(tmp_path / f"processor{r}" / "constant" / "polyMesh")
+        ff.write_poly_mesh(d, sub, binary=(r % 2 == 0))
+        back = ff.read_poly_mesh(d)
+        geo = back.fv_geometry()
+        np.testing.assert_allclose(geo["C"], hm.cell_centres(), atol=1e-14)
+        np.testing.assert_allclose(geo["V"], hm.volumes(), rtol=1e-13)
+        for p in back.patches:                     # every boundary face points out of its (new) owner
+            f = np.arange(p.startFace, p.startFace + p.nFaces)
+            out = geo["Cf"][f] - geo["C"][back.owner[f]]
+            assert np.all(np.einsum("ij,ij->i", out, geo["Sf"][f]) > 0)
+    # the two sides of every processor patch list the same global faces in the same order
+    for r, (sub, cells, faceG) in enumerate(parts):
+        for p in sub.patches:
+            if p.type != "processor":
+                continue
+            mine = faceG[p.startFace:p.startFace + p.nFaces]
+            osub, _, oG = parts[p.neighbProcNo]
+            q = [x for x in osub.patches if x.type == "processor" and x.neighbProcNo == r][0]
+            theirs = oG[q.startFace:q.startFace + q.nFaces]
+            gm = np.where(mine >= 0, mine, -mine - 1)
+            gt = np.where(theirs >= 0, theirs, -theirs - 1)
+            assert np.array_equal(gm, gt) and np.all((mine >= 0) != (theirs >= 0))
+    # solve through the decomposed files (threads as ranks) == single domain, with the diagonal preconditioner
+    gm_, gc_ = dh.global_case(meshmod, n, "P")
+    ga, gM = dh.oracle_matrix(orc, gm_, gc_)
+    xs = meshmod.cell_field_global(gm_, 42)
+    b = gM.amul(xs)
+    psi_ref, pref, href = gM.solve("PCG", "diagonal", np.zeros(g.nCells), b, tolerance=1e-9, maxIter=500)
+    ex = dh.ThreadExchange(nR)
+
+    def rank_fn(r):
+        hm, coef = dh.local_case(meshmod, n, nR, r, "P")           # coefficients of the local piece
+        sub = ff.read_poly_mesh(str(tmp_path / f"processor{r}" / "constant" / "polyMesh"), geometry=False)
+        lo, up = sub.ldu()
+        ps, fc, nr = sub.coupled_interface_arrays()
+        a = orc.Addr(sub.nCells, lo, up, ps, fc, neighbRank=nr)    # addressing straight from the files
+        M = orc.Matrix(a, coef["diag"], coef["upper"], coef["lower"], coef["bou"], coef["int"])
+        comm = ex.comm(orc, r, hm, n ** 3)
+        psi, perf, hist = M.solve("PCG", "diagonal", np.zeros(sub.nCells), b[hm.cellGlobal], comm=comm,
+                                  tolerance=1e-9, maxIter=500)
+        return hm.cellGlobal, psi, perf.nIterations, hist
+    res = dh.run_threads(nR, rank_fn)
+    for cg, psi, nit, hist in res:
+        assert abs(nit - pref.nIterations) <= 1
+        np.testing.assert_allclose(psi, psi_ref[cg], atol=1e-7)
+        np.testing.assert_allclose(hist[:25], href[:25], rtol=1e-9)
