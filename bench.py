@@ -136,26 +136,68 @@ def host_threads(orc):
     return max(1, n)
 
 
+def set_omp_threads(n):
+    """libgomp is shared by the oracle port and the OpenMP build of the reference code: set its team size."""
+    import ctypes
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass
+
+
+def cpu_pcg(meshmod, orc, mesh, coef, nT):
+    """The CPU PCG used by the reference arm and the cpu_baseline leg.  Where the reference's own solver
+    sources were compiled here (oracle/_ref/libref_solvers_omp.so: PCG.C, AINVPreconditioner.C,
+    lduMatrixATmul.C ... on thrust's OpenMP host back end, oracle/ref_harness/) that code runs, with the
+    reference's default favourSpeedOverMemory 2 (etc/controlDict:66) -- kind "reference"; otherwise the
+    oracle's OpenMP port -- kind "port".  Returns (run(iters, b) -> nIterations, kind, description)."""
+    try:
+        from oracle import ref_ldu
+        if ref_ldu.omp_available():
+            os_, ls, lo = ref_ldu.ldu_arrays(mesh.nCells, mesh.lower, mesh.upper)
+            fixed = (mesh.nCells, np.ascontiguousarray(mesh.lower, np.int32), np.ascontiguousarray(mesh.upper, np.int32),
+                     os_, ls, lo, np.ascontiguousarray(coef["diag"]), np.ascontiguousarray(coef["upper"]), None)
+            set_omp_threads(nT)
+            z = np.zeros(mesh.nCells)
+
+            def run_ref(iters, b):
+                _, p = ref_ldu.solve("PCG", "DIC", *fixed, z, b, tolerance=0.0, maxIter=iters - 1, favourSpeed=2,
+                                     omp=True)
+                return p["nIterations"]
+            run_ref(1, np.ones(mesh.nCells))   # loads the library, starts the OpenMP team
+            return run_ref, "reference", ("reference PCG.C + AINVPreconditioner.C + lduMatrixATmul.C compiled for the "
+                                           "host, thrust OpenMP back end")
+    except Exception as e:  # noqa: BLE001 -- any problem with the optional library: use the port
+        sys.stderr.write(f"reference-code CPU arm unavailable ({e}); using the oracle port\n")
+    oa = orc.Addr(mesh.nCells, mesh.lower, mesh.upper)
+    om = orc.Matrix(oa, coef["diag"], coef["upper"], None)
+
+    def run_port(iters, b):
+        _, perf = om.pcg_omp("DIC", np.zeros(mesh.nCells), b, nThreads=nT, tolerance=0.0, maxIter=iters - 1)
+        return perf.nIterations
+    run_port._keep = (oa, om)
+    return run_port, "port", "oracle OpenMP rows (oracle/ldu_oracle_omp.c)"
+
+
 def run_reference(args, rank, world):
-    """CPU arm: the oracle's OpenMP PCG (RapidCFD numerics: AINV for DIC) on all host threads."""
+    """CPU arm on all physical host cores: the reference's own PCG loop where it compiled (oracle/_ref), else
+    the oracle's OpenMP port -- RapidCFD numerics either way (AINV for DIC)."""
     if rank != 0:
         return
     meshmod = importlib.import_module("rapidcfd-dev_b200.mesh")
     from oracle import ldu_oracle as orc
     n = args.n
     mesh, coef, b = build_case(meshmod, n, 1, 0)
-    oa = orc.Addr(mesh.nCells, mesh.lower, mesh.upper)
-    om = orc.Matrix(oa, coef["diag"], coef["upper"], None)
     nT = host_threads(orc)
+    run, kind, what = cpu_pcg(meshmod, orc, mesh, coef, nT)
     iters = args.ref_iters
-    kw = dict(tolerance=0.0, maxIter=iters - 1)
     for _ in range(args.warmup):
-        om.pcg_omp("DIC", np.zeros(mesh.nCells), b, nThreads=nT, **kw)
+        run(iters, b)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, perf = om.pcg_omp("DIC", np.zeros(mesh.nCells), b, nThreads=nT, **kw)
+        nit = run(iters, b)
     dt = time.perf_counter() - t0
-    assert perf.nIterations == iters
+    assert nit == iters
     val = mesh.nCells * iters * args.steps / dt / 1e6
     line = {"impl": "reference", "metric": "Mcell-iters/sec (PCG pressure solve, 256^3 hex cavity)",
             "value": val, "unit": "Mcell-iters/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -163,8 +205,8 @@ def run_reference(args, rank, world):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"icoFoam cavity {n}^3 hex, PCG+DIC(AINV) pressure solve", "n": n,
                        "iterations_per_step": iters, "preconditioner": "DIC->AINV"},
-            "cpu_baseline": {"value": val, "unit": "Mcell-iters/s", "cores": nT, "kind": "port",
-                             "sample": f"{n}^3 cells x {iters} PCG iterations per step, OpenMP rows"},
+            "cpu_baseline": {"value": val, "unit": "Mcell-iters/s", "cores": nT, "kind": kind,
+                             "sample": f"{n}^3 cells x {iters} PCG iterations per step; {what}"},
             "e2e": {"value": val, "unit": "Mcell-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -304,15 +346,26 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import ldu_oracle as orc
-        oa = orc.Addr(mesh.nCells, mesh.lower, mesh.upper)
-        om = orc.Matrix(oa, coef["diag"], coef["upper"], None)
         nT = host_threads(orc)
         ci = args.cpu_baseline_iters
+        run, kind, what = cpu_pcg(meshmod, orc, mesh, coef, nT)
         t0 = time.perf_counter()
-        _, cperf = om.pcg_omp("DIC", np.zeros(mesh.nCells), b, nThreads=nT, tolerance=0.0, maxIter=ci - 1)
+        nit = run(ci, b)
         cdt = time.perf_counter() - t0
-        cpu = {"value": mesh.nCells * ci / cdt / 1e6, "unit": "Mcell-iters/s", "cores": nT, "kind": "port",
-               "sample": f"{n}^3 cells x {ci} PCG(AINV) iterations, oracle OpenMP rows, {cdt:.1f} s"}
+        assert nit == ci
+        cpu = {"value": mesh.nCells * ci / cdt / 1e6, "unit": "Mcell-iters/s", "cores": nT, "kind": kind,
+               "sample": f"{n}^3 cells x {ci} PCG(AINV) iterations, {what}, {cdt:.1f} s"}
+        if kind == "reference":   # the oracle's own OpenMP port beside it
+            oa = orc.Addr(mesh.nCells, mesh.lower, mesh.upper)
+            om = orc.Matrix(oa, coef["diag"], coef["upper"], None)
+            t0 = time.perf_counter()
+            om.pcg_omp("DIC", np.zeros(mesh.nCells), b, nThreads=nT, tolerance=0.0, maxIter=ci - 1)
+            pdt = time.perf_counter() - t0
+            cpu["port"] = {"value": mesh.nCells * ci / pdt / 1e6, "unit": "Mcell-iters/s", "cores": nT,
+                           "sample": f"oracle OpenMP rows, {pdt:.1f} s"}
+        else:
+            oa = orc.Addr(mesh.nCells, mesh.lower, mesh.upper)
+            om = orc.Matrix(oa, coef["diag"], coef["upper"], None)
         # stock CPU OpenFOAM numerics for context (true DIC + face-loop Amul, one core = one rank)
         si = max(2, min(8, ci // 2))
         t0 = time.perf_counter()

@@ -104,23 +104,37 @@ public:
 };
 
 // global sums on one rank, in index order (the oracle's order; the reference's thrust::reduce order is
-// unspecified)
+// unspecified).  REF_OMP (the all-core timing build, oracle/Makefile `ref`): OpenMP reductions instead.
+#ifdef REF_OMP
+#define REF_REDUCE(var) _Pragma("omp parallel for schedule(static) reduction(+ : s)")
+#else
+#define REF_REDUCE(var)
+#endif
 inline scalar gSumMag(const scalargpuField &f, int)
 {
     scalar s = 0;
-    for (label i = 0; i < f.size(); i++) s += std::fabs(f.data()[i]);
+    const scalar *p = f.data();
+    const label n = f.size();
+    REF_REDUCE(s)
+    for (label i = 0; i < n; i++) s += std::fabs(p[i]);
     return s;
 }
 inline scalar gSumProd(const scalargpuField &a, const scalargpuField &b, int)
 {
     scalar s = 0;
-    for (label i = 0; i < a.size(); i++) s += a.data()[i] * b.data()[i];
+    const scalar *p = a.data(), *q = b.data();
+    const label n = a.size();
+    REF_REDUCE(s)
+    for (label i = 0; i < n; i++) s += p[i] * q[i];
     return s;
 }
 inline scalar gAverage(const scalargpuField &f, int)
 {
     scalar s = 0;
-    for (label i = 0; i < f.size(); i++) s += f.data()[i];
+    const scalar *p = f.data();
+    const label n = f.size();
+    REF_REDUCE(s)
+    for (label i = 0; i < n; i++) s += p[i];
     return s / f.size();
 }
 
@@ -201,12 +215,15 @@ public:
     {
         matrix_.sumA(tmpField, interfaceBouCoeffs_, interfaces_);
         const scalar average = gAverage(psi, 0);
-        scalar factor = 0;
-        for (label i = 0; i < psi.size(); i++) {
-            const scalar tmpVal = average * tmpField.data()[i];
-            factor += mag(Apsi.data()[i] - tmpVal) + mag(source.data()[i] - tmpVal);
+        scalar s = 0;
+        const scalar *t = tmpField.data(), *ap = Apsi.data(), *sr = source.data();
+        const label n = psi.size();
+        REF_REDUCE(s)
+        for (label i = 0; i < n; i++) {
+            const scalar tmpVal = average * t[i];
+            s += std::fabs(ap[i] - tmpVal) + std::fabs(sr[i] - tmpVal);
         }
-        return factor + solverPerformance::small_;
+        return s + solverPerformance::small_;
     }
 };
 

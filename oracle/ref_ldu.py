@@ -116,27 +116,42 @@ _LIB_SOLVERS = os.path.join(_HERE, "_ref", "libref_solvers.so")
 _libs = None
 
 
+_LIB_SOLVERS_OMP = os.path.join(_HERE, "_ref", "libref_solvers_omp.so")
+_libs_omp = None
+
+
+def omp_available():
+    """True when the all-core build of the reference solver loops exists (thrust host algorithms on OpenMP)."""
+    return available() and os.path.exists(_LIB_SOLVERS_OMP)
+
+
 def solve(solver, precond, nCells, lower, upper, ownerStart, losortStart, losort, diag, upperC, lowerC, psi0, source,
-          tolerance=1e-6, relTol=0.0, maxIter=1000, minIter=0, favourSpeed=0, nSweeps=1, omega=-1.0):
+          tolerance=1e-6, relTol=0.0, maxIter=1000, minIter=0, favourSpeed=0, nSweeps=1, omega=-1.0, omp=False):
     """The reference's PCG::solve / PBiCG::solve / PBiCGStab::solve (PCG.C:69-208, PBiCG.C:68-246,
     PBiCGStab.C:66-300) with its own preconditioner classes, or smoothSolver::solve (smoothSolver.C:77-193,
     `precond` = smoother word, nSweeps, omega < 0 = not in the dictionary) with its JacobiSmoother.  Returns (psi, dict(initialResidual,
     finalResidual, nIterations, converged, singular, solverName))."""
-    global _libs
-    if _libs is None:
-        if not available() or not os.path.exists(_LIB_SOLVERS):
-            raise RuntimeError("oracle/_ref/libref_solvers.so is not built (needs /root/reference)")
-        _libs = C.CDLL(_LIB_SOLVERS)
-        _libs.ref_solve.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8 + \
+    global _libs, _libs_omp
+    if (_libs_omp if omp else _libs) is None:
+        path = _LIB_SOLVERS_OMP if omp else _LIB_SOLVERS
+        if not available() or not os.path.exists(path):
+            raise RuntimeError(f"{path} is not built (needs /root/reference)")
+        L = C.CDLL(path)
+        L.ref_solve.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8 + \
             [C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int,
              C.c_int, C.c_double]
+        if omp:
+            _libs_omp = L
+        else:
+            _libs = L
+    _L = _libs_omp if omp else _libs
     l, u, os_, ls, lo = _i(lower), _i(upper), _i(ownerStart), _i(losortStart), _i(losort)
     dg, up, low = _d(diag), _d(upperC), _d(lowerC)
     psi = _d(psi0).copy()
     src = _d(source)
     perf = np.zeros(5)
     name = C.create_string_buffer(64)
-    rc = _libs.ref_solve(solver.encode(), precond.encode(), int(favourSpeed), int(nCells), len(l), _p(l), _p(u), _p(os_),
+    rc = _L.ref_solve(solver.encode(), precond.encode(), int(favourSpeed), int(nCells), len(l), _p(l), _p(u), _p(os_),
                          _p(ls), _p(lo), _p(dg), _p(up), _p(low), float(tolerance), float(relTol), int(maxIter),
                          int(minIter), _p(psi), _p(src), _p(perf), name, 64, int(nSweeps), float(omega))
     if rc != 0:
