@@ -190,12 +190,10 @@ def ldu_arrays(nCells, lower, upper):
     """ownerStart, losortStart, losort of an LDU addressing (lduAddressing.C:169-344: faces are sorted by
     owner already; losort = faces stably sorted by neighbour)."""
     l, u = _i(lower), _i(upper)
-    ownerStart = np.zeros(int(nCells) + 1, np.int32)
-    np.add.at(ownerStart, l + 1, 1)
-    losortStart = np.zeros(int(nCells) + 1, np.int32)
-    np.add.at(losortStart, u + 1, 1)
-    return np.cumsum(ownerStart).astype(np.int32), np.cumsum(losortStart).astype(np.int32), \
-        np.argsort(u, kind="stable").astype(np.int32)
+    n = int(nCells)
+    ownerStart = np.concatenate([[0], np.cumsum(np.bincount(l, minlength=n))]).astype(np.int32)
+    losortStart = np.concatenate([[0], np.cumsum(np.bincount(u, minlength=n))]).astype(np.int32)
+    return ownerStart, losortStart, np.argsort(u, kind="stable").astype(np.int32)
 
 
 def reference_hierarchy(nCells, lower, upper, faceWeights, nCellsInCoarsestLevel, diag, upperC, lowerC, forward=1,
