@@ -179,6 +179,36 @@ def cpu_pcg(meshmod, orc, mesh, coef, nT):
     return run_port, "port", "oracle OpenMP rows (oracle/ldu_oracle_omp.c)"
 
 
+def cpu_baseline_leg(meshmod, mesh, coef, b, n, ci):
+    """cpu_baseline object of the JSON line: `ci` PCG iterations of the CPU arm (cpu_pcg), the oracle port
+    beside it when the reference code ran, and stock OpenFOAM's serial DIC-PCG for context."""
+    from oracle import ldu_oracle as orc
+    nT = host_threads(orc)
+    run, kind, what = cpu_pcg(meshmod, orc, mesh, coef, nT)
+    t0 = time.perf_counter()
+    nit = run(ci, b)
+    cdt = time.perf_counter() - t0
+    assert nit == ci
+    cpu = {"value": mesh.nCells * ci / cdt / 1e6, "unit": "Mcell-iters/s", "cores": nT, "kind": kind,
+           "sample": f"{n}^3 cells x {ci} PCG(AINV) iterations, {what}, {cdt:.1f} s"}
+    oa = orc.Addr(mesh.nCells, mesh.lower, mesh.upper)
+    om = orc.Matrix(oa, coef["diag"], coef["upper"], None)
+    if kind == "reference":   # the oracle's own OpenMP port beside it
+        t0 = time.perf_counter()
+        om.pcg_omp("DIC", np.zeros(mesh.nCells), b, nThreads=nT, tolerance=0.0, maxIter=ci - 1)
+        pdt = time.perf_counter() - t0
+        cpu["port"] = {"value": mesh.nCells * ci / pdt / 1e6, "unit": "Mcell-iters/s", "cores": nT,
+                       "sample": f"oracle OpenMP rows, {pdt:.1f} s"}
+    # stock CPU OpenFOAM numerics for context (true DIC + face-loop Amul, one core = one rank)
+    si = max(2, min(8, ci // 2))
+    t0 = time.perf_counter()
+    om.pcg_stock_dic(np.zeros(mesh.nCells), b, tolerance=0.0, maxIter=si - 1)
+    sdt = time.perf_counter() - t0
+    cpu["stock_dic_serial"] = {"value": mesh.nCells * si / sdt / 1e6, "unit": "Mcell-iters/s", "cores": 1,
+                               "sample": f"{n}^3 cells x {si} PCG(true DIC) iterations, serial, {sdt:.1f} s"}
+    return cpu
+
+
 def run_reference(args, rank, world):
     """CPU arm on all physical host cores: the reference's own PCG loop where it compiled (oracle/_ref), else
     the oracle's OpenMP port -- RapidCFD numerics either way (AINV for DIC)."""
@@ -345,34 +375,7 @@ def main():
     # ---------------- CPU baseline (rank 0, N=1 only, bounded sample) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import ldu_oracle as orc
-        nT = host_threads(orc)
-        ci = args.cpu_baseline_iters
-        run, kind, what = cpu_pcg(meshmod, orc, mesh, coef, nT)
-        t0 = time.perf_counter()
-        nit = run(ci, b)
-        cdt = time.perf_counter() - t0
-        assert nit == ci
-        cpu = {"value": mesh.nCells * ci / cdt / 1e6, "unit": "Mcell-iters/s", "cores": nT, "kind": kind,
-               "sample": f"{n}^3 cells x {ci} PCG(AINV) iterations, {what}, {cdt:.1f} s"}
-        if kind == "reference":   # the oracle's own OpenMP port beside it
-            oa = orc.Addr(mesh.nCells, mesh.lower, mesh.upper)
-            om = orc.Matrix(oa, coef["diag"], coef["upper"], None)
-            t0 = time.perf_counter()
-            om.pcg_omp("DIC", np.zeros(mesh.nCells), b, nThreads=nT, tolerance=0.0, maxIter=ci - 1)
-            pdt = time.perf_counter() - t0
-            cpu["port"] = {"value": mesh.nCells * ci / pdt / 1e6, "unit": "Mcell-iters/s", "cores": nT,
-                           "sample": f"oracle OpenMP rows, {pdt:.1f} s"}
-        else:
-            oa = orc.Addr(mesh.nCells, mesh.lower, mesh.upper)
-            om = orc.Matrix(oa, coef["diag"], coef["upper"], None)
-        # stock CPU OpenFOAM numerics for context (true DIC + face-loop Amul, one core = one rank)
-        si = max(2, min(8, ci // 2))
-        t0 = time.perf_counter()
-        _, sperf = om.pcg_stock_dic(np.zeros(mesh.nCells), b, tolerance=0.0, maxIter=si - 1)
-        sdt = time.perf_counter() - t0
-        cpu["stock_dic_serial"] = {"value": mesh.nCells * si / sdt / 1e6, "unit": "Mcell-iters/s", "cores": 1,
-                                   "sample": f"{n}^3 cells x {si} PCG(true DIC) iterations, serial, {sdt:.1f} s"}
+        cpu = cpu_baseline_leg(meshmod, mesh, coef, b, n, args.cpu_baseline_iters)
 
     if rank == 0:
         pcg_bytes = (160 * N + 32 * F)  # per iteration and rank, reference op list with AINV
