@@ -1,0 +1,18 @@
+# First GPU call of the next round (1 GPU, ~6 min of box time): everything written after the round-1 GPU
+# budget ran out gets its first run on a B200, and the kernels that only have CUDA-event numbers get ncu captures.
+#   gpurun --timeout 900 -- 'bash tools/gpu_next_round.sh'
+set -x
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q 2>&1 | tail -15 > gpurun_out/r02a_tests.log
+python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE-OK')" > gpurun_out/r02a_smoke.log 2>&1
+python bench.py --impl reference > gpurun_out/r02a_bench_ref.json 2> gpurun_out/r02a_bench_ref.err
+python bench.py > gpurun_out/r02a_bench_n1.json 2> gpurun_out/r02a_bench_n1.err
+# engine variants (Jacobi, residual, AINV, asymmetric Amul/Tmul), face sums, GAMG transfer kernels
+ncu --set full --clock-control none --import-source on \
+    -k regex:"JacobiOp|ResidualOp|AinvOp|OffDiagOp|surface_integrate|gauss_grad|interpolate_linear|laplacian_fill|convection_fill|grad_linear|flux_linear|faceH_kernel" \
+    -c 24 -f -o gpurun_out/r02a_kernels python bench_kernels.py --n 128 --reps 1 > gpurun_out/r02a_ncu_kernels.log 2>&1
+ncu --set full --clock-control none --import-source on \
+    -k regex:"restrict_kernel|prolong_kernel|agg_diag_kernel|agg_faces_kernel|dense_apply" \
+    -c 16 -f -o gpurun_out/r02a_gamg python bench_kernels.py --n 64 --reps 1 > gpurun_out/r02a_ncu_gamg.log 2>&1
+cat gpurun_out/r02a_tests.log gpurun_out/r02a_smoke.log | tail -20
+cut -c1-300 gpurun_out/r02a_bench_ref.json gpurun_out/r02a_bench_n1.json
