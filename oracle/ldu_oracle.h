@@ -10,7 +10,8 @@
  * (wmake + flex + MPI + all of libOpenFOAM).  Its hot-path SOURCE FILES, however, compile for the
  * host against small type shims (oracle/ref_harness/, `make -C oracle ref` -> oracle/_ref/), and
  * tests/test_reference_functors.py runs them beside this restatement:
- *   PINNED to reference code, bit for bit on hex meshes: Amul, Tmul, sumA, residual, H1
+ *   PINNED to reference code, bit for bit on hex meshes: the derived addressing arrays
+ *     (lduAddressing.C), Amul, Tmul, sumA, residual, H1
  *     (lduMatrixATmul.C), H, faceH (lduMatrixTemplates.C), sumDiag / negSumDiag / sumMagOffDiag, the
  *     coupled-interface update arithmetic (matrixPatchOperation + matrixInterfaceFunctor), AINV
  *     precondition / preconditionT, the Jacobi sweep, smoothSolver, the GAMG V-cycle with scaling and

@@ -337,3 +337,40 @@ def coarse_levels(nCells, lower, upper, map0, nCoarse0, map1=None, nCoarse1=0, d
     if diag is not None:   # coarse coefficients assembled by the reference's functors (single step)
         out.update(coarseDiag=cD[:nc], coarseUpper=cU[:k], coarseLower=None if lowerC is None else cL[:k])
     return out
+
+
+_LIB_LDUADDR = os.path.join(_HERE, "_ref", "libref_lduaddr.so")
+_libla = None
+
+
+def ldu_addressing(nCells, lower, upper, patchStart=None, faceCells=None):
+    """The reference's lduAddressing.C: ownerStart, losortStart, losort, ownerSort (thrust sorts / scans,
+    :169-400), the per-patch sort addressing (:38-167) and band() (:453-498).  Returns a dict; the patch
+    entries are lists (one array per patch)."""
+    global _libla
+    if _libla is None:
+        if not available() or not os.path.exists(_LIB_LDUADDR):
+            raise RuntimeError("oracle/_ref/libref_lduaddr.so is not built (needs /root/reference)")
+        _libla = C.CDLL(_LIB_LDUADDR)
+    l, u = _i(lower), _i(upper)
+    n, nF = int(nCells), len(l)
+    ps = _i(patchStart if patchStart is not None else [0])
+    fc = _i(faceCells if faceCells is not None else [])
+    nP, tot = len(ps) - 1, int(ps[-1])
+    os_, ls = np.zeros(n + 1, np.int32), np.zeros(n + 1, np.int32)
+    lo, osrt = np.zeros(max(nF, 1), np.int32), np.zeros(max(nF, 1), np.int32)
+    psa, psc, pss = (np.zeros(max(tot, 1), np.int32) for _ in range(3))
+    nu = np.zeros(max(nP, 1), np.int32)
+    band = np.zeros(2)
+    rc = _libla.ref_ldu_addressing(n, nF, _p(l), _p(u), nP, _p(ps), _p(fc), _p(os_), _p(ls), _p(lo), _p(osrt), _p(psa),
+                                   _p(psc), _p(pss), _p(nu), _p(band))
+    if rc != 0:
+        raise RuntimeError("the reference code raised a FatalError")
+    out = dict(ownerStart=os_, losortStart=ls, losort=lo[:nF], ownerSort=osrt[:nF], bandwidth=int(band[0]),
+               profile=band[1], patchSortAddr=[], patchSortCells=[], patchSortStart=[])
+    for p in range(nP):
+        s, e, k = int(ps[p]), int(ps[p + 1]), int(nu[p])
+        out["patchSortAddr"].append(psa[s:e].copy())
+        out["patchSortCells"].append(psc[s:s + k].copy())
+        out["patchSortStart"].append(np.append(pss[s:s + k], e - s))
+    return out

@@ -335,3 +335,40 @@ def test_interface_update_matches_reference_functor(meshmod, orc):
             t = co[i] * v[i]
             exp[fcs[i]] = exp[fcs[i]] + (t if negate else -t)
         assert np.array_equal(ref_ldu.interface_update(5, fcs, co, v, r0, negate), exp)
+
+
+def test_derived_addressing_matches_reference_code(meshmod, orc):
+    """lduAddressing.C (the reference's own thrust sorts and scans): ownerStart, losortStart, losort,
+    ownerSort equal the oracle's arrays (row a1 of SURVEY section 8) on a hex mesh, on a randomly
+    renumbered one and on a decomposed piece; the per-patch sort addressing groups the patch faces by
+    cell in ascending patch-face order, which is the order the oracle applies interface terms in."""
+    from test_foamfile_cpu import _scrambled
+    ff = importlib.import_module("rapidcfd-dev_b200.foamfile")
+    cases = [meshmod.hex_mesh(7, 5, 4), meshmod.decompose(8, 4, 1)]
+    pm, _ = _scrambled(ff, meshmod, (6, 5, 4), 5)
+    lo_s, up_s = pm.ldu()
+    for m in cases + [None]:
+        if m is None:
+            n, lo, up, ps, fc = pm.nCells, lo_s, up_s, None, None
+        else:
+            n, lo, up = m.nCells, m.lower, m.upper
+            ps, fc = m.patch_start_facecells()
+            if len(ps) == 1:
+                ps = fc = None
+        a = orc.Addr(n, lo, up) if ps is None else orc.Addr(n, lo, up, ps, fc)
+        R = ref_ldu.ldu_addressing(n, lo, up, ps, fc)
+        assert np.array_equal(R["ownerStart"], a.owner_start())
+        assert np.array_equal(R["losortStart"], a.losort_start())
+        assert np.array_equal(R["losort"], a.losort())
+        assert np.array_equal(R["ownerSort"], np.asarray(lo)[a.losort()])
+        os2, ls2, lo2 = ref_ldu.ldu_arrays(n, lo, up)           # the numpy helper used by the harness drivers
+        assert np.array_equal(os2, R["ownerStart"]) and np.array_equal(ls2, R["losortStart"]) and np.array_equal(lo2, R["losort"])
+        assert R["bandwidth"] == int((np.asarray(up) - np.asarray(lo)).max())
+        if ps is not None:
+            for p in range(len(ps) - 1):
+                cells = np.asarray(fc[ps[p]:ps[p + 1]])
+                order = R["patchSortAddr"][p]
+                assert np.array_equal(order, np.argsort(cells, kind="stable"))      # by cell, then ascending patch face
+                assert np.array_equal(R["patchSortCells"][p], np.unique(cells))
+                st = R["patchSortStart"][p]
+                assert st[0] == 0 and st[-1] == len(cells) and np.all(np.diff(st) > 0)
