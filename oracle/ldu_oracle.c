@@ -777,6 +777,7 @@ int orc_solve(const orc_matrix *m, const char *solver, const char *pre, const or
             if (m->symmetric) return -3; /* asymMatrix table only PBiCG.C:36-37 */
             return orc_pbicg(m, pk, c, psi, source, comm, perf, hist, histCap);
         }
+        if (m->symmetric) return -3; /* asymMatrix table only: PBiCGStab.C:34-37 */
         return orc_pbicgstab(m, pk, c, psi, source, comm, perf, hist, histCap);
     }
     if (!strcmp(solver, "smoothSolver")) {

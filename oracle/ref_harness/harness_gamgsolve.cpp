@@ -42,6 +42,8 @@ public:
 } // namespace Foam
 
 #include "lduMatrixATmul.C"
+#include "lduMatrixSolver.C" /* solver base: constructor, readControls, normFactor, New */
+#include "diagonalSolver.C"
 #include "AINVPreconditioner.C"
 #include "diagonalPreconditioner.C"
 #include "noPreconditioner.C"

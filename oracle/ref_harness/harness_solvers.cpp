@@ -9,6 +9,8 @@
  *   LDU/preconditioners/AINVPreconditioner/AINVPreconditioner.C, AINVPreconditionerF.H
  *   LDU/preconditioners/diagonalPreconditioner/diagonalPreconditioner.C
  *   LDU/preconditioners/noPreconditioner/noPreconditioner.C
+ *   LDU/lduMatrix/lduMatrixSolver.C:43-236       lduMatrix::solver::New, readControls, normFactor
+ *   LDU/solvers/diagonalSolver/diagonalSolver.C
  *   LDU/lduMatrix/lduMatrixATmul.C, lduMatrixFunctors.H, lduMatrixSolverFunctors.H,
  *   LDU/lduAddressing/lduAddressingFunctors.H
  * against oracle/ref_harness/shim_solvers/ (+ shim/).  What the shims restate instead of including is
@@ -17,6 +19,8 @@
 #include "lduMatrix.H" /* shim_solvers */
 
 #include "lduMatrixATmul.C"
+#include "lduMatrixSolver.C" /* solver::New (run-time selection), readControls, normFactor */
+#include "diagonalSolver.C"
 #include "AINVPreconditioner.C"
 #include "diagonalPreconditioner.C"
 #include "noPreconditioner.C"
@@ -121,17 +125,13 @@ int ref_solve(const char *solverName, const char *precond, int favourSpeed, int 
                    : !(p == "DIC" || p == "DILU" || p == "AINV" || p == "diagonal" || p == "none"))
             return -2;
     }
-    std::unique_ptr<lduMatrix::solver> s;
-    if (!strcmp(solverName, "PCG"))
-        s.reset(new PCG("psi", m, noCoeffs, noCoeffs, noInterfaces, d));
-    else if (!strcmp(solverName, "PBiCG"))
-        s.reset(new PBiCG("psi", m, noCoeffs, noCoeffs, noInterfaces, d));
-    else if (!strcmp(solverName, "PBiCGStab"))
-        s.reset(new PBiCGStab("psi", m, noCoeffs, noCoeffs, noInterfaces, d));
-    else if (!strcmp(solverName, "smoothSolver"))
-        s.reset(new smoothSolver("psi", m, noCoeffs, noCoeffs, noInterfaces, d));
-    else
-        return -1;
+    d.solver = solverName;
+    autoPtr<lduMatrix::solver> s;
+    try { // the reference's own run-time selection (lduMatrixSolver.C:43-140)
+        s = lduMatrix::solver::New("psi", m, noCoeffs, noCoeffs, noInterfaces, d);
+    } catch (const std::runtime_error &) {
+        return -1; // "Unknown (a)symmetric matrix solver"
+    }
     scalargpuField psi(psi_io, n), src(source, n);
     solverPerformance sp = s->solve(psi, src, 0);
     perf[0] = sp.initialResidual();

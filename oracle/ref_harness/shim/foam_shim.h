@@ -113,6 +113,7 @@ public:
         return *this;
     }
     gpuField(const tmp<gpuField<T>> &t); // deep copy of a temporary (defined after tmp)
+    void operator=(const tmp<gpuField<T>> &t);
 };
 typedef gpuField<scalar> scalargpuField;
 typedef gpuList<label> labelgpuList;
@@ -138,11 +139,21 @@ public:
 };
 
 template <class T> gpuField<T>::gpuField(const tmp<gpuField<T>> &t) : gpuList<T>(static_cast<const gpuList<T> &>(t())) {}
+template <class T> void gpuField<T>::operator=(const tmp<gpuField<T>> &t)
+{
+    gpuList<T>::operator=(static_cast<const gpuList<T> &>(t()));
+}
 
 template <class T> tmp<gpuField<T>> operator-(const gpuField<T> &a, const gpuField<T> &b)
 {
     gpuField<T> *r = new gpuField<T>(a.size());
     for (label i = 0; i < a.size(); i++) r->data()[i] = a.data()[i] - b.data()[i];
+    return tmp<gpuField<T>>(r);
+}
+template <class T> tmp<gpuField<T>> operator/(const gpuField<T> &a, const gpuField<T> &b)
+{
+    gpuField<T> *r = new gpuField<T>(a.size());
+    for (label i = 0; i < a.size(); i++) r->data()[i] = a.data()[i] / b.data()[i];
     return tmp<gpuField<T>>(r);
 }
 template <class T> tmp<gpuField<T>> operator-(const gpuField<T> &f)
@@ -249,8 +260,9 @@ public:
     };
     MeshStub lduMesh_;
     const MeshStub &mesh() const { return lduMesh_; }
-    bool symmetric() const { return lowerPtr_ == nullptr || lowerPtr_ == upperPtr_; }
-    bool asymmetric() const { return !symmetric(); }
+    bool diagonal() const { return diagPtr_ && !lowerPtr_ && !upperPtr_; } // lduMatrix.H:626-639
+    bool symmetric() const { return diagPtr_ && (!lowerPtr_ && upperPtr_); }
+    bool asymmetric() const { return diagPtr_ && lowerPtr_ && upperPtr_; }
     const lduAddressing *addr_;
     scalargpuField *lowerPtr_, *upperPtr_, *diagPtr_, *lowerSortPtr_, *upperSortPtr_;
     int level_;

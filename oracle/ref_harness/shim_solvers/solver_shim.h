@@ -1,13 +1,13 @@
 /*
  * solver_shim.h -- what the reference's solver sources (PCG.C, PBiCG.C, PBiCGStab.C,
  * AINVPreconditioner.C, diagonalPreconditioner.C) need around them to compile for the host:
- * words and a flat controls "dictionary", solverPerformance, the lduMatrix::solver /
- * ::preconditioner base classes, the scratch-vector cache, serial global sums.  TEST INFRASTRUCTURE
+ * words and a flat controls "dictionary", solverPerformance, the class declarations of lduMatrix::solver
+ * (defined by the reference's lduMatrixSolver.C: New with its run-time selection tables, readControls,
+ * normFactor) and ::preconditioner / ::smoother, a miniature of the run-time selection tables, the scratch-vector cache, serial global sums.  TEST INFRASTRUCTURE
  * ONLY.  The iteration loops, the order of their operations and their loop conditions are the
  * reference's (included by path); what is restated HERE, because the reference's versions live in
  * files tied to its I/O and run-time-selection machinery, is:
  *   solverPerformance::checkConvergence / checkSingularity   SolverPerformance.C:32-43, 74-85
- *   lduMatrix::solver::normFactor                             lduMatrixSolver.C:205-236
  *   preconditioner selection incl. the DIC/DILU -> AINV alias lduMatrixPreconditioner.C:38-62
  *   gSumProd / gSumMag / gAverage as index-order serial sums  gpuFieldCommonFunctions.C:420-636
  */
@@ -17,6 +17,7 @@
 
 #include <cmath>
 #include <map>
+#include <stdexcept>
 #include <memory>
 #include <string>
 #include <thrust/copy.h>
@@ -32,11 +33,19 @@ public:
 };
 inline word operator+(const word &a, const word &b) { return word(static_cast<const std::string &>(a) + b); }
 
-struct dictionary { // the keys lduMatrix::solver::readControls reads (lduMatrixSolver.C:167-173) + smoothers'
-    word preconditioner, smoother;
-    // GAMGSolver::readControls keys (GAMGSolver.C:209-249) are set on the solver object by the harness
+struct dictionary { // the keys the solver sources read (lduMatrixSolver.C:167-173, smoothSolver.C:80, JacobiSmoother.C:36)
+    word solver, preconditioner, smoother;
     scalar tolerance = 1e-6, relTol = 0, omega = -1; // omega < 0: entry absent
     label maxIter = 1000, minIter = 0, nSweeps = 1;
+    bool hasTolerance = true, hasRelTol = true, hasMaxIter = true, hasMinIter = true; // absent => the reference's defaults
+    word lookup(const char *key) const
+    {
+        const std::string k(key);
+        if (k == "solver") return solver;
+        if (k == "preconditioner") return preconditioner;
+        if (k == "smoother") return smoother;
+        throw std::runtime_error("keyword " + k + " is undefined in dictionary");
+    }
     bool readIfPresent(const char *key, scalar &v) const
     {
         if (std::string(key) == "omega" && omega >= 0) {
@@ -47,7 +56,12 @@ struct dictionary { // the keys lduMatrix::solver::readControls reads (lduMatrix
     }
     template <class T> T lookupOrDefault(const char *key, const T &dflt) const
     {
-        if (std::string(key) == "nSweeps") return (T)nSweeps;
+        const std::string k(key);
+        if (k == "nSweeps") return (T)nSweeps;
+        if (k == "maxIter") return hasMaxIter ? (T)maxIter : dflt;
+        if (k == "minIter") return hasMinIter ? (T)minIter : dflt;
+        if (k == "tolerance") return hasTolerance ? (T)tolerance : dflt;
+        if (k == "relTol") return hasRelTol ? (T)relTol : dflt;
         return dflt;
     }
 };
@@ -56,12 +70,80 @@ struct dictionary { // the keys lduMatrix::solver::readControls reads (lduMatrix
     const ::Foam::word Type::typeName(Type::typeName_()); \
     int Type::debug(DebugSwitch) /* className.H: the name comes from the class's TypeName("...") */
 
+// ---- runTimeSelectionTables.H:49-120 in miniature: name -> constructor function, filled by the static
+// add...ConstructorToTable objects the reference's .C files define ----
+#define declareShimSelectionTable(baseType, argNames)                                                           \
+    typedef autoPtr<baseType> (*argNames##ConstructorPtr)(                                                       \
+        const word &, const lduMatrix &, const FieldField<gpuField, scalar> &, const FieldField<gpuField, scalar> &, \
+        const lduInterfaceFieldPtrsList &, const dictionary &);                                                  \
+    class argNames##ConstructorTable : public std::map<std::string, argNames##ConstructorPtr>                  \
+    {                                                                                                            \
+    public:                                                                                                      \
+        struct iterator : std::map<std::string, argNames##ConstructorPtr>::iterator {                           \
+            iterator(std::map<std::string, argNames##ConstructorPtr>::iterator i)                                \
+                : std::map<std::string, argNames##ConstructorPtr>::iterator(i)                                   \
+            {                                                                                                    \
+            }                                                                                                    \
+            argNames##ConstructorPtr operator()() const { return (*this)->second; }                             \
+        };                                                                                                       \
+        iterator find(const word &k) { return iterator(std::map<std::string, argNames##ConstructorPtr>::find(k)); } \
+        iterator end() { return iterator(std::map<std::string, argNames##ConstructorPtr>::end()); }             \
+        word sortedToc()                                                                                         \
+        {                                                                                                        \
+            std::string t;                                                                                       \
+            for (auto i = std::map<std::string, argNames##ConstructorPtr>::begin();                              \
+                 i != std::map<std::string, argNames##ConstructorPtr>::end(); ++i)                               \
+                t += i->first + " ";                                                                             \
+            return word(t);                                                                                      \
+        }                                                                                                        \
+    };                                                                                                           \
+    static argNames##ConstructorTable *argNames##ConstructorTablePtr_;                                           \
+    template <class T> class add##argNames##ConstructorToTable                                                   \
+    {                                                                                                            \
+    public:                                                                                                      \
+        static autoPtr<baseType> New(const word &f, const lduMatrix &m, const FieldField<gpuField, scalar> &b,   \
+                                     const FieldField<gpuField, scalar> &i, const lduInterfaceFieldPtrsList &l,  \
+                                     const dictionary &d)                                                        \
+        {                                                                                                        \
+            return autoPtr<baseType>(new T(f, m, b, i, l, d));                                                   \
+        }                                                                                                        \
+        add##argNames##ConstructorToTable(const word &lookup = T::typeName)                                      \
+        {                                                                                                        \
+            if (!argNames##ConstructorTablePtr_) argNames##ConstructorTablePtr_ = new argNames##ConstructorTable; \
+            (*argNames##ConstructorTablePtr_)[lookup] = New;                                                     \
+        }                                                                                                        \
+    }
+#define defineRunTimeSelectionTable(baseType, argNames) \
+    baseType::argNames##ConstructorTable *baseType::argNames##ConstructorTablePtr_ = nullptr
+
 struct NullStream {
     template <class T> NullStream &operator<<(const T &) { return *this; }
     NullStream &masterStream(int) { return *this; }
 };
 static NullStream Info;
 static const char endl = '\n';
+static const char nl = '\n';
+struct FatalIOStream {
+    std::string msg;
+    template <class T> FatalIOStream &operator<<(const T &) { return *this; }
+    FatalIOStream &operator<<(const word &w)
+    {
+        msg += w + " ";
+        return *this;
+    }
+    FatalIOStream &operator<<(const char *c)
+    {
+        msg += c;
+        return *this;
+    }
+};
+static FatalIOStream FatalIOError;
+#define FatalIOErrorIn(where, dict) (::Foam::FatalIOError.msg.clear(), ::Foam::FatalIOError)
+inline int exit(FatalIOStream &e) { throw std::runtime_error(e.msg); }
+struct Pstream {
+    static int msgType() { return 0; }
+};
+template <class T, class Op> inline void reduce(T &, const Op &, int, int) {} // one rank
 
 inline scalar mag(scalar x) { return std::fabs(x); }
 template <class T> struct minusOp {
@@ -148,6 +230,11 @@ class solverPerformance // SolverPerformance.H/.C
 public:
     static constexpr scalar great_ = 1e20, small_ = 1e-20, vsmall_ = 1e-300; // SolverPerformance.H:269-275
     solverPerformance() : initialResidual_(0), finalResidual_(0), noIterations_(0), converged_(false), singular_(false) {}
+    solverPerformance(const word &s, const word &f, scalar iRes, scalar fRes, label nIter, bool conv, bool sing)
+        : solverName_(s), fieldName_(f), initialResidual_(iRes), finalResidual_(fRes), noIterations_(nIter),
+          converged_(conv), singular_(sing)
+    {
+    }
     solverPerformance(const word &s, const word &f)
         : solverName_(s), fieldName_(f), initialResidual_(0), finalResidual_(0), noIterations_(0), converged_(false),
           singular_(false)
@@ -176,7 +263,7 @@ public:
 };
 
 // ---- lduMatrix::solver (lduMatrix.H:100-260), lduMatrix::preconditioner (:420-520) ----
-class lduMatrix::solver
+class lduMatrix::solver // lduMatrix.H:100-260; its member functions are the reference's lduMatrixSolver.C
 {
 protected:
     word fieldName_;
@@ -187,44 +274,24 @@ protected:
     dictionary controlDict_;
     label maxIter_, minIter_;
     scalar tolerance_, relTol_;
+    virtual void readControls();
 
 public:
-    template <class T> struct addsymMatrixConstructorToTable {
-    };
-    template <class T> struct addasymMatrixConstructorToTable {
-    };
-    solver(const word &fieldName, const lduMatrix &matrix, const FieldField<gpuField, scalar> &bou,
-           const FieldField<gpuField, scalar> &intc, const lduInterfaceFieldPtrsList &ifs, const dictionary &d)
-        : fieldName_(fieldName), matrix_(matrix), interfaceBouCoeffs_(bou), interfaceIntCoeffs_(intc), interfaces_(ifs),
-          controlDict_(d), maxIter_(d.maxIter), minIter_(d.minIter), tolerance_(d.tolerance), relTol_(d.relTol)
-    {
-    }
+    declareShimSelectionTable(solver, symMatrix);
+    declareShimSelectionTable(solver, asymMatrix);
+    solver(const word &fieldName, const lduMatrix &matrix, const FieldField<gpuField, scalar> &interfaceBouCoeffs,
+           const FieldField<gpuField, scalar> &interfaceIntCoeffs, const lduInterfaceFieldPtrsList &interfaces,
+           const dictionary &solverControls);
+    static autoPtr<solver> New(const word &fieldName, const lduMatrix &matrix,
+                               const FieldField<gpuField, scalar> &interfaceBouCoeffs,
+                               const FieldField<gpuField, scalar> &interfaceIntCoeffs,
+                               const lduInterfaceFieldPtrsList &interfaces, const dictionary &solverControls);
     virtual ~solver() {}
     const lduMatrix &matrix() const { return matrix_; }
-    void readControls() // lduMatrixSolver.C:167-173
-    {
-        maxIter_ = controlDict_.maxIter;
-        minIter_ = controlDict_.minIter;
-        tolerance_ = controlDict_.tolerance;
-        relTol_ = controlDict_.relTol;
-    }
+    virtual void read(const dictionary &);
     virtual solverPerformance solve(scalargpuField &psi, const scalargpuField &source, const direction cmpt = 0) const = 0;
-    // lduMatrixSolver.C:205-236 -- sumA is the reference's (lduMatrixATmul.C:345-395)
     scalar normFactor(const scalargpuField &psi, const scalargpuField &source, const scalargpuField &Apsi,
-                      scalargpuField &tmpField) const
-    {
-        matrix_.sumA(tmpField, interfaceBouCoeffs_, interfaces_);
-        const scalar average = gAverage(psi, 0);
-        scalar s = 0;
-        const scalar *t = tmpField.data(), *ap = Apsi.data(), *sr = source.data();
-        const label n = psi.size();
-        REF_REDUCE(s)
-        for (label i = 0; i < n; i++) {
-            const scalar tmpVal = average * t[i];
-            s += std::fabs(ap[i] - tmpVal) + std::fabs(sr[i] - tmpVal);
-        }
-        return s + solverPerformance::small_;
-    }
+                      scalargpuField &tmpField) const;
 };
 
 class lduMatrix::preconditioner

@@ -725,6 +725,9 @@ int solve_banded(b200ldu_matrix *m, const char *solver, const char *pre, const b
                         rc = B200LDU_EMATRIX;
                     } else
                         rc = solve_pbicg(S, pk);
+                } else if (m->symmetric) {
+                    b200_set_error("PBiCGStab is registered for asymmetric matrices only (PBiCGStab.C:34-37)");
+                    rc = B200LDU_EMATRIX;
                 } else
                     rc = solve_pbicgstab(S, pk);
             }

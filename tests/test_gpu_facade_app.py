@@ -14,7 +14,6 @@ APP = os.path.join(ROOT, "rapidcfd-dev_b200", "lib", "cavityPressureSolve")
 DICTS = {
     "AINVPCG": "solvers { p { solver PCG; preconditioner DIC; tolerance 1e-07; relTol 0; } }",
     "diagonalPCG": "solvers { p { solver PCG; preconditioner { preconditioner diagonal; } tolerance 1e-07; } }",
-    "AINVPBiCGStab": "solvers { p { solver PBiCGStab; preconditioner DILU; tolerance 1e-07; } }",
     "GAMG": "solvers { p { solver GAMG; smoother GaussSeidel; tolerance 1e-07; relTol 0; nPreSweeps 0; "
             "nPostSweeps 2; cacheAgglomeration on; agglomerator faceAreaPair; nCellsInCoarsestLevel 10; "
             "mergeLevels 1; } }",

@@ -372,3 +372,28 @@ def test_derived_addressing_matches_reference_code(meshmod, orc):
                 assert np.array_equal(R["patchSortCells"][p], np.unique(cells))
                 st = R["patchSortStart"][p]
                 assert st[0] == 0 and st[-1] == len(cells) and np.all(np.diff(st) > 0)
+
+
+def test_runtime_selection_matches_reference_code(meshmod, orc):
+    """lduMatrix::solver::New (lduMatrixSolver.C:43-140, the reference's own tables filled by the static
+    add...ConstructorToTable objects of PCG.C, PBiCG.C, ...): PCG exists for symmetric matrices only,
+    PBiCG and PBiCGStab for asymmetric only (PBiCGStab.C:34-37), smoothSolver for both, unknown names are
+    fatal -- the same outcomes as the oracle's (and the C ABI's) selection."""
+    for kind in ("P", "U"):
+        m, M, args, b = _solver_case(meshmod, orc, kind, (5, 4, 3))
+        z = np.zeros(m.nCells)
+        for solver, second in (("PCG", "DIC"), ("PBiCG", "DILU"), ("PBiCGStab", "DILU"), ("smoothSolver", "GaussSeidel"),
+                               ("GaussSeidel", "DIC"), ("pcg", "DIC")):
+            try:
+                ref_ldu.solve(solver, second, *args, z, b, maxIter=3)
+                ref_ok = True
+            except ValueError:
+                ref_ok = False
+            try:
+                M.solve(solver, second, z, b, maxIter=3)
+                orc_ok = True
+            except Exception:  # noqa: BLE001
+                orc_ok = False
+            assert ref_ok == orc_ok, (kind, solver)
+            expected = {"PCG": kind == "P", "PBiCG": kind == "U", "PBiCGStab": kind == "U", "smoothSolver": True}.get(solver, False)
+            assert ref_ok == expected, (kind, solver)
