@@ -766,18 +766,18 @@ int orc_solve(const orc_matrix *m, const char *solver, const char *pre, const or
         pre = "DILU";
     }
     if (!strcmp(solver, "PCG") || !strcmp(solver, "PBiCG") || !strcmp(solver, "PBiCGStab")) {
+        /* solver::New looks the name up in the table of the matrix kind first (lduMatrixSolver.C:70-133):
+         * PCG symmetric only (PCG.C:36), PBiCG / PBiCGStab asymmetric only (PBiCG.C:36, PBiCGStab.C:36) */
+        int wantSym = !strcmp(solver, "PCG");
+        if (wantSym != (m->symmetric ? 1 : 0)) return -3;
+        /* preconditioner::New inside solve(): DIC is registered for symmetric matrices, DILU for asymmetric
+         * ones, AINV / diagonal / none for both (DICPreconditioner.C:35, DILUPreconditioner.C:35, ...) */
         int pk = orc_precond_kind(pre, pname);
         if (pk < 0) return -2;
+        if (pre && ((!strcmp(pre, "DILU") && m->symmetric) || (!strcmp(pre, "DIC") && !m->symmetric))) return -2;
         snprintf(perf->solverName, sizeof(perf->solverName), "%s%s", pname, solver);
-        if (!strcmp(solver, "PCG")) {
-            if (!m->symmetric) return -3; /* PCG only in the symMatrix table PCG.C:36-37 */
-            return orc_pcg(m, pk, c, psi, source, comm, perf, hist, histCap);
-        }
-        if (!strcmp(solver, "PBiCG")) {
-            if (m->symmetric) return -3; /* asymMatrix table only PBiCG.C:36-37 */
-            return orc_pbicg(m, pk, c, psi, source, comm, perf, hist, histCap);
-        }
-        if (m->symmetric) return -3; /* asymMatrix table only: PBiCGStab.C:34-37 */
+        if (!strcmp(solver, "PCG")) return orc_pcg(m, pk, c, psi, source, comm, perf, hist, histCap);
+        if (!strcmp(solver, "PBiCG")) return orc_pbicg(m, pk, c, psi, source, comm, perf, hist, histCap);
         return orc_pbicgstab(m, pk, c, psi, source, comm, perf, hist, histCap);
     }
     if (!strcmp(solver, "smoothSolver")) {

@@ -44,12 +44,17 @@ public:
 #include "lduMatrixATmul.C"
 #include "lduMatrixSolver.C" /* solver base: constructor, readControls, normFactor, New */
 #include "diagonalSolver.C"
+#include "lduMatrixPreconditioner.C" /* preconditioner::New / getName with the reference's tables */
+#include "lduMatrixSmoother.C"       /* smoother::New / getName */
 #include "AINVPreconditioner.C"
+#include "DICPreconditioner.C"
+#include "DILUPreconditioner.C"
 #include "diagonalPreconditioner.C"
 #include "noPreconditioner.C"
 #include "PCG.C"
 #include "PBiCG.C"
 #include "JacobiSmoother.C"
+#include "GaussSeidelSmoother.C"
 #include "GAMGSolverSolve.C"
 #include "GAMGSolverScale.C"
 #include "GAMGSolverInterpolate.C"
@@ -66,26 +71,7 @@ GAMGSolver::~GAMGSolver() { delete coarsestBufferPtr_; }
 const gpuField<scalar> &lduMatrixSolutionCache::first(label size) { return ScratchPool::get("first", size); }
 const gpuField<scalar> &lduMatrixSolutionCache::second(label size) { return ScratchPool::get("second", size); }
 
-word lduMatrix::preconditioner::getName(const dictionary &d)
-{
-    if (d.preconditioner == "DIC" || d.preconditioner == "DILU") return AINVPreconditioner::typeName;
-    return d.preconditioner;
-}
-autoPtr<lduMatrix::preconditioner> lduMatrix::preconditioner::New(const solver &sol, const dictionary &d)
-{
-    const word &n = d.preconditioner;
-    if (n == "DIC" || n == "DILU" || n == "AINV") return autoPtr<preconditioner>(new AINVPreconditioner(sol, d));
-    if (n == "diagonal") return autoPtr<preconditioner>(new diagonalPreconditioner(sol, d));
-    return autoPtr<preconditioner>(new noPreconditioner(sol, d));
-}
-autoPtr<lduMatrix::smoother> lduMatrix::smoother::New(const word &fieldName, const lduMatrix &matrix,
-                                                      const FieldField<gpuField, scalar> &bou,
-                                                      const FieldField<gpuField, scalar> &intc,
-                                                      const lduInterfaceFieldPtrsList &ifs, const dictionary &d)
-{
-    return autoPtr<smoother>(new JacobiSmoother(fieldName, matrix, bou, intc, ifs, d)); // GaussSeidel == Jacobi here
-}
-
+const dictionary dictionary::null;
 } // namespace Foam
 
 using namespace Foam;

@@ -21,13 +21,18 @@
 #include "lduMatrixATmul.C"
 #include "lduMatrixSolver.C" /* solver::New (run-time selection), readControls, normFactor */
 #include "diagonalSolver.C"
+#include "lduMatrixPreconditioner.C" /* preconditioner::New / getName with the reference's tables */
+#include "lduMatrixSmoother.C"       /* smoother::New / getName */
 #include "AINVPreconditioner.C"
+#include "DICPreconditioner.C"
+#include "DILUPreconditioner.C"
 #include "diagonalPreconditioner.C"
 #include "noPreconditioner.C"
 #include "PCG.C"
 #include "PBiCG.C"
 #include "PBiCGStab.C"
 #include "JacobiSmoother.C"
+#include "GaussSeidelSmoother.C"
 #include "smoothSolver.C"
 
 #include <cstring>
@@ -39,33 +44,7 @@ int lduMatrix::debug = 0;
 const gpuField<scalar> &lduMatrixSolutionCache::first(label size) { return ScratchPool::get("first", size); }
 const gpuField<scalar> &lduMatrixSolutionCache::second(label size) { return ScratchPool::get("second", size); }
 
-// lduMatrixSmoother.C: selection by the `smoother` word; GaussSeidel is a JacobiSmoother subclass in RapidCFD
-// (GaussSeidelSmoother.C:43-69)
-autoPtr<lduMatrix::smoother> lduMatrix::smoother::New(const word &fieldName, const lduMatrix &matrix,
-                                                      const FieldField<gpuField, scalar> &bou,
-                                                      const FieldField<gpuField, scalar> &intc,
-                                                      const lduInterfaceFieldPtrsList &ifs, const dictionary &d)
-{
-    if (d.smoother == "GaussSeidel" || d.smoother == "Jacobi")
-        return autoPtr<smoother>(new JacobiSmoother(fieldName, matrix, bou, intc, ifs, d));
-    return autoPtr<smoother>(nullptr);
-}
-
-// lduMatrixPreconditioner.C:38-62 (name as printed) and :65-140 (selection; DIC and DILU are registered
-// names of the AINV implementation in RapidCFD)
-word lduMatrix::preconditioner::getName(const dictionary &d)
-{
-    if (d.preconditioner == "DIC" || d.preconditioner == "DILU") return AINVPreconditioner::typeName;
-    return d.preconditioner;
-}
-autoPtr<lduMatrix::preconditioner> lduMatrix::preconditioner::New(const solver &sol, const dictionary &d)
-{
-    const word &n = d.preconditioner;
-    if (n == "DIC" || n == "DILU" || n == "AINV") return autoPtr<preconditioner>(new AINVPreconditioner(sol, d));
-    if (n == "diagonal") return autoPtr<preconditioner>(new diagonalPreconditioner(sol, d));
-    if (n == "none") return autoPtr<preconditioner>(new noPreconditioner(sol, d));
-    return autoPtr<preconditioner>(nullptr);
-}
+const dictionary dictionary::null;
 } // namespace Foam
 
 using namespace Foam;
@@ -117,14 +96,6 @@ int ref_solve(const char *solverName, const char *precond, int favourSpeed, int 
     d.minIter = minIter;
     FieldField<gpuField, scalar> noCoeffs(0);
     lduInterfaceFieldPtrsList noInterfaces;
-    {
-        // unknown preconditioner: the reference aborts in preconditioner::New; report it instead
-        const word p(precond);
-        const bool smooth = !strcmp(solverName, "smoothSolver");
-        if (smooth ? !(p == "GaussSeidel" || p == "Jacobi")
-                   : !(p == "DIC" || p == "DILU" || p == "AINV" || p == "diagonal" || p == "none"))
-            return -2;
-    }
     d.solver = solverName;
     autoPtr<lduMatrix::solver> s;
     try { // the reference's own run-time selection (lduMatrixSolver.C:43-140)
@@ -133,7 +104,12 @@ int ref_solve(const char *solverName, const char *precond, int favourSpeed, int 
         return -1; // "Unknown (a)symmetric matrix solver"
     }
     scalargpuField psi(psi_io, n), src(source, n);
-    solverPerformance sp = s->solve(psi, src, 0);
+    solverPerformance sp;
+    try { // preconditioner::New / smoother::New are called inside solve(): unknown names are fatal there
+        sp = s->solve(psi, src, 0);
+    } catch (const std::runtime_error &) {
+        return -2;
+    }
     perf[0] = sp.initialResidual();
     perf[1] = sp.finalResidual();
     perf[2] = sp.nIterations();

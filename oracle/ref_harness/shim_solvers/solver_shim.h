@@ -8,7 +8,6 @@
  * reference's (included by path); what is restated HERE, because the reference's versions live in
  * files tied to its I/O and run-time-selection machinery, is:
  *   solverPerformance::checkConvergence / checkSingularity   SolverPerformance.C:32-43, 74-85
- *   preconditioner selection incl. the DIC/DILU -> AINV alias lduMatrixPreconditioner.C:38-62
  *   gSumProd / gSumMag / gAverage as index-order serial sums  gpuFieldCommonFunctions.C:420-636
  */
 #ifndef SOLVER_SHIM_H
@@ -32,7 +31,10 @@ public:
     word(const std::string &s) : std::string(s) {}
 };
 inline word operator+(const word &a, const word &b) { return word(static_cast<const std::string &>(a) + b); }
+inline void operator>>(const word &in, word &out) { out = in; } // `dict.lookup("key") >> name`
 
+struct dictionary;
+typedef struct dictionary dictionaryFwd;
 struct dictionary { // the keys the solver sources read (lduMatrixSolver.C:167-173, smoothSolver.C:80, JacobiSmoother.C:36)
     word solver, preconditioner, smoother;
     scalar tolerance = 1e-6, relTol = 0, omega = -1; // omega < 0: entry absent
@@ -46,6 +48,19 @@ struct dictionary { // the keys the solver sources read (lduMatrixSolver.C:167-1
         if (k == "smoother") return smoother;
         throw std::runtime_error("keyword " + k + " is undefined in dictionary");
     }
+    // dictionary::lookupEntry(...): the word behind `preconditioner` / `smoother` (always a primitive entry here)
+    struct entryStream {
+        word w;
+        void operator>>(word &out) const { out = w; }
+    };
+    struct entry {
+        word w;
+        bool isDict() const { return false; }
+        const dictionary &dict() const { return dictionary::null; }
+        entryStream stream() const { return entryStream{w}; }
+    };
+    static const dictionary null;
+    entry lookupEntry(const char *key, bool, bool) const { return entry{lookup(key)}; }
     bool readIfPresent(const char *key, scalar &v) const
     {
         if (std::string(key) == "omega" && omega >= 0) {
@@ -66,16 +81,16 @@ struct dictionary { // the keys the solver sources read (lduMatrixSolver.C:167-1
     }
 };
 
+typedef dictionary::entry entry;
+
 #define defineTypeNameAndDebug(Type, DebugSwitch)         \
     const ::Foam::word Type::typeName(Type::typeName_()); \
     int Type::debug(DebugSwitch) /* className.H: the name comes from the class's TypeName("...") */
 
 // ---- runTimeSelectionTables.H:49-120 in miniature: name -> constructor function, filled by the static
 // add...ConstructorToTable objects the reference's .C files define ----
-#define declareShimSelectionTable(baseType, argNames)                                                           \
-    typedef autoPtr<baseType> (*argNames##ConstructorPtr)(                                                       \
-        const word &, const lduMatrix &, const FieldField<gpuField, scalar> &, const FieldField<gpuField, scalar> &, \
-        const lduInterfaceFieldPtrsList &, const dictionary &);                                                  \
+#define declareShimSelectionTable(baseType, argNames, argList, parList)                                          \
+    typedef autoPtr<baseType>(*argNames##ConstructorPtr) argList;                                                \
     class argNames##ConstructorTable : public std::map<std::string, argNames##ConstructorPtr>                  \
     {                                                                                                            \
     public:                                                                                                      \
@@ -101,18 +116,17 @@ struct dictionary { // the keys the solver sources read (lduMatrixSolver.C:167-1
     template <class T> class add##argNames##ConstructorToTable                                                   \
     {                                                                                                            \
     public:                                                                                                      \
-        static autoPtr<baseType> New(const word &f, const lduMatrix &m, const FieldField<gpuField, scalar> &b,   \
-                                     const FieldField<gpuField, scalar> &i, const lduInterfaceFieldPtrsList &l,  \
-                                     const dictionary &d)                                                        \
-        {                                                                                                        \
-            return autoPtr<baseType>(new T(f, m, b, i, l, d));                                                   \
-        }                                                                                                        \
+        static autoPtr<baseType> New argList { return autoPtr<baseType>(new T parList); }                        \
         add##argNames##ConstructorToTable(const word &lookup = T::typeName)                                      \
         {                                                                                                        \
             if (!argNames##ConstructorTablePtr_) argNames##ConstructorTablePtr_ = new argNames##ConstructorTable; \
             (*argNames##ConstructorTablePtr_)[lookup] = New;                                                     \
         }                                                                                                        \
     }
+#define SHIM_SOLVER_ARGS                                                                                         \
+    (const word &f, const lduMatrix &m, const FieldField<gpuField, scalar> &b, const FieldField<gpuField, scalar> &i, \
+     const lduInterfaceFieldPtrsList &l, const dictionary &d)
+#define SHIM_SOLVER_PARS (f, m, b, i, l, d)
 #define defineRunTimeSelectionTable(baseType, argNames) \
     baseType::argNames##ConstructorTable *baseType::argNames##ConstructorTablePtr_ = nullptr
 
@@ -277,8 +291,8 @@ protected:
     virtual void readControls();
 
 public:
-    declareShimSelectionTable(solver, symMatrix);
-    declareShimSelectionTable(solver, asymMatrix);
+    declareShimSelectionTable(solver, symMatrix, SHIM_SOLVER_ARGS, SHIM_SOLVER_PARS);
+    declareShimSelectionTable(solver, asymMatrix, SHIM_SOLVER_ARGS, SHIM_SOLVER_PARS);
     solver(const word &fieldName, const lduMatrix &matrix, const FieldField<gpuField, scalar> &interfaceBouCoeffs,
            const FieldField<gpuField, scalar> &interfaceIntCoeffs, const lduInterfaceFieldPtrsList &interfaces,
            const dictionary &solverControls);
@@ -294,16 +308,14 @@ public:
                       scalargpuField &tmpField) const;
 };
 
-class lduMatrix::preconditioner
+class lduMatrix::preconditioner // lduMatrix.H:420-520; New / getName are the reference's lduMatrixPreconditioner.C
 {
 protected:
     const solver &solver_;
 
 public:
-    template <class T> struct addsymMatrixConstructorToTable {
-    };
-    template <class T> struct addasymMatrixConstructorToTable {
-    };
+    declareShimSelectionTable(preconditioner, symMatrix, (const solver &sol, const dictionary &d), (sol, d));
+    declareShimSelectionTable(preconditioner, asymMatrix, (const solver &sol, const dictionary &d), (sol, d));
     preconditioner(const solver &sol) : solver_(sol) {}
     virtual ~preconditioner() {}
     virtual void precondition(scalargpuField &wA, const scalargpuField &rA, const direction cmpt = 0) const = 0;
@@ -315,7 +327,7 @@ public:
     static autoPtr<preconditioner> New(const solver &sol, const dictionary &solverControls);
 };
 
-class lduMatrix::smoother // lduMatrix.H:262-414
+class lduMatrix::smoother // lduMatrix.H:262-414; New / getName are the reference's lduMatrixSmoother.C
 {
 protected:
     word fieldName_;
@@ -325,18 +337,14 @@ protected:
     lduInterfaceFieldPtrsList interfaces_;
 
 public:
-    template <class T> struct addsymMatrixConstructorToTable {
-    };
-    template <class T> struct addasymMatrixConstructorToTable {
-    };
+    declareShimSelectionTable(smoother, symMatrix, SHIM_SOLVER_ARGS, SHIM_SOLVER_PARS);
+    declareShimSelectionTable(smoother, asymMatrix, SHIM_SOLVER_ARGS, SHIM_SOLVER_PARS);
     smoother(const word &fieldName, const lduMatrix &matrix, const FieldField<gpuField, scalar> &bou,
-             const FieldField<gpuField, scalar> &intc, const lduInterfaceFieldPtrsList &ifs)
-        : fieldName_(fieldName), matrix_(matrix), interfaceBouCoeffs_(bou), interfaceIntCoeffs_(intc), interfaces_(ifs)
-    {
-    }
+             const FieldField<gpuField, scalar> &intc, const lduInterfaceFieldPtrsList &ifs);
     virtual ~smoother() {}
     virtual void smooth(scalargpuField &psi, const scalargpuField &source, const direction cmpt,
                         const label nSweeps) const = 0;
+    static word getName(const dictionary &);
     static autoPtr<smoother> New(const word &fieldName, const lduMatrix &matrix, const FieldField<gpuField, scalar> &bou,
                                  const FieldField<gpuField, scalar> &intc, const lduInterfaceFieldPtrsList &ifs,
                                  const dictionary &solverControls);

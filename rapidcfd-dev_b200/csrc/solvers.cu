@@ -703,33 +703,35 @@ int solve_banded(b200ldu_matrix *m, const char *solver, const char *pre, const b
             pre = "DILU";
         }
         if (!strcmp(sv, "PCG") || !strcmp(sv, "PBiCG") || !strcmp(sv, "PBiCGStab")) {
-            int pk = precond_kind(pre, pname);
-            if (pk < 0) {
+            // solver::New looks the name up in the table of the matrix kind first (lduMatrixSolver.C:70-133); the
+            // preconditioner is selected inside solve() from the tables of the same kind: DIC symmetric, DILU
+            // asymmetric, AINV / diagonal / none both (DICPreconditioner.C:35, DILUPreconditioner.C:35, ...)
+            const bool wantSym = !strcmp(sv, "PCG");
+            int pk = -1;
+            if (wantSym != (bool)m->symmetric) {
+                b200_set_error("%s is registered for %s matrices only (PCG.C:36, PBiCG.C:36, PBiCGStab.C:36)", sv,
+                               wantSym ? "symmetric" : "asymmetric");
+                rc = B200LDU_EMATRIX;
+            } else if ((pk = precond_kind(pre, pname)) < 0) {
+                rc = B200LDU_ENOPRECOND;
+            } else if (pre && ((!strcmp(pre, "DILU") && m->symmetric) || (!strcmp(pre, "DIC") && !m->symmetric))) {
+                b200_set_error("Unknown %s matrix preconditioner %s; valid %s matrix preconditioners: (AINV %s diagonal none)",
+                               m->symmetric ? "symmetric" : "asymmetric", pre, m->symmetric ? "symmetric" : "asymmetric",
+                               m->symmetric ? "DIC" : "DILU");
                 rc = B200LDU_ENOPRECOND;
             } else {
                 snprintf(perf->solverName, sizeof(perf->solverName), "%s%s", pname, sv);
                 if (!strcmp(sv, "PCG")) {
-                    if (!m->symmetric) {
-                        b200_set_error("PCG is registered for symmetric matrices only (PCG.C:36-37)");
-                        rc = B200LDU_EMATRIX;
-                    } else {
-                        // the fused form needs the peer-memory halo (or no halo); B200LDU_PCG_FUSED=0 keeps
-                        // the reference's 7-kernel op list
-                        const char *ev = getenv("B200LDU_PCG_FUSED");
-                        bool fused = !(ev && atoi(ev) == 0) && (a->L.nRecv == 0 || a->p2pHalo);
-                        rc = fused ? solve_pcg_fused(S, pk) : solve_pcg(S, pk);
-                    }
+                    // the fused form needs the peer-memory halo (or no halo); B200LDU_PCG_FUSED=0 keeps
+                    // the reference's 7-kernel op list
+                    const char *ev = getenv("B200LDU_PCG_FUSED");
+                    bool fused = !(ev && atoi(ev) == 0) && (a->L.nRecv == 0 || a->p2pHalo);
+                    rc = fused ? solve_pcg_fused(S, pk) : solve_pcg(S, pk);
                 } else if (!strcmp(sv, "PBiCG")) {
-                    if (m->symmetric) {
-                        b200_set_error("PBiCG is registered for asymmetric matrices only (PBiCG.C:36-37)");
-                        rc = B200LDU_EMATRIX;
-                    } else
-                        rc = solve_pbicg(S, pk);
-                } else if (m->symmetric) {
-                    b200_set_error("PBiCGStab is registered for asymmetric matrices only (PBiCGStab.C:34-37)");
-                    rc = B200LDU_EMATRIX;
-                } else
+                    rc = solve_pbicg(S, pk);
+                } else {
                     rc = solve_pbicgstab(S, pk);
+                }
             }
         } else if (!strcmp(sv, "smoothSolver")) {
             if (!smoother_ok(pre))

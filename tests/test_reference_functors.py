@@ -397,3 +397,38 @@ def test_runtime_selection_matches_reference_code(meshmod, orc):
             assert ref_ok == orc_ok, (kind, solver)
             expected = {"PCG": kind == "P", "PBiCG": kind == "U", "PBiCGStab": kind == "U", "smoothSolver": True}.get(solver, False)
             assert ref_ok == expected, (kind, solver)
+
+
+def test_preconditioner_and_smoother_selection_matches_reference_code(meshmod, orc):
+    """lduMatrix::preconditioner::New / smoother::New (lduMatrixPreconditioner.C, lduMatrixSmoother.C) with
+    the tables the reference's classes register into: DIC exists for symmetric matrices only, DILU for
+    asymmetric only (both are AINV), AINV / diagonal / none for both; GaussSeidel and Jacobi smoothers for
+    both; anything else is fatal.  The oracle accepts and rejects the same names."""
+    for kind in ("P", "U"):
+        m, M, args, b = _solver_case(meshmod, orc, kind, (5, 4, 3))
+        z = np.zeros(m.nCells)
+        solver = "PCG" if kind == "P" else "PBiCG"
+        cases = [(solver, p) for p in ("DIC", "DILU", "AINV", "diagonal", "none", "FDIC", "GAMG")]
+        cases += [("smoothSolver", s) for s in ("GaussSeidel", "Jacobi", "symGaussSeidel", "DIC")]
+        for sv, second in cases:
+            try:
+                _, pr = ref_ldu.solve(sv, second, *args, z, b, maxIter=2)
+                ref_ok = True
+            except ValueError:
+                ref_ok = False
+            try:
+                _, po, _ = M.solve(sv, second, z, b, maxIter=2)
+                orc_ok = True
+            except Exception:  # noqa: BLE001
+                orc_ok = False
+            assert ref_ok == orc_ok, (kind, sv, second)
+            if ref_ok:
+                assert pr["solverName"] == po.solverName.decode(), (kind, sv, second)
+        expected_ok = {"P": {"DIC", "AINV", "diagonal", "none"}, "U": {"DILU", "AINV", "diagonal", "none"}}[kind]
+        for p in ("DIC", "DILU", "AINV", "diagonal", "none"):
+            try:
+                ref_ldu.solve(solver, p, *args, z, b, maxIter=1)
+                ok = True
+            except ValueError:
+                ok = False
+            assert ok == (p in expected_ok), (kind, p)
