@@ -382,3 +382,74 @@ def test_decompose_poly_mesh_matches_brick_decomposition(ff, meshmod, orc, tmp_p
         assert abs(nit - pref.nIterations) <= 1
         np.testing.assert_allclose(psi, psi_ref[cg], atol=1e-7)
         np.testing.assert_allclose(hist[:25], href[:25], rtol=1e-9)
+
+
+# ---- property tests (hypothesis): list files and dictionaries survive a write/parse round trip ----
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.lists(st.integers(min_value=-2**31, max_value=2**31 - 1), max_size=60), st.booleans())
+def test_label_list_roundtrip(tmp_path_factory, values, binary):
+    ff = importlib.import_module("rapidcfd-dev_b200.foamfile")
+    p = str(tmp_path_factory.mktemp("ll") / "owner")
+    ff.write_list(p, "label", np.array(values, dtype=np.int64), binary)
+    assert ff.read_list(p, "label").tolist() == values
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.lists(st.tuples(*[st.floats(allow_nan=False, allow_infinity=False, width=64)] * 3), max_size=40), st.booleans())
+def test_vector_list_roundtrip_is_exact(tmp_path_factory, values, binary):
+    ff = importlib.import_module("rapidcfd-dev_b200.foamfile")
+    p = str(tmp_path_factory.mktemp("vl") / "points")
+    a = np.array(values, dtype=np.float64).reshape(-1, 3)
+    ff.write_list(p, "vector", a, binary)
+    back = ff.read_list(p, "vector")
+    assert back.shape == a.shape and np.array_equal(back, a)      # repr() round-trips doubles exactly
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.lists(st.lists(st.integers(min_value=0, max_value=10**6), min_size=3, max_size=9), max_size=30), st.booleans())
+def test_face_list_roundtrip(tmp_path_factory, faces, binary):
+    ff = importlib.import_module("rapidcfd-dev_b200.foamfile")
+    p = str(tmp_path_factory.mktemp("fl") / "faces")
+    offs = np.concatenate([[0], np.cumsum([len(f) for f in faces])]).astype(np.int32)
+    labels = np.array([v for f in faces for v in f], dtype=np.int32)
+    ff.write_list(p, "face", (offs, labels), binary)
+    o2, l2 = ff.read_list(p, "face")
+    assert np.array_equal(o2, offs) and np.array_equal(l2, labels)
+
+
+_word = st.text(alphabet="abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ_", min_size=1, max_size=8)
+_scalar = st.one_of(st.integers(min_value=-10**6, max_value=10**6),
+                    st.floats(allow_nan=False, allow_infinity=False, min_value=-1e12, max_value=1e12), _word)
+# lists are homogeneous (all scalars or all lists): `N ( ... )` is OpenFOAM's sized-list notation, so an integer
+# directly followed by a list inside a list is genuinely ambiguous and not generated
+_value = st.one_of(_scalar, st.lists(_scalar, max_size=4), st.lists(st.lists(_scalar, max_size=3), max_size=3))
+_dict = st.recursive(st.dictionaries(_word, _value, max_size=4),
+                     lambda inner: st.dictionaries(_word, st.one_of(_value, inner), max_size=4), max_leaves=10)
+
+
+def _emit(d, ind=0):
+    pad = "    " * ind
+    out = []
+    for k, v in d.items():
+        if isinstance(v, dict):
+            out.append(f"{pad}{k}\n{pad}{{\n{_emit(v, ind + 1)}{pad}}}\n")
+        else:
+            out.append(f"{pad}{k} {_emit_value(v)};   // c\n")
+    return "".join(out)
+
+
+def _emit_value(v):
+    if isinstance(v, list):
+        return "( " + " ".join(_emit_value(x) for x in v) + " )"
+    return repr(v) if isinstance(v, float) else str(v)
+
+
+@settings(max_examples=60, deadline=None)
+@given(_dict)
+def test_dictionary_roundtrip(d):
+    ff = importlib.import_module("rapidcfd-dev_b200.foamfile")
+    text = "/* header */\n" + _emit(d)
+    assert ff.parse_dict(text).to_python() == d
