@@ -432,3 +432,39 @@ def test_preconditioner_and_smoother_selection_matches_reference_code(meshmod, o
             except ValueError:
                 ok = False
             assert ok == (p in expected_ok), (kind, p)
+
+
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.tuples(st.integers(1, 6), st.integers(1, 6), st.integers(1, 5)), st.integers(0, 2**31 - 1), st.booleans(),
+       st.sampled_from([0, 1, 2]))
+def test_random_matrices_match_reference_code(dims, seed, symmetric, favourSpeed):
+    """property: on any hex box with arbitrary coefficients the oracle's row operations equal the
+    reference's code bit for bit (any favourSpeed path)"""
+    import importlib as _il
+    meshmod = _il.import_module("rapidcfd-dev_b200.mesh")
+    from oracle import ldu_oracle as orc
+    m = meshmod.hex_mesh(*dims)
+    rng = np.random.default_rng(seed)
+    nF = m.nFaces
+    D = rng.uniform(1.0, 9.0, m.nCells) * rng.choice([-1.0, 1.0])
+    U = rng.standard_normal(nF)
+    L = None if symmetric else rng.standard_normal(nF)
+    a = orc.Addr(m.nCells, m.lower, m.upper)
+    M = orc.Matrix(a, D, U, L)
+    R = ref_ldu.RefMatrix(m.nCells, m.lower, m.upper, a.owner_start(), a.losort_start(), a.losort(), D, U, L)
+    x, b = rng.standard_normal(m.nCells), rng.standard_normal(m.nCells)
+    assert np.array_equal(R.op("amul", favourSpeed, x), M.amul(x))
+    assert np.array_equal(R.op("tmul", favourSpeed, x), M.tmul(x))
+    assert np.array_equal(R.op("residual", favourSpeed, x, b), M.residual(x, b))
+    assert np.array_equal(R.op("sumA", favourSpeed), M.sumA())
+    assert np.array_equal(R.op("H", 0, x), M.H(x))
+    if nF:
+        assert np.array_equal(R.op("faceH", 0, x), M.faceH(x))
+    fast = favourSpeed > 0
+    assert np.array_equal(R.ainv(x, fast, False), M.precondition("DIC", x, False))
+    assert np.array_equal(R.ainv(x, fast, True), M.precondition("DIC", x, True))
+    omega = float(rng.uniform(0.3, 1.0))
+    assert np.array_equal(R.jacobi(x, b, omega, fast), M.jacobi(x, b, 1, omega=omega))
