@@ -744,3 +744,120 @@ def decompose_poly_mesh(pm, cellToProc):
             sub.faceLabels = pl[labels].astype(np.int32)
         out.append((sub, cells, faceG))
     return out
+
+
+# ---------------------------------------------------------------------------
+# field files (0/p, 0/U, ...: volScalarField / volVectorField / surfaceScalarField)
+# ---------------------------------------------------------------------------
+_FIELD_ENTRY = re.compile(rb"(internalField|value)\s+(uniform|nonuniform)\s+")
+
+
+def read_field(path, nInternal=None):
+    """Read a FoamFile field: dict(cls, dimensions, internalField, boundaryField={patch: dict(type, value?, ...)}).
+    `uniform` values stay scalars / 3-vectors unless `nInternal` is given (then they are expanded);
+    `nonuniform List<scalar|vector>` is read in ascii or binary (`format binary;` in the header)."""
+    raw = _read_bytes(path)
+    hdr, i0 = _split_header(raw)
+    binary = hdr.lookupOrDefault("format", "ascii") == "binary"
+    cls = str(hdr.lookupOrDefault("class", ""))
+
+    def take_value(i):
+        """parse `uniform X;` or `nonuniform List<T> N(...);` starting at i; returns (value, end offset)"""
+        i = _skip_ws_comments(raw, i)
+        if raw.startswith(b"uniform", i):
+            j = raw.index(b";", i)
+            toks = tokenize(raw[i + 7:j].decode("latin-1"))
+            vals = [float(t) for t in toks if t not in ("(", ")")]
+            return (np.array(vals) if len(vals) > 1 else vals[0]), j + 1
+        if not raw.startswith(b"nonuniform", i):
+            raise ValueError(f"{path}: uniform/nonuniform expected")
+        i = _skip_ws_comments(raw, i + 10)
+        m = re.compile(rb"List<(\w+)>").match(raw, i)
+        if not m:
+            raise ValueError(f"{path}: List<...> expected")
+        kind = m.group(1).decode()
+        ncmp = {"scalar": 1, "vector": 3, "symmTensor": 6, "tensor": 9}[kind]
+        n, i = _read_count(raw, m.end())
+        if binary:
+            a, i = _binary_block(raw, i, n * ncmp, np.float64)
+        else:
+            i = _skip_ws_comments(raw, i)
+            depth, j = 0, i
+            while True:                       # matching ')' of the list
+                c = raw[j:j + 1]
+                if c == b"(":
+                    depth += 1
+                elif c == b")":
+                    depth -= 1
+                    if depth == 0:
+                        break
+                elif not c:
+                    raise ValueError(f"{path}: unterminated list")
+                j += 1
+            a = np.array(re.findall(r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eE][-+]?\d+)?", raw[i:j + 1].decode("latin-1")),
+                         dtype=np.float64)
+            if len(a) != n * ncmp:
+                _short(path, n * ncmp, len(a))
+            i = j + 1
+        i = raw.index(b";", i) + 1
+        return (a.reshape(n, ncmp) if ncmp > 1 else a), i
+
+    # cut the (possibly binary) values out, parse the rest as a dictionary
+    values, pieces, pos = [], [], i0
+    for m in _FIELD_ENTRY.finditer(raw, i0):
+        if m.start() < pos:
+            continue
+        v, end = take_value(m.start(2))
+        pieces.append(raw[pos:m.start(2)])
+        pieces.append(b"__value%d__;" % len(values))
+        values.append(v)
+        pos = end
+    pieces.append(raw[pos:])
+    d = parse_dict(b"".join(pieces).decode("latin-1"))
+
+    def resolve(x):
+        if isinstance(x, str) and x.startswith("__value") and x.endswith("__"):
+            return values[int(x[7:-2])]
+        return x
+    internal = resolve(d.lookup("internalField"))
+    if nInternal is not None and (np.isscalar(internal) or np.ndim(internal) == 1 and cls.startswith("volVector")):
+        internal = np.tile(np.atleast_1d(internal), (nInternal, 1)) if np.ndim(internal) == 1 else np.full(nInternal, internal)
+    bf = {}
+    for name, sub in d.subDict("boundaryField").entries.items():
+        bf[name] = {k: resolve(v) for k, v in sub.entries.items()}
+    return dict(cls=cls, dimensions=d.lookupOrDefault("dimensions", None), internalField=internal, boundaryField=bf)
+
+
+def write_field(path, cls, dimensions, internalField, boundaryField, binary=False, location="0"):
+    """Write a field file (the inverse of read_field for scalar / vector fields)."""
+    def fmt_value(v):
+        a = np.asarray(v, dtype=np.float64)
+        if a.ndim == 0:
+            return b"uniform %r" % float(a)
+        if a.ndim == 1 and cls.startswith(("volVector", "surfaceVector")) and a.shape == (3,):
+            return b"uniform (%r %r %r)" % tuple(map(float, a))
+        kind = b"vector" if a.ndim == 2 else b"scalar"
+        n = len(a)
+        if binary:
+            return b"nonuniform List<%s> %d(" % (kind, n) + a.tobytes() + b")"
+        if a.ndim == 2:
+            body = b"\n".join(b"(%r %r %r)" % tuple(map(float, r)) for r in a)
+        else:
+            body = b"\n".join(b"%r" % float(x) for x in a)
+        return b"nonuniform List<%s> %d\n(\n" % (kind, n) + body + b"\n)"
+    out = [_BANNER.encode(), ("FoamFile\n{\n    version     2.0;\n    format      %s;\n    class       %s;\n"
+                              "    location    \"%s\";\n    object      %s;\n}\n\n"
+                              % ("binary" if binary else "ascii", cls, location, os.path.basename(path))).encode(),
+           ("dimensions      [%s];\n\n" % " ".join(str(x) for x in dimensions)).encode(),
+           b"internalField   ", fmt_value(internalField), b";\n\nboundaryField\n{\n"]
+    for name, entries in boundaryField.items():
+        out.append(("    %s\n    {\n" % name).encode())
+        for k, v in entries.items():
+            if k == "value" or isinstance(v, (np.ndarray, float)):
+                out += [("        %-15s " % k).encode(), fmt_value(v), b";\n"]
+            else:
+                out.append(("        %-15s %s;\n" % (k, v)).encode())
+        out.append(b"    }\n")
+    out.append(b"}\n")
+    with open(path, "wb") as f:
+        f.write(b"".join(out))

@@ -453,3 +453,32 @@ def test_dictionary_roundtrip(d):
     ff = importlib.import_module("rapidcfd-dev_b200.foamfile")
     text = "/* header */\n" + _emit(d)
     assert ff.parse_dict(text).to_python() == d
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_field_files_roundtrip(ff, tmp_path, binary):
+    """0/p and 0/U as icoFoam's cavity case has them (uniform internal fields, fixedValue lid) and a
+    restart-style nonuniform pair, ascii and binary."""
+    rng = np.random.default_rng(0)
+    n = 12
+    p_bf = {"movingWall": {"type": "zeroGradient"}, "fixedWalls": {"type": "zeroGradient"}, "frontAndBack": {"type": "empty"}}
+    U_bf = {"movingWall": {"type": "fixedValue", "value": np.array([1.0, 0.0, 0.0])},
+            "fixedWalls": {"type": "fixedValue", "value": np.array([0.0, 0.0, 0.0])}, "frontAndBack": {"type": "empty"}}
+    ff.write_field(str(tmp_path / "p"), "volScalarField", [0, 2, -2, 0, 0, 0, 0], 0.0, p_bf, binary)
+    ff.write_field(str(tmp_path / "U"), "volVectorField", [0, 1, -1, 0, 0, 0, 0], np.zeros(3), U_bf, binary)
+    p = ff.read_field(str(tmp_path / "p"), nInternal=n)
+    U = ff.read_field(str(tmp_path / "U"), nInternal=n)
+    assert p["cls"] == "volScalarField" and p["dimensions"] == [0, 2, -2, 0, 0, 0, 0]
+    assert p["internalField"].shape == (n,) and not p["internalField"].any()
+    assert U["internalField"].shape == (n, 3) and U["boundaryField"]["movingWall"]["type"] == "fixedValue"
+    assert np.array_equal(U["boundaryField"]["movingWall"]["value"], [1.0, 0.0, 0.0])
+    assert p["boundaryField"]["frontAndBack"] == {"type": "empty"}
+    pv, Uv = rng.standard_normal(n), rng.standard_normal((n, 3))
+    lid = rng.standard_normal((4, 3))
+    U_bf["movingWall"]["value"] = lid
+    ff.write_field(str(tmp_path / "p1"), "volScalarField", [0, 2, -2, 0, 0, 0, 0], pv, p_bf, binary)
+    ff.write_field(str(tmp_path / "U1"), "volVectorField", [0, 1, -1, 0, 0, 0, 0], Uv, U_bf, binary)
+    p1, U1 = ff.read_field(str(tmp_path / "p1")), ff.read_field(str(tmp_path / "U1"))
+    assert np.array_equal(p1["internalField"], pv) and np.array_equal(U1["internalField"], Uv)
+    assert np.array_equal(U1["boundaryField"]["movingWall"]["value"], lid)
+    assert np.array_equal(U1["boundaryField"]["fixedWalls"]["value"], [0.0, 0.0, 0.0])
