@@ -37,18 +37,19 @@ def tokenize(text):
     return _TOKEN.findall(_strip_comments(text))
 
 
+_INT = re.compile(r"[-+]?\d+")
+_FLOAT = re.compile(r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eE][-+]?\d+)?")
+
+
 def _atom(tok):
     """word | number | quoted string (kept with its quotes removed, flagged by FoamString)"""
     if tok.startswith('"'):
         return FoamString(tok[1:-1])
-    try:
+    if _INT.fullmatch(tok):
         return int(tok)
-    except ValueError:
-        pass
-    try:
+    if _FLOAT.fullmatch(tok):      # digits required: `inf`, `nan`, `Infinity` stay words
         return float(tok)
-    except ValueError:
-        return tok
+    return tok
 
 
 class FoamString(str):
