@@ -18,14 +18,16 @@
  *     all sweep controls (GAMGSolverSolve.C, GAMGSolverScale.C), the pair agglomeration maps
  *     (pairGAMGAgglomerate.C), coarse addressing / face restrict / flip maps and combineLevels
  *     (GAMGAgglomerateLduAddressing.C), coarse-matrix assembly (the reference's restriction and
- *     agglomeration functors), the coarsest-level LU (scalarMatrices.C LUDecompose/LUBacksubstitute);
+ *     agglomeration functors), the coarsest-level LU (scalarMatrices.C LUDecompose/LUBacksubstitute),
+ *     the scalar face sums fvc::surfaceIntegrate / surfaceSum / gaussGrad::gradf (fvcSurfaceIntegrate.C,
+ *     gaussGrad.C);
  *   PINNED to rounding level (the reference's vector updates run unfused on the host, here they are
  *     the FMAs nvcc emits): PCG, PBiCG, PBiCGStab loops incl. iteration counts, names, loop limits
  *     (run-time selection and normFactor -- lduMatrixSolver.C -- bit for bit);
  *   UNPINNED (restated from the source, checked by analytic properties only): the exchange side of
  *     the coupled interfaces (processor send/receive, cyclic pairing) and their coarse-level
  *     construction, the convergence test (restated inside the shims too), the
- *     face-sum kernels' oracle.  Rows with more than three faces per side (coarse GAMG levels,
+ *     Laplacian / convection coefficient fills and the fvMatrix boundary folding.  Rows with more than three faces per side (coarse GAMG levels,
  *     polyhedral meshes) are summed in plain row order here, the reference unrolls three per side
  *     first: same terms, different association.
  * Analytic checks (dense-matrix SpMV, adjointness, CG exactness on tiny systems, eigenpairs of the

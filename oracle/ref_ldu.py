@@ -374,3 +374,41 @@ def ldu_addressing(nCells, lower, upper, patchStart=None, faceCells=None):
         out["patchSortCells"].append(psc[s:s + k].copy())
         out["patchSortStart"].append(np.append(pss[s:s + k], e - s))
     return out
+
+
+_LIB_FV = os.path.join(_HERE, "_ref", "libref_fv.so")
+_libfv = None
+
+
+def surface_integrate(nCells, lower, upper, ssf, bFaceCells, bssf, V, integrate=True):
+    """The reference's fvc::surfaceIntegrate(ivf, ssf) for a scalar surface field
+    (fvcSurfaceIntegrate.C:41-205): per cell, owner faces added, neighbour faces subtracted, then the
+    boundary faces (handed over as one patch, see harness_fv.cpp), then the division by the volumes.
+    integrate=False: fvc::surfaceSum (:261-352) -- all faces added, no division."""
+    global _libfv
+    if _libfv is None:
+        if not available() or not os.path.exists(_LIB_FV):
+            raise RuntimeError("oracle/_ref/libref_fv.so is not built (needs /root/reference)")
+        _libfv = C.CDLL(_LIB_FV)
+    l, u = _i(lower), _i(upper)
+    os_, ls, lo = ldu_arrays(nCells, l, u)
+    s, bs, v = _d(ssf), _d(bssf), _d(V)
+    bfc = _i(bFaceCells)
+    out = np.zeros(int(nCells))
+    _libfv.ref_surface_integrate(int(bool(integrate)), int(nCells), len(l), _p(l), _p(u), _p(_i(os_)), _p(_i(ls)), _p(_i(lo)), _p(s),
+                                 len(bfc), _p(bfc), _p(bs), _p(v), _p(out))
+    return out
+
+
+def gauss_gradf(nCells, lower, upper, Sf, ssf, bFaceCells, bSf, bssf, V):
+    """The reference's fv::gaussGrad<scalar>::gradf (gaussGrad.C:34-243): per cell the sum of Sf*ssf over the
+    owner faces, minus the neighbour faces, plus the boundary faces, divided by the volume.  Returns (nCells, 3)."""
+    surface_integrate(1, [], [], [], [], [], [1.0])  # loads the library
+    l, u = _i(lower), _i(upper)
+    os_, ls, lo = ldu_arrays(nCells, l, u)
+    A, s, bA, bs, v = _d(np.ravel(Sf)), _d(ssf), _d(np.ravel(bSf)), _d(bssf), _d(V)
+    bfc = _i(bFaceCells)
+    out = np.zeros(3 * int(nCells))
+    _libfv.ref_gauss_gradf(int(nCells), len(l), _p(l), _p(u), _p(_i(os_)), _p(_i(ls)), _p(_i(lo)), _p(A), _p(s),
+                           len(bfc), _p(bfc), _p(bA), _p(bs), _p(v), _p(out))
+    return out.reshape(-1, 3)

@@ -1,6 +1,6 @@
 """Generates tests/golden/ref_golden.npz -- fixtures produced by EXECUTING THE REFERENCE'S OWN SOURCE
 (oracle/_ref/libref_*.so: lduMatrixATmul.C, lduMatrixTemplates.C, AINVPreconditioner, JacobiSmoother,
-smoothSolver, PCG/PBiCG/PBiCGStab, pairGAMGAgglomerate.C, GAMGAgglomerateLduAddressing.C, the
+smoothSolver, PCG/PBiCG/PBiCGStab, fvcSurfaceIntegrate.C, gaussGrad.C, pairGAMGAgglomerate.C, GAMGAgglomerateLduAddressing.C, the
 agglomeration functors, GAMGSolverSolve/Scale -- compiled for the host, see oracle/ref_harness/).
 The oracle is NOT used here: inputs come from rapidcfd-dev_b200/mesh.py and the seeds below, outputs
 from oracle/ref_ldu.py only.  Needs /root/reference (to build oracle/_ref); the stored vectors let the
@@ -28,6 +28,7 @@ SOLVE_CASES = [  # (name, dims, kind, solver, preconditioner / smoother, control
 GAMG_CASES = [("gamgP", (16, 14, 12), "P", dict(tolerance=1e-8, maxIter=100)),
               ("gamgU", (16, 14, 12), "U", dict(tolerance=1e-8, maxIter=100)),
               ("gamgPpre", (12, 10, 8), "P", dict(tolerance=1e-8, maxIter=100, nPreSweeps=1, nFinestSweeps=1))]
+FV_CASES = [("fv", (9, 7, 5))]   # fvc::surfaceIntegrate, fvc::surfaceSum, gaussGrad<scalar>::gradf
 HIST_K = 12   # residual after k loop bodies, k = 1..HIST_K (one reference solve per k, tolerance 0)
 
 
@@ -42,8 +43,25 @@ def ref_matrix(ref, m, c):
     return ref.RefMatrix(m.nCells, m.lower, m.upper, os_, ls, lo, c["diag"], c["upper"], c["lower"]), (os_, ls, lo)
 
 
+def fv_inputs(meshmod, dims):
+    m = meshmod.hex_mesh(*dims)
+    rng = np.random.default_rng(11)
+    bfc = np.concatenate([p.faceCells for p in m.patches]).astype(np.int32)
+    Sf = m.Sf() + rng.uniform(-0.1, 0.1, (m.nFaces, 3))
+    bSf = np.concatenate([p.Sf for p in m.patches]) + rng.uniform(-0.1, 0.1, (len(bfc), 3))
+    return m, dict(bfc=bfc, Sf=Sf, bSf=bSf, V=m.volumes() * rng.uniform(0.9, 1.1, m.nCells),
+                   ssf=rng.uniform(-1, 1, m.nFaces), bssf=rng.uniform(-1, 1, len(bfc)))
+
+
 def generate(meshmod, ref):
     out = {}
+    for name, dims in FV_CASES:
+        m, d = fv_inputs(meshmod, dims)
+        out[f"{name}.integrate"] = ref.surface_integrate(m.nCells, m.lower, m.upper, d["ssf"], d["bfc"], d["bssf"], d["V"])
+        out[f"{name}.sum"] = ref.surface_integrate(m.nCells, m.lower, m.upper, d["ssf"], d["bfc"], d["bssf"], d["V"],
+                                                   integrate=False)
+        out[f"{name}.grad"] = ref.gauss_gradf(m.nCells, m.lower, m.upper, d["Sf"], d["ssf"], d["bfc"], d["bSf"],
+                                              d["bssf"], d["V"])
     for name, dims, kind in OPS_CASES:
         m, c = coefficients(meshmod, dims, kind)
         R, _ = ref_matrix(ref, m, c)

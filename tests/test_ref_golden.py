@@ -53,6 +53,17 @@ def test_oracle_matrix_ops_vs_reference_vectors(meshmod, orc, ref_golden, name, 
     assert np.array_equal(M.jacobi(x, b, 1), G("jacobi1"))
 
 
+@pytest.mark.parametrize("name,dims", mrg.FV_CASES)
+def test_oracle_fv_face_sums_vs_reference_vectors(meshmod, orc, ref_golden, name, dims):
+    m, d = mrg.fv_inputs(meshmod, dims)
+    a = orc.Addr(m.nCells, m.lower, m.upper)
+    G = lambda k: ref_golden[f"{name}.{k}"]
+    assert np.array_equal(orc.surface_integrate(a, d["ssf"], d["bfc"], d["bssf"], d["V"], 1), G("integrate"))
+    assert np.array_equal(orc.surface_integrate(a, d["ssf"], d["bfc"], d["bssf"], d["V"], 1, False, +1), G("sum"))
+    g = orc.gauss_grad(a, d["Sf"].ravel(), d["ssf"], d["bfc"], d["bSf"].ravel(), d["bssf"], d["V"], 1)
+    assert np.array_equal(np.asarray(g).reshape(-1, 3), G("grad"))
+
+
 @pytest.mark.parametrize("name,dims,kind,solver,pre,ctl", mrg.SOLVE_CASES)
 def test_oracle_solvers_vs_reference_vectors(meshmod, orc, ref_golden, name, dims, kind, solver, pre, ctl):
     m, c, a, M = _oracle(meshmod, orc, dims, kind)
@@ -154,6 +165,29 @@ def test_gpu_matrix_ops_vs_reference_vectors(gpu, meshmod, ref_golden, name, dim
         np.testing.assert_allclose(mat.precondition("DIC", xd, T).cpu().numpy(), ref, rtol=1e-13,
                                    atol=1e-13 * np.abs(ref).max())
     mat.close()
+    addr.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,dims", mrg.FV_CASES)
+def test_gpu_fv_face_sums_vs_reference_vectors(gpu, meshmod, ref_golden, name, dims):
+    capi, ctx, torch = gpu
+    if not hasattr(capi, "lib"):
+        pytest.skip("raw C-ABI calls: not covered by the dry-run stand-in")
+    m, d = mrg.fv_inputs(meshmod, dims)
+    addr = capi.mesh_to_device(ctx, m)
+    L, dp = capi.lib(), capi._dp
+    capi.check(L.b200ldu_fv_boundary_set(addr.h, len(d["bfc"]), d["bfc"].ctypes.data))
+    T = {k: torch.from_numpy(np.ascontiguousarray(v).ravel()).to(ctx.device) for k, v in d.items() if k != "bfc"}
+    G = lambda k: ref_golden[f"{name}.{k}"]
+    out = torch.empty(m.nCells, dtype=torch.float64, device=ctx.device)
+    for div, sign, key in ((1, -1, "integrate"), (0, 1, "sum")):
+        capi.check(L.b200ldu_fv_surface_integrate(addr.h, 1, dp(T["ssf"]), dp(T["bssf"]), dp(T["V"]), dp(out), div, sign))
+        assert np.array_equal(out.cpu().numpy(), G(key)), key
+    grad = torch.empty(m.nCells * 3, dtype=torch.float64, device=ctx.device)
+    capi.check(L.b200ldu_fv_gauss_grad(addr.h, 1, dp(T["Sf"]), dp(T["ssf"]), dp(T["bSf"]), dp(T["bssf"]), dp(T["V"]),
+                                       dp(grad)))
+    assert np.array_equal(grad.cpu().numpy().reshape(-1, 3), G("grad"))
     addr.close()
 
 
