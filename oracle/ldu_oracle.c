@@ -791,3 +791,6 @@ int orc_solve(const orc_matrix *m, const char *solver, const char *pre, const or
 /* accessors for tests */
 const int *orc_addr_lower(const orc_addr *a) { return a->l; }
 const int *orc_addr_upper(const orc_addr *a) { return a->u; }
+int orc_addr_npatches(const orc_addr *a) { return a->nPatches; }
+const int *orc_addr_patch_start(const orc_addr *a) { return a->patchStart; }
+const int *orc_addr_face_cells(const orc_addr *a) { return a->faceCells; }

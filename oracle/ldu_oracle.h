@@ -20,14 +20,15 @@
  *     (GAMGAgglomerateLduAddressing.C), coarse-matrix assembly (the reference's restriction and
  *     agglomeration functors), the coarsest-level LU (scalarMatrices.C LUDecompose/LUBacksubstitute),
  *     the scalar face sums fvc::surfaceIntegrate / surfaceSum / gaussGrad::gradf (fvcSurfaceIntegrate.C,
- *     gaussGrad.C);
+ *     gaussGrad.C), the coarse processor interfaces of a decomposed case and their coefficient sums
+ *     (GAMGAgglomerateLduAddressing.C interface branch, GAMGInterface.C, processorGAMGInterface.C);
  *   PINNED to rounding level (the reference's vector updates run unfused on the host, here they are
  *     the FMAs nvcc emits): PCG, PBiCG, PBiCGStab loops incl. iteration counts, names, loop limits
  *     (run-time selection and normFactor -- lduMatrixSolver.C -- bit for bit);
- *   UNPINNED (restated from the source, checked by analytic properties only): the exchange side of
- *     the coupled interfaces (processor send/receive, cyclic pairing) and their coarse-level
- *     construction, the convergence test (restated inside the shims too), the
- *     Laplacian / convection coefficient fills and the fvMatrix boundary folding.  Rows with more than three faces per side (coarse GAMG levels,
+ *   UNPINNED (restated from the source, checked by analytic properties only): the finest-level
+ *     exchange of the coupled interfaces (processor send/receive, cyclic pairing), the convergence
+ *     test (restated inside the shims too), the Laplacian / convection coefficient fills and the
+ *     fvMatrix boundary folding.  Rows with more than three faces per side (coarse GAMG levels,
  *     polyhedral meshes) are summed in plain row order here, the reference unrolls three per side
  *     first: same terms, different association.
  * Analytic checks (dense-matrix SpMV, adjointness, CG exactness on tiny systems, eigenpairs of the
@@ -107,6 +108,9 @@ const int *orc_addr_losort(const orc_addr *a);
 const int *orc_addr_losort_start(const orc_addr *a);
 const int *orc_addr_lower(const orc_addr *a);
 const int *orc_addr_upper(const orc_addr *a);
+int orc_addr_npatches(const orc_addr *a);
+const int *orc_addr_patch_start(const orc_addr *a); /* nPatches + 1 offsets into faceCells */
+const int *orc_addr_face_cells(const orc_addr *a);
 
 /* ---- matrix ---- */
 orc_matrix *orc_matrix_create(const orc_addr *a, const double *diag, const double *upper,
@@ -158,6 +162,10 @@ int orc_gamg_solve(const orc_matrix *m, orc_gamg *g, const char *smoother, const
                    double *psi, const double *source, const orc_comm *comm, orc_perf *perf, double *hist,
                    int histCap);
 int orc_gamg_npatchfaces(const orc_gamg *g, int lev); /* coupled-patch faces of coarse level lev */
+const int *orc_gamg_patch_face_restrict(const orc_gamg *g, int lev); /* fine patch face -> coarse patch face (flat) */
+/* GAMGInterface::agglomerateCoeffs over all patches of level lev (GAMGInterface.C:120-172): coarse[cpf] = sum of
+ * the fine coefficients mapped to it, in ascending fine patch-face order */
+void orc_gamg_agglomerate_patch_coeffs(const orc_gamg *g, int lev, const double *fine, double *coarse);
 
 /* ---- finite-volume face-sum loops (Appendix A.11) ---- */
 /* nComp = 1 (scalar) or 3 (vector); fields are AoS: x[c*nComp + k]. */

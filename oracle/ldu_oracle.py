@@ -108,6 +108,13 @@ def lib():
         L.orc_gamg_face_restrict_addr.argtypes = [C.c_void_p, C.c_int]
         L.orc_gamg_face_flip.restype = C.POINTER(C.c_ubyte)
         L.orc_gamg_face_flip.argtypes = [C.c_void_p, C.c_int]
+        L.orc_gamg_patch_face_restrict.restype = c_ip
+        L.orc_gamg_patch_face_restrict.argtypes = [C.c_void_p, C.c_int]
+        L.orc_gamg_agglomerate_patch_coeffs.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp]
+        L.orc_addr_npatches.argtypes = [C.c_void_p]
+        for nm in ("orc_addr_patch_start", "orc_addr_face_cells"):
+            getattr(L, nm).restype = c_ip
+            getattr(L, nm).argtypes = [C.c_void_p]
         L.orc_gamg_addr.restype = C.c_void_p
         L.orc_gamg_addr.argtypes = [C.c_void_p, C.c_int]
         L.orc_gamg_solve.restype = C.c_int
@@ -185,6 +192,19 @@ class Addr:
 
     def upper(self):
         return np.ctypeslib.as_array(lib().orc_addr_upper(self.h), (max(self.nFaces, 1),))[: self.nFaces].copy()
+
+    def patch_start(self):
+        nP = lib().orc_addr_npatches(self.h)
+        if nP == 0:
+            return np.zeros(0, np.int32)
+        return np.ctypeslib.as_array(lib().orc_addr_patch_start(self.h), (nP + 1,)).copy()
+
+    def face_cells(self):
+        ps = self.patch_start()
+        n = int(ps[-1]) if len(ps) else 0
+        if n == 0:
+            return np.zeros(0, np.int32)
+        return np.ctypeslib.as_array(lib().orc_addr_face_cells(self.h), (n,)).copy()
 
     def owner_start(self):
         return np.ctypeslib.as_array(lib().orc_addr_owner_start(self.h), (self.nCells + 1,)).copy()
@@ -373,6 +393,20 @@ class Gamg:
     def face_flip(self, lev):
         n = self.addr.nFaces if lev == 0 else self.nfaces(lev - 1)
         return np.ctypeslib.as_array(lib().orc_gamg_face_flip(self.h, lev), (max(n, 1),))[:n].copy()
+
+    def patch_face_restrict(self, lev):
+        """fine coupled-patch face (flat over the patches of level lev's fine side) -> coarse patch face (flat)"""
+        fine = self.addr if lev == 0 else self.level_addr(lev - 1)
+        ps = fine.patch_start()
+        n = int(ps[-1]) if len(ps) else 0
+        if n == 0:
+            return np.zeros(0, np.int32)
+        return np.ctypeslib.as_array(lib().orc_gamg_patch_face_restrict(self.h, lev), (n,)).copy()
+
+    def agglomerate_patch_coeffs(self, lev, fine):
+        out = np.zeros(max(self.npatchfaces(lev), 1))
+        lib().orc_gamg_agglomerate_patch_coeffs(self.h, lev, _d(f64(fine)), _d(out))
+        return out[: self.npatchfaces(lev)]
 
     def level_addr(self, lev):
         a = Addr(self.ncells(lev), None, None, _handle=lib().orc_gamg_addr(self.h, lev))

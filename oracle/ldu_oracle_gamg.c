@@ -1,8 +1,9 @@
 /*
  * ldu_oracle_gamg.c -- CPU restatement of the RapidCFD-dev GAMG solver (pair
  * agglomeration, coarse addressing, Galerkin-by-summation coarse matrices, V-cycle).
- * TEST INFRASTRUCTURE ONLY (see ldu_oracle.h: V-cycle, pair agglomeration, coarse addressing and
- * combineLevels are pinned to the reference's own code; coarse matrices / interfaces are not).
+ * TEST INFRASTRUCTURE ONLY (see ldu_oracle.h: V-cycle, pair agglomeration, coarse addressing,
+ * combineLevels, coarse matrices, coarse processor interfaces and the LU are pinned to the
+ * reference's own code, tests/test_reference_functors.py).
  *
  * Paths relative to /root/reference/src/OpenFOAM/matrices/lduMatrix/solvers/GAMG/
  * (abbreviated GAMG/).  Multi-rank: processor interfaces are agglomerated as in
@@ -366,6 +367,19 @@ const int *orc_gamg_restrict_addr(const orc_gamg *g, int lev) { return g->restri
 const int *orc_gamg_face_restrict_addr(const orc_gamg *g, int lev) { return g->faceRestrict[lev]; }
 const unsigned char *orc_gamg_face_flip(const orc_gamg *g, int lev) { return g->faceFlip[lev]; }
 const orc_addr *orc_gamg_addr(const orc_gamg *g, int lev) { return g->addr[lev]; }
+const int *orc_gamg_patch_face_restrict(const orc_gamg *g, int lev) { return g->patchFaceRestrict[lev]; }
+
+/* GAMGInterface::agglomerateCoeffs (GAMGInterface.C:120-172; segments of a stable sort: ascending fine index) */
+void orc_gamg_agglomerate_patch_coeffs(const orc_gamg *g, int lev, const double *fine, double *coarse)
+{
+    const orc_addr *ca = g->addr[lev];
+    int nCP = ca->nPatches ? ca->patchStart[ca->nPatches] : 0;
+    for (int i = 0; i < nCP; i++) coarse[i] = 0.0;
+    for (int i = 0; i < g->nFinePatchFaces[lev]; i++) {
+        int cpf = g->patchFaceRestrict[lev][i];
+        coarse[cpf] = coarse[cpf] + fine[i];
+    }
+}
 
 /* restrictField: GAMGAgglomerationTemplates.C:35-61, GAMGAgglomerationF.H:10-40.
  * Segments come from a stable sort, so each coarse value is the sum of its fine
@@ -427,10 +441,9 @@ static void agglomerate_matrix(const orc_gamg *g, int lev, const double *fd, con
     int nCP = ca->nPatches ? ca->patchStart[ca->nPatches] : 0;
     cm->bou = (double *)calloc((size_t)(nCP > 0 ? nCP : 1), sizeof(double));
     cm->intc = (double *)calloc((size_t)(nCP > 0 ? nCP : 1), sizeof(double));
-    for (int i = 0; i < g->nFinePatchFaces[lev]; i++) {
-        int cpf = g->patchFaceRestrict[lev][i];
-        cm->bou[cpf] = cm->bou[cpf] + fbou[i];
-        cm->intc[cpf] = cm->intc[cpf] + fint[i];
+    if (g->nFinePatchFaces[lev] > 0) {
+        orc_gamg_agglomerate_patch_coeffs(g, lev, fbou, cm->bou);
+        orc_gamg_agglomerate_patch_coeffs(g, lev, fint, cm->intc);
     }
     cm->m = orc_matrix_create(ca, cm->diag, cm->upper, cm->lower, nCP ? cm->bou : NULL, nCP ? cm->intc : NULL);
 }

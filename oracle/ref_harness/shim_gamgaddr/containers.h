@@ -44,6 +44,8 @@ namespace Foam
 typedef double scalar;
 typedef int label;
 
+struct Istream; // no streams in the harnesses: the Istream constructors of the reference compile and throw
+
 template <class T> class List
 {
 protected:
@@ -56,6 +58,12 @@ public:
     explicit List(label n) : v_((size_t)n) {}
     List(label n, const T &x) : v_((size_t)n, x) {}
     List(const T *p, label n) : v_(p, p + n) {}
+    explicit List(Istream &) { throw std::runtime_error("no streams in the harness"); }
+    template <class DL> void transfer(DL &dl) // List::transfer(DynamicList&): take the contents over
+    {
+        v_.assign(dl.begin(), dl.end());
+        dl.clear();
+    }
     label size() const { return (label)v_.size(); }
     void setSize(label n) { v_.resize((size_t)n); }
     T &operator[](label i) { return v_[(size_t)i]; }

@@ -412,3 +412,82 @@ def gauss_gradf(nCells, lower, upper, Sf, ssf, bFaceCells, bSf, bssf, V):
     _libfv.ref_gauss_gradf(int(nCells), len(l), _p(l), _p(u), _p(_i(os_)), _p(_i(ls)), _p(_i(lo)), _p(A), _p(s),
                            len(bfc), _p(bfc), _p(bA), _p(bs), _p(v), _p(out))
     return out.reshape(-1, 3)
+
+
+_LIB_GAMGIFACE = os.path.join(_HERE, "_ref", "libref_gamgiface.so")
+_libgi = None
+
+
+class InterfaceAgglomeration:
+    """The reference's multi-rank coarse-level construction (GAMGAgglomerateLduAddressing.C with its interface
+    branch, GAMGInterface.C, processorGAMGInterface.C): all ranks of a decomposed case in this process.
+    ranks: list of dicts(nCells, lower, upper, patchStart, faceCells, neighbRank)."""
+
+    def __init__(self, ranks):
+        global _libgi
+        if _libgi is None:
+            if not available() or not os.path.exists(_LIB_GAMGIFACE):
+                raise RuntimeError("oracle/_ref/libref_gamgiface.so is not built (needs /root/reference)")
+            _libgi = C.CDLL(_LIB_GAMGIFACE)
+        self.nRanks = len(ranks)
+        self.h = _libgi.ref_ia_create(self.nRanks)
+        self.fine = []          # per level, per rank: (nCells, nFaces, patch sizes) of the FINE side
+        lev0 = []
+        for r, d in enumerate(ranks):
+            l, u, ps, fc, nb = _i(d["lower"]), _i(d["upper"]), _i(d["patchStart"]), _i(d["faceCells"]), _i(d["neighbRank"])
+            _libgi.ref_ia_set_rank(self.h, r, int(d["nCells"]), len(l), _p(l), _p(u), len(ps) - 1, _p(ps), _p(fc), _p(nb))
+            lev0.append((int(d["nCells"]), len(l), np.diff(ps).astype(int)))
+        self.fine.append(lev0)
+
+    def agglomerate(self, level, maps, nCoarse):
+        """maps[r]: restrict map of rank r from level to level+1.  Returns per rank a dict with the coarse
+        addressing, the face restrict / flip maps, coarse patchStart / faceCells and the patch-face restrict map."""
+        for r in range(self.nRanks):
+            m = _i(maps[r])
+            _libgi.ref_ia_set_map(self.h, level, r, _p(m), len(m), int(nCoarse[r]))
+        if _libgi.ref_ia_agglomerate(self.h, level) != 0:
+            raise RuntimeError("the reference code raised a FatalError")
+        return self._collect(level, level)
+
+    def combine(self, level):
+        """combineLevels(level): folds level into level-1 on every rank; returns the new description of level-1."""
+        if _libgi.ref_ia_combine(self.h, level) != 0:
+            raise RuntimeError("the reference code raised a FatalError")
+        self.fine.pop()
+        return self._collect(level - 1, level - 1)
+
+    def _collect(self, level, fineLevel):
+        out, nxt = [], []
+        for r in range(self.nRanks):
+            nFineCells, nFineFaces, finePatch = self.fine[fineLevel][r]
+            sz = np.zeros(3 + len(finePatch) + 1, np.int32)
+            _libgi.ref_ia_sizes(self.h, level, r, _p(sz))
+            nC, nCF, nP = int(sz[0]), int(sz[1]), int(sz[2])
+            cps = np.concatenate([[0], np.cumsum(sz[3:3 + nP])]).astype(np.int32)
+            own, nei = np.zeros(max(nCF, 1), np.int32), np.zeros(max(nCF, 1), np.int32)
+            fr, fl = np.zeros(max(nFineFaces, 1), np.int32), np.zeros(max(nFineFaces, 1), np.uint8)
+            cfc = np.zeros(max(int(cps[-1]), 1), np.int32)
+            pfr = np.zeros(max(int(finePatch.sum()), 1), np.int32)
+            _libgi.ref_ia_get(self.h, level, r, _p(own), _p(nei), _p(fr), fl.ctypes.data_as(C.c_void_p), _p(cfc), _p(pfr))
+            out.append(dict(nCells=nC, lower=own[:nCF], upper=nei[:nCF], faceRestrict=fr[:nFineFaces],
+                            faceFlip=fl[:nFineFaces], patchStart=cps, faceCells=cfc[:int(cps[-1])],
+                            patchFaceRestrict=pfr[:int(finePatch.sum())], finePatchSizes=finePatch))
+            nxt.append((nC, nCF, np.diff(cps).astype(int)))
+        if len(self.fine) == fineLevel + 1:
+            self.fine.append(nxt)
+        else:
+            self.fine[fineLevel + 1] = nxt
+        return out
+
+    def agglomerate_coeffs(self, level, r, patch, fine):
+        f = _d(fine)
+        out = np.zeros(max(len(f), 1))
+        n = _libgi.ref_ia_coeffs(self.h, level, r, int(patch), _p(f), len(f), _p(out))
+        if n < 0:
+            raise RuntimeError("the reference code raised a FatalError")
+        return out[:n]
+
+    def __del__(self):
+        if _libgi is not None and getattr(self, "h", None) is not None:
+            _libgi.ref_ia_destroy(self.h)
+            self.h = None

@@ -464,6 +464,94 @@ def test_fv_face_sums_match_reference_code(meshmod, orc, dims):
     ref = ref_ldu.gauss_gradf(m.nCells, m.lower, m.upper, Sf, ssf, bfc, bSf, bssf, V)
     np.testing.assert_array_equal(got, ref)
 
+
+def _oracle_rank_hierarchies(meshmod, orc, n, nR, mergeLevels, dims=None):
+    import dist_helpers as dh
+    ex = dh.ThreadExchange(nR)
+
+    def rank_fn(r):
+        m, c = dh.local_case(meshmod, n, nR, r, "P", dims=dims)
+        a, M = dh.oracle_matrix(orc, m, c)
+        comm = ex.comm(orc, r, m, n ** 3)
+        g = orc.Gamg(a, meshmod.face_area_pair_weights(m), 6, mergeLevels=mergeLevels, comm=comm)
+        levels = []
+        for k in range(g.nLevels):
+            ca = g.level_addr(k)
+            levels.append(dict(restrict=g.restrict_addr(k), nCells=g.ncells(k), lower=ca.lower(), upper=ca.upper(),
+                               faceRestrict=g.face_restrict_addr(k), faceFlip=g.face_flip(k),
+                               patchStart=ca.patch_start(), faceCells=ca.face_cells(),
+                               patchFaceRestrict=g.patch_face_restrict(k)))
+        ps, fc = m.patch_start_facecells()
+        fine = dict(nCells=m.nCells, lower=m.lower, upper=m.upper, patchStart=ps, faceCells=fc,
+                    neighbRank=[p.neighbRank for p in m.coupled_patches()])
+        rng = np.random.default_rng(100 + r)
+        coeffs = [rng.uniform(-1, 1, int(ps[-1]))]
+        for k in range(g.nLevels):
+            coeffs.append(g.agglomerate_patch_coeffs(k, coeffs[-1]))
+        return fine, levels, coeffs
+    return dh.run_threads(nR, rank_fn)
+
+
+@pytest.mark.parametrize("nR,dims", [(2, None), (4, None), (8, None), (4, (10, 6, 5))])
+def test_coarse_interfaces_match_reference_code(meshmod, orc, nR, dims):
+    """Row a14 (coarse-level side): the oracle's processor-interface agglomeration -- coarse patch faces as unique
+    (master cell, slave cell) pairs in order of appearance, identical on both sides, the patch-face restrict map,
+    the coefficient sums -- against the reference's GAMGAgglomerateLduAddressing.C (interface branch),
+    GAMGInterface.C and processorGAMGInterface.C, all ranks of the decomposition in one process."""
+    res = _oracle_rank_hierarchies(meshmod, orc, 8, nR, 1, dims)
+    nLev = min(len(r[1]) for r in res)
+    assert nLev >= 2
+    ia = ref_ldu.InterfaceAgglomeration([r[0] for r in res])
+    for k in range(nLev):
+        got = ia.agglomerate(k, [r[1][k]["restrict"] for r in res], [r[1][k]["nCells"] for r in res])
+        for r in range(nR):
+            o, g = res[r][1][k], got[r]
+            assert g["nCells"] == o["nCells"]
+            for key in ("lower", "upper", "faceRestrict", "patchStart", "faceCells"):
+                assert np.array_equal(g[key], o[key]), (k, r, key)
+            inter = o["faceRestrict"] >= 0           # the flip of a face that collapses into a cell is never read
+            assert np.array_equal(g["faceFlip"][inter] != 0, o["faceFlip"][inter] != 0)
+            # the reference numbers coarse patch faces per patch, the oracle over all patches of the rank
+            fineStart = np.concatenate([[0], np.cumsum(g["finePatchSizes"])])
+            flat = np.concatenate([g["patchFaceRestrict"][fineStart[p]:fineStart[p + 1]] + g["patchStart"][p]
+                                   for p in range(len(g["finePatchSizes"]))]) if len(g["finePatchSizes"]) else []
+            assert np.array_equal(flat, o["patchFaceRestrict"]), (k, r)
+            # GAMGInterface::agglomerateCoeffs, patch by patch, bit for bit
+            fine, coarse = res[r][2][k], res[r][2][k + 1]
+            for p in range(len(g["finePatchSizes"])):
+                ref = ia.agglomerate_coeffs(k, r, p, fine[fineStart[p]:fineStart[p + 1]])
+                assert np.array_equal(ref, coarse[g["patchStart"][p]:g["patchStart"][p + 1]]), (k, r, p)
+    # both sides of every coarse interface enumerate the same faces: sizes agree pairwise on every level
+    for k in range(nLev):
+        for r in range(nR):
+            nbrs = res[r][0]["neighbRank"]
+            for p, nb in enumerate(nbrs):
+                q = res[nb][0]["neighbRank"].index(r)
+                mine, theirs = res[r][1][k]["patchStart"], res[nb][1][k]["patchStart"]
+                assert mine[p + 1] - mine[p] == theirs[q + 1] - theirs[q]
+
+
+def test_merged_coarse_interfaces_match_reference_code(meshmod, orc):
+    """mergeLevels 2 over processor interfaces: combineLevels (GAMGAgglomerateLduAddressing.C:606-765) composes
+    the patch-face maps and GAMGInterface::combine the interfaces."""
+    nR = 2
+    steps = _oracle_rank_hierarchies(meshmod, orc, 8, nR, 1)
+    merged = _oracle_rank_hierarchies(meshmod, orc, 8, nR, 2)
+    ia = ref_ldu.InterfaceAgglomeration([r[0] for r in steps])
+    for k in (0, 1):
+        ia.agglomerate(k, [r[1][k]["restrict"] for r in steps], [r[1][k]["nCells"] for r in steps])
+    got = ia.combine(1)
+    for r in range(nR):
+        o, g = merged[r][1][0], got[r]
+        assert g["nCells"] == o["nCells"]
+        for key in ("lower", "upper", "faceRestrict", "patchStart"):
+            assert np.array_equal(g[key], o[key]), (r, key)
+        fineStart = np.concatenate([[0], np.cumsum(g["finePatchSizes"])])
+        flat = np.concatenate([g["patchFaceRestrict"][fineStart[p]:fineStart[p + 1]] + g["patchStart"][p]
+                               for p in range(len(g["finePatchSizes"]))])
+        assert np.array_equal(flat, o["patchFaceRestrict"])
+        assert np.array_equal(g["faceCells"], o["faceCells"])
+
 from hypothesis import given, settings, strategies as st  # noqa: E402
 
 
