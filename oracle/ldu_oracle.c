@@ -158,6 +158,15 @@ double *orc_halo_exchange(const orc_addr *a, const double *psi, const orc_comm *
     return recv;
 }
 
+/* coupledFvPatchField::patchNeighbourField for every coupled patch face (tests, fvMatrix glue) */
+void orc_patch_neighbour_field(const orc_addr *a, const double *psi, const orc_comm *comm, double *out)
+{
+    int tot = a->nPatches ? a->patchStart[a->nPatches] : 0;
+    double *pnf = orc_halo_exchange(a, psi, comm);
+    for (int i = 0; i < tot; i++) out[i] = pnf[i];
+    free(pnf);
+}
+
 /* result[faceCell] -= coeff*pnf (negate=false) or += (negate=true):
  * lduAddressingFunctors.H:237-262, coupledFvPatchField.C:221-257. The product is
  * rounded, its sign flipped, then added. */

@@ -112,6 +112,9 @@ int orc_addr_npatches(const orc_addr *a);
 const int *orc_addr_patch_start(const orc_addr *a); /* nPatches + 1 offsets into faceCells */
 const int *orc_addr_face_cells(const orc_addr *a);
 
+/* psi of the cell across every coupled patch face (processor: halo exchange; cyclic: partner patch) */
+void orc_patch_neighbour_field(const orc_addr *a, const double *psi, const orc_comm *comm, double *out);
+
 /* ---- matrix ---- */
 orc_matrix *orc_matrix_create(const orc_addr *a, const double *diag, const double *upper,
                               const double *lower /* NULL => symmetric */,

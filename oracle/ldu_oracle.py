@@ -115,6 +115,7 @@ def lib():
         for nm in ("orc_addr_patch_start", "orc_addr_face_cells"):
             getattr(L, nm).restype = c_ip
             getattr(L, nm).argtypes = [C.c_void_p]
+        L.orc_patch_neighbour_field.argtypes = [C.c_void_p, c_dp, C.c_void_p, c_dp]
         L.orc_gamg_addr.restype = C.c_void_p
         L.orc_gamg_addr.argtypes = [C.c_void_p, C.c_int]
         L.orc_gamg_solve.restype = C.c_int
@@ -205,6 +206,15 @@ class Addr:
         if n == 0:
             return np.zeros(0, np.int32)
         return np.ctypeslib.as_array(lib().orc_addr_face_cells(self.h), (n,)).copy()
+
+    def patch_neighbour_field(self, psi, comm=None):
+        """psi of the cell across every coupled patch face, flat over the patches"""
+        ps = self.patch_start()
+        n = int(ps[-1]) if len(ps) else 0
+        out = np.zeros(max(n, 1))
+        if n:
+            lib().orc_patch_neighbour_field(self.h, _d(f64(psi)), _commp(comm), _d(out))
+        return out[:n]
 
     def owner_start(self):
         return np.ctypeslib.as_array(lib().orc_addr_owner_start(self.h), (self.nCells + 1,)).copy()
