@@ -211,6 +211,51 @@ int b200ldu_fv_add_boundary_diag(b200ldu_addr *a, const double *internalCoeffs_d
 int b200ldu_fv_add_boundary_source(b200ldu_addr *a, const double *boundaryCoeffs_d,
                                    double *source_d);
 
+/* ---- fvMatrix glue around the solvers (FV/fvMatrices/fvMatrix/fvMatrix.C,
+ * fvScalarMatrix/fvScalarMatrix.C, fvMatrixSolve.C).  The matrix handle supplies diag / upper / lower and, for
+ * the coupled patches of its addressing, interfaceIntCoeffs / interfaceBouCoeffs (one scalar per face, used for
+ * every component) as given to the last b200ldu_matrix_set.  The non-coupled boundary faces are the flat list of
+ * b200ldu_fv_boundary_set (patch order) with internalCoeffs / boundaryCoeffs [nBFaces*nComp]; nComp is 1 or 3,
+ * components interleaved.  pnf_d = patchNeighbourField of the coupled patch faces [nCoupledFaces*nComp], which
+ * the reference asks of the boundary condition (coupledFvPatchField.H); may be NULL without coupled patches.
+ *   add_boundary_diag    diagOut = diagIn + internalCoeffs.component(cmpt)   (fvMatrix.C:209-226); cmpt = -1:
+ *                        cmptAv(internalCoeffs) (addCmptAvBoundaryDiag :230-243); diagIn NULL = zero; in place ok
+ *   add_boundary_source  sourceOut = sourceIn + boundaryCoeffs [+ interfaceBouCoeffs*pnf when pnf_d != NULL]
+ *                        (:290-348, `couples` = pnf_d != NULL)
+ *   A                    (diag + cmptAv boundary diagonal)/V                  (:1375-1430)
+ *   H                    (lduMatrix::H(psi) + source + boundary source)/V     (:1458-1508, fvScalarMatrix.C:252-283;
+ *                        like the reference, without the boundary-diagonal term of stock OpenFOAM)
+ *   flux                 internal faces upper*psi[nei] - lower*psi[own]; boundary faces internalCoeffs*psi[cell] -
+ *                        boundaryCoeffs (coupled: - interfaceBouCoeffs*pnf)    (:1591-1660)
+ *   residual             scalar fields: fvScalarMatrix.C:195-240 as written (coupled neighbour term counted by both
+ *                        lduMatrix::residual and addBoundarySource)
+ *   relax                in place on diag_d / source_d                         (:1088-1345)
+ *   set_reference        source[celli] += diag[celli]*value; diag[celli] *= 2; celli < 0: no-op   (:965-983)
+ *   solve                solveSegregated: scalar fvScalarMatrix.C:142-192, vector component loop
+ *                        fvMatrixSolve.C:104-226; perf[nComp]; the matrix is re-pointed at a folded diagonal for
+ *                        the solve and back at the caller's arrays afterwards (saveDiag) */
+int b200ldu_fvm_add_boundary_diag(b200ldu_matrix *m, int nComp, int cmpt, const double *internalCoeffs_d,
+                                  const double *diagIn_d, double *diagOut_d);
+int b200ldu_fvm_add_boundary_source(b200ldu_matrix *m, int nComp, const double *boundaryCoeffs_d,
+                                    const double *pnf_d, const double *sourceIn_d, double *sourceOut_d);
+int b200ldu_fvm_A(b200ldu_matrix *m, int nComp, const double *internalCoeffs_d, const double *V_d, double *A_d);
+int b200ldu_fvm_H(b200ldu_matrix *m, int nComp, const double *psi_d, const double *source_d,
+                  const double *boundaryCoeffs_d, const double *pnf_d, const double *V_d, double *H_d);
+int b200ldu_fvm_flux(b200ldu_matrix *m, int nComp, const double *psi_d, const double *internalCoeffs_d,
+                     const double *boundaryCoeffs_d, const double *pnf_d, double *flux_d, double *boundaryFlux_d,
+                     double *coupledFlux_d);
+int b200ldu_fvm_residual(b200ldu_matrix *m, const double *psi_d, const double *source_d,
+                         const double *internalCoeffs_d, const double *boundaryCoeffs_d, const double *pnf_d,
+                         double *residual_d);
+int b200ldu_fvm_relax(b200ldu_matrix *m, int nComp, double alpha, const double *psi_d,
+                      const double *internalCoeffs_d, double *diag_d, double *source_d);
+int b200ldu_fvm_set_reference(b200ldu_matrix *m, int celli, int nComp, const double *value_h, double *diag_d,
+                              double *source_d);
+int b200ldu_fvm_solve(b200ldu_matrix *m, int nComp, const char *solver, const char *precondOrSmoother,
+                      const b200ldu_controls *controls, b200ldu_gamg *gamg, double *psi_d, const double *source_d,
+                      const double *internalCoeffs_d, const double *boundaryCoeffs_d, const double *pnf_d,
+                      b200ldu_perf *perf);
+
 /* ---- structural self-check of the banded layout (host only, no GPU, no arithmetic);
  * used by the CPU test-suite.  what: 0 perm 1 iperm 2 sliceStart(int64) 3 sliceW(u16)
  * 4 sliceWL(u16) 5 col(u16) 6 code(int32) 7 haloStart 8 haloIdx 9 dims{nPad,nBands,bandRows,

@@ -63,6 +63,9 @@ EXPORTS = [
     "b200ldu_fv_laplacian_fill", "b200ldu_fv_convection_fill", "b200ldu_fv_interpolate_linear",
     "b200ldu_fv_add_boundary_diag", "b200ldu_fv_add_boundary_source", "b200ldu_fv_grad_linear",
     "b200ldu_fv_flux_linear",
+    "b200ldu_fvm_add_boundary_diag", "b200ldu_fvm_add_boundary_source", "b200ldu_fvm_A", "b200ldu_fvm_H",
+    "b200ldu_fvm_flux", "b200ldu_fvm_residual", "b200ldu_fvm_relax", "b200ldu_fvm_set_reference",
+    "b200ldu_fvm_solve",
 ]
 
 _lib = None
@@ -128,6 +131,16 @@ def lib():
     L.b200ldu_fv_flux_linear.argtypes = [vp, vp, vp, vp, vp]
     L.b200ldu_fv_add_boundary_diag.argtypes = [vp, vp, vp]
     L.b200ldu_fv_add_boundary_source.argtypes = [vp, vp, vp]
+    L.b200ldu_fvm_add_boundary_diag.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    L.b200ldu_fvm_add_boundary_source.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    L.b200ldu_fvm_A.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.b200ldu_fvm_H.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
+    L.b200ldu_fvm_flux.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+    L.b200ldu_fvm_residual.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.b200ldu_fvm_relax.argtypes = [vp, C.c_int, C.c_double, vp, vp, vp, vp]
+    L.b200ldu_fvm_set_reference.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    L.b200ldu_fvm_solve.argtypes = [vp, C.c_int, C.c_char_p, C.c_char_p, C.POINTER(Controls), vp, vp, vp, vp, vp, vp,
+                                    C.POINTER(Perf)]
     _lib = L
     return L
 
@@ -340,6 +353,76 @@ class LduMatrix:
             self.h = vp()
 
 
+class FvMatrix:
+    """fvMatrix<Type> around an LduMatrix (FV/fvMatrices/fvMatrix/fvMatrix.H), with
+    the reference's member names.  Type = scalar (nComp 1) or vector (nComp 3); fields are device tensors with
+    the components interleaved.  The non-coupled boundary faces are the flat list given to
+    b200ldu_fv_boundary_set; internalCoeffs / boundaryCoeffs hold nBFaces*nComp values.  Coupled patches take their
+    coefficients from the LduMatrix (set(..., bouCoeffs, intCoeffs)) and their patchNeighbourField from `pnf`."""
+
+    def __init__(self, matrix, nComp, diag, source, psi, V, internalCoeffs=None, boundaryCoeffs=None):
+        self.m, self.nc = matrix, int(nComp)
+        self.diag, self.source, self.psi, self.V = diag, source, psi, V
+        self.ic, self.bc = internalCoeffs, boundaryCoeffs
+
+    def _new(self, n):
+        import torch
+        return torch.empty(n, dtype=torch.float64, device=self.psi.device)
+
+    def addBoundaryDiag(self, diag, cmpt):
+        check(lib().b200ldu_fvm_add_boundary_diag(self.m.h, self.nc, cmpt, _dp(self.ic), _dp(diag), _dp(diag)))
+
+    def addCmptAvBoundaryDiag(self, diag):
+        check(lib().b200ldu_fvm_add_boundary_diag(self.m.h, self.nc, -1, _dp(self.ic), _dp(diag), _dp(diag)))
+
+    def addBoundarySource(self, source, pnf=None):
+        check(lib().b200ldu_fvm_add_boundary_source(self.m.h, self.nc, _dp(self.bc), _dp(pnf), _dp(source), _dp(source)))
+
+    def A(self):
+        out = self._new(self.m.addr.nCells)
+        check(lib().b200ldu_fvm_A(self.m.h, self.nc, _dp(self.ic), _dp(self.V), _dp(out)))
+        return out
+
+    def H(self, pnf=None):
+        out = self._new(self.m.addr.nCells * self.nc)
+        check(lib().b200ldu_fvm_H(self.m.h, self.nc, _dp(self.psi), _dp(self.source), _dp(self.bc), _dp(pnf),
+                                  _dp(self.V), _dp(out)))
+        return out
+
+    def flux(self, nBFaces, nCoupledFaces=0, pnf=None):
+        """(internal faces, non-coupled boundary faces, coupled faces), each with nComp values per face"""
+        f = self._new(max(self.m.addr.nFaces * self.nc, 1))
+        b = self._new(max(nBFaces * self.nc, 1))
+        c = self._new(max(nCoupledFaces * self.nc, 1))
+        check(lib().b200ldu_fvm_flux(self.m.h, self.nc, _dp(self.psi), _dp(self.ic), _dp(self.bc), _dp(pnf), _dp(f),
+                                     _dp(b), _dp(c)))
+        return f[: self.m.addr.nFaces * self.nc], b[: nBFaces * self.nc], c[: nCoupledFaces * self.nc]
+
+    def residual(self, pnf=None):
+        out = self._new(self.m.addr.nCells)
+        check(lib().b200ldu_fvm_residual(self.m.h, _dp(self.psi), _dp(self.source), _dp(self.ic), _dp(self.bc),
+                                         _dp(pnf), _dp(out)))
+        return out
+
+    def relax(self, alpha):
+        """in place on diag and source; the LduMatrix has to be set() again before it is used"""
+        check(lib().b200ldu_fvm_relax(self.m.h, self.nc, float(alpha), _dp(self.psi), _dp(self.ic), _dp(self.diag),
+                                      _dp(self.source)))
+
+    def setReference(self, celli, value):
+        v = np.ascontiguousarray(np.atleast_1d(np.asarray(value, np.float64)))
+        check(lib().b200ldu_fvm_set_reference(self.m.h, int(celli), self.nc, _hp(v), _dp(self.diag), _dp(self.source)))
+
+    def solve(self, solver, pre, gamg=None, pnf=None, **ctl):
+        """solveSegregated: psi updated in place; returns the list of Perf, one per component"""
+        c = controls(**ctl)
+        perfs = (Perf * self.nc)()
+        check(lib().b200ldu_fvm_solve(self.m.h, self.nc, solver.encode(), (pre or "").encode(), C.byref(c),
+                                      gamg.h if gamg is not None else None, _dp(self.psi), _dp(self.source),
+                                      _dp(self.ic), _dp(self.bc), _dp(pnf), perfs))
+        return list(perfs)
+
+
 class GamgAgglomeration:
     def __init__(self, addr, faceWeights, nCellsInCoarsestLevel=10, mergeLevels=1, forward=1):
         self.addr = addr
@@ -369,6 +452,12 @@ class GamgAgglomeration:
         if self.h:
             lib().b200ldu_gamg_destroy(self.h)
             self.h = vp()
+
+
+def fv_boundary_set(addr, bFaceCells):
+    """the non-coupled boundary faces (all patches, patch order) of the FV face sums and the fvMatrix glue"""
+    bfc = _np_i32(bFaceCells)
+    check(lib().b200ldu_fv_boundary_set(addr.h, len(bfc), _hp(bfc)))
 
 
 def mesh_to_device(ctx, mesh, with_centres=True):

@@ -1,0 +1,577 @@
+// fvmatrix.cu -- the fvMatrix glue around the linear solvers, caller-order
+// fields.  Reference (FV/ = src/finiteVolume/): addBoundaryDiag / addCmptAvBoundaryDiag / addBoundarySource
+// FV/fvMatrices/fvMatrix/fvMatrix.C:209-348; setReference :965-983; relax :1088-1345; D / A :1375-1455;
+// H :1458-1508 (scalar: fvScalarMatrix.C:252-283); flux :1591-1660; residual fvScalarMatrix.C:195-240;
+// solveSegregated fvScalarMatrix.C:142-192 (scalar), fvMatrixSolve.C:104-226 (component loop).
+//
+// Boundary model (same as oracle/fvm_oracle.py): the non-coupled boundary faces of all patches are the flat list
+// given to b200ldu_fv_boundary_set (patch order), with internalCoeffs / boundaryCoeffs [nBFaces*nComp]; the coupled
+// patches are those of the addressing and their coefficients the interfaceIntCoeffs / interfaceBouCoeffs of the
+// last b200ldu_matrix_set (one scalar per face, used for every component).  Where the reference asks a coupled
+// patch for patchNeighbourField() the caller passes it (pnf [nCoupledFaces*nComp]).
+//
+// The reference runs one small kernel per patch and operation; here a cell walks its boundary faces (ascending,
+// non-coupled list first, then the coupled patches -- mesh order) inside ONE kernel per operation, and the
+// element-wise field algebra around it (the /V, the +source, the max / divide / subtract of relax) is fused
+// into the same pass.  Products are rounded separately and summed in the reference's order, so the results
+// are bit-comparable with the oracle.
+#include <algorithm>
+
+#include "internal.h"
+
+namespace
+{
+struct BoundaryLists { // per-cell CSR over the non-coupled boundary faces and over the coupled patch faces
+    const int *bStart, *bFaces, *cStart, *cFaces;
+};
+
+int coupled_lists(b200ldu_addr *a)
+{
+    if (a->d_cCellStart || a->nPatches == 0) return B200LDU_OK;
+    const int tot = a->patchStart.empty() ? 0 : a->patchStart[a->nPatches];
+    if (tot == 0) return B200LDU_OK;
+    std::vector<int> start((size_t)a->nCells + 1, 0), faces((size_t)tot);
+    for (int i = 0; i < tot; i++) start[a->faceCells[i] + 1]++;
+    for (int c = 0; c < a->nCells; c++) start[c + 1] += start[c];
+    std::vector<int> cur(start.begin(), start.end() - 1);
+    for (int i = 0; i < tot; i++) faces[cur[a->faceCells[i]]++] = i;
+    TRY(dev_upload(&a->d_cCellStart, start));
+    TRY(dev_upload(&a->d_cCellFaces, faces));
+    TRY(dev_upload(&a->d_cFaceCells, a->faceCells));
+    a->nCFaces = tot;
+    return B200LDU_OK;
+}
+
+int lists(b200ldu_addr *a, BoundaryLists *L)
+{
+    TRY(coupled_lists(a));
+    L->bStart = a->nBFaces ? a->d_bCellStart : nullptr;
+    L->bFaces = a->d_bCellFaces;
+    L->cStart = a->nCFaces ? a->d_cCellStart : nullptr;
+    L->cFaces = a->d_cCellFaces;
+    return B200LDU_OK;
+}
+
+int scratch(b200ldu_addr *a, int slot, size_t doubles, double **out)
+{
+    if (a->fvmScratchLen[slot] < doubles) {
+        if (a->d_fvmScratch[slot]) CUDA_TRY(cudaFree(a->d_fvmScratch[slot]));
+        a->d_fvmScratch[slot] = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&a->d_fvmScratch[slot], sizeof(double) * std::max<size_t>(doubles, 1)));
+        a->fvmScratchLen[slot] = doubles;
+    }
+    *out = a->d_fvmScratch[slot];
+    return B200LDU_OK;
+}
+
+__device__ __forceinline__ double cmpt_av(const double *v, int nc) // VectorSpaceI.H:428-447: ((x + y) + z)/3
+{
+    if (nc == 1) return v[0];
+    double s = v[0];
+    for (int k = 1; k < nc; k++) s = __dadd_rn(s, v[k]);
+    return __ddiv_rn(s, (double)nc);
+}
+
+// out[c] = in[c] + sum_b internalCoeffs(bf)[cmpt | average] + sum_coupled interfaceIntCoeffs(pf)
+__global__ void boundary_diag_kernel(int nCells, BoundaryLists L, const double *__restrict__ ic, int nc, int cmpt,
+                                     const double *__restrict__ couInt, const double *in, double *out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    double acc = in ? in[c] : 0.0;
+    if (L.bStart)
+        for (int j = L.bStart[c]; j < L.bStart[c + 1]; j++) {
+            const double *v = ic + (size_t)L.bFaces[j] * nc;
+            acc = __dadd_rn(acc, cmpt >= 0 ? v[cmpt] : cmpt_av(v, nc));
+        }
+    if (L.cStart)
+        for (int j = L.cStart[c]; j < L.cStart[c + 1]; j++) acc = __dadd_rn(acc, couInt[L.cFaces[j]]);
+    out[c] = acc;
+}
+
+// out[c][k] = in[c][k] + sum_b boundaryCoeffs(bf)[k] + (pnf ? sum_coupled interfaceBouCoeffs(pf)*pnf(pf)[k])
+template <int NC>
+__global__ void boundary_source_kernel(int nCells, BoundaryLists L, const double *__restrict__ bc,
+                                       const double *__restrict__ couBou, const double *__restrict__ pnf,
+                                       const double *in, double *out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    double acc[NC];
+#pragma unroll
+    for (int k = 0; k < NC; k++) acc[k] = in[(size_t)c * NC + k];
+    if (L.bStart)
+        for (int j = L.bStart[c]; j < L.bStart[c + 1]; j++) {
+            const int bf = L.bFaces[j];
+#pragma unroll
+            for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], bc[(size_t)bf * NC + k]);
+        }
+    if (L.cStart && pnf)
+        for (int j = L.cStart[c]; j < L.cStart[c + 1]; j++) {
+            const int pf = L.cFaces[j];
+            const double b = couBou[pf];
+#pragma unroll
+            for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], __dmul_rn(b, pnf[(size_t)pf * NC + k]));
+        }
+#pragma unroll
+    for (int k = 0; k < NC; k++) out[(size_t)c * NC + k] = acc[k];
+}
+
+// component k of an interleaved field, minus the coupled products again when pnf is given
+// (updateMatrixInterfaces on the source inside the component loop, fvMatrixSolve.C:170-186)
+__global__ void component_kernel(int nCells, int nc, int k, BoundaryLists L, const double *__restrict__ couBou,
+                                 const double *__restrict__ pnf, const double *__restrict__ in, double *__restrict__ out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    double acc = in[(size_t)c * nc + k];
+    if (L.cStart && pnf)
+        for (int j = L.cStart[c]; j < L.cStart[c + 1]; j++) {
+            const int pf = L.cFaces[j];
+            acc = __dsub_rn(acc, __dmul_rn(couBou[pf], pnf[(size_t)pf * nc + k]));
+        }
+    out[c] = acc;
+}
+
+__global__ void set_component_kernel(int nCells, int nc, int k, const double *__restrict__ in, double *__restrict__ out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < nCells) out[(size_t)c * nc + k] = in[c];
+}
+
+// A = (diag + sum_b cmptAv(internalCoeffs) + sum_coupled interfaceIntCoeffs)/V
+__global__ void A_kernel(int nCells, BoundaryLists L, const double *__restrict__ ic, int nc,
+                         const double *__restrict__ couInt, const double *__restrict__ diag,
+                         const double *__restrict__ V, double *__restrict__ out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    double acc = diag[c];
+    if (L.bStart)
+        for (int j = L.bStart[c]; j < L.bStart[c + 1]; j++)
+            acc = __dadd_rn(acc, cmpt_av(ic + (size_t)L.bFaces[j] * nc, nc));
+    if (L.cStart)
+        for (int j = L.cStart[c]; j < L.cStart[c + 1]; j++) acc = __dadd_rn(acc, couInt[L.cFaces[j]]);
+    out[c] = __ddiv_rn(acc, V[c]);
+}
+
+// H = ((lduMatrix::H(psi) + source) + boundary source)/V with lduMatrix::H = 0 - sum_own upper*psi[nei]
+// - sum_nei lower*psi[own] (lduMatrixTemplates.C:50-84; products rounded, negated, added)
+template <int NC>
+__global__ void H_kernel(int nCells, const int *__restrict__ ownerStart, const int *__restrict__ u,
+                         const int *__restrict__ losortStart, const int *__restrict__ losort, const int *__restrict__ l,
+                         const double *__restrict__ upper, const double *__restrict__ lower, BoundaryLists L,
+                         const double *__restrict__ bc, const double *__restrict__ couBou,
+                         const double *__restrict__ pnf, const double *__restrict__ psi,
+                         const double *__restrict__ source, const double *__restrict__ V, double *__restrict__ out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    double acc[NC];
+#pragma unroll
+    for (int k = 0; k < NC; k++) acc[k] = 0.0;
+    for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++) {
+        const double a = upper[f];
+        const int n = u[f];
+#pragma unroll
+        for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], -__dmul_rn(a, psi[(size_t)n * NC + k]));
+    }
+    for (int q = losortStart[c]; q < losortStart[c + 1]; q++) {
+        const int f = losort[q];
+        const double a = lower[f];
+        const int o = l[f];
+#pragma unroll
+        for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], -__dmul_rn(a, psi[(size_t)o * NC + k]));
+    }
+#pragma unroll
+    for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], source[(size_t)c * NC + k]);
+    if (L.bStart)
+        for (int j = L.bStart[c]; j < L.bStart[c + 1]; j++) {
+            const int bf = L.bFaces[j];
+#pragma unroll
+            for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], bc[(size_t)bf * NC + k]);
+        }
+    if (L.cStart && pnf)
+        for (int j = L.cStart[c]; j < L.cStart[c + 1]; j++) {
+            const int pf = L.cFaces[j];
+            const double b = couBou[pf];
+#pragma unroll
+            for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], __dmul_rn(b, pnf[(size_t)pf * NC + k]));
+        }
+    const double v = V[c];
+#pragma unroll
+    for (int k = 0; k < NC; k++) out[(size_t)c * NC + k] = __ddiv_rn(acc[k], v);
+}
+
+// flux: internal faces upper*psi[nei] - lower*psi[own] per component (lduMatrixTemplates.C:40-49,108-149)
+template <int NC>
+__global__ void flux_internal_kernel(int nFaces, const int *__restrict__ l, const int *__restrict__ u,
+                                     const double *__restrict__ upper, const double *__restrict__ lower,
+                                     const double *__restrict__ psi, double *__restrict__ out)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nFaces) return;
+    const double a = upper[f], b = lower[f];
+    const int o = l[f], n = u[f];
+#pragma unroll
+    for (int k = 0; k < NC; k++)
+        out[(size_t)f * NC + k] = __dsub_rn(__dmul_rn(a, psi[(size_t)n * NC + k]), __dmul_rn(b, psi[(size_t)o * NC + k]));
+}
+
+// boundary faces: internalCoeffs*psi[cell] - boundaryCoeffs (coupled: - boundaryCoeffs*pnf), fvMatrix.C:1622-1654
+template <int NC>
+__global__ void flux_boundary_kernel(int nB, const int *__restrict__ faceCells, const double *__restrict__ ic,
+                                     int icStride, const double *__restrict__ bc, int bcStride,
+                                     const double *__restrict__ pnf, const double *__restrict__ psi,
+                                     double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nB) return;
+    const int c = faceCells[i];
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+        const double a = ic[(size_t)i * icStride + (icStride == 1 ? 0 : k)];
+        const double b = bc[(size_t)i * bcStride + (bcStride == 1 ? 0 : k)];
+        const double nb = pnf ? __dmul_rn(b, pnf[(size_t)i * NC + k]) : b;
+        out[(size_t)i * NC + k] = __dsub_rn(__dmul_rn(a, psi[(size_t)c * NC + k]), nb);
+    }
+}
+
+// source - boundaryDiag*psi (fvScalarMatrixResidualFunctor, fvScalarMatrix.C:195-227)
+__global__ void residual_source_kernel(int nCells, BoundaryLists L, const double *__restrict__ ic,
+                                       const double *__restrict__ couInt, const double *__restrict__ psi,
+                                       const double *__restrict__ source, double *__restrict__ out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    double bd = 0.0;
+    if (L.bStart)
+        for (int j = L.bStart[c]; j < L.bStart[c + 1]; j++) bd = __dadd_rn(bd, ic[L.bFaces[j]]);
+    if (L.cStart)
+        for (int j = L.cStart[c]; j < L.cStart[c + 1]; j++) bd = __dadd_rn(bd, couInt[L.cFaces[j]]);
+    out[c] = __dsub_rn(source[c], __dmul_rn(bd, psi[c]));
+}
+
+// relax (fvMatrix.C:1088-1345), one pass: D0 = D; sumOff = sum |upper| (owner side) + sum |lower| (neighbour
+// side) [+ |boundaryCoeffs| of coupled faces]; D += max |internalCoeffs| (coupled: component 0);
+// D = max(|D|, sumOff)/alpha; D -= min internalCoeffs (coupled: component 0); S += (D - D0)*psi
+template <int NC>
+__global__ void relax_kernel(int nCells, const int *__restrict__ ownerStart, const int *__restrict__ losortStart,
+                             const int *__restrict__ losort, const double *__restrict__ upper,
+                             const double *__restrict__ lower, BoundaryLists L, const double *__restrict__ ic,
+                             const double *__restrict__ couInt, const double *__restrict__ couBou, double alpha,
+                             const double *__restrict__ psi, double *diag, double *source)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    const double D0 = diag[c];
+    double sumOff = 0.0;
+    for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++) sumOff = __dadd_rn(sumOff, fabs(upper[f]));
+    for (int q = losortStart[c]; q < losortStart[c + 1]; q++) sumOff = __dadd_rn(sumOff, fabs(lower[losort[q]]));
+    double D = D0;
+    if (L.bStart)
+        for (int j = L.bStart[c]; j < L.bStart[c + 1]; j++) {
+            const double *v = ic + (size_t)L.bFaces[j] * NC;
+            double m = fabs(v[0]);
+#pragma unroll
+            for (int k = 1; k < NC; k++) m = fmax(m, fabs(v[k]));
+            D = __dadd_rn(D, m);
+        }
+    if (L.cStart)
+        for (int j = L.cStart[c]; j < L.cStart[c + 1]; j++) {
+            const int pf = L.cFaces[j];
+            D = __dadd_rn(D, couInt[pf]);
+            sumOff = __dadd_rn(sumOff, fabs(couBou[pf]));
+        }
+    D = fmax(fabs(D), sumOff);
+    D = __ddiv_rn(D, alpha);
+    if (L.bStart)
+        for (int j = L.bStart[c]; j < L.bStart[c + 1]; j++) {
+            const double *v = ic + (size_t)L.bFaces[j] * NC;
+            double m = v[0];
+#pragma unroll
+            for (int k = 1; k < NC; k++) m = fmin(m, v[k]);
+            D = __dadd_rn(D, -m);
+        }
+    if (L.cStart)
+        for (int j = L.cStart[c]; j < L.cStart[c + 1]; j++) D = __dadd_rn(D, -couInt[L.cFaces[j]]);
+    diag[c] = D;
+    const double dD = __dsub_rn(D, D0);
+#pragma unroll
+    for (int k = 0; k < NC; k++)
+        source[(size_t)c * NC + k] = __dadd_rn(source[(size_t)c * NC + k], __dmul_rn(dD, psi[(size_t)c * NC + k]));
+}
+
+__global__ void set_reference_kernel(int cell, int nc, double v0, double v1, double v2, double *diag, double *source)
+{
+    const double v[3] = {v0, v1, v2};
+    const double d = diag[cell];
+    for (int k = 0; k < nc; k++)
+        source[(size_t)cell * nc + k] = __dadd_rn(source[(size_t)cell * nc + k], __dmul_rn(d, v[k]));
+    diag[cell] = __dmul_rn(2.0, d);
+}
+
+inline dim3 grid(int n, int b) { return dim3((unsigned)((n + b - 1) / b)); }
+
+bool bad_nc(int nc) { return nc != 1 && nc != 3; }
+
+int need_boundary(const b200ldu_addr *a, const void *ic, const char *what)
+{
+    if (a->nBFaces && !ic) {
+        b200_set_error("%s: boundary coefficients required (b200ldu_fv_boundary_set holds %d faces)", what, a->nBFaces);
+        return B200LDU_EINVAL;
+    }
+    return B200LDU_OK;
+}
+} // namespace
+
+extern "C" int b200ldu_fvm_add_boundary_diag(b200ldu_matrix *m, int nComp, int cmpt, const double *internalCoeffs_d,
+                                             const double *diagIn_d, double *diagOut_d)
+{
+    if (!m || !diagOut_d || bad_nc(nComp) || cmpt >= nComp) return B200LDU_EINVAL;
+    b200ldu_addr *a = m->a;
+    TRY(need_boundary(a, internalCoeffs_d, "fvm_add_boundary_diag"));
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    BoundaryLists L;
+    TRY(lists(a, &L));
+    boundary_diag_kernel<<<grid(a->nCells, 256), 256, 0, a->ctx->stream>>>(a->nCells, L, internalCoeffs_d, nComp, cmpt,
+                                                                           m->int_ext, diagIn_d, diagOut_d);
+    a->ctx->launches++;
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}
+
+extern "C" int b200ldu_fvm_add_boundary_source(b200ldu_matrix *m, int nComp, const double *boundaryCoeffs_d,
+                                               const double *pnf_d, const double *sourceIn_d, double *sourceOut_d)
+{
+    if (!m || !sourceIn_d || !sourceOut_d || bad_nc(nComp)) return B200LDU_EINVAL;
+    b200ldu_addr *a = m->a;
+    TRY(need_boundary(a, boundaryCoeffs_d, "fvm_add_boundary_source"));
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    BoundaryLists L;
+    TRY(lists(a, &L));
+    if (nComp == 1)
+        boundary_source_kernel<1><<<grid(a->nCells, 256), 256, 0, a->ctx->stream>>>(a->nCells, L, boundaryCoeffs_d,
+                                                                                    m->bou_ext, pnf_d, sourceIn_d, sourceOut_d);
+    else
+        boundary_source_kernel<3><<<grid(a->nCells, 256), 256, 0, a->ctx->stream>>>(a->nCells, L, boundaryCoeffs_d,
+                                                                                    m->bou_ext, pnf_d, sourceIn_d, sourceOut_d);
+    a->ctx->launches++;
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}
+
+extern "C" int b200ldu_fvm_A(b200ldu_matrix *m, int nComp, const double *internalCoeffs_d, const double *V_d,
+                             double *A_d)
+{
+    if (!m || !V_d || !A_d || bad_nc(nComp) || !m->diag_ext) return B200LDU_EINVAL;
+    b200ldu_addr *a = m->a;
+    TRY(need_boundary(a, internalCoeffs_d, "fvm_A"));
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    BoundaryLists L;
+    TRY(lists(a, &L));
+    A_kernel<<<grid(a->nCells, 256), 256, 0, a->ctx->stream>>>(a->nCells, L, internalCoeffs_d, nComp, m->int_ext,
+                                                               m->diag_ext, V_d, A_d);
+    a->ctx->launches++;
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}
+
+extern "C" int b200ldu_fvm_H(b200ldu_matrix *m, int nComp, const double *psi_d, const double *source_d,
+                             const double *boundaryCoeffs_d, const double *pnf_d, const double *V_d, double *H_d)
+{
+    if (!m || !psi_d || !source_d || !V_d || !H_d || bad_nc(nComp) || !m->diag_ext) return B200LDU_EINVAL;
+    b200ldu_addr *a = m->a;
+    TRY(need_boundary(a, boundaryCoeffs_d, "fvm_H"));
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    BoundaryLists L;
+    TRY(lists(a, &L));
+    if (L.cStart && !pnf_d) {
+        b200_set_error("fvm_H: the coupled patches need their patchNeighbourField (fvMatrix.C:318-346)");
+        return B200LDU_EINVAL;
+    }
+    if (nComp == 1)
+        H_kernel<1><<<grid(a->nCells, 128), 128, 0, a->ctx->stream>>>(
+            a->nCells, a->d_ownerStart, a->d_u, a->d_losortStart, a->d_losort, a->d_l, m->upper_ext, m->lower_ext, L,
+            boundaryCoeffs_d, m->bou_ext, pnf_d, psi_d, source_d, V_d, H_d);
+    else
+        H_kernel<3><<<grid(a->nCells, 128), 128, 0, a->ctx->stream>>>(
+            a->nCells, a->d_ownerStart, a->d_u, a->d_losortStart, a->d_losort, a->d_l, m->upper_ext, m->lower_ext, L,
+            boundaryCoeffs_d, m->bou_ext, pnf_d, psi_d, source_d, V_d, H_d);
+    a->ctx->launches++;
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}
+
+extern "C" int b200ldu_fvm_flux(b200ldu_matrix *m, int nComp, const double *psi_d, const double *internalCoeffs_d,
+                                const double *boundaryCoeffs_d, const double *pnf_d, double *flux_d,
+                                double *boundaryFlux_d, double *coupledFlux_d)
+{
+    if (!m || !psi_d || bad_nc(nComp) || !m->diag_ext) return B200LDU_EINVAL;
+    b200ldu_addr *a = m->a;
+    if ((a->nFaces && !flux_d) || (a->nBFaces && (!boundaryFlux_d || !internalCoeffs_d || !boundaryCoeffs_d)))
+        return B200LDU_EINVAL;
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    BoundaryLists L;
+    TRY(lists(a, &L));
+    if (a->nCFaces && (!coupledFlux_d || !pnf_d)) {
+        b200_set_error("fvm_flux: the coupled patches need their patchNeighbourField and an output (fvMatrix.C:1636-1648)");
+        return B200LDU_EINVAL;
+    }
+    cudaStream_t st = a->ctx->stream;
+    if (a->nFaces) {
+        if (nComp == 1)
+            flux_internal_kernel<1><<<grid(a->nFaces, 256), 256, 0, st>>>(a->nFaces, a->d_l, a->d_u, m->upper_ext,
+                                                                          m->lower_ext, psi_d, flux_d);
+        else
+            flux_internal_kernel<3><<<grid(a->nFaces, 256), 256, 0, st>>>(a->nFaces, a->d_l, a->d_u, m->upper_ext,
+                                                                          m->lower_ext, psi_d, flux_d);
+        a->ctx->launches++;
+    }
+    if (a->nBFaces) {
+        if (nComp == 1)
+            flux_boundary_kernel<1><<<grid(a->nBFaces, 256), 256, 0, st>>>(a->nBFaces, a->d_bFaceCells, internalCoeffs_d,
+                                                                           1, boundaryCoeffs_d, 1, nullptr, psi_d,
+                                                                           boundaryFlux_d);
+        else
+            flux_boundary_kernel<3><<<grid(a->nBFaces, 256), 256, 0, st>>>(a->nBFaces, a->d_bFaceCells, internalCoeffs_d,
+                                                                           3, boundaryCoeffs_d, 3, nullptr, psi_d,
+                                                                           boundaryFlux_d);
+        a->ctx->launches++;
+    }
+    if (a->nCFaces) {
+        if (nComp == 1)
+            flux_boundary_kernel<1><<<grid(a->nCFaces, 256), 256, 0, st>>>(a->nCFaces, a->d_cFaceCells, m->int_ext, 1,
+                                                                           m->bou_ext, 1, pnf_d, psi_d, coupledFlux_d);
+        else
+            flux_boundary_kernel<3><<<grid(a->nCFaces, 256), 256, 0, st>>>(a->nCFaces, a->d_cFaceCells, m->int_ext, 1,
+                                                                           m->bou_ext, 1, pnf_d, psi_d, coupledFlux_d);
+        a->ctx->launches++;
+    }
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}
+
+extern "C" int b200ldu_fvm_residual(b200ldu_matrix *m, const double *psi_d, const double *source_d,
+                                    const double *internalCoeffs_d, const double *boundaryCoeffs_d,
+                                    const double *pnf_d, double *residual_d)
+{
+    if (!m || !psi_d || !source_d || !residual_d || !m->diag_ext) return B200LDU_EINVAL;
+    b200ldu_addr *a = m->a;
+    TRY(need_boundary(a, internalCoeffs_d, "fvm_residual"));
+    TRY(need_boundary(a, boundaryCoeffs_d, "fvm_residual"));
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    BoundaryLists L;
+    TRY(lists(a, &L));
+    if (L.cStart && !pnf_d) {
+        b200_set_error("fvm_residual: the coupled patches need their patchNeighbourField (addBoundarySource)");
+        return B200LDU_EINVAL;
+    }
+    double *tmp = nullptr;
+    TRY(scratch(a, 0, (size_t)a->nCells, &tmp));
+    residual_source_kernel<<<grid(a->nCells, 256), 256, 0, a->ctx->stream>>>(a->nCells, L, internalCoeffs_d, m->int_ext,
+                                                                             psi_d, source_d, tmp);
+    a->ctx->launches++;
+    KERNEL_CHECK();
+    TRY(b200ldu_residual(m, psi_d, tmp, residual_d)); // lduMatrix::residual incl. the interface update
+    return b200ldu_fvm_add_boundary_source(m, 1, boundaryCoeffs_d, pnf_d, residual_d, residual_d);
+}
+
+extern "C" int b200ldu_fvm_relax(b200ldu_matrix *m, int nComp, double alpha, const double *psi_d,
+                                 const double *internalCoeffs_d, double *diag_d, double *source_d)
+{
+    if (!m || !psi_d || !diag_d || !source_d || bad_nc(nComp) || !m->diag_ext) return B200LDU_EINVAL;
+    if (alpha <= 0) return B200LDU_OK; // fvMatrix.C:1090-1093
+    b200ldu_addr *a = m->a;
+    TRY(need_boundary(a, internalCoeffs_d, "fvm_relax"));
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    BoundaryLists L;
+    TRY(lists(a, &L));
+    if (nComp == 1)
+        relax_kernel<1><<<grid(a->nCells, 128), 128, 0, a->ctx->stream>>>(
+            a->nCells, a->d_ownerStart, a->d_losortStart, a->d_losort, m->upper_ext, m->lower_ext, L, internalCoeffs_d,
+            m->int_ext, m->bou_ext, alpha, psi_d, diag_d, source_d);
+    else
+        relax_kernel<3><<<grid(a->nCells, 128), 128, 0, a->ctx->stream>>>(
+            a->nCells, a->d_ownerStart, a->d_losortStart, a->d_losort, m->upper_ext, m->lower_ext, L, internalCoeffs_d,
+            m->int_ext, m->bou_ext, alpha, psi_d, diag_d, source_d);
+    a->ctx->launches++;
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}
+
+extern "C" int b200ldu_fvm_set_reference(b200ldu_matrix *m, int celli, int nComp, const double *value_h,
+                                         double *diag_d, double *source_d)
+{
+    if (!m || !value_h || !diag_d || !source_d || bad_nc(nComp) || celli >= m->a->nCells) return B200LDU_EINVAL;
+    if (celli < 0) return B200LDU_OK; // the reference cell lives on another rank (fvMatrix.C:972)
+    b200ldu_addr *a = m->a;
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    set_reference_kernel<<<1, 1, 0, a->ctx->stream>>>(celli, nComp, value_h[0], nComp > 1 ? value_h[1] : 0.0,
+                                                      nComp > 2 ? value_h[2] : 0.0, diag_d, source_d);
+    a->ctx->launches++;
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}
+
+// solveSegregated: fold the boundary into diagonal and source, solve, put the diagonal back.
+// Scalar: fvScalarMatrix.C:142-192.  Vector: fvMatrixSolve.C:104-226 -- the coupled boundary source goes in once
+// for all components and is taken out again per component through the interface update on the source.
+extern "C" int b200ldu_fvm_solve(b200ldu_matrix *m, int nComp, const char *solver, const char *precondOrSmoother,
+                                 const b200ldu_controls *controls, b200ldu_gamg *gamg, double *psi_d,
+                                 const double *source_d, const double *internalCoeffs_d,
+                                 const double *boundaryCoeffs_d, const double *pnf_d, b200ldu_perf *perf)
+{
+    if (!m || !solver || !psi_d || !source_d || !perf || bad_nc(nComp) || !m->diag_ext) return B200LDU_EINVAL;
+    b200ldu_addr *a = m->a;
+    TRY(need_boundary(a, internalCoeffs_d, "fvm_solve"));
+    TRY(need_boundary(a, boundaryCoeffs_d, "fvm_solve"));
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    BoundaryLists L;
+    TRY(lists(a, &L));
+    if (nComp > 1 && L.cStart && !pnf_d) {
+        b200_set_error("fvm_solve: the component loop needs the patchNeighbourField of the coupled patches");
+        return B200LDU_EINVAL;
+    }
+    const int n = a->nCells;
+    cudaStream_t st = a->ctx->stream;
+    // the caller's coefficient arrays: the matrix is re-pointed at the folded diagonal for the solve
+    const double *diag0 = m->diag_ext, *upper = m->upper_ext, *lower = m->symmetric ? nullptr : m->lower_ext;
+    const double *bou = m->bou_ext, *intc = m->int_ext;
+    double *dK = nullptr, *total = nullptr, *sK = nullptr, *pK = nullptr;
+    TRY(scratch(a, 0, (size_t)n, &dK));
+    TRY(scratch(a, 1, (size_t)n * nComp, &total));
+    int rc = B200LDU_OK;
+    if (nComp == 1) {
+        boundary_diag_kernel<<<grid(n, 256), 256, 0, st>>>(n, L, internalCoeffs_d, 1, 0, intc, diag0, dK);
+        boundary_source_kernel<1><<<grid(n, 256), 256, 0, st>>>(n, L, boundaryCoeffs_d, bou, nullptr, source_d, total);
+        a->ctx->launches += 2;
+        KERNEL_CHECK();
+        rc = b200ldu_matrix_set(m, dK, upper, lower, bou, intc);
+        if (rc == B200LDU_OK) rc = b200ldu_solve(m, solver, precondOrSmoother, controls, gamg, psi_d, total, &perf[0], nullptr, 0);
+    } else {
+        TRY(scratch(a, 2, (size_t)n, &sK));
+        TRY(scratch(a, 3, (size_t)n, &pK));
+        boundary_source_kernel<3><<<grid(n, 256), 256, 0, st>>>(n, L, boundaryCoeffs_d, bou, pnf_d, source_d, total);
+        a->ctx->launches++;
+        KERNEL_CHECK();
+        BoundaryLists none = L;
+        none.cStart = nullptr;
+        for (int k = 0; k < nComp && rc == B200LDU_OK; k++) {
+            boundary_diag_kernel<<<grid(n, 256), 256, 0, st>>>(n, L, internalCoeffs_d, nComp, k, intc, diag0, dK);
+            component_kernel<<<grid(n, 256), 256, 0, st>>>(n, nComp, k, L, bou, pnf_d, total, sK);
+            component_kernel<<<grid(n, 256), 256, 0, st>>>(n, nComp, k, none, nullptr, nullptr, psi_d, pK);
+            a->ctx->launches += 3;
+            KERNEL_CHECK();
+            rc = b200ldu_matrix_set(m, dK, upper, lower, bou, intc);
+            if (rc == B200LDU_OK) rc = b200ldu_solve(m, solver, precondOrSmoother, controls, gamg, pK, sK, &perf[k], nullptr, 0);
+            if (rc == B200LDU_OK) {
+                set_component_kernel<<<grid(n, 256), 256, 0, st>>>(n, nComp, k, pK, psi_d);
+                a->ctx->launches++;
+                KERNEL_CHECK();
+            }
+        }
+    }
+    const int rc2 = b200ldu_matrix_set(m, diag0, upper, lower, bou, intc); // diag() = saveDiag
+    return rc != B200LDU_OK ? rc : rc2;
+}

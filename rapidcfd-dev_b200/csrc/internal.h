@@ -162,6 +162,12 @@ struct b200ldu_addr {
     int *d_bFaceCells = nullptr;    // boundary faces (all patches, patch order)
     int *d_bCellStart = nullptr, *d_bCellFaces = nullptr, *d_bCells = nullptr; // per boundary cell lists
     int nBCells = 0;
+    // fvMatrix glue (fvmatrix.cu): per-cell lists over the coupled patch faces, built at first use, and
+    // grow-only scratch vectors
+    int nCFaces = 0;
+    int *d_cCellStart = nullptr, *d_cCellFaces = nullptr, *d_cFaceCells = nullptr;
+    double *d_fvmScratch[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t fvmScratchLen[4] = {0, 0, 0, 0};
     // host-only structural self-check (b200ldu_layout_debug_*): no GPU, no compute
     bool hostOnly = false;
     std::vector<long long> dbg_sliceStart;

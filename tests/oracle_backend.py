@@ -1,14 +1,15 @@
 """Dry-run aid for the GPU tests (NOT part of the product and not used by default): an object with the
 surface of rapidcfd-dev_b200.capi backed by the CPU oracle and CPU torch tensors.
 
-    B200LDU_DRYRUN_ORACLE=1 python -m pytest tests/test_ref_golden.py tests/test_zz_golden.py -m gpu -q
+    B200LDU_DRYRUN_ORACLE=1 python -m pytest tests/test_ref_golden.py tests/test_zz_golden.py tests/test_zzz_fvm_gpu.py -m gpu -q
 
-runs the `-m gpu` tests of those two files with this stand-in instead of the CUDA library: it checks the
+runs the `-m gpu` tests of those files with this stand-in instead of the CUDA library: it checks the
 tests' own logic (indexing of the fixtures, shapes, iteration windows, tolerances) where no GPU is
 available.  It says nothing about the CUDA path; on a GPU box the variable is unset and the real library
 is used."""
 import numpy as np
 
+from oracle import fvm_oracle as fo
 from oracle import ldu_oracle as orc
 
 
@@ -40,6 +41,7 @@ class LduMatrix:
 
     def set(self, diag, upper, lower=None, bou=None, intc=None):
         self.m = orc.Matrix(self.addr.o, _np(diag), _np(upper), _np(lower), _np(bou), _np(intc))
+        self.coeffs = (diag, upper, lower, bou, intc)
         return self
 
     def _t(self, a):
@@ -85,6 +87,72 @@ class LduMatrix:
         pass
 
 
+class FvMatrix:
+    """surface of capi.FvMatrix over oracle/fvm_oracle.py (dry runs of tests/test_zzz_fvm_gpu.py)"""
+
+    def __init__(self, matrix, nComp, diag, source, psi, V, internalCoeffs=None, boundaryCoeffs=None):
+        self.m, self.nc = matrix, int(nComp)
+        self.diag, self.source, self.psi, self.V, self.ic, self.bc = diag, source, psi, V, internalCoeffs, boundaryCoeffs
+
+    def _o(self, diag=None, source=None):
+        _, upper, lower, bou, intc = self.m.coeffs
+        a = self.m.addr
+        return fo.FvMatrix(orc, a.o, self.nc, _np(self.diag if diag is None else diag), _np(upper), _np(lower),
+                           _np(self.source if source is None else source), _np(self.psi), _np(self.V), a.bfc,
+                           _np(self.ic), _np(self.bc), couInt=_np(intc), couBou=_np(bou))
+
+    def _t(self, a):
+        import torch
+        return torch.from_numpy(np.ascontiguousarray(a).ravel())
+
+    def _pnf(self, pnf):
+        return None if pnf is None else _np(pnf).reshape(-1, self.nc)
+
+    def addBoundaryDiag(self, diag, cmpt):
+        d = _np(diag).copy()
+        self._o().addBoundaryDiag(d, cmpt)
+        diag.copy_(self._t(d))
+
+    def addCmptAvBoundaryDiag(self, diag):
+        d = _np(diag).copy()
+        self._o().addCmptAvBoundaryDiag(d)
+        diag.copy_(self._t(d))
+
+    def addBoundarySource(self, source, pnf=None):
+        s = _np(source).reshape(-1, self.nc).copy()
+        self._o().addBoundarySource(s, pnf is not None, self._pnf(pnf))
+        source.copy_(self._t(s))
+
+    def A(self):
+        return self._t(self._o().A())
+
+    def H(self, pnf=None):
+        return self._t(self._o().H(pnf=self._pnf(pnf)))
+
+    def flux(self, nBFaces, nCoupledFaces=0, pnf=None):
+        return tuple(self._t(x) for x in self._o().flux(self._pnf(pnf)))
+
+    def residual(self, pnf=None):
+        return self._t(self._o().residual(self._pnf(pnf)))
+
+    def relax(self, alpha):
+        o = self._o()
+        o.relax(alpha)
+        self.diag.copy_(self._t(o.diag))
+        self.source.copy_(self._t(o.source))
+
+    def setReference(self, celli, value):
+        o = self._o()
+        o.setReference(celli, value)
+        self.diag.copy_(self._t(o.diag))
+        self.source.copy_(self._t(o.source))
+
+    def solve(self, solver, pre, gamg=None, pnf=None, **ctl):
+        psi, perfs, _ = self._o().solve(solver, pre, gamg.o if gamg is not None else None, self._pnf(pnf), **ctl)
+        self.psi.copy_(self._t(psi))
+        return perfs
+
+
 class GamgAgglomeration:
     def __init__(self, addr, faceWeights, nCellsInCoarsestLevel=10, mergeLevels=1, forward=1):
         self.o = orc.Gamg(addr.o, faceWeights, nCellsInCoarsestLevel, mergeLevels=mergeLevels, forward=forward)
@@ -107,6 +175,11 @@ class GamgAgglomeration:
 class _Capi:
     LduAddressing = LduAddressing
     LduMatrix = LduMatrix
+    FvMatrix = FvMatrix
+
+    @staticmethod
+    def fv_boundary_set(addr, bFaceCells):
+        addr.bfc = np.asarray(bFaceCells, np.int32).copy()
     GamgAgglomeration = GamgAgglomeration
 
     @staticmethod

@@ -4,6 +4,9 @@
 set -x
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -15 > gpurun_out/r02a_tests.log
+# row a17 (csrc/fvmatrix.cu) has never run on a GPU: its own log, verbose, and under compute-sanitizer once
+python -m pytest tests/test_zzz_fvm_gpu.py -m gpu -v 2>&1 | tail -30 > gpurun_out/r02a_fvm_tests.log
+compute-sanitizer --tool memcheck python -m pytest tests/test_zzz_fvm_gpu.py -m gpu -q -x 2>&1 | tail -25 > gpurun_out/r02a_fvm_memcheck.log
 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE-OK')" > gpurun_out/r02a_smoke.log 2>&1
 python bench.py --impl reference > gpurun_out/r02a_bench_ref.json 2> gpurun_out/r02a_bench_ref.err
 python bench.py > gpurun_out/r02a_bench_n1.json 2> gpurun_out/r02a_bench_n1.err
@@ -14,5 +17,5 @@ ncu --set full --clock-control none --import-source on \
 ncu --set full --clock-control none --import-source on \
     -k regex:"restrict_kernel|prolong_kernel|agg_diag_kernel|agg_faces_kernel|dense_apply" \
     -c 16 -f -o gpurun_out/r02a_gamg python bench_kernels.py --n 64 --reps 1 > gpurun_out/r02a_ncu_gamg.log 2>&1
-cat gpurun_out/r02a_tests.log gpurun_out/r02a_smoke.log | tail -20
+cat gpurun_out/r02a_tests.log gpurun_out/r02a_fvm_tests.log gpurun_out/r02a_smoke.log | tail -40
 cut -c1-300 gpurun_out/r02a_bench_ref.json gpurun_out/r02a_bench_n1.json
