@@ -1,0 +1,52 @@
+"""one icoFoam step restated (oracle/piso_oracle.py) has to produce the physics of
+the lid-driven cavity -- there is no reference build to compare with, so these are property checks."""
+import numpy as np
+
+from oracle import piso_oracle as po
+
+
+def test_cavity_steps_conserve_mass_and_spin_up(meshmod, orc):
+    n = 8
+    m, case = po.cavity_from_hex(orc, meshmod, n, nu=0.01)
+    ke, conts = [], []
+    for step in range(6):
+        perfs, cont = case.step(nCorr=2, pControls=dict(tolerance=1e-10, relTol=0.0),
+                                UControls=dict(tolerance=1e-10, relTol=0.0))
+        assert all(p.converged for p in perfs["U"]) and all(p.converged for p in perfs["p"])
+        assert len(perfs["p"]) == 2                               # one pressure solve per PISO corrector
+        conts.append(cont[-1][0])
+        ke.append(0.5 * (case.U ** 2).sum(axis=1) @ case.V)
+    # the corrected face flux is divergence free to the pressure solver's tolerance
+    assert max(conts) < 1e-9
+    div = case.div(case.phi, case.bphi)
+    assert np.abs(div).max() < 1e-6
+    # the lid drags the fluid along: kinetic energy grows monotonically during spin-up, the top layer moves with
+    # the lid, the return flow below goes the other way, nothing leaves through the walls
+    assert all(b > a for a, b in zip(ke, ke[1:]))
+    cc = m.cell_centres()
+    top = cc[:, 1] > 1 - m.h
+    assert case.U[top, 0].mean() > 0.1
+    assert case.U[(cc[:, 1] > 0.4) & (cc[:, 1] < 0.7), 0].mean() < 0
+    assert np.array_equal(case.bphi, np.zeros_like(case.bphi))
+    # the case is symmetric about the mid-plane z = 1/2: so is the solution (to solver tolerance)
+    idx = np.arange(m.nCells).reshape(n, n, n)                    # [k, j, i]
+    mirror = idx[::-1].ravel()
+    np.testing.assert_allclose(case.U[mirror, 0], case.U[:, 0], atol=1e-8)
+    np.testing.assert_allclose(case.U[mirror, 2], -case.U[:, 2], atol=1e-8)
+    np.testing.assert_allclose(case.p[mirror], case.p, atol=1e-8)
+
+
+def test_pressure_correction_projects_the_flux(meshmod, orc):
+    """One corrector with an already converged momentum field: phi = phiHbyA - flux(p) removes exactly the divergence
+    that div(phiHbyA) had put into the pressure equation's source."""
+    m, case = po.cavity_from_hex(orc, meshmod, 6, nu=0.05)
+    for _ in range(3):
+        case.step(nCorr=2, pControls=dict(tolerance=1e-12, relTol=0.0), UControls=dict(tolerance=1e-12, relTol=0.0))
+    U_before = case.U.copy()
+    perfs, cont = case.step(nCorr=3, pControls=dict(tolerance=1e-12, relTol=0.0),
+                            UControls=dict(tolerance=1e-12, relTol=0.0))
+    assert cont[-1][0] < 1e-11 and abs(cont[-1][1]) < 1e-12
+    # successive correctors converge: the later ones need fewer pressure iterations than the first
+    its = [p.nIterations for p in perfs["p"]]
+    assert its[-1] <= its[0]
+    assert np.abs(case.U - U_before).max() < 0.2                  # a time step changes the field smoothly
