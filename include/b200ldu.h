@@ -256,6 +256,19 @@ int b200ldu_fvm_solve(b200ldu_matrix *m, int nComp, const char *solver, const ch
                       const double *internalCoeffs_d, const double *boundaryCoeffs_d, const double *pnf_d,
                       b200ldu_perf *perf);
 
+/* ---- element-wise field operators between the kernels (the gpuField operator set of
+ * src/OpenFOAM/fields/Fields/gpuField/gpuFieldFunctionsM.C:200-330): one rounding per element and operator, so a
+ * caller that composes them in the reference's order reproduces the reference's field expressions.  n = elements;
+ * a 1-component operand combines with a 3-component one component-wise (scalargpuField * vectorgpuField).
+ *   binary op: 0 a+b, 1 a-b, 2 a*b, 3 a/b, 4 min(a,b), 5 max(a,b)
+ *   unary  op (n = number of doubles): 0 -a, 1 |a|, 2 s*a, 3 s/a, 4 a+s, 5 s-a, 6 min(a,s), 7 max(a,s), 8 a-s, 9 a/s, 10 a
+ *   dot3: (a.x*b.x + a.y*b.y) + a.z*b.z per element;  gather: patchInternalField, out[i] = field[cells[i]] */
+int b200ldu_field_binary(b200ldu_ctx *ctx, int op, long long n, int nCompA, const double *a_d, int nCompB,
+                         const double *b_d, double *out_d);
+int b200ldu_field_unary(b200ldu_ctx *ctx, int op, long long n, double s, const double *a_d, double *out_d);
+int b200ldu_field_dot3(b200ldu_ctx *ctx, long long n, const double *a_d, const double *b_d, double *out_d);
+int b200ldu_field_gather(b200ldu_ctx *ctx, int n, int nComp, const int *cells_d, const double *field_d, double *out_d);
+
 /* ---- structural self-check of the banded layout (host only, no GPU, no arithmetic);
  * used by the CPU test-suite.  what: 0 perm 1 iperm 2 sliceStart(int64) 3 sliceW(u16)
  * 4 sliceWL(u16) 5 col(u16) 6 code(int32) 7 haloStart 8 haloIdx 9 dims{nPad,nBands,bandRows,

@@ -66,6 +66,7 @@ EXPORTS = [
     "b200ldu_fvm_add_boundary_diag", "b200ldu_fvm_add_boundary_source", "b200ldu_fvm_A", "b200ldu_fvm_H",
     "b200ldu_fvm_flux", "b200ldu_fvm_residual", "b200ldu_fvm_relax", "b200ldu_fvm_set_reference",
     "b200ldu_fvm_solve",
+    "b200ldu_field_binary", "b200ldu_field_unary", "b200ldu_field_dot3", "b200ldu_field_gather",
 ]
 
 _lib = None
@@ -139,6 +140,10 @@ def lib():
     L.b200ldu_fvm_residual.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.b200ldu_fvm_relax.argtypes = [vp, C.c_int, C.c_double, vp, vp, vp, vp]
     L.b200ldu_fvm_set_reference.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    L.b200ldu_field_binary.argtypes = [vp, C.c_int, C.c_longlong, C.c_int, vp, C.c_int, vp, vp]
+    L.b200ldu_field_unary.argtypes = [vp, C.c_int, C.c_longlong, C.c_double, vp, vp]
+    L.b200ldu_field_dot3.argtypes = [vp, C.c_longlong, vp, vp, vp]
+    L.b200ldu_field_gather.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     L.b200ldu_fvm_solve.argtypes = [vp, C.c_int, C.c_char_p, C.c_char_p, C.POINTER(Controls), vp, vp, vp, vp, vp, vp,
                                     C.POINTER(Perf)]
     _lib = L
@@ -452,6 +457,119 @@ class GamgAgglomeration:
         if self.h:
             lib().b200ldu_gamg_destroy(self.h)
             self.h = vp()
+
+
+class FieldOps:
+    """The gpuField operator set between the kernels (b200ldu_field_*): one rounded operation per call, composed by
+    the caller in the reference's order.  Fields are flat device tensors; nc* = components per element."""
+    ADD, SUB, MUL, DIV, MIN, MAX = range(6)
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def _new(self, like, n):
+        import torch
+        return torch.empty(n, dtype=torch.float64, device=like.device)
+
+    def binary(self, op, a, b, nca=1, ncb=1):
+        n = a.numel() // nca
+        assert b.numel() // ncb == n
+        out = self._new(a, n * max(nca, ncb))
+        check(lib().b200ldu_field_binary(self.ctx.h, op, n, nca, _dp(a), ncb, _dp(b), _dp(out)))
+        return out
+
+    def add(self, a, b, nca=1, ncb=1):
+        return self.binary(self.ADD, a, b, nca, ncb)
+
+    def sub(self, a, b, nca=1, ncb=1):
+        return self.binary(self.SUB, a, b, nca, ncb)
+
+    def mul(self, a, b, nca=1, ncb=1):
+        return self.binary(self.MUL, a, b, nca, ncb)
+
+    def div(self, a, b, nca=1, ncb=1):
+        return self.binary(self.DIV, a, b, nca, ncb)
+
+    def unary(self, op, a, s=0.0):
+        out = self._new(a, a.numel())
+        check(lib().b200ldu_field_unary(self.ctx.h, op, a.numel(), float(s), _dp(a), _dp(out)))
+        return out
+
+    def neg(self, a):
+        return self.unary(0, a)
+
+    def mag(self, a):
+        return self.unary(1, a)
+
+    def smul(self, s, a):            # s*a
+        return self.unary(2, a, s)
+
+    def rdiv(self, s, a):            # s/a
+        return self.unary(3, a, s)
+
+    def sadd(self, a, s):            # a + s
+        return self.unary(4, a, s)
+
+    def rsub(self, s, a):            # s - a
+        return self.unary(5, a, s)
+
+    def smin(self, a, s):            # min(a, s)
+        return self.unary(6, a, s)
+
+    def dot3(self, a, b):
+        out = self._new(a, a.numel() // 3)
+        check(lib().b200ldu_field_dot3(self.ctx.h, a.numel() // 3, _dp(a), _dp(b), _dp(out)))
+        return out
+
+    def gather(self, cells, f, nc=1):
+        out = self._new(f, cells.numel() * nc)
+        check(lib().b200ldu_field_gather(self.ctx.h, cells.numel(), nc, _dp(cells), _dp(f), _dp(out)))
+        return out
+
+
+def _newlike(t, n):
+    import torch
+    return torch.empty(n, dtype=torch.float64, device=t.device)
+
+
+def fv_convection_fill(addr, weights, phi):
+    """gaussConvectionScheme::fvmDiv coefficients: (lower, upper, diag)"""
+    lo, up, dg = _newlike(phi, addr.nFaces), _newlike(phi, addr.nFaces), _newlike(phi, addr.nCells)
+    check(lib().b200ldu_fv_convection_fill(addr.h, _dp(weights), _dp(phi), _dp(lo), _dp(up), _dp(dg)))
+    return lo, up, dg
+
+
+def fv_laplacian_fill(addr, deltaCoeffs, gammaMagSf):
+    """gaussLaplacianScheme::fvmLaplacianUncorrected coefficients: (upper, diag)"""
+    up, dg = _newlike(gammaMagSf, addr.nFaces), _newlike(gammaMagSf, addr.nCells)
+    check(lib().b200ldu_fv_laplacian_fill(addr.h, _dp(deltaCoeffs), _dp(gammaMagSf), _dp(up), _dp(dg)))
+    return up, dg
+
+
+def fv_interpolate_linear(addr, nComp, w, vf):
+    sf = _newlike(vf, addr.nFaces * nComp)
+    check(lib().b200ldu_fv_interpolate_linear(addr.h, nComp, _dp(w), _dp(vf), _dp(sf)))
+    return sf
+
+
+def fv_flux_linear(addr, Sf, w, U):
+    """interpolate(U) & Sf per internal face"""
+    phi = _newlike(U, addr.nFaces)
+    check(lib().b200ldu_fv_flux_linear(addr.h, _dp(Sf), _dp(w), _dp(U), _dp(phi)))
+    return phi
+
+
+def fv_grad_linear(addr, nComp, Sf, w, vf, bSf, bvf, V):
+    """gaussGrad(linear): gradf(interpolate(vf)) without the face field"""
+    g = _newlike(vf, addr.nCells * 3 * nComp)
+    check(lib().b200ldu_fv_grad_linear(addr.h, nComp, _dp(Sf), _dp(w), _dp(vf), _dp(bSf), _dp(bvf), _dp(V), _dp(g)))
+    return g
+
+
+def fv_surface_integrate(addr, nComp, ssf, bssf, V, divideByV=True, neiSign=-1):
+    out = _newlike(ssf, addr.nCells * nComp)
+    check(lib().b200ldu_fv_surface_integrate(addr.h, nComp, _dp(ssf), _dp(bssf), _dp(V), _dp(out), int(divideByV), neiSign))
+    return out
 
 
 def fv_boundary_set(addr, bFaceCells):

@@ -153,6 +153,62 @@ class FvMatrix:
         return perfs
 
 
+class FieldOps:
+    """surface of capi.FieldOps in numpy (one rounded operation per call, like the device kernels)"""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    @staticmethod
+    def _t(a):
+        import torch
+        return torch.from_numpy(np.ascontiguousarray(a).ravel())
+
+    def _bin(self, f, a, b, nca, ncb):
+        A, B = _np(a).reshape(-1, nca), _np(b).reshape(-1, ncb)
+        return self._t(f(A, B))
+
+    def add(self, a, b, nca=1, ncb=1):
+        return self._bin(np.add, a, b, nca, ncb)
+
+    def sub(self, a, b, nca=1, ncb=1):
+        return self._bin(np.subtract, a, b, nca, ncb)
+
+    def mul(self, a, b, nca=1, ncb=1):
+        return self._bin(np.multiply, a, b, nca, ncb)
+
+    def div(self, a, b, nca=1, ncb=1):
+        return self._bin(np.divide, a, b, nca, ncb)
+
+    def neg(self, a):
+        return self._t(-_np(a))
+
+    def mag(self, a):
+        return self._t(np.abs(_np(a)))
+
+    def smul(self, s, a):
+        return self._t(s * _np(a))
+
+    def rdiv(self, s, a):
+        return self._t(s / _np(a))
+
+    def sadd(self, a, s):
+        return self._t(_np(a) + s)
+
+    def rsub(self, s, a):
+        return self._t(s - _np(a))
+
+    def smin(self, a, s):
+        return self._t(np.minimum(_np(a), s))
+
+    def dot3(self, a, b):
+        A, B = _np(a).reshape(-1, 3), _np(b).reshape(-1, 3)
+        return self._t((A[:, 0] * B[:, 0] + A[:, 1] * B[:, 1]) + A[:, 2] * B[:, 2])
+
+    def gather(self, cells, f, nc=1):
+        return self._t(_np(f).reshape(-1, nc)[_np(cells)])
+
+
 class GamgAgglomeration:
     def __init__(self, addr, faceWeights, nCellsInCoarsestLevel=10, mergeLevels=1, forward=1):
         self.o = orc.Gamg(addr.o, faceWeights, nCellsInCoarsestLevel, mergeLevels=mergeLevels, forward=forward)
@@ -176,6 +232,34 @@ class _Capi:
     LduAddressing = LduAddressing
     LduMatrix = LduMatrix
     FvMatrix = FvMatrix
+    FieldOps = FieldOps
+
+    @staticmethod
+    def fv_convection_fill(addr, w, phi):
+        return tuple(FieldOps._t(x) for x in orc.convection_fill(addr.o, _np(w), _np(phi)))
+
+    @staticmethod
+    def fv_laplacian_fill(addr, delta, g):
+        return tuple(FieldOps._t(x) for x in orc.laplacian_fill(addr.o, _np(delta), _np(g)))
+
+    @staticmethod
+    def fv_interpolate_linear(addr, nc, w, vf):
+        return FieldOps._t(orc.interpolate_linear(addr.o, _np(w), _np(vf), nc))
+
+    @staticmethod
+    def fv_flux_linear(addr, Sf, w, U):
+        Uf = np.asarray(orc.interpolate_linear(addr.o, _np(w), _np(U), 3)).reshape(-1, 3)
+        S = _np(Sf).reshape(-1, 3)
+        return FieldOps._t((S[:, 0] * Uf[:, 0] + S[:, 1] * Uf[:, 1]) + S[:, 2] * Uf[:, 2])
+
+    @staticmethod
+    def fv_grad_linear(addr, nc, Sf, w, vf, bSf, bvf, V):
+        sf = orc.interpolate_linear(addr.o, _np(w), _np(vf), nc)
+        return FieldOps._t(orc.gauss_grad(addr.o, _np(Sf), np.asarray(sf).ravel(), addr.bfc, _np(bSf), _np(bvf), _np(V), nc))
+
+    @staticmethod
+    def fv_surface_integrate(addr, nc, ssf, bssf, V, divideByV=True, neiSign=-1):
+        return FieldOps._t(orc.surface_integrate(addr.o, _np(ssf), addr.bfc, _np(bssf), _np(V), nc, divideByV, neiSign))
 
     @staticmethod
     def fv_boundary_set(addr, bFaceCells):

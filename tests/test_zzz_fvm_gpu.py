@@ -186,3 +186,32 @@ def test_fvm_with_coupled_patches(gpu, meshmod, orc):
     np.testing.assert_allclose(host(Dz.psi, nc), psi_ref, rtol=0, atol=1e-8)
     Dz.mat.close()
     D.close()
+
+
+def test_icofoam_step_matches_oracle(gpu, meshmod, orc):
+    """the device icoFoam step (rapidcfd-dev_b200/icofoam.py over the C ABI) against the
+    oracle's step (oracle/piso_oracle.py) on the lid-driven cavity.  Same operator sequence, so everything except the
+    linear solves is bit for bit; the solves run to 1e-12 and the fields are compared at 1e-9."""
+    from oracle import piso_oracle as po
+    capi, ctx, torch = gpu
+    ico = importlib.import_module("rapidcfd-dev_b200.icofoam")
+    n = 8
+    m, ref = po.cavity_from_hex(orc, meshmod, n, nu=0.01)
+    m2, dev = ico.cavity(capi, ctx, torch, n, nu=0.01)
+    ctl = dict(tolerance=1e-12, relTol=0.0)
+    for step in range(3):
+        rp, rc = ref.step(nCorr=2, UControls=ctl, pControls=ctl)
+        dp_, dc = dev.step(nCorr=2, UControls=ctl, pControls=ctl)
+        assert len(dp_["U"]) == 3 and len(dp_["p"]) == len(rp["p"]) == 2
+        assert all(p.converged for p in dp_["U"]) and all(p.converged for p in dp_["p"])
+        for a, b in zip(dp_["p"], rp["p"]):
+            assert abs(a.nIterations - b.nIterations) <= 2
+        np.testing.assert_allclose(host(dev.U, 3), ref.U, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(host(dev.p), ref.p, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(host(dev.phi), ref.phi, rtol=0, atol=1e-11)
+        assert dc[-1][0] < 1e-10 and rc[-1][0] < 1e-10
+    # physics, on the device fields: the top layer follows the lid, mass is conserved
+    cc = m.cell_centres()
+    assert host(dev.U, 3)[cc[:, 1] > 1 - m.h, 0].mean() > 0.1
+    assert float(dev.div(dev.phi, dev.bphi).abs().max()) < 1e-7
+    dev.close()
