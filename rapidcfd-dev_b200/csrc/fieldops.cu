@@ -9,75 +9,10 @@
 // producing kernels is what csrc/fv.cu and csrc/fvmatrix.cu do for the heavy ones.
 #include "internal.h"
 
-namespace
-{
-enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_DIV = 3, OP_MIN = 4, OP_MAX = 5 };
-enum { UN_NEG = 0, UN_MAG = 1, UN_S_MUL = 2, UN_S_RDIV = 3, UN_S_ADD = 4, UN_S_RSUB = 5, UN_S_MIN = 6, UN_S_MAX = 7,
-       UN_S_SUB = 8, UN_S_DIV = 9, UN_COPY = 10 };
+#include "fieldops_kernels.cuh"
 
-__device__ __forceinline__ double bin(int op, double a, double b)
-{
-    switch (op) {
-    case OP_ADD: return __dadd_rn(a, b);
-    case OP_SUB: return __dsub_rn(a, b);
-    case OP_MUL: return __dmul_rn(a, b);
-    case OP_DIV: return __ddiv_rn(a, b);
-    case OP_MIN: return fmin(a, b);
-    default: return fmax(a, b);
-    }
-}
+using namespace fieldk;
 
-// out[i][k] = a[i][k or 0] op b[i][k or 0]; nc = components of the result
-__global__ void binary_kernel(long long n, int nc, int ncA, int ncB, int op, const double *a, const double *b, double *out)
-{
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * nc) return;
-    const long long e = i / nc;
-    const int k = (int)(i - e * nc);
-    const double x = a[ncA == 1 ? e : e * ncA + k], y = b[ncB == 1 ? e : e * ncB + k];
-    out[i] = bin(op, x, y);
-}
-
-__global__ void unary_kernel(long long n, int op, double s, const double *a, double *out)
-{
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double x = a[i];
-    double r;
-    switch (op) {
-    case UN_NEG: r = -x; break;
-    case UN_MAG: r = fabs(x); break;
-    case UN_S_MUL: r = __dmul_rn(s, x); break;
-    case UN_S_RDIV: r = __ddiv_rn(s, x); break;
-    case UN_S_ADD: r = __dadd_rn(x, s); break;
-    case UN_S_RSUB: r = __dsub_rn(s, x); break;
-    case UN_S_MIN: r = fmin(x, s); break;
-    case UN_S_MAX: r = fmax(x, s); break;
-    case UN_S_SUB: r = __dsub_rn(x, s); break;
-    case UN_S_DIV: r = __ddiv_rn(x, s); break;
-    default: r = x; break;
-    }
-    out[i] = r;
-}
-
-// Vector & Vector per element: (a.x*b.x + a.y*b.y) + a.z*b.z  (VectorI.H operator&)
-__global__ void dot3_kernel(long long n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out)
-{
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double s = __dadd_rn(__dmul_rn(a[3 * i], b[3 * i]), __dmul_rn(a[3 * i + 1], b[3 * i + 1]));
-    out[i] = __dadd_rn(s, __dmul_rn(a[3 * i + 2], b[3 * i + 2]));
-}
-
-// patchInternalField: out[i][k] = field[cells[i]][k]
-__global__ void gather_kernel(int n, int nc, const int *__restrict__ cells, const double *__restrict__ f, double *__restrict__ out)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * nc) return;
-    const int e = i / nc, k = i - e * nc;
-    out[i] = f[(size_t)cells[e] * nc + k];
-}
-} // namespace
 
 extern "C" int b200ldu_field_binary(b200ldu_ctx *ctx, int op, long long n, int ncA, const double *a_d, int ncB,
                                     const double *b_d, double *out_d)

@@ -1,0 +1,149 @@
+/*
+ * Host execution of the device code of csrc/fvmatrix.cu and csrc/fieldops.cu (their *_kernels.cuh headers): the CUDA
+ * qualifiers are defined away, the rounding intrinsics become plain fp64 operations (compiled with
+ * -ffp-contract=off, so each is one rounding as on the device) and a launcher loop sets blockIdx / threadIdx for
+ * every thread of the grid in turn.  TEST INFRASTRUCTURE ONLY: lets the CPU suite run the same kernel source
+ * against the oracle where no GPU is available.  It executes the kernels' index arithmetic, ordering and rounding;
+ * it does not exercise the launch code of the .cu files nor anything about the real device.
+ */
+#include <cmath>
+#include <cstddef>
+
+#define __global__
+#define __device__
+#define __forceinline__ inline
+struct Dim3 {
+    unsigned x, y, z;
+};
+static thread_local Dim3 blockIdx, blockDim, threadIdx;
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+using std::fabs;
+using std::fmax;
+using std::fmin;
+
+#include "fieldops_kernels.cuh"
+#include "fvmatrix_kernels.cuh"
+
+template <class K, class... A> static void launch(long long nThreads, int block, K k, A... args)
+{
+    const long long nBlocks = (nThreads + block - 1) / block;
+    blockDim = {(unsigned)block, 1, 1};
+    for (long long b = 0; b < nBlocks; b++)
+        for (int t = 0; t < block; t++) {
+            blockIdx = {(unsigned)b, 0, 0};
+            threadIdx = {(unsigned)t, 0, 0};
+            k(args...);
+        }
+}
+
+using namespace fvmk;
+
+extern "C" {
+struct HostCase { /* what csrc/fvmatrix.cu reads from the addressing and the matrix handle */
+    int nCells, nFaces, nB, nC;
+    const int *l, *u, *ownerStart, *losortStart, *losort;
+    const int *bStart, *bFaces, *bFaceCells, *cStart, *cFaces, *cFaceCells;
+    const double *diag, *upper, *lower, *couInt, *couBou;
+};
+
+static BoundaryLists lists(const HostCase *h)
+{
+    return BoundaryLists{h->nB ? h->bStart : nullptr, h->bFaces, h->nC ? h->cStart : nullptr, h->cFaces};
+}
+
+void hk_boundary_diag(const HostCase *h, int nc, int cmpt, const double *ic, const double *in, double *out)
+{
+    launch(h->nCells, 256, boundary_diag_kernel, h->nCells, lists(h), ic, nc, cmpt, h->couInt, in, out);
+}
+
+void hk_boundary_source(const HostCase *h, int nc, const double *bc, const double *pnf, const double *in, double *out)
+{
+    if (nc == 1)
+        launch(h->nCells, 256, boundary_source_kernel<1>, h->nCells, lists(h), bc, h->couBou, pnf, in, out);
+    else
+        launch(h->nCells, 256, boundary_source_kernel<3>, h->nCells, lists(h), bc, h->couBou, pnf, in, out);
+}
+
+void hk_component(const HostCase *h, int nc, int k, int withCoupled, const double *pnf, const double *in, double *out)
+{
+    BoundaryLists L = lists(h);
+    if (!withCoupled) L.cStart = nullptr;
+    launch(h->nCells, 256, component_kernel, h->nCells, nc, k, L, h->couBou, pnf, in, out);
+}
+
+void hk_set_component(const HostCase *h, int nc, int k, const double *in, double *out)
+{
+    launch(h->nCells, 256, set_component_kernel, h->nCells, nc, k, in, out);
+}
+
+void hk_A(const HostCase *h, int nc, const double *ic, const double *V, double *out)
+{
+    launch(h->nCells, 256, A_kernel, h->nCells, lists(h), ic, nc, h->couInt, h->diag, V, out);
+}
+
+void hk_H(const HostCase *h, int nc, const double *psi, const double *source, const double *bc, const double *pnf,
+          const double *V, double *out)
+{
+    if (nc == 1)
+        launch(h->nCells, 128, H_kernel<1>, h->nCells, h->ownerStart, h->u, h->losortStart, h->losort, h->l, h->upper,
+               h->lower, lists(h), bc, h->couBou, pnf, psi, source, V, out);
+    else
+        launch(h->nCells, 128, H_kernel<3>, h->nCells, h->ownerStart, h->u, h->losortStart, h->losort, h->l, h->upper,
+               h->lower, lists(h), bc, h->couBou, pnf, psi, source, V, out);
+}
+
+void hk_flux(const HostCase *h, int nc, const double *psi, const double *ic, const double *bc, const double *pnf,
+             double *flux, double *bflux, double *cflux)
+{
+    if (nc == 1) {
+        launch(h->nFaces, 256, flux_internal_kernel<1>, h->nFaces, h->l, h->u, h->upper, h->lower, psi, flux);
+        if (h->nB) launch(h->nB, 256, flux_boundary_kernel<1>, h->nB, h->bFaceCells, ic, 1, bc, 1, (const double *)nullptr, psi, bflux);
+        if (h->nC) launch(h->nC, 256, flux_boundary_kernel<1>, h->nC, h->cFaceCells, h->couInt, 1, h->couBou, 1, pnf, psi, cflux);
+    } else {
+        launch(h->nFaces, 256, flux_internal_kernel<3>, h->nFaces, h->l, h->u, h->upper, h->lower, psi, flux);
+        if (h->nB) launch(h->nB, 256, flux_boundary_kernel<3>, h->nB, h->bFaceCells, ic, 3, bc, 3, (const double *)nullptr, psi, bflux);
+        if (h->nC) launch(h->nC, 256, flux_boundary_kernel<3>, h->nC, h->cFaceCells, h->couInt, 1, h->couBou, 1, pnf, psi, cflux);
+    }
+}
+
+void hk_residual_source(const HostCase *h, const double *ic, const double *psi, const double *source, double *out)
+{
+    launch(h->nCells, 256, residual_source_kernel, h->nCells, lists(h), ic, h->couInt, psi, source, out);
+}
+
+void hk_relax(const HostCase *h, int nc, double alpha, const double *psi, const double *ic, double *diag, double *source)
+{
+    if (nc == 1)
+        launch(h->nCells, 128, relax_kernel<1>, h->nCells, h->ownerStart, h->losortStart, h->losort, h->upper, h->lower,
+               lists(h), ic, h->couInt, h->couBou, alpha, psi, diag, source);
+    else
+        launch(h->nCells, 128, relax_kernel<3>, h->nCells, h->ownerStart, h->losortStart, h->losort, h->upper, h->lower,
+               lists(h), ic, h->couInt, h->couBou, alpha, psi, diag, source);
+}
+
+void hk_set_reference(int cell, int nc, const double *v, double *diag, double *source)
+{
+    launch(1, 1, set_reference_kernel, cell, nc, v[0], nc > 1 ? v[1] : 0.0, nc > 2 ? v[2] : 0.0, diag, source);
+}
+
+void hk_field_binary(int op, long long n, int ncA, const double *a, int ncB, const double *b, double *out)
+{
+    const int nc = ncA > ncB ? ncA : ncB;
+    launch(n * nc, 256, fieldk::binary_kernel, n, nc, ncA, ncB, op, a, b, out);
+}
+
+void hk_field_unary(int op, long long n, double s, const double *a, double *out)
+{
+    launch(n, 256, fieldk::unary_kernel, n, op, s, a, out);
+}
+
+void hk_field_dot3(long long n, const double *a, const double *b, double *out) { launch(n, 256, fieldk::dot3_kernel, n, a, b, out); }
+
+void hk_field_gather(int n, int nc, const int *cells, const double *f, double *out)
+{
+    launch((long long)n * nc, 256, fieldk::gather_kernel, n, nc, cells, f, out);
+}
+}
