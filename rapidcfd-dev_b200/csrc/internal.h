@@ -198,10 +198,8 @@ struct b200ldu_matrix {
     double *d_valT = nullptr; // banded coefficients for Tmul   (aliases d_val when symmetric)
     double *d_valSh = nullptr; // shared-coefficient value stream (symmetric matrices)
     bool shared = false;       // Amul-type sweeps run on the shared-coefficient layout
-    bool valValid = false;     // general per-entry stream filled for the current coefficients
     double *d_diag = nullptr; // banded diagonal [nPad] (padding rows = 1)
-    double *d_rD = nullptr;   // 1/diag, built lazily per matrix_set
-    bool rDValid = false;
+    double *d_rD = nullptr;   // 1/diag, filled by matrix_set
     // caller-order pointers kept for faceH (caller owns)
     const double *upper_ext = nullptr, *lower_ext = nullptr, *diag_ext = nullptr, *bou_ext = nullptr,
                  *int_ext = nullptr;
