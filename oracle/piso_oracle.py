@@ -58,7 +58,10 @@ class Cavity:
         return np.asarray(self.orc.surface_integrate(self.addr, phi, self.bfc, bphi, self.V, 1))
 
     # ---- one time step: icoFoam.C:55-103 --------------------------------------------------------------
-    def step(self, nCorr=2, nNonOrthCorr=0, UControls=None, pControls=None, momentumPredictor=True):
+    def step(self, nCorr=2, nNonOrthCorr=0, UControls=None, pControls=None, momentumPredictor=True,
+             USolver=("PBiCG", "DILU"), pSolver=("PCG", "DIC"), gamg=None):
+        """USolver / pSolver: (solver, preconditioner or smoother) as fvSolution names them; gamg: the cached
+        agglomeration (orc.Gamg) when pSolver is GAMG"""
         orc = self.orc
         U0, phi0 = self.U.copy(), self.phi.copy()                    # oldTime fields
         rDeltaT = 1.0 / self.deltaT
@@ -88,7 +91,7 @@ class Cavity:
             gradP = self.grad(self.p, pb)
             src = source + self.V[:, None] * (-gradP)
             UEqn = fo.FvMatrix(orc, self.addr, 3, diag, upper, lower, src, self.U, self.V, self.bfc, ic, bc)
-            self.U, perfs["U"], _ = UEqn.solve("PBiCG", "DILU", **(UControls or dict(tolerance=1e-5, relTol=0.0)))
+            self.U, perfs["U"], _ = UEqn.solve(USolver[0], USolver[1], **(UControls or dict(tolerance=1e-5, relTol=0.0)))
         cont = []
         for corr in range(nCorr):
             UEqn = fo.FvMatrix(orc, self.addr, 3, diag, upper, lower, source, self.U, self.V, self.bfc, ic, bc)
@@ -109,7 +112,7 @@ class Cavity:
                 zero = np.zeros((len(self.bfc), 1))
                 pEqn = fo.FvMatrix(orc, self.addr, 1, pDiag, pUpper, None, pSource, self.p, self.V, self.bfc, zero, zero)
                 pEqn.setReference(self.pRefCell, self.pRefValue)
-                psi, perf, _ = pEqn.solve("PCG", "DIC", **(pControls or dict(tolerance=1e-6, relTol=0.0)))
+                psi, perf, _ = pEqn.solve(pSolver[0], pSolver[1], gamg, **(pControls or dict(tolerance=1e-6, relTol=0.0)))
                 self.p = psi[:, 0]
                 perfs.setdefault("p", []).append(perf[0])
                 if nonOrth == nNonOrthCorr:

@@ -57,8 +57,11 @@ class IcoFoam:
     def div(self, phi, bphi):
         return self.capi.fv_surface_integrate(self.addr, 1, phi, bphi, self.V, True, -1)
 
-    def step(self, nCorr=2, nNonOrthCorr=0, UControls=None, pControls=None, momentumPredictor=True):
-        """icoFoam.C:55-103; returns ({"U": [Perf x3], "p": [Perf per pressure solve]}, continuity errors)"""
+    def step(self, nCorr=2, nNonOrthCorr=0, UControls=None, pControls=None, momentumPredictor=True,
+             USolver=("PBiCG", "DILU"), pSolver=("PCG", "DIC"), gamg=None):
+        """icoFoam.C:55-103; returns ({"U": [Perf x3], "p": [Perf per pressure solve]}, continuity errors).
+        USolver / pSolver: (solver, preconditioner or smoother) as system/fvSolution names them; gamg: the cached
+        agglomeration (capi.GamgAgglomeration over self.addr) when pSolver is GAMG."""
         capi, o, a = self.capi, self.ops, self.addr
         U0, phi0 = self.U.clone(), self.phi.clone()
         rDeltaT = 1.0 / self.deltaT
@@ -83,7 +86,7 @@ class IcoFoam:
             # solve(UEqn == -fvc::grad(p))
             src = o.add(source, o.mul(self.V, o.neg(self.grad(self.p)), 1, 3))
             UEqn = capi.FvMatrix(self.matU, 3, diag, src, self.U, self.V, ic, bc)
-            perfs["U"] = UEqn.solve("PBiCG", "DILU", **(UControls or dict(tolerance=1e-5, relTol=0.0)))
+            perfs["U"] = UEqn.solve(USolver[0], USolver[1], **(UControls or dict(tolerance=1e-5, relTol=0.0)))
         cont = []
         for corr in range(nCorr):
             UEqn = capi.FvMatrix(self.matU, 3, diag, source, self.U, self.V, ic, bc)
@@ -103,7 +106,7 @@ class IcoFoam:
                 pEqn = capi.FvMatrix(self.matP, 1, pDiag, pSource, self.p, self.V, self.zeroB1, self.zeroB1)
                 self.matP.set(pDiag, pUpper)
                 pEqn.setReference(self.pRefCell, self.pRefValue)
-                perfs.setdefault("p", []).extend(pEqn.solve("PCG", "DIC", **(pControls or dict(tolerance=1e-6, relTol=0.0))))
+                perfs.setdefault("p", []).extend(pEqn.solve(pSolver[0], pSolver[1], gamg, **(pControls or dict(tolerance=1e-6, relTol=0.0))))
                 if nonOrth == nNonOrthCorr:
                     internal, boundary, _ = pEqn.flux(self.nB)
                     self.phi = o.sub(phiHbyA, internal)
@@ -135,3 +138,135 @@ def cavity(capi, ctx, torch, n, nu=0.01, deltaT=None, lid=(1.0, 0.0, 0.0)):
     return m, IcoFoam(capi, ctx, torch, m.nCells, m.lower, m.upper, m.Sf(), m.magSf(), m.weights(), m.deltaCoeffs(),
                       m.volumes(), bfc, bSf, np.full(nB, m.h * m.h), np.full(nB, 2.0 / m.h), Ub, nu, deltaT,
                       cellCentres=m.cell_centres())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# icoFoam on a case directory (SURVEY.md section 8(f) ranks 2 + 3): constant/polyMesh, constant/transportProperties,
+# system/controlDict, system/fvSolution and the start-time U, p as the reference's application reads them
+# (createFields.H, readPISOControls.H, createTime.H).  Supported: 3-D single-domain cases whose boundary patches are all
+# `fixedValue` for U and `zeroGradient` for p (the lid-driven cavity); anything else is refused by name.
+# ---------------------------------------------------------------------------------------------------------
+def _last_number(v):
+    """`nu nu [0 2 -1 0 0 0 0] 0.01;` / `nu [..] 0.01;` / `0.01` -> 0.01"""
+    if isinstance(v, (int, float)):
+        return float(v)
+    items = v if isinstance(v, (list, tuple)) else [v]
+    nums = [x for x in items if isinstance(x, (int, float)) and not isinstance(x, bool)]
+    if not nums:
+        raise ValueError(f"no number in {v!r}")
+    return float(nums[-1])
+
+
+def perf_line(pf, fieldName):
+    """solverPerformance::print (SolverPerformance.C:96-123)"""
+    nm = pf.solverName.decode() if isinstance(pf.solverName, bytes) else str(pf.solverName)
+    if pf.singular:
+        return f"{nm}:  Solving for {fieldName}:  solution singularity"
+    return (f"{nm}:  Solving for {fieldName}, Initial residual = {pf.initialResidual:g}, "
+            f"Final residual = {pf.finalResidual:g}, No Iterations {pf.nIterations}")
+
+
+def _time_name(t):
+    s = f"{t:.6g}"      # Time::timeName with the default precision 6
+    return s
+
+
+def load_case(capi, ctx, torch, caseDir):
+    """Build the IcoFoam object and the run controls from a case directory."""
+    import os
+    ff = importlib.import_module("rapidcfd-dev_b200.foamfile")
+    j = lambda *a: os.path.join(caseDir, *a)
+    control = ff.read_dict(j("system", "controlDict"))
+    fvSolution = ff.read_dict(j("system", "fvSolution"))
+    transport = ff.read_dict(j("constant", "transportProperties"))
+    pm = ff.read_poly_mesh(j("constant", "polyMesh"))
+    if pm.points is None:
+        raise ValueError("constant/polyMesh needs points and faces (geometry)")
+    if pm.coupled_patches():
+        raise NotImplementedError("icoFoam step: coupled (processor / cyclic) patches are not supported yet")
+    geo = pm.fv_geometry()
+    nI = pm.nInternalFaces
+    lower, upper = pm.ldu()
+    bfc = pm.boundary_face_cells()
+    startTime = _time_name(float(control.lookupOrDefault("startTime", 0)))
+    n = pm.nCells
+    Ufile = ff.read_field(j(startTime, "U"), nInternal=n)
+    pfile = ff.read_field(j(startTime, "p"), nInternal=n)
+    Ub = np.zeros((len(bfc), 3))
+    for p in pm.patches:
+        s = slice(p.startFace - nI, p.startFace - nI + p.nFaces)
+        ub, pb = Ufile["boundaryField"].get(p.name), pfile["boundaryField"].get(p.name)
+        if ub is None or pb is None:
+            raise KeyError(f"patch {p.name} has no entry in the boundaryField of U / p")
+        if str(ub["type"]) != "fixedValue" or str(pb["type"]) != "zeroGradient":
+            raise NotImplementedError(f"patch {p.name}: U {ub['type']} / p {pb['type']} -- this step supports "
+                                      "fixedValue U with zeroGradient p only")
+        Ub[s] = np.asarray(ub["value"], float).reshape(-1, 3) if np.ndim(ub["value"]) == 2 else np.asarray(ub["value"], float)
+    # boundary deltaCoeffs: 1/|Cf - C_owner| (surfaceInterpolation.C:300-340, fvPatch::delta)
+    bDelta = 1.0 / np.linalg.norm(geo["Cf"][nI:] - geo["C"][bfc], axis=1)
+    piso = fvSolution.subDict("PISO")
+    case = IcoFoam(capi, ctx, torch, n, lower, upper, geo["Sf"][:nI], geo["magSf"][:nI], geo["weights"], geo["deltaCoeffs"],
+                   geo["V"], bfc, geo["Sf"][nI:], geo["magSf"][nI:], bDelta, Ub, _last_number(transport.lookup("nu")),
+                   float(control.lookup("deltaT")), int(piso.lookupOrDefault("pRefCell", 0)),
+                   float(piso.lookupOrDefault("pRefValue", 0.0)), cellCentres=geo["C"])
+    case.U = case._t(Ufile["internalField"])
+    case.p = case._t(pfile["internalField"])
+    case.phi = capi.fv_flux_linear(case.addr, case.Sf, case.w, case.U)      # createPhi.H
+    us, up_, uc = ff.solver_controls(fvSolution, "U")
+    ps, pp, pc = ff.solver_controls(fvSolution, "p")
+    run = dict(startTime=float(control.lookupOrDefault("startTime", 0)), endTime=float(control.lookup("endTime")),
+               deltaT=float(control.lookup("deltaT")), nCorr=int(piso.lookupOrDefault("nCorrectors", 2)),
+               nNonOrthCorr=int(piso.lookupOrDefault("nNonOrthogonalCorrectors", 0)),
+               momentumPredictor=bool(ff._switch(piso.lookupOrDefault("momentumPredictor", "yes"))),
+               USolver=(us, up_), UControls=uc, pSolver=(ps, pp), pControls=pc, patches=pm.patches, nInternalFaces=nI,
+               Ufile=Ufile, pfile=pfile, polyMesh=pm, geometry=geo)
+    return case, run
+
+
+def run_case(capi, ctx, torch, caseDir, log=print, write=True, maxSteps=None):
+    """The time loop of icoFoam.C:48-110 on `caseDir`; prints the reference's log lines; writes U and p of the last
+    time step into <caseDir>/<time>/ when `write`.  Returns (case, list of per-step (perfs, continuity errors))."""
+    import os
+    ff = importlib.import_module("rapidcfd-dev_b200.foamfile")
+    case, run = load_case(capi, ctx, torch, caseDir)
+    gamg = None
+    if run["pSolver"][0] == "GAMG":
+        geo = run["geometry"]
+        Sf = geo["Sf"][:run["nInternalFaces"]]
+        mag = np.linalg.norm(Sf, axis=1)
+        wts = np.linalg.norm(Sf / np.sqrt(mag)[:, None] * np.array([1.0, 1.01, 1.02]), axis=1)   # faceAreaPair weights
+        gamg = capi.GamgAgglomeration(case.addr, wts, int(run["pControls"].get("nCellsInCoarsestLevel", 10)),
+                                      int(run["pControls"].get("mergeLevels", 1)))
+    nSteps = int(round((run["endTime"] - run["startTime"]) / run["deltaT"]))
+    if maxSteps is not None:
+        nSteps = min(nSteps, maxSteps)
+    history, cumulative, t = [], 0.0, run["startTime"]
+    log("\nStarting time loop\n")
+    for _ in range(nSteps):
+        t += run["deltaT"]
+        log(f"Time = {_time_name(t)}\n")
+        perfs, cont = case.step(run["nCorr"], run["nNonOrthCorr"], run["UControls"] or None, run["pControls"] or None,
+                                run["momentumPredictor"], run["USolver"], run["pSolver"], gamg)
+        for k, pf in enumerate(perfs.get("U", [])):
+            log(perf_line(pf, "U" + "xyz"[k]))
+        per = len(perfs["p"]) // max(run["nCorr"], 1)
+        for c in range(run["nCorr"]):
+            for pf in perfs["p"][c * per:(c + 1) * per]:
+                log(perf_line(pf, "p"))
+            cumulative += cont[c][1]
+            log(f"time step continuity errors : sum local = {cont[c][0]:g}, global = {cont[c][1]:g}, "
+                f"cumulative = {cumulative:g}")
+        history.append((perfs, cont))
+    if write and nSteps:
+        tdir = os.path.join(caseDir, _time_name(t))
+        os.makedirs(tdir, exist_ok=True)
+        U = case.U.cpu().numpy().reshape(-1, 3)
+        p = case.p.cpu().numpy()
+        ff.write_field(os.path.join(tdir, "U"), "volVectorField", [0, 1, -1, 0, 0, 0, 0], U,
+                       run["Ufile"]["boundaryField"], location=_time_name(t))
+        ff.write_field(os.path.join(tdir, "p"), "volScalarField", [0, 2, -2, 0, 0, 0, 0], p,
+                       run["pfile"]["boundaryField"], location=_time_name(t))
+    log("End\n")
+    if gamg is not None:
+        gamg.close()
+    return case, history

@@ -1,0 +1,95 @@
+"""SURVEY.md section 8(f) ranks 2 + 3 together, host side: `icofoam.run_case` reads an OpenFOAM case directory
+(polyMesh, transportProperties, controlDict, fvSolution, 0/U, 0/p), runs the time loop and writes the result.
+The device calls go to the oracle-backed stand-in (tests/oracle_backend.py), so this checks the case reading, the
+control flow and the log, not the CUDA path (tests/test_zzz_fvm_gpu.py holds that against the same oracle)."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+import oracle_backend
+from oracle import piso_oracle as po
+
+CONTROL = """FoamFile { version 2.0; format ascii; class dictionary; object controlDict; }
+application icoFoam; startFrom startTime; startTime 0; stopAt endTime; endTime %r; deltaT %r;
+writeControl timeStep; writeInterval 20;
+"""
+FVSOLUTION = """FoamFile { version 2.0; format ascii; class dictionary; object fvSolution; }
+solvers
+{
+    p { solver %s; %s tolerance 1e-12; relTol 0; }
+    U { solver PBiCG; preconditioner DILU; tolerance 1e-12; relTol 0; }
+}
+PISO { nCorrectors 2; nNonOrthogonalCorrectors 0; pRefCell 0; pRefValue 0; }
+"""
+TRANSPORT = """FoamFile { version 2.0; format ascii; class dictionary; object transportProperties; }
+nu nu [0 2 -1 0 0 0 0] 0.01;
+"""
+
+
+def write_cavity(ff, meshmod, root, n, psolver="PCG", psecond="preconditioner DIC;", steps=2):
+    m = meshmod.hex_mesh(n)
+    pm = ff.from_hex_mesh(m)
+    os.makedirs(os.path.join(root, "constant", "polyMesh"))
+    os.makedirs(os.path.join(root, "system"))
+    os.makedirs(os.path.join(root, "0"))
+    ff.write_poly_mesh(os.path.join(root, "constant", "polyMesh"), pm)
+    dt = 0.5 * m.h
+    open(os.path.join(root, "system", "controlDict"), "w").write(CONTROL % (steps * dt, dt))
+    open(os.path.join(root, "system", "fvSolution"), "w").write(FVSOLUTION % (psolver, psecond))
+    open(os.path.join(root, "constant", "transportProperties"), "w").write(TRANSPORT)
+    Ubf = {p.name: {"type": "fixedValue", "value": np.array([1.0, 0, 0]) if p.name == "movingWall" else np.zeros(3)}
+           for p in pm.patches}
+    pbf = {p.name: {"type": "zeroGradient"} for p in pm.patches}
+    ff.write_field(os.path.join(root, "0", "U"), "volVectorField", [0, 1, -1, 0, 0, 0, 0], np.zeros(3), Ubf)
+    ff.write_field(os.path.join(root, "0", "p"), "volScalarField", [0, 2, -2, 0, 0, 0, 0], 0.0, pbf)
+    return m, dt
+
+
+@pytest.mark.parametrize("psolver,psecond", [("PCG", "preconditioner DIC;"), ("GAMG", "smoother GaussSeidel; nCellsInCoarsestLevel 10; mergeLevels 1; agglomerator faceAreaPair;")])
+def test_run_case_reads_the_case_and_matches_the_oracle_step(meshmod, orc, tmp_path, psolver, psecond):
+    ff = importlib.import_module("rapidcfd-dev_b200.foamfile")
+    ico = importlib.import_module("rapidcfd-dev_b200.icofoam")
+    n = 6
+    root = str(tmp_path / "cavity")
+    m, dt = write_cavity(ff, meshmod, root, n, psolver, psecond)
+    capi, ctx, torch = oracle_backend.fixture()
+    lines = []
+    case, hist = ico.run_case(capi, ctx, torch, root, log=lines.append)
+    assert len(hist) == 2
+    # the same two steps straight on the oracle with the analytic hex geometry
+    _, ref = po.cavity_from_hex(orc, meshmod, n, nu=0.01, deltaT=dt)
+    ctl = dict(tolerance=1e-12, relTol=0.0)
+    for _ in range(2):
+        ref.step(UControls=ctl, pControls=ctl)
+    U = case.U.numpy().reshape(-1, 3)
+    np.testing.assert_allclose(U, ref.U, rtol=0, atol=1e-8)
+    np.testing.assert_allclose(case.p.numpy(), ref.p, rtol=0, atol=1e-8)
+    # the log carries the reference's lines: one per velocity component, two pressure solves and a continuity line per step
+    text = "\n".join(lines)
+    assert text.count("Solving for Ux") == 2 and text.count("Solving for p") == 4
+    assert text.count("time step continuity errors") == 4 and "Time = " in text and lines[-1].startswith("End")
+    name = "GAMG" if psolver == "GAMG" else "AINVPCG"
+    assert f"{name}:  Solving for p, Initial residual" in text and "AINVPBiCG:  Solving for Ux" in text
+    # the last time directory holds U and p as field files that read back
+    tdir = os.path.join(root, ico._time_name(2 * dt))
+    Uf = ff.read_field(os.path.join(tdir, "U"))
+    pf = ff.read_field(os.path.join(tdir, "p"))
+    np.testing.assert_allclose(Uf["internalField"], U, rtol=1e-15)
+    np.testing.assert_allclose(pf["internalField"], case.p.numpy(), rtol=1e-15)
+    assert str(Uf["boundaryField"]["movingWall"]["type"]) == "fixedValue"
+
+
+def test_run_case_refuses_what_the_step_does_not_cover(meshmod, tmp_path):
+    ff = importlib.import_module("rapidcfd-dev_b200.foamfile")
+    ico = importlib.import_module("rapidcfd-dev_b200.icofoam")
+    root = str(tmp_path / "c")
+    write_cavity(ff, meshmod, root, 4)
+    pm = ff.read_poly_mesh(os.path.join(root, "constant", "polyMesh"))
+    pbf = {p.name: {"type": "zeroGradient"} for p in pm.patches}
+    pbf["movingWall"] = {"type": "fixedValue", "value": 0.0}
+    ff.write_field(os.path.join(root, "0", "p"), "volScalarField", [0, 2, -2, 0, 0, 0, 0], 0.0, pbf)
+    capi, ctx, torch = oracle_backend.fixture()
+    with pytest.raises(NotImplementedError, match="movingWall"):
+        ico.run_case(capi, ctx, torch, root, log=lambda s: None)

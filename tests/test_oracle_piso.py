@@ -50,3 +50,18 @@ def test_pressure_correction_projects_the_flux(meshmod, orc):
     its = [p.nIterations for p in perfs["p"]]
     assert its[-1] <= its[0]
     assert np.abs(case.U - U_before).max() < 0.2                  # a time step changes the field smoothly
+
+
+def test_gamg_pressure_solver_gives_the_same_step(meshmod, orc):
+    """fvSolution `p { solver GAMG; smoother GaussSeidel; }`: the step is the same to the solvers' tolerance"""
+    n = 8
+    m, a = po.cavity_from_hex(orc, meshmod, n)
+    _, b = po.cavity_from_hex(orc, meshmod, n)
+    g = orc.Gamg(b.addr, meshmod.face_area_pair_weights(m), 10)
+    ctl = dict(tolerance=1e-12, relTol=0.0)
+    for _ in range(2):
+        a.step(UControls=ctl, pControls=ctl)
+        perfs, _ = b.step(UControls=ctl, pControls=dict(ctl, maxIter=200), pSolver=("GAMG", "GaussSeidel"), gamg=g)
+        assert all(p.converged for p in perfs["p"]) and perfs["p"][0].solverName == b"GAMG"
+    np.testing.assert_allclose(b.U, a.U, atol=1e-9)
+    np.testing.assert_allclose(b.p, a.p, atol=1e-9)

@@ -215,3 +215,30 @@ def test_icofoam_step_matches_oracle(gpu, meshmod, orc):
     assert host(dev.U, 3)[cc[:, 1] > 1 - m.h, 0].mean() > 0.1
     assert float(dev.div(dev.phi, dev.bphi).abs().max()) < 1e-7
     dev.close()
+
+
+@pytest.mark.parametrize("psolver,psecond", [("PCG", "preconditioner DIC;"),
+                                             ("GAMG", "smoother GaussSeidel; nCellsInCoarsestLevel 10; mergeLevels 1;")])
+def test_icofoam_case_directory_on_the_device(gpu, meshmod, orc, tmp_path, psolver, psecond):
+    """icofoam.run_case on a written cavity case (polyMesh + dictionaries + 0/U, 0/p), device fields, against the
+    oracle's steps; the pressure solver comes from system/fvSolution (PCG+DIC or GAMG+GaussSeidel)."""
+    from oracle import piso_oracle as po
+    from test_icofoam_case_cpu import write_cavity
+    capi, ctx, torch = gpu
+    ff = importlib.import_module("rapidcfd-dev_b200.foamfile")
+    ico = importlib.import_module("rapidcfd-dev_b200.icofoam")
+    n = 8
+    root = str(tmp_path / "cavity")
+    m, dt = write_cavity(ff, meshmod, root, n, psolver, psecond, steps=2)
+    lines = []
+    case, hist = ico.run_case(capi, ctx, torch, root, log=lines.append)
+    _, ref = po.cavity_from_hex(orc, meshmod, n, nu=0.01, deltaT=dt)
+    ctl = dict(tolerance=1e-12, relTol=0.0)
+    for _ in range(2):
+        ref.step(UControls=ctl, pControls=ctl)
+    np.testing.assert_allclose(host(case.U, 3), ref.U, rtol=0, atol=1e-8)
+    np.testing.assert_allclose(host(case.p), ref.p, rtol=0, atol=1e-8)
+    text = "\n".join(lines)
+    assert text.count("Solving for p") == 4 and ("GAMG:" in text) == (psolver == "GAMG")
+    assert all(c[0] < 1e-9 for _, cont in hist for c in cont)
+    case.close()
