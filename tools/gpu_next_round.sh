@@ -17,5 +17,19 @@ ncu --set full --clock-control none --import-source on \
 ncu --set full --clock-control none --import-source on \
     -k regex:"restrict_kernel|prolong_kernel|agg_diag_kernel|agg_faces_kernel|dense_apply" \
     -c 16 -f -o gpurun_out/r02a_gamg python bench_kernels.py --n 64 --reps 1 > gpurun_out/r02a_ncu_gamg.log 2>&1
+# section 8(f) rank 2: a 64^3 cavity, 5 steps, log + wall time
+python - > gpurun_out/r02a_icofoam.log 2>&1 <<'PY'
+import importlib, sys, time, tempfile, os
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+import torch
+from test_icofoam_case_cpu import write_cavity
+ff = importlib.import_module("rapidcfd-dev_b200.foamfile"); meshmod = importlib.import_module("rapidcfd-dev_b200.mesh")
+capi = importlib.import_module("rapidcfd-dev_b200.capi"); ico = importlib.import_module("rapidcfd-dev_b200.icofoam")
+root = os.path.join(tempfile.mkdtemp(), "cavity")
+write_cavity(ff, meshmod, root, 64, steps=5)
+ctx = capi.Context(0)
+t0 = time.perf_counter(); case, hist = ico.run_case(capi, ctx, torch, root); torch.cuda.synchronize()
+print("icoFoam 64^3, 5 steps:", time.perf_counter() - t0, "s wall (incl. case reading and layout build)")
+PY
 cat gpurun_out/r02a_tests.log gpurun_out/r02a_fvm_tests.log gpurun_out/r02a_smoke.log | tail -40
 cut -c1-300 gpurun_out/r02a_bench_ref.json gpurun_out/r02a_bench_n1.json
