@@ -234,6 +234,10 @@ int b200ldu_fv_add_boundary_source(b200ldu_addr *a, const double *boundaryCoeffs
  *   solve                solveSegregated: scalar fvScalarMatrix.C:142-192, vector component loop
  *                        fvMatrixSolve.C:104-226; perf[nComp]; the matrix is re-pointed at a folded diagonal for
  *                        the solve and back at the caller's arrays afterwards (saveDiag) */
+/* patchNeighbourField of all coupled patch faces of a caller-order field (coupledFvPatchField::patchNeighbourField:
+ * processorFvPatchField.C:196-262 exchange with the neighbour rank, cyclicFvPatchField.C:133-160 partner patch);
+ * pnf_d [nCoupledFaces*nComp] in the order of b200ldu_addr_create's faceCells */
+int b200ldu_fv_patch_neighbour_field(b200ldu_addr *a, int nComp, const double *field_d, double *pnf_d);
 int b200ldu_fvm_add_boundary_diag(b200ldu_matrix *m, int nComp, int cmpt, const double *internalCoeffs_d,
                                   const double *diagIn_d, double *diagOut_d);
 int b200ldu_fvm_add_boundary_source(b200ldu_matrix *m, int nComp, const double *boundaryCoeffs_d,

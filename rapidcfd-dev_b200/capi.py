@@ -65,7 +65,7 @@ EXPORTS = [
     "b200ldu_fv_flux_linear",
     "b200ldu_fvm_add_boundary_diag", "b200ldu_fvm_add_boundary_source", "b200ldu_fvm_A", "b200ldu_fvm_H",
     "b200ldu_fvm_flux", "b200ldu_fvm_residual", "b200ldu_fvm_relax", "b200ldu_fvm_set_reference",
-    "b200ldu_fvm_solve",
+    "b200ldu_fvm_solve", "b200ldu_fv_patch_neighbour_field",
     "b200ldu_field_binary", "b200ldu_field_unary", "b200ldu_field_dot3", "b200ldu_field_gather",
 ]
 
@@ -140,6 +140,7 @@ def lib():
     L.b200ldu_fvm_residual.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.b200ldu_fvm_relax.argtypes = [vp, C.c_int, C.c_double, vp, vp, vp, vp]
     L.b200ldu_fvm_set_reference.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    L.b200ldu_fv_patch_neighbour_field.argtypes = [vp, C.c_int, vp, vp]
     L.b200ldu_field_binary.argtypes = [vp, C.c_int, C.c_longlong, C.c_int, vp, C.c_int, vp, vp]
     L.b200ldu_field_unary.argtypes = [vp, C.c_int, C.c_longlong, C.c_double, vp, vp]
     L.b200ldu_field_dot3.argtypes = [vp, C.c_longlong, vp, vp, vp]
@@ -570,6 +571,13 @@ def fv_surface_integrate(addr, nComp, ssf, bssf, V, divideByV=True, neiSign=-1):
     out = _newlike(ssf, addr.nCells * nComp)
     check(lib().b200ldu_fv_surface_integrate(addr.h, nComp, _dp(ssf), _dp(bssf), _dp(V), _dp(out), int(divideByV), neiSign))
     return out
+
+
+def fv_patch_neighbour_field(addr, nComp, field):
+    """coupledFvPatchField::patchNeighbourField of every coupled patch face (processor: exchanged, cyclic: partner)"""
+    pnf = _newlike(field, max(addr.nPatchFaces * nComp, 1))
+    check(lib().b200ldu_fv_patch_neighbour_field(addr.h, nComp, _dp(field), _dp(pnf)))
+    return pnf[: addr.nPatchFaces * nComp]
 
 
 def fv_boundary_set(addr, bFaceCells):

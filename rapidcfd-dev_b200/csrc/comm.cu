@@ -387,3 +387,37 @@ int comm_allgather_dev(b200ldu_ctx *ctx, const double *d_mine, int n, double *d_
     NCCL_TRY(ncclAllGather(d_mine, d_all, n, ncclDouble, (ncclComm_t)ctx->nccl, ctx->stream));
     return B200LDU_OK;
 }
+
+// coupled-patch exchange of a caller-order field (processorFvPatchField::initEvaluate / evaluate,
+// processorFvPatchField.C:196-262; cyclic: cyclicFvPatchField::patchNeighbourField, :133-160): send_d holds the
+// patchInternalField of every coupled face (nComp values each, patches concatenated), recv_d receives the
+// neighbour's.  In stream; processor patches through one NCCL group, cyclic pairs by a device copy.
+int comm_exchange_patch_field(b200ldu_addr *a, int nComp, const double *send_d, double *recv_d)
+{
+    b200ldu_ctx *ctx = a->ctx;
+    bool remote = false;
+    for (int p = 0; p < a->nPatches; p++) {
+        const int s = a->patchStart[p], n = a->patchStart[p + 1] - s, nb = a->neighbRank[p];
+        if (nb >= 0) {
+            remote = true;
+            continue;
+        }
+        const int q = -nb - 1; // validated at addr_create
+        CUDA_TRY(cudaMemcpyAsync(recv_d + (size_t)s * nComp, send_d + (size_t)a->patchStart[q] * nComp,
+                                 sizeof(double) * (size_t)n * nComp, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (!remote) return B200LDU_OK;
+    if (!ctx->nccl) {
+        b200_set_error("patch field exchange: processor patches present but no communicator (b200ldu_comm_init)");
+        return B200LDU_ENCCL;
+    }
+    NCCL_TRY(ncclGroupStart());
+    for (int p = 0; p < a->nPatches; p++) {
+        const int s = a->patchStart[p], n = a->patchStart[p + 1] - s, nb = a->neighbRank[p];
+        if (nb < 0) continue;
+        NCCL_TRY(ncclSend(send_d + (size_t)s * nComp, (size_t)n * nComp, ncclDouble, nb, (ncclComm_t)ctx->nccl, ctx->stream));
+        NCCL_TRY(ncclRecv(recv_d + (size_t)s * nComp, (size_t)n * nComp, ncclDouble, nb, (ncclComm_t)ctx->nccl, ctx->stream));
+    }
+    NCCL_TRY(ncclGroupEnd());
+    return B200LDU_OK;
+}

@@ -10,3 +10,4 @@ int comm_exchange_patch_ints(b200ldu_ctx *ctx, int nPatches, const int *patchSta
                              const int *send, int *recv);
 int comm_allgather_host(b200ldu_ctx *ctx, const double *mine, int n, double *all);
 int comm_allgather_dev(b200ldu_ctx *ctx, const double *d_mine, int n, double *d_all);
+int comm_exchange_patch_field(b200ldu_addr *a, int nComp, const double *send_d, double *recv_d);

@@ -6,6 +6,8 @@
 
 namespace fieldk
 {
+namespace // internal linkage: the headers are included by more than one translation unit
+{
 enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_DIV = 3, OP_MIN = 4, OP_MAX = 5 };
 enum { UN_NEG = 0, UN_MAG = 1, UN_S_MUL = 2, UN_S_RDIV = 3, UN_S_ADD = 4, UN_S_RSUB = 5, UN_S_MIN = 6, UN_S_MAX = 7,
        UN_S_SUB = 8, UN_S_DIV = 9, UN_COPY = 10 };
@@ -72,5 +74,6 @@ __global__ void gather_kernel(int n, int nc, const int *__restrict__ cells, cons
     const int e = i / nc, k = i - e * nc;
     out[i] = f[(size_t)cells[e] * nc + k];
 }
+} // namespace
 } // namespace fieldk
 #endif

@@ -17,8 +17,10 @@
 // are bit-comparable with the oracle.
 #include <algorithm>
 
-#include "internal.h"
+#include "comm.h"
+#include "fieldops_kernels.cuh"
 #include "fvmatrix_kernels.cuh"
+#include "internal.h"
 
 using namespace fvmk;
 
@@ -76,6 +78,24 @@ int need_boundary(const b200ldu_addr *a, const void *ic, const char *what)
     return B200LDU_OK;
 }
 } // namespace
+
+// patchNeighbourField of every coupled patch face (what the fvm_* calls take as pnf_d): the patchInternalField is
+// gathered, processor patches exchange it with their neighbour rank, cyclic patches read their partner patch
+extern "C" int b200ldu_fv_patch_neighbour_field(b200ldu_addr *a, int nComp, const double *field_d, double *pnf_d)
+{
+    if (!a || !field_d || bad_nc(nComp)) return B200LDU_EINVAL;
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    TRY(coupled_lists(a));
+    if (a->nCFaces == 0) return B200LDU_OK;
+    if (!pnf_d) return B200LDU_EINVAL;
+    double *send = nullptr;
+    TRY(scratch(a, 3, (size_t)a->nCFaces * nComp, &send));
+    fieldk::gather_kernel<<<grid(a->nCFaces * nComp, 256), 256, 0, a->ctx->stream>>>(a->nCFaces, nComp, a->d_cFaceCells,
+                                                                                      field_d, send);
+    a->ctx->launches++;
+    KERNEL_CHECK();
+    return comm_exchange_patch_field(a, nComp, send, pnf_d);
+}
 
 extern "C" int b200ldu_fvm_add_boundary_diag(b200ldu_matrix *m, int nComp, int cmpt, const double *internalCoeffs_d,
                                              const double *diagIn_d, double *diagOut_d)

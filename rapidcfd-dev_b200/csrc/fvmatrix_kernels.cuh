@@ -7,6 +7,8 @@
 
 namespace fvmk
 {
+namespace // internal linkage: the headers are included by more than one translation unit
+{
 struct BoundaryLists { // per-cell CSR over the non-coupled boundary faces and over the coupled patch faces
     const int *bStart, *bFaces, *cStart, *cFaces;
 };
@@ -257,5 +259,6 @@ __global__ void set_reference_kernel(int cell, int nc, double v0, double v1, dou
         source[(size_t)cell * nc + k] = __dadd_rn(source[(size_t)cell * nc + k], __dmul_rn(d, v[k]));
     diag[cell] = __dmul_rn(2.0, d);
 }
+} // namespace
 } // namespace fvmk
 #endif

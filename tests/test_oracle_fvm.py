@@ -164,14 +164,11 @@ def test_set_reference_and_relax(meshmod, orc):
     assert f4.diag[7] == 2 * d["diag"][7]
 
 
-@pytest.mark.parametrize("nR", [2, 4])
-def test_decomposed_glue_matches_single_domain(meshmod, orc, nR):
-    """Coupled patches: solve, H, flux and residual of the decomposed case reproduce the single domain."""
-    n = 8
+def decomposed_global(meshmod, orc, n):
+    """-laplacian(gamma, U) of a vector with fixedValue walls on the single n^3 domain (the data every rank cuts from)"""
     gm = meshmod.hex_mesh(n)
     rng = np.random.default_rng(9)
     gamma = rng.uniform(0.5, 1.5, gm.nFaces)
-    ga = orc.Addr(gm.nCells, gm.lower, gm.upper)
     upper = -(gm.deltaCoeffs() * (gamma * gm.magSf()))
     diag = np.zeros(gm.nCells)
     np.subtract.at(diag, gm.lower, upper)
@@ -182,67 +179,89 @@ def test_decomposed_glue_matches_single_domain(meshmod, orc, nR):
     gd = dict(diag=diag, upper=upper, lower=None, source=rng.uniform(-1, 1, (gm.nCells, 3)) * gm.h ** 3, bfc=bfc,
               ic=-ic, bc=-bc, V=gm.volumes())
     x = rng.uniform(-1, 1, (gm.nCells, 3))
+    fkey = {(int(l), int(u)): f for f, (l, u) in enumerate(zip(gm.lower, gm.upper))}
+    wkey, off = {}, 0
+    for p in gm.wall_patches():
+        for i, c in enumerate(p.faceCells):
+            wkey[(int(c), p.name)] = off + i
+        off += len(p.faceCells)
+    return dict(gm=gm, gd=gd, x=x, upper=upper, fkey=fkey, wkey=wkey, n=n)
+
+
+def decomposed_rank(meshmod, G, nR, r):
+    """rank r's cut of decomposed_global: (mesh, fvMatrix arrays, coupled coefficient per coupled face).  A coupled face
+    carries internalCoeffs = -upper_f (what the missing neighbour row would have put on the diagonal) and
+    boundaryCoeffs = -upper_f (Amul subtracts boundaryCoeffs*psi_nbr)."""
+    gm, gd, upper, fkey, wkey = G["gm"], G["gd"], G["upper"], G["fkey"], G["wkey"]
+    m = meshmod.decompose(G["n"], nR, r)
+    cg = m.cellGlobal
+    gl = np.array([fkey[(int(cg[l]), int(cg[u]))] for l, u in zip(m.lower, m.upper)])
+    cou = []
+    for p in m.coupled_patches():
+        mine, theirs = cg[p.faceCells], p.nbrGlobalCells
+        cou.append(np.array([upper[fkey[(min(int(i), int(j)), max(int(i), int(j)))]] for i, j in zip(mine, theirs)]))
+    cou = np.concatenate(cou)
+    d0 = np.zeros(m.nCells)
+    np.subtract.at(d0, m.lower, upper[gl])
+    np.subtract.at(d0, m.upper, upper[gl])
+    wsel = np.array([wkey[(int(cg[c]), p.name)] for p in m.wall_patches() for c in p.faceCells], int)
+    wb = np.concatenate([p.faceCells for p in m.wall_patches()]).astype(np.int32)
+    d = dict(diag=d0, upper=upper[gl], lower=None, source=gd["source"][cg], bfc=wb, ic=gd["ic"][wsel],
+             bc=gd["bc"][wsel], V=gm.volumes()[cg])
+    return m, d, cou
+
+
+def oracle_rank_results(meshmod, orc, G, nR, ctl):
+    """what every rank's oracle FvMatrix produces (threads): list of dicts, one per rank"""
+    ex = dh.ThreadExchange(nR)
+    x, n = G["x"], G["n"]
+
+    def rank_fn(r):
+        m, d, cou = decomposed_rank(meshmod, G, nR, r)
+        cg = m.cellGlobal
+        ps, fc = m.patch_start_facecells()
+        a = orc.Addr(m.nCells, m.lower, m.upper, ps, fc, neighbRank=[p.neighbRank for p in m.coupled_patches()])
+        kw = dict(couInt=-cou, couBou=-cou, comm=ex.comm(orc, r, m, n ** 3))
+        f = make(orc, a, d, 3, x[cg], **kw)
+        pnf = f.patchNeighbourField()
+        H, Aphi = f.H(), f.A()
+        internal, boundary, coupled = f.flux()
+        fz = make(orc, a, d, 3, **kw)
+        psi, perfs, _ = fz.solve("PCG", "DIC", **ctl)
+        fsc = make(orc, a, dict(d, source=d["source"][:, 0], ic=d["ic"][:, :1], bc=d["bc"][:, :1]), 1, x[cg][:, :1], **kw)
+        return dict(cg=cg, H=H, A=Aphi, psi=psi, res=fsc.residual(), internal=internal, boundary=boundary,
+                    coupled=coupled, pnf=pnf, conv=[p.converged for p in perfs], nIter=[p.nIterations for p in perfs],
+                    cou=cou, m=m)
+    return dh.run_threads(nR, rank_fn)
+
+
+@pytest.mark.parametrize("nR", [2, 4])
+def test_decomposed_glue_matches_single_domain(meshmod, orc, nR):
+    """Coupled patches: solve, H, flux and residual of the decomposed case reproduce the single domain."""
+    G = decomposed_global(meshmod, orc, 8)
+    gm, gd, x = G["gm"], G["gd"], G["x"]
+    ga = orc.Addr(gm.nCells, gm.lower, gm.upper)
     gf = make(orc, ga, gd, 3, x)
     gH, gA = gf.H(), gf.A()
     gpsi, _, _ = make(orc, ga, gd, 3).solve("PCG", "DIC", tolerance=1e-13, maxIter=800)
     gs = make(orc, ga, dict(gd, source=gd["source"][:, 0], ic=gd["ic"][:, :1], bc=gd["bc"][:, :1]), 1, x[:, :1])
     gres = gs.residual()
-    # global face -> coefficient, wall face (cell, direction) -> coefficients
-    fkey = {(int(l), int(u)): f for f, (l, u) in enumerate(zip(gm.lower, gm.upper))}
-    wkey = {}
-    off = 0
-    for p in gm.wall_patches():
-        for i, c in enumerate(p.faceCells):
-            wkey[(int(c), p.name)] = off + i
-        off += len(p.faceCells)
-    ex = dh.ThreadExchange(nR)
-
-    def rank_fn(r):
-        m = meshmod.decompose(n, nR, r)
-        cg = m.cellGlobal
-        gl = np.array([fkey[(int(cg[l]), int(cg[u]))] for l, u in zip(m.lower, m.upper)])
-        ps, fc = m.patch_start_facecells()
-        a = orc.Addr(m.nCells, m.lower, m.upper, ps, fc, neighbRank=[p.neighbRank for p in m.coupled_patches()])
-        cou = []
-        for p in m.coupled_patches():
-            mine, theirs = cg[p.faceCells], p.nbrGlobalCells
-            cou.append(np.array([upper[fkey[(min(int(i), int(j)), max(int(i), int(j)))]] for i, j in zip(mine, theirs)]))
-        cou = np.concatenate(cou)
-        d0 = np.zeros(m.nCells)
-        np.subtract.at(d0, m.lower, upper[gl])
-        np.subtract.at(d0, m.upper, upper[gl])
-        # a coupled face carries internalCoeffs = -upper_f (what the missing neighbour row would have put on the
-        # diagonal) and boundaryCoeffs = -upper_f (Amul subtracts boundaryCoeffs*psi_nbr)
-        wsel = np.array([wkey[(int(cg[c]), p.name)] for p in m.wall_patches() for c in p.faceCells], int)
-        wb = np.concatenate([p.faceCells for p in m.wall_patches()]).astype(np.int32)
-        comm = ex.comm(orc, r, m, n ** 3)
-        kw = dict(couInt=-cou, couBou=-cou, comm=comm)
-        d = dict(diag=d0, upper=upper[gl], lower=None, source=gd["source"][cg], bfc=wb, ic=gd["ic"][wsel],
-                 bc=gd["bc"][wsel], V=gm.volumes()[cg])
-        f = make(orc, a, d, 3, x[cg], **kw)
-        H, Aphi = f.H(), f.A()
-        internal, boundary, coupled = f.flux()
-        psi, perfs, _ = make(orc, a, d, 3, **kw).solve("PCG", "DIC", tolerance=1e-13, maxIter=800)
-        fsc = make(orc, a, dict(d, source=d["source"][:, 0], ic=d["ic"][:, :1], bc=d["bc"][:, :1]), 1, x[cg][:, :1], **kw)
-        return cg, H, Aphi, psi, fsc.residual(), coupled, [p.converged for p in perfs], cou, m
-    res = dh.run_threads(nR, rank_fn)
-    for cg, H, Aphi, psi, rres, coupled, conv, cou, m in res:
-        assert all(conv)
-        np.testing.assert_allclose(H, gH[cg], rtol=1e-11, atol=1e-11)
-        np.testing.assert_allclose(Aphi, gA[cg], rtol=1e-13)
-        np.testing.assert_allclose(psi, gpsi[cg], rtol=0, atol=1e-9)
+    for R in oracle_rank_results(meshmod, orc, G, nR, dict(tolerance=1e-13, maxIter=800)):
+        cg, m, cou = R["cg"], R["m"], R["cou"]
+        assert all(R["conv"])
+        np.testing.assert_allclose(R["H"], gH[cg], rtol=1e-11, atol=1e-11)
+        np.testing.assert_allclose(R["A"], gA[cg], rtol=1e-13)
+        np.testing.assert_allclose(R["psi"], gpsi[cg], rtol=0, atol=1e-9)
         # fvScalarMatrix.C:195-240 counts the coupled neighbour term twice: once inside lduMatrix::residual (the
         # interface update) and once more in addBoundarySource(res) whose `couples` defaults to true -- as written
         extra = np.zeros(len(cg))
         nbr = np.concatenate([p.nbrGlobalCells for p in m.coupled_patches()])
         np.add.at(extra, np.concatenate([p.faceCells for p in m.coupled_patches()]), (-cou) * x[nbr, 0])
-        np.testing.assert_allclose(rres, gres[cg] + extra, rtol=1e-11, atol=1e-11)
-        # flux through a processor face = the single-domain face flux, outward from this rank
+        np.testing.assert_allclose(R["res"], gres[cg] + extra, rtol=1e-11, atol=1e-11)
+        assert np.array_equal(R["pnf"], x[nbr])
+        # flux through a processor face: internalCoeffs*psi_i - boundaryCoeffs*psi_j
         k = 0
         for p in m.coupled_patches():
-            mine, theirs = m.cellGlobal[p.faceCells], p.nbrGlobalCells
-            for i, j in zip(mine, theirs):
-                ref = -cou[k] * (x[j] - x[i]) * -1.0             # internalCoeffs*psi_i - boundaryCoeffs*psi_j
-                np.testing.assert_allclose(coupled[k], (-cou[k]) * x[i] - (-cou[k]) * x[j], rtol=1e-13)
-                assert ref.shape == (3,)
+            for i, j in zip(m.cellGlobal[p.faceCells], p.nbrGlobalCells):
+                np.testing.assert_allclose(R["coupled"][k], (-cou[k]) * x[i] - (-cou[k]) * x[j], rtol=1e-13)
                 k += 1

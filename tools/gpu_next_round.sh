@@ -1,6 +1,8 @@
 # First GPU call of the next round (1 GPU, ~6 min of box time): everything written after the round-1 GPU
 # budget ran out gets its first run on a B200, and the kernels that only have CUDA-event numbers get ncu captures.
 #   gpurun --timeout 900 -- 'bash tools/gpu_next_round.sh'
+# then, on 2 GPUs (the glue over processor patches):
+#   gpurun --gpus 2 --timeout 600 -- 'python -m pytest tests/test_zzz_fvm_gpu.py tests/test_gpu_multi.py -m gpu -q -k "multi_gpu" 2>&1 | tail -15'
 set -x
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -15 > gpurun_out/r02a_tests.log
