@@ -158,6 +158,12 @@ double *orc_halo_exchange(const orc_addr *a, const double *psi, const orc_comm *
     return recv;
 }
 
+/* reduce(v, sumOp) over the ranks, for tests that compose the oracle from Python */
+void orc_comm_sum(const orc_comm *comm, double *vals, int n)
+{
+    if (comm && comm->sum) comm->sum(comm->ctx, vals, n);
+}
+
 /* coupledFvPatchField::patchNeighbourField for every coupled patch face (tests, fvMatrix glue) */
 void orc_patch_neighbour_field(const orc_addr *a, const double *psi, const orc_comm *comm, double *out)
 {

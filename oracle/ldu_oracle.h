@@ -112,6 +112,7 @@ int orc_addr_npatches(const orc_addr *a);
 const int *orc_addr_patch_start(const orc_addr *a); /* nPatches + 1 offsets into faceCells */
 const int *orc_addr_face_cells(const orc_addr *a);
 
+void orc_comm_sum(const orc_comm *comm, double *vals, int n); /* global sum of each entry */
 /* psi of the cell across every coupled patch face (processor: halo exchange; cyclic: partner patch) */
 void orc_patch_neighbour_field(const orc_addr *a, const double *psi, const orc_comm *comm, double *out);
 

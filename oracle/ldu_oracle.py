@@ -115,6 +115,7 @@ def lib():
         for nm in ("orc_addr_patch_start", "orc_addr_face_cells"):
             getattr(L, nm).restype = c_ip
             getattr(L, nm).argtypes = [C.c_void_p]
+        L.orc_comm_sum.argtypes = [C.c_void_p, c_dp, C.c_int]
         L.orc_patch_neighbour_field.argtypes = [C.c_void_p, c_dp, C.c_void_p, c_dp]
         L.orc_gamg_addr.restype = C.c_void_p
         L.orc_gamg_addr.argtypes = [C.c_void_p, C.c_int]

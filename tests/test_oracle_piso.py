@@ -65,3 +65,43 @@ def test_gamg_pressure_solver_gives_the_same_step(meshmod, orc):
         assert all(p.converged for p in perfs["p"]) and perfs["p"][0].solverName == b"GAMG"
     np.testing.assert_allclose(b.U, a.U, atol=1e-9)
     np.testing.assert_allclose(b.p, a.p, atol=1e-9)
+
+
+import pytest  # noqa: E402
+
+import dist_helpers as dh  # noqa: E402
+
+
+@pytest.mark.parametrize("nR", [2, 4, 8])
+def test_decomposed_cavity_reproduces_the_single_domain(meshmod, orc, nR):
+    """icoFoam over processor patches: every rank runs the same step on its brick (interpolation, fluxes, matrix
+    coefficients and the glue on the coupled faces, halo exchanges, global sums) and the fields agree with the
+    single-domain run to the solvers' tolerance."""
+    n = 8
+    ctl = dict(tolerance=1e-12, relTol=0.0)
+    _, ref = po.cavity_from_hex(orc, meshmod, n)
+    for _ in range(3):
+        rp, rc = ref.step(UControls=ctl, pControls=ctl)
+    ex = dh.ThreadExchange(nR)
+
+    def rank_fn(r):
+        m0 = meshmod.decompose(n, nR, r)
+        comm = ex.comm(orc, r, m0, n ** 3)
+        m, case = po.cavity_rank(orc, meshmod, n, nR, r, comm)
+        for _ in range(3):
+            perfs, cont = case.step(UControls=ctl, pControls=ctl)
+        return m.cellGlobal, case.U, case.p, cont, [p.converged for p in perfs["U"] + perfs["p"]], case
+    res = dh.run_threads(nR, rank_fn)
+    for cg, U, p, cont, conv, case in res:
+        assert all(conv)
+        np.testing.assert_allclose(U, ref.U[cg], rtol=0, atol=1e-8)
+        np.testing.assert_allclose(p, ref.p[cg], rtol=0, atol=1e-8)
+        assert cont[-1][0] < 1e-10 and cont == res[0][3]          # global sums: the same numbers on every rank
+    # both sides of a processor patch hold the same flux with opposite sign
+    for r, (cg, U, p, cont, conv, case) in enumerate(res):
+        ps = case.addr.patch_start()
+        for i, nb in enumerate(case.addr.neighbRank):
+            other = res[nb][5]
+            q = list(other.addr.neighbRank).index(r)
+            qs = other.addr.patch_start()
+            np.testing.assert_allclose(case.cphi[ps[i]:ps[i + 1]], -other.cphi[qs[q]:qs[q + 1]], rtol=0, atol=1e-14)
