@@ -18,19 +18,38 @@ SMALL = 1e-15   # doubleScalar.H
 
 
 class IcoFoam:
+    """One rank of the case.  Boundary faces: the fixedValue patches (`bFaceCells`, patch order) and, on a decomposed
+    case, the processor patches (`cou*` arrays, flat in patch order, as given to the addressing).  The face-sum kernels
+    see all of them as one boundary list; the fvMatrix glue gets zero internal / boundary coefficients for the
+    processor faces there and their real coefficients through the matrix' interface coefficients."""
+
     def __init__(self, capi, ctx, torch, nCells, lower, upper, Sf, magSf, weights, deltaCoeffs, V, bFaceCells, bSf,
-                 bMagSf, bDeltaCoeffs, Ub, nu, deltaT, pRefCell=0, pRefValue=0.0, cellCentres=None, addr=None):
-        self.capi, self.ctx, self.torch = capi, ctx, torch
+                 bMagSf, bDeltaCoeffs, Ub, nu, deltaT, pRefCell=0, pRefValue=0.0, cellCentres=None, addr=None,
+                 couPatchStart=None, couFaceCells=None, neighbRank=None, couSf=None, couMagSf=None, couWeights=None,
+                 couDeltaCoeffs=None, allsum=None):
+        self.capi, self.ctx, self.torch, self.allsum = capi, ctx, torch, allsum
         self.n, self.nF = int(nCells), len(lower)
-        self.addr = addr if addr is not None else capi.LduAddressing(ctx, nCells, lower, upper, cellCentres=cellCentres)
+        cfc = np.zeros(0, np.int32) if couFaceCells is None else np.ascontiguousarray(couFaceCells, dtype=np.int32)
+        self.nC = len(cfc)
+        if addr is not None:
+            self.addr = addr
+        elif self.nC:
+            self.addr = capi.LduAddressing(ctx, nCells, lower, upper, couPatchStart, cfc, neighbRank, cellCentres)
+        else:
+            self.addr = capi.LduAddressing(ctx, nCells, lower, upper, cellCentres=cellCentres)
         bfc = np.ascontiguousarray(bFaceCells, dtype=np.int32)
         self.nB = len(bfc)
-        capi.fv_boundary_set(self.addr, bfc)
+        capi.fv_boundary_set(self.addr, np.concatenate([bfc, cfc]))
         self.ops = capi.FieldOps(ctx)
         t = self._t
         self.Sf, self.magSf, self.w, self.delta, self.V = t(Sf), t(magSf), t(weights), t(deltaCoeffs), t(V)
         self.bfc = torch.from_numpy(np.array(bfc)).to(ctx.device)
+        self.cfc = torch.from_numpy(np.array(cfc)).to(ctx.device)
         self.bSf, self.Ub = t(bSf), t(Ub)
+        self.cSf = t(np.zeros((0, 3)) if couSf is None else couSf)
+        self.allSf = torch.cat([self.bSf, self.cSf])
+        z = np.zeros(self.nC)
+        self.cMagSf, self.cw, self.cDelta = (t(z if x is None else x) for x in (couMagSf, couWeights, couDeltaCoeffs))
         self.nu, self.deltaT, self.pRefCell, self.pRefValue = float(nu), float(deltaT), int(pRefCell), float(pRefValue)
         # boundary-condition coefficients (constant): fvm::laplacian(nu, U) on fixedValue patches
         # (gaussLaplacianScheme.C:66-86, fixedValueFvPatchField.C:136-146)
@@ -38,32 +57,48 @@ class IcoFoam:
         d = np.asarray(bDeltaCoeffs, float)[:, None]
         Ubh = np.asarray(Ub, float).reshape(self.nB, 3)
         self.lIc, self.lBc = t(g * (-d) * np.ones_like(Ubh)), t((-g) * (d * Ubh))
-        self.zeroB3, self.zeroB1 = t(np.zeros((self.nB, 3))), t(np.zeros(self.nB))
+        self.zeroB3, self.zeroB1 = t(np.zeros((self.nB, 3))), t(np.zeros(self.nB + self.nC))
+        self.zeroC3 = t(np.zeros((self.nC, 3)))
         self.U, self.p = t(np.zeros((self.n, 3))), t(np.zeros(self.n))
         # createPhi.H: phi = linearInterpolate(U) & mesh.Sf()
         self.phi = capi.fv_flux_linear(self.addr, self.Sf, self.w, self.U)
-        self.bphi = self.ops.dot3(self.Ub, self.bSf)
         self.bUSf = self.ops.dot3(self.Ub, self.bSf)
+        self.bphi = self.bUSf.clone()
+        self.cphi = self.ops.dot3(self.interpolate_coupled(self.U, 3), self.cSf) if self.nC else t(z)
         self.matU, self.matP = capi.LduMatrix(self.addr), capi.LduMatrix(self.addr)
 
     def _t(self, a):
         return self.torch.from_numpy(np.array(a, dtype=np.float64).ravel()).to(self.ctx.device)
 
-    def grad(self, p):
-        """fvc::grad(p), Gauss linear, p zeroGradient at the boundary"""
-        pb = self.ops.gather(self.bfc, p, 1)
-        return self.capi.fv_grad_linear(self.addr, 1, self.Sf, self.w, p, self.bSf, pb, self.V)
+    def interpolate_coupled(self, vf, nc):
+        """processor faces: w*patchInternalField + (1 - w)*patchNeighbourField (surfaceInterpolationScheme.C:246-262)"""
+        o = self.ops
+        pnf = self.capi.fv_patch_neighbour_field(self.addr, nc, vf)
+        return o.add(o.mul(self.cw, o.gather(self.cfc, vf, nc), 1, nc), o.mul(o.rsub(1.0, self.cw), pnf, 1, nc), nc, nc)
 
-    def div(self, phi, bphi):
-        return self.capi.fv_surface_integrate(self.addr, 1, phi, bphi, self.V, True, -1)
+    def grad(self, p):
+        """fvc::grad(p), Gauss linear, p zeroGradient at the walls, interpolated on the processor faces"""
+        pb = self.ops.gather(self.bfc, p, 1)
+        if self.nC:
+            pb = self.torch.cat([pb, self.interpolate_coupled(p, 1)])
+        return self.capi.fv_grad_linear(self.addr, 1, self.Sf, self.w, p, self.allSf, pb, self.V)
+
+    def div(self, phi, bphi, cphi=None):
+        cphi = self.cphi if cphi is None else cphi
+        return self.capi.fv_surface_integrate(self.addr, 1, phi, self.torch.cat([bphi, cphi]) if self.nC else bphi,
+                                              self.V, True, -1)
+
+    def _gsum3(self, a, b, c):
+        v = [float(a), float(b), float(c)]
+        return v if self.allsum is None else [float(x) for x in self.allsum(np.array(v))]
 
     def step(self, nCorr=2, nNonOrthCorr=0, UControls=None, pControls=None, momentumPredictor=True,
              USolver=("PBiCG", "DILU"), pSolver=("PCG", "DIC"), gamg=None):
         """icoFoam.C:55-103; returns ({"U": [Perf x3], "p": [Perf per pressure solve]}, continuity errors).
         USolver / pSolver: (solver, preconditioner or smoother) as system/fvSolution names them; gamg: the cached
         agglomeration (capi.GamgAgglomeration over self.addr) when pSolver is GAMG."""
-        capi, o, a = self.capi, self.ops, self.addr
-        U0, phi0 = self.U.clone(), self.phi.clone()
+        capi, o, a, cat, nC = self.capi, self.ops, self.addr, self.torch.cat, self.nC
+        U0, phi0, cphi0 = self.U.clone(), self.phi.clone(), self.cphi.clone()
         rDeltaT = 1.0 / self.deltaT
         # fvm::ddt(U)
         ddtDiag = o.smul(rDeltaT, self.V)
@@ -80,18 +115,27 @@ class IcoFoam:
         source = ddtSource
         ic = o.sub(self.zeroB3, self.lIc)
         bc = o.sub(cBc, self.lBc)
-        self.matU.set(diag, upper, lower)
+        ci = cb = None
+        if nC:
+            # processor patches (coupledFvPatchField.C:162-209): convection patchFlux*w / -patchFlux*(1 - w), diffusion
+            # pGamma*(-delta) / -pGamma*delta; the glue's boundary list carries zeros for these faces
+            cGamma = o.smul(self.nu, self.cMagSf)
+            ci = o.sub(o.mul(self.cphi, self.cw), o.mul(cGamma, o.neg(self.cDelta)))
+            cb = o.sub(o.mul(o.neg(self.cphi), o.rsub(1.0, self.cw)), o.mul(o.neg(cGamma), self.cDelta))
+            ic, bc = cat([ic, self.zeroC3]), cat([bc, self.zeroC3])
+        self.matU.set(diag, upper, lower, cb, ci)
+        pnfU = (lambda f: capi.fv_patch_neighbour_field(a, 3, f)) if nC else (lambda f: None)
         perfs = {}
         if momentumPredictor:
             # solve(UEqn == -fvc::grad(p))
             src = o.add(source, o.mul(self.V, o.neg(self.grad(self.p)), 1, 3))
             UEqn = capi.FvMatrix(self.matU, 3, diag, src, self.U, self.V, ic, bc)
-            perfs["U"] = UEqn.solve(USolver[0], USolver[1], **(UControls or dict(tolerance=1e-5, relTol=0.0)))
+            perfs["U"] = UEqn.solve(USolver[0], USolver[1], pnf=pnfU(self.U), **(UControls or dict(tolerance=1e-5, relTol=0.0)))
         cont = []
         for corr in range(nCorr):
             UEqn = capi.FvMatrix(self.matU, 3, diag, source, self.U, self.V, ic, bc)
             rAU = o.rdiv(1.0, UEqn.A())
-            HbyA = o.mul(rAU, UEqn.H(), 1, 3)
+            HbyA = o.mul(rAU, UEqn.H(pnfU(self.U)), 1, 3)
             # phiHbyA = (interpolate(HbyA) & Sf) + interpolate(rAU)*ddtCorr(U, phi)
             phiCorr = o.sub(phi0, capi.fv_flux_linear(a, self.Sf, self.w, U0))
             coeff = o.rsub(1.0, o.smin(o.div(o.mag(phiCorr), o.sadd(o.mag(phi0), SMALL)), 1.0))
@@ -99,22 +143,35 @@ class IcoFoam:
             rAUf = capi.fv_interpolate_linear(a, 1, self.w, rAU)
             phiHbyA = o.add(capi.fv_flux_linear(a, self.Sf, self.w, HbyA), o.mul(rAUf, ddtCorr))
             bphiHbyA = self.bUSf
+            cphiHbyA, crAUf = self.cphi, None
+            if nC:      # the same expression on the processor faces (their coupling coefficient is not zeroed)
+                cphiCorr = o.sub(cphi0, o.dot3(self.cSf, self.interpolate_coupled(U0, 3)))
+                ccoeff = o.rsub(1.0, o.smin(o.div(o.mag(cphiCorr), o.sadd(o.mag(cphi0), SMALL)), 1.0))
+                crAUf = self.interpolate_coupled(rAU, 1)
+                cphiHbyA = o.add(o.dot3(self.interpolate_coupled(HbyA, 3), self.cSf),
+                                 o.mul(crAUf, o.mul(o.smul(rDeltaT, ccoeff), cphiCorr)))
             for nonOrth in range(nNonOrthCorr + 1):
                 # pEqn: fvm::laplacian(rAU, p) == fvc::div(phiHbyA)
                 pUpper, pDiag = capi.fv_laplacian_fill(a, self.delta, o.mul(rAUf, self.magSf))
-                pSource = o.mul(self.V, self.div(phiHbyA, bphiHbyA))
+                pSource = o.mul(self.V, self.div(phiHbyA, bphiHbyA, cphiHbyA))
+                pCi = pCb = None
+                if nC:
+                    pGamma = o.mul(crAUf, self.cMagSf)
+                    pCi, pCb = o.mul(pGamma, o.neg(self.cDelta)), o.mul(o.neg(pGamma), self.cDelta)
                 pEqn = capi.FvMatrix(self.matP, 1, pDiag, pSource, self.p, self.V, self.zeroB1, self.zeroB1)
-                self.matP.set(pDiag, pUpper)
+                self.matP.set(pDiag, pUpper, None, pCb, pCi)
                 pEqn.setReference(self.pRefCell, self.pRefValue)
                 perfs.setdefault("p", []).extend(pEqn.solve(pSolver[0], pSolver[1], gamg, **(pControls or dict(tolerance=1e-6, relTol=0.0))))
                 if nonOrth == nNonOrthCorr:
-                    internal, boundary, _ = pEqn.flux(self.nB)
+                    pnfP = capi.fv_patch_neighbour_field(a, 1, self.p) if nC else None
+                    internal, boundary, coupled = pEqn.flux(self.nB + nC, nC, pnfP)
                     self.phi = o.sub(phiHbyA, internal)
-                    self.bphi = o.sub(bphiHbyA, boundary)
+                    self.bphi = o.sub(bphiHbyA, boundary[: self.nB])
+                    if nC:
+                        self.cphi = o.sub(cphiHbyA, coupled)
             contErr = self.div(self.phi, self.bphi)
-            vol = float(self.V.sum())
-            cont.append((self.deltaT * float((contErr.abs() * self.V).sum()) / vol,
-                         self.deltaT * float((contErr * self.V).sum()) / vol))
+            tot = self._gsum3((contErr.abs() * self.V).sum(), (contErr * self.V).sum(), self.V.sum())
+            cont.append((self.deltaT * tot[0] / tot[2], self.deltaT * tot[1] / tot[2]))
             # U = HbyA - rAU*fvc::grad(p)
             self.U = o.sub(HbyA, o.mul(rAU, self.grad(self.p), 1, 3), 3, 3)
         return perfs, cont
@@ -123,6 +180,28 @@ class IcoFoam:
         self.matU.close()
         self.matP.close()
         self.addr.close()
+
+
+def cavity_rank(capi, ctx, torch, n, nRanks, rank, allsum, nu=0.01, deltaT=None, lid=(1.0, 0.0, 0.0)):
+    """rank `rank` of the brick decomposition of the cavity (mesh.decompose): fixedValue walls + processor patches;
+    `allsum(ndarray) -> ndarray` sums over the ranks (continuity report).  The pressure reference cell is global cell 0."""
+    meshmod = importlib.import_module("rapidcfd-dev_b200.mesh")
+    m = meshmod.decompose(n, nRanks, rank)
+    walls, procs = m.wall_patches(), m.coupled_patches()
+    bfc = np.concatenate([p.faceCells for p in walls]).astype(np.int32)
+    bSf = np.concatenate([p.Sf for p in walls])
+    Ub = np.concatenate([np.tile(lid if p.name == "movingWall" else (0.0, 0.0, 0.0), (len(p.faceCells), 1)) for p in walls])
+    nB = len(bfc)
+    ps, fc = m.patch_start_facecells()
+    nC = len(fc)
+    deltaT = deltaT if deltaT is not None else 0.5 * m.h / max(abs(v) for v in lid)
+    ref = np.nonzero(m.cellGlobal == 0)[0]
+    return m, IcoFoam(capi, ctx, torch, m.nCells, m.lower, m.upper, m.Sf(), m.magSf(), m.weights(), m.deltaCoeffs(),
+                      m.volumes(), bfc, bSf, np.full(nB, m.h * m.h), np.full(nB, 2.0 / m.h), Ub, nu, deltaT,
+                      pRefCell=int(ref[0]) if len(ref) else -1, cellCentres=m.cell_centres(), couPatchStart=ps,
+                      couFaceCells=fc, neighbRank=[p.neighbRank for p in procs], couSf=np.concatenate([p.Sf for p in procs]),
+                      couMagSf=np.full(nC, m.h * m.h), couWeights=np.full(nC, 0.5), couDeltaCoeffs=np.full(nC, 1.0 / m.h),
+                      allsum=allsum)
 
 
 def cavity(capi, ctx, torch, n, nu=0.01, deltaT=None, lid=(1.0, 0.0, 0.0)):

@@ -16,12 +16,17 @@ from oracle import ldu_oracle as orc
 class _Ctx:
     device = "cpu"
 
+    def __init__(self, comm=None):
+        self.comm = comm       # orc.PyComm of this rank (multi-rank dry runs), None on a single domain
+
     def close(self):
         pass
 
 
 class LduAddressing:
     def __init__(self, ctx, nCells, lower, upper, patchStart=None, faceCells=None, neighbRank=None, cellCentres=None):
+        self.ctx = ctx
+        self.nPatchFaces = 0 if patchStart is None else int(patchStart[-1])
         self.nCells, self.nFaces = int(nCells), len(lower)
         self.o = orc.Addr(nCells, lower, upper) if patchStart is None else orc.Addr(nCells, lower, upper, patchStart,
                                                                                      faceCells, neighbRank=neighbRank)
@@ -77,9 +82,9 @@ class LduMatrix:
 
     def solve(self, solver, pre, psi, source, gamg=None, histCap=0, **ctl):
         if solver == "GAMG":
-            out, perf, hist = gamg.o.solve(self.m, pre, _np(psi), _np(source), **ctl)
+            out, perf, hist = gamg.o.solve(self.m, pre, _np(psi), _np(source), comm=self.addr.ctx.comm, **ctl)
         else:
-            out, perf, hist = self.m.solve(solver, pre, _np(psi), _np(source), **ctl)
+            out, perf, hist = self.m.solve(solver, pre, _np(psi), _np(source), comm=self.addr.ctx.comm, **ctl)
         psi.copy_(self._t(out))
         return perf, (hist if histCap else hist[:0])
 
@@ -99,7 +104,7 @@ class FvMatrix:
         a = self.m.addr
         return fo.FvMatrix(orc, a.o, self.nc, _np(self.diag if diag is None else diag), _np(upper), _np(lower),
                            _np(self.source if source is None else source), _np(self.psi), _np(self.V), a.bfc,
-                           _np(self.ic), _np(self.bc), couInt=_np(intc), couBou=_np(bou))
+                           _np(self.ic), _np(self.bc), couInt=_np(intc), couBou=_np(bou), comm=a.ctx.comm)
 
     def _t(self, a):
         import torch
@@ -233,6 +238,12 @@ class _Capi:
     LduMatrix = LduMatrix
     FvMatrix = FvMatrix
     FieldOps = FieldOps
+
+    @staticmethod
+    def fv_patch_neighbour_field(addr, nc, field):
+        f = _np(field).reshape(-1, nc)
+        cols = [addr.o.patch_neighbour_field(np.ascontiguousarray(f[:, k]), addr.ctx.comm) for k in range(nc)]
+        return FieldOps._t(np.stack(cols, axis=1))
 
     @staticmethod
     def fv_convection_fill(addr, w, phi):

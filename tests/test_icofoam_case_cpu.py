@@ -93,3 +93,38 @@ def test_run_case_refuses_what_the_step_does_not_cover(meshmod, tmp_path):
     capi, ctx, torch = oracle_backend.fixture()
     with pytest.raises(NotImplementedError, match="movingWall"):
         ico.run_case(capi, ctx, torch, root, log=lambda s: None)
+
+
+@pytest.mark.parametrize("nR", [2, 4])
+def test_decomposed_device_step_sequencing(meshmod, orc, nR):
+    """The multi-rank branch of icofoam.IcoFoam (processor patches: coupled interpolation, interface coefficients,
+    patchNeighbourField exchanges, the zero-padded boundary list for the glue) through the stand-in, one thread per
+    rank, against the single-domain oracle run."""
+    import dist_helpers as dh
+    ico = importlib.import_module("rapidcfd-dev_b200.icofoam")
+    n = 8
+    ctl = dict(tolerance=1e-12, relTol=0.0)
+    _, ref = po.cavity_from_hex(orc, meshmod, n)
+    for _ in range(2):
+        ref.step(UControls=ctl, pControls=ctl)
+    ex = dh.ThreadExchange(nR)
+
+    def rank_fn(r):
+        m0 = meshmod.decompose(n, nR, r)
+        comm = ex.comm(orc, r, m0, n ** 3)
+        capi, _, torch = oracle_backend.fixture()
+        ctx = oracle_backend._Ctx(comm)
+
+        def allsum(v):
+            out = np.array(v, float)
+            orc.lib().orc_comm_sum(comm.ptr(), orc._d(out), len(out))
+            return out
+        m, case = ico.cavity_rank(capi, ctx, torch, n, nR, r, allsum)
+        for _ in range(2):
+            perfs, cont = case.step(UControls=ctl, pControls=ctl)
+        return m.cellGlobal, case.U.numpy().reshape(-1, 3), case.p.numpy(), cont
+    res = dh.run_threads(nR, rank_fn)
+    for cg, U, p, cont in res:
+        np.testing.assert_allclose(U, ref.U[cg], rtol=0, atol=1e-8)
+        np.testing.assert_allclose(p, ref.p[cg], rtol=0, atol=1e-8)
+        assert cont[-1][0] < 1e-10 and cont == res[0][3]

@@ -260,3 +260,21 @@ def test_multi_gpu_fvm(world):
                        timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-4000:]
     assert p.stdout.count("MULTI-GPU-FVM-OK") == 3 * world
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_multi_gpu_icofoam(world):
+    """the decomposed cavity, one rank per GPU, against the single-domain oracle (needs >= 2 GPUs; skipped otherwise)"""
+    import subprocess
+    import sys
+    import torch
+    if os.environ.get("B200LDU_DRYRUN_ORACLE") == "1" or torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29800 + world),
+           os.path.join(root, "tests", "multi_gpu_icofoam_worker.py")]
+    p = subprocess.run(cmd, cwd=root, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), capture_output=True, text=True,
+                       timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-4000:]
+    assert p.stdout.count("MULTI-GPU-ICOFOAM-OK") == world
