@@ -250,29 +250,41 @@ def _time_name(t):
     return s
 
 
-def load_case(capi, ctx, torch, caseDir):
-    """Build the IcoFoam object and the run controls from a case directory."""
+def load_case(capi, ctx, torch, caseDir, rank=None, allsum=None):
+    """Build the IcoFoam object and the run controls from a case directory.  rank = None: the undecomposed case;
+    otherwise rank `rank` of a decomposed one: mesh and fields from <caseDir>/processor<rank>/ (decomposePar layout,
+    `processor` patches last), dictionaries from the case itself; needs the communicator on `ctx` and
+    `allsum(ndarray) -> ndarray` for the continuity report."""
     import os
     ff = importlib.import_module("rapidcfd-dev_b200.foamfile")
     j = lambda *a: os.path.join(caseDir, *a)
+    base = caseDir if rank is None else j(f"processor{rank}")
+    jb = lambda *a: os.path.join(base, *a)
     control = ff.read_dict(j("system", "controlDict"))
     fvSolution = ff.read_dict(j("system", "fvSolution"))
     transport = ff.read_dict(j("constant", "transportProperties"))
-    pm = ff.read_poly_mesh(j("constant", "polyMesh"))
+    pm = ff.read_poly_mesh(jb("constant", "polyMesh"))
     if pm.points is None:
         raise ValueError("constant/polyMesh needs points and faces (geometry)")
-    if pm.coupled_patches():
-        raise NotImplementedError("icoFoam step: coupled (processor / cyclic) patches are not supported yet")
+    coupled = pm.coupled_patches()
+    if any(p.type != "processor" for p in coupled):
+        raise NotImplementedError("icoFoam step: cyclic / processorCyclic patches are not supported yet")
+    if coupled and rank is None:
+        raise ValueError("processor patches in an undecomposed case")
     geo = pm.fv_geometry()
     nI = pm.nInternalFaces
     lower, upper = pm.ldu()
-    bfc = pm.boundary_face_cells()
     startTime = _time_name(float(control.lookupOrDefault("startTime", 0)))
     n = pm.nCells
-    Ufile = ff.read_field(j(startTime, "U"), nInternal=n)
-    pfile = ff.read_field(j(startTime, "p"), nInternal=n)
-    Ub = np.zeros((len(bfc), 3))
-    for p in pm.patches:
+    Ufile = ff.read_field(jb(startTime, "U"), nInternal=n)
+    pfile = ff.read_field(jb(startTime, "p"), nInternal=n)
+    walls = [p for p in pm.patches if p.type != "processor"]
+    if coupled and pm.patches[-len(coupled):] != coupled:
+        raise ValueError("processor patches have to follow the physical patches")
+    nW = sum(p.nFaces for p in walls)
+    bfc = pm.owner[nI:nI + nW].astype(np.int32)
+    Ub = np.zeros((nW, 3))
+    for p in walls:
         s = slice(p.startFace - nI, p.startFace - nI + p.nFaces)
         ub, pb = Ufile["boundaryField"].get(p.name), pfile["boundaryField"].get(p.name)
         if ub is None or pb is None:
@@ -280,34 +292,61 @@ def load_case(capi, ctx, torch, caseDir):
         if str(ub["type"]) != "fixedValue" or str(pb["type"]) != "zeroGradient":
             raise NotImplementedError(f"patch {p.name}: U {ub['type']} / p {pb['type']} -- this step supports "
                                       "fixedValue U with zeroGradient p only")
-        Ub[s] = np.asarray(ub["value"], float).reshape(-1, 3) if np.ndim(ub["value"]) == 2 else np.asarray(ub["value"], float)
+        if p.nFaces:
+            Ub[s] = np.asarray(ub["value"], float).reshape(-1, 3) if np.ndim(ub["value"]) == 2 else np.asarray(ub["value"], float)
     # boundary deltaCoeffs: 1/|Cf - C_owner| (surfaceInterpolation.C:300-340, fvPatch::delta)
-    bDelta = 1.0 / np.linalg.norm(geo["Cf"][nI:] - geo["C"][bfc], axis=1)
+    wf = slice(nI, nI + nW)
+    bDelta = 1.0 / np.linalg.norm(geo["Cf"][wf] - geo["C"][bfc], axis=1)
     piso = fvSolution.subDict("PISO")
+    pRefCell = int(piso.lookupOrDefault("pRefCell", 0))
+    kw = {}
+    if coupled:
+        ps, fc, nr = pm.coupled_interface_arrays()
+        cf = slice(nI + nW, nI + nW + len(fc))
+        # the reference cell is a GLOBAL label: the rank holding it uses its local one (setRefCell.C:100-140)
+        cpa = jb("constant", "polyMesh", "cellProcAddressing")
+        if os.path.exists(cpa) or os.path.exists(cpa + ".gz"):
+            mine = np.nonzero(ff.read_list(cpa, "label") == pRefCell)[0]
+            pRefCell = int(mine[0]) if len(mine) else -1
+        elif rank != 0:
+            pRefCell = -1
+        # coupled weights and deltaCoeffs need the neighbour cell centres (coupledFvPatch::makeWeights,
+        # processorFvPatch::delta): one patchNeighbourField exchange of C at start-up
+        addr = capi.LduAddressing(ctx, n, lower, upper, ps, fc, nr, geo["C"])
+        Cd = torch.from_numpy(np.ascontiguousarray(geo["C"], dtype=np.float64).ravel()).to(ctx.device)
+        Cn = capi.fv_patch_neighbour_field(addr, 3, Cd).cpu().numpy().reshape(-1, 3)
+        Sfc, Cfc, Co = geo["Sf"][cf], geo["Cf"][cf], geo["C"][fc]
+        dOwn = np.abs(np.einsum("ij,ij->i", Sfc, Cfc - Co))
+        dNei = np.abs(np.einsum("ij,ij->i", Sfc, Cn - Cfc))
+        kw = dict(addr=addr, couPatchStart=ps, couFaceCells=fc, neighbRank=nr, couSf=Sfc, couMagSf=geo["magSf"][cf],
+                  couWeights=dNei / (dOwn + dNei), couDeltaCoeffs=1.0 / np.linalg.norm(Cn - Co, axis=1), allsum=allsum)
     case = IcoFoam(capi, ctx, torch, n, lower, upper, geo["Sf"][:nI], geo["magSf"][:nI], geo["weights"], geo["deltaCoeffs"],
-                   geo["V"], bfc, geo["Sf"][nI:], geo["magSf"][nI:], bDelta, Ub, _last_number(transport.lookup("nu")),
-                   float(control.lookup("deltaT")), int(piso.lookupOrDefault("pRefCell", 0)),
-                   float(piso.lookupOrDefault("pRefValue", 0.0)), cellCentres=geo["C"])
+                   geo["V"], bfc, geo["Sf"][wf], geo["magSf"][wf], bDelta, Ub, _last_number(transport.lookup("nu")),
+                   float(control.lookup("deltaT")), pRefCell, float(piso.lookupOrDefault("pRefValue", 0.0)),
+                   cellCentres=geo["C"], **kw)
     case.U = case._t(Ufile["internalField"])
     case.p = case._t(pfile["internalField"])
     case.phi = capi.fv_flux_linear(case.addr, case.Sf, case.w, case.U)      # createPhi.H
+    if case.nC:
+        case.cphi = case.ops.dot3(case.interpolate_coupled(case.U, 3), case.cSf)
     us, up_, uc = ff.solver_controls(fvSolution, "U")
-    ps, pp, pc = ff.solver_controls(fvSolution, "p")
+    ps_, pp, pc = ff.solver_controls(fvSolution, "p")
     run = dict(startTime=float(control.lookupOrDefault("startTime", 0)), endTime=float(control.lookup("endTime")),
                deltaT=float(control.lookup("deltaT")), nCorr=int(piso.lookupOrDefault("nCorrectors", 2)),
                nNonOrthCorr=int(piso.lookupOrDefault("nNonOrthogonalCorrectors", 0)),
                momentumPredictor=bool(ff._switch(piso.lookupOrDefault("momentumPredictor", "yes"))),
-               USolver=(us, up_), UControls=uc, pSolver=(ps, pp), pControls=pc, patches=pm.patches, nInternalFaces=nI,
-               Ufile=Ufile, pfile=pfile, polyMesh=pm, geometry=geo)
+               USolver=(us, up_), UControls=uc, pSolver=(ps_, pp), pControls=pc, patches=pm.patches, nInternalFaces=nI,
+               Ufile=Ufile, pfile=pfile, polyMesh=pm, geometry=geo, base=base)
     return case, run
 
 
-def run_case(capi, ctx, torch, caseDir, log=print, write=True, maxSteps=None):
-    """The time loop of icoFoam.C:48-110 on `caseDir`; prints the reference's log lines; writes U and p of the last
-    time step into <caseDir>/<time>/ when `write`.  Returns (case, list of per-step (perfs, continuity errors))."""
+def run_case(capi, ctx, torch, caseDir, log=print, write=True, maxSteps=None, rank=None, allsum=None):
+    """The time loop of icoFoam.C:48-110 on `caseDir` (or on processor<rank>/ of it, see load_case); prints the
+    reference's log lines; writes U and p of the last time step into <time>/ of the (processor) directory when `write`.
+    Returns (case, list of per-step (perfs, continuity errors))."""
     import os
     ff = importlib.import_module("rapidcfd-dev_b200.foamfile")
-    case, run = load_case(capi, ctx, torch, caseDir)
+    case, run = load_case(capi, ctx, torch, caseDir, rank, allsum)
     gamg = None
     if run["pSolver"][0] == "GAMG":
         geo = run["geometry"]
@@ -337,7 +376,7 @@ def run_case(capi, ctx, torch, caseDir, log=print, write=True, maxSteps=None):
                 f"cumulative = {cumulative:g}")
         history.append((perfs, cont))
     if write and nSteps:
-        tdir = os.path.join(caseDir, _time_name(t))
+        tdir = os.path.join(run["base"], _time_name(t))
         os.makedirs(tdir, exist_ok=True)
         U = case.U.cpu().numpy().reshape(-1, 3)
         p = case.p.cpu().numpy()
