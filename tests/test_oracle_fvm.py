@@ -265,3 +265,17 @@ def test_decomposed_glue_matches_single_domain(meshmod, orc, nR):
             for i, j in zip(m.cellGlobal[p.faceCells], p.nbrGlobalCells):
                 np.testing.assert_allclose(R["coupled"][k], (-cou[k]) * x[i] - (-cou[k]) * x[j], rtol=1e-13)
                 k += 1
+
+
+def test_oracle_reproduces_fvm_golden(meshmod, orc):
+    """tests/golden/fvm_golden.npz (self-generated, make_fvm_golden.py): the glue and two icoFoam steps, bit for bit"""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_fvm_golden as mg
+    golden = np.load(os.path.join(here, "golden", "fvm_golden.npz"))
+    fresh = mg.generate(meshmod, orc)
+    assert sorted(fresh) == sorted(golden.files)
+    for k in golden.files:
+        assert np.array_equal(fresh[k], golden[k]), k

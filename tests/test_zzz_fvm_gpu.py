@@ -278,3 +278,39 @@ def test_multi_gpu_icofoam(world):
                        timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-4000:]
     assert p.stdout.count("MULTI-GPU-ICOFOAM-OK") == world
+
+
+def test_gpu_fvm_vs_golden(gpu, meshmod, orc):
+    """the glue and two icoFoam steps against tests/golden/fvm_golden.npz (self-generated; make_fvm_golden.py)"""
+    here = os.path.dirname(os.path.abspath(__file__))
+    import sys
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_fvm_golden as mg
+    capi, ctx, torch = gpu
+    G = np.load(os.path.join(here, "golden", "fvm_golden.npz"))
+    for nc in (1, 3):
+        m, a, d, x, make_ = mg.fvm_case(meshmod, orc, nc)
+        D = Dev(gpu, m, d, nc, x)
+        assert np.array_equal(host(D.fv.A()), G[f"fvm{nc}.A"])
+        assert np.array_equal(host(D.fv.H(), nc), G[f"fvm{nc}.H"])
+        fi, fb, _ = D.fv.flux(D.nB)
+        assert np.array_equal(host(fi, nc), G[f"fvm{nc}.flux"]) and np.array_equal(host(fb, nc), G[f"fvm{nc}.bflux"])
+        if nc == 1:
+            assert np.array_equal(host(D.fv.residual()), G["fvm1.residual"])
+        D.fv.relax(0.7)
+        assert np.array_equal(host(D.diag), G[f"fvm{nc}.relaxDiag"])
+        assert np.array_equal(host(D.source, nc), G[f"fvm{nc}.relaxSource"])
+        Z = Dev(gpu, m, d, nc, np.zeros((m.nCells, nc)), addr=D.addr)
+        perfs = Z.fv.solve("PCG" if nc == 1 else "PBiCG", "DIC" if nc == 1 else "DILU", tolerance=1e-12, maxIter=500)
+        assert all(abs(p.nIterations - k) <= 2 for p, k in zip(perfs, G[f"fvm{nc}.nIter"]))
+        np.testing.assert_allclose(host(Z.psi, nc), G[f"fvm{nc}.psi"], rtol=0, atol=1e-9)
+        Z.mat.close()
+        D.close()
+    ico = importlib.import_module("rapidcfd-dev_b200.icofoam")
+    _, dev = ico.cavity(capi, ctx, torch, mg.PISO_N)
+    for _ in range(mg.PISO_STEPS):
+        dev.step(UControls=mg.PISO_CTL, pControls=mg.PISO_CTL)
+    np.testing.assert_allclose(host(dev.U, 3), G["piso.U"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(host(dev.p), G["piso.p"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(host(dev.phi), G["piso.phi"], rtol=0, atol=1e-11)
+    dev.close()
