@@ -1,0 +1,159 @@
+/*
+ * harness_fvm.cpp -- runs the REFERENCE'S OWN fvMatrix<scalar> glue on the CPU.  TEST INFRASTRUCTURE ONLY.  Included by
+ * path from /root/reference (src/finiteVolume/fvMatrices/):
+ *   fvMatrix/fvMatrix.H, fvMatrix/fvMatrix.C     addToInternalField + functors, addBoundaryDiag, addCmptAvBoundaryDiag,
+ *                                                addBoundarySource, setReference, relax, D, A, flux
+ *   fvMatrix/fvMatrixSolve.C                     (parsed; the component loop needs a vector type and is not instantiated)
+ *   fvScalarMatrix/fvScalarMatrix.H, .C          solveSegregated, residual, H for scalars
+ * against oracle/ref_harness/shim_fvm/.  The linear solver behind solveSegregated is a recorder: it keeps the diagonal and
+ * the source it is handed, which is what the folding has to get right.
+ */
+#define protected public
+#define private public
+#include "fvm_shim.h"
+
+#include "fvMatrix.H" /* reference (pulls fvMatrix.C, fvMatrixSolve.C, fvScalarMatrix.H) */
+#undef protected
+#undef private
+#include "fvScalarMatrix.C" /* reference */
+
+#include <algorithm>
+
+namespace Foam
+{
+std::vector<scalar> lduMatrix::solver::seenDiag, lduMatrix::solver::seenSource;
+int solverPerformance::debug = 0;
+int dimensionSet::debug = 0;
+template <> int fvMatrix<scalar>::debug = 0;
+template <> const word zeroGradientFvPatchField<scalar>::typeName("zeroGradient");
+const char *pTraits<scalar>::componentNames[] = {""};
+} // namespace Foam
+using namespace Foam;
+
+namespace
+{
+struct Case {
+    fvMesh mesh;
+    volScalarField psi;
+    std::unique_ptr<fvMatrix<scalar>> M;
+    Case(int n, int nF, const int *l, const int *u, const int *ownerStart, const int *losortStart, const int *losort,
+         int nP, const int *patchStart, const int *faceCells, const int *coupled, const double *pnf, const double *V,
+         const double *psiv, const double *diag, const double *upper, const double *lower, const double *source,
+         const double *ic, const double *bc)
+    {
+        lduAddressing &a = mesh.addr_;
+        a.nCells_ = n;
+        a.lower_ = labelgpuList(l, nF);
+        a.upper_ = labelgpuList(u, nF);
+        a.ownerStart_ = labelgpuList(ownerStart, n + 1);
+        a.losortStart_ = labelgpuList(losortStart, n + 1);
+        a.losort_ = labelgpuList(losort, nF);
+        mesh.V_.f_ = scalargpuField(V, n);
+        psi.mesh_ = &mesh;
+        psi.internal_ = scalargpuField(psiv, n);
+        psi.boundary_.p_.resize((size_t)nP);
+        for (int p = 0; p < nP; p++) {
+            const int s = patchStart[p], np = patchStart[p + 1] - s;
+            fvPatch fp;
+            fp.size_ = np;
+            fp.faceCells_ = labelgpuList(faceCells + s, np);
+            mesh.boundary_.p_.push_back(fp);
+            // per-patch sort addressing (lduAddressing.C:38-130): unique cells, faces sorted stably by cell
+            std::vector<label> order(np), cells, start;
+            for (int i = 0; i < np; i++) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](label x, label y) { return faceCells[s + x] < faceCells[s + y]; });
+            for (int k = 0; k < np; k++) {
+                const label c = faceCells[s + order[k]];
+                if (cells.empty() || cells.back() != c) {
+                    cells.push_back(c);
+                    start.push_back(k);
+                }
+            }
+            start.push_back(np);
+            a.patchCells_.push_back(labelgpuList(cells.data(), (label)cells.size()));
+            a.patchSort_.push_back(labelgpuList(order.data(), np));
+            a.patchSortStart_.push_back(labelgpuList(start.data(), (label)start.size()));
+        }
+        for (int p = 0; p < nP; p++) { // after the vector stopped growing: the patch fields point into it
+            const int s = patchStart[p], np = patchStart[p + 1] - s;
+            fvPatchField<scalar> &pf = psi.boundary_.p_[(size_t)p];
+            pf.setSize(np);
+            pf.faceCells_ = &mesh.boundary_.p_[(size_t)p].faceCells_;
+            pf.internal_ = &psi.internal_;
+            pf.coupled_ = coupled[p] != 0;
+            pf.pnf_ = scalargpuField(pnf + s, np);
+        }
+        M.reset(new fvMatrix<scalar>(psi, dimensionSet()));
+        M->diag() = tmp<scalargpuField>(new scalargpuField(diag, n));
+        M->upper() = tmp<scalargpuField>(new scalargpuField(upper, nF));
+        if (lower) M->lower() = tmp<scalargpuField>(new scalargpuField(lower, nF));
+        M->source() = tmp<scalargpuField>(new scalargpuField(source, n));
+        for (int p = 0; p < nP; p++) {
+            const int s = patchStart[p], np = patchStart[p + 1] - s;
+            M->internalCoeffs()[p] = tmp<scalargpuField>(new scalargpuField(ic + s, np));
+            M->boundaryCoeffs()[p] = tmp<scalargpuField>(new scalargpuField(bc + s, np));
+        }
+    }
+};
+void put(const scalargpuField &f, double *out) { std::copy(f.begin(), f.end(), out); }
+} // namespace
+
+extern "C" {
+/* op: 0 addBoundaryDiag(x, 0) on x = in1 | 1 addCmptAvBoundaryDiag | 2 addBoundarySource(x, couples = iarg) | 3 setReference(cell
+ * iarg, value darg, forced) -> out1 diag, out2 source | 4 relax(darg) -> out1 diag, out2 source | 5 D | 6 A | 7 flux -> out1
+ * internal faces, out2 boundary faces (flat) | 8 H | 9 residual | 10 solveSegregated -> out1 diagonal and out2 source as the
+ * solver sees them, out3 the diagonal afterwards */
+int ref_fvm(int op, int n, int nF, const int *l, const int *u, const int *ownerStart, const int *losortStart, const int *losort,
+            int nP, const int *patchStart, const int *faceCells, const int *coupled, const double *pnf, const double *V,
+            const double *psi, const double *diag, const double *upper, const double *lower, const double *source,
+            const double *ic, const double *bc, int iarg, double darg, const double *in1, double *out1, double *out2,
+            double *out3)
+{
+    try {
+        Case C(n, nF, l, u, ownerStart, losortStart, losort, nP, patchStart, faceCells, coupled, pnf, V, psi, diag, upper, lower,
+               source, ic, bc);
+        fvMatrix<scalar> &M = *C.M;
+        if (op == 0 || op == 1 || op == 2) {
+            scalargpuField x(in1, n);
+            if (op == 0) M.addBoundaryDiag(x, 0);
+            if (op == 1) M.addCmptAvBoundaryDiag(x);
+            if (op == 2) M.addBoundarySource(x, iarg != 0);
+            put(x, out1);
+        } else if (op == 3) {
+            M.setReference(iarg, darg, true);
+            put(M.diag(), out1);
+            put(M.source(), out2);
+        } else if (op == 4) {
+            M.relax(darg);
+            put(M.diag(), out1);
+            put(M.source(), out2);
+        } else if (op == 5) {
+            put(M.D()(), out1);
+        } else if (op == 6) {
+            put(M.A()().internalField(), out1);
+        } else if (op == 7) {
+            GeometricField<scalar, fvsPatchField, surfaceMesh> phi;
+            phi.mesh_ = &C.mesh;
+            phi.internal_.setSize(nF);
+            phi.boundary_.p_.resize((size_t)nP);
+            for (int p = 0; p < nP; p++) phi.boundary_.p_[(size_t)p].setSize(patchStart[p + 1] - patchStart[p]);
+            M.flux(phi);
+            put(phi.internal_, out1);
+            for (int p = 0; p < nP; p++) put(phi.boundary_.p_[(size_t)p], out2 + patchStart[p]);
+        } else if (op == 8) {
+            put(M.H()().internalField(), out1);
+        } else if (op == 9) {
+            put(M.residual()(), out1);
+        } else if (op == 10) {
+            M.solveSegregated(dictionary());
+            std::copy(lduMatrix::solver::seenDiag.begin(), lduMatrix::solver::seenDiag.end(), out1);
+            std::copy(lduMatrix::solver::seenSource.begin(), lduMatrix::solver::seenSource.end(), out2);
+            put(M.diag(), out3);
+        } else
+            return -2;
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+}

@@ -491,3 +491,50 @@ class InterfaceAgglomeration:
         if _libgi is not None and getattr(self, "h", None) is not None:
             _libgi.ref_ia_destroy(self.h)
             self.h = None
+
+
+_LIB_FVM = os.path.join(_HERE, "_ref", "libref_fvm.so")
+_libfvm = None
+FVM_OPS = dict(addBoundaryDiag=0, addCmptAvBoundaryDiag=1, addBoundarySource=2, setReference=3, relax=4, D=5, A=6, flux=7,
+               H=8, residual=9, solveSegregated=10)
+
+
+def fvm(op, nCells, lower, upper, patches, V, psi, diag, upperC, lowerC, source, iarg=0, darg=0.0, x=None):
+    """The reference's fvMatrix<scalar> (fvMatrix.C, fvScalarMatrix.C compiled for the host) on one matrix.
+    patches: list of dict(faceCells, ic, bc, coupled=False, pnf=None) in mesh order.  Returns the op's outputs:
+    addBoundary*: the updated x; setReference / relax: (diag, source); D, A, H, residual: the field; flux: (internal faces,
+    boundary faces flat); solveSegregated: (diagonal seen by the solver, source seen by the solver, diagonal afterwards)."""
+    global _libfvm
+    if _libfvm is None:
+        if not available() or not os.path.exists(_LIB_FVM):
+            raise RuntimeError("oracle/_ref/libref_fvm.so is not built (needs /root/reference)")
+        _libfvm = C.CDLL(_LIB_FVM)
+    l, u = _i(lower), _i(upper)
+    n, nF = int(nCells), len(l)
+    os_, ls, lo = ldu_arrays(n, l, u)
+    ps = np.zeros(len(patches) + 1, np.int32)
+    for k, p in enumerate(patches):
+        ps[k + 1] = ps[k] + len(p["faceCells"])
+    cat = lambda key, dt, dflt=None: (np.concatenate([np.asarray(p.get(key) if p.get(key) is not None else dflt(p), dt).ravel()
+                                                      for p in patches]) if patches else np.zeros(0, dt))
+    fc = _i(cat("faceCells", np.int32))
+    ic, bc = _d(cat("ic", float)), _d(cat("bc", float))
+    pnf = _d(cat("pnf", float, lambda p: np.zeros(len(p["faceCells"]))))
+    coupled = _i([1 if p.get("coupled") else 0 for p in patches] or [0])
+    tot = int(ps[-1])
+    o1, o2, o3 = np.zeros(max(n, nF, 1)), np.zeros(max(n, tot, 1)), np.zeros(max(n, 1))
+    xin = _d(np.zeros(n) if x is None else x)
+    lowp = None if lowerC is None else _p(_d(lowerC))
+    d = [_d(a) for a in (V, psi, diag, upperC, source)]
+    rc = _libfvm.ref_fvm(FVM_OPS[op], n, nF, _p(l), _p(u), _p(_i(os_)), _p(_i(ls)), _p(_i(lo)), len(patches), _p(ps), _p(fc),
+                         _p(coupled), _p(pnf), _p(d[0]), _p(d[1]), _p(d[2]), _p(d[3]), lowp, _p(d[4]), _p(ic), _p(bc),
+                         int(iarg), C.c_double(darg), _p(xin), _p(o1), _p(o2), _p(o3))
+    if rc != 0:
+        raise RuntimeError(f"the reference code raised a FatalError (rc {rc})")
+    if op in ("addBoundaryDiag", "addCmptAvBoundaryDiag", "addBoundarySource", "D", "A", "H", "residual"):
+        return o1[:n].copy()
+    if op in ("setReference", "relax"):
+        return o1[:n].copy(), o2[:n].copy()
+    if op == "flux":
+        return o1[:nF].copy(), o2[:tot].copy()
+    return o1[:n].copy(), o2[:n].copy(), o3[:n].copy()

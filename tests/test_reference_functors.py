@@ -586,3 +586,88 @@ def test_random_matrices_match_reference_code(dims, seed, symmetric, favourSpeed
     assert np.array_equal(R.ainv(x, fast, True), M.precondition("DIC", x, True))
     omega = float(rng.uniform(0.3, 1.0))
     assert np.array_equal(R.jacobi(x, b, omega, fast), M.jacobi(x, b, 1, omega=omega))
+
+
+def _fvm_patches(m, d, cyc=None):
+    """the flat wall list of tests/test_oracle_fvm.py split back into patches (+ the cyclic pair as coupled patches)"""
+    out, off = [], 0
+    for p in m.wall_patches():
+        if cyc is not None and p.name in ("xmin", "xmax"):
+            continue
+        k = len(p.faceCells)
+        out.append(dict(faceCells=p.faceCells, ic=d["ic"][off:off + k, 0], bc=d["bc"][off:off + k, 0]))
+        off += k
+    assert off == len(d["bfc"])
+    if cyc is not None:
+        for fcells, ci, cb, pnf in cyc:
+            out.append(dict(faceCells=fcells, ic=ci, bc=cb, coupled=True, pnf=pnf))
+    return out
+
+
+@pytest.mark.parametrize("case", ["poisson", "momentum0", "cyclic"])
+def test_fvmatrix_glue_matches_reference_code(meshmod, orc, case):
+    """Row a17 for scalar fields: oracle/fvm_oracle.py against the reference's own fvMatrix.C / fvScalarMatrix.C
+    (compiled for the host against oracle/ref_harness/shim_fvm/), bit for bit: boundary folding, setReference, relax, D, A,
+    H, flux, residual and what solveSegregated hands to the linear solver.  `cyclic` adds a coupled patch pair."""
+    import test_oracle_fvm as tf
+    from oracle import fvm_oracle as fo
+    from test_oracle_core import _cyclic_case
+    rng = np.random.default_rng(12)
+    cyc, kw = None, {}
+    if case == "poisson":
+        m, a, d = tf.poisson_case(meshmod, orc, (7, 6, 5))
+    elif case == "momentum0":
+        m, a, d3 = tf.momentum_case(meshmod, orc, (6, 5, 4))
+        d = dict(d3, source=d3["source"][:, 0].copy(), ic=d3["ic"][:, :1].copy(), bc=d3["bc"][:, :1].copy())
+    else:
+        m, c, ps, fc, nr, lo, hi = _cyclic_case(meshmod, "U")
+        wall = np.concatenate([p.faceCells for p in m.wall_patches() if p.name not in ("xmin", "xmax")]).astype(np.int32)
+        ic, bc = fo.fixedValue_laplacian_coeffs(np.full(len(wall), 0.01 * m.h * m.h), np.full(len(wall), 2.0 / m.h),
+                                                rng.uniform(-1, 1, (len(wall), 1)))
+        diag = c["diag"].copy()
+        np.subtract.at(diag, fc, c["int"])
+        d = dict(diag=diag, upper=c["upper"], lower=c["lower"], source=rng.uniform(-1, 1, m.nCells) * m.h ** 3, bfc=wall,
+                 ic=-ic, bc=-bc, V=m.volumes())
+        a = orc.Addr(m.nCells, m.lower, m.upper, ps, fc, neighbRank=nr)
+        kw = dict(couInt=c["int"], couBou=c["bou"])
+    x = rng.uniform(-1, 1, (m.nCells, 1))
+    mk = lambda: tf.make(orc, a, d, 1, x, **kw)
+    if case == "cyclic":
+        pnf = mk().patchNeighbourField()[:, 0]
+        n = len(lo)
+        cyc = [(lo, c["int"][:n], c["bou"][:n], pnf[:n]), (hi, c["int"][n:], c["bou"][n:], pnf[n:])]
+    P = _fvm_patches(m, d, cyc)
+    args = (m.nCells, m.lower, m.upper, P, d["V"], x[:, 0], d["diag"], d["upper"], d["lower"], np.ravel(d["source"]))
+    R = lambda op, **k: ref_ldu.fvm(op, *args, **k)
+    o = mk()
+    for op, fn in (("addBoundaryDiag", lambda v: o.addBoundaryDiag(v, 0)), ("addCmptAvBoundaryDiag", o.addCmptAvBoundaryDiag)):
+        v = d["diag"].copy()
+        fn(v)
+        assert np.array_equal(R(op, x=d["diag"]), v), op
+    for couples in (0, 1):
+        v = np.array(d["source"], float).reshape(-1, 1).copy()
+        o.addBoundarySource(v, bool(couples))
+        assert np.array_equal(R("addBoundarySource", x=np.ravel(d["source"]), iarg=couples), v[:, 0]), couples
+    assert np.array_equal(R("D"), o.D()) and np.array_equal(R("A"), o.A())
+    assert np.array_equal(R("H"), o.H()[:, 0])
+    fi, fb = R("flux")
+    oi, ob, oc = o.flux()
+    assert np.array_equal(fi, oi[:, 0]) and np.array_equal(fb, np.concatenate([ob[:, 0], oc[:, 0]]))
+    if case != "cyclic":          # the harness' lduMatrix::residual has no interface update
+        assert np.array_equal(R("residual"), o.residual())
+    for alpha in (1.0, 0.6):
+        r = mk()
+        r.relax(alpha)
+        dg, sr = R("relax", darg=alpha)
+        assert np.array_equal(dg, r.diag) and np.array_equal(sr, r.source[:, 0]), alpha
+    r = mk()
+    r.setReference(5, 0.75)
+    dg, sr = R("setReference", iarg=5, darg=0.75)
+    assert np.array_equal(dg, r.diag) and np.array_equal(sr, r.source[:, 0])
+    # solveSegregated: the diagonal and the source the linear solver is handed, and the diagonal put back afterwards
+    seenDiag, seenSource, after = R("solveSegregated")
+    v = d["diag"].copy()
+    o.addBoundaryDiag(v, 0)
+    s = np.array(d["source"], float).reshape(-1, 1).copy()
+    o.addBoundarySource(s, False)
+    assert np.array_equal(seenDiag, v) and np.array_equal(seenSource, s[:, 0]) and np.array_equal(after, d["diag"])
