@@ -2,9 +2,14 @@
 INFRASTRUCTURE ONLY, like the rest of oracle/.  numpy compositions of the C oracle's primitives; numpy rounds
 every elementwise operation separately (no contraction) and np.add.at / np.subtract.at accumulate sequentially
 in index order, which is the order of the reference's per-patch functors (ascending patch face per cell,
-patches in mesh order).  PARITY UNPINNED: fvMatrix.C needs the whole GeometricField machinery and does not
-compile against a shim; every method cites the lines it restates and tests/test_oracle_fvm.py checks it
-against dense-matrix algebra.
+patches in mesh order).  PINNED to the reference's own source: fvMatrix.H / fvMatrix.C / fvMatrixSolve.C /
+fvScalarMatrix.C compile for the host against oracle/ref_harness/shim_fvm/ (fields, GeometricField, fvMesh and
+lduMatrix reduced to what the exercised members touch; the linear solver behind solveSegregated records the
+diagonal and source it is handed) and tests/test_reference_functors.py compares, bit for bit, for scalar and
+vector fields with and without coupled patches: addBoundaryDiag / addCmptAvBoundaryDiag / addBoundarySource,
+setReference, relax, D, A, H, flux and residual (scalar), and what solveSegregated passes to the solver per
+component.  Not pinned: the residual over coupled patches (the harness' lduMatrix::residual has no interface
+update).  tests/test_oracle_fvm.py adds dense-matrix algebra and decomposed-case checks.
 
 Paths: FV/ = /root/reference/src/finiteVolume/.
 
@@ -14,7 +19,7 @@ addressing, their coefficients the matrix' interfaceIntCoeffs / interfaceBouCoef
 used for every component (what processorFvPatchField produces for vectors, coupledFvPatchField.C:116-176).
 Fields with nc components are (n, nc) arrays.
 
-Findings while restating (mirrored, not corrected):
+Findings while restating (mirrored, not corrected; the first one confirmed by running the reference's code):
  * fvMatrix<Type>::H (fvMatrix.C:1458-1485) fills Hphi with boundaryDiagCmpt*psi and then calls the two-argument
    lduMatrix::H(Hphi, psi), which starts with Hpsi = 0 (lduMatrixTemplates.C:53): the boundary-diagonal term of
    stock OpenFOAM is lost.  It vanishes anyway when internalCoeffs are equal in all components (fixedValue,
@@ -77,9 +82,9 @@ class FvMatrix:
         np.add.at(diag, self.cfc, self.couInt)
 
     def addCmptAvBoundaryDiag(self, diag):
-        """:230-243"""
+        """:230-243; a coupled patch of a vector field holds (c, c, c), whose average ((c + c) + c)/3 is not always c"""
         np.add.at(diag, self.bfc, _cmptAv(self.ic))
-        np.add.at(diag, self.cfc, self.couInt)
+        np.add.at(diag, self.cfc, _cmptAv(np.repeat(self.couInt[:, None], self.nc, axis=1)))
 
     # ---- fvMatrix.C:290-348 ---------------------------------------------------------------------------
     def addBoundarySource(self, source, couples=True, pnf=None):

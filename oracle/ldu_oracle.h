@@ -21,14 +21,16 @@
  *     agglomeration functors), the coarsest-level LU (scalarMatrices.C LUDecompose/LUBacksubstitute),
  *     the scalar face sums fvc::surfaceIntegrate / surfaceSum / gaussGrad::gradf (fvcSurfaceIntegrate.C,
  *     gaussGrad.C), the coarse processor interfaces of a decomposed case and their coefficient sums
- *     (GAMGAgglomerateLduAddressing.C interface branch, GAMGInterface.C, processorGAMGInterface.C);
+ *     (GAMGAgglomerateLduAddressing.C interface branch, GAMGInterface.C, processorGAMGInterface.C), the
+ *     fvMatrix glue of oracle/fvm_oracle.py for scalar and vector fields (fvMatrix.C, fvMatrixSolve.C,
+ *     fvScalarMatrix.C);
  *   PINNED to rounding level (the reference's vector updates run unfused on the host, here they are
  *     the FMAs nvcc emits): PCG, PBiCG, PBiCGStab loops incl. iteration counts, names, loop limits
  *     (run-time selection and normFactor -- lduMatrixSolver.C -- bit for bit);
  *   UNPINNED (restated from the source, checked by analytic properties only): the finest-level
  *     exchange of the coupled interfaces (processor send/receive, cyclic pairing), the convergence
- *     test (restated inside the shims too), the Laplacian / convection coefficient fills and the
- *     fvMatrix boundary folding.  Rows with more than three faces per side (coarse GAMG levels,
+ *     test (restated inside the shims too), the Laplacian / convection coefficient fills, the icoFoam
+ *     step of oracle/piso_oracle.py as a whole.  Rows with more than three faces per side (coarse GAMG levels,
  *     polyhedral meshes) are summed in plain row order here, the reference unrolls three per side
  *     first: same terms, different association.
  * Analytic checks (dense-matrix SpMV, adjointness, CG exactness on tiny systems, eigenpairs of the

@@ -25,6 +25,9 @@ std::vector<scalar> lduMatrix::solver::seenDiag, lduMatrix::solver::seenSource;
 int solverPerformance::debug = 0;
 int dimensionSet::debug = 0;
 template <> int fvMatrix<scalar>::debug = 0;
+template <> int fvMatrix<vector>::debug = 0;
+template <> const word zeroGradientFvPatchField<vector>::typeName("zeroGradient");
+const char *pTraits<vector>::componentNames[] = {"x", "y", "z"};
 template <> const word zeroGradientFvPatchField<scalar>::typeName("zeroGradient");
 const char *pTraits<scalar>::componentNames[] = {""};
 } // namespace Foam
@@ -32,15 +35,17 @@ using namespace Foam;
 
 namespace
 {
-struct Case {
+template <class Type> struct Case { // Type = scalar or vector; component arrays interleaved (3 doubles per vector)
     fvMesh mesh;
-    volScalarField psi;
-    std::unique_ptr<fvMatrix<scalar>> M;
+    GeometricField<Type, fvPatchField, volMesh> psi;
+    std::unique_ptr<fvMatrix<Type>> M;
+    static gpuField<Type> fld(const double *p, label n) { return gpuField<Type>(reinterpret_cast<const Type *>(p), n); }
     Case(int n, int nF, const int *l, const int *u, const int *ownerStart, const int *losortStart, const int *losort,
          int nP, const int *patchStart, const int *faceCells, const int *coupled, const double *pnf, const double *V,
          const double *psiv, const double *diag, const double *upper, const double *lower, const double *source,
          const double *ic, const double *bc)
     {
+        const int nc = sizeof(Type) / sizeof(double);
         lduAddressing &a = mesh.addr_;
         a.nCells_ = n;
         a.lower_ = labelgpuList(l, nF);
@@ -50,7 +55,7 @@ struct Case {
         a.losort_ = labelgpuList(losort, nF);
         mesh.V_.f_ = scalargpuField(V, n);
         psi.mesh_ = &mesh;
-        psi.internal_ = scalargpuField(psiv, n);
+        psi.internal_ = fld(psiv, n);
         psi.boundary_.p_.resize((size_t)nP);
         for (int p = 0; p < nP; p++) {
             const int s = patchStart[p], np = patchStart[p + 1] - s;
@@ -76,26 +81,31 @@ struct Case {
         }
         for (int p = 0; p < nP; p++) { // after the vector stopped growing: the patch fields point into it
             const int s = patchStart[p], np = patchStart[p + 1] - s;
-            fvPatchField<scalar> &pf = psi.boundary_.p_[(size_t)p];
+            fvPatchField<Type> &pf = psi.boundary_.p_[(size_t)p];
             pf.setSize(np);
             pf.faceCells_ = &mesh.boundary_.p_[(size_t)p].faceCells_;
             pf.internal_ = &psi.internal_;
             pf.coupled_ = coupled[p] != 0;
-            pf.pnf_ = scalargpuField(pnf + s, np);
+            pf.pnf_ = fld(pnf + (size_t)s * nc, np);
         }
-        M.reset(new fvMatrix<scalar>(psi, dimensionSet()));
+        M.reset(new fvMatrix<Type>(psi, dimensionSet()));
         M->diag() = tmp<scalargpuField>(new scalargpuField(diag, n));
         M->upper() = tmp<scalargpuField>(new scalargpuField(upper, nF));
         if (lower) M->lower() = tmp<scalargpuField>(new scalargpuField(lower, nF));
-        M->source() = tmp<scalargpuField>(new scalargpuField(source, n));
+        M->source() = tmp<gpuField<Type>>(new gpuField<Type>(fld(source, n)));
         for (int p = 0; p < nP; p++) {
             const int s = patchStart[p], np = patchStart[p + 1] - s;
-            M->internalCoeffs()[p] = tmp<scalargpuField>(new scalargpuField(ic + s, np));
-            M->boundaryCoeffs()[p] = tmp<scalargpuField>(new scalargpuField(bc + s, np));
+            M->internalCoeffs()[p] = tmp<gpuField<Type>>(new gpuField<Type>(fld(ic + (size_t)s * nc, np)));
+            M->boundaryCoeffs()[p] = tmp<gpuField<Type>>(new gpuField<Type>(fld(bc + (size_t)s * nc, np)));
         }
     }
 };
 void put(const scalargpuField &f, double *out) { std::copy(f.begin(), f.end(), out); }
+void put(const gpuField<vector> &f, double *out)
+{
+    const double *p = reinterpret_cast<const double *>(f.data());
+    std::copy(p, p + 3 * (size_t)f.size(), out);
+}
 } // namespace
 
 extern "C" {
@@ -110,7 +120,7 @@ int ref_fvm(int op, int n, int nF, const int *l, const int *u, const int *ownerS
             double *out3)
 {
     try {
-        Case C(n, nF, l, u, ownerStart, losortStart, losort, nP, patchStart, faceCells, coupled, pnf, V, psi, diag, upper, lower,
+        Case<scalar> C(n, nF, l, u, ownerStart, losortStart, losort, nP, patchStart, faceCells, coupled, pnf, V, psi, diag, upper, lower,
                source, ic, bc);
         fvMatrix<scalar> &M = *C.M;
         if (op == 0 || op == 1 || op == 2) {
@@ -145,6 +155,56 @@ int ref_fvm(int op, int n, int nF, const int *l, const int *u, const int *ownerS
         } else if (op == 9) {
             put(M.residual()(), out1);
         } else if (op == 10) {
+            lduMatrix::solver::seenDiag.clear();
+            lduMatrix::solver::seenSource.clear();
+            M.solveSegregated(dictionary());
+            std::copy(lduMatrix::solver::seenDiag.begin(), lduMatrix::solver::seenDiag.end(), out1);
+            std::copy(lduMatrix::solver::seenSource.begin(), lduMatrix::solver::seenSource.end(), out2);
+            put(M.diag(), out3);
+        } else
+            return -2;
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+
+/* the same for fvMatrix<vector> (component arrays interleaved): op 0 addBoundaryDiag(x, cmpt = iarg) | 1 addCmptAvBoundaryDiag |
+ * 2 addBoundarySource(x [n*3], couples = iarg) | 4 relax(darg) -> out1 diag, out2 source [n*3] | 5 D | 6 A | 8 H [n*3] (the
+ * generic fvMatrix<Type>::H) | 10 solveSegregated -> out1 three diagonals, out2 three sources as the solver sees them, one block
+ * per component, out3 the diagonal afterwards */
+int ref_fvm_vec(int op, int n, int nF, const int *l, const int *u, const int *ownerStart, const int *losortStart,
+                const int *losort, int nP, const int *patchStart, const int *faceCells, const int *coupled, const double *pnf,
+                const double *V, const double *psi, const double *diag, const double *upper, const double *lower,
+                const double *source, const double *ic, const double *bc, int iarg, double darg, const double *in1,
+                double *out1, double *out2, double *out3)
+{
+    try {
+        Case<vector> C(n, nF, l, u, ownerStart, losortStart, losort, nP, patchStart, faceCells, coupled, pnf, V, psi, diag, upper,
+                       lower, source, ic, bc);
+        fvMatrix<vector> &M = *C.M;
+        if (op == 0 || op == 1) {
+            scalargpuField x(in1, n);
+            if (op == 0) M.addBoundaryDiag(x, (direction)iarg);
+            if (op == 1) M.addCmptAvBoundaryDiag(x);
+            put(x, out1);
+        } else if (op == 2) {
+            gpuField<vector> x(reinterpret_cast<const vector *>(in1), n);
+            M.addBoundarySource(x, iarg != 0);
+            put(x, out1);
+        } else if (op == 4) {
+            M.relax(darg);
+            put(M.diag(), out1);
+            put(M.source(), out2);
+        } else if (op == 5) {
+            put(M.D()(), out1);
+        } else if (op == 6) {
+            put(M.A()().internalField(), out1);
+        } else if (op == 8) {
+            put(M.H()().internalField(), out1);
+        } else if (op == 10) {
+            lduMatrix::solver::seenDiag.clear();
+            lduMatrix::solver::seenSource.clear();
             M.solveSegregated(dictionary());
             std::copy(lduMatrix::solver::seenDiag.begin(), lduMatrix::solver::seenDiag.end(), out1);
             std::copy(lduMatrix::solver::seenSource.begin(), lduMatrix::solver::seenSource.end(), out2);

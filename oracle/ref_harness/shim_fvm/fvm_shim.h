@@ -91,6 +91,64 @@ inline scalar cmptAv(scalar x) { return x; }
 using std::max;
 using std::min;
 
+// Vector<Cmpt> reduced to what fvMatrix<vector> touches; component-wise operators as VectorSpaceI.H defines them
+template <class Cmpt> class Vector
+{
+public:
+    Cmpt v_[3];
+    enum { nComponents = 3, rank = 1 };
+    typedef Vector<label> labelType;
+    Vector() {}
+    Vector(Cmpt x, Cmpt y, Cmpt z) : v_{x, y, z} {}
+    Cmpt &operator[](direction d) { return v_[d]; }
+    const Cmpt &operator[](direction d) const { return v_[d]; }
+    void operator+=(const Vector &o)
+    {
+        for (int i = 0; i < 3; i++) v_[i] += o.v_[i];
+    }
+    void operator-=(const Vector &o)
+    {
+        for (int i = 0; i < 3; i++) v_[i] -= o.v_[i];
+    }
+    void operator/=(scalar s)
+    {
+        for (int i = 0; i < 3; i++) v_[i] /= s;
+    }
+    void operator*=(scalar s)
+    {
+        for (int i = 0; i < 3; i++) v_[i] *= s;
+    }
+};
+typedef Vector<scalar> vector;
+template <class V, int r> struct powProduct;
+template <> struct powProduct<Vector<label>, 1> {
+    typedef Vector<label> type;
+};
+template <> struct pTraits<Vector<label>> {
+    static const Vector<label> zero;
+};
+inline const Vector<label> pTraits<Vector<label>>::zero(0, 0, 0);
+inline Vector<label> pow(const Vector<label> &v, const Vector<label> &) { return v; }   // solutionD: every direction solved
+template <> struct pTraits<vector> {
+    static const vector zero, one;
+    enum { nComponents = 3 };
+    static const char *componentNames[];
+};
+inline const vector pTraits<vector>::zero(0, 0, 0);
+inline const vector pTraits<vector>::one(1, 1, 1);
+inline vector operator+(const vector &a, const vector &b) { return vector(a.v_[0] + b.v_[0], a.v_[1] + b.v_[1], a.v_[2] + b.v_[2]); }
+inline vector operator-(const vector &a, const vector &b) { return vector(a.v_[0] - b.v_[0], a.v_[1] - b.v_[1], a.v_[2] - b.v_[2]); }
+inline vector operator-(const vector &a) { return vector(-a.v_[0], -a.v_[1], -a.v_[2]); }
+inline vector operator*(scalar s, const vector &a) { return vector(s * a.v_[0], s * a.v_[1], s * a.v_[2]); }
+inline vector operator*(const vector &a, scalar s) { return vector(a.v_[0] * s, a.v_[1] * s, a.v_[2] * s); }
+inline vector operator/(const vector &a, scalar s) { return vector(a.v_[0] / s, a.v_[1] / s, a.v_[2] / s); }
+inline scalar component(const vector &a, direction d) { return a.v_[d]; }
+inline vector cmptMultiply(const vector &a, const vector &b) { return vector(a.v_[0] * b.v_[0], a.v_[1] * b.v_[1], a.v_[2] * b.v_[2]); }
+inline vector cmptMag(const vector &a) { return vector(std::fabs(a.v_[0]), std::fabs(a.v_[1]), std::fabs(a.v_[2])); }
+inline scalar cmptMax(const vector &a) { return std::max(std::max(a.v_[0], a.v_[1]), a.v_[2]); }   // VectorSpaceI.H:402-423
+inline scalar cmptMin(const vector &a) { return std::min(std::min(a.v_[0], a.v_[1]), a.v_[2]); }
+inline scalar cmptAv(const vector &a) { return ((a.v_[0] + a.v_[1]) + a.v_[2]) / 3; }              // :428-447
+
 struct refCount {
 };
 struct zero {
@@ -140,7 +198,8 @@ public:
         for (auto &e : this->v_) e = -e;
     }
     tmp<gpuField<scalar>> component(direction) const;
-    void replace(direction, const gpuField<scalar> &f) { this->v_.assign(f.begin(), f.end()); }
+    void replace(direction d, const gpuField<scalar> &f);
+    void replace(direction d, const tmp<gpuField<scalar>> &f);
     void operator+=(const gpuField &o)
     {
         for (label i = 0; i < this->size(); i++) this->v_[(size_t)i] += o.data()[i];
@@ -179,8 +238,7 @@ template <class A, class B, class R> struct multiplyOperatorFunctor {
 // coupled-matrix solve and component bookkeeping: named by the parts of the sources that only have to parse
 template <class Type, class DType, class LUType> class LduMatrix;
 template <class Type> class SolverPerformance;
-template <class T> class Vector;
-template <class V, int r> struct powProduct;
+
 
 template <class T> class tmp
 {
@@ -211,11 +269,31 @@ template <class T> gpuField<T>::gpuField(const tmp<gpuField<T>> &t) : gpuList<T>
 template <class T> void gpuField<T>::operator=(const tmp<gpuField<T>> &t) { this->v_.assign(t().begin(), t().end()); }
 template <class T> void gpuField<T>::operator+=(const tmp<gpuField<T>> &t) { *this += t(); }
 template <class T> void gpuField<T>::operator-=(const tmp<gpuField<T>> &t) { *this -= t(); }
-template <class T> tmp<gpuField<scalar>> gpuField<T>::component(direction) const
+template <class T> tmp<gpuField<scalar>> gpuField<T>::component(direction d) const
 {
-    return tmp<gpuField<scalar>>(new gpuField<scalar>(this->data(), this->size()));
+    gpuField<scalar> *r = new gpuField<scalar>(this->size());
+    for (label i = 0; i < this->size(); i++) r->data()[i] = Foam::component(this->data()[i], d);
+    return tmp<gpuField<scalar>>(r);
 }
-inline void component(scalargpuField &out, const scalargpuField &f, direction) { out = tmp<scalargpuField>(f); }
+template <> inline void gpuField<scalar>::replace(direction, const gpuField<scalar> &f) { this->v_.assign(f.begin(), f.end()); }
+template <> inline void gpuField<vector>::replace(direction d, const gpuField<scalar> &f)
+{
+    for (label i = 0; i < this->size(); i++) this->v_[(size_t)i].v_[d] = f.data()[i];
+}
+template <class T> void gpuField<T>::replace(direction d, const tmp<gpuField<scalar>> &f) { replace(d, f()); }
+template <class T> void component(scalargpuField &out, const gpuField<T> &f, direction d) { out = f.component(d); }
+inline tmp<gpuField<vector>> operator*(const tmp<scalargpuField> &a, const gpuField<vector> &b)
+{
+    gpuField<vector> *r = new gpuField<vector>(b.size());
+    for (label i = 0; i < b.size(); i++) r->data()[i] = a().data()[i] * b.data()[i];
+    return tmp<gpuField<vector>>(r);
+}
+inline tmp<scalargpuField> cmptAv(const gpuField<vector> &f)
+{
+    scalargpuField *r = new scalargpuField(f.size());
+    for (label i = 0; i < f.size(); i++) r->data()[i] = cmptAv(f.data()[i]);
+    return tmp<scalargpuField>(r);
+}
 // the field algebra relax() and D()/A() spell out (gpuFieldFunctions.C: one rounded operation per element)
 #define SHIM_BINOP(op)                                                                              \
     inline tmp<scalargpuField> operator op(const scalargpuField &a, const scalargpuField &b)        \
@@ -270,7 +348,12 @@ public:
     const Field<T> &operator[](label i) const { return *v_[(size_t)i]; }
     void set(label i, Field<T> *p) { v_[(size_t)i].reset(p); }
     void set(label i, const tmp<Field<T>> &t) { v_[(size_t)i] = std::make_shared<Field<T>>(t()); }
-    FieldField<Field, scalar> component(direction) const { return *this; }
+    FieldField<Field, scalar> component(direction d) const
+    {
+        FieldField<Field, scalar> r(size());
+        forAll((*this), i) r.set(i, (*this)[i].component(d));
+        return r;
+    }
     void negate()
     {
         for (auto &p : v_) p->negate();
@@ -366,7 +449,10 @@ public:
     const labelgpuList &patchSortStartAddr(label p) const { return patchSortStart_[(size_t)p]; }
 };
 class fvMesh;
+// the coupled patches as the component loop of solveSegregated sees them: result[faceCells] -= coeffs*pnf[cmpt]
+// (coupledFvPatchField::updateInterfaceMatrix, lduAddressingFunctors.H:237-262 -- pinned through libref_ldu)
 struct lduInterfaceFieldPtrsList {
+    std::vector<std::function<void(const gpuField<scalar> &, gpuField<scalar> &, direction)>> update;
 };
 class solverPerformance
 {
@@ -409,8 +495,8 @@ public:
         void read(const dictionary &) {}
         solverPerformance solve(scalargpuField &, const scalargpuField &source, const direction = 0) const
         {
-            seenDiag.assign(m_.diag().begin(), m_.diag().end());
-            seenSource.assign(source.begin(), source.end());
+            seenDiag.insert(seenDiag.end(), m_.diag().begin(), m_.diag().end());      // one block per component solved
+            seenSource.insert(seenSource.end(), source.begin(), source.end());
             return solverPerformance();
         }
     };
@@ -492,9 +578,11 @@ public:
                               scalargpuField &, const direction) const
     {
     }
-    void updateMatrixInterfaces(const FieldField<gpuField, scalar> &, const lduInterfaceFieldPtrsList &, const scalargpuField &,
-                                scalargpuField &, const direction) const
+    void updateMatrixInterfaces(const FieldField<gpuField, scalar> &coeffs, const lduInterfaceFieldPtrsList &ifs,
+                                const scalargpuField &, scalargpuField &result, const direction cmpt) const
     {
+        for (size_t p = 0; p < ifs.update.size(); p++)
+            if (ifs.update[p]) ifs.update[p](coeffs[(label)p], result, cmpt);
     }
 };
 
@@ -565,9 +653,7 @@ struct VolumeField {
     scalargpuField f_;
     const scalargpuField &getField() const { return f_; }
 };
-struct Vector3Label {
-    label v[3] = {1, 1, 1};
-};
+
 class fvMesh
 {
 public:
@@ -594,7 +680,7 @@ public:
     struct data {
         template <class T> T lookupOrDefault(const word &, const T &d) const { return d; }
     };
-    Vector3Label solutionD() const { return Vector3Label(); }
+    Vector<label> solutionD() const { return Vector<label>(1, 1, 1); }
 };
 inline const lduAddressing &lduMatrix::lduAddr() const { return mesh_.lduAddr(); }
 // The row operations below are the ones pinned through libref_ldu (lduMatrixATmul.C, lduMatrixTemplates.C,
@@ -655,7 +741,23 @@ public:
         PatchField<Type> &operator[](label i) { return p_[(size_t)i]; }
         const PatchField<Type> &operator[](label i) const { return p_[(size_t)i]; }
         void updateCoeffs() {}
-        lduInterfaceFieldPtrsList scalarInterfaces() const { return lduInterfaceFieldPtrsList(); }
+        lduInterfaceFieldPtrsList scalarInterfaces() const
+        {
+            lduInterfaceFieldPtrsList l;
+            l.update.resize(p_.size());
+            for (size_t p = 0; p < p_.size(); p++) {
+                if (!p_[p].coupled()) continue;
+                const PatchField<Type> *pf = &p_[p];
+                l.update[p] = [pf](const gpuField<scalar> &c, gpuField<scalar> &result, direction d) {
+                    forAll((*pf->faceCells_), i)
+                    {
+                        const scalar v = c.data()[i] * component(pf->pnf_.data()[i], d);
+                        result.data()[pf->faceCells_->data()[i]] = result.data()[pf->faceCells_->data()[i]] + (-v);
+                    }
+                };
+            }
+            return l;
+        }
         lduInterfaceFieldPtrsList interfaces() const { return lduInterfaceFieldPtrsList(); }
     };
     const fvMesh *mesh_ = nullptr;
@@ -702,6 +804,7 @@ public:
     dimensionSet dimensions() const { return dimensionSet(); }
 };
 typedef fvPatchField<scalar> fvPatchScalarField;
+typedef GeometricField<vector, fvPatchField, volMesh> volVectorField;
 typedef GeometricField<scalar, fvPatchField, volMesh> volScalarField;
 typedef GeometricField<scalar, fvsPatchField, surfaceMesh> surfaceScalarField;
 typedef DimensionedField<scalar, volMesh> volScalarFieldDimensioned;

@@ -499,11 +499,13 @@ FVM_OPS = dict(addBoundaryDiag=0, addCmptAvBoundaryDiag=1, addBoundarySource=2, 
                H=8, residual=9, solveSegregated=10)
 
 
-def fvm(op, nCells, lower, upper, patches, V, psi, diag, upperC, lowerC, source, iarg=0, darg=0.0, x=None):
+def fvm(op, nCells, lower, upper, patches, V, psi, diag, upperC, lowerC, source, iarg=0, darg=0.0, x=None, nc=1):
     """The reference's fvMatrix<scalar> (fvMatrix.C, fvScalarMatrix.C compiled for the host) on one matrix.
     patches: list of dict(faceCells, ic, bc, coupled=False, pnf=None) in mesh order.  Returns the op's outputs:
     addBoundary*: the updated x; setReference / relax: (diag, source); D, A, H, residual: the field; flux: (internal faces,
-    boundary faces flat); solveSegregated: (diagonal seen by the solver, source seen by the solver, diagonal afterwards)."""
+    boundary faces flat); solveSegregated: (diagonal seen by the solver, source seen by the solver, diagonal afterwards).
+    nc = 3: fvMatrix<vector> (fields (n, 3), patch ic / bc / pnf (faces, 3)); setReference, flux and residual are scalar
+    only; solveSegregated returns one (nCells) block per component in the first two outputs."""
     global _libfvm
     if _libfvm is None:
         if not available() or not os.path.exists(_LIB_FVM):
@@ -519,22 +521,27 @@ def fvm(op, nCells, lower, upper, patches, V, psi, diag, upperC, lowerC, source,
                                                       for p in patches]) if patches else np.zeros(0, dt))
     fc = _i(cat("faceCells", np.int32))
     ic, bc = _d(cat("ic", float)), _d(cat("bc", float))
-    pnf = _d(cat("pnf", float, lambda p: np.zeros(len(p["faceCells"]))))
+    pnf = _d(cat("pnf", float, lambda p: np.zeros(len(p["faceCells"]) * nc)))
     coupled = _i([1 if p.get("coupled") else 0 for p in patches] or [0])
     tot = int(ps[-1])
-    o1, o2, o3 = np.zeros(max(n, nF, 1)), np.zeros(max(n, tot, 1)), np.zeros(max(n, 1))
-    xin = _d(np.zeros(n) if x is None else x)
+    o1, o2, o3 = np.zeros(max(n, nF, 1) * 3), np.zeros(max(n, tot, 1) * 3), np.zeros(max(n, 1))
+    xin = _d(np.zeros(n * nc) if x is None else np.ravel(x))
     lowp = None if lowerC is None else _p(_d(lowerC))
-    d = [_d(a) for a in (V, psi, diag, upperC, source)]
-    rc = _libfvm.ref_fvm(FVM_OPS[op], n, nF, _p(l), _p(u), _p(_i(os_)), _p(_i(ls)), _p(_i(lo)), len(patches), _p(ps), _p(fc),
+    d = [_d(np.ravel(a)) for a in (V, psi, diag, upperC, source)]
+    rc = (_libfvm.ref_fvm if nc == 1 else _libfvm.ref_fvm_vec)(FVM_OPS[op], n, nF, _p(l), _p(u), _p(_i(os_)), _p(_i(ls)), _p(_i(lo)), len(patches), _p(ps), _p(fc),
                          _p(coupled), _p(pnf), _p(d[0]), _p(d[1]), _p(d[2]), _p(d[3]), lowp, _p(d[4]), _p(ic), _p(bc),
                          int(iarg), C.c_double(darg), _p(xin), _p(o1), _p(o2), _p(o3))
     if rc != 0:
         raise RuntimeError(f"the reference code raised a FatalError (rc {rc})")
-    if op in ("addBoundaryDiag", "addCmptAvBoundaryDiag", "addBoundarySource", "D", "A", "H", "residual"):
+    vec = lambda a: a[:n * nc].reshape(n, nc).copy() if nc > 1 else a[:n].copy()
+    if op in ("addBoundaryDiag", "addCmptAvBoundaryDiag", "D", "A", "residual"):
         return o1[:n].copy()
+    if op in ("addBoundarySource", "H"):
+        return vec(o1)
     if op in ("setReference", "relax"):
-        return o1[:n].copy(), o2[:n].copy()
+        return o1[:n].copy(), vec(o2)
     if op == "flux":
         return o1[:nF].copy(), o2[:tot].copy()
-    return o1[:n].copy(), o2[:n].copy(), o3[:n].copy()
+    if nc == 1:
+        return o1[:n].copy(), o2[:n].copy(), o3[:n].copy()
+    return o1[:n * nc].reshape(nc, n).copy(), o2[:n * nc].reshape(nc, n).copy(), o3[:n].copy()

@@ -21,6 +21,14 @@ __device__ __forceinline__ double cmpt_av(const double *v, int nc) // VectorSpac
     return __ddiv_rn(s, (double)nc);
 }
 
+// the component average of a coupled coefficient: the patch holds (c, c, c) for a vector field, and ((c + c) + c)/3 is
+// not always c
+__device__ __forceinline__ double coupled_av(double c, int nc)
+{
+    if (nc == 1) return c;
+    return __ddiv_rn(__dadd_rn(__dadd_rn(c, c), c), 3.0);
+}
+
 // out[c] = in[c] + sum_b internalCoeffs(bf)[cmpt | average] + sum_coupled interfaceIntCoeffs(pf)
 __global__ void boundary_diag_kernel(int nCells, BoundaryLists L, const double *__restrict__ ic, int nc, int cmpt,
                                      const double *__restrict__ couInt, const double *in, double *out)
@@ -34,7 +42,8 @@ __global__ void boundary_diag_kernel(int nCells, BoundaryLists L, const double *
             acc = __dadd_rn(acc, cmpt >= 0 ? v[cmpt] : cmpt_av(v, nc));
         }
     if (L.cStart)
-        for (int j = L.cStart[c]; j < L.cStart[c + 1]; j++) acc = __dadd_rn(acc, couInt[L.cFaces[j]]);
+        for (int j = L.cStart[c]; j < L.cStart[c + 1]; j++)
+            acc = __dadd_rn(acc, cmpt >= 0 ? couInt[L.cFaces[j]] : coupled_av(couInt[L.cFaces[j]], nc));
     out[c] = acc;
 }
 
@@ -100,7 +109,7 @@ __global__ void A_kernel(int nCells, BoundaryLists L, const double *__restrict__
         for (int j = L.bStart[c]; j < L.bStart[c + 1]; j++)
             acc = __dadd_rn(acc, cmpt_av(ic + (size_t)L.bFaces[j] * nc, nc));
     if (L.cStart)
-        for (int j = L.cStart[c]; j < L.cStart[c + 1]; j++) acc = __dadd_rn(acc, couInt[L.cFaces[j]]);
+        for (int j = L.cStart[c]; j < L.cStart[c + 1]; j++) acc = __dadd_rn(acc, coupled_av(couInt[L.cFaces[j]], nc));
     out[c] = __ddiv_rn(acc, V[c]);
 }
 

@@ -671,3 +671,83 @@ def test_fvmatrix_glue_matches_reference_code(meshmod, orc, case):
     s = np.array(d["source"], float).reshape(-1, 1).copy()
     o.addBoundarySource(s, False)
     assert np.array_equal(seenDiag, v) and np.array_equal(seenSource, s[:, 0]) and np.array_equal(after, d["diag"])
+
+
+@pytest.mark.parametrize("case", ["momentum", "cyclic"])
+def test_vector_fvmatrix_glue_matches_reference_code(meshmod, orc, case):
+    """Row a17 for vector fields: fvMatrix<vector> of the reference (fvMatrix.C, fvMatrixSolve.C compiled for the host)
+    against oracle/fvm_oracle.py, bit for bit: component-wise boundary folding, the component average, relax with the
+    largest / smallest component of the internal coefficients, H -- including the reference's loss of the boundary-diagonal
+    term -- and the component loop of solveSegregated with the coupled source going in once and out per component."""
+    import test_oracle_fvm as tf
+    from oracle import fvm_oracle as fo
+    from test_oracle_core import _cyclic_case
+    rng = np.random.default_rng(13)
+    cyc, kw = None, {}
+    if case == "momentum":
+        m, a, d = tf.momentum_case(meshmod, orc, (6, 5, 4))
+        d = dict(d, ic=d["ic"] * np.array([1.0, 2.0, 3.0]))      # component-dependent internal coefficients
+        walls = m.wall_patches()
+    else:
+        m, c, ps, fc, nr, lo, hi = _cyclic_case(meshmod, "U")
+        walls = [p for p in m.wall_patches() if p.name not in ("xmin", "xmax")]
+        wall = np.concatenate([p.faceCells for p in walls]).astype(np.int32)
+        ic, bc = fo.fixedValue_laplacian_coeffs(np.full(len(wall), 0.01 * m.h * m.h), np.full(len(wall), 2.0 / m.h),
+                                                rng.uniform(-1, 1, (len(wall), 3)))
+        diag = c["diag"].copy()
+        np.subtract.at(diag, fc, c["int"])
+        d = dict(diag=diag, upper=c["upper"], lower=c["lower"], source=rng.uniform(-1, 1, (m.nCells, 3)) * m.h ** 3, bfc=wall,
+                 ic=-ic * np.array([1.0, 0.5, 2.0]), bc=-bc, V=m.volumes())
+        a = orc.Addr(m.nCells, m.lower, m.upper, ps, fc, neighbRank=nr)
+        kw = dict(couInt=c["int"], couBou=c["bou"])
+    x = rng.uniform(-1, 1, (m.nCells, 3))
+    mk = lambda: tf.make(orc, a, d, 3, x, **kw)
+    P, off = [], 0
+    for p in walls:
+        k = len(p.faceCells)
+        P.append(dict(faceCells=p.faceCells, ic=d["ic"][off:off + k], bc=d["bc"][off:off + k]))
+        off += k
+    if case == "cyclic":
+        pnf = mk().patchNeighbourField()
+        n = len(lo)
+        three = lambda v: np.repeat(v[:, None], 3, axis=1)       # the coupled coefficient of every component
+        P += [dict(faceCells=lo, ic=three(c["int"][:n]), bc=three(c["bou"][:n]), coupled=True, pnf=pnf[:n]),
+              dict(faceCells=hi, ic=three(c["int"][n:]), bc=three(c["bou"][n:]), coupled=True, pnf=pnf[n:])]
+    args = (m.nCells, m.lower, m.upper, P, d["V"], x, d["diag"], d["upper"], d["lower"], d["source"])
+    R = lambda op, **k: ref_ldu.fvm(op, *args, nc=3, **k)
+    o = mk()
+    for cmpt in range(3):
+        v = d["diag"].copy()
+        o.addBoundaryDiag(v, cmpt)
+        assert np.array_equal(R("addBoundaryDiag", x=d["diag"], iarg=cmpt), v), cmpt
+    v = d["diag"].copy()
+    o.addCmptAvBoundaryDiag(v)
+    assert np.array_equal(R("addCmptAvBoundaryDiag", x=d["diag"]), v)
+    for couples in (0, 1):
+        v = d["source"].copy()
+        o.addBoundarySource(v, bool(couples))
+        assert np.array_equal(R("addBoundarySource", x=d["source"], iarg=couples), v), couples
+    assert np.array_equal(R("D"), o.D()) and np.array_equal(R("A"), o.A())
+    # H: the reference's result is the oracle's default (the boundary-diagonal term of stock OpenFOAM is lost) ...
+    Href = R("H")
+    assert np.array_equal(Href, o.H())
+    # ... and differs from the stock expression when the internal coefficients differ between components
+    assert not np.allclose(Href, o.H(boundaryDiagInH=True))
+    for alpha in (1.0, 0.6):
+        r = mk()
+        r.relax(alpha)
+        dg, sr = R("relax", darg=alpha)
+        assert np.array_equal(dg, r.diag) and np.array_equal(sr, r.source), alpha
+    # the component loop: diagonals and sources the solver is handed, per component
+    seenDiag, seenSource, after = R("solveSegregated")
+    src = d["source"].copy()
+    o.addBoundarySource(src, True)
+    pn = o.patchNeighbourField() if case == "cyclic" else None
+    for k in range(3):
+        v = d["diag"].copy()
+        o.addBoundaryDiag(v, k)
+        sk = np.ascontiguousarray(src[:, k])
+        if pn is not None:
+            np.subtract.at(sk, o.cfc, o.couBou * pn[:, k])
+        assert np.array_equal(seenDiag[k], v) and np.array_equal(seenSource[k], sk), k
+    assert np.array_equal(after, d["diag"])
