@@ -28,8 +28,7 @@
  *     the FMAs nvcc emits): PCG, PBiCG, PBiCGStab loops incl. iteration counts, names, loop limits
  *     (run-time selection and normFactor -- lduMatrixSolver.C -- bit for bit);
  *   UNPINNED (restated from the source, checked by analytic properties only): the finest-level
- *     exchange of the coupled interfaces (processor send/receive, cyclic pairing), the convergence
- *     test (restated inside the shims too), the Laplacian / convection coefficient fills, the icoFoam
+ *     exchange of the coupled interfaces (processor send/receive, cyclic pairing), the Laplacian / convection coefficient fills, the icoFoam
  *     step of oracle/piso_oracle.py as a whole.  Rows with more than three faces per side (coarse GAMG levels,
  *     polyhedral meshes) are summed in plain row order here, the reference unrolls three per side
  *     first: same terms, different association.

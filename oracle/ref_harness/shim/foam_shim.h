@@ -319,7 +319,9 @@ public:
 
 template <class T> struct pTraits;
 template <> struct pTraits<scalar> {
-    static constexpr scalar zero = 0.0;
+    static constexpr scalar zero = 0.0, one = 1.0;
+    enum { nComponents = 1 };
+    static constexpr const char *componentNames[1] = {""};
 };
 struct FatalStream {
     template <class T> FatalStream &operator<<(const T &) { return *this; }

@@ -1,13 +1,13 @@
 /*
  * solver_shim.h -- what the reference's solver sources (PCG.C, PBiCG.C, PBiCGStab.C,
  * AINVPreconditioner.C, diagonalPreconditioner.C) need around them to compile for the host:
- * words and a flat controls "dictionary", solverPerformance, the class declarations of lduMatrix::solver
+ * words and a flat controls "dictionary", what SolverPerformance.H / .C name around them (those two files are the
+ * reference's, included by path: convergence and singularity tests), the class declarations of lduMatrix::solver
  * (defined by the reference's lduMatrixSolver.C: New with its run-time selection tables, readControls,
  * normFactor) and ::preconditioner / ::smoother, a miniature of the run-time selection tables, the scratch-vector cache, serial global sums.  TEST INFRASTRUCTURE
  * ONLY.  The iteration loops, the order of their operations and their loop conditions are the
  * reference's (included by path); what is restated HERE, because the reference's versions live in
  * files tied to its I/O and run-time-selection machinery, is:
- *   solverPerformance::checkConvergence / checkSingularity   SolverPerformance.C:32-43, 74-85
  *   gSumProd / gSumMag / gAverage as index-order serial sums  gpuFieldCommonFunctions.C:420-636
  */
 #ifndef SOLVER_SHIM_H
@@ -234,47 +234,56 @@ inline scalar gAverage(const scalargpuField &f, int)
     return s / f.size();
 }
 
-class solverPerformance // SolverPerformance.H/.C
+// ---- SolverPerformance<Type>: the REFERENCE'S OWN SolverPerformance.H / .C (checkConvergence, checkSingularity,
+// singular, max, print) are included below by path; this block is what those two files name around them ----
+template <class T, unsigned N> class FixedList
 {
-    word solverName_, fieldName_;
-    scalar initialResidual_, finalResidual_;
-    label noIterations_;
-    bool converged_, singular_;
+    T v_[N];
 
 public:
-    static constexpr scalar great_ = 1e20, small_ = 1e-20, vsmall_ = 1e-300; // SolverPerformance.H:269-275
-    solverPerformance() : initialResidual_(0), finalResidual_(0), noIterations_(0), converged_(false), singular_(false) {}
-    solverPerformance(const word &s, const word &f, scalar iRes, scalar fRes, label nIter, bool conv, bool sing)
-        : solverName_(s), fieldName_(f), initialResidual_(iRes), finalResidual_(fRes), noIterations_(nIter),
-          converged_(conv), singular_(sing)
+    FixedList() {}
+    FixedList(const T &x)
     {
+        for (unsigned i = 0; i < N; i++) v_[i] = x;
     }
-    solverPerformance(const word &s, const word &f)
-        : solverName_(s), fieldName_(f), initialResidual_(0), finalResidual_(0), noIterations_(0), converged_(false),
-          singular_(false)
+    T &operator[](label i) { return v_[i]; }
+    const T &operator[](label i) const { return v_[i]; }
+    bool operator!=(const FixedList &o) const
     {
-    }
-    const word &solverName() const { return solverName_; }
-    scalar &initialResidual() { return initialResidual_; }
-    scalar &finalResidual() { return finalResidual_; }
-    label &nIterations() { return noIterations_; }
-    bool converged() const { return converged_; }
-    bool singular() const { return singular_; }
-    bool checkConvergence(const scalar Tolerance, const scalar RelTolerance) // SolverPerformance.C:74-85
-    {
-        if (finalResidual_ < Tolerance || (RelTolerance > small_ && finalResidual_ < RelTolerance * initialResidual_))
-            converged_ = true;
-        else
-            converged_ = false;
-        return converged_;
-    }
-    template <class S> void print(S &) const {}
-    bool checkSingularity(const scalar residual) // SolverPerformance.C:32-43
-    {
-        singular_ = residual < vsmall_;
-        return singular_;
+        for (unsigned i = 0; i < N; i++)
+            if (v_[i] != o.v_[i]) return true;
+        return false;
     }
 };
+typedef NullStream Ostream;
+struct Istream {
+    void readBeginList(const char *) {}
+    void readEndList(const char *) {}
+    template <class T> Istream &operator>>(T &) { return *this; }
+};
+namespace token
+{
+enum punctuationToken { BEGIN_LIST = '(', END_LIST = ')', SPACE = ' ' };
+}
+inline scalar component(const scalar &s, const direction) { return s; }
+inline scalar cmptMultiply(const scalar &a, const scalar &b) { return a * b; }
+using std::max;
+static const scalar VSMALL = 1e-300; // doubleScalar.H
+#define ClassName(name)                             \
+    static const char *typeName_() { return name; } \
+    static const ::Foam::word typeName;             \
+    static int debug
+#define defineNamedTemplateTypeNameAndDebug(Type, DebugSwitch) \
+    template <> const ::Foam::word Type::typeName(Type::typeName_()); \
+    template <> int Type::debug(DebugSwitch)
+} // namespace Foam
+#define NoRepository
+#include "SolverPerformance.H" /* reference: class declaration; pulls SolverPerformance.C */
+namespace Foam
+{
+typedef SolverPerformance<scalar> solverPerformance;          // solverPerformance.H:40-44
+makeSolverPerformance(scalar); /* the reference's macro (SolverPerformance.H:261-276, used as in solverPerformance.C:31):
+                                  great_ 1e20, small_ 1e-20, vsmall_ VSMALL */
 
 // ---- lduMatrix::solver (lduMatrix.H:100-260), lduMatrix::preconditioner (:420-520) ----
 class lduMatrix::solver // lduMatrix.H:100-260; its member functions are the reference's lduMatrixSolver.C
