@@ -62,6 +62,7 @@ public:
     gpuList(const gpuList &parent, label n) : p_(parent.p_), n_(n) {}                  // "delegate": a view
     gpuList &operator=(const gpuList &o)
     {
+        if (n_ != o.n_ && (label)own_.size() == n_) setSize(o.n_); // an owning (or empty) list takes the size; a view does not
         for (label i = 0; i < n_ && i < o.n_; i++) p_[i] = o.p_[i];
         return *this;
     }
@@ -167,24 +168,28 @@ template <class T> tmp<gpuField<T>> operator-(const gpuField<T> &f)
 template <template <class> class Field, class T> class FieldField
 {
     label n_;
+    std::vector<const Field<T> *> p_; // optional: entries pointed at caller fields (setPtr); unset entries read as empty
 
 public:
-    explicit FieldField(label n = 0) : n_(n) {}
+    explicit FieldField(label n = 0) : n_(n), p_((size_t)n, nullptr) {}
     label size() const { return n_; }
-    const Field<T> &operator[](label) const
+    const Field<T> &operator[](label i) const
     {
         static Field<T> none;
-        return none;
+        return (i < (label)p_.size() && p_[(size_t)i]) ? *p_[(size_t)i] : none;
     }
     void set(label, const tmp<Field<T>> &) {}
+    void setPtr(label i, const Field<T> *f) { p_[(size_t)i] = f; }
 };
 
+#ifndef SHIM_REFERENCE_MATRIX_INTERFACES
 class lduInterfaceFieldPtrsList
 {
 public:
     label size() const { return 0; }
     bool set(label) const { return false; }
 };
+#endif
 
 // ---- ops.H (src/OpenFOAM/primitives/ops/ops.H:227-238 and the unary-operator functor macro) ----
 template <class T> class unityOp
@@ -241,9 +246,14 @@ public:
     const labelgpuList &ownerSortAddr() const { return ownerSort_; }
     // coupled-patch sort addressing of ONE patch (lduAddressing.C:38-167), supplied by the harness
     labelgpuList patchCells_, patchSort_, patchSortStart_;
-    const labelgpuList &patchSortCells(label) const { return patchCells_; }
-    const labelgpuList &patchSortAddr(label) const { return patchSort_; }
-    const labelgpuList &patchSortStartAddr(label) const { return patchSortStart_; }
+    // ... or of every patch, by patch index, when the harness fills these
+    std::vector<labelgpuList> patchCellsV_, patchSortV_, patchSortStartV_;
+    const labelgpuList &patchSortCells(label p) const { return patchCellsV_.empty() ? patchCells_ : patchCellsV_[(size_t)p]; }
+    const labelgpuList &patchSortAddr(label p) const { return patchSortV_.empty() ? patchSort_ : patchSortV_[(size_t)p]; }
+    const labelgpuList &patchSortStartAddr(label p) const
+    {
+        return patchSortStartV_.empty() ? patchSortStart_ : patchSortStartV_[(size_t)p];
+    }
 };
 
 // ---- lduMatrix: declarations of the members defined in the reference's lduMatrixATmul.C ----
@@ -276,6 +286,18 @@ public:
     const scalargpuField &upperSort() const { return *upperSortPtr_; }
     bool coarsestLevel() const { return coarsest_; }
     int level() const { return level_; }
+#ifdef SHIM_REFERENCE_MATRIX_INTERFACES
+    // defined by the reference (lduMatrixUpdateMatrixInterfaces.C:30-276)
+    void initMatrixInterfaces(const FieldField<gpuField, scalar> &, const lduInterfaceFieldPtrsList &,
+                              const scalargpuField &, scalargpuField &, const direction, const bool negate = false) const;
+    void updateMatrixInterfaces(const FieldField<gpuField, scalar> &, const lduInterfaceFieldPtrsList &,
+                                const scalargpuField &, scalargpuField &, const direction, const bool negate = false) const;
+    const lduSchedule &patchSchedule() const
+    {
+        static lduSchedule none;
+        return none;
+    }
+#else
     void initMatrixInterfaces(const FieldField<gpuField, scalar> &, const lduInterfaceFieldPtrsList &,
                               const scalargpuField &, scalargpuField &, const direction) const
     {
@@ -293,6 +315,8 @@ public:
                                 const scalargpuField &, scalargpuField &, const direction, bool) const
     {
     }
+
+#endif
 
     // defined by the reference (lduMatrixATmul.C:183-554)
     void Amul(scalargpuField &, const tmp<scalargpuField> &, const FieldField<gpuField, scalar> &,

@@ -1,0 +1,221 @@
+/*
+ * procfield_shim.h -- what the reference's finest-level interface exchange needs around it to compile for the host:
+ *   lduMatrixUpdateMatrixInterfaces.C          lduMatrix::initMatrixInterfaces / updateMatrixInterfaces (comms-type branches)
+ *   processorFvPatchScalarField.C              processorFvPatchField<scalar>::initInterfaceMatrixUpdate / updateInterfaceMatrix
+ *   lduAddressingFunctors.H                    matrixPatchOperation + matrixInterfaceFunctor (the update arithmetic)
+ * are included by path; declared here: lduInterfaceField, the pointer list, Pstream / UIPstream / UOPstream over an in-process
+ * mailbox (all ranks of a decomposed case live in one process), processorFvPatch, and the class declarations of
+ * coupledFvPatchField / processorFvPatchField with the members those files touch (coupledFvPatchField::updateInterfaceMatrix
+ * is the ten-line wrapper of coupledFvPatchField.C:221-257 around the reference's matrixPatchOperation).  TEST INFRASTRUCTURE ONLY.
+ */
+#ifndef PROCFIELD_SHIM_H
+#define PROCFIELD_SHIM_H
+#define SHIM_REFERENCE_MATRIX_INTERFACES
+#include <cstring>
+#include <thrust/copy.h>
+#include <map>
+#include <streambuf>
+#include <tuple>
+#include <vector>
+
+namespace Foam
+{
+typedef int label;
+class lduInterfaceField;
+class lduInterfaceFieldPtrsList
+{
+    std::vector<const lduInterfaceField *> v_;
+
+public:
+    lduInterfaceFieldPtrsList() {}
+    explicit lduInterfaceFieldPtrsList(label n) : v_((size_t)n, nullptr) {}
+    label size() const { return (label)v_.size(); }
+    bool set(label i) const { return v_[(size_t)i] != nullptr; }
+    void set(label i, const lduInterfaceField *p) { v_[(size_t)i] = p; }
+    const lduInterfaceField &operator[](label i) const { return *v_[(size_t)i]; }
+};
+struct lduScheduleEntry {
+    label patch;
+    bool init;
+};
+struct lduSchedule {
+    label size() const { return 0; }
+    lduScheduleEntry operator[](label) const { return lduScheduleEntry{0, false}; }
+};
+} // namespace Foam
+
+#include "foam_shim.h"
+
+namespace Foam
+{
+template <class T> using Field = gpuField<T>;
+
+// ---- Pstream over a mailbox: write() posts the bytes, read() registers where they go, waitRequest() delivers ----
+struct Mail {
+    static int &me()
+    {
+        static int r = 0;
+        return r;
+    }
+    static std::map<std::tuple<int, int, int>, std::vector<char>> &box()
+    {
+        static std::map<std::tuple<int, int, int>, std::vector<char>> b;
+        return b;
+    }
+    struct Pending {
+        int from, to, tag;
+        char *dst;
+        std::streamsize n;
+    };
+    static std::vector<Pending> &pending()
+    {
+        static std::vector<Pending> p;
+        return p;
+    }
+};
+struct UPstream {
+    enum commsTypes { blocking, scheduled, nonBlocking };
+    static commsTypes defaultCommsType;
+    static bool floatTransfer, gpuDirectTransfer;
+    static const char *commsTypeNames[3];
+    static bool parRun() { return true; }
+    static label nPollProcInterfaces;
+    static label nRequests() { return (label)Mail::pending().size(); }
+    // the ranks run one after the other here: request storage is kept until the harness resets the case
+    static void resetRequests(label) {}
+    static void waitRequests() {}
+    static void waitRequest(label i)
+    {
+        Mail::Pending &p = Mail::pending()[(size_t)i];
+        const std::vector<char> &m = Mail::box().at(std::make_tuple(p.from, p.to, p.tag));
+        if ((std::streamsize)m.size() != p.n) throw std::runtime_error("mailbox size");
+        std::memcpy(p.dst, m.data(), (size_t)p.n);
+    }
+};
+typedef UPstream Pstream;
+struct UIPstream {
+    static label read(UPstream::commsTypes, int fromProc, char *buf, std::streamsize n, int tag, int)
+    {
+        Mail::pending().push_back(Mail::Pending{fromProc, Mail::me(), tag, buf, n});
+        return (label)n;
+    }
+};
+struct UOPstream {
+    static bool write(UPstream::commsTypes, int toProc, const char *buf, std::streamsize n, int tag, int)
+    {
+        Mail::box()[std::make_tuple(Mail::me(), toProc, tag)].assign(buf, buf + n);
+        return true;
+    }
+};
+static FatalStream Info;
+inline int abort(FatalStream &) { throw std::runtime_error("FatalError"); }
+
+// ---- lduInterfaceField.H:60-160 ----
+class lduInterfaceField
+{
+    bool updatedMatrix_ = false;
+
+public:
+    virtual ~lduInterfaceField() {}
+    bool updatedMatrix() const { return updatedMatrix_; }
+    bool &updatedMatrix() { return updatedMatrix_; }
+    virtual bool ready() const { return true; }
+    virtual void initInterfaceMatrixUpdate(scalargpuField &, const scalargpuField &, const scalargpuField &, const direction,
+                                           const Pstream::commsTypes, const bool negate = false) const
+    {
+    }
+    virtual void updateInterfaceMatrix(scalargpuField &, const scalargpuField &, const scalargpuField &, const direction,
+                                       const Pstream::commsTypes, const bool negate = false) const = 0;
+};
+
+// ---- processorFvPatch.H / fvPatch.H: rank pair, face cells, patchInternalField, compressed transfers ----
+class fvMeshStub
+{
+public:
+    lduAddressing addr_;
+    const lduAddressing &lduAddr() const { return addr_; }
+};
+class processorFvPatch
+{
+public:
+    const fvMeshStub *mesh_;
+    label index_;
+    labelgpuList faceCells_;
+    int myProcNo_, neighbProcNo_, tag_;
+    struct BoundaryMesh {
+        const fvMeshStub *m;
+        const fvMeshStub &mesh() const { return *m; }
+    };
+    const char *name() const { return "procBoundary"; }
+    label index() const { return index_; }
+    label size() const { return faceCells_.size(); }
+    BoundaryMesh boundaryMesh() const { return BoundaryMesh{mesh_}; }
+    int myProcNo() const { return myProcNo_; }
+    int neighbProcNo() const { return neighbProcNo_; }
+    int tag() const { return tag_; }
+    int comm() const { return 0; }
+    // fvPatch::patchInternalField(f, pif): pif[i] = f[faceCells[i]] (fvPatchTemplates.C)
+    template <class T> void patchInternalField(const gpuList<T> &f, gpuField<T> &pif) const
+    {
+        pif.setSize(size());
+        for (label i = 0; i < size(); i++) pif.data()[i] = f.data()[faceCells_.data()[i]];
+    }
+    // processorLduInterface::compressedSend / compressedReceive without compression (floatTransfer off)
+    template <class T> void compressedSend(const Pstream::commsTypes ct, const gpuList<T> &f) const
+    {
+        UOPstream::write(ct, neighbProcNo_, reinterpret_cast<const char *>(f.data()), f.byteSize(), tag_, 0);
+    }
+    template <class T> void compressedReceive(const Pstream::commsTypes, gpuList<T> &f) const
+    {
+        const std::vector<char> &m = Mail::box().at(std::make_tuple(neighbProcNo_, myProcNo_, tag_));
+        if ((label)m.size() != f.byteSize()) throw std::runtime_error("mailbox size");
+        std::memcpy(f.data(), m.data(), m.size());
+    }
+};
+} // namespace Foam
+
+#include "lduAddressingFunctors.H" /* reference: matrixPatchOperation, matrixInterfaceFunctor */
+
+namespace Foam
+{
+template <class Type> class coupledFvPatchField : public lduInterfaceField
+{
+    const processorFvPatch &patch_;
+
+public:
+    coupledFvPatchField(const processorFvPatch &p) : patch_(p) {}
+    const processorFvPatch &patch() const { return patch_; }
+    label size() const { return patch_.size(); }
+    // coupledFvPatchField.C:221-257
+    void updateInterfaceMatrix(scalargpuField &result, const scalargpuField &coeffs, const scalargpuField &pnf,
+                               const bool negate) const
+    {
+        if (negate)
+            matrixPatchOperation(patch().index(), result, patch().boundaryMesh().mesh().lduAddr(),
+                                 matrixInterfaceFunctor<scalar, true>(coeffs.data(), pnf.data()));
+        else
+            matrixPatchOperation(patch().index(), result, patch().boundaryMesh().mesh().lduAddr(),
+                                 matrixInterfaceFunctor<scalar, false>(coeffs.data(), pnf.data()));
+    }
+};
+
+template <class Type> class processorFvPatchField : public coupledFvPatchField<Type> // processorFvPatchField.H:60-330
+{
+    const processorFvPatch &procPatch_;
+    mutable label outstandingSendRequest_ = -1, outstandingRecvRequest_ = -1;
+    mutable gpuField<scalar> scalargpuSendBuf_, scalargpuReceiveBuf_;
+    mutable Field<scalar> scalarSendBuf_, scalarReceiveBuf_;
+
+public:
+    static int debug;
+    processorFvPatchField(const processorFvPatch &p) : coupledFvPatchField<Type>(p), procPatch_(p) {}
+    virtual bool ready() const { return true; }
+    virtual void initInterfaceMatrixUpdate(scalargpuField &result, const scalargpuField &psiInternal,
+                                           const scalargpuField &coeffs, const direction cmpt,
+                                           const Pstream::commsTypes commsType, const bool negate = false) const;
+    virtual void updateInterfaceMatrix(scalargpuField &result, const scalargpuField &psiInternal, const scalargpuField &coeffs,
+                                       const direction cmpt, const Pstream::commsTypes commsType,
+                                       const bool negate = false) const;
+};
+} // namespace Foam
+#endif

@@ -545,3 +545,32 @@ def fvm(op, nCells, lower, upper, patches, V, psi, diag, upperC, lowerC, source,
     if nc == 1:
         return o1[:n].copy(), o2[:n].copy(), o3[:n].copy()
     return o1[:n * nc].reshape(nc, n).copy(), o2[:n * nc].reshape(nc, n).copy(), o3[:n].copy()
+
+
+_LIB_PF = os.path.join(_HERE, "_ref", "libref_procfield.so")
+_libpf = None
+
+
+def processor_interface_update(ranks, commsType="nonBlocking", negate=False, nPoll=0, gpuDirect=False):
+    """The reference's finest-level coupled-interface update over all ranks of a decomposed case (in one process):
+    lduMatrix::initMatrixInterfaces on every rank, then lduMatrix::updateMatrixInterfaces
+    (lduMatrixUpdateMatrixInterfaces.C, processorFvPatchScalarField.C, matrixPatchOperation / matrixInterfaceFunctor).
+    ranks: list of dict(nCells, patchStart, faceCells, neighbRank, coeffs, psi, result).  Returns the updated results."""
+    global _libpf
+    if _libpf is None:
+        if not available() or not os.path.exists(_LIB_PF):
+            raise RuntimeError("oracle/_ref/libref_procfield.so is not built (needs /root/reference)")
+        _libpf = C.CDLL(_LIB_PF)
+    _libpf.ref_pf_reset(len(ranks))
+    for r, d in enumerate(ranks):
+        ps, fc, nr = _i(d["patchStart"]), _i(d["faceCells"]), _i(d["neighbRank"])
+        co, psi, res = _d(d["coeffs"]), _d(d["psi"]), _d(d["result"])
+        _libpf.ref_pf_set_rank(r, int(d["nCells"]), len(ps) - 1, _p(ps), _p(fc), _p(nr), _p(co), _p(psi), _p(res))
+    if _libpf.ref_pf_update({"blocking": 0, "nonBlocking": 2}[commsType], int(bool(negate)), int(nPoll), int(bool(gpuDirect))) != 0:
+        raise RuntimeError("the reference code raised a FatalError")
+    out = []
+    for r, d in enumerate(ranks):
+        res = np.zeros(int(d["nCells"]))
+        _libpf.ref_pf_get(r, _p(res))
+        out.append(res)
+    return out
