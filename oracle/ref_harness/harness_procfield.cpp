@@ -6,6 +6,8 @@
  *   LDU/lduMatrix/lduMatrixUpdateMatrixInterfaces.C                       :30-276
  *   FV/fields/fvPatchFields/constraint/processor/processorFvPatchScalarField.C  :37-172
  *   LDU/lduAddressing/lduAddressingFunctors.H                             matrixPatchOperation, matrixInterfaceFunctor
+ *   GAMG/interfaceFields/processorGAMGInterfaceField/processorGAMGInterfaceField.H/.C  :94-248 (coarse levels)
+ *   GAMG/interfaces/GAMGInterface/GAMGInterfaceFunctors.H                 GAMGUpdateInterfaceMatrix
  * against oracle/ref_harness/shim_procfield/ (+ shim/foam_shim.h).
  */
 #include "procfield_shim.h"
@@ -15,12 +17,15 @@
 
 #include "lduMatrixUpdateMatrixInterfaces.C" /* reference */
 #include "processorFvPatchScalarField.C"     /* reference */
+#include "processorGAMGInterfaceField.H"     /* reference: class declaration */
+#include "processorGAMGInterfaceField.C"     /* reference */
 
 namespace Foam
 {
 UPstream::commsTypes UPstream::defaultCommsType = UPstream::nonBlocking;
 bool UPstream::floatTransfer = false, UPstream::gpuDirectTransfer = false;
 label UPstream::nPollProcInterfaces = 0;
+label UPstream::warnComm = -1;
 const char *UPstream::commsTypeNames[3] = {"blocking", "scheduled", "nonBlocking"};
 template <> int processorFvPatchField<scalar>::debug = 0;
 int lduMatrix::debug = 0;
@@ -34,6 +39,8 @@ struct Rank {
     fvMeshStub mesh;
     std::vector<std::unique_ptr<processorFvPatch>> patches;
     std::vector<std::unique_ptr<processorFvPatchField<scalar>>> fields;
+    std::vector<std::unique_ptr<processorGAMGInterface>> gamgPatches;     // coarse-level variant
+    std::vector<std::unique_ptr<processorGAMGInterfaceField>> gamgFields;
     std::vector<scalargpuField> coeffs;
     lduMatrix M;
     lduInterfaceFieldPtrsList interfaces;
@@ -54,7 +61,7 @@ void ref_pf_reset(int nRanks)
 
 /* one rank: cells, its coupled patches (face cells, neighbour ranks, coefficients), psi and the vector to update */
 void ref_pf_set_rank(int r, int nCells, int nPatches, const int *patchStart, const int *faceCells, const int *neighbRank,
-                     const double *coeffs, const double *psi, const double *result)
+                     const double *coeffs, const double *psi, const double *result, int gamgLevel)
 {
     Rank &R = *g_ranks[(size_t)r];
     lduAddressing &a = R.mesh.addr_;
@@ -78,6 +85,20 @@ void ref_pf_set_rank(int r, int nCells, int nPatches, const int *patchStart, con
         a.patchCellsV_.push_back(labelgpuList(cells.data(), (label)cells.size()));
         a.patchSortV_.push_back(labelgpuList(order.data(), np));
         a.patchSortStartV_.push_back(labelgpuList(start.data(), (label)start.size()));
+        R.coeffs[(size_t)p] = scalargpuField(coeffs + s, np);
+        if (gamgLevel) { // processorGAMGInterface with the cell-sorted face lists of GAMGInterface::updateAddressing
+            processorGAMGInterface *gp = new processorGAMGInterface;
+            gp->faceCells_ = labelgpuList(faceCells + s, np);
+            gp->sortCells_ = labelgpuList(cells.data(), (label)cells.size());
+            gp->cellFaces_ = labelgpuList(order.data(), np);
+            gp->cellFacesStart_ = labelgpuList(start.data(), (label)start.size());
+            gp->myProcNo_ = r;
+            gp->neighbProcNo_ = neighbRank[p];
+            gp->tag_ = 1;
+            R.gamgPatches.emplace_back(gp);
+            R.gamgFields.emplace_back(new processorGAMGInterfaceField(*gp, false, 0));
+            continue;
+        }
         processorFvPatch *pp = new processorFvPatch;
         pp->mesh_ = &R.mesh;
         pp->index_ = p;
@@ -87,10 +108,10 @@ void ref_pf_set_rank(int r, int nCells, int nPatches, const int *patchStart, con
         pp->tag_ = 1;
         R.patches.emplace_back(pp);
         R.fields.emplace_back(new processorFvPatchField<scalar>(*pp));
-        R.coeffs[(size_t)p] = scalargpuField(coeffs + s, np);
     }
     for (int p = 0; p < nPatches; p++) { // after the vectors stopped growing
-        R.interfaces.set(p, R.fields[(size_t)p].get());
+        R.interfaces.set(p, gamgLevel ? static_cast<const lduInterfaceField *>(R.gamgFields[(size_t)p].get())
+                                      : static_cast<const lduInterfaceField *>(R.fields[(size_t)p].get()));
         R.coupleCoeffs.setPtr(p, &R.coeffs[(size_t)p]);
     }
     R.M.addr_ = &a;

@@ -3,6 +3,8 @@
  *   lduMatrixUpdateMatrixInterfaces.C          lduMatrix::initMatrixInterfaces / updateMatrixInterfaces (comms-type branches)
  *   processorFvPatchScalarField.C              processorFvPatchField<scalar>::initInterfaceMatrixUpdate / updateInterfaceMatrix
  *   lduAddressingFunctors.H                    matrixPatchOperation + matrixInterfaceFunctor (the update arithmetic)
+ *   processorGAMGInterfaceField.C              the same exchange on the coarse GAMG levels (:94-248)
+ *   GAMGInterfaceFunctors.H                    GAMGUpdateInterfaceMatrix over the interface's cell-sorted face lists
  * are included by path; declared here: lduInterfaceField, the pointer list, Pstream / UIPstream / UOPstream over an in-process
  * mailbox (all ranks of a decomposed case live in one process), processorFvPatch, and the class declarations of
  * coupledFvPatchField / processorFvPatchField with the members those files touch (coupledFvPatchField::updateInterfaceMatrix
@@ -75,6 +77,7 @@ struct Mail {
 };
 struct UPstream {
     enum commsTypes { blocking, scheduled, nonBlocking };
+    static label warnComm;
     static commsTypes defaultCommsType;
     static bool floatTransfer, gpuDirectTransfer;
     static const char *commsTypeNames[3];
@@ -93,6 +96,10 @@ struct UPstream {
     }
 };
 typedef UPstream Pstream;
+struct UIPstream;
+struct UOPstream;
+typedef UIPstream IPstream;
+typedef UOPstream OPstream;
 struct UIPstream {
     static label read(UPstream::commsTypes, int fromProc, char *buf, std::streamsize n, int tag, int)
     {
@@ -217,5 +224,83 @@ public:
                                        const direction cmpt, const Pstream::commsTypes commsType,
                                        const bool negate = false) const;
 };
+
+// ---- coarse GAMG levels: GAMGInterface / processorGAMGInterface reduced to what the field class reads ----
+typedef gpuList<scalar> scalargpuList;
+template <class T> struct plusEqOp { // ops.H: x += y
+    void operator()(T &x, const T &y) const { x += y; }
+};
+template <class T> struct minusEqOp {
+    void operator()(T &x, const T &y) const { x -= y; }
+};
+struct tensor {
+    scalar v_[9];
+};
+typedef gpuField<tensor> tensorField, tensorgpuField;
+class GAMGInterface
+{
+public:
+    labelgpuList faceCells_, sortCells_, cellFaces_, cellFacesStart_;
+    virtual ~GAMGInterface() {}
+    label size() const { return faceCells_.size(); }
+    const labelgpuList &sortCells() const { return sortCells_; }
+    const labelgpuList &cellFaces() const { return cellFaces_; }
+    const labelgpuList &cellFacesStart() const { return cellFacesStart_; }
+    // GAMGInterfaceTemplates.C:45-68
+    template <class T> void interfaceInternalField(const gpuList<T> &iF, gpuList<T> &result) const
+    {
+        result.setSize(size());
+        for (label i = 0; i < size(); i++) result.data()[i] = iF.data()[faceCells_.data()[i]];
+    }
+};
+class processorGAMGInterface : public GAMGInterface
+{
+public:
+    int myProcNo_, neighbProcNo_, tag_;
+    tensorField T_;
+    int comm() const { return 0; }
+    int myProcNo() const { return myProcNo_; }
+    int neighbProcNo() const { return neighbProcNo_; }
+    int tag() const { return tag_; }
+    const tensorField &forwardT() const { return T_; }
+    const tensorgpuField &getForwardT() const { return T_; }
+    template <class T> void compressedSend(const Pstream::commsTypes ct, const gpuList<T> &f) const
+    {
+        UOPstream::write(ct, neighbProcNo_, reinterpret_cast<const char *>(f.data()), f.byteSize(), tag_, 0);
+    }
+    template <class T> void compressedReceive(const Pstream::commsTypes, gpuList<T> &f) const
+    {
+        const std::vector<char> &m = Mail::box().at(std::make_tuple(neighbProcNo_, myProcNo_, tag_));
+        if ((label)m.size() != f.byteSize()) throw std::runtime_error("mailbox size");
+        std::memcpy(f.data(), m.data(), m.size());
+    }
+};
+template <class To, class From> To &refCast(From &r) { return dynamic_cast<To &>(r); }
+class processorLduInterfaceField
+{
+public:
+    virtual ~processorLduInterfaceField() {}
+    virtual bool doTransform() const = 0;
+    virtual int rank() const = 0;
+    // processorLduInterfaceField.C:37-62: scalars and untransformed couplings pass through
+    void transformCoupleField(scalargpuField &, const direction) const
+    {
+        if (doTransform()) throw std::runtime_error("transformed couplings are not part of the harness");
+    }
+};
+class GAMGInterfaceField : public lduInterfaceField
+{
+public:
+    GAMGInterfaceField(const GAMGInterface &, const lduInterfaceField &) {}
+    GAMGInterfaceField(const GAMGInterface &, const bool, const int) {}
+};
+#define TypeName(name)                              \
+    static const char *typeName_() { return name; } \
+    static const char *typeName;                    \
+    static int debug
+#define defineTypeNameAndDebug(Type, DebugSwitch) \
+    const char *Type::typeName = Type::typeName_(); \
+    int Type::debug = DebugSwitch
+#define addToRunTimeSelectionTable(baseType, thisType, argNames) struct thisType##argNames##Unused
 } // namespace Foam
 #endif

@@ -551,11 +551,13 @@ _LIB_PF = os.path.join(_HERE, "_ref", "libref_procfield.so")
 _libpf = None
 
 
-def processor_interface_update(ranks, commsType="nonBlocking", negate=False, nPoll=0, gpuDirect=False):
+def processor_interface_update(ranks, commsType="nonBlocking", negate=False, nPoll=0, gpuDirect=False, gamgLevel=False):
     """The reference's finest-level coupled-interface update over all ranks of a decomposed case (in one process):
     lduMatrix::initMatrixInterfaces on every rank, then lduMatrix::updateMatrixInterfaces
     (lduMatrixUpdateMatrixInterfaces.C, processorFvPatchScalarField.C, matrixPatchOperation / matrixInterfaceFunctor).
-    ranks: list of dict(nCells, patchStart, faceCells, neighbRank, coeffs, psi, result).  Returns the updated results."""
+    ranks: list of dict(nCells, patchStart, faceCells, neighbRank, coeffs, psi, result).  Returns the updated results.
+    gamgLevel: the interfaces are processorGAMGInterfaceField objects (processorGAMGInterfaceField.C:94-248,
+    GAMGUpdateInterfaceMatrix) as on the coarse GAMG levels instead of processorFvPatchField<scalar>."""
     global _libpf
     if _libpf is None:
         if not available() or not os.path.exists(_LIB_PF):
@@ -565,7 +567,8 @@ def processor_interface_update(ranks, commsType="nonBlocking", negate=False, nPo
     for r, d in enumerate(ranks):
         ps, fc, nr = _i(d["patchStart"]), _i(d["faceCells"]), _i(d["neighbRank"])
         co, psi, res = _d(d["coeffs"]), _d(d["psi"]), _d(d["result"])
-        _libpf.ref_pf_set_rank(r, int(d["nCells"]), len(ps) - 1, _p(ps), _p(fc), _p(nr), _p(co), _p(psi), _p(res))
+        _libpf.ref_pf_set_rank(r, int(d["nCells"]), len(ps) - 1, _p(ps), _p(fc), _p(nr), _p(co), _p(psi), _p(res),
+                               int(bool(gamgLevel)))
     if _libpf.ref_pf_update({"blocking": 0, "nonBlocking": 2}[commsType], int(bool(negate)), int(nPoll), int(bool(gpuDirect))) != 0:
         raise RuntimeError("the reference code raised a FatalError")
     out = []

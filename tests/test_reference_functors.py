@@ -753,14 +753,16 @@ def test_vector_fvmatrix_glue_matches_reference_code(meshmod, orc, case):
     assert np.array_equal(after, d["diag"])
 
 
+@pytest.mark.parametrize("gamg", [False, True])
 @pytest.mark.parametrize("nR", [2, 4, 8])
 @pytest.mark.parametrize("mode", [("nonBlocking", 0, False), ("nonBlocking", 1, True), ("blocking", 0, False)])
-def test_processor_interface_exchange_matches_reference_code(meshmod, orc, nR, mode):
+def test_processor_interface_exchange_matches_reference_code(meshmod, orc, nR, mode, gamg):
     """Row a6: the finest-level halo exchange + interface update of the reference -- lduMatrix::initMatrixInterfaces /
     updateMatrixInterfaces, processorFvPatchField<scalar>::initInterfaceMatrixUpdate / updateInterfaceMatrix with their
     send / receive buffers and requests, matrixPatchOperation -- all ranks in one process behind a Pstream mailbox, against
     the oracle's Amul of the decomposed case (threads): identical vectors on every rank, for the non-blocking (polling or
-    not, direct or staged buffers) and the blocking communication types, and with the smoothers' negated sign."""
+    not, direct or staged buffers) and the blocking communication types, and with the smoothers' negated sign.
+    gamg: the same through processorGAMGInterfaceField + GAMGUpdateInterfaceMatrix, the coarse-level classes (row a14)."""
     import dist_helpers as dh
     n = 8
     gm, _ = dh.global_case(meshmod, n, "U")
@@ -778,12 +780,12 @@ def test_processor_interface_exchange_matches_reference_code(meshmod, orc, nR, m
         return dict(nCells=m.nCells, patchStart=ps, faceCells=fc, neighbRank=[p.neighbRank for p in m.coupled_patches()],
                     coeffs=c["bou"], psi=x[m.cellGlobal], result=without), with_if, without
     res = dh.run_threads(nR, rank_fn)
-    got = ref_ldu.processor_interface_update([r[0] for r in res], mode[0], False, mode[1], mode[2])
+    got = ref_ldu.processor_interface_update([r[0] for r in res], mode[0], False, mode[1], mode[2], gamg)
     for r in range(nR):
         assert np.array_equal(got[r], res[r][1]), r
         assert not np.array_equal(res[r][1], res[r][2])
     # negate = true (the smoothers): the term is added instead
-    got = ref_ldu.processor_interface_update([r[0] for r in res], mode[0], True, mode[1], mode[2])
+    got = ref_ldu.processor_interface_update([r[0] for r in res], mode[0], True, mode[1], mode[2], gamg)
     for r in range(nR):
         d = res[r][0]
         expect = d["result"].copy()
