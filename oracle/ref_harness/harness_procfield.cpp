@@ -8,6 +8,7 @@
  *   LDU/lduAddressing/lduAddressingFunctors.H                             matrixPatchOperation, matrixInterfaceFunctor
  *   GAMG/interfaceFields/processorGAMGInterfaceField/processorGAMGInterfaceField.H/.C  :94-248 (coarse levels)
  *   GAMG/interfaces/GAMGInterface/GAMGInterfaceFunctors.H                 GAMGUpdateInterfaceMatrix
+ *   FV/fields/fvPatchFields/constraint/cyclic/cyclicFvPatchField.C        updateInterfaceMatrix :212-231 (cyclic pairs)
  * against oracle/ref_harness/shim_procfield/ (+ shim/foam_shim.h).
  */
 #include "procfield_shim.h"
@@ -17,6 +18,7 @@
 
 #include "lduMatrixUpdateMatrixInterfaces.C" /* reference */
 #include "processorFvPatchScalarField.C"     /* reference */
+#include "cyclicFvPatchField.C"              /* reference: updateInterfaceMatrix :212-231 */
 #include "processorGAMGInterfaceField.H"     /* reference: class declaration */
 #include "processorGAMGInterfaceField.C"     /* reference */
 
@@ -28,6 +30,7 @@ label UPstream::nPollProcInterfaces = 0;
 label UPstream::warnComm = -1;
 const char *UPstream::commsTypeNames[3] = {"blocking", "scheduled", "nonBlocking"};
 template <> int processorFvPatchField<scalar>::debug = 0;
+template <> const char *cyclicFvPatchField<scalar>::typeName = "cyclic";
 int lduMatrix::debug = 0;
 int lduMatrixSolutionCache::favourSpeed = 0;
 } // namespace Foam
@@ -39,6 +42,9 @@ struct Rank {
     fvMeshStub mesh;
     std::vector<std::unique_ptr<processorFvPatch>> patches;
     std::vector<std::unique_ptr<processorFvPatchField<scalar>>> fields;
+    std::vector<std::unique_ptr<cyclicFvPatch>> cycPatches;               // neighbRank < 0: cyclic partner -(q+1)
+    std::vector<std::unique_ptr<cyclicFvPatchField<scalar>>> cycFields;
+    std::vector<const lduInterfaceField *> ifaceOf;
     std::vector<std::unique_ptr<processorGAMGInterface>> gamgPatches;     // coarse-level variant
     std::vector<std::unique_ptr<processorGAMGInterfaceField>> gamgFields;
     std::vector<scalargpuField> coeffs;
@@ -99,6 +105,17 @@ void ref_pf_set_rank(int r, int nCells, int nPatches, const int *patchStart, con
             R.gamgFields.emplace_back(new processorGAMGInterfaceField(*gp, false, 0));
             continue;
         }
+        if (neighbRank[p] < 0) { // cyclic: the neighbour values are psi at the partner patch's face cells
+            cyclicFvPatch *cp = new cyclicFvPatch;
+            cp->mesh_ = &R.mesh;
+            cp->index_ = p;
+            cp->faceCells_ = labelgpuList(faceCells + s, np);
+            cp->nbrID_ = -neighbRank[p] - 1;
+            R.cycPatches.emplace_back(cp);
+            R.cycFields.emplace_back(new cyclicFvPatchField<scalar>(*cp, 0));
+            R.ifaceOf.push_back(R.cycFields.back().get());
+            continue;
+        }
         processorFvPatch *pp = new processorFvPatch;
         pp->mesh_ = &R.mesh;
         pp->index_ = p;
@@ -108,10 +125,13 @@ void ref_pf_set_rank(int r, int nCells, int nPatches, const int *patchStart, con
         pp->tag_ = 1;
         R.patches.emplace_back(pp);
         R.fields.emplace_back(new processorFvPatchField<scalar>(*pp));
+        R.ifaceOf.push_back(R.fields.back().get());
     }
+    for (auto &cp : R.cycPatches) // partner patches: located by their index among this rank's patches
+        for (auto &cq : R.cycPatches)
+            if (cq->index_ == cp->nbrID_) cp->nbr_ = cq.get();
     for (int p = 0; p < nPatches; p++) { // after the vectors stopped growing
-        R.interfaces.set(p, gamgLevel ? static_cast<const lduInterfaceField *>(R.gamgFields[(size_t)p].get())
-                                      : static_cast<const lduInterfaceField *>(R.fields[(size_t)p].get()));
+        R.interfaces.set(p, gamgLevel ? static_cast<const lduInterfaceField *>(R.gamgFields[(size_t)p].get()) : R.ifaceOf[(size_t)p]);
         R.coupleCoeffs.setPtr(p, &R.coeffs[(size_t)p]);
     }
     R.M.addr_ = &a;

@@ -113,6 +113,10 @@ public:
         gpuList<T>::operator=(o);
         return *this;
     }
+    gpuField(const gpuList<T> &f, const gpuList<label> &map) : gpuList<T>(map.size()) // gpuField(mapF, mapAddressing)
+    {
+        for (label i = 0; i < map.size(); i++) this->data()[i] = f.data()[map.data()[i]];
+    }
     gpuField(const tmp<gpuField<T>> &t); // deep copy of a temporary (defined after tmp)
     void operator=(const tmp<gpuField<T>> &t);
 };

@@ -142,21 +142,27 @@ public:
     lduAddressing addr_;
     const lduAddressing &lduAddr() const { return addr_; }
 };
-class processorFvPatch
+class fvPatch
 {
 public:
     const fvMeshStub *mesh_;
     label index_;
     labelgpuList faceCells_;
-    int myProcNo_, neighbProcNo_, tag_;
     struct BoundaryMesh {
         const fvMeshStub *m;
         const fvMeshStub &mesh() const { return *m; }
     };
-    const char *name() const { return "procBoundary"; }
+    virtual ~fvPatch() {}
+    const char *type() const { return "patch"; }
+    const char *name() const { return "patch"; }
     label index() const { return index_; }
     label size() const { return faceCells_.size(); }
     BoundaryMesh boundaryMesh() const { return BoundaryMesh{mesh_}; }
+};
+class processorFvPatch : public fvPatch
+{
+public:
+    int myProcNo_, neighbProcNo_, tag_;
     int myProcNo() const { return myProcNo_; }
     int neighbProcNo() const { return neighbProcNo_; }
     int tag() const { return tag_; }
@@ -187,11 +193,13 @@ namespace Foam
 {
 template <class Type> class coupledFvPatchField : public lduInterfaceField
 {
-    const processorFvPatch &patch_;
+    const fvPatch &patch_;
 
 public:
-    coupledFvPatchField(const processorFvPatch &p) : patch_(p) {}
-    const processorFvPatch &patch() const { return patch_; }
+    coupledFvPatchField(const fvPatch &p) : patch_(p) {}
+    template <class... A> coupledFvPatchField(const fvPatch &p, const A &...) : patch_(p) {} // the other constructors only parse
+    const fvPatch &patch() const { return patch_; }
+    void evaluate(const Pstream::commsTypes) {}
     label size() const { return patch_.size(); }
     // coupledFvPatchField.C:221-257
     void updateInterfaceMatrix(scalargpuField &result, const scalargpuField &coeffs, const scalargpuField &pnf,
@@ -215,7 +223,8 @@ template <class Type> class processorFvPatchField : public coupledFvPatchField<T
 
 public:
     static int debug;
-    processorFvPatchField(const processorFvPatch &p) : coupledFvPatchField<Type>(p), procPatch_(p) {}
+    processorFvPatchField(const processorFvPatch &p) : coupledFvPatchField<Type>(static_cast<const fvPatch &>(p)), procPatch_(p) {}
+    const processorFvPatch &patch() const { return procPatch_; }
     virtual bool ready() const { return true; }
     virtual void initInterfaceMatrixUpdate(scalargpuField &result, const scalargpuField &psiInternal,
                                            const scalargpuField &coeffs, const direction cmpt,
@@ -223,6 +232,84 @@ public:
     virtual void updateInterfaceMatrix(scalargpuField &result, const scalargpuField &psiInternal, const scalargpuField &coeffs,
                                        const direction cmpt, const Pstream::commsTypes commsType,
                                        const bool negate = false) const;
+};
+
+struct tensor {
+    scalar v_[9];
+};
+typedef gpuField<tensor> tensorField, tensorgpuField;
+
+// ---- cyclic patches: cyclicFvPatchField.H:60-250 (its members are the reference's cyclicFvPatchField.C) ----
+class cyclicFvPatch : public fvPatch
+{
+public:
+    const cyclicFvPatch *nbr_ = nullptr;
+    label nbrID_ = -1;
+    struct Nbr {
+        const cyclicFvPatch *p;
+        const labelgpuList &getFaceCells() const { return p->faceCells_; }
+    };
+    struct Poly {
+        const cyclicFvPatch *p;
+        Nbr neighbPatch() const { return Nbr{p->nbr_}; }
+    };
+    Poly cyclicPatch() const { return Poly{this}; }
+    label neighbPatchID() const { return nbrID_; }
+    const cyclicFvPatch &neighbFvPatch() const { return *nbr_; }
+};
+template <class T> bool isA(const fvPatch &p) { return dynamic_cast<const T *>(&p) != nullptr; }
+struct volMesh {
+};
+struct fvPatchFieldMapper {
+};
+struct dictionary {
+};
+struct Ostream {
+};
+template <class Type, class GeoMesh> class DimensionedField;
+template <class Type, template <class> class PatchField, class GeoMesh> class GeometricField;
+template <class Type> class fvPatchField
+{
+public:
+    static void write(Ostream &) {}
+};
+static FatalStream FatalIOError;
+#define FatalIOErrorIn(where, ios) ::Foam::FatalIOError
+inline int exit(FatalStream &, int) { throw std::runtime_error("FatalError"); }
+template <class A, class B, class C> struct transformBinaryFunctionSFFunctor;
+class cyclicLduInterfaceField
+{
+public:
+    virtual ~cyclicLduInterfaceField() {}
+    bool doTransform() const { return false; }
+    struct TensorList { // only named by the transforming branch of patchNeighbourField, which is never instantiated
+        tensor operator[](label) const { return tensor(); }
+    };
+    TensorList forwardT() const { return TensorList(); }
+    template <class F> void transformCoupleField(F &, const direction) const {} // scalars: no transformation
+    template <class F> void transformCoupleField(F &) const {}
+};
+template <class Type> class cyclicFvPatchField : public cyclicLduInterfaceField, public coupledFvPatchField<Type>
+{
+    const cyclicFvPatch &cyclicPatch_;
+
+public:
+    cyclicFvPatchField(const fvPatch &, const DimensionedField<Type, volMesh> &);
+    cyclicFvPatchField(const fvPatch &, const DimensionedField<Type, volMesh> &, const dictionary &);
+    cyclicFvPatchField(const cyclicFvPatchField<Type> &, const fvPatch &, const DimensionedField<Type, volMesh> &,
+                       const fvPatchFieldMapper &);
+    cyclicFvPatchField(const cyclicFvPatchField<Type> &);
+    cyclicFvPatchField(const cyclicFvPatchField<Type> &, const DimensionedField<Type, volMesh> &);
+    cyclicFvPatchField(const cyclicFvPatch &p, int) : coupledFvPatchField<Type>(static_cast<const fvPatch &>(p)), cyclicPatch_(p) {} // harness
+    static const char *typeName;
+    const cyclicFvPatch &cyclicPatch() const { return cyclicPatch_; }
+    tmp<gpuField<Type>> patchNeighbourField() const;
+    const cyclicFvPatchField<Type> &neighbourPatchField() const;
+    virtual void updateInterfaceMatrix(scalargpuField &result, const scalargpuField &psiInternal, const scalargpuField &coeffs,
+                                       const direction cmpt, const Pstream::commsTypes commsType, const bool negate = false) const;
+    virtual void updateInterfaceMatrix(gpuField<Type> &result, const gpuField<Type> &psiInternal, const scalargpuField &coeffs,
+                                       const Pstream::commsTypes commsType) const;
+    virtual void write(Ostream &) const;
 };
 
 // ---- coarse GAMG levels: GAMGInterface / processorGAMGInterface reduced to what the field class reads ----
@@ -233,10 +320,6 @@ template <class T> struct plusEqOp { // ops.H: x += y
 template <class T> struct minusEqOp {
     void operator()(T &x, const T &y) const { x -= y; }
 };
-struct tensor {
-    scalar v_[9];
-};
-typedef gpuField<tensor> tensorField, tensorgpuField;
 class GAMGInterface
 {
 public:

@@ -791,3 +791,21 @@ def test_processor_interface_exchange_matches_reference_code(meshmod, orc, nR, m
         expect = d["result"].copy()
         delta = res[r][1] - res[r][2]          # -(coeff*pnf) summed per cell by the oracle
         np.testing.assert_allclose(got[r], expect - delta, rtol=1e-14, atol=1e-15)
+
+
+@pytest.mark.parametrize("kind", ["P", "U"])
+def test_cyclic_interface_update_matches_reference_code(meshmod, orc, kind):
+    """Cyclic patch pairs: cyclicFvPatchField<scalar>::updateInterfaceMatrix of the reference (cyclicFvPatchField.C:212-231 --
+    psi gathered at the partner patch's face cells, then the coupled update) driven by lduMatrix::updateMatrixInterfaces,
+    against the oracle's Amul / Tmul with the cyclic pairing (neighbRank = -(partner + 1))."""
+    from test_oracle_core import _cyclic_case
+    m, c, ps, fc, nr, lo, hi = _cyclic_case(meshmod, kind)
+    a = orc.Addr(m.nCells, m.lower, m.upper, ps, fc, neighbRank=nr)
+    M = orc.Matrix(a, c["diag"], c["upper"], c["lower"], c["bou"], c["int"])
+    M0 = orc.Matrix(orc.Addr(m.nCells, m.lower, m.upper), c["diag"], c["upper"], c["lower"])
+    x = np.random.default_rng(4).standard_normal(m.nCells)
+    for coeffs, with_if, without in ((c["bou"], M.amul(x), M0.amul(x)), (c["int"], M.tmul(x), M0.tmul(x))):
+        rank = dict(nCells=m.nCells, patchStart=ps, faceCells=fc, neighbRank=nr, coeffs=coeffs, psi=x, result=without)
+        for mode in ("nonBlocking", "blocking"):
+            got = ref_ldu.processor_interface_update([rank], mode)[0]
+            assert np.array_equal(got, with_if) and not np.array_equal(with_if, without)
