@@ -8,8 +8,7 @@ lduMatrix reduced to what the exercised members touch; the linear solver behind 
 diagonal and source it is handed) and tests/test_reference_functors.py compares, bit for bit, for scalar and
 vector fields with and without coupled patches: addBoundaryDiag / addCmptAvBoundaryDiag / addBoundarySource,
 setReference, relax, D, A, H, flux and residual (scalar), and what solveSegregated passes to the solver per
-component.  Not pinned: the residual over coupled patches (the harness' lduMatrix::residual has no interface
-update).  tests/test_oracle_fvm.py adds dense-matrix algebra and decomposed-case checks.
+component.  tests/test_oracle_fvm.py adds dense-matrix algebra and decomposed-case checks.
 
 Paths: FV/ = /root/reference/src/finiteVolume/.
 
@@ -19,7 +18,7 @@ addressing, their coefficients the matrix' interfaceIntCoeffs / interfaceBouCoef
 used for every component (what processorFvPatchField produces for vectors, coupledFvPatchField.C:116-176).
 Fields with nc components are (n, nc) arrays.
 
-Findings while restating (mirrored, not corrected; the first one confirmed by running the reference's code):
+Findings while restating (mirrored, not corrected; both reproduced by running the reference's code):
  * fvMatrix<Type>::H (fvMatrix.C:1458-1485) fills Hphi with boundaryDiagCmpt*psi and then calls the two-argument
    lduMatrix::H(Hphi, psi), which starts with Hpsi = 0 (lduMatrixTemplates.C:53): the boundary-diagonal term of
    stock OpenFOAM is lost.  It vanishes anyway when internalCoeffs are equal in all components (fixedValue,

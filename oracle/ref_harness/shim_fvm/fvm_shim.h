@@ -191,20 +191,14 @@ public:
     template <class Type> void faceH(gpuField<Type> &, const gpuField<Type> &) const;
     tmp<scalargpuField> H1() const { throw std::runtime_error("not used by the harness"); }
     void H1(scalargpuField &) const { throw std::runtime_error("not used by the harness"); }
-    // lduMatrixATmul.C:397-496 without interfaces: rA = source - diag*psi - sum(off-diagonal*psi)
+    // lduMatrixATmul.C:397-496: rA = source - diag*psi - sum(off-diagonal*psi), then the coupled interfaces with the
+    // negated coefficients of :455-463 (pinned through libref_ldu / libref_procfield; restated here for fvMatrix.C only)
     void residual(scalargpuField &rA, const scalargpuField &psi, const scalargpuField &source,
-                  const FieldField<gpuField, scalar> &, const lduInterfaceFieldPtrsList &, const direction) const
+                  const FieldField<gpuField, scalar> &bouCoeffs, const lduInterfaceFieldPtrsList &ifs, const direction cmpt) const
     {
-        gpuField<scalar> h(psi.size());
-        H(h, psi);
-        for (label c = 0; c < psi.size(); c++) {
-            // same association as the reference functor: (source - diag*psi) + (-u*psi) + ...
-            scalar out = source.data()[c] - diag_.data()[c] * psi.data()[c];
-            rA.data()[c] = out;
-        }
         const lduAddressing &a = lduAddr();
         for (label c = 0; c < psi.size(); c++) {
-            scalar out = rA.data()[c];
+            scalar out = source.data()[c] - diag_.data()[c] * psi.data()[c];
             for (label f = a.ownerStart_.data()[c]; f < a.ownerStart_.data()[c + 1]; f++) {
                 scalar p = upper().data()[f] * psi.data()[a.upper_.data()[f]];
                 out = out + (-p);
@@ -216,6 +210,12 @@ public:
             }
             rA.data()[c] = out;
         }
+        for (size_t p = 0; p < ifs.update.size(); p++)
+            if (ifs.update[p]) {
+                gpuField<scalar> m(bouCoeffs[(label)p].data(), bouCoeffs[(label)p].size());
+                m.negate();
+                ifs.update[p](m, rA, cmpt);
+            }
     }
     void initMatrixInterfaces(const FieldField<gpuField, scalar> &, const lduInterfaceFieldPtrsList &, const scalargpuField &,
                               scalargpuField &, const direction) const
