@@ -5,6 +5,8 @@
  *                                                addBoundarySource, setReference, relax, D, A, flux
  *   fvMatrix/fvMatrixSolve.C                     (parsed; the component loop needs a vector type and is not instantiated)
  *   fvScalarMatrix/fvScalarMatrix.H, .C          solveSegregated, residual, H for scalars
+ *   FV/finiteVolume/convectionSchemes/gaussConvectionScheme/gaussConvectionScheme.C   fvmDiv (coefficient fill + patch coefficients)
+ *   FV/finiteVolume/laplacianSchemes/gaussLaplacianScheme/gaussLaplacianScheme.C      fvmLaplacianUncorrected
  * against oracle/ref_harness/shim_fvm/.  The linear solver behind solveSegregated is a recorder: it keeps the diagonal and
  * the source it is handed, which is what the folding has to get right.
  */
@@ -16,6 +18,9 @@
 #undef protected
 #undef private
 #include "fvScalarMatrix.C" /* reference */
+#include "schemes_shim.h"
+#include "gaussConvectionScheme.C" /* reference: fvmDiv :76-115 */
+#include "gaussLaplacianScheme.C"  /* reference: fvmLaplacianUncorrected :46-89 */
 
 #include <algorithm>
 
@@ -211,6 +216,76 @@ int ref_fvm_vec(int op, int n, int nF, const int *l, const int *u, const int *ow
             put(M.diag(), out3);
         } else
             return -2;
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+
+/* Coefficient fills through the reference's schemes, for a scalar (nc 1) or vector (nc 3) field whose patches are fixedValue
+ * (kind 0, values in pvalue), zeroGradient (kind 1) or coupled (kind 2):
+ *   which 0: gaussConvectionScheme::fvmDiv(faceFlux, vf) with the given interpolation weights
+ *   which 1: gaussLaplacianScheme::fvmLaplacianUncorrected(gammaMagSf, deltaCoeffs, vf)
+ * a / b: internal-face fields (which 0: weights, faceFlux; which 1: gammaMagSf, deltaCoeffs); pa / pb: the same on the patch
+ * faces (flat); pdelta: patch().deltaCoeffs() of the patch faces.  Outputs: lower (which 0 only), upper, diag, internalCoeffs,
+ * boundaryCoeffs (flat, nc per face). */
+int ref_fvm_fill(int which, int nc, int n, int nF, const int *l, const int *u, const int *ownerStart, const int *losortStart,
+                 const int *losort, int nP, const int *patchStart, const int *faceCells, const int *kind, const double *pvalue,
+                 const double *pdelta, const double *a, const double *b, const double *pa, const double *pb, double *lower,
+                 double *upper, double *diag, double *ic, double *bc)
+{
+    try {
+        std::vector<int> coupled((size_t)std::max(nP, 1));
+        for (int p = 0; p < nP; p++) coupled[(size_t)p] = kind[p] == 2;
+        const int tot = nP ? patchStart[nP] : 0;
+        std::vector<double> zerosN((size_t)n * 3 + 3, 0.0), zerosF((size_t)nF + 1, 0.0), zerosP((size_t)tot * 3 + 3, 0.0), ones((size_t)n, 1.0);
+        auto surf = [&](surfaceScalarField &f, const fvMesh &mesh, const double *in, const double *pin) {
+            f.mesh_ = &mesh;
+            f.internal_ = scalargpuField(in, nF);
+            f.boundary_.p_.resize((size_t)nP);
+            for (int p = 0; p < nP; p++)
+                static_cast<scalargpuField &>(f.boundary_.p_[(size_t)p]) = tmp<scalargpuField>(
+                    new scalargpuField(pin + patchStart[p], patchStart[p + 1] - patchStart[p]));
+        };
+        auto run = [&](auto &C, auto tag) {
+            typedef decltype(tag) Type;
+            const int k = sizeof(Type) / sizeof(double);
+            for (int p = 0; p < nP; p++) {
+                fvPatchField<Type> &pf = C.psi.boundary_.p_[(size_t)p];
+                const int s = patchStart[p], np = patchStart[p + 1] - s;
+                pf.kind_ = kind[p];
+                pf.patchDelta_ = scalargpuField(pdelta + s, np);
+                static_cast<gpuField<Type> &>(pf) = tmp<gpuField<Type>>(
+                    new gpuField<Type>(reinterpret_cast<const Type *>(pvalue + (size_t)s * k), np));
+            }
+            surfaceScalarField A, B;
+            surf(A, C.mesh, a, pa);
+            surf(B, C.mesh, b, pb);
+            tmp<fvMatrix<Type>> tM = which == 0
+                                         ? fv::gaussConvectionScheme<Type>(C.mesh, B, tmp<surfaceInterpolationScheme<Type>>(
+                                                                                          new surfaceInterpolationScheme<Type>(A)))
+                                               .fvmDiv(B, C.psi)
+                                         : fv::gaussLaplacianScheme<Type, scalar>::fvmLaplacianUncorrected(A, B, C.psi);
+            fvMatrix<Type> &M = tM();
+            if (which == 0) put(M.lower(), lower);
+            put(M.upper(), upper);
+            put(M.diag(), diag);
+            for (int p = 0; p < nP; p++) {
+                put(M.internalCoeffs()[p], ic + (size_t)patchStart[p] * k);
+                put(M.boundaryCoeffs()[p], bc + (size_t)patchStart[p] * k);
+            }
+        };
+        if (nc == 1) {
+            Case<scalar> C(n, nF, l, u, ownerStart, losortStart, losort, nP, patchStart, faceCells, coupled.data(), zerosP.data(),
+                           ones.data(), zerosN.data(), zerosN.data(), zerosF.data(), nullptr, zerosN.data(), zerosP.data(),
+                           zerosP.data());
+            run(C, scalar());
+        } else {
+            Case<vector> C(n, nF, l, u, ownerStart, losortStart, losort, nP, patchStart, faceCells, coupled.data(), zerosP.data(),
+                           ones.data(), zerosN.data(), zerosN.data(), zerosF.data(), nullptr, zerosN.data(), zerosP.data(),
+                           zerosP.data());
+            run(C, vector());
+        }
         return 0;
     } catch (const std::exception &) {
         return -1;

@@ -184,7 +184,8 @@ public:
     void operator*=(scalar) { throw std::runtime_error("not used by the harness"); }
     // lduMatrixOperations.C:82-104 in the order its functors run (owner side: |upper|, neighbour side: |lower|)
     void sumMagOffDiag(scalargpuField &sumOff) const;
-    void negSumDiag() { throw std::runtime_error("not used by the harness"); }
+    // lduMatrixOperations.C:59-80 in the order its functors run (owner side: -lower, neighbour side: -upper)
+    void negSumDiag();
     // lduMatrixTemplates.C:50-149 (pinned separately through libref_ldu)
     template <class Type> tmp<gpuField<Type>> H(const gpuField<Type> &psi) const;
     template <class Type> void H(gpuField<Type> &, const gpuField<Type> &) const;
@@ -244,6 +245,54 @@ public:
     using gpuField<Type>::gpuField;
     using gpuField<Type>::operator=;
     bool coupled() const { return coupled_; }
+    // boundary-condition coefficient functions (kind_: 0 fixedValue, fixedValueFvPatchField.C:113-146; 1 zeroGradient,
+    // zeroGradientFvPatchField.C:111-150; coupled patches: coupledFvPatchField.C:162-209); patchDelta_ = patch().deltaCoeffs()
+    int kind_ = 0;
+    gpuField<scalar> patchDelta_;
+    tmp<gpuField<Type>> valueInternalCoeffs(const tmp<gpuField<scalar>> &w) const
+    {
+        gpuField<Type> *r = new gpuField<Type>(this->size(), pTraits<Type>::zero);
+        if (coupled_)
+            for (label i = 0; i < r->size(); i++) r->data()[i] = Type(pTraits<Type>::one) * w().data()[i];
+        else if (kind_ == 1)
+            *r = Type(pTraits<Type>::one);
+        return tmp<gpuField<Type>>(r);
+    }
+    tmp<gpuField<Type>> valueBoundaryCoeffs(const tmp<gpuField<scalar>> &w) const
+    {
+        gpuField<Type> *r = new gpuField<Type>(this->size(), pTraits<Type>::zero);
+        if (coupled_)
+            for (label i = 0; i < r->size(); i++) r->data()[i] = Type(pTraits<Type>::one) * (1.0 - w().data()[i]);
+        else if (kind_ == 0)
+            for (label i = 0; i < r->size(); i++) r->data()[i] = this->data()[i];
+        return tmp<gpuField<Type>>(r);
+    }
+    tmp<gpuField<Type>> gradientInternalCoeffs(const gpuField<scalar> &deltaCoeffs) const // coupled
+    {
+        gpuField<Type> *r = new gpuField<Type>(this->size());
+        for (label i = 0; i < r->size(); i++) r->data()[i] = -Type(pTraits<Type>::one) * deltaCoeffs.data()[i];
+        return tmp<gpuField<Type>>(r);
+    }
+    tmp<gpuField<Type>> gradientBoundaryCoeffs(const gpuField<scalar> &deltaCoeffs) const // coupled: -gradientInternalCoeffs
+    {
+        gpuField<Type> *r = new gpuField<Type>(this->size());
+        for (label i = 0; i < r->size(); i++) r->data()[i] = -(-Type(pTraits<Type>::one) * deltaCoeffs.data()[i]);
+        return tmp<gpuField<Type>>(r);
+    }
+    tmp<gpuField<Type>> gradientInternalCoeffs() const
+    {
+        gpuField<Type> *r = new gpuField<Type>(this->size(), pTraits<Type>::zero);
+        if (kind_ == 0)
+            for (label i = 0; i < r->size(); i++) r->data()[i] = -Type(pTraits<Type>::one) * patchDelta_.data()[i];
+        return tmp<gpuField<Type>>(r);
+    }
+    tmp<gpuField<Type>> gradientBoundaryCoeffs() const
+    {
+        gpuField<Type> *r = new gpuField<Type>(this->size(), pTraits<Type>::zero);
+        if (kind_ == 0)
+            for (label i = 0; i < r->size(); i++) r->data()[i] = patchDelta_.data()[i] * this->data()[i];
+        return tmp<gpuField<Type>>(r);
+    }
     tmp<gpuField<Type>> patchInternalField() const
     {
         gpuField<Type> *r = new gpuField<Type>(faceCells_->size());
@@ -297,9 +346,17 @@ struct VolumeField {
     const scalargpuField &getField() const { return f_; }
 };
 
+template <class Type> class fvsPatchField;
+template <class Type, template <class> class PatchField, class GeoMesh> class GeometricField;
 class fvMesh
 {
 public:
+    // geometry fields the scheme sources name (only parsed unless the harness points them somewhere)
+    const GeometricField<scalar, fvsPatchField, surfaceMesh> *magSf_ = nullptr, *deltaCoeffs_ = nullptr;
+    const GeometricField<vector, fvsPatchField, surfaceMesh> *Sf_ = nullptr;
+    const GeometricField<scalar, fvsPatchField, surfaceMesh> &magSf() const { return *magSf_; }
+    const GeometricField<scalar, fvsPatchField, surfaceMesh> &deltaCoeffs() const { return *deltaCoeffs_; }
+    const GeometricField<vector, fvsPatchField, surfaceMesh> &Sf() const { return *Sf_; }
     lduAddressing addr_;
     fvBoundaryMesh boundary_;
     VolumeField V_;
@@ -338,6 +395,18 @@ inline void lduMatrix::sumMagOffDiag(scalargpuField &sumOff) const
         for (label k = a.losortStart_.data()[c]; k < a.losortStart_.data()[c + 1]; k++)
             out = out + std::fabs(lower().data()[a.losort_.data()[k]]);
         sumOff.data()[c] = out;
+    }
+}
+inline void lduMatrix::negSumDiag()
+{
+    const lduAddressing &a = lduAddr();
+    if ((label)diag_.size() != a.size()) diag_ = tmp<scalargpuField>(new scalargpuField(a.size(), 0.0));
+    const lduMatrix &cm = *this; // the const lower() aliases upper() for a symmetric matrix (lduMatrix.C:328-345)
+    for (label c = 0; c < a.size(); c++) {
+        scalar out = diag_.data()[c];
+        for (label f = a.ownerStart_.data()[c]; f < a.ownerStart_.data()[c + 1]; f++) out = out - cm.lower().data()[f];
+        for (label k = a.losortStart_.data()[c]; k < a.losortStart_.data()[c + 1]; k++) out = out - cm.upper().data()[a.losort_.data()[k]];
+        diag_.data()[c] = out;
     }
 }
 template <class Type> void lduMatrix::H(gpuField<Type> &Hpsi, const gpuField<Type> &psi) const
@@ -447,6 +516,7 @@ public:
     dimensionSet dimensions() const { return dimensionSet(); }
 };
 typedef fvPatchField<scalar> fvPatchScalarField;
+typedef fvsPatchField<scalar> fvsPatchScalarField;
 typedef GeometricField<vector, fvPatchField, volMesh> volVectorField;
 typedef GeometricField<scalar, fvPatchField, volMesh> volScalarField;
 typedef GeometricField<scalar, fvsPatchField, surfaceMesh> surfaceScalarField;

@@ -577,3 +577,37 @@ def processor_interface_update(ranks, commsType="nonBlocking", negate=False, nPo
         _libpf.ref_pf_get(r, _p(res))
         out.append(res)
     return out
+
+
+def fvm_fill(which, nc, nCells, lower, upper, patches, a, b):
+    """Coefficient fills through the reference's schemes: which = "div": gaussConvectionScheme::fvmDiv(faceFlux = b, vf) with
+    interpolation weights a; which = "laplacian": gaussLaplacianScheme::fvmLaplacianUncorrected(gammaMagSf = a, deltaCoeffs = b,
+    vf).  patches: list of dict(faceCells, kind ("fixedValue" | "zeroGradient" | "coupled"), value (faces, nc) for fixedValue,
+    delta = patch deltaCoeffs, a, b = the two surface fields on the patch faces).  Returns dict(lower (div only), upper, diag,
+    ic, bc) with ic / bc flat over the patches, (faces, nc)."""
+    fvm("D", 1, [], [], [], [1.0], [0.0], [1.0], [], None, [0.0])   # loads the library
+    l, u = _i(lower), _i(upper)
+    n, nF = int(nCells), len(l)
+    os_, ls, lo = ldu_arrays(n, l, u)
+    ps = np.zeros(len(patches) + 1, np.int32)
+    for k, p in enumerate(patches):
+        ps[k + 1] = ps[k] + len(p["faceCells"])
+    tot = int(ps[-1])
+    kinds = _i([{"fixedValue": 0, "zeroGradient": 1, "coupled": 2}[p["kind"]] for p in patches] or [0])
+    cat = lambda f: _d(np.concatenate([np.ravel(f(p)) for p in patches]) if patches else np.zeros(1))
+    fc = _i(np.concatenate([p["faceCells"] for p in patches]) if patches else [0])
+    pvalue = cat(lambda p: np.asarray(p.get("value", np.zeros((len(p["faceCells"]), nc))), float))
+    pdelta = cat(lambda p: np.asarray(p.get("delta", np.zeros(len(p["faceCells"]))), float))
+    pa, pb = cat(lambda p: p["a"]), cat(lambda p: p["b"])
+    A, B = _d(a), _d(b)
+    low, upp, dg = np.zeros(max(nF, 1)), np.zeros(max(nF, 1)), np.zeros(n)
+    ic, bc = np.zeros(max(tot * nc, 1)), np.zeros(max(tot * nc, 1))
+    rc = _libfvm.ref_fvm_fill({"div": 0, "laplacian": 1}[which], int(nc), n, nF, _p(l), _p(u), _p(_i(os_)), _p(_i(ls)), _p(_i(lo)),
+                              len(patches), _p(ps), _p(fc), _p(kinds), _p(pvalue), _p(pdelta), _p(A), _p(B), _p(pa), _p(pb),
+                              _p(low), _p(upp), _p(dg), _p(ic), _p(bc))
+    if rc != 0:
+        raise RuntimeError("the reference code raised a FatalError")
+    out = dict(upper=upp[:nF], diag=dg, ic=ic[:tot * nc].reshape(tot, nc), bc=bc[:tot * nc].reshape(tot, nc))
+    if which == "div":
+        out["lower"] = low[:nF]
+    return out

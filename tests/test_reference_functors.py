@@ -809,3 +809,56 @@ def test_cyclic_interface_update_matches_reference_code(meshmod, orc, kind):
         for mode in ("nonBlocking", "blocking"):
             got = ref_ldu.processor_interface_update([rank], mode)[0]
             assert np.array_equal(got, with_if) and not np.array_equal(with_if, without)
+
+
+@pytest.mark.parametrize("nc", [1, 3])
+def test_coefficient_fills_match_reference_schemes(meshmod, orc, nc):
+    """Row a16, the matrix fills: gaussConvectionScheme::fvmDiv and gaussLaplacianScheme::fvmLaplacianUncorrected of the
+    reference (compiled for the host) against the oracle's convection_fill / laplacian_fill and against the patch-coefficient
+    expressions oracle/piso_oracle.py uses for fixedValue and coupled (processor) patches, bit for bit."""
+    from oracle import fvm_oracle as fo
+    m = meshmod.decompose(8, 2, 0)                       # walls + one processor patch
+    a = orc.Addr(m.nCells, m.lower, m.upper)
+    rng = np.random.default_rng(21)
+    w, phi = rng.uniform(0.3, 0.7, m.nFaces), rng.uniform(-1, 1, m.nFaces)
+    gamma, delta = rng.uniform(0.5, 1.5, m.nFaces), rng.uniform(5, 9, m.nFaces)
+    P = []
+    for p in m.patches:
+        k = len(p.faceCells)
+        d = dict(faceCells=p.faceCells, delta=rng.uniform(10, 20, k), pw=rng.uniform(0.3, 0.7, k), pphi=rng.uniform(-1, 1, k),
+                 pgamma=rng.uniform(0.5, 1.5, k))
+        if p.kind == "processor":
+            d.update(kind="coupled")
+        else:
+            d.update(kind="fixedValue", value=rng.uniform(-1, 1, (k, nc)))
+        P.append(d)
+    one = np.ones((1, nc))
+    # fvm::div
+    got = ref_ldu.fvm_fill("div", nc, m.nCells, m.lower, m.upper, [dict(p, a=p["pw"], b=p["pphi"]) for p in P], w, phi)
+    lo, up, dg = orc.convection_fill(a, w, phi)
+    assert np.array_equal(got["lower"], lo) and np.array_equal(got["upper"], up) and np.array_equal(got["diag"], dg)
+    ic, bc = [], []
+    for p in P:
+        f = p["pphi"][:, None]
+        if p["kind"] == "coupled":       # oracle/piso_oracle.py: cCi = cphi*cw, cCb = (-cphi)*(1 - cw)
+            ic.append((p["pphi"] * p["pw"])[:, None] * one)
+            bc.append(((-p["pphi"]) * (1.0 - p["pw"]))[:, None] * one)
+        else:                            # cIc = 0, cBc = (-bphi)*Ub
+            ic.append(f * np.zeros_like(p["value"]))
+            bc.append((-f) * p["value"])
+    assert np.array_equal(got["ic"], np.concatenate(ic)) and np.array_equal(got["bc"], np.concatenate(bc))
+    # fvm::laplacian (uncorrected)
+    gms = gamma * 0.01
+    got = ref_ldu.fvm_fill("laplacian", nc, m.nCells, m.lower, m.upper, [dict(p, a=p["pgamma"], b=p["delta"]) for p in P], gms, delta)
+    up, dg = orc.laplacian_fill(a, delta, gms)
+    assert np.array_equal(got["upper"], up) and np.array_equal(got["diag"], dg)
+    ic, bc = [], []
+    for p in P:
+        if p["kind"] == "coupled":       # lCi = cGamma*(-cDelta), lCb = (-cGamma)*cDelta
+            ic.append((p["pgamma"] * (-p["delta"]))[:, None] * one)
+            bc.append(((-p["pgamma"]) * p["delta"])[:, None] * one)
+        else:
+            i, b = fo.fixedValue_laplacian_coeffs(p["pgamma"], p["delta"], p["value"])
+            ic.append(i)
+            bc.append(b)
+    assert np.array_equal(got["ic"], np.concatenate(ic)) and np.array_equal(got["bc"], np.concatenate(bc))
