@@ -108,4 +108,54 @@ int ref_gauss_gradf(int n, int nF, const int *l, const int *u, const int *ownerS
         for (int k = 0; k < 3; k++) out[3 * c + k] = g[c].v_[k];
     return 0;
 }
+
+/* the same two face sums for a VECTOR surface field (ssf, bssf: 3 per face): surfaceIntegrate / surfaceSum -> out [n*3];
+ * gaussGrad<vector>::gradf -> the tensor field, out [n*9], T_ij = d_i u_j */
+int ref_surface_integrate_vec(int integrate, int n, int nF, const int *l, const int *u, const int *ownerStart,
+                              const int *losortStart, const int *losort, const double *ssf, int nB, const int *bFaceCells,
+                              const double *bssf, const double *V, double *out)
+{
+    MeshCase mc(n, nF, l, u, ownerStart, losortStart, losort, nB, bFaceCells, V);
+    fvMesh &mesh = mc.mesh;
+    GeometricField<vector, fvsPatchField, surfaceMesh> sf;
+    sf.mesh_ = &mesh;
+    sf.internal_.view(reinterpret_cast<const vector *>(ssf), nF);
+    if (nB) {
+        sf.boundary_.resize(1);
+        sf.boundary_[0].view(reinterpret_cast<const vector *>(bssf), nB);
+    }
+    if (integrate) {
+        gpuField<vector> ivf(reinterpret_cast<vector *>(out), n);
+        fvc::surfaceIntegrate(ivf, sf);
+    } else {
+        tmp<GeometricField<vector, fvPatchField, volMesh>> t = fvc::surfaceSum(sf);
+        std::copy(reinterpret_cast<const double *>(t().getField().data()),
+                  reinterpret_cast<const double *>(t().getField().data()) + 3 * (size_t)n, out);
+    }
+    return 0;
+}
+
+int ref_gauss_gradf_vec(int n, int nF, const int *l, const int *u, const int *ownerStart, const int *losortStart,
+                        const int *losort, const double *Sf, const double *ssf, int nB, const int *bFaceCells,
+                        const double *bSf, const double *bssf, const double *V, double *out)
+{
+    MeshCase mc(n, nF, l, u, ownerStart, losortStart, losort, nB, bFaceCells, V);
+    fvMesh &mesh = mc.mesh;
+    GeometricField<vector, fvsPatchField, surfaceMesh> area, sf;
+    area.mesh_ = sf.mesh_ = &mesh;
+    area.internal_.view(reinterpret_cast<const vector *>(Sf), nF);
+    sf.internal_.view(reinterpret_cast<const vector *>(ssf), nF);
+    if (nB) {
+        area.boundary_.resize(1);
+        area.boundary_[0].view(reinterpret_cast<const vector *>(bSf), nB);
+        sf.boundary_.resize(1);
+        sf.boundary_[0].view(reinterpret_cast<const vector *>(bssf), nB);
+    }
+    mesh.Sf_ = &area;
+    tmp<GeometricField<tensor, fvPatchField, volMesh>> t = fv::gaussGrad<vector>::gradf(sf, word("grad"));
+    const tensor *g = t().getField().data();
+    for (int c = 0; c < n; c++)
+        for (int k = 0; k < 9; k++) out[9 * c + k] = g[c].v_[k];
+    return 0;
+}
 }

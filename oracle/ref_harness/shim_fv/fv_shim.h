@@ -52,6 +52,43 @@ template <class A, class B> struct outerProduct;
 template <> struct outerProduct<vector, scalar> {
     typedef vector type;
 };
+// Tensor<scalar> for grad(vector): T_ij = a_i*b_j (TensorI.H:439-448), component-wise +=, -=, / (VectorSpaceI.H)
+struct tensor {
+    scalar v_[9];
+    tensor() {}
+    void operator+=(const tensor &o)
+    {
+        for (int i = 0; i < 9; i++) v_[i] += o.v_[i];
+    }
+    void operator-=(const tensor &o)
+    {
+        for (int i = 0; i < 9; i++) v_[i] -= o.v_[i];
+    }
+};
+inline tensor operator*(const vector &a, const vector &b)
+{
+    tensor t;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) t.v_[3 * i + j] = a.v_[i] * b.v_[j];
+    return t;
+}
+inline tensor operator/(const tensor &a, scalar s)
+{
+    tensor t;
+    for (int i = 0; i < 9; i++) t.v_[i] = a.v_[i] / s;
+    return t;
+}
+template <> struct pTraits<tensor> {
+    static const tensor zero;
+};
+inline const tensor pTraits<tensor>::zero = [] {
+    tensor t;
+    for (int i = 0; i < 9; i++) t.v_[i] = 0;
+    return t;
+}();
+template <> struct outerProduct<vector, vector> {
+    typedef tensor type;
+};
 
 struct dimensionSet {
 };
@@ -133,6 +170,10 @@ inline void operator/=(gpuField<scalar> &a, const gpuField<scalar> &b)
     for (label i = 0; i < a.size(); i++) a.data()[i] /= b.data()[i];
 }
 inline void operator/=(gpuField<vector> &a, const gpuField<scalar> &b) // FieldFunctions: f[i] = f[i] / s[i]
+{
+    for (label i = 0; i < a.size(); i++) a.data()[i] = a.data()[i] / b.data()[i];
+}
+inline void operator/=(gpuField<tensor> &a, const gpuField<scalar> &b)
 {
     for (label i = 0; i < a.size(); i++) a.data()[i] = a.data()[i] / b.data()[i];
 }

@@ -400,6 +400,30 @@ def surface_integrate(nCells, lower, upper, ssf, bFaceCells, bssf, V, integrate=
     return out
 
 
+def surface_integrate_vec(nCells, lower, upper, ssf, bFaceCells, bssf, V, integrate=True):
+    """fvc::surfaceIntegrate / surfaceSum of a VECTOR surface field ((faces, 3) arrays) -> (nCells, 3)"""
+    surface_integrate(1, [], [], [], [], [], [1.0])  # loads the library
+    l, u = _i(lower), _i(upper)
+    os_, ls, lo = ldu_arrays(nCells, l, u)
+    s, bs, v, bfc = _d(np.ravel(ssf)), _d(np.ravel(bssf)), _d(V), _i(bFaceCells)
+    out = np.zeros(3 * int(nCells))
+    _libfv.ref_surface_integrate_vec(int(bool(integrate)), int(nCells), len(l), _p(l), _p(u), _p(_i(os_)), _p(_i(ls)),
+                                     _p(_i(lo)), _p(s), len(bfc), _p(bfc), _p(bs), _p(v), _p(out))
+    return out.reshape(-1, 3)
+
+
+def gauss_gradf_vec(nCells, lower, upper, Sf, ssf, bFaceCells, bSf, bssf, V):
+    """fv::gaussGrad<vector>::gradf: the tensor field T_ij = d_i u_j, (nCells, 3, 3)"""
+    surface_integrate(1, [], [], [], [], [], [1.0])
+    l, u = _i(lower), _i(upper)
+    os_, ls, lo = ldu_arrays(nCells, l, u)
+    A, s, bA, bs, v, bfc = _d(np.ravel(Sf)), _d(np.ravel(ssf)), _d(np.ravel(bSf)), _d(np.ravel(bssf)), _d(V), _i(bFaceCells)
+    out = np.zeros(9 * int(nCells))
+    _libfv.ref_gauss_gradf_vec(int(nCells), len(l), _p(l), _p(u), _p(_i(os_)), _p(_i(ls)), _p(_i(lo)), _p(A), _p(s), len(bfc),
+                               _p(bfc), _p(bA), _p(bs), _p(v), _p(out))
+    return out.reshape(-1, 3, 3)
+
+
 def gauss_gradf(nCells, lower, upper, Sf, ssf, bFaceCells, bSf, bssf, V):
     """The reference's fv::gaussGrad<scalar>::gradf (gaussGrad.C:34-243): per cell the sum of Sf*ssf over the
     owner faces, minus the neighbour faces, plus the boundary faces, divided by the volume.  Returns (nCells, 3)."""

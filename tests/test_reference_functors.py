@@ -463,6 +463,14 @@ def test_fv_face_sums_match_reference_code(meshmod, orc, dims):
     got = np.asarray(orc.gauss_grad(a, Sf.ravel(), ssf, bfc, bSf.ravel(), bssf, V, 1)).reshape(m.nCells, 3)
     ref = ref_ldu.gauss_gradf(m.nCells, m.lower, m.upper, Sf, ssf, bfc, bSf, bssf, V)
     np.testing.assert_array_equal(got, ref)
+    # the vector instantiations: surfaceIntegrate / surfaceSum of a vector flux, gaussGrad<vector>::gradf (tensor result)
+    vsf, bvsf = rng.uniform(-1, 1, (m.nFaces, 3)), rng.uniform(-1, 1, (len(bfc), 3))
+    got = np.asarray(orc.surface_integrate(a, vsf.ravel(), bfc, bvsf.ravel(), V, 3)).reshape(m.nCells, 3)
+    np.testing.assert_array_equal(got, ref_ldu.surface_integrate_vec(m.nCells, m.lower, m.upper, vsf, bfc, bvsf, V))
+    got = np.asarray(orc.surface_integrate(a, vsf.ravel(), bfc, bvsf.ravel(), V, 3, False, +1)).reshape(m.nCells, 3)
+    np.testing.assert_array_equal(got, ref_ldu.surface_integrate_vec(m.nCells, m.lower, m.upper, vsf, bfc, bvsf, V, False))
+    got = np.asarray(orc.gauss_grad(a, Sf.ravel(), vsf.ravel(), bfc, bSf.ravel(), bvsf.ravel(), V, 3)).reshape(m.nCells, 3, 3)
+    np.testing.assert_array_equal(got, ref_ldu.gauss_gradf_vec(m.nCells, m.lower, m.upper, Sf, vsf, bfc, bSf, bvsf, V))
 
 
 def _oracle_rank_hierarchies(meshmod, orc, n, nR, mergeLevels, dims=None):
