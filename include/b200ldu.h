@@ -272,6 +272,11 @@ int b200ldu_field_binary(b200ldu_ctx *ctx, int op, long long n, int nCompA, cons
 int b200ldu_field_unary(b200ldu_ctx *ctx, int op, long long n, double s, const double *a_d, double *out_d);
 int b200ldu_field_dot3(b200ldu_ctx *ctx, long long n, const double *a_d, const double *b_d, double *out_d);
 int b200ldu_field_gather(b200ldu_ctx *ctx, int n, int nComp, const int *cells_d, const double *field_d, double *out_d);
+/* snGradScheme::snGrad on the internal faces (FV/finiteVolume/snGradSchemes/snGradScheme/snGradScheme.C:101-160):
+ * out[f] = deltaCoeffs[f]*(vf[nei] - vf[own]).  With it fvc::laplacian (gaussLaplacianSchemes.C:95-112: div(gamma*snGrad*magSf))
+ * and the non-orthogonal correction (correctedSnGrad.C:44-75, gaussLaplacianScheme.C:92-130: corrVecs & interpolate(grad))
+ * are compositions of entry points of this header (rapidcfd-dev_b200/fvc.py: laplacian, snGrad_correction). */
+int b200ldu_fv_sngrad(b200ldu_addr *a, int nComp, const double *deltaCoeffs_d, const double *vf_d, double *out_d);
 
 /* ---- structural self-check of the banded layout (host only, no GPU, no arithmetic);
  * used by the CPU test-suite.  what: 0 perm 1 iperm 2 sliceStart(int64) 3 sliceW(u16)

@@ -175,6 +175,7 @@ const int *orc_gamg_patch_face_restrict(const orc_gamg *g, int lev); /* fine pat
 void orc_gamg_agglomerate_patch_coeffs(const orc_gamg *g, int lev, const double *fine, double *coarse);
 
 /* ---- finite-volume face-sum loops (Appendix A.11) ---- */
+void orc_sngrad(const orc_addr *a, int nComp, const double *deltaCoeffs, const double *vf, double *out);
 /* nComp = 1 (scalar) or 3 (vector); fields are AoS: x[c*nComp + k]. */
 void orc_surface_integrate(const orc_addr *a, int nComp, const double *ssf,
                            int nBFaces, const int *bFaceCells, const double *bssf,

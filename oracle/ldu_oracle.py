@@ -115,6 +115,7 @@ def lib():
         for nm in ("orc_addr_patch_start", "orc_addr_face_cells"):
             getattr(L, nm).restype = c_ip
             getattr(L, nm).argtypes = [C.c_void_p]
+        L.orc_sngrad.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp, c_dp]
         L.orc_comm_sum.argtypes = [C.c_void_p, c_dp, C.c_int]
         L.orc_patch_neighbour_field.argtypes = [C.c_void_p, c_dp, C.c_void_p, c_dp]
         L.orc_gamg_addr.restype = C.c_void_p
@@ -472,6 +473,13 @@ def convection_fill(addr, weights, phi):
     diag = np.zeros(addr.nCells)
     lib().orc_convection_fill(addr.h, _d(f64(weights)), _d(f64(phi)), _d(lower), _d(upper), _d(diag))
     return lower, upper, diag
+
+
+def sngrad(addr, deltaCoeffs, vf, nComp=1):
+    """snGradScheme::snGrad on the internal faces: deltaCoeffs*(vf[nei] - vf[own])"""
+    out = np.zeros(addr.nFaces * nComp)
+    lib().orc_sngrad(addr.h, nComp, _d(f64(deltaCoeffs)), _d(f64(vf)), _d(out))
+    return out.reshape(addr.nFaces, nComp) if nComp > 1 else out
 
 
 def interpolate_linear(addr, w, vf, nComp=1):

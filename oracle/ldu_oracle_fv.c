@@ -135,3 +135,14 @@ void orc_add_boundary_source(int nBFaces, const int *bFaceCells, const double *b
     for (int bf = 0; bf < nBFaces; bf++)
         source[bFaceCells[bf]] = source[bFaceCells[bf]] + boundaryCoeffs[bf];
 }
+
+/* snGradScheme::snGrad on the internal faces: FV/finiteVolume/snGradSchemes/snGradScheme/snGradScheme.C:101-160
+ * (snGradFunctor: d*(vf[neighbour] - vf[owner])) */
+void orc_sngrad(const orc_addr *a, int nComp, const double *deltaCoeffs, const double *vf, double *out)
+{
+    for (int f = 0; f < a->nFaces; f++)
+        for (int k = 0; k < nComp; k++) {
+            double d = vf[(size_t)a->u[f] * nComp + k] - vf[(size_t)a->l[f] * nComp + k];
+            out[(size_t)f * nComp + k] = deltaCoeffs[f] * d;
+        }
+}

@@ -66,7 +66,7 @@ EXPORTS = [
     "b200ldu_fvm_add_boundary_diag", "b200ldu_fvm_add_boundary_source", "b200ldu_fvm_A", "b200ldu_fvm_H",
     "b200ldu_fvm_flux", "b200ldu_fvm_residual", "b200ldu_fvm_relax", "b200ldu_fvm_set_reference",
     "b200ldu_fvm_solve", "b200ldu_fv_patch_neighbour_field",
-    "b200ldu_field_binary", "b200ldu_field_unary", "b200ldu_field_dot3", "b200ldu_field_gather",
+    "b200ldu_fv_sngrad", "b200ldu_field_binary", "b200ldu_field_unary", "b200ldu_field_dot3", "b200ldu_field_gather",
 ]
 
 _lib = None
@@ -141,6 +141,7 @@ def lib():
     L.b200ldu_fvm_relax.argtypes = [vp, C.c_int, C.c_double, vp, vp, vp, vp]
     L.b200ldu_fvm_set_reference.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     L.b200ldu_fv_patch_neighbour_field.argtypes = [vp, C.c_int, vp, vp]
+    L.b200ldu_fv_sngrad.argtypes = [vp, C.c_int, vp, vp, vp]
     L.b200ldu_field_binary.argtypes = [vp, C.c_int, C.c_longlong, C.c_int, vp, C.c_int, vp, vp]
     L.b200ldu_field_unary.argtypes = [vp, C.c_int, C.c_longlong, C.c_double, vp, vp]
     L.b200ldu_field_dot3.argtypes = [vp, C.c_longlong, vp, vp, vp]
@@ -578,6 +579,13 @@ def fv_patch_neighbour_field(addr, nComp, field):
     pnf = _newlike(field, max(addr.nPatchFaces * nComp, 1))
     check(lib().b200ldu_fv_patch_neighbour_field(addr.h, nComp, _dp(field), _dp(pnf)))
     return pnf[: addr.nPatchFaces * nComp]
+
+
+def fv_sngrad(addr, nComp, deltaCoeffs, vf):
+    """snGradScheme::snGrad on the internal faces"""
+    out = _newlike(vf, addr.nFaces * nComp)
+    check(lib().b200ldu_fv_sngrad(addr.h, nComp, _dp(deltaCoeffs), _dp(vf), _dp(out)))
+    return out
 
 
 def fv_boundary_set(addr, bFaceCells):

@@ -62,3 +62,17 @@ extern "C" int b200ldu_field_gather(b200ldu_ctx *ctx, int n, int nComp, const in
     KERNEL_CHECK();
     return B200LDU_OK;
 }
+
+// snGradScheme::snGrad of a cell field on the internal faces (the boundary values come from the boundary conditions)
+extern "C" int b200ldu_fv_sngrad(b200ldu_addr *a, int nComp, const double *deltaCoeffs_d, const double *vf_d, double *out_d)
+{
+    if (!a || !deltaCoeffs_d || !vf_d || !out_d || (nComp != 1 && nComp != 3)) return B200LDU_EINVAL;
+    if (a->nFaces == 0) return B200LDU_OK;
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    const long long tot = (long long)a->nFaces * nComp;
+    sngrad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, a->ctx->stream>>>(a->nFaces, nComp, a->d_l, a->d_u, deltaCoeffs_d, vf_d,
+                                                                             out_d);
+    a->ctx->launches++;
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}

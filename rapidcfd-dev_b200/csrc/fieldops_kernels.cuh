@@ -66,6 +66,16 @@ __global__ void dot3_kernel(long long n, const double *__restrict__ a, const dou
     out[i] = __dadd_rn(s, __dmul_rn(a[3 * i + 2], b[3 * i + 2]));
 }
 
+// snGradScheme::snGrad on the internal faces (snGradScheme.C:101-160): d*(vf[nei] - vf[own])
+__global__ void sngrad_kernel(int nFaces, int nc, const int *__restrict__ l, const int *__restrict__ u,
+                              const double *__restrict__ delta, const double *__restrict__ vf, double *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nFaces * nc) return;
+    const int f = (int)(i / nc), k = (int)(i - (long long)f * nc);
+    out[i] = __dmul_rn(delta[f], __dsub_rn(vf[(size_t)u[f] * nc + k], vf[(size_t)l[f] * nc + k]));
+}
+
 // patchInternalField: out[i][k] = field[cells[i]][k]
 __global__ void gather_kernel(int n, int nc, const int *__restrict__ cells, const double *__restrict__ f, double *__restrict__ out)
 {

@@ -146,4 +146,9 @@ void hk_field_gather(int n, int nc, const int *cells, const double *f, double *o
 {
     launch((long long)n * nc, 256, fieldk::gather_kernel, n, nc, cells, f, out);
 }
+
+void hk_sngrad(int nFaces, int nc, const int *l, const int *u, const double *delta, const double *vf, double *out)
+{
+    launch((long long)nFaces * nc, 256, fieldk::sngrad_kernel, nFaces, nc, l, u, delta, vf, out);
+}
 }

@@ -246,6 +246,10 @@ class _Capi:
         return FieldOps._t(np.stack(cols, axis=1))
 
     @staticmethod
+    def fv_sngrad(addr, nc, delta, vf):
+        return FieldOps._t(orc.sngrad(addr.o, _np(delta), _np(vf), nc))
+
+    @staticmethod
     def fv_convection_fill(addr, w, phi):
         return tuple(FieldOps._t(x) for x in orc.convection_fill(addr.o, _np(w), _np(phi)))
 

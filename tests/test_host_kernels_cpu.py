@@ -195,3 +195,17 @@ def test_fieldops_kernels_on_host(hk):
         out = np.zeros((77, nc))
         hk.hk_field_gather(77, nc, _d(cells), _d(np.ascontiguousarray(f)), _d(out))
         assert np.array_equal(out, f.reshape(n, nc)[cells])
+
+
+def test_sngrad_kernel_on_host(hk, meshmod, orc):
+    m = meshmod.hex_mesh(5, 4, 3)
+    a = orc.Addr(m.nCells, m.lower, m.upper)
+    rng = np.random.default_rng(3)
+    delta = rng.uniform(1, 2, m.nFaces)
+    l, u = np.ascontiguousarray(m.lower, dtype=np.int32), np.ascontiguousarray(m.upper, dtype=np.int32)
+    for nc in (1, 3):
+        vf = rng.uniform(-1, 1, (m.nCells, nc))
+        out = np.zeros((m.nFaces, nc))
+        hk.hk_sngrad(m.nFaces, nc, _d(l), _d(u), _d(delta), _d(np.ascontiguousarray(vf)), _d(out))
+        assert np.array_equal(out, np.asarray(orc.sngrad(a, delta, vf.ravel(), nc)).reshape(m.nFaces, nc))
+        assert np.array_equal(out, delta[:, None] * (vf[m.upper] - vf[m.lower]))
