@@ -9,6 +9,11 @@ import oracle_backend
 
 
 def test_corrected_sngrad_and_explicit_laplacian_on_a_sheared_mesh(meshmod, orc):
+    run_sheared_case(meshmod, *oracle_backend.fixture())
+
+
+def run_sheared_case(meshmod, capi, ctx, torch):
+    """shared with the `-m gpu` test of tests/test_zzz_fvm_gpu.py (there capi is the CUDA library)"""
     ff = importlib.import_module("rapidcfd-dev_b200.foamfile")
     fvc = importlib.import_module("rapidcfd-dev_b200.fvc")
     m = meshmod.hex_mesh(6, 5, 4)
@@ -27,20 +32,20 @@ def test_corrected_sngrad_and_explicit_laplacian_on_a_sheared_mesh(meshmod, orc)
     assert np.abs(corrVecs).max() > 0.05                      # the mesh really is non-orthogonal
     g = np.array([0.7, -1.3, 0.4])
     psi = C @ g
-    capi, ctx, torch = oracle_backend.fixture()
     addr = capi.LduAddressing(ctx, pm.nCells, lower, upper)
     capi.fv_boundary_set(addr, bfc)
     ops = capi.FieldOps(ctx)
-    t = lambda a: torch.from_numpy(np.array(a, dtype=np.float64).ravel())
+    t = lambda a: torch.from_numpy(np.array(a, dtype=np.float64).ravel()).to(ctx.device)
+    h = lambda x: x.cpu().numpy()
     bvf = Cf[nI:] @ g                                         # exact boundary face values
     corr = fvc.snGrad_correction(capi, addr, ops, t(corrVecs), t(Sf[:nI]), t(geo["weights"]), t(psi), t(Sf[nI:]), t(bvf), t(V))
     sn = capi.fv_sngrad(addr, 1, t(nonOrthDelta), t(psi))
-    np.testing.assert_allclose(sn.numpy() + corr.numpy(), n[:nI] @ g, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(h(sn) + h(corr), n[:nI] @ g, rtol=0, atol=1e-10)
     # explicit Laplacian of the linear field with exact boundary fluxes: zero
     gamma = 1.7
     bFlux = gamma * magSf[nI:] * (n[nI:] @ g)
     lap = fvc.laplacian(capi, addr, ops, 1, t(gamma * magSf[:nI]), t(nonOrthDelta), t(psi), t(bFlux), t(V), correction=corr)
-    np.testing.assert_allclose(lap.numpy(), 0, atol=1e-9)
+    np.testing.assert_allclose(h(lap), 0, atol=1e-9)
     # without the correction the operator is what fvc::div(gamma*snGrad*magSf) gives with the uncorrected scheme
     lap0 = fvc.laplacian(capi, addr, ops, 1, t(gamma * magSf[:nI]), t(nonOrthDelta), t(psi), t(bFlux), t(V))
     flux = gamma * magSf[:nI] * (nonOrthDelta * (psi[upper] - psi[lower]))
@@ -48,5 +53,5 @@ def test_corrected_sngrad_and_explicit_laplacian_on_a_sheared_mesh(meshmod, orc)
     np.add.at(ref, lower, flux)
     np.subtract.at(ref, upper, flux)
     np.add.at(ref, bfc, bFlux)
-    np.testing.assert_allclose(lap0.numpy(), ref / V, rtol=1e-12, atol=1e-12)
-    assert np.abs(lap0.numpy()).max() > 1e-3                  # ... which is not zero on this mesh
+    np.testing.assert_allclose(h(lap0), ref / V, rtol=1e-12, atol=1e-12)
+    assert np.abs(h(lap0)).max() > 1e-3                  # ... which is not zero on this mesh

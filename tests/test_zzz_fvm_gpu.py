@@ -314,3 +314,10 @@ def test_gpu_fvm_vs_golden(gpu, meshmod, orc):
     np.testing.assert_allclose(host(dev.p), G["piso.p"], rtol=0, atol=1e-9)
     np.testing.assert_allclose(host(dev.phi), G["piso.phi"], rtol=0, atol=1e-11)
     dev.close()
+
+
+def test_fvc_compositions_on_the_device(gpu, meshmod):
+    """snGrad kernel, corrected snGrad and explicit Laplacian (rapidcfd-dev_b200/fvc.py) on a sheared mesh"""
+    from test_fvc_cpu import run_sheared_case
+    capi, ctx, torch = gpu
+    run_sheared_case(meshmod, capi, ctx, torch)
