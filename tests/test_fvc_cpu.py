@@ -55,3 +55,4 @@ def run_sheared_case(meshmod, capi, ctx, torch):
     np.add.at(ref, bfc, bFlux)
     np.testing.assert_allclose(h(lap0), ref / V, rtol=1e-12, atol=1e-12)
     assert np.abs(h(lap0)).max() > 1e-3                  # ... which is not zero on this mesh
+    addr.close()
