@@ -183,7 +183,7 @@ int b200ldu_gamg_restrict_addr(const b200ldu_gamg *g, int lev, int *out_h);
  * fvc::surfaceIntegrate / surfaceSum: FV/finiteVolume/fvc/fvcSurfaceIntegrate.C:138-203,
  * :264-360 ; gaussGrad::gradf: FV/finiteVolume/gradSchemes/gaussGrad/gaussGrad.C:143-242 ;
  * fvmLaplacianUncorrected fill: gaussLaplacianScheme.C:63-64 ; fvmDiv fill:
- * gaussConvectionScheme.C:95-97 ; linear interpolate: surfaceInterpolationScheme.C:159-240 ;
+ * gaussConvectionScheme.C:95-97 ; linear interpolate: surfaceInterpolationScheme.C:272-351 ;
  * addBoundaryDiag/Source: FV/fvMatrices/fvMatrix/fvMatrix.C:209-226,290-312. */
 int b200ldu_fv_boundary_set(b200ldu_addr *a, int nBFaces, const int *bFaceCells_h);
 int b200ldu_fv_surface_integrate(b200ldu_addr *a, int nComp, const double *ssf_d,

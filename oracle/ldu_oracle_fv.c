@@ -107,16 +107,18 @@ void orc_convection_fill(const orc_addr *a, const double *weights, const double 
 
 /* linear surface interpolation of a cell field to internal faces:
  * FV/interpolation/surfaceInterpolation/surfaceInterpolationScheme/
- * surfaceInterpolationScheme.C:159-240 -- sf = w*vf[own] + (1-w)*vf[nei]
+ * surfaceInterpolationScheme.C:272-351 (the one-weight form that interpolate(vf) reaches, :376-400;
+ * not the two-weight form of :159-262) -- sf = w*(vf[own] - vf[nei]) + vf[nei]
  * (next-row component) */
 void orc_interpolate_linear(const orc_addr *a, int nComp, const double *w, const double *vf,
                             double *sf)
 {
     for (int f = 0; f < a->nFaces; f++)
         for (int k = 0; k < nComp; k++) {
-            double p1 = w[f] * vf[(size_t)a->l[f] * nComp + k];
-            double p2 = (1 - w[f]) * vf[(size_t)a->u[f] * nComp + k];
-            sf[(size_t)f * nComp + k] = p1 + p2;
+            double own = vf[(size_t)a->l[f] * nComp + k], nei = vf[(size_t)a->u[f] * nComp + k];
+            double d = own - nei;
+            double p = w[f] * d;
+            sf[(size_t)f * nComp + k] = p + nei;
         }
 }
 

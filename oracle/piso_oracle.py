@@ -4,9 +4,10 @@ Follows /root/reference/applications/solvers/incompressible/icoFoam/icoFoam.C:55
 field expression evaluated as the reference's gpuField operators evaluate it: one rounded elementwise operation per
 operator, in the written order (numpy does the same).  Schemes: ddt Euler, div Gauss linear, laplacian Gauss linear
 uncorrected (orthogonal meshes), grad Gauss linear, interpolate linear -- the cavity tutorial's fvSchemes.  Boundary
-conditions: U fixedValue on every boundary face, p zeroGradient (the lid-driven cavity); single domain.  PARITY
-UNPINNED (the application needs the whole library); checked by the physics it has to produce
-(tests/test_oracle_piso.py).  FV/ = src/finiteVolume/.
+conditions: U fixedValue on every boundary face, p zeroGradient (the lid-driven cavity); single domain.  The
+pieces are pinned (matrix glue, coefficient fills, face sums, solvers, the Euler ddt statements:
+tests/test_reference_functors.py); the step AS A WHOLE is PARITY UNPINNED (the application needs the whole library)
+and is checked by the physics it has to produce (tests/test_oracle_piso.py).  FV/ = src/finiteVolume/.
 """
 import numpy as np
 
@@ -54,9 +55,9 @@ class Cavity:
         return (a[:, 0] * b[:, 0] + a[:, 1] * b[:, 1]) + a[:, 2] * b[:, 2]
 
     def interpolate(self, vf):
-        """linear: w*vf[own] + (1 - w)*vf[nei] (surfaceInterpolationScheme.C:159-240)"""
+        """linear: w*(vf[own] - vf[nei]) + vf[nei] (surfaceInterpolationScheme.C:272-351, the form interpolate(vf) uses)"""
         w = self.w if vf.ndim == 1 else self.w[:, None]
-        return w * vf[self.lower] + (1 - w) * vf[self.upper]
+        return w * (vf[self.lower] - vf[self.upper]) + vf[self.upper]
 
     def pnf(self, vf):
         """patchNeighbourField of the processor patches, (nCoupledFaces[, 3])"""
@@ -67,7 +68,7 @@ class Cavity:
         return np.stack([self.addr.patch_neighbour_field(np.ascontiguousarray(vf[:, k]), self.comm) for k in range(3)], axis=1)
 
     def interpolate_coupled(self, vf, pnf=None):
-        """coupled patch faces: w*patchInternalField + (1 - w)*patchNeighbourField (:246-262)"""
+        """coupled patch faces: w*patchInternalField + (1 - w)*patchNeighbourField (:357-370)"""
         pnf = self.pnf(vf) if pnf is None else pnf
         w = self.cw if vf.ndim == 1 else self.cw[:, None]
         return w * vf[self.cfc] + (1 - w) * pnf

@@ -7,6 +7,7 @@
  *   fvScalarMatrix/fvScalarMatrix.H, .C          solveSegregated, residual, H for scalars
  *   FV/finiteVolume/convectionSchemes/gaussConvectionScheme/gaussConvectionScheme.C   fvmDiv (coefficient fill + patch coefficients)
  *   FV/finiteVolume/laplacianSchemes/gaussLaplacianScheme/gaussLaplacianScheme.C      fvmLaplacianUncorrected
+ *   FV/finiteVolume/ddtSchemes/ddtScheme/ddtScheme.C, EulerDdtScheme/EulerDdtScheme.C  fvmDdt, fvcDdtPhiCorr, fvcDdtPhiCoeff
  * against oracle/ref_harness/shim_fvm/.  The linear solver behind solveSegregated is a recorder: it keeps the diagonal and
  * the source it is handed, which is what the folding has to get right.
  */
@@ -21,6 +22,9 @@
 #include "schemes_shim.h"
 #include "gaussConvectionScheme.C" /* reference: fvmDiv :76-115 */
 #include "gaussLaplacianScheme.C"  /* reference: fvmLaplacianUncorrected :46-89 */
+#include "ddt_shim.h"
+#include "ddtScheme.C"      /* reference: fvcDdtPhiCoeff :139-174 */
+#include "EulerDdtScheme.C" /* reference: fvmDdt :331-361, fvcDdtPhiCorr :523-551 */
 
 #include <algorithm>
 
@@ -286,6 +290,63 @@ int ref_fvm_fill(int which, int nc, int n, int nF, const int *l, const int *u, c
                            zerosP.data());
             run(C, vector());
         }
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+
+/* Euler ddt of a vector field U (old-time values U0 [n*3], boundary values per patch face [tot*3], fixesValue per patch):
+ * EulerDdtScheme<vector>::fvmDdt(U) -> diag [n], source [n*3];  fvcDdtPhiCorr(U, phi) with phi.oldTime() = phi0 (internal
+ * faces) / bphi0 (patch faces), face areas Sf / bSf, linear weights w -> ddtCorr on the internal faces [nF] and patch faces
+ * [tot] */
+int ref_ddt(int n, int nF, const int *l, const int *u, const int *ownerStart, const int *losortStart, const int *losort, int nP,
+            const int *patchStart, const int *faceCells, const int *fixesValue, double deltaT, const double *V, const double *U0,
+            const double *bU0, const double *phi0, const double *bphi0, const double *Sf, const double *bSf, const double *w,
+            double *diag, double *source, double *ddtCorr, double *bddtCorr)
+{
+    try {
+        const int tot = nP ? patchStart[nP] : 0;
+        std::vector<int> coupled((size_t)std::max(nP, 1), 0);
+        std::vector<double> zerosN((size_t)n * 3 + 3, 0.0), zerosF((size_t)nF + 1, 0.0), zerosP((size_t)tot * 3 + 3, 0.0);
+        Case<vector> C(n, nF, l, u, ownerStart, losortStart, losort, nP, patchStart, faceCells, coupled.data(), zerosP.data(), V, U0,
+                       zerosN.data(), zerosF.data(), nullptr, zerosN.data(), zerosP.data(), zerosP.data());
+        C.mesh.time_.deltaT_ = deltaT;
+        for (int p = 0; p < nP; p++) {
+            fvPatchField<vector> &pf = C.psi.boundary_.p_[(size_t)p];
+            const int s = patchStart[p], np = patchStart[p + 1] - s;
+            pf.kind_ = fixesValue[p] ? 0 : 1;
+            static_cast<gpuField<vector> &>(pf) = tmp<gpuField<vector>>(
+                new gpuField<vector>(reinterpret_cast<const vector *>(bU0 + (size_t)s * 3), np));
+        }
+        auto surfS = [&](surfaceScalarField &f, const double *in, const double *pin) {
+            f.mesh_ = &C.mesh;
+            f.internal_ = scalargpuField(in, nF);
+            f.boundary_.p_.resize((size_t)nP);
+            for (int p = 0; p < nP; p++)
+                static_cast<scalargpuField &>(f.boundary_.p_[(size_t)p]) =
+                    tmp<scalargpuField>(new scalargpuField(pin + patchStart[p], patchStart[p + 1] - patchStart[p]));
+        };
+        surfaceScalarField phi, weights;
+        surfS(phi, phi0, bphi0);
+        std::vector<double> half((size_t)tot + 1, 0.5);
+        surfS(weights, w, half.data());
+        surfaceVectorField area;
+        area.mesh_ = &C.mesh;
+        area.internal_ = gpuField<vector>(reinterpret_cast<const vector *>(Sf), nF);
+        area.boundary_.p_.resize((size_t)nP);
+        for (int p = 0; p < nP; p++)
+            static_cast<gpuField<vector> &>(area.boundary_.p_[(size_t)p]) = tmp<gpuField<vector>>(
+                new gpuField<vector>(reinterpret_cast<const vector *>(bSf + (size_t)patchStart[p] * 3), patchStart[p + 1] - patchStart[p]));
+        C.mesh.Sf_ = &area;
+        C.mesh.weights_ = &weights;
+        fv::EulerDdtScheme<vector> scheme(C.mesh);
+        tmp<fvMatrix<vector>> tM = scheme.fvmDdt(C.psi);
+        put(tM().diag(), diag);
+        put(tM().source(), source);
+        tmp<surfaceScalarField> tc = scheme.fvcDdtPhiCorr(C.psi, phi);
+        put(tc().internal_, ddtCorr);
+        for (int p = 0; p < nP; p++) put(tc().boundary_.p_[(size_t)p], bddtCorr + patchStart[p]);
         return 0;
     } catch (const std::exception &) {
         return -1;

@@ -249,6 +249,7 @@ public:
     // zeroGradientFvPatchField.C:111-150; coupled patches: coupledFvPatchField.C:162-209); patchDelta_ = patch().deltaCoeffs()
     int kind_ = 0;
     gpuField<scalar> patchDelta_;
+    bool fixesValue() const { return !coupled_ && kind_ == 0; } // fixedValueFvPatchField.H fixesValue
     tmp<gpuField<Type>> valueInternalCoeffs(const tmp<gpuField<scalar>> &w) const
     {
         gpuField<Type> *r = new gpuField<Type>(this->size(), pTraits<Type>::zero);
@@ -352,7 +353,8 @@ class fvMesh
 {
 public:
     // geometry fields the scheme sources name (only parsed unless the harness points them somewhere)
-    const GeometricField<scalar, fvsPatchField, surfaceMesh> *magSf_ = nullptr, *deltaCoeffs_ = nullptr;
+    const GeometricField<scalar, fvsPatchField, surfaceMesh> *magSf_ = nullptr, *deltaCoeffs_ = nullptr, *weights_ = nullptr;
+    const GeometricField<scalar, fvsPatchField, surfaceMesh> &weights() const { return *weights_; }
     const GeometricField<vector, fvsPatchField, surfaceMesh> *Sf_ = nullptr;
     const GeometricField<scalar, fvsPatchField, surfaceMesh> &magSf() const { return *magSf_; }
     const GeometricField<scalar, fvsPatchField, surfaceMesh> &deltaCoeffs() const { return *deltaCoeffs_; }
@@ -360,6 +362,23 @@ public:
     lduAddressing addr_;
     fvBoundaryMesh boundary_;
     VolumeField V_;
+    // Time and the volumes as the ddt schemes read them
+    struct TimeStub {
+        scalar deltaT_ = 1;
+        scalar deltaTValue() const { return deltaT_; }
+        dimensioned<scalar> deltaT() const { return dimensioned<scalar>(deltaT_); }
+        word timeName() const { return word("0"); }
+    };
+    TimeStub time_;
+    const TimeStub &time() const { return time_; }
+    bool moving() const { return false; }
+    struct VscHolder {
+        const gpuField<scalar> *f;
+        const VscHolder &operator()() const { return *this; }
+        const gpuField<scalar> &getField() const { return *f; }
+    };
+    VscHolder Vsc() const { return VscHolder{&V_.f_}; }
+    VscHolder Vsc0() const { return VscHolder{&V_.f_}; }
     const lduAddressing &lduAddr() const { return addr_; }
     const labelgpuList &owner() const { return addr_.lower_; }
     const labelgpuList &neighbour() const { return addr_.upper_; }
@@ -453,6 +472,10 @@ public:
         PatchField<Type> &operator[](label i) { return p_[(size_t)i]; }
         const PatchField<Type> &operator[](label i) const { return p_[(size_t)i]; }
         void updateCoeffs() {}
+        // boundary-field algebra named by scheme variants that are parsed but never run here
+        template <class O> GeometricBoundaryField operator*(const O &) const { throw std::runtime_error("not used"); }
+        template <class O> GeometricBoundaryField operator-(const O &) const { throw std::runtime_error("not used"); }
+        friend GeometricBoundaryField operator*(scalar, const GeometricBoundaryField &) { throw std::runtime_error("not used"); }
         lduInterfaceFieldPtrsList scalarInterfaces() const
         {
             lduInterfaceFieldPtrsList l;
@@ -477,8 +500,17 @@ public:
     GeometricBoundaryField boundary_;
     label eventNo_ = 0;
     bool needReference_ = false;
+    const GeometricField *old_ = nullptr; // the old-time level, when the harness provides one
+    const GeometricField &oldTime() const { return old_ ? *old_ : *this; }
     GeometricField() {}
     template <class... A> GeometricField(const IOobject &, const fvMesh &m, const A &...) : mesh_(&m), internal_(m.lduAddr().size()) {}
+    GeometricField(const IOobject &, const tmp<GeometricField> &t) : mesh_(t().mesh_), internal_(t().internal_), boundary_(t().boundary_) {}
+    GeometricField(const tmp<GeometricField> &t) : mesh_(t().mesh_), internal_(t().internal_), boundary_(t().boundary_) {}
+    static const GeometricField &null()
+    {
+        static GeometricField n;
+        return n;
+    }
     const word &name() const
     {
         static word w("psi");

@@ -635,3 +635,33 @@ def fvm_fill(which, nc, nCells, lower, upper, patches, a, b):
     if which == "div":
         out["lower"] = low[:nF]
     return out
+
+
+def euler_ddt(nCells, lower, upper, patches, deltaT, V, U0, phi0, Sf, w):
+    """EulerDdtScheme<vector>::fvmDdt(U) and ::fvcDdtPhiCorr(U, phi) (with ddtScheme::fvcDdtPhiCoeff) run from the reference's
+    sources on a field whose old-time level is U0 and a flux whose old-time level is phi0.  patches: list of dict(faceCells,
+    fixesValue (bool), value (faces, 3) = U0 on the patch, phi0 (faces), Sf (faces, 3)).  Returns dict(diag, source (n, 3),
+    ddtCorr (nF), bddtCorr (flat over the patches))."""
+    fvm("D", 1, [], [], [], [1.0], [0.0], [1.0], [], None, [0.0])   # loads the library
+    l, u = _i(lower), _i(upper)
+    n, nF = int(nCells), len(l)
+    os_, ls, lo = ldu_arrays(n, l, u)
+    ps = np.zeros(len(patches) + 1, np.int32)
+    for k, p in enumerate(patches):
+        ps[k + 1] = ps[k] + len(p["faceCells"])
+    tot = int(ps[-1])
+    cat = lambda f, w_: _d(np.concatenate([np.ravel(f(p)) for p in patches]) if patches else np.zeros(w_))
+    fc = _i(np.concatenate([p["faceCells"] for p in patches]) if patches else [0])
+    fixes = _i([1 if p["fixesValue"] else 0 for p in patches] or [0])
+    bU, bphi, bSf = cat(lambda p: p["value"], 3), cat(lambda p: p["phi0"], 1), cat(lambda p: p["Sf"], 3)
+    diag, source = np.zeros(n), np.zeros(n * 3)
+    corr, bcorr = np.zeros(max(nF, 1)), np.zeros(max(tot, 1))
+    V_, U0_, phi0_, Sf_, w_ = _d(V), _d(np.ravel(U0)), _d(phi0), _d(np.ravel(Sf)), _d(w)
+    _libfvm.ref_ddt.restype = C.c_int
+    rc = _libfvm.ref_ddt(n, nF, _p(l), _p(u), _p(_i(os_)), _p(_i(ls)), _p(_i(lo)), len(patches), _p(ps), _p(fc), _p(fixes),
+                         C.c_double(float(deltaT)), _p(V_), _p(U0_), _p(bU), _p(phi0_), _p(bphi), _p(Sf_), _p(bSf), _p(w_),
+                         _p(diag), _p(source), _p(corr), _p(bcorr))
+    if rc != 0:
+        raise RuntimeError("the reference code raised a FatalError")
+    return dict(diag=diag, source=source.reshape(n, 3), ddtCorr=corr[:nF], bddtCorr=bcorr[:tot])
+

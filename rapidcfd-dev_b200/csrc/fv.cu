@@ -4,7 +4,7 @@
 // FV/finiteVolume/fvc/fvcSurfaceIntegrate.C:41-97,138-203,264-360; gaussGrad::gradf
 // FV/finiteVolume/gradSchemes/gaussGrad/gaussGrad.C:34-139,143-242; Laplacian fill
 // gaussLaplacianScheme.C:63-64; convection fill gaussConvectionScheme.C:95-97; linear
-// interpolation surfaceInterpolationScheme.C:159-240; addBoundaryDiag/Source
+// interpolation surfaceInterpolationScheme.C:272-351; addBoundaryDiag/Source
 // FV/fvMatrices/fvMatrix/fvMatrix.C:209-226,290-312.
 //
 // One thread per cell walks the cell's owner faces (contiguous) and neighbour faces
@@ -235,6 +235,13 @@ extern "C" int b200ldu_fv_convection_fill(b200ldu_addr *a, const double *weights
     return B200LDU_OK;
 }
 
+// linear face value as interpolate(vf) forms it: w*(own - nei) + nei (surfaceInterpolationScheme.C:272-351), each operation
+// rounded on its own
+__device__ __forceinline__ double lin_face(double w, double own, double nei)
+{
+    return __dadd_rn(__dmul_rn(w, __dsub_rn(own, nei)), nei);
+}
+
 template <int NC>
 __global__ void interpolate_linear_kernel(int nFaces, const int *__restrict__ l, const int *__restrict__ u,
                                           const double *__restrict__ w, const double *__restrict__ vf,
@@ -242,12 +249,11 @@ __global__ void interpolate_linear_kernel(int nFaces, const int *__restrict__ l,
 {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nFaces) return;
-    double ww = w[f], w1 = 1 - ww;
+    double ww = w[f];
     int o = l[f], n = u[f];
 #pragma unroll
     for (int k = 0; k < NC; k++)
-        sf[(size_t)f * NC + k] =
-            __dadd_rn(__dmul_rn(ww, vf[(size_t)o * NC + k]), __dmul_rn(w1, vf[(size_t)n * NC + k]));
+        sf[(size_t)f * NC + k] = lin_face(ww, vf[(size_t)o * NC + k], vf[(size_t)n * NC + k]);
 }
 
 extern "C" int b200ldu_fv_interpolate_linear(b200ldu_addr *a, int nComp, const double *w_d,
@@ -305,8 +311,8 @@ extern "C" int b200ldu_fv_add_boundary_source(b200ldu_addr *a, const double *bou
 // surface interpolation fused into the face sums, so the
 // F-sized interpolated face field (401 MB - 1.2 GB at 256^3) is never written or re-read.
 // gaussGrad::calcGrad = gradf(interpolate(vsf)) (gaussGrad.C:256-271 with the linear scheme,
-// surfaceInterpolationScheme.C:159-240): the face value w*psi[own] + (1-w)*psi[nei] is
-// formed on the fly with the same two rounded products and one add as the unfused pipeline,
+// surfaceInterpolationScheme.C:272-351): the face value w*(psi[own] - psi[nei]) + psi[nei] is
+// formed on the fly with the same rounded subtract, product and add as the unfused pipeline,
 // so the result equals b200ldu_fv_gauss_grad(b200ldu_fv_interpolate_linear(...)) bit for bit.
 // ---------------------------------------------------------------------------
 template <int NC>
@@ -328,22 +334,22 @@ __global__ void grad_linear_kernel(int nCells, const int *__restrict__ ownerStar
     for (int k = 0; k < 3 * NC; k++) acc[k] = 0.0;
     for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++) {
         const int n = upper[f];
-        const double ww = w[f], w1 = 1 - ww;
+        const double ww = w[f];
         const double s[3] = {Sf[(size_t)f * 3], Sf[(size_t)f * 3 + 1], Sf[(size_t)f * 3 + 2]};
 #pragma unroll
         for (int j = 0; j < NC; j++) {
-            const double fv = __dadd_rn(__dmul_rn(ww, mine[j]), __dmul_rn(w1, vf[(size_t)n * NC + j]));
+            const double fv = lin_face(ww, mine[j], vf[(size_t)n * NC + j]);
 #pragma unroll
             for (int i = 0; i < 3; i++) acc[i * NC + j] = __dadd_rn(acc[i * NC + j], __dmul_rn(s[i], fv));
         }
     }
     for (int q = losortStart[c]; q < losortStart[c + 1]; q++) {
         const int f = losort[q], o = lower[f];
-        const double ww = w[f], w1 = 1 - ww;
+        const double ww = w[f];
         const double s[3] = {Sf[(size_t)f * 3], Sf[(size_t)f * 3 + 1], Sf[(size_t)f * 3 + 2]};
 #pragma unroll
         for (int j = 0; j < NC; j++) {
-            const double fv = __dadd_rn(__dmul_rn(ww, vf[(size_t)o * NC + j]), __dmul_rn(w1, mine[j]));
+            const double fv = lin_face(ww, vf[(size_t)o * NC + j], mine[j]);
 #pragma unroll
             for (int i = 0; i < 3; i++) acc[i * NC + j] = __dsub_rn(acc[i * NC + j], __dmul_rn(s[i], fv));
         }
@@ -393,12 +399,12 @@ __global__ void flux_linear_kernel(int nFaces, const int *__restrict__ l, const 
 {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nFaces) return;
-    const double ww = w[f], w1 = 1 - ww;
+    const double ww = w[f];
     const int o = l[f], n = u[f];
     double acc = 0.0;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const double fv = __dadd_rn(__dmul_rn(ww, U[(size_t)o * 3 + k]), __dmul_rn(w1, U[(size_t)n * 3 + k]));
+        const double fv = lin_face(ww, U[(size_t)o * 3 + k], U[(size_t)n * 3 + k]);
         const double p = __dmul_rn(Sf[(size_t)f * 3 + k], fv);
         acc = k == 0 ? p : __dadd_rn(acc, p);
     }

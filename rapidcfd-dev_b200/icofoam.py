@@ -71,7 +71,7 @@ class IcoFoam:
         return self.torch.from_numpy(np.array(a, dtype=np.float64).ravel()).to(self.ctx.device)
 
     def interpolate_coupled(self, vf, nc):
-        """processor faces: w*patchInternalField + (1 - w)*patchNeighbourField (surfaceInterpolationScheme.C:246-262)"""
+        """processor faces: w*patchInternalField + (1 - w)*patchNeighbourField (surfaceInterpolationScheme.C:357-370)"""
         o = self.ops
         pnf = self.capi.fv_patch_neighbour_field(self.addr, nc, vf)
         return o.add(o.mul(self.cw, o.gather(self.cfc, vf, nc), 1, nc), o.mul(o.rsub(1.0, self.cw), pnf, 1, nc), nc, nc)

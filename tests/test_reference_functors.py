@@ -870,3 +870,46 @@ def test_coefficient_fills_match_reference_schemes(meshmod, orc, nc):
             ic.append(i)
             bc.append(b)
     assert np.array_equal(got["ic"], np.concatenate(ic)) and np.array_equal(got["bc"], np.concatenate(bc))
+
+
+def test_euler_ddt_terms_match_reference_schemes(meshmod, orc):
+    """The time-derivative pieces of the PISO step (§8 f2): EulerDdtScheme<vector>::fvmDdt, ::fvcDdtPhiCorr and
+    ddtScheme::fvcDdtPhiCoeff of the reference (compiled for the host) against the expressions oracle/piso_oracle.py composes
+    (ddtDiag, ddtSource, phiCorr, coeff, ddtCorr), bit for bit.  Patches that fix the value get a zero coefficient
+    (ddtScheme.C:156-162); the others keep the face expression, which is what the oracle applies on processor faces."""
+    m = meshmod.decompose(8, 2, 0)
+    rng = np.random.default_rng(33)
+    n, nF = m.nCells, m.nFaces
+    V = rng.uniform(0.5, 1.5, n) * 1e-3
+    U0 = rng.uniform(-1, 1, (n, 3))
+    Sf = rng.uniform(-1, 1, (nF, 3)) * 1e-2
+    w = rng.uniform(0.3, 0.7, nF)
+    phi0 = rng.uniform(-1, 1, nF) * 1e-2
+    phi0[::7] = 0.0                                      # faces without flux: the SMALL in the coefficient's denominator
+    deltaT = 0.005
+    P = []
+    for k, p in enumerate(m.patches):
+        f = len(p.faceCells)
+        P.append(dict(faceCells=p.faceCells, fixesValue=(p.kind != "processor"), value=rng.uniform(-1, 1, (f, 3)),
+                      phi0=rng.uniform(-1, 1, f) * 1e-2, Sf=rng.uniform(-1, 1, (f, 3)) * 1e-2))
+    got = ref_ldu.euler_ddt(n, m.lower, m.upper, P, deltaT, V, U0, phi0, Sf, w)
+    # oracle/piso_oracle.py Cavity.step, the same statements
+    SMALL = 1e-15
+    rDeltaT = 1.0 / deltaT
+    dot = lambda a, b: (a[:, 0] * b[:, 0] + a[:, 1] * b[:, 1]) + a[:, 2] * b[:, 2]
+    assert np.array_equal(got["diag"], rDeltaT * V)
+    assert np.array_equal(got["source"], (rDeltaT * U0) * V[:, None])
+    l, u = np.asarray(m.lower), np.asarray(m.upper)
+    Uf = w[:, None] * (U0[l] - U0[u]) + U0[u]            # surfaceInterpolationScheme.C:323-326
+    phiCorr = phi0 - dot(Sf, Uf)
+    coeff = 1.0 - np.minimum(np.abs(phiCorr) / (np.abs(phi0) + SMALL), 1.0)
+    assert np.array_equal(got["ddtCorr"], (coeff * rDeltaT) * phiCorr)
+    b = []
+    for p in P:
+        if p["fixesValue"]:
+            b.append(np.zeros(len(p["faceCells"])))
+        else:
+            pc = p["phi0"] - dot(p["Sf"], p["value"])
+            cc = 1.0 - np.minimum(np.abs(pc) / (np.abs(p["phi0"]) + SMALL), 1.0)
+            b.append((cc * rDeltaT) * pc)
+    assert np.array_equal(got["bddtCorr"], np.concatenate(b))
