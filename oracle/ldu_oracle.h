@@ -27,13 +27,13 @@
  *     (lduMatrixUpdateMatrixInterfaces.C, processorFvPatchScalarField.C, processorGAMGInterfaceField.C) and the
  *     cyclic pairing (cyclicFvPatchField.C), the Laplacian / convection coefficient fills
  *     (gaussLaplacianScheme.C, gaussConvectionScheme.C), the Euler ddt statements of oracle/piso_oracle.py
- *     (EulerDdtScheme.C fvmDdt / fvcDdtPhiCorr, ddtScheme.C fvcDdtPhiCoeff);
+ *     (EulerDdtScheme.C fvmDdt / fvcDdtPhiCorr, ddtScheme.C fvcDdtPhiCoeff), the linear face interpolation
+ *     (surfaceInterpolationScheme.C interpolate(vf));
  *   PINNED to rounding level (the reference's vector updates run unfused on the host, here they are
  *     the FMAs nvcc emits): PCG, PBiCG, PBiCGStab loops incl. iteration counts, names, loop limits
  *     (run-time selection and normFactor -- lduMatrixSolver.C -- bit for bit);
  *   UNPINNED (restated from the source, checked by analytic properties only): the icoFoam
- *     step of oracle/piso_oracle.py as a whole (the order in which it combines the pinned pieces) and the linear
- *     interpolation expression (surfaceInterpolationScheme.C:272-351).  Rows with more than three faces per side (coarse GAMG levels,
+ *     step of oracle/piso_oracle.py as a whole (the order in which it combines the pinned pieces).  Rows with more than three faces per side (coarse GAMG levels,
  *     polyhedral meshes) are summed in plain row order here, the reference unrolls three per side
  *     first: same terms, different association.
  * Analytic checks (dense-matrix SpMV, adjointness, CG exactness on tiny systems, eigenpairs of the

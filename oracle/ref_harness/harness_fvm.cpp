@@ -7,6 +7,7 @@
  *   fvScalarMatrix/fvScalarMatrix.H, .C          solveSegregated, residual, H for scalars
  *   FV/finiteVolume/convectionSchemes/gaussConvectionScheme/gaussConvectionScheme.C   fvmDiv (coefficient fill + patch coefficients)
  *   FV/finiteVolume/laplacianSchemes/gaussLaplacianScheme/gaussLaplacianScheme.C      fvmLaplacianUncorrected
+ *   FV/interpolation/surfaceInterpolation/surfaceInterpolationScheme/surfaceInterpolationScheme.C  interpolate(vf)
  *   FV/finiteVolume/ddtSchemes/ddtScheme/ddtScheme.C, EulerDdtScheme/EulerDdtScheme.C  fvmDdt, fvcDdtPhiCorr, fvcDdtPhiCoeff
  * against oracle/ref_harness/shim_fvm/.  The linear solver behind solveSegregated is a recorder: it keeps the diagonal and
  * the source it is handed, which is what the folding has to get right.
@@ -23,6 +24,8 @@
 #include "gaussConvectionScheme.C" /* reference: fvmDiv :76-115 */
 #include "gaussLaplacianScheme.C"  /* reference: fvmLaplacianUncorrected :46-89 */
 #include "ddt_shim.h"
+namespace Foam { int surfaceInterpolation::debug = 0; }
+#include "surfaceInterpolationScheme.C" /* reference: interpolate(vf) :376-400 -> interpolate(vf, weights) :272-373 */
 #include "ddtScheme.C"      /* reference: fvcDdtPhiCoeff :139-174 */
 #include "EulerDdtScheme.C" /* reference: fvmDdt :331-361, fvcDdtPhiCorr :523-551 */
 
@@ -117,6 +120,34 @@ void put(const gpuField<vector> &f, double *out)
 }
 } // namespace
 
+/* surfaceInterpolationScheme<Type>::interpolate(vf) with the linear weights w (internal faces) / pw (patch faces): nc = 1 or 3;
+ * patch values bvf, patchNeighbourField pnf (read on coupled patches) -> out [nF*nc], bout [tot*nc] */
+template <class Type>
+static int run_interpolate(int n, int nF, const int *l, const int *u, const int *ownerStart, const int *losortStart, const int *losort,
+                           int nP, const int *patchStart, const int *faceCells, const int *coupled, const double *w, const double *pw,
+                           const double *vf, const double *bvf, const double *pnf, double *out, double *bout)
+{
+    const int nc = sizeof(Type) / sizeof(double);
+    const int tot = nP ? patchStart[nP] : 0;
+    std::vector<double> zerosN((size_t)n * nc + 3, 0.0), zerosF((size_t)nF + 1, 0.0), zerosP((size_t)tot * nc + 3, 0.0), ones((size_t)n + 1, 1.0);
+    Case<Type> C(n, nF, l, u, ownerStart, losortStart, losort, nP, patchStart, faceCells, coupled, pnf, ones.data(), vf, zerosN.data(),
+                 zerosF.data(), nullptr, zerosN.data(), zerosP.data(), zerosP.data());
+    for (int p = 0; p < nP; p++)
+        static_cast<gpuField<Type> &>(C.psi.boundary_.p_[(size_t)p]) = tmp<gpuField<Type>>(
+            new gpuField<Type>(reinterpret_cast<const Type *>(bvf + (size_t)patchStart[p] * nc), patchStart[p + 1] - patchStart[p]));
+    surfaceScalarField weights;
+    weights.mesh_ = &C.mesh;
+    weights.internal_ = scalargpuField(w, nF);
+    weights.boundary_.p_.resize((size_t)nP);
+    for (int p = 0; p < nP; p++)
+        static_cast<scalargpuField &>(weights.boundary_.p_[(size_t)p]) =
+            tmp<scalargpuField>(new scalargpuField(pw + patchStart[p], patchStart[p + 1] - patchStart[p]));
+    C.mesh.weights_ = &weights;
+    tmp<GeometricField<Type, fvsPatchField, surfaceMesh>> t = surfaceInterpolationScheme<Type>(C.mesh).interpolate(C.psi);
+    put(t().internal_, out);
+    for (int p = 0; p < nP; p++) put(t().boundary_.p_[(size_t)p], bout + (size_t)patchStart[p] * nc);
+    return 0;
+}
 extern "C" {
 /* op: 0 addBoundaryDiag(x, 0) on x = in1 | 1 addCmptAvBoundaryDiag | 2 addBoundarySource(x, couples = iarg) | 3 setReference(cell
  * iarg, value darg, forced) -> out1 diag, out2 source | 4 relax(darg) -> out1 diag, out2 source | 5 D | 6 A | 7 flux -> out1
@@ -348,6 +379,20 @@ int ref_ddt(int n, int nF, const int *l, const int *u, const int *ownerStart, co
         put(tc().internal_, ddtCorr);
         for (int p = 0; p < nP; p++) put(tc().boundary_.p_[(size_t)p], bddtCorr + patchStart[p]);
         return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+
+int ref_interpolate(int nc, int n, int nF, const int *l, const int *u, const int *ownerStart, const int *losortStart, const int *losort,
+                    int nP, const int *patchStart, const int *faceCells, const int *coupled, const double *w, const double *pw,
+                    const double *vf, const double *bvf, const double *pnf, double *out, double *bout)
+{
+    try {
+        return nc == 1 ? run_interpolate<scalar>(n, nF, l, u, ownerStart, losortStart, losort, nP, patchStart, faceCells, coupled, w, pw,
+                                                 vf, bvf, pnf, out, bout)
+                       : run_interpolate<vector>(n, nF, l, u, ownerStart, losortStart, losort, nP, patchStart, faceCells, coupled, w, pw,
+                                                 vf, bvf, pnf, out, bout);
     } catch (const std::exception &) {
         return -1;
     }

@@ -119,29 +119,12 @@ inline tmp<gpuField<vector>> operator*(const tmp<gpuField<vector>> &a, const sca
 
 namespace fvc
 {
-// fvc::interpolate with the linear scheme, the shim's stand-in (surfaceInterpolationScheme.C:272-373, the one-weight form
-// interpolate(vf) reaches): lambda*(vf[P] - vf[N]) + vf[N] on the internal faces, the patch value on non-coupled patches;
-// weights from the mesh
+// fvc::interpolate with the linear scheme (surfaceInterpolate.C:300-316 -> scheme(mesh, name)().interpolate(vf)): the
+// reference's surfaceInterpolationScheme<Type>::interpolate(vf) with the mesh's linear weights
 template <class Type>
 tmp<GeometricField<Type, fvsPatchField, surfaceMesh>> interpolate(const GeometricField<Type, fvPatchField, volMesh> &vf)
 {
-    const fvMesh &mesh = vf.mesh();
-    const surfaceScalarField &w = mesh.weights();
-    GeometricField<Type, fvsPatchField, surfaceMesh> *r = new GeometricField<Type, fvsPatchField, surfaceMesh>;
-    r->mesh_ = &mesh;
-    const label nF = mesh.owner().size();
-    r->internal_.setSize(nF);
-    for (label f = 0; f < nF; f++) {
-        const scalar l = w.internal_.data()[f];
-        const Type &own = vf.internal_.data()[mesh.owner().data()[f]], &nei = vf.internal_.data()[mesh.neighbour().data()[f]];
-        r->internal_.data()[f] = l * (own - nei) + nei;
-    }
-    r->boundary_.p_.resize(vf.boundary_.p_.size());
-    for (size_t p = 0; p < vf.boundary_.p_.size(); p++) {
-        r->boundary_.p_[p].setSize(vf.boundary_.p_[p].size());
-        for (label i = 0; i < vf.boundary_.p_[p].size(); i++) r->boundary_.p_[p].data()[i] = vf.boundary_.p_[p].data()[i];
-    }
-    return tmp<GeometricField<Type, fvsPatchField, surfaceMesh>>(r);
+    return surfaceInterpolationScheme<Type>(vf.mesh()).interpolate(vf);
 }
 } // namespace fvc
 

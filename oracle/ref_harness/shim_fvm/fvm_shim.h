@@ -503,7 +503,14 @@ public:
     const GeometricField *old_ = nullptr; // the old-time level, when the harness provides one
     const GeometricField &oldTime() const { return old_ ? *old_ : *this; }
     GeometricField() {}
-    template <class... A> GeometricField(const IOobject &, const fvMesh &m, const A &...) : mesh_(&m), internal_(m.lduAddr().size()) {}
+    template <class... A> GeometricField(const IOobject &, const fvMesh &m, const A &...) : mesh_(&m), internal_(m.lduAddr().size())
+    {
+        if constexpr (std::is_same<GeoMesh, surfaceMesh>::value) { // a face field: internal faces + one entry per patch
+            internal_.setSize(m.nInternalFaces());
+            boundary_.p_.resize((size_t)m.boundary().size());
+        }
+    }
+    word type() const { return word("field"); }
     GeometricField(const IOobject &, const tmp<GeometricField> &t) : mesh_(t().mesh_), internal_(t().internal_), boundary_(t().boundary_) {}
     GeometricField(const tmp<GeometricField> &t) : mesh_(t().mesh_), internal_(t().internal_), boundary_(t().boundary_) {}
     static const GeometricField &null()

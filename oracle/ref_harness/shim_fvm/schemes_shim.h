@@ -24,22 +24,80 @@ tmp<GeometricField<T, fvsPatchField, surfaceMesh>> operator*(const surfaceScalar
 {
     throw std::runtime_error("not used"); // faceFlux*correction(vf): only on the corrected() branch
 }
+// patch-field algebra of the coupled branch of surfaceInterpolationScheme.C:357-370 (one rounded operation per element)
+inline tmp<scalargpuField> operator-(scalar s, const scalargpuField &b)
+{
+    scalargpuField *r = new scalargpuField(b.size());
+    for (label i = 0; i < b.size(); i++) r->data()[i] = s - b.data()[i];
+    return tmp<scalargpuField>(r);
+}
+inline tmp<gpuField<vector>> operator*(const scalargpuField &a, const tmp<gpuField<vector>> &b)
+{
+    gpuField<vector> *r = new gpuField<vector>(a.size());
+    for (label i = 0; i < a.size(); i++) r->data()[i] = a.data()[i] * b().data()[i];
+    return tmp<gpuField<vector>>(r);
+}
+inline tmp<gpuField<vector>> operator*(const tmp<scalargpuField> &a, const tmp<gpuField<vector>> &b) { return a() * b; }
+inline tmp<gpuField<vector>> operator+(const tmp<gpuField<vector>> &a, const tmp<gpuField<vector>> &b)
+{
+    gpuField<vector> *r = new gpuField<vector>(a().size());
+    for (label i = 0; i < a().size(); i++) r->data()[i] = a().data()[i] + b().data()[i];
+    return tmp<gpuField<vector>>(r);
+}
+// Declaration for the reference's surfaceInterpolationScheme.C (FV/interpolation/surfaceInterpolation/
+// surfaceInterpolationScheme/surfaceInterpolationScheme.H:56-260, the members its .C file defines); not virtual here, so only
+// the members the harness calls are instantiated.  weights(vf): the field given at construction, else the mesh's linear
+// weights (linear.H:88-97).
+struct surfaceInterpolation {
+    static int debug;
+};
 template <class Type> class surfaceInterpolationScheme : public refCount
 {
-    const surfaceScalarField *w_;
+    const fvMesh *mesh_ = nullptr;
+    const surfaceScalarField *w_ = nullptr;
 
 public:
+    struct ConstructorTableStub {
+        struct iterator {
+            bool operator==(const iterator &) const { return true; }
+            struct Maker {
+                template <class... A> tmp<surfaceInterpolationScheme<Type>> operator()(const A &...) const
+                {
+                    throw std::runtime_error("no run-time selection in the harness");
+                }
+            };
+            Maker operator()() const { return Maker(); }
+        };
+        iterator find(const word &) { return iterator(); }
+        iterator end() { return iterator(); }
+        word sortedToc() const { return word(); }
+    };
+    typedef ConstructorTableStub MeshConstructorTable;
+    typedef ConstructorTableStub MeshFluxConstructorTable;
+    static MeshConstructorTable *MeshConstructorTablePtr_;
+    static MeshFluxConstructorTable *MeshFluxConstructorTablePtr_;
+    surfaceInterpolationScheme(const fvMesh &mesh) : mesh_(&mesh) {}
     surfaceInterpolationScheme(const surfaceScalarField &w) : w_(&w) {}
-    tmp<surfaceScalarField> weights(const GeometricField<Type, fvPatchField, volMesh> &) const { return tmp<surfaceScalarField>(*w_); }
-    bool corrected() const { return false; }
-    template <class F> tmp<GeometricField<Type, fvsPatchField, surfaceMesh>> interpolate(const F &) const
+    static tmp<surfaceInterpolationScheme<Type>> New(const fvMesh &mesh, Istream &schemeData);
+    static tmp<surfaceInterpolationScheme<Type>> New(const fvMesh &mesh, const surfaceScalarField &faceFlux, Istream &schemeData);
+    ~surfaceInterpolationScheme();
+    const fvMesh &mesh() const { return *mesh_; }
+    tmp<surfaceScalarField> weights(const GeometricField<Type, fvPatchField, volMesh> &) const
     {
-        throw std::runtime_error("not used by the harness");
+        return tmp<surfaceScalarField>(new surfaceScalarField(w_ ? *w_ : mesh_->weights()));
     }
+    bool corrected() const { return false; }
     template <class F> tmp<GeometricField<Type, fvsPatchField, surfaceMesh>> correction(const F &) const
     {
         throw std::runtime_error("not used by the harness");
     }
+    static tmp<GeometricField<Type, fvsPatchField, surfaceMesh>> interpolate(const GeometricField<Type, fvPatchField, volMesh> &,
+                                                                             const tmp<surfaceScalarField> &,
+                                                                             const tmp<surfaceScalarField> &);
+    static tmp<GeometricField<Type, fvsPatchField, surfaceMesh>> interpolate(const GeometricField<Type, fvPatchField, volMesh> &,
+                                                                             const tmp<surfaceScalarField> &);
+    tmp<GeometricField<Type, fvsPatchField, surfaceMesh>> interpolate(const GeometricField<Type, fvPatchField, volMesh> &) const;
+    tmp<GeometricField<Type, fvsPatchField, surfaceMesh>> interpolate(const tmp<GeometricField<Type, fvPatchField, volMesh>> &) const;
 };
 template <class Type> class snGradScheme : public refCount
 {

@@ -665,3 +665,30 @@ def euler_ddt(nCells, lower, upper, patches, deltaT, V, U0, phi0, Sf, w):
         raise RuntimeError("the reference code raised a FatalError")
     return dict(diag=diag, source=source.reshape(n, 3), ddtCorr=corr[:nF], bddtCorr=bcorr[:tot])
 
+
+def interpolate_linear(nc, nCells, lower, upper, patches, w, vf):
+    """surfaceInterpolationScheme<Type>::interpolate(vf) of the reference with linear weights w.  patches: list of
+    dict(faceCells, coupled (bool), w (faces), value (faces, nc) = the patch field, pnf (faces, nc) = patchNeighbourField of a
+    coupled patch).  Returns (internal face values (nF[, nc]), patch face values flat over the patches (tot[, nc]))."""
+    fvm("D", 1, [], [], [], [1.0], [0.0], [1.0], [], None, [0.0])   # loads the library
+    l, u = _i(lower), _i(upper)
+    n, nF = int(nCells), len(l)
+    os_, ls, lo = ldu_arrays(n, l, u)
+    ps = np.zeros(len(patches) + 1, np.int32)
+    for k, p in enumerate(patches):
+        ps[k + 1] = ps[k] + len(p["faceCells"])
+    tot = int(ps[-1])
+    cat = lambda f: _d(np.concatenate([np.ravel(f(p)) for p in patches]) if patches else np.zeros(nc))
+    fc = _i(np.concatenate([p["faceCells"] for p in patches]) if patches else [0])
+    cpl = _i([1 if p["coupled"] else 0 for p in patches] or [0])
+    zero = lambda p: np.zeros((len(p["faceCells"]), nc))
+    pw, bvf, pnf = cat(lambda p: p["w"]), cat(lambda p: p.get("value", zero(p))), cat(lambda p: p.get("pnf", zero(p)))
+    out, bout = np.zeros(max(nF * nc, 1)), np.zeros(max(tot * nc, 1))
+    _libfvm.ref_interpolate.restype = C.c_int
+    rc = _libfvm.ref_interpolate(int(nc), n, nF, _p(l), _p(u), _p(_i(os_)), _p(_i(ls)), _p(_i(lo)), len(patches), _p(ps), _p(fc),
+                                 _p(cpl), _p(_d(w)), _p(pw), _p(_d(np.ravel(vf))), _p(bvf), _p(pnf), _p(out), _p(bout))
+    if rc != 0:
+        raise RuntimeError("the reference code raised a FatalError")
+    shape = (lambda k: (k,)) if nc == 1 else (lambda k: (k, nc))
+    return out[:nF * nc].reshape(shape(nF)), bout[:tot * nc].reshape(shape(tot))
+
