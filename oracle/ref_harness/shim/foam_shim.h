@@ -92,6 +92,18 @@ public:
     {
         for (label i = 0; i < n_; i++) p_[i] += o.p_[i];
     }
+    void operator*=(const gpuList &o)
+    {
+        for (label i = 0; i < n_; i++) p_[i] *= o.p_[i];
+    }
+    void operator*=(const T &s)
+    {
+        for (label i = 0; i < n_; i++) p_[i] *= s;
+    }
+    void negate()
+    {
+        for (label i = 0; i < n_; i++) p_[i] = -p_[i];
+    }
     T *data() { return p_; }
     const T *data() const { return p_; }
     iterator begin() { return p_; }
@@ -290,6 +302,32 @@ public:
     const scalargpuField &upperSort() const { return *upperSortPtr_; }
     bool coarsestLevel() const { return coarsest_; }
     int level() const { return level_; }
+#ifdef SHIM_REFERENCE_MATRIX_OPERATIONS
+    // defined by the reference (lduMatrixOperations.C:36-470)
+    void sumDiag();
+    void negSumDiag();
+    void sumMagOffDiag(scalargpuField &) const;
+    void operator=(const lduMatrix &);
+    void negate();
+    void operator+=(const lduMatrix &);
+    void operator-=(const lduMatrix &);
+    void operator*=(const scalargpuField &);
+    void operator*=(scalar);
+    // the allocate-on-demand accessors those operators rely on (lduMatrix.C:219-270): a missing triangle starts as a copy of
+    // the other one, else as zeros; the harness owns (and leaks, per call) what they allocate
+    scalargpuField &lower()
+    {
+        if (!lowerPtr_) lowerPtr_ = upperPtr_ ? new scalargpuField(*upperPtr_) : new scalargpuField(lduAddr().lowerAddr().size(), 0.0);
+        lowerSortPtr_ = NULL;
+        return *lowerPtr_;
+    }
+    scalargpuField &upper()
+    {
+        if (!upperPtr_) upperPtr_ = lowerPtr_ ? new scalargpuField(*lowerPtr_) : new scalargpuField(lduAddr().lowerAddr().size(), 0.0);
+        upperSortPtr_ = NULL;
+        return *upperPtr_;
+    }
+#endif
 #ifdef SHIM_REFERENCE_MATRIX_INTERFACES
     // defined by the reference (lduMatrixUpdateMatrixInterfaces.C:30-276)
     void initMatrixInterfaces(const FieldField<gpuField, scalar> &, const lduInterfaceFieldPtrsList &,
@@ -342,7 +380,11 @@ public:
     template <class Type> void faceH(gpuField<Type> &, const gpuField<Type> &) const;
     template <class Type> tmp<gpuField<Type>> faceH(const gpuField<Type> &) const;
     template <class Type> tmp<gpuField<Type>> faceH(const tmp<gpuField<Type>> &) const;
-    scalargpuField &diag() { return *diagPtr_; }
+    scalargpuField &diag() // lduMatrix.C:237-245
+    {
+        if (!diagPtr_) diagPtr_ = new scalargpuField(lduAddr().size(), 0.0);
+        return *diagPtr_;
+    }
 };
 
 template <class T> struct pTraits;

@@ -692,3 +692,43 @@ def interpolate_linear(nc, nCells, lower, upper, patches, w, vf):
     shape = (lambda k: (k,)) if nc == 1 else (lambda k: (k, nc))
     return out[:nF * nc].reshape(shape(nF)), bout[:tot * nc].reshape(shape(tot))
 
+
+_LIB_LDUOPS = os.path.join(_HERE, "_ref", "libref_lduops.so")
+_liblduops = None
+
+
+def ldu_combine(nCells, lower, upper, A, op1, B, op2=0, Cm=None):
+    """lduMatrix::operator+= / operator-= of the reference (lduMatrixOperations.C:235-397): A (op1) B (op2) Cm with op = +1 / -1;
+    each matrix a dict with any of diag, upper, lower (absent = the reference matrix has no such array).  Returns the dict of the
+    arrays the result holds."""
+    global _liblduops
+    if _liblduops is None:
+        if not os.path.exists(_LIB_LDUOPS):
+            raise RuntimeError("oracle/_ref/libref_lduops.so is missing: run `make -C oracle ref` where /root/reference exists")
+        _liblduops = C.CDLL(_LIB_LDUOPS)
+        _liblduops.ref_ldu_combine.restype = C.c_int
+    l, u = _i(lower), _i(upper)
+    n, nF = int(nCells), len(l)
+    keep = []
+
+    def arr(m, k):
+        if m is None or m.get(k) is None:
+            return None
+        keep.append(_d(m[k]))
+        return _p(keep[-1])
+    Cm = Cm or {}
+    dO, uO, lO, has = np.zeros(n), np.zeros(max(nF, 1)), np.zeros(max(nF, 1)), np.zeros(3, np.int32)
+    rc = _liblduops.ref_ldu_combine(n, nF, _p(l), _p(u), arr(A, "diag"), arr(A, "upper"), arr(A, "lower"), int(op1), arr(B, "diag"),
+                                    arr(B, "upper"), arr(B, "lower"), int(op2), arr(Cm, "diag"), arr(Cm, "upper"), arr(Cm, "lower"),
+                                    _p(dO), _p(uO), _p(lO), _p(has))
+    if rc != 0:
+        raise RuntimeError("the reference code raised a FatalError")
+    out = {}
+    if has[0]:
+        out["diag"] = dO
+    if has[1]:
+        out["upper"] = uO[:nF]
+    if has[2]:
+        out["lower"] = lO[:nF]
+    return out
+

@@ -945,3 +945,32 @@ def test_linear_interpolation_matches_reference_scheme(meshmod, orc, nc):
     # the two-weight form differs in the last bit on some faces: the distinction is observable
     two = (w if nc == 1 else w[:, None]) * vf[np.asarray(m.lower)] + (1 - (w if nc == 1 else w[:, None])) * vf[np.asarray(m.upper)]
     assert not np.array_equal(two, got) and np.allclose(two, got, rtol=1e-13, atol=1e-15)
+
+
+def test_matrix_algebra_matches_reference_operators(meshmod, orc):
+    """The combination that forms icoFoam's momentum matrix (fvm::ddt + fvm::div - fvm::laplacian): the reference's
+    lduMatrix::operator+= / operator-= (lduMatrixOperations.C, compiled for the host) against the assembly statements of
+    oracle/piso_oracle.py -- a diagonal matrix += an asymmetric one takes its triangles, -= a symmetric one subtracts its
+    upper from both triangles -- and the pressure matrix (symmetric only), bit for bit."""
+    m = meshmod.hex_mesh(6, 5, 4)
+    a = orc.Addr(m.nCells, m.lower, m.upper)
+    rng = np.random.default_rng(77)
+    V = rng.uniform(0.5, 1.5, m.nCells) * 1e-3
+    ddtDiag = (1.0 / 0.005) * V
+    cLower, cUpper, cDiag = orc.convection_fill(a, rng.uniform(0.3, 0.7, m.nFaces), rng.uniform(-1, 1, m.nFaces) * 1e-2)
+    lUpper, lDiag = orc.laplacian_fill(a, rng.uniform(5, 9, m.nFaces), rng.uniform(0.5, 1.5, m.nFaces) * 1e-3)
+    got = ref_ldu.ldu_combine(m.nCells, m.lower, m.upper, dict(diag=ddtDiag), +1, dict(diag=cDiag, upper=cUpper, lower=cLower), -1,
+                              dict(diag=lDiag, upper=lUpper))
+    # oracle/piso_oracle.py Cavity.step: diag = (ddtDiag + cDiag) - lDiag; upper = cUpper - lUpper; lower = cLower - lUpper
+    assert sorted(got) == ["diag", "lower", "upper"]
+    assert np.array_equal(got["diag"], (ddtDiag + cDiag) - lDiag)
+    assert np.array_equal(got["upper"], cUpper - lUpper)
+    assert np.array_equal(got["lower"], cLower - lUpper)
+    # symmetric with symmetric stays symmetric (the pressure equation's single laplacian; also a sum of two)
+    got = ref_ldu.ldu_combine(m.nCells, m.lower, m.upper, dict(diag=lDiag, upper=lUpper), +1, dict(diag=lDiag * 0.5, upper=lUpper * 0.5))
+    assert sorted(got) == ["diag", "upper"]
+    assert np.array_equal(got["diag"], lDiag + lDiag * 0.5) and np.array_equal(got["upper"], lUpper + lUpper * 0.5)
+    # symmetric -= asymmetric: the missing lower starts as a copy of the upper (lduMatrix.C:219-235)
+    got = ref_ldu.ldu_combine(m.nCells, m.lower, m.upper, dict(diag=lDiag, upper=lUpper), -1, dict(diag=cDiag, upper=cUpper, lower=cLower))
+    assert np.array_equal(got["upper"], lUpper - cUpper) and np.array_equal(got["lower"], lUpper - cLower)
+    assert np.array_equal(got["diag"], lDiag - cDiag)
