@@ -29,7 +29,7 @@
  *     (gaussLaplacianScheme.C, gaussConvectionScheme.C), the Euler ddt statements of oracle/piso_oracle.py
  *     (EulerDdtScheme.C fvmDdt / fvcDdtPhiCorr, ddtScheme.C fvcDdtPhiCoeff), the linear face interpolation
  *     (surfaceInterpolationScheme.C interpolate(vf)), the matrix sums that form the momentum matrix
- *     (lduMatrixOperations.C operator+= / operator-=);
+ *     (lduMatrixOperations.C operator+= / operator-=; fvMatrix.C operator+ / - / ==);
  *   PINNED to rounding level (the reference's vector updates run unfused on the host, here they are
  *     the FMAs nvcc emits): PCG, PBiCG, PBiCGStab loops incl. iteration counts, names, loop limits
  *     (run-time selection and normFactor -- lduMatrixSolver.C -- bit for bit);

@@ -397,4 +397,56 @@ int ref_interpolate(int nc, int n, int nF, const int *l, const int *u, const int
         return -1;
     }
 }
+
+/* UEqn = (A + B - C) == su with the reference's fvMatrix operators (fvMatrix.C operator+ :1839, operator- :1990, operator==
+ * :2252-2276, operator+= / -= :1750-1815) on three vector matrices over the same field: A diagonal (diag, source), B asymmetric
+ * (diag, upper, lower, ic, bc), C symmetric (diag, upper, ic, bc); su [n*3].  Outputs: the coefficient arrays of the result. */
+int ref_fvm_assemble(int n, int nF, const int *l, const int *u, const int *ownerStart, const int *losortStart, const int *losort, int nP,
+                     const int *patchStart, const int *faceCells, const double *V, const double *aDiag, const double *aSource,
+                     const double *bDiag, const double *bUpper, const double *bLower, const double *bIc, const double *bBc,
+                     const double *cDiag, const double *cUpper, const double *cIc, const double *cBc, const double *su, double *diag,
+                     double *upper, double *lower, double *source, double *ic, double *bc)
+{
+    try {
+        const int tot = nP ? patchStart[nP] : 0;
+        std::vector<int> coupled((size_t)std::max(nP, 1), 0);
+        std::vector<double> zN((size_t)n * 3 + 3, 0.0), zF((size_t)nF + 1, 0.0), zP((size_t)tot * 3 + 3, 0.0);
+        Case<vector> C(n, nF, l, u, ownerStart, losortStart, losort, nP, patchStart, faceCells, coupled.data(), zP.data(), V, zN.data(),
+                       zN.data(), zF.data(), nullptr, zN.data(), zP.data(), zP.data());
+        auto fld = [](const double *p, label k) { return tmp<gpuField<vector>>(new gpuField<vector>(reinterpret_cast<const vector *>(p), k)); };
+        auto make = [&](const double *d, const double *up, const double *lo, const double *src, const double *i, const double *b) {
+            tmp<fvMatrix<vector>> t(new fvMatrix<vector>(C.psi, dimensionSet()));
+            fvMatrix<vector> &M = t();
+            M.diag() = tmp<scalargpuField>(new scalargpuField(d, n));
+            if (up) M.upper() = tmp<scalargpuField>(new scalargpuField(up, nF));
+            if (lo) M.lower() = tmp<scalargpuField>(new scalargpuField(lo, nF));
+            M.source() = fld(src ? src : zN.data(), n);
+            for (int p = 0; p < nP; p++) {
+                const int s = patchStart[p], np = patchStart[p + 1] - s;
+                M.internalCoeffs()[p] = fld((i ? i : zP.data()) + (size_t)s * 3, np);
+                M.boundaryCoeffs()[p] = fld((b ? b : zP.data()) + (size_t)s * 3, np);
+            }
+            return t;
+        };
+        tmp<fvMatrix<vector>> tA = make(aDiag, nullptr, nullptr, aSource, nullptr, nullptr);
+        tmp<fvMatrix<vector>> tB = make(bDiag, bUpper, bLower, nullptr, bIc, bBc);
+        tmp<fvMatrix<vector>> tC = make(cDiag, cUpper, nullptr, nullptr, cIc, cBc);
+        DimensionedField<vector, volMesh> suF;
+        suF.f_ = gpuField<vector>(reinterpret_cast<const vector *>(su), n);
+        suF.mesh_ = &C.mesh;
+        tmp<fvMatrix<vector>> tR = ((tA + tB) - tC) == suF;
+        fvMatrix<vector> &R = tR();
+        put(R.diag(), diag);
+        put(R.upper(), upper);
+        put(static_cast<const lduMatrix &>(R).lower(), lower);
+        put(R.source(), source);
+        for (int p = 0; p < nP; p++) {
+            put(R.internalCoeffs()[p], ic + (size_t)patchStart[p] * 3);
+            put(R.boundaryCoeffs()[p], bc + (size_t)patchStart[p] * 3);
+        }
+        return R.asymmetric() ? 2 : (R.symmetric() ? 1 : 0);
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
 }

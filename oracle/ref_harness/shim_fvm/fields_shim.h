@@ -287,6 +287,12 @@ inline tmp<gpuField<vector>> operator*(const tmp<scalargpuField> &a, const gpuFi
     for (label i = 0; i < b.size(); i++) r->data()[i] = a().data()[i] * b.data()[i];
     return tmp<gpuField<vector>>(r);
 }
+inline tmp<gpuField<vector>> operator*(const scalargpuField &a, const gpuField<vector> &b) // V*su of fvMatrix.C operator==
+{
+    gpuField<vector> *r = new gpuField<vector>(b.size());
+    for (label i = 0; i < b.size(); i++) r->data()[i] = a.data()[i] * b.data()[i];
+    return tmp<gpuField<vector>>(r);
+}
 inline tmp<scalargpuField> cmptAv(const gpuField<vector> &f)
 {
     scalargpuField *r = new scalargpuField(f.size());

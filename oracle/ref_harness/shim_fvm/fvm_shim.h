@@ -178,8 +178,41 @@ public:
         upper_.negate();
         lower_.negate();
     }
-    void operator+=(const lduMatrix &) { throw std::runtime_error("not used by the harness"); }
-    void operator-=(const lduMatrix &) { throw std::runtime_error("not used by the harness"); }
+    // lduMatrixOperations.C:235-397, the kind analysis restated for this shim's storage (the reference's own operators are
+    // pinned through libref_lduops; here they only carry fvMatrix::operator+= / -= of fvMatrix.C)
+    void combine(const lduMatrix &A, const int sgn)
+    {
+        auto acc = [sgn](scalargpuField &t, const scalargpuField &a) {
+            for (label i = 0; i < t.size(); i++) t.data()[i] = sgn > 0 ? t.data()[i] + a.data()[i] : t.data()[i] - a.data()[i];
+        };
+        auto take = [sgn](scalargpuField &t, const scalargpuField &a) {
+            t = tmp<scalargpuField>(new scalargpuField(a.data(), a.size()));
+            if (sgn < 0) t.negate();
+        };
+        if (A.hasDiag()) acc(diag_, A.diag_);
+        if (symmetric() && A.symmetric())
+            acc(upper_, A.upper_);
+        else if (symmetric() && A.asymmetric()) {
+            lower_ = tmp<scalargpuField>(new scalargpuField(upper_.data(), upper_.size()));
+            hasLower_ = true;
+            acc(upper_, A.upper_);
+            acc(lower_, A.lower_);
+        } else if (asymmetric() && A.symmetric()) {
+            acc(lower_, A.upper_);
+            acc(upper_, A.upper_);
+        } else if (asymmetric() && A.asymmetric()) {
+            acc(lower_, A.lower_);
+            acc(upper_, A.upper_);
+        } else if (diagonal()) {
+            if (A.hasUpper()) take(upper_, A.upper_);
+            if (A.hasLower_) {
+                take(lower_, A.lower_);
+                hasLower_ = true;
+            }
+        }
+    }
+    void operator+=(const lduMatrix &A) { combine(A, +1); }
+    void operator-=(const lduMatrix &A) { combine(A, -1); }
     void operator*=(const scalargpuField &) { throw std::runtime_error("not used by the harness"); }
     void operator*=(scalar) { throw std::runtime_error("not used by the harness"); }
     // lduMatrixOperations.C:82-104 in the order its functors run (owner side: |upper|, neighbour side: |lower|)
@@ -540,6 +573,8 @@ public:
     word select(bool) const { return name(); }
     template <class F> void replace(direction, const F &) {}
     void operator+=(const GeometricField &) {}
+    void operator-=(const GeometricField &) {}   // face-flux corrections: never present in the harness
+    tmp<GeometricField> operator-() const { throw std::runtime_error("not used by the harness"); }
     void rename(const word &) {}
 };
 template <class Type, class GeoMesh> class DimensionedField
@@ -548,9 +583,12 @@ public:
     gpuField<Type> f_;
     const gpuField<Type> &field() const { return f_; }
     const gpuField<Type> &getField() const { return f_; }
+    const fvMesh *mesh_ = nullptr;
+    word name() const { return word("su"); }
     const fvMesh &mesh() const
     {
-        throw std::runtime_error("not used by the harness");
+        if (!mesh_) throw std::runtime_error("not used by the harness");
+        return *mesh_;
     }
     dimensionSet dimensions() const { return dimensionSet(); }
 };

@@ -732,3 +732,31 @@ def ldu_combine(nCells, lower, upper, A, op1, B, op2=0, Cm=None):
         out["lower"] = lO[:nF]
     return out
 
+
+def fvm_assemble(nCells, lower, upper, patches, V, A, B, Cm, su):
+    """((A + B) - Cm) == su through the reference's fvMatrix operators (fvMatrix.C operator+ / operator- / operator== and
+    operator+= / -=) for vector matrices over one field: A = dict(diag, source (n, 3)) diagonal, B = dict(diag, upper, lower, ic,
+    bc) asymmetric, Cm = dict(diag, upper, ic, bc) symmetric; ic / bc flat over the patches (tot, 3); patches: list of face-cell
+    arrays.  Returns dict(diag, upper, lower, source, ic, bc, kind)."""
+    fvm("D", 1, [], [], [], [1.0], [0.0], [1.0], [], None, [0.0])   # loads the library
+    l, u = _i(lower), _i(upper)
+    n, nF = int(nCells), len(l)
+    os_, ls, lo = ldu_arrays(n, l, u)
+    ps = np.zeros(len(patches) + 1, np.int32)
+    for k, fcs in enumerate(patches):
+        ps[k + 1] = ps[k] + len(fcs)
+    tot = int(ps[-1])
+    fc = _i(np.concatenate(patches) if patches else [0])
+    flat = lambda x: _d(np.ravel(x))
+    keep = [flat(A["diag"]), flat(A["source"]), flat(B["diag"]), flat(B["upper"]), flat(B["lower"]), flat(B["ic"]), flat(B["bc"]),
+            flat(Cm["diag"]), flat(Cm["upper"]), flat(Cm["ic"]), flat(Cm["bc"]), flat(su)]
+    dg, up, low = np.zeros(n), np.zeros(max(nF, 1)), np.zeros(max(nF, 1))
+    src, ic, bc = np.zeros(n * 3), np.zeros(max(tot * 3, 1)), np.zeros(max(tot * 3, 1))
+    _libfvm.ref_fvm_assemble.restype = C.c_int
+    rc = _libfvm.ref_fvm_assemble(n, nF, _p(l), _p(u), _p(_i(os_)), _p(_i(ls)), _p(_i(lo)), len(patches), _p(ps), _p(fc), _p(_d(V)),
+                                  *[_p(k) for k in keep], _p(dg), _p(up), _p(low), _p(src), _p(ic), _p(bc))
+    if rc < 0:
+        raise RuntimeError("the reference code raised a FatalError")
+    return dict(diag=dg, upper=up[:nF], lower=low[:nF], source=src.reshape(n, 3), ic=ic[:tot * 3].reshape(tot, 3),
+                bc=bc[:tot * 3].reshape(tot, 3), kind={0: "diagonal", 1: "symmetric", 2: "asymmetric"}[rc])
+

@@ -974,3 +974,30 @@ def test_matrix_algebra_matches_reference_operators(meshmod, orc):
     got = ref_ldu.ldu_combine(m.nCells, m.lower, m.upper, dict(diag=lDiag, upper=lUpper), -1, dict(diag=cDiag, upper=cUpper, lower=cLower))
     assert np.array_equal(got["upper"], lUpper - cUpper) and np.array_equal(got["lower"], lUpper - cLower)
     assert np.array_equal(got["diag"], lDiag - cDiag)
+
+
+def test_momentum_equation_assembly_matches_reference_operators(meshmod, orc):
+    """UEqn of icoFoam.C:57-64, `fvm::ddt(U) + fvm::div(phi, U) - fvm::laplacian(nu, U)` and `UEqn == -fvc::grad(p)`: the
+    reference's fvMatrix operators (fvMatrix.C operator+ / operator- / operator== with a field / operator+= / -=, compiled for
+    the host) against the assembly statements of oracle/piso_oracle.py (coefficients, source + V*su, internal / boundary
+    coefficients of the patches), bit for bit."""
+    m = meshmod.decompose(8, 2, 0)
+    a = orc.Addr(m.nCells, m.lower, m.upper)
+    rng = np.random.default_rng(99)
+    n, nF = m.nCells, m.nFaces
+    V = rng.uniform(0.5, 1.5, n) * 1e-3
+    ddtDiag, ddtSource = 200.0 * V, (200.0 * rng.uniform(-1, 1, (n, 3))) * V[:, None]
+    cLower, cUpper, cDiag = orc.convection_fill(a, rng.uniform(0.3, 0.7, nF), rng.uniform(-1, 1, nF) * 1e-2)
+    lUpper, lDiag = orc.laplacian_fill(a, rng.uniform(5, 9, nF), rng.uniform(0.5, 1.5, nF) * 1e-3)
+    patches = [p.faceCells for p in m.patches]
+    tot = sum(len(p) for p in patches)
+    cIc, cBc, lIc, lBc = (rng.uniform(-1, 1, (tot, 3)) for _ in range(4))
+    su = rng.uniform(-1, 1, (n, 3))      # -fvc::grad(p)
+    got = ref_ldu.fvm_assemble(n, m.lower, m.upper, patches, V, dict(diag=ddtDiag, source=ddtSource),
+                               dict(diag=cDiag, upper=cUpper, lower=cLower, ic=cIc, bc=cBc), dict(diag=lDiag, upper=lUpper, ic=lIc, bc=lBc), su)
+    assert got["kind"] == "asymmetric"
+    # oracle/piso_oracle.py Cavity.step
+    assert np.array_equal(got["diag"], (ddtDiag + cDiag) - lDiag)
+    assert np.array_equal(got["upper"], cUpper - lUpper) and np.array_equal(got["lower"], cLower - lUpper)
+    assert np.array_equal(got["source"], ddtSource + V[:, None] * su)
+    assert np.array_equal(got["ic"], cIc - lIc) and np.array_equal(got["bc"], cBc - lBc)
