@@ -87,6 +87,9 @@ int b200ldu_ctx_destroy(b200ldu_ctx *ctx);
  * broadcast by the host program. */
 int b200ldu_comm_unique_id(void *out128);
 int b200ldu_comm_init(b200ldu_ctx *ctx, const void *nccl_unique_id_128, int rank, int nRanks);
+/* data path of the two exchanges: 1 peer-memory kernels over NVLink, 0 NCCL, -1 not applicable (single rank / no
+ * coupled patches).  The peer-memory path needs CUDA IPC between all ranks; otherwise every rank falls back to NCCL. */
+int b200ldu_comm_info(const b200ldu_ctx *ctx, const b200ldu_addr *a, int *allreduceP2P, int *haloP2P);
 /* stream all work of this context is enqueued on (a cudaStream_t); NULL out => legacy stream */
 int b200ldu_ctx_set_stream(b200ldu_ctx *ctx, void *cudaStream);
 int b200ldu_ctx_sync(b200ldu_ctx *ctx);
@@ -99,7 +102,10 @@ int b200ldu_ctx_sync(b200ldu_ctx *ctx);
  * neighbPatchID, face i pairs with face i; scalar fields, no transform).  Cyclic patches are
  * served by the Krylov and smooth solvers and all matrix operations; GAMG rejects them.
  * cellCentres_h: optional HOST double[3*nCells] (fvMesh::C()) used only to choose the
- * band renumbering; NULL => graph-distance embedding of the addressing itself. */
+ * band renumbering; NULL => graph-distance embedding of the addressing itself.
+ * COLLECTIVE once b200ldu_comm_init has run with nRanks > 1: every rank of the communicator
+ * must call it in the same order (one all-gather of the patch table and the cell counts),
+ * also a rank whose addressing has no processor patch. */
 int b200ldu_addr_create(b200ldu_ctx *ctx, int nCells, int nFaces, const int *lower_h,
                         const int *upper_h, int nPatches, const int *patchStart_h,
                         const int *faceCells_h, const int *neighbRank_h,
@@ -113,7 +119,14 @@ int b200ldu_addr_perm(const b200ldu_addr *a, int *perm_h);
 
 /* ---- lduMatrix coefficients (LDU/lduMatrix/lduMatrix.H:78-96, lduMatrix.C:221-471) ----
  * Copies diag/upper/lower (+ interfaceBouCoeffs/interfaceIntCoeffs, flat over coupled
- * patches in patch order) into the banded layout; replaces calcSortCoeffs/lowerSort. */
+ * patches in patch order): once into the banded coefficient streams (replaces
+ * calcSortCoeffs/lowerSort) and once, caller order, into arrays the matrix owns -- faceH, the
+ * b200ldu_fvm_* glue and the GAMG coarse-level assembly read those later.  The caller may free
+ * or overwrite its arrays as soon as the call returns; changing coefficients (relax,
+ * setReference on the caller's diag) takes another b200ldu_matrix_set to reach the matrix,
+ * exactly as a non-const lduMatrix::diag()/upper() access invalidates the reference's sorted
+ * copies (lduMatrix.C:238,269).  intCoeffs_d == bouCoeffs_d (same pointer) declares A^T's
+ * interface coefficients equal to A's. */
 int b200ldu_matrix_create(b200ldu_addr *a, b200ldu_matrix **out);
 int b200ldu_matrix_set(b200ldu_matrix *m, const double *diag_d, const double *upper_d,
                        const double *lower_d /* NULL => symmetric */,
@@ -232,8 +245,9 @@ int b200ldu_fv_add_boundary_source(b200ldu_addr *a, const double *boundaryCoeffs
  *   relax                in place on diag_d / source_d                         (:1088-1345)
  *   set_reference        source[celli] += diag[celli]*value; diag[celli] *= 2; celli < 0: no-op   (:965-983)
  *   solve                solveSegregated: scalar fvScalarMatrix.C:142-192, vector component loop
- *                        fvMatrixSolve.C:104-226; perf[nComp]; the matrix is re-pointed at a folded diagonal for
- *                        the solve and back at the caller's arrays afterwards (saveDiag) */
+ *                        fvMatrixSolve.C:104-226; perf[nComp]; only the banded diagonal is refilled with the folded
+ *                        diagonal for the solve and with the matrix's own afterwards (saveDiag): the
+ *                        off-diagonal streams are not touched */
 /* patchNeighbourField of all coupled patch faces of a caller-order field (coupledFvPatchField::patchNeighbourField:
  * processorFvPatchField.C:196-262 exchange with the neighbour rank, cyclicFvPatchField.C:133-160 partner patch);
  * pnf_d [nCoupledFaces*nComp] in the order of b200ldu_addr_create's faceCells */

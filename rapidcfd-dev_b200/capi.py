@@ -50,7 +50,7 @@ class Perf(C.Structure):
 
 EXPORTS = [
     "b200ldu_last_error", "b200ldu_controls_default", "b200ldu_ctx_create", "b200ldu_ctx_destroy",
-    "b200ldu_comm_unique_id", "b200ldu_comm_init", "b200ldu_ctx_set_stream", "b200ldu_ctx_sync",
+    "b200ldu_comm_unique_id", "b200ldu_comm_init", "b200ldu_comm_info", "b200ldu_ctx_set_stream", "b200ldu_ctx_sync",
     "b200ldu_addr_create", "b200ldu_addr_destroy", "b200ldu_addr_info", "b200ldu_addr_perm",
     "b200ldu_matrix_create", "b200ldu_matrix_set", "b200ldu_matrix_destroy",
     "b200ldu_amul", "b200ldu_tmul", "b200ldu_sumA", "b200ldu_residual", "b200ldu_H", "b200ldu_H1",
@@ -95,6 +95,7 @@ def lib():
     L.b200ldu_ctx_destroy.argtypes = [vp]
     L.b200ldu_comm_unique_id.argtypes = [vp]
     L.b200ldu_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.b200ldu_comm_info.argtypes = [vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.b200ldu_ctx_set_stream.argtypes = [vp, vp]
     L.b200ldu_ctx_sync.argtypes = [vp]
     L.b200ldu_addr_create.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, C.POINTER(vp)]

@@ -132,6 +132,16 @@ extern "C" int b200ldu_comm_init(b200ldu_ctx *ctx, const void *id128, int rank, 
     return p2p_setup(ctx);
 }
 
+// which data path the two exchanges of the hot path take (reported by bench.py): 1 = hand-written peer-memory
+// kernels over NVLink, 0 = NCCL (ncclSend/ncclRecv halo, ncclAllReduce of the solver scalars), -1 = not applicable
+extern "C" int b200ldu_comm_info(const b200ldu_ctx *ctx, const b200ldu_addr *a, int *allreduceP2P, int *haloP2P)
+{
+    if (!ctx) return B200LDU_EINVAL;
+    if (allreduceP2P) *allreduceP2P = ctx->nRanks > 1 ? (ctx->p2p ? 1 : 0) : -1;
+    if (haloP2P) *haloP2P = (a && a->L.nRecv > 0) ? (a->p2pHalo ? 1 : 0) : -1;
+    return B200LDU_OK;
+}
+
 int comm_destroy(b200ldu_ctx *ctx)
 {
     if (ctx->region) {
@@ -180,7 +190,9 @@ int comm_addr_setup(b200ldu_addr *a)
     a->L.haloSeq = nullptr;
     a->L.tail0 = a->L.tail1 = nullptr;
     a->L.nNbr = 0;
-    if (ctx->nRanks == 1 || !ctx->nccl || a->nPatches == 0) return B200LDU_OK;
+    // COLLECTIVE over the communicator: every rank takes part in the gather below, also one whose addressing
+    // has no processor patch (it contributes an empty row and still learns the global cell count)
+    if (ctx->nRanks == 1 || !ctx->nccl) return B200LDU_OK;
     cudaStream_t st = ctx->stream;
     ncclComm_t comm = (ncclComm_t)ctx->nccl;
     const int R = ctx->nRanks;
@@ -197,6 +209,7 @@ int comm_addr_setup(b200ldu_addr *a)
         row[nb] = a->patchStart[p];
         row[R + nb] = a->patchStart[p + 1] - a->patchStart[p];
     }
+    if (a->L.nRecv == 0) simple = true; // nothing to exchange: does not block the peers' peer-memory halo
     if (!simple)
         for (int r = 0; r < R; r++) row[r] = -2;
     row[2 * R] = a->nCells;
@@ -217,7 +230,7 @@ int comm_addr_setup(b200ldu_addr *a)
             if (all[(size_t)(2 * R + 1) * r + q] == -2) everySimple = false;
     }
     a->nCellsGlobal = ncg;
-    if (!ctx->p2p || !everySimple) return B200LDU_OK;
+    if (!ctx->p2p || !everySimple || a->nPatches == 0) return B200LDU_OK;
     std::vector<PackPatch> pp(a->nPatches);
     std::vector<PackChunk> pc;
     for (int p = 0; p < a->nPatches; p++) {

@@ -21,6 +21,7 @@
 #include "fieldops_kernels.cuh"
 #include "fvmatrix_kernels.cuh"
 #include "internal.h"
+#include "ldu.h"
 
 using namespace fvmk;
 
@@ -308,7 +309,7 @@ extern "C" int b200ldu_fvm_solve(b200ldu_matrix *m, int nComp, const char *solve
     const int n = a->nCells;
     cudaStream_t st = a->ctx->stream;
     // the caller's coefficient arrays: the matrix is re-pointed at the folded diagonal for the solve
-    const double *diag0 = m->diag_ext, *upper = m->upper_ext, *lower = m->symmetric ? nullptr : m->lower_ext;
+    const double *diag0 = m->diag_ext;
     const double *bou = m->bou_ext, *intc = m->int_ext;
     double *dK = nullptr, *total = nullptr, *sK = nullptr, *pK = nullptr;
     TRY(scratch(a, 0, (size_t)n, &dK));
@@ -319,7 +320,7 @@ extern "C" int b200ldu_fvm_solve(b200ldu_matrix *m, int nComp, const char *solve
         boundary_source_kernel<1><<<grid(n, 256), 256, 0, st>>>(n, L, boundaryCoeffs_d, bou, nullptr, source_d, total);
         a->ctx->launches += 2;
         KERNEL_CHECK();
-        rc = b200ldu_matrix_set(m, dK, upper, lower, bou, intc);
+        rc = matrix_set_diag(m, dK); // the off-diagonal streams are unchanged
         if (rc == B200LDU_OK) rc = b200ldu_solve(m, solver, precondOrSmoother, controls, gamg, psi_d, total, &perf[0], nullptr, 0);
     } else {
         TRY(scratch(a, 2, (size_t)n, &sK));
@@ -335,7 +336,7 @@ extern "C" int b200ldu_fvm_solve(b200ldu_matrix *m, int nComp, const char *solve
             component_kernel<<<grid(n, 256), 256, 0, st>>>(n, nComp, k, none, nullptr, nullptr, psi_d, pK);
             a->ctx->launches += 3;
             KERNEL_CHECK();
-            rc = b200ldu_matrix_set(m, dK, upper, lower, bou, intc);
+            rc = matrix_set_diag(m, dK);
             if (rc == B200LDU_OK) rc = b200ldu_solve(m, solver, precondOrSmoother, controls, gamg, pK, sK, &perf[k], nullptr, 0);
             if (rc == B200LDU_OK) {
                 set_component_kernel<<<grid(n, 256), 256, 0, st>>>(n, nComp, k, pK, psi_d);
@@ -344,6 +345,6 @@ extern "C" int b200ldu_fvm_solve(b200ldu_matrix *m, int nComp, const char *solve
             }
         }
     }
-    const int rc2 = b200ldu_matrix_set(m, diag0, upper, lower, bou, intc); // diag() = saveDiag
+    const int rc2 = matrix_set_diag(m, diag0); // diag() = saveDiag
     return rc != B200LDU_OK ? rc : rc2;
 }

@@ -43,6 +43,11 @@ void b200_set_error(const char *fmt, ...);
 // indices with 32-bit loads (ushort2).
 constexpr int SLICE_ROWS = 64;
 constexpr int ENGINE_THREADS = 256;
+// resident CTAs per SM the engine kernels are compiled for: 5 => 48 registers per thread (no spills in the
+// slot loop), 6 => 40 registers (a few 8-byte spills per group of four slots)
+#ifndef ENGINE_MINB
+#define ENGINE_MINB 5
+#endif
 
 struct b200ldu_ctx {
     int device = 0;
@@ -104,7 +109,9 @@ struct LayoutDev {
     const long long *sliceStart; // [nSlices+1] entry offset of each slice (multiple of 64)
     const uint16_t *sliceW;      // slots per row in the slice, all entries
     const uint16_t *sliceWL;     // slots holding owner/neighbour entries only (no interfaces)
-    const uint16_t *col;         // [nEntries] band-local column: < bandRows own band, else halo slot
+    const int *cStart;           // [nSlices+1] offset of each slice's column blob, in 16-byte words
+    const uint4 *cblob;          // compressed band-local columns (layout.cu 3b): < bandRows own band, else halo slot
+    int wbufBytes;               // longest blob: size of one per-warp staging buffer
     const int *haloStart;        // [nBands+1]
     const int *haloIdx;          // banded extended index: < nPad local row, else nPad + recv slot
     const int *perm;             // [nCells] caller cell -> banded row
@@ -120,16 +127,6 @@ struct LayoutDev {
     const int *sendRows;           // banded row of every coupled-patch face cell
     unsigned long long *seqs;      // device counters: [1] halo sequence, [6] CTAs done, [8+p] chunks done
     int nPackChunks;
-    // shared-coefficient layout for symmetric matrices (layout_shared.cu); null when unused
-    const long long *sh_vStart;  // [nSlices+1] offsets into the value stream (doubles)
-    const long long *sh_nStart;  // [nSlices+1] offsets into the neighbour stream (entries)
-    const uint16_t *sh_VS;       // value slots per row (owner + interface)
-    const uint16_t *sh_WO;       // owner slots per row
-    const uint16_t *sh_WN;       // neighbour slots per row
-    const uint16_t *sh_colV;     // column of every value-stream element (extras: unused)
-    const uint32_t *sh_nbr;      // neighbour entries: column | ref << 16
-    int sh_warpDoubles;          // doubles of the longest per-slice value stream
-    int sh_bufBytes, sh_colOff, sh_nbrOff; // per-warp stream buffer: values | columns | neighbour entries
 };
 
 struct b200ldu_addr {
@@ -146,7 +143,9 @@ struct b200ldu_addr {
     std::vector<double> centres_h; // optional cell centres (kept for GAMG coarse-level banding)
     // device arrays owned
     long long *d_sliceStart = nullptr;
-    uint16_t *d_sliceW = nullptr, *d_sliceWL = nullptr, *d_col = nullptr;
+    uint16_t *d_sliceW = nullptr, *d_sliceWL = nullptr;
+    int *d_cStart = nullptr;
+    uint32_t *d_cblob = nullptr;
     int *d_code = nullptr; // [nEntries] value source: 2f+side | -1 pad | -2-pf interface
     int *d_haloStart = nullptr, *d_haloIdx = nullptr, *d_perm = nullptr, *d_iperm = nullptr;
     int *d_sendRows = nullptr; // [nRecv] banded row of faceCells (pack kernel)
@@ -172,19 +171,8 @@ struct b200ldu_addr {
     bool hostOnly = false;
     std::vector<long long> dbg_sliceStart;
     std::vector<uint16_t> dbg_sliceW, dbg_sliceWL, dbg_col;
-    std::vector<int> dbg_code, dbg_haloStart, dbg_haloIdx;
-    // shared-coefficient layout (built lazily at the first symmetric matrix_set)
-    bool sharedBuilt = false, sharedOk = false;
-    long long sh_nV = 0, sh_nN = 0;
-    int sh_warpDoubles = 0;
-    long long *d_shVStart = nullptr, *d_shNStart = nullptr;
-    uint16_t *d_shVS = nullptr, *d_shWO = nullptr, *d_shWN = nullptr, *d_shColV = nullptr;
-    int *d_shCodeV = nullptr;
-    uint32_t *d_shNbr = nullptr;
-    std::vector<long long> dbg_shVStart, dbg_shNStart;
-    std::vector<uint16_t> dbg_shVS, dbg_shWO, dbg_shWN, dbg_shColV;
-    std::vector<int> dbg_shCodeV;
-    std::vector<uint32_t> dbg_shNbr;
+    std::vector<int> dbg_code, dbg_haloStart, dbg_haloIdx, dbg_cStart;
+    std::vector<uint32_t> dbg_cblob;
     // workspace pool for caller-order entry points (banded vectors)
     std::vector<double *> pool;
     long long vecLen = 0; // nPad + nRecv (padded to even)
@@ -196,11 +184,14 @@ struct b200ldu_matrix {
     bool haveT = false;
     double *d_val = nullptr;  // banded coefficients for Amul   [nEntries]
     double *d_valT = nullptr; // banded coefficients for Tmul   (aliases d_val when symmetric)
-    double *d_valSh = nullptr; // shared-coefficient value stream (symmetric matrices)
-    bool shared = false;       // Amul-type sweeps run on the shared-coefficient layout
     double *d_diag = nullptr; // banded diagonal [nPad] (padding rows = 1)
     double *d_rD = nullptr;   // 1/diag, filled by matrix_set
-    // caller-order pointers kept for faceH (caller owns)
+    // caller-order coefficients OWNED by the matrix (copied by matrix_set): diag, upper, lower, interfaceBouCoeffs,
+    // interfaceIntCoeffs -- read by faceH, the fvMatrix glue and the GAMG coarse-level assembly
+    double *own[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t ownLen[5] = {0, 0, 0, 0, 0};
+    // current views of them (diag_ext is re-pointed at the boundary-folded diagonal for the duration of fvm_solve;
+    // lower_ext aliases upper_ext when symmetric, int_ext aliases bou_ext when the caller passed one array for both)
     const double *upper_ext = nullptr, *lower_ext = nullptr, *diag_ext = nullptr, *bou_ext = nullptr,
                  *int_ext = nullptr;
     // solver workspace (allocated once, reused across solves -- PCGCache.H:9-58)
@@ -216,7 +207,6 @@ struct b200ldu_matrix {
 // cross-file helpers
 // ---------------------------------------------------------------------------
 int layout_build(b200ldu_addr *a, const double *centres);
-int layout_build_shared(b200ldu_addr *a);
 int addr_alloc_vec(b200ldu_addr *a, double **out); // banded vector of vecLen doubles, zeroed
 double *addr_pool_vec(b200ldu_addr *a, int slot);  // reusable scratch (grows on demand)
 

@@ -12,9 +12,11 @@
 //  * entries of 64 consecutive rows are stored slot-major ("slice"): slot j of row q
 //    sits at sliceStart + 64*j + q, so a warp reads one slot of its 64 rows with a
 //    single 128-bit load per lane;
-//  * columns are 16-bit indices into the band's shared-memory psi tile: the band's own
-//    rows first, then the band's halo list (rows of other bands / received interface
-//    values) which is gathered once per band.
+//  * columns are indices into the band's shared-memory psi tile: the band's own rows
+//    first, then the band's halo list (rows of other bands / received interface values)
+//    which is gathered once per band.  They are stored compressed: per slice and slot one
+//    row offset shared by the regular rows + a bit mask and a short list of 16-bit columns
+//    for the others (section 3b).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -185,10 +187,10 @@ int layout_build(b200ldu_addr *a, const double *centres)
     int bits[3] = {0, 0, 0};
     {
         long long tiles = 1;
-        // tiles of ~one slice (64 rows): slices become small cubes (most of a row's faces stay inside
-        // its slice: that is what the shared-coefficient layout exploits) and Morton order keeps
-        // every run of bandRows/64 consecutive tiles a compact brick
-        while ((double)nCells / (double)tiles > (double)SLICE_ROWS && bits[0] + bits[1] + bits[2] < 45) {
+        // tiles of ~one band (bandRows rows), caller order inside a tile: a band is a compact brick, and on
+        // block-structured meshes (lexicographic caller numbering) a row's neighbours sit at a constant row
+        // offset for whole slices -- which is what the column compression below exploits
+        while ((double)nCells / (double)tiles > (double)bandRows && bits[0] + bits[1] + bits[2] < 45) {
             int best = 2; // ties go to the last axis so x keeps the longest runs
             double bestExt = -1;
             for (int k = 2; k >= 0; k--) {
@@ -383,6 +385,84 @@ int layout_build(b200ldu_addr *a, const double *centres)
     for (int b = 0; b < nBands; b++)
         std::copy(halo[b].begin(), halo[b].end(), haloIdx.begin() + haloStart[b]);
 
+    // ---- 3b. compressed columns ---------------------------------------------
+    // Per slice one blob of 16-byte words: W slot descriptors {mask lo, mask hi, delta, exception offset}
+    // followed by the slice's exception list (16-bit columns, padded to 8).  Row q of the slice reads slot j
+    // at tile column (local row + delta) unless bit q of the mask is set, in which case the column is
+    // exc[offset + number of mask bits below q].  delta = the most frequent (column - local row) of the slot;
+    // on band-sized bricks of a structured mesh only the references into the halo are exceptions
+    // (~8 % of the entries): 16-bit columns cost 2 B per entry, this ~0.4 B.
+    std::vector<int> cStart((size_t)nSlices + 1, 0);
+    std::vector<std::vector<uint32_t>> blobs(nSlices);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int s = 0; s < nSlices; s++) {
+        const int W = sliceW[s];
+        const long long base = sliceStart[s];
+        const int lr0 = (s % slicesPerBand) * SLICE_ROWS;
+        std::vector<uint32_t> &bl = blobs[s];
+        bl.assign((size_t)4 * W, 0);
+        std::vector<uint16_t> exc;
+        for (int j = 0; j < W; j++) {
+            const uint16_t *cj = &col[base + (long long)j * SLICE_ROWS];
+            int d[SLICE_ROWS], best = 0, bestN = 0;
+            for (int q = 0; q < SLICE_ROWS; q++) d[q] = (int)cj[q] - (lr0 + q);
+            {
+                int t[SLICE_ROWS];
+                std::copy(d, d + SLICE_ROWS, t);
+                std::sort(t, t + SLICE_ROWS);
+                for (int q = 0; q < SLICE_ROWS;) { // longest run; ties go to the smallest offset
+                    int e = q;
+                    while (e < SLICE_ROWS && t[e] == t[q]) e++;
+                    if (e - q > bestN) {
+                        bestN = e - q;
+                        best = t[q];
+                    }
+                    q = e;
+                }
+            }
+            uint64_t mask = 0;
+            const uint32_t off = (uint32_t)exc.size();
+            for (int q = 0; q < SLICE_ROWS; q++)
+                if (d[q] != best) {
+                    mask |= 1ull << q;
+                    exc.push_back(cj[q]);
+                }
+            bl[4 * (size_t)j + 0] = (uint32_t)mask;
+            bl[4 * (size_t)j + 1] = (uint32_t)(mask >> 32);
+            bl[4 * (size_t)j + 2] = (uint32_t)best;
+            bl[4 * (size_t)j + 3] = off;
+        }
+        while (exc.size() % 8) exc.push_back(0);
+        for (size_t i = 0; i < exc.size(); i += 2) bl.push_back((uint32_t)exc[i] | ((uint32_t)exc[i + 1] << 16));
+    }
+    int maxBlobWords16 = 0; // longest blob in 16-byte words (per-warp staging buffer of the engine)
+    for (int s = 0; s < nSlices; s++) {
+        const int w16 = (int)(blobs[s].size() / 4);
+        cStart[s + 1] = cStart[s] + w16;
+        maxBlobWords16 = std::max(maxBlobWords16, w16);
+    }
+    std::vector<uint32_t> cblob((size_t)std::max(cStart[nSlices], 1) * 4, 0);
+#pragma omp parallel for schedule(static)
+    for (int s = 0; s < nSlices; s++) std::copy(blobs[s].begin(), blobs[s].end(), cblob.begin() + (size_t)cStart[s] * 4);
+    blobs.clear();
+    blobs.shrink_to_fit();
+    {
+        // tile(s) + the per-warp double buffers must fit next to each other in shared memory
+        const size_t wb = (size_t)(ENGINE_THREADS / 32) * 2 * 16 * (size_t)maxBlobWords16;
+        if ((size_t)(bandRows + maxHalo + 2) * 2 * sizeof(double) + wb > TILE_BYTES_MAX + 16 * 1024) {
+            if (bandRows > SLICE_ROWS) {
+                const int saved = g_bandRowsRetry;
+                g_bandRowsRetry = bandRows / 2;
+                int rc = layout_build(a, centres);
+                g_bandRowsRetry = saved;
+                return rc;
+            }
+            b200_set_error("layout_build: rows of up to %d entries: the per-warp column buffers do not fit in shared memory",
+                           maxBlobWords16);
+            return B200LDU_ELAYOUT;
+        }
+    }
+
     std::vector<int> sendRows(std::max(nRecv, 1));
     for (int i = 0; i < nRecv; i++) sendRows[i] = perm[a->faceCells[i]];
 
@@ -396,6 +476,7 @@ int layout_build(b200ldu_addr *a, const double *centres)
     a->L.slicesPerBand = slicesPerBand;
     a->L.nRecv = nRecv;
     a->L.maxHalo = maxHalo;
+    a->L.wbufBytes = 16 * maxBlobWords16;
     if (a->hostOnly) { // structural self-check path (tests): keep the host arrays, no GPU
         a->dbg_sliceStart.swap(sliceStart);
         a->dbg_sliceW.swap(sliceW);
@@ -404,6 +485,8 @@ int layout_build(b200ldu_addr *a, const double *centres)
         a->dbg_code.swap(code);
         a->dbg_haloStart.swap(haloStart);
         a->dbg_haloIdx.swap(haloIdx);
+        a->dbg_cStart.swap(cStart);
+        a->dbg_cblob.swap(cblob);
         return B200LDU_OK;
     }
 
@@ -411,7 +494,8 @@ int layout_build(b200ldu_addr *a, const double *centres)
     TRY(dev_upload(&a->d_sliceStart, sliceStart));
     TRY(dev_upload(&a->d_sliceW, sliceW));
     TRY(dev_upload(&a->d_sliceWL, sliceWL));
-    TRY(dev_upload(&a->d_col, col));
+    TRY(dev_upload(&a->d_cStart, cStart));
+    TRY(dev_upload(&a->d_cblob, cblob));
     TRY(dev_upload(&a->d_code, code));
     TRY(dev_upload(&a->d_haloStart, haloStart));
     TRY(dev_upload(&a->d_haloIdx, haloIdx));
@@ -435,7 +519,9 @@ int layout_build(b200ldu_addr *a, const double *centres)
     L.sliceStart = a->d_sliceStart;
     L.sliceW = a->d_sliceW;
     L.sliceWL = a->d_sliceWL;
-    L.col = a->d_col;
+    L.cStart = a->d_cStart;
+    L.cblob = reinterpret_cast<const uint4 *>(a->d_cblob);
+    L.wbufBytes = 16 * maxBlobWords16;
     L.haloStart = a->d_haloStart;
     L.haloIdx = a->d_haloIdx;
     L.perm = a->d_perm;
@@ -467,7 +553,6 @@ extern "C" int b200ldu_layout_debug_create(int nCells, int nFaces, const int *lo
         a->faceCells.assign(faceCells_h, faceCells_h + a->patchStart[nPatches]);
     }
     int rc = layout_build(a, cellCentres_h);
-    if (rc == B200LDU_OK) rc = layout_build_shared(a);
     if (rc != B200LDU_OK) {
         delete a;
         return rc;
@@ -478,6 +563,7 @@ extern "C" int b200ldu_layout_debug_create(int nCells, int nFaces, const int *lo
 
 // what: 0 perm(int32) 1 iperm(int32) 2 sliceStart(int64) 3 sliceW(u16) 4 sliceWL(u16) 5 col(u16)
 //       6 code(int32) 7 haloStart(int32) 8 haloIdx(int32) 9 dims {nPad,nBands,bandRows,nRecv,maxHalo}(int32)
+//       10 cStart(int32, 16-byte words) 11 cblob(uint32 words: compressed columns, see layout_build 3b)
 // returns the element count (copies min(count, cap) elements when out != NULL)
 extern "C" long long b200ldu_layout_debug_get(const b200ldu_addr *a, int what, void *out, long long cap)
 {
@@ -498,14 +584,8 @@ extern "C" long long b200ldu_layout_debug_get(const b200ldu_addr *a, int what, v
     case 7: return give(a->dbg_haloStart.data(), 4, (long long)a->dbg_haloStart.size());
     case 8: return give(a->dbg_haloIdx.data(), 4, a->nHaloTotal);
     case 9: return give(dims, 4, 5);
-    case 10: return give(a->dbg_shVStart.data(), 8, (long long)a->dbg_shVStart.size());
-    case 11: return give(a->dbg_shNStart.data(), 8, (long long)a->dbg_shNStart.size());
-    case 12: return give(a->dbg_shVS.data(), 2, (long long)a->dbg_shVS.size());
-    case 13: return give(a->dbg_shWO.data(), 2, (long long)a->dbg_shWO.size());
-    case 14: return give(a->dbg_shWN.data(), 2, (long long)a->dbg_shWN.size());
-    case 15: return give(a->dbg_shColV.data(), 2, a->sh_nV);
-    case 16: return give(a->dbg_shCodeV.data(), 4, a->sh_nV);
-    case 17: return give(a->dbg_shNbr.data(), 4, a->sh_nN);
+    case 10: return give(a->dbg_cStart.data(), 4, (long long)a->dbg_cStart.size());
+    case 11: return give(a->dbg_cblob.data(), 4, (long long)a->dbg_cblob.size());
     }
     return -1;
 }

@@ -199,12 +199,11 @@ extern "C" int b200ldu_addr_destroy(b200ldu_addr *a)
     if (!a) return B200LDU_OK;
     cudaSetDevice(a->ctx->device);
     cudaStreamSynchronize(a->ctx->stream);
-    void *ptrs[] = {a->d_sliceStart, a->d_sliceW, a->d_sliceWL, a->d_col, a->d_code, a->d_haloStart,
+    void *ptrs[] = {a->d_sliceStart, a->d_sliceW, a->d_sliceWL, a->d_cStart, a->d_cblob, a->d_code, a->d_haloStart,
                     a->d_haloIdx, a->d_perm, a->d_iperm, a->d_sendRows, a->d_l, a->d_u,
                     a->d_ownerStart, a->d_losort, a->d_losortStart, a->d_bFaceCells, a->d_cyclicSrc,
                     a->d_bCellStart, a->d_bCellFaces, a->d_bCells, a->d_packPatches, a->d_packChunks,
-                    a->d_shVStart, a->d_shNStart, a->d_shVS, a->d_shWO, a->d_shWN, a->d_shColV, a->d_shCodeV,
-                    a->d_shNbr, a->d_cCellStart, a->d_cCellFaces, a->d_cFaceCells, a->d_fvmScratch[0],
+                    a->d_cCellStart, a->d_cCellFaces, a->d_cFaceCells, a->d_fvmScratch[0],
                     a->d_fvmScratch[1], a->d_fvmScratch[2], a->d_fvmScratch[3]};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -326,7 +325,7 @@ extern "C" int b200ldu_matrix_destroy(b200ldu_matrix *m)
     cudaStreamSynchronize(m->a->ctx->stream);
     if (m->d_valT && m->d_valT != m->d_val) cudaFree(m->d_valT);
     void *ptrs[] = {m->d_val, m->d_diag, m->d_rD, m->d_partials, m->d_scal, m->d_hist, m->d_sendBuf,
-                    m->d_valSh};
+                    m->own[0], m->own[1], m->own[2], m->own[3], m->own[4]};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (double *p : m->work)
@@ -374,6 +373,37 @@ __global__ void fill_diag_kernel(long long n, int nPad, const int *__restrict__ 
     rD[r] = __ddiv_rn(1.0, d); // AINVPreconditioner.C:34-41, diagonalPreconditioner.C:60-66
 }
 
+// caller-order copy kept by the matrix (slot k of m->own), grown on demand
+static int own_copy(b200ldu_matrix *m, int k, const double *src, size_t n, const double **out)
+{
+    *out = nullptr;
+    if (!src || n == 0) return B200LDU_OK;
+    if (m->ownLen[k] < n) {
+        if (m->own[k]) cudaFree(m->own[k]);
+        m->own[k] = nullptr;
+        m->ownLen[k] = 0;
+        CUDA_TRY(cudaMalloc((void **)&m->own[k], sizeof(double) * n));
+        m->ownLen[k] = n;
+    }
+    if (src != m->own[k])
+        CUDA_TRY(cudaMemcpyAsync(m->own[k], src, sizeof(double) * n, cudaMemcpyDeviceToDevice, m->a->ctx->stream));
+    *out = m->own[k];
+    return B200LDU_OK;
+}
+
+// banded diagonal + reciprocal from a caller-order diagonal (also used by fvm_solve, which folds the
+// boundary coefficients into the diagonal for the duration of a solve: fvScalarMatrix.C:161-185)
+int matrix_set_diag(b200ldu_matrix *m, const double *diag_d)
+{
+    b200ldu_addr *a = m->a;
+    fill_diag_kernel<<<(unsigned)((a->vecLen + 255) / 256), 256, 0, a->ctx->stream>>>(a->vecLen, a->L.nPad, a->d_iperm,
+                                                                                      diag_d, m->d_diag, m->d_rD);
+    a->ctx->launches++;
+    KERNEL_CHECK();
+    m->diag_ext = diag_d;
+    return B200LDU_OK;
+}
+
 extern "C" int b200ldu_matrix_set(b200ldu_matrix *m, const double *diag_d, const double *upper_d,
                                   const double *lower_d, const double *bou_d, const double *int_d)
 {
@@ -386,67 +416,53 @@ extern "C" int b200ldu_matrix_set(b200ldu_matrix *m, const double *diag_d, const
         b200_set_error("matrix_set: interface coefficients required for coupled patches");
         return B200LDU_EINVAL;
     }
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
     cudaStream_t st = a->ctx->stream;
     m->symmetric = (lower_d == nullptr);
-    const double *lo = lower_d ? lower_d : upper_d;
+    const bool sameIfc = (bou_d == int_d);
+    // The matrix keeps its own caller-order copies (the reference's lduMatrix owns diag/upper/lower,
+    // lduMatrix.C:202-218): faceH, the fvMatrix glue and the GAMG coarse-level assembly read them
+    // later, so the caller may free or overwrite its arrays as soon as this call returns.
+    const double *dg, *up, *lw, *bo, *in;
+    TRY(own_copy(m, 0, diag_d, (size_t)a->nCells, &dg));
+    TRY(own_copy(m, 1, upper_d, (size_t)a->nFaces, &up));
+    TRY(own_copy(m, 2, lower_d, (size_t)a->nFaces, &lw));
+    TRY(own_copy(m, 3, bou_d, (size_t)a->L.nRecv, &bo));
+    if (sameIfc)
+        in = bo;
+    else
+        TRY(own_copy(m, 4, int_d, (size_t)a->L.nRecv, &in));
+    const double *lo = lw ? lw : up;
     long long ne = a->nEntries;
     // Tmul needs its own coefficient stream when A != A^T (asymmetric coefficients or
     // interfaceIntCoeffs != interfaceBouCoeffs)
-    bool needT = !m->symmetric || (a->L.nRecv && bou_d != int_d);
-    // Optional shared-coefficient layout for symmetric matrices (one value per face, 16 B/face
-    // instead of 20).  Measured on B200 (profiles/r01_ncu_shared_layout.txt) it moves 14 % fewer
-    // bytes but is bound by shared-memory wavefronts (fp64 gathers of coefficients AND psi), 265 us
-    // vs 223 us per 256^3 Amul, so the per-entry layout stays the default; B200LDU_SHARED=1 opts in.
-    bool useShared = false;
-    if (m->symmetric && a->nFaces > 0) {
-        const char *ev = getenv("B200LDU_SHARED");
-        if (ev && atoi(ev) == 1) {
-            TRY(layout_build_shared(a));
-            useShared = a->sharedOk;
-        }
+    bool needT = !m->symmetric || (a->L.nRecv && !sameIfc);
+    size_t nb = sizeof(double) * (size_t)(ne > 0 ? ne : 1);
+    if (!m->d_val) CUDA_TRY(cudaMalloc((void **)&m->d_val, nb));
+    if (needT && (!m->d_valT || m->d_valT == m->d_val)) {
+        m->d_valT = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&m->d_valT, nb));
     }
-    m->shared = useShared;
-    if (useShared) {
-        if (!m->d_valSh) CUDA_TRY(cudaMalloc((void **)&m->d_valSh, sizeof(double) * (size_t)(a->sh_nV > 0 ? a->sh_nV : 1)));
-        fill_val_kernel<<<(unsigned)((a->sh_nV + 255) / 256), 256, 0, st>>>(a->sh_nV, a->d_shCodeV, upper_d, lo, bou_d,
-                                                                            m->d_valSh, 0);
+    if (ne > 0) {
+        unsigned g = (unsigned)((ne + 255) / 256);
+        fill_val_kernel<<<g, 256, 0, st>>>(ne, a->d_code, up, lo, bo, m->d_val, 0);
         a->ctx->launches++;
-    }
-    const bool needGeneral = !useShared;
-    if (needGeneral || needT) {
-        size_t nb = sizeof(double) * (size_t)(ne > 0 ? ne : 1);
-        if (needGeneral && !m->d_val) CUDA_TRY(cudaMalloc((void **)&m->d_val, nb));
-        if (needT && (!m->d_valT || m->d_valT == m->d_val)) {
-            m->d_valT = nullptr;
-            CUDA_TRY(cudaMalloc((void **)&m->d_valT, nb));
-        }
-        if (ne > 0) {
-            unsigned g = (unsigned)((ne + 255) / 256);
-            if (needGeneral) {
-                fill_val_kernel<<<g, 256, 0, st>>>(ne, a->d_code, upper_d, lo, bou_d, m->d_val, 0);
-                a->ctx->launches++;
-            }
-            if (needT) {
-                fill_val_kernel<<<g, 256, 0, st>>>(ne, a->d_code, upper_d, lo, int_d, m->d_valT, 1);
-                a->ctx->launches++;
-            }
+        if (needT) {
+            fill_val_kernel<<<g, 256, 0, st>>>(ne, a->d_code, up, lo, in, m->d_valT, 1);
+            a->ctx->launches++;
         }
     }
     if (!needT) {
         if (m->d_valT && m->d_valT != m->d_val) cudaFree(m->d_valT);
         m->d_valT = m->d_val; // A^T == A
     }
-    fill_diag_kernel<<<(unsigned)((a->vecLen + 255) / 256), 256, 0, st>>>(a->vecLen, a->L.nPad, a->d_iperm,
-                                                                          diag_d, m->d_diag, m->d_rD);
-    a->ctx->launches++;
     KERNEL_CHECK();
     m->haveT = needT;
-    m->upper_ext = upper_d;
-    m->diag_ext = diag_d;
-    m->bou_ext = bou_d;
-    m->int_ext = int_d;
+    m->upper_ext = up;
+    m->bou_ext = bo;
+    m->int_ext = in;
     m->lower_ext = lo;
-    return B200LDU_OK;
+    return matrix_set_diag(m, dg);
 }
 
 // ---------------------------------------------------------------------------

@@ -15,7 +15,6 @@ struct SolverScalars {
     int nIterations, converged, singular, stop;
     int maxIter, minIter, histCap, nSweeps;
     int bodies; // fused PCG: iteration bodies whose A.p product has been formed
-    unsigned tailCount; // ticket counter of the fused scalar tail (engine.cuh)
 };
 
 struct OpBase {
@@ -389,11 +388,7 @@ __device__ __forceinline__ void scalar_body(const double *partials, int nPartial
                 __threadfence_system();
                 unsigned long long *f = p2p.flag[r] + (par * P2P_MAXR + p2p.rank);
                 asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(seq) : "memory");
-                const unsigned long long *w = p2p.flag[p2p.rank] + (par * P2P_MAXR + r);
-                unsigned long long v;
-                do {
-                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
-                } while (v < seq);
+                spin_until(p2p.flag[p2p.rank] + (par * P2P_MAXR + r), seq, p2p.seq + 7);
                 const double *src = p2p.mail[p2p.rank] + ((size_t)(par * P2P_MAXR + r) * 8);
                 for (int k = 0; k < NRED; k++) got[r][k] = __ldcg(src + k);
             }
@@ -420,17 +415,3 @@ __global__ void __launch_bounds__(256) scalar_kernel(const double *partials, int
     if (sc->stop) return;
     scalar_body<NRED, RUN_LOGIC>(partials, nPartials, sc, g, p2p);
 }
-
-// the same step as the tail of an engine kernel (run by the CTA that finishes last)
-template <int NRED, class G>
-struct ScalarTail {
-    static constexpr bool ACTIVE = true;
-    SolverScalars *sc;
-    G g;
-    P2PRed p2p;
-    __device__ __forceinline__ unsigned *counter() const { return &sc->tailCount; }
-    __device__ __forceinline__ void run(const double *partials, int nPartials)
-    {
-        scalar_body<NRED, true>(partials, nPartials, sc, g, p2p);
-    }
-};

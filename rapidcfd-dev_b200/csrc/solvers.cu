@@ -178,7 +178,7 @@ int solve_pcg(Solve &S, int pk)
         TRY(mat_amul(m, false, pA, wA, 1, nullptr, S.partials, stop));
         TRY(scalar_step<1>(S, a->L.nBands, [=] __device__(SolverScalars *s) {
             s->wApA = s->sum[0];
-            if (fabs(s->wApA) / s->normFactor < VSMALL_) { // checkSingularity PCG.C:170
+            if (!(fabs(s->wApA) / s->normFactor > VSMALL_)) { // checkSingularity PCG.C:170
                 s->singular = 1;
                 s->stop = 1;
                 return;
@@ -211,11 +211,9 @@ int solve_pcg(Solve &S, int pk)
 // convergence decision of body k is taken in the first scalar step of body k+1 (the extra
 // preconditioner sweep that has then already run only overwrote scratch).
 // ---------------------------------------------------------------------------
-// fused PCG sweeps (ops.cuh PcgAinvOp / PcgAmulOp), optionally with the scalar step as tail
-template <class Tail>
+// fused PCG sweeps (ops.cuh PcgAinvOp / PcgAmulOp)
 static int pcg_ka(b200ldu_matrix *m, const double *rOld, double *rNew, const double *w, const double *p,
-                  double *psi, double *z, const SolverScalars *sc, double *partials, const int *stop,
-                  const Tail &tail)
+                  double *psi, double *z, const SolverScalars *sc, double *partials, const int *stop)
 {
     PcgAinvOp op;
     op.stop = stop;
@@ -228,12 +226,11 @@ static int pcg_ka(b200ldu_matrix *m, const double *rOld, double *rNew, const dou
     op.z = z;
     op.rD = m->d_rD;
     op.sc = sc;
-    return engine_launch_m(m, false, op, tail);
+    return engine_launch_m(m, false, op);
 }
 
-template <class Tail>
 static int pcg_kb(b200ldu_matrix *m, const double *z, const double *pOld, double *pNew, double *w,
-                  const SolverScalars *sc, double *partials, const int *stop, const Tail &tail)
+                  const SolverScalars *sc, double *partials, const int *stop)
 {
     int wait = 0;
     TRY(mat_halo(m, pNew, stop, &wait)); // peer-memory path: nothing is launched, the send is fused
@@ -247,7 +244,7 @@ static int pcg_kb(b200ldu_matrix *m, const double *z, const double *pOld, double
     op.out = w;
     op.diag = m->d_diag;
     op.sc = sc;
-    return engine_launch_m(m, false, op, tail);
+    return engine_launch_m(m, false, op);
 }
 
 int solve_pcg_fused(Solve &S, int pk)
@@ -262,13 +259,6 @@ int solve_pcg_fused(Solve &S, int pk)
     double *pb[2] = {S.vec(0), S.vec(4)}, *w = S.vec(1), *rb[2] = {S.vec(2), S.vec(3)}, *z = S.vec(5);
     if (!pb[0] || !pb[1] || !w || !rb[0] || !rb[1] || !z) return B200LDU_ECUDA;
     const double *rD = m->d_rD;
-    // scalar steps as kernel tails (last-finishing CTA): needs the sums to be combinable inside a
-    // kernel, i.e. one rank or the peer-memory all-reduce.  Opt-in (B200LDU_TAIL=1): measured
-    // slower than the separate one-CTA launches on one GPU ("what did not pay").
-    const char *te = getenv("B200LDU_TAIL");
-    const bool tailOK = (S.ctx->nRanks == 1 || S.ctx->p2p) && (te && atoi(te) != 0);
-    const P2PRed pr = (S.ctx->nRanks > 1 && S.ctx->p2p) ? comm_p2p_red(S.ctx) : P2PRed();
-
     TRY(mat_amul(m, false, psi, w, 0, nullptr, nullptr, nullptr));
     TRY(init_residual(S, psi, b, w, rb[0], pb[0]));
 
@@ -285,7 +275,7 @@ int solve_pcg_fused(Solve &S, int pk)
     // scalar step B: alpha of body k
     auto gB = [=] __device__(SolverScalars *s) {
         s->wApA = s->sum[0];
-        if (fabs(s->wApA) / s->normFactor < VSMALL_) { // checkSingularity PCG.C:170
+        if (!(fabs(s->wApA) / s->normFactor > VSMALL_)) { // checkSingularity PCG.C:170
             s->singular = 1;
             s->stop = 1;
             return;
@@ -293,47 +283,37 @@ int solve_pcg_fused(Solve &S, int pk)
         s->alpha = s->wArA / s->wApA;
         s->bodies++;
     };
-    const ScalarTail<2, decltype(gA)> tailA{sc, gA, pr};
-    const ScalarTail<1, decltype(gB)> tailB{sc, gB, pr};
 
     auto body = [&](long long k) -> int {
         const double *rOld = rb[k & 1], *pPrev = pb[k & 1];
         double *rNew = rb[(k + 1) & 1], *pNew = pb[(k + 1) & 1];
         int np = a->L.nBands;
-        if (pk == 2 && tailOK) {
-            TRY(pcg_ka(m, rOld, rNew, w, pPrev, psi, z, sc, S.partials, stop, tailA));
+        if (pk == 2) {
+            TRY(pcg_ka(m, rOld, rNew, w, pPrev, psi, z, sc, S.partials, stop));
         } else {
-            if (pk == 2) {
-                TRY(pcg_ka(m, rOld, rNew, w, pPrev, psi, z, sc, S.partials, stop, NoTail()));
-            } else {
-                TRY(ew_launch<2>(S.ctx, n2, stop, S.partials, &np, [=] __device__(int i, double *red) {
-                    double2 r = CV2(rOld)[i];
-                    if (sc->bodies > 0) {
-                        const double alpha = sc->alpha;
-                        double2 ww = CV2(w)[i], pp = CV2(pPrev)[i], x = CV2(psi)[i];
-                        r.x = fma(-alpha, ww.x, r.x);
-                        r.y = fma(-alpha, ww.y, r.y);
-                        V2(psi)[i] = make_double2(fma(alpha, pp.x, x.x), fma(alpha, pp.y, x.y));
-                    }
-                    V2(rNew)[i] = r;
-                    double2 zz = r;
-                    if (pk == 1) {
-                        double2 d = CV2(rD)[i];
-                        zz = make_double2(__dmul_rn(d.x, r.x), __dmul_rn(d.y, r.y));
-                    }
-                    V2(z)[i] = zz;
-                    red[0] += zz.x * r.x + zz.y * r.y;
-                    red[1] += fabs(r.x) + fabs(r.y);
-                }));
-            }
-            TRY(scalar_step<2>(S, np, gA));
+            TRY(ew_launch<2>(S.ctx, n2, stop, S.partials, &np, [=] __device__(int i, double *red) {
+                double2 r = CV2(rOld)[i];
+                if (sc->bodies > 0) {
+                    const double alpha = sc->alpha;
+                    double2 ww = CV2(w)[i], pp = CV2(pPrev)[i], x = CV2(psi)[i];
+                    r.x = fma(-alpha, ww.x, r.x);
+                    r.y = fma(-alpha, ww.y, r.y);
+                    V2(psi)[i] = make_double2(fma(alpha, pp.x, x.x), fma(alpha, pp.y, x.y));
+                }
+                V2(rNew)[i] = r;
+                double2 zz = r;
+                if (pk == 1) {
+                    double2 d = CV2(rD)[i];
+                    zz = make_double2(__dmul_rn(d.x, r.x), __dmul_rn(d.y, r.y));
+                }
+                V2(z)[i] = zz;
+                red[0] += zz.x * r.x + zz.y * r.y;
+                red[1] += fabs(r.x) + fabs(r.y);
+            }));
         }
-        if (tailOK) {
-            TRY(pcg_kb(m, z, pPrev, pNew, w, sc, S.partials, stop, tailB));
-        } else {
-            TRY(pcg_kb(m, z, pPrev, pNew, w, sc, S.partials, stop, NoTail()));
-            TRY(scalar_step<1>(S, a->L.nBands, gB));
-        }
+        TRY(scalar_step<2>(S, np, gA));
+        TRY(pcg_kb(m, z, pPrev, pNew, w, sc, S.partials, stop));
+        TRY(scalar_step<1>(S, a->L.nBands, gB));
         return B200LDU_OK;
     };
     long long mb = (long long)S.c.maxIter + 1 > S.c.minIter ? (long long)S.c.maxIter + 1 : S.c.minIter;
@@ -385,7 +365,7 @@ int solve_pbicg(Solve &S, int pk)
         TRY(mat_amul(m, false, pA, wA, 3, pT, S.partials, stop)); // wApT = <wA, pT>
         TRY(scalar_step<1>(S, a->L.nBands, [=] __device__(SolverScalars *s) {
             s->wApA = s->sum[0];
-            if (fabs(s->wApA) / s->normFactor < VSMALL_) {
+            if (!(fabs(s->wApA) / s->normFactor > VSMALL_)) {
                 s->singular = 1;
                 s->stop = 1;
                 return;
@@ -446,13 +426,13 @@ int solve_pbicgstab(Solve &S, int pk)
         TRY(scalar_step<1>(S, np, [=] __device__(SolverScalars *s) {
             s->rA0rAold = s->rA0rA;
             s->rA0rA = s->sum[0];
-            if (fabs(s->rA0rA) < VSMALL_) { // :141-144
+            if (!(fabs(s->rA0rA) > VSMALL_)) { // :141-144
                 s->singular = 1;
                 s->stop = 1;
                 return;
             }
             if (s->nIterations > 0) {
-                if (fabs(s->omega) < VSMALL_) { // :153-156
+                if (!(fabs(s->omega) > VSMALL_)) { // :153-156
                     s->singular = 1;
                     s->stop = 1;
                     return;
@@ -761,7 +741,16 @@ int solve_banded(b200ldu_matrix *m, const char *solver, const char *pre, const b
         // read back the scalars (one synchronisation per solve)
         SolverScalars *hp = (SolverScalars *)((char *)pin + 1024);
         CUDA_TRY(cudaMemcpyAsync(hp, S.sc, sizeof(SolverScalars), cudaMemcpyDeviceToHost, ctx->stream));
+        unsigned long long *peerErr = (unsigned long long *)((char *)pin + 2048);
+        *peerErr = 0;
+        if (ctx->d_seq) // a bounded wait on a peer's flag gave up (engine.cuh spin_until)
+            CUDA_TRY(cudaMemcpyAsync(peerErr, ctx->d_seq + 7, sizeof(*peerErr), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (*peerErr) {
+            b200_set_error("solve: timed out waiting for a peer GPU's halo / all-reduce flag (a rank died or did not "
+                           "enter the matching solve)");
+            rc = B200LDU_ENCCL;
+        }
         if (!S.noScalars) {
             perf->initialResidual = hp->initialResidual;
             perf->finalResidual = hp->finalResidual;

@@ -68,7 +68,7 @@ def _layout(capi, mesh, centres=True, band=None):
     for what, (name, dt) in enumerate([("perm", np.int32), ("iperm", np.int32), ("sliceStart", np.int64),
                                        ("sliceW", np.uint16), ("sliceWL", np.uint16), ("col", np.uint16),
                                        ("code", np.int32), ("haloStart", np.int32), ("haloIdx", np.int32),
-                                       ("dims", np.int32)]):
+                                       ("dims", np.int32), ("cStart", np.int32), ("cblob", np.uint32)]):
         n = L.b200ldu_layout_debug_get(h, what, None, 0)
         a = np.zeros(max(n, 1), dtype=dt)
         L.b200ldu_layout_debug_get(h, what, a.ctypes.data, n)
@@ -172,106 +172,6 @@ def test_layout_rejects_bad_addressing(capi):
     assert rc == -1
 
 
-def _shared(capi, lay_handle_getter):
-    pass
-
-
-def _layout_shared(capi, mesh, centres=True, band=None):
-    """general + shared-coefficient layout arrays (host-only debug build)"""
-    L = capi.lib()
-    L.b200ldu_layout_debug_get.restype = C.c_longlong
-    L.b200ldu_layout_debug_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong]
-    L.b200ldu_layout_debug_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
-                                              C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
-    L.b200ldu_layout_debug_destroy.argtypes = [C.c_void_p]
-    if band:
-        os.environ["B200LDU_BAND_ROWS"] = str(band)
-    ps, fc = mesh.patch_start_facecells()
-    nP = len(ps) - 1
-    l = np.ascontiguousarray(mesh.lower, np.int32)
-    u = np.ascontiguousarray(mesh.upper, np.int32)
-    cc = np.ascontiguousarray(mesh.cell_centres()) if centres else None
-    h = C.c_void_p()
-    rc = L.b200ldu_layout_debug_create(mesh.nCells, mesh.nFaces, l.ctypes.data, u.ctypes.data, nP,
-                                       ps.ctypes.data if nP else None, fc.ctypes.data if nP else None,
-                                       cc.ctypes.data if cc is not None else None, C.byref(h))
-    os.environ.pop("B200LDU_BAND_ROWS", None)
-    assert rc == 0
-    names = {0: ("perm", np.int32), 1: ("iperm", np.int32), 7: ("haloStart", np.int32), 8: ("haloIdx", np.int32),
-             9: ("dims", np.int32), 10: ("vStart", np.int64), 11: ("nStart", np.int64), 12: ("VS", np.uint16),
-             13: ("WO", np.uint16), 14: ("WN", np.uint16), 15: ("colV", np.uint16), 16: ("codeV", np.int32),
-             17: ("nbr", np.uint32)}
-    out = {}
-    for what, (name, dt) in names.items():
-        n = L.b200ldu_layout_debug_get(h, what, None, 0)
-        a = np.zeros(max(n, 1), dtype=dt)
-        L.b200ldu_layout_debug_get(h, what, a.ctypes.data, n)
-        out[name] = a[:n]
-    L.b200ldu_layout_debug_destroy(h)
-    return out
-
-
-@pytest.mark.parametrize("dims,centres,band,nR", [((8, 8, 8), True, None, 1), ((9, 6, 5), False, 128, 1),
-                                                  ((12, 12, 12), True, 256, 1), ((8, 8, 8), True, 64, 4),
-                                                  ((3, 2, 1), True, None, 1)])
-def test_shared_layout_structure(capi, meshmod, dims, centres, band, nR):
-    """The shared-coefficient layout reproduces every row in reference order: owner faces
-    (own value slot), neighbour faces (ref to the owner's slot in the same slice, or to the
-    slice's extras), interface faces; each face's coefficient is stored once per slice."""
-    mesh = meshmod.hex_mesh(*dims) if nR == 1 else meshmod.decompose(dims[0], nR, 1)
-    lay = _layout_shared(capi, mesh, centres, band)
-    nPad, nBands, bandRows, nRecv, maxHalo = [int(x) for x in lay["dims"]]
-    perm, iperm = lay["perm"], lay["iperm"]
-    assert len(lay["vStart"]) == nPad // 64 + 1
-    n = mesh.nCells
-    own = [[] for _ in range(n)]
-    nei = [[] for _ in range(n)]
-    for f in range(mesh.nFaces):
-        own[mesh.lower[f]].append(f)
-        nei[mesh.upper[f]].append(f)
-    ps, fc = mesh.patch_start_facecells()
-    ifc = [[] for _ in range(n)]
-    for i, c in enumerate(fc):
-        ifc[c].append(i)
-    stored = 0
-    for s in range(nPad // 64):
-        vb, nb = int(lay["vStart"][s]), int(lay["nStart"][s])
-        nV = int(lay["vStart"][s + 1]) - vb
-        VS, WO, WN = int(lay["VS"][s]), int(lay["WO"][s]), int(lay["WN"][s])
-        band = (s * 64) // bandRows
-        halo = lay["haloIdx"][lay["haloStart"][band]:lay["haloStart"][band + 1]]
-        codes = lay["codeV"][vb:vb + nV]
-        assert nV % 2 == 0 and nV >= VS * 64 + 1
-        stored += int((codes >= 0).sum())
-
-        def target(cv):
-            return band * bandRows + cv if cv < bandRows else int(halo[cv - bandRows])
-        for q in range(64):
-            r = s * 64 + q
-            c = iperm[r]
-            colv = [int(lay["colV"][vb + j * 64 + q]) for j in range(VS)]
-            codv = [int(codes[j * 64 + q]) for j in range(VS)]
-            nbrs = [int(lay["nbr"][nb + j * 64 + q]) for j in range(WN)]
-            if c < 0:
-                assert all(x == -1 for x in codv)
-                assert all(codes[e >> 16] == -1 for e in nbrs)
-                continue
-            got_o = [(codv[j], target(colv[j])) for j in range(WO) if codv[j] != -1]
-            assert got_o == [(2 * f, int(perm[mesh.upper[f]])) for f in own[c]]
-            got_n = [(int(codes[e >> 16]), target(e & 0xffff)) for e in nbrs if codes[e >> 16] != -1]
-            assert got_n == [(2 * f, int(perm[mesh.lower[f]])) for f in nei[c]]
-            for e in nbrs:  # refs into owner slots must point at the owner's row inside this slice
-                ref = e >> 16
-                if ref < VS * 64 and codes[ref] != -1:
-                    assert s * 64 + ref % 64 == perm[mesh.lower[codes[ref] // 2]]
-            got_i = [(codv[j], target(colv[j])) for j in range(WO, VS) if codv[j] != -1]
-            assert got_i == [(-2 - i, nPad + i) for i in ifc[c]]
-    # every face stored once as an owner value, plus once per slice that only sees its neighbour side
-    assert stored >= mesh.nFaces
-    if dims == (12, 12, 12):
-        assert stored < 1.45 * mesh.nFaces  # cube-shaped slices: most faces are slice-internal
-
-
 class _RandomGraph:
     """LDU pattern of a random graph without any locality (worst case for the band tiles)."""
 
@@ -299,3 +199,48 @@ def test_layout_narrows_bands_until_the_tile_fits(capi):
     nPad, nBands, bandRows, nRecv, maxHalo = [int(x) for x in lay["dims"]]
     assert bandRows < 16384 and (bandRows + maxHalo + 2) * 16 <= 200 * 1024
     _check_layout(g, lay)
+
+
+def _decode_columns(lay):
+    """columns of every entry from the compressed blob (layout.cu 3b), as the engine decodes them"""
+    nPad, nBands, bandRows, nRecv, maxHalo = [int(x) for x in lay["dims"]]
+    spb = bandRows // 64
+    nSlices = nPad // 64
+    out = np.zeros(len(lay["col"]), np.int64)
+    blob = lay["cblob"]
+    nExc = 0
+    for s in range(nSlices):
+        base, W = int(lay["sliceStart"][s]), int(lay["sliceW"][s])
+        w0, w1 = int(lay["cStart"][s]) * 4, int(lay["cStart"][s + 1]) * 4
+        words = blob[w0:w1]
+        exc = words[4 * W:].view(np.uint16)
+        assert len(exc) % 8 == 0
+        lr0 = (s % spb) * 64
+        for j in range(W):
+            lo, hi, delta, off = (int(x) for x in words[4 * j:4 * j + 4])
+            mask = lo | (hi << 32)
+            delta = delta - (1 << 32) if delta >= (1 << 31) else delta
+            k = off
+            for q in range(64):
+                if (mask >> q) & 1:
+                    out[base + 64 * j + q] = exc[k]
+                    k += 1
+                else:
+                    out[base + 64 * j + q] = lr0 + q + delta
+            nExc += k - off
+    return out, nExc
+
+
+@pytest.mark.parametrize("dims,centres,band,nR", [((16, 16, 16), True, None, 1), ((7, 3, 5), False, None, 1),
+                                                  ((12, 12, 12), True, 256, 1), ((8, 8, 8), True, 64, 4),
+                                                  ((32, 32, 16), True, 2048, 1)])
+def test_compressed_columns_reproduce_the_columns(capi, meshmod, dims, centres, band, nR):
+    """the engine reads its columns from the compressed blob: decoding it must give back the explicit
+    16-bit column of every entry; on band-sized bricks of a hex mesh only a small part are exceptions"""
+    mesh = meshmod.hex_mesh(*dims) if nR == 1 else meshmod.decompose(dims[0], nR, 1)
+    lay = _layout(capi, mesh, centres, band)
+    got, nExc = _decode_columns(lay)
+    assert np.array_equal(got, lay["col"].astype(np.int64))
+    if dims == (32, 32, 16):
+        # 16x16x8 bricks: only references into the halo (and the rows shifted at the mesh boundary) are exceptions
+        assert nExc < 0.2 * len(got), (nExc, len(got))
