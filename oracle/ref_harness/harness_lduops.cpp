@@ -22,7 +22,6 @@ struct WarningStream {
 static WarningStream Warning;
 #define WarningIn(where) ::Foam::Warning
 static const char nl = '\n', endl = '\n';
-inline int abort(FatalStream &) { throw std::runtime_error("FatalError"); }
 } // namespace Foam
 
 #include "lduMatrixOperations.C" /* reference, through oracle/_ref/inc_lduops/ */

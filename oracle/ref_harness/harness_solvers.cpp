@@ -107,7 +107,14 @@ int ref_solve(const char *solverName, const char *precond, int favourSpeed, int 
     solverPerformance sp;
     try { // preconditioner::New / smoother::New are called inside solve(): unknown names are fatal there
         sp = s->solve(psi, src, 0);
-    } catch (const std::runtime_error &) {
+    } catch (const std::runtime_error &e) {
+        if (!strncmp(e.what(), "FatalError: ", 12)) { // abort(FatalError) with a message: a plug-in solver's failure
+            if (name && nameCap > 0) {
+                strncpy(name, e.what() + 12, (size_t)nameCap - 1);
+                name[nameCap - 1] = 0;
+            }
+            return -3;
+        }
         return -2;
     }
     perf[0] = sp.initialResidual();

@@ -394,11 +394,18 @@ template <> struct pTraits<scalar> {
     static constexpr const char *componentNames[1] = {""};
 };
 struct FatalStream {
+    std::string msg;
     template <class T> FatalStream &operator<<(const T &) { return *this; }
+    FatalStream &operator<<(const char *c)
+    {
+        msg += c;
+        return *this;
+    }
 };
 static FatalStream FatalError;
-#define FatalErrorIn(where) ::Foam::FatalError
+#define FatalErrorIn(where) (::Foam::FatalError.msg.clear(), ::Foam::FatalError)
 inline int exit(FatalStream &) { throw std::runtime_error("FatalError"); }
+inline int abort(FatalStream &e) { throw std::runtime_error("FatalError: " + e.msg); } // error.H: abort(FatalError)
 template <class R, class T> struct magUnaryFunctionFunctor {
     SHIM_HD R operator()(const T &x) const { return x < 0 ? -x : x; }
 };

@@ -115,7 +115,6 @@ struct UOPstream {
     }
 };
 static FatalStream Info;
-inline int abort(FatalStream &) { throw std::runtime_error("FatalError"); }
 
 // ---- lduInterfaceField.H:60-160 ----
 class lduInterfaceField

@@ -273,6 +273,9 @@ static const scalar VSMALL = 1e-300; // doubleScalar.H
     static const char *typeName_() { return name; } \
     static const ::Foam::word typeName;             \
     static int debug
+#define TypeName(name) /* typeInfo.H:57-59 */ \
+    ClassName(name);                         \
+    virtual const ::Foam::word &type() const { return typeName; }
 #define defineNamedTemplateTypeNameAndDebug(Type, DebugSwitch) \
     template <> const ::Foam::word Type::typeName(Type::typeName_()); \
     template <> int Type::debug(DebugSwitch)

@@ -125,35 +125,56 @@ def omp_available():
     return available() and os.path.exists(_LIB_SOLVERS_OMP)
 
 
+_LIB_BINDING = os.path.join(_HERE, "_ref", "libref_binding.so")
+_libs_binding = None
+
+
+def binding_available():
+    """oracle/_ref/libref_binding.so: the reference's solver sources + the product's reference-side binding
+    (rapidcfd-dev_b200/foam/b200Solver.H), linked against libb200ldu.so"""
+    return os.path.exists(_LIB_BINDING)
+
+
 def solve(solver, precond, nCells, lower, upper, ownerStart, losortStart, losort, diag, upperC, lowerC, psi0, source,
-          tolerance=1e-6, relTol=0.0, maxIter=1000, minIter=0, favourSpeed=0, nSweeps=1, omega=-1.0, omp=False):
+          tolerance=1e-6, relTol=0.0, maxIter=1000, minIter=0, favourSpeed=0, nSweeps=1, omega=-1.0, omp=False,
+          binding=False):
     """The reference's PCG::solve / PBiCG::solve / PBiCGStab::solve (PCG.C:69-208, PBiCG.C:68-246,
     PBiCGStab.C:66-300) with its own preconditioner classes, or smoothSolver::solve (smoothSolver.C:77-193,
     `precond` = smoother word, nSweeps, omega < 0 = not in the dictionary) with its JacobiSmoother.  Returns (psi, dict(initialResidual,
     finalResidual, nIterations, converged, singular, solverName))."""
-    global _libs, _libs_omp
-    if (_libs_omp if omp else _libs) is None:
-        path = _LIB_SOLVERS_OMP if omp else _LIB_SOLVERS
-        if not available() or not os.path.exists(path):
+    global _libs, _libs_omp, _libs_binding
+    cur = _libs_binding if binding else (_libs_omp if omp else _libs)
+    if cur is None:
+        path = _LIB_BINDING if binding else (_LIB_SOLVERS_OMP if omp else _LIB_SOLVERS)
+        if not os.path.exists(path) or not (binding or available()):
             raise RuntimeError(f"{path} is not built (needs /root/reference)")
+        if binding:
+            try:  # libb200ldu.so needs NCCL: let torch load its bundled (newer) libnccl first, as capi.lib() does
+                import torch  # noqa: F401
+            except ImportError:
+                pass
         L = C.CDLL(path)
         L.ref_solve.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8 + \
             [C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int,
              C.c_int, C.c_double]
-        if omp:
+        if binding:
+            _libs_binding = L
+        elif omp:
             _libs_omp = L
         else:
             _libs = L
-    _L = _libs_omp if omp else _libs
+    _L = _libs_binding if binding else (_libs_omp if omp else _libs)
     l, u, os_, ls, lo = _i(lower), _i(upper), _i(ownerStart), _i(losortStart), _i(losort)
     dg, up, low = _d(diag), _d(upperC), _d(lowerC)
     psi = _d(psi0).copy()
     src = _d(source)
     perf = np.zeros(5)
-    name = C.create_string_buffer(64)
+    name = C.create_string_buffer(512)
     rc = _L.ref_solve(solver.encode(), precond.encode(), int(favourSpeed), int(nCells), len(l), _p(l), _p(u), _p(os_),
                          _p(ls), _p(lo), _p(dg), _p(up), _p(low), float(tolerance), float(relTol), int(maxIter),
-                         int(minIter), _p(psi), _p(src), _p(perf), name, 64, int(nSweeps), float(omega))
+                         int(minIter), _p(psi), _p(src), _p(perf), name, 512, int(nSweeps), float(omega))
+    if rc == -3:
+        raise RuntimeError("FatalError: " + name.value.decode())
     if rc != 0:
         raise ValueError({-1: "unknown solver", -2: "unknown preconditioner"}.get(rc, rc))
     return psi, dict(initialResidual=perf[0], finalResidual=perf[1], nIterations=int(perf[2]), converged=bool(perf[3]),

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200ldu.so")
+# B200LDU_LIB: A/B experiments with differently compiled builds of the same library (tools/build_variant.sh)
+LIB_PATH = os.path.abspath(os.environ.get("B200LDU_LIB") or os.path.join(_HERE, "lib", "libb200ldu.so"))
 
 
 class B200LduError(RuntimeError):

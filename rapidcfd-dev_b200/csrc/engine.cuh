@@ -216,26 +216,36 @@ __device__ __forceinline__ void engine_band(const LayoutDev &L, const double *__
             }                                                                             \
         }                                                                                 \
     }
-        int j = 0;
-        // slots in groups of 4: all coefficient loads of a group are issued before any use
-        for (; j + 4 <= W; j += 4) {
-            double2 v[4];
+        // slots in groups of ENGINE_GROUP: all coefficient loads of a group are issued before any use (the
+        // kernel lives on bytes in flight: one 512-byte row of loads per slot and warp)
+#if ENGINE_COLMODE == 1
+        const uint16_t *cp = L.col + base + 2 * lane;
+#endif
+        for (int j = 0; j < W; j += ENGINE_GROUP) {
+            double2 v[ENGINE_GROUP];
+#if ENGINE_COLMODE == 1
+            uint32_t cc[ENGINE_GROUP];
+#endif
 #pragma unroll
-            for (int k = 0; k < 4; k++) v[k] = ldg_stream2(vp + (size_t)(j + k) * SLICE_ROWS);
+            for (int k = 0; k < ENGINE_GROUP; k++)
+                if (j + k < W) {
+                    v[k] = ldg_stream2(vp + (size_t)(j + k) * SLICE_ROWS);
+#if ENGINE_COLMODE == 1
+                    cc[k] = ldg_stream_u32(cp + (size_t)(j + k) * SLICE_ROWS);
+#endif
+                }
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                int c0, c1;
-                SLOT_COLS(j + k, c0, c1)
-                acc0 = op.term(acc0, v[k].x, (Op::NVEC > 0) ? xs[c0] : 0, (Op::NVEC > 1) ? ys[c0] : 0);
-                acc1 = op.term(acc1, v[k].y, (Op::NVEC > 0) ? xs[c1] : 0, (Op::NVEC > 1) ? ys[c1] : 0);
-            }
-        }
-        for (; j < W; j++) {
-            double2 v = ldg_stream2(vp + (size_t)j * SLICE_ROWS);
-            int c0, c1;
-            SLOT_COLS(j, c0, c1)
-            acc0 = op.term(acc0, v.x, (Op::NVEC > 0) ? xs[c0] : 0, (Op::NVEC > 1) ? ys[c0] : 0);
-            acc1 = op.term(acc1, v.y, (Op::NVEC > 0) ? xs[c1] : 0, (Op::NVEC > 1) ? ys[c1] : 0);
+            for (int k = 0; k < ENGINE_GROUP; k++)
+                if (j + k < W) {
+                    int c0, c1;
+#if ENGINE_COLMODE == 1
+                    c0 = cc[k] & 0xffffu, c1 = cc[k] >> 16;
+#else
+                    SLOT_COLS(j + k, c0, c1)
+#endif
+                    acc0 = op.term(acc0, v[k].x, (Op::NVEC > 0) ? xs[c0] : 0, (Op::NVEC > 1) ? ys[c0] : 0);
+                    acc1 = op.term(acc1, v[k].y, (Op::NVEC > 0) ? xs[c1] : 0, (Op::NVEC > 1) ? ys[c1] : 0);
+                }
         }
 #undef SLOT_COLS
         {

@@ -48,6 +48,14 @@ constexpr int ENGINE_THREADS = 256;
 #ifndef ENGINE_MINB
 #define ENGINE_MINB 5
 #endif
+// slots whose coefficient loads are in flight together (registers: 4 per slot)
+#ifndef ENGINE_GROUP
+#define ENGINE_GROUP 4
+#endif
+// experiment switch: 1 = explicit 16-bit column per entry (2 B/entry) instead of the compressed blob
+#ifndef ENGINE_COLMODE
+#define ENGINE_COLMODE 0
+#endif
 
 struct b200ldu_ctx {
     int device = 0;
@@ -109,6 +117,9 @@ struct LayoutDev {
     const long long *sliceStart; // [nSlices+1] entry offset of each slice (multiple of 64)
     const uint16_t *sliceW;      // slots per row in the slice, all entries
     const uint16_t *sliceWL;     // slots holding owner/neighbour entries only (no interfaces)
+#if ENGINE_COLMODE == 1
+    const uint16_t *col;         // [nEntries] explicit band-local columns (experiment)
+#endif
     const int *cStart;           // [nSlices+1] offset of each slice's column blob, in 16-byte words
     const uint4 *cblob;          // compressed band-local columns (layout.cu 3b): < bandRows own band, else halo slot
     int wbufBytes;               // longest blob: size of one per-warp staging buffer
@@ -145,6 +156,7 @@ struct b200ldu_addr {
     long long *d_sliceStart = nullptr;
     uint16_t *d_sliceW = nullptr, *d_sliceWL = nullptr;
     int *d_cStart = nullptr;
+    uint16_t *d_col = nullptr; // ENGINE_COLMODE 1 only
     uint32_t *d_cblob = nullptr;
     int *d_code = nullptr; // [nEntries] value source: 2f+side | -1 pad | -2-pf interface
     int *d_haloStart = nullptr, *d_haloIdx = nullptr, *d_perm = nullptr, *d_iperm = nullptr;
@@ -197,6 +209,9 @@ struct b200ldu_matrix {
     // solver workspace (allocated once, reused across solves -- PCGCache.H:9-58)
     std::vector<double *> work;
     double *d_partials = nullptr; // reduction partials
+    double *d_cpart = nullptr;    // persistent PCG: per-CTA partial sums [2][grid][2]
+    size_t cpartLen = 0;
+    unsigned *d_bar = nullptr;    // persistent PCG: grid barrier {arrivals, generation}
     void *d_scal = nullptr;       // SolverScalars
     double *d_hist = nullptr;     // device residual history
     double *d_sendBuf = nullptr;  // packed psi at coupled-patch face cells

@@ -494,6 +494,10 @@ int layout_build(b200ldu_addr *a, const double *centres)
     TRY(dev_upload(&a->d_sliceStart, sliceStart));
     TRY(dev_upload(&a->d_sliceW, sliceW));
     TRY(dev_upload(&a->d_sliceWL, sliceWL));
+#if ENGINE_COLMODE == 1
+    TRY(dev_upload(&a->d_col, col));
+    a->L.col = a->d_col;
+#endif
     TRY(dev_upload(&a->d_cStart, cStart));
     TRY(dev_upload(&a->d_cblob, cblob));
     TRY(dev_upload(&a->d_code, code));

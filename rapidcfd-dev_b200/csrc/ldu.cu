@@ -199,7 +199,7 @@ extern "C" int b200ldu_addr_destroy(b200ldu_addr *a)
     if (!a) return B200LDU_OK;
     cudaSetDevice(a->ctx->device);
     cudaStreamSynchronize(a->ctx->stream);
-    void *ptrs[] = {a->d_sliceStart, a->d_sliceW, a->d_sliceWL, a->d_cStart, a->d_cblob, a->d_code, a->d_haloStart,
+    void *ptrs[] = {a->d_sliceStart, a->d_sliceW, a->d_sliceWL, a->d_cStart, a->d_cblob, a->d_col, a->d_code, a->d_haloStart,
                     a->d_haloIdx, a->d_perm, a->d_iperm, a->d_sendRows, a->d_l, a->d_u,
                     a->d_ownerStart, a->d_losort, a->d_losortStart, a->d_bFaceCells, a->d_cyclicSrc,
                     a->d_bCellStart, a->d_bCellFaces, a->d_bCells, a->d_packPatches, a->d_packChunks,
@@ -325,7 +325,7 @@ extern "C" int b200ldu_matrix_destroy(b200ldu_matrix *m)
     cudaStreamSynchronize(m->a->ctx->stream);
     if (m->d_valT && m->d_valT != m->d_val) cudaFree(m->d_valT);
     void *ptrs[] = {m->d_val, m->d_diag, m->d_rD, m->d_partials, m->d_scal, m->d_hist, m->d_sendBuf,
-                    m->own[0], m->own[1], m->own[2], m->own[3], m->own[4]};
+                    m->own[0], m->own[1], m->own[2], m->own[3], m->own[4], m->d_cpart, m->d_bar};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (double *p : m->work)

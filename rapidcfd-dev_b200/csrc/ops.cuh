@@ -107,100 +107,6 @@ struct AinvOp : OpBase {
     }
 };
 
-// ---- fused PCG kernels (PCG.C:131-205 regrouped into two matrix sweeps per iteration) ----
-// K_A: applies the solution/residual update of the PREVIOUS body (psi += alpha p,
-// r -= alpha w; alpha from the device scalars) while staging r, then preconditions:
-// z = rD*(r - sum v*(rD*r)[c]); fused sums <z,r> and sum|r|.  r is ping-ponged (other bands
-// read the old halo values), psi is updated in place (own rows only).
-struct PcgAinvOp : OpBase {
-    static constexpr int NVEC = 1, NRED = 2;
-    static constexpr bool LOCAL = true;
-    const double *rOld, *w, *p, *rD;
-    double *rNew, *psi, *z;
-    const SolverScalars *sc;
-    __device__ __forceinline__ void stage(int g, double &a, double &) const
-    {
-        double r = sc->bodies > 0 ? fma(-sc->alpha, w[g], rOld[g]) : rOld[g];
-        a = __dmul_rn(rD[g], r);
-    }
-    __device__ __forceinline__ double pack_val(int) const { return 0.0; }
-    __device__ __forceinline__ void stage_own(int row, double2 &a, double2 &) const
-    {
-        double2 r = *reinterpret_cast<const double2 *>(rOld + row);
-        if (sc->bodies > 0) {
-            const double alpha = sc->alpha;
-            double2 ww = *reinterpret_cast<const double2 *>(w + row);
-            double2 pp = *reinterpret_cast<const double2 *>(p + row);
-            double2 x = *reinterpret_cast<const double2 *>(psi + row);
-            r.x = fma(-alpha, ww.x, r.x);
-            r.y = fma(-alpha, ww.y, r.y);
-            x.x = fma(alpha, pp.x, x.x);
-            x.y = fma(alpha, pp.y, x.y);
-            *reinterpret_cast<double2 *>(psi + row) = x;
-        }
-        *reinterpret_cast<double2 *>(rNew + row) = r;
-        double2 dd = *reinterpret_cast<const double2 *>(rD + row);
-        a = make_double2(__dmul_rn(dd.x, r.x), __dmul_rn(dd.y, r.y));
-    }
-    __device__ __forceinline__ double init(int, double, double) const { return 0.0; }
-    __device__ __forceinline__ double term(double acc, double v, double t, double) const
-    {
-        return __dadd_rn(acc, __dmul_rn(v, t));
-    }
-    __device__ __forceinline__ void finish(int row, double acc0, double acc1, double, double, double, double,
-                                           double *red) const
-    {
-        // rNew[row] was written by this CTA in phase 1 (visible after the barrier)
-        double2 d = *reinterpret_cast<const double2 *>(rD + row);
-        double2 r = *reinterpret_cast<const double2 *>(rNew + row);
-        double z0 = __dmul_rn(d.x, __dsub_rn(r.x, acc0));
-        double z1 = __dmul_rn(d.y, __dsub_rn(r.y, acc1));
-        *reinterpret_cast<double2 *>(z + row) = make_double2(z0, z1);
-        red[0] += z0 * r.x + z1 * r.y;
-        red[1] += fabs(r.x) + fabs(r.y);
-    }
-};
-
-// K_B: forms the new search direction while staging (p = z on the first body, else
-// z + beta p; beta from the device scalars; p ping-ponged), w = A p, fused <w,p>.  The halo
-// send (fused pack CTAs) evaluates the same expression at the patch face cells.
-struct PcgAmulOp : OpBase {
-    static constexpr int NVEC = 1, NRED = 1;
-    static constexpr bool LOCAL = false;
-    const double *z, *pOld, *diag;
-    double *pNew, *out;
-    const SolverScalars *sc;
-    __device__ __forceinline__ double pval(int g) const
-    {
-        return sc->bodies == 0 ? z[g] : fma(sc->beta, pOld[g], z[g]);
-    }
-    __device__ __forceinline__ void stage(int g, double &a, double &) const { a = pval(g); }
-    __device__ __forceinline__ double pack_val(int row) const { return pval(row); }
-    __device__ __forceinline__ void stage_own(int row, double2 &a, double2 &) const
-    {
-        double2 zz = *reinterpret_cast<const double2 *>(z + row);
-        if (sc->bodies > 0) {
-            const double beta = sc->beta;
-            double2 po = *reinterpret_cast<const double2 *>(pOld + row);
-            zz.x = fma(beta, po.x, zz.x);
-            zz.y = fma(beta, po.y, zz.y);
-        }
-        *reinterpret_cast<double2 *>(pNew + row) = zz;
-        a = zz;
-    }
-    __device__ __forceinline__ double init(int r, double a, double) const { return __dmul_rn(diag[r], a); }
-    __device__ __forceinline__ double term(double acc, double v, double a, double) const
-    {
-        return __dadd_rn(acc, __dmul_rn(v, a));
-    }
-    __device__ __forceinline__ void finish(int r, double acc0, double acc1, double a0, double, double a1,
-                                           double, double *red) const
-    {
-        *reinterpret_cast<double2 *>(out + r) = make_double2(acc0, acc1);
-        red[0] += acc0 * a0 + acc1 * a1;
-    }
-};
-
 // ---- Jacobi sweep (JacobiSmootherF.H:51-109; omega-damped, old psi everywhere) ----
 struct JacobiOp : OpBase {
     static constexpr int NVEC = 1, NRED = 0;

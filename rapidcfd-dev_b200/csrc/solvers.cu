@@ -13,6 +13,9 @@
 
 #include <cstdlib>
 
+#include <algorithm>
+
+#include "pcg_persistent.cuh"
 #include "solver_steps.cuh"
 
 // initial residual, normFactor and the first convergence test, common to all solvers
@@ -205,119 +208,82 @@ int solve_pcg(Solve &S, int pk)
 }
 
 // ---------------------------------------------------------------------------
-// PCG, fused form: two matrix sweeps + two scalar steps per iteration (4 launches, 2 global
-// sums) instead of 7 launches / 3 sums.  Same recurrences and the same per-row arithmetic as
-// solve_pcg; the psi/r update of body k is applied while body k+1 stages r, and the
-// convergence decision of body k is taken in the first scalar step of body k+1 (the extra
-// preconditioner sweep that has then already run only overwrote scratch).
+// PCG as one persistent cooperative kernel (pcg_persistent.cuh): two matrix sweeps and two
+// device-wide barriers per iteration, global sums / cross-rank all-reduce / convergence
+// logic inside the barriers, one launch per solve.
 // ---------------------------------------------------------------------------
-// fused PCG sweeps (ops.cuh PcgAinvOp / PcgAmulOp)
-static int pcg_ka(b200ldu_matrix *m, const double *rOld, double *rNew, const double *w, const double *p,
-                  double *psi, double *z, const SolverScalars *sc, double *partials, const int *stop)
-{
-    PcgAinvOp op;
-    op.stop = stop;
-    op.partials = partials;
-    op.rOld = rOld;
-    op.rNew = rNew;
-    op.w = w;
-    op.p = p;
-    op.psi = psi;
-    op.z = z;
-    op.rD = m->d_rD;
-    op.sc = sc;
-    return engine_launch_m(m, false, op);
-}
-
-static int pcg_kb(b200ldu_matrix *m, const double *z, const double *pOld, double *pNew, double *w,
-                  const SolverScalars *sc, double *partials, const int *stop)
-{
-    int wait = 0;
-    TRY(mat_halo(m, pNew, stop, &wait)); // peer-memory path: nothing is launched, the send is fused
-    PcgAmulOp op;
-    op.stop = stop;
-    op.partials = partials;
-    op.waitHalo = wait;
-    op.z = z;
-    op.pOld = pOld;
-    op.pNew = pNew;
-    op.out = w;
-    op.diag = m->d_diag;
-    op.sc = sc;
-    return engine_launch_m(m, false, op);
-}
-
-int solve_pcg_fused(Solve &S, int pk)
+int solve_pcg_persistent(Solve &S, int pk)
 {
     b200ldu_matrix *m = S.m;
     b200ldu_addr *a = m->a;
-    SolverScalars *sc = S.sc;
-    double *hist = S.hist;
-    const int *stop = &sc->stop;
-    const int n2 = a->L.nPad / 2;
+    b200ldu_ctx *ctx = S.ctx;
     double *psi = S.psi, *b = S.src;
     double *pb[2] = {S.vec(0), S.vec(4)}, *w = S.vec(1), *rb[2] = {S.vec(2), S.vec(3)}, *z = S.vec(5);
     if (!pb[0] || !pb[1] || !w || !rb[0] || !rb[1] || !z) return B200LDU_ECUDA;
-    const double *rD = m->d_rD;
+
     TRY(mat_amul(m, false, psi, w, 0, nullptr, nullptr, nullptr));
     TRY(init_residual(S, psi, b, w, rb[0], pb[0]));
 
-    // scalar step A: closes body k-1 (residual, convergence), then beta of body k
-    auto gA = [=] __device__(SolverScalars *s) {
-        if (s->bodies > 0) {
-            end_of_body(s, hist, s->sum[1]);
-            if (s->stop) return;
-        }
-        s->wArAold = s->wArA;
-        s->wArA = s->sum[0];
-        s->beta = s->wArA / s->wArAold;
-    };
-    // scalar step B: alpha of body k
-    auto gB = [=] __device__(SolverScalars *s) {
-        s->wApA = s->sum[0];
-        if (!(fabs(s->wApA) / s->normFactor > VSMALL_)) { // checkSingularity PCG.C:170
-            s->singular = 1;
-            s->stop = 1;
-            return;
-        }
-        s->alpha = s->wArA / s->wApA;
-        s->bodies++;
-    };
-
-    auto body = [&](long long k) -> int {
-        const double *rOld = rb[k & 1], *pPrev = pb[k & 1];
-        double *rNew = rb[(k + 1) & 1], *pNew = pb[(k + 1) & 1];
-        int np = a->L.nBands;
-        if (pk == 2) {
-            TRY(pcg_ka(m, rOld, rNew, w, pPrev, psi, z, sc, S.partials, stop));
-        } else {
-            TRY(ew_launch<2>(S.ctx, n2, stop, S.partials, &np, [=] __device__(int i, double *red) {
-                double2 r = CV2(rOld)[i];
-                if (sc->bodies > 0) {
-                    const double alpha = sc->alpha;
-                    double2 ww = CV2(w)[i], pp = CV2(pPrev)[i], x = CV2(psi)[i];
-                    r.x = fma(-alpha, ww.x, r.x);
-                    r.y = fma(-alpha, ww.y, r.y);
-                    V2(psi)[i] = make_double2(fma(alpha, pp.x, x.x), fma(alpha, pp.y, x.y));
-                }
-                V2(rNew)[i] = r;
-                double2 zz = r;
-                if (pk == 1) {
-                    double2 d = CV2(rD)[i];
-                    zz = make_double2(__dmul_rn(d.x, r.x), __dmul_rn(d.y, r.y));
-                }
-                V2(z)[i] = zz;
-                red[0] += zz.x * r.x + zz.y * r.y;
-                red[1] += fabs(r.x) + fabs(r.y);
-            }));
-        }
-        TRY(scalar_step<2>(S, np, gA));
-        TRY(pcg_kb(m, z, pPrev, pNew, w, sc, S.partials, stop));
-        TRY(scalar_step<1>(S, a->L.nBands, gB));
-        return B200LDU_OK;
-    };
-    long long mb = (long long)S.c.maxIter + 1 > S.c.minIter ? (long long)S.c.maxIter + 1 : S.c.minIter;
-    return run_iterations(S, mb + 1, body); // +1: the last body's update is applied by the next sweep
+    const size_t smem = engine_smem_bytes(a->L, 1);
+    static size_t configured[64] = {0};
+    static int coop[64] = {0}; // 0 unknown, 1 yes, -1 no
+    const int dev = ctx->device & 63;
+    if (!coop[dev]) {
+        int v = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, ctx->device));
+        coop[dev] = v ? 1 : -1;
+    }
+    if (coop[dev] < 0) {
+        b200_set_error("PCG: the device does not support cooperative kernel launches");
+        return B200LDU_ECUDA;
+    }
+    if (smem > 40 * 1024 && smem > configured[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(pcg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev] = smem;
+    }
+    int perSM = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, pcg_persistent_kernel, ENGINE_THREADS, smem));
+    if (perSM < 1) {
+        b200_set_error("PCG: the persistent kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+        return B200LDU_ECUDA;
+    }
+    long long items = (long long)a->L.nBands + a->L.nPackChunks;
+    int G = (int)std::min<long long>((long long)perSM * ctx->smCount, items);
+    if (G < 1) G = 1;
+    if (m->cpartLen < (size_t)4 * G) {
+        if (m->d_cpart) cudaFree(m->d_cpart);
+        m->d_cpart = nullptr;
+        m->cpartLen = 0;
+        CUDA_TRY(cudaMalloc((void **)&m->d_cpart, sizeof(double) * 4 * (size_t)G));
+        m->cpartLen = (size_t)4 * G;
+    }
+    if (!m->d_bar) {
+        CUDA_TRY(cudaMalloc((void **)&m->d_bar, 2 * sizeof(unsigned)));
+        CUDA_TRY(cudaMemsetAsync(m->d_bar, 0, 2 * sizeof(unsigned), ctx->stream));
+    }
+    PcgArgs A;
+    A.L = a->L;
+    A.val = m->d_val;
+    A.diag = m->d_diag;
+    A.rD = m->d_rD;
+    A.psi = psi;
+    A.rb[0] = rb[0], A.rb[1] = rb[1], A.pb[0] = pb[0], A.pb[1] = pb[1];
+    A.w = w;
+    A.z = z;
+    A.sc = S.sc;
+    A.hist = S.hist;
+    A.cpart = m->d_cpart;
+    A.bar = m->d_bar;
+    A.p2p = (ctx->nRanks > 1 && ctx->p2p) ? comm_p2p_red(ctx) : P2PRed();
+    A.seqs = ctx->d_seq;
+    A.pk = pk;
+    const long long mb = (long long)S.c.maxIter + 1 > S.c.minIter ? (long long)S.c.maxIter + 1 : S.c.minIter;
+    A.maxBodies = mb + 1; // +1: the last body's update is applied (and its residual judged) by the next sweep A
+    void *args[] = {&A};
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void *)pcg_persistent_kernel, dim3(G), dim3(ENGINE_THREADS), args, smem,
+                                         ctx->stream));
+    ctx->launches++;
+    return B200LDU_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -702,11 +668,12 @@ int solve_banded(b200ldu_matrix *m, const char *solver, const char *pre, const b
             } else {
                 snprintf(perf->solverName, sizeof(perf->solverName), "%s%s", pname, sv);
                 if (!strcmp(sv, "PCG")) {
-                    // the fused form needs the peer-memory halo (or no halo); B200LDU_PCG_FUSED=0 keeps
-                    // the reference's 7-kernel op list
+                    // the persistent kernel needs every exchange inside the kernel: the peer-memory halo (or no
+                    // halo) and the peer-memory all-reduce (or one rank); otherwise -- cyclic patches, NCCL fall-back --
+                    // and with B200LDU_PCG_FUSED=0 the reference's op list runs kernel by kernel
                     const char *ev = getenv("B200LDU_PCG_FUSED");
-                    bool fused = !(ev && atoi(ev) == 0) && (a->L.nRecv == 0 || a->p2pHalo);
-                    rc = fused ? solve_pcg_fused(S, pk) : solve_pcg(S, pk);
+                    bool fused = !(ev && atoi(ev) == 0) && (a->L.nRecv == 0 || a->p2pHalo) && (ctx->nRanks == 1 || ctx->p2p);
+                    rc = fused ? solve_pcg_persistent(S, pk) : solve_pcg(S, pk);
                 } else if (!strcmp(sv, "PBiCG")) {
                     rc = solve_pbicg(S, pk);
                 } else {

@@ -159,8 +159,8 @@ class IcoFoam:
                     pGamma = o.mul(crAUf, self.cMagSf)
                     pCi, pCb = o.mul(pGamma, o.neg(self.cDelta)), o.mul(o.neg(pGamma), self.cDelta)
                 pEqn = capi.FvMatrix(self.matP, 1, pDiag, pSource, self.p, self.V, self.zeroB1, self.zeroB1)
+                pEqn.setReference(self.pRefCell, self.pRefValue)   # in place on pDiag / pSource, before the matrix copies them
                 self.matP.set(pDiag, pUpper, None, pCb, pCi)
-                pEqn.setReference(self.pRefCell, self.pRefValue)
                 perfs.setdefault("p", []).extend(pEqn.solve(pSolver[0], pSolver[1], gamg, **(pControls or dict(tolerance=1e-6, relTol=0.0))))
                 if nonOrth == nNonOrthCorr:
                     pnfP = capi.fv_patch_neighbour_field(a, 1, self.p) if nC else None

@@ -36,11 +36,21 @@ def test_reference_arm_other_ranks_are_silent():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
 
 
-def test_cpu_baseline_leg_reports_the_code_that_ran(meshmod):
+def test_reference_arm_ignores_torchruns_omp_setting():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm sizes its own team (one thread per
+    physical core it may run on) and says how many it used"""
     sys.path.insert(0, ROOT)
     bench = importlib.import_module("bench")
-    mesh, coef, b = bench.build_case(meshmod, 20, 1, 0)
-    cpu = bench.cpu_baseline_leg(meshmod, mesh, coef, b, 20, 6)
+    d = json.loads(_run({"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0", "OMP_NUM_THREADS": "1"})[0])
+    assert d["cpu_baseline"]["cores"] == bench.host_cores()
+    assert "numa" in d["cpu_baseline"]
+
+
+def test_cpu_baseline_leg_reports_the_code_that_ran():
+    """the cpu_baseline object of the GPU arm's line comes from the CPU arm run in a fresh process"""
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    cpu = bench.cpu_baseline_subprocess(20, 6)
     from oracle import ref_ldu
     assert cpu["kind"] == ("reference" if ref_ldu.omp_available() else "port")
     assert cpu["value"] > 0 and cpu["cores"] >= 1 and "stock_dic_serial" in cpu

@@ -82,9 +82,14 @@ def test_matrix_ops_bit_exact(gpu, meshmod, orc, dims, kind, centres, band):
     cs.close()
 
 
-def _cmp_hist(h, href, first=30, rtol=1e-9):
+def _cmp_hist(h, href, first=30, rtol=1e-9, floor=0.0):
+    """the documented contract: normalised residual per iteration within rel 1e-9 over the first 30 iterations.
+    `floor`: entries below it are compared against the floor instead -- the bi-conjugate recurrences are held to
+    1e-9 while the residual is above 1e-8; below that both sides are rounding noise of the recurrence (measured:
+    tools/diag_hist.py, profiles/r02_hist_deviation.txt: <= 1.3e-11 above the floor, 1.6e-9 at a residual of 7e-11)"""
     k = min(first, len(h), len(href))
-    np.testing.assert_allclose(h[:k], href[:k], rtol=rtol, atol=0)
+    h, href = np.asarray(h[:k]), np.asarray(href[:k])
+    np.testing.assert_allclose(h, href, rtol=rtol, atol=rtol * floor)
 
 
 @pytest.mark.parametrize("pre", ["none", "diagonal", "DIC"])
@@ -144,7 +149,7 @@ def test_asym_solver_history(gpu, meshmod, orc, solver, pre):
         if not quirk:
             assert abs(perf.nIterations - pr.nIterations) <= 1
             np.testing.assert_allclose(psi.cpu().numpy(), xs, atol=1e-6)
-        _cmp_hist(hist, href, first=10, rtol=1e-5)
+        _cmp_hist(hist, href, first=30, rtol=1e-9, floor=1e-8)
     cs.close()
 
 
@@ -356,8 +361,8 @@ def test_cyclic_interfaces(gpu, meshmod, orc, kind):
     rhs = om.amul(x)
     solvers = (("PCG", "DIC"), ("PCG", "none")) if kind == "P" else (("PBiCG", "DILU"), ("PBiCGStab", "DILU"))
     for solver, pre in solvers + (("smoothSolver", "GaussSeidel"),):
-        # 120 cells: the recurrences reach rounding level within ~20 iterations, so the history is
-        # compared over the first 10 at 1e-5 (a wrong or missing interface term shows at O(1))
+        # 120 cells: the recurrences reach rounding level within ~20 iterations; the history is held to the
+        # documented 1e-9 while the residual is above 1e-8 (a wrong or missing interface term shows at O(1))
         smooth = solver == "smoothSolver"  # damped Jacobi crawls on the Laplacian: fixed 60 sweeps there
         ctl = dict(tolerance=1e-7, maxIter=60 if smooth else 400)
         psi_ref, pr, href = om.solve(solver, pre, np.zeros(m.nCells), rhs, **ctl)
@@ -365,7 +370,7 @@ def test_cyclic_interfaces(gpu, meshmod, orc, kind):
         perf, hist = mat.solve(solver, pre, psi, t(rhs), histCap=512, **ctl)
         assert perf.converged == pr.converged and (smooth or perf.converged)
         assert abs(perf.nIterations - pr.nIterations) <= 2, (solver, perf.nIterations, pr.nIterations)
-        _cmp_hist(hist, href, first=10, rtol=1e-5)
+        _cmp_hist(hist, href, first=30, rtol=1e-9, floor=1e-8)
         np.testing.assert_allclose(psi.cpu().numpy(), psi_ref, rtol=0, atol=1e-5)
     with pytest.raises(Exception, match="cyclic"):
         capi.GamgAgglomeration(addr, np.ones(m.nFaces), 4)

@@ -207,7 +207,8 @@ def test_gpu_solvers_vs_reference_vectors(gpu, meshmod, orc, ref_golden, name, d
     k = min(len(gh), len(hist) - 1, 10 if solver.startswith("PBiCG") else 12)
     if solver == "PBiCGStab":
         k = min(k, len(hist) - 2)   # see the oracle test above
-    np.testing.assert_allclose(hist[1:k + 1], gh[:k], rtol=1e-5 if solver.startswith("PBiCG") else 1e-9, atol=0)
+    # 1e-9 while the residual is above 1e-8 (below it the bi-conjugate recurrences are rounding noise on both sides)
+    np.testing.assert_allclose(hist[1:k + 1], gh[:k], rtol=1e-9, atol=1e-17 if not solver.startswith("PBiCG") else 1e-17)
     np.testing.assert_allclose(psi.cpu().numpy(), ref_golden[f"{name}.psi"], rtol=0, atol=5e-6)
     mat.close()
     addr.close()
