@@ -132,7 +132,7 @@ __device__ __forceinline__ void engine_band(const LayoutDev &L, const double *__
                                             const int band, double *smem, double *red, const HaloWait hw)
 {
     const int rowBase = band * L.bandRows;
-    const int stride = (L.bandRows + L.maxHalo + 1) & ~1; // keep the second tile 16-byte aligned
+    const int stride = L.tileLen; // even: keeps the second tile 16-byte aligned
     double *xs = smem;
     double *ys = smem + ((Op::NVEC > 1) ? stride : 0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -144,11 +144,17 @@ __device__ __forceinline__ void engine_band(const LayoutDev &L, const double *__
 
     // ---- phase 1: stage the band's vector tile + halo ----
     if (Op::NVEC > 0) {
+        const uint32_t *rowPos = L.rowPos + (rowBase >> 1);
         for (int i = tid; i < (L.bandRows >> 1); i += ENGINE_THREADS) {
             double2 a, b = make_double2(0, 0);
             op.stage_own(rowBase + 2 * i, a, b);
-            reinterpret_cast<double2 *>(xs)[i] = a;
-            if (Op::NVEC > 1) reinterpret_cast<double2 *>(ys)[i] = b;
+            const uint32_t pp = __ldg(rowPos + i); // tile positions of rows 2i, 2i+1
+            xs[pp & 0xffffu] = a.x;
+            xs[pp >> 16] = a.y;
+            if (Op::NVEC > 1) {
+                ys[pp & 0xffffu] = b.x;
+                ys[pp >> 16] = b.y;
+            }
         }
         const int hs = L.haloStart[band], hn = L.haloStart[band + 1] - hs;
         // peer-memory halo: bands that reference received values wait for the neighbours' arrival
@@ -164,8 +170,9 @@ __device__ __forceinline__ void engine_band(const LayoutDev &L, const double *__
                 a = __ldcg(hw.remoteTail + (g - L.nPad));
             else
                 op.stage(g, a, b);
-            xs[L.bandRows + i] = a;
-            if (Op::NVEC > 1) ys[L.bandRows + i] = b;
+            const int hp = __ldg(L.haloPos + hs + i);
+            xs[hp] = a;
+            if (Op::NVEC > 1) ys[hp] = b;
         }
         __syncthreads();
     }
@@ -186,26 +193,24 @@ __device__ __forceinline__ void engine_band(const LayoutDev &L, const double *__
         const int Wall = L.sliceW[s];
         const int W = Op::LOCAL ? L.sliceWL[s] : Wall;
         const uint4 *meta = reinterpret_cast<const uint4 *>(buf);
-        const uint16_t *exc = reinterpret_cast<const uint16_t *>(buf + 16 * Wall);
+        const uint32_t posw = reinterpret_cast<const uint32_t *>(buf + 16 * Wall)[lane];
+        const int p0 = posw & 0xffffu, p1 = posw >> 16; // tile positions of this lane's two rows
+        const uint16_t *exc = reinterpret_cast<const uint16_t *>(buf + 16 * Wall + 2 * SLICE_ROWS);
         const int lr = sl * SLICE_ROWS + 2 * lane; // local row of this lane's first row
         double acc0, acc1;
-        {
-            const double2 a = (Op::NVEC > 0) ? *reinterpret_cast<const double2 *>(xs + lr) : make_double2(0, 0);
-            const double2 b = (Op::NVEC > 1) ? *reinterpret_cast<const double2 *>(ys + lr) : make_double2(0, 0);
-            acc0 = op.init(rowBase + lr, a.x, b.x);
-            acc1 = op.init(rowBase + lr + 1, a.y, b.y);
-        }
+        acc0 = op.init(rowBase + lr, (Op::NVEC > 0) ? xs[p0] : 0, (Op::NVEC > 1) ? ys[p0] : 0);
+        acc1 = op.init(rowBase + lr + 1, (Op::NVEC > 0) ? xs[p1] : 0, (Op::NVEC > 1) ? ys[p1] : 0);
         const double *vp = val + base + 2 * lane;
         const unsigned sh = (2u * lane) & 31u;
         const unsigned lowMask = (1u << sh) - 1u;
-        // columns of slot j for this lane's two rows: regular rows sit at (local row + delta), the others
+        // columns of slot j for this lane's two rows: regular rows sit at (the row's tile position + delta), the others
         // read their 16-bit column from the slice's exception list
 #define SLOT_COLS(J, C0, C1)                                                              \
     {                                                                                     \
         const uint4 md_ = meta[J];                                                        \
         const unsigned word_ = lane < 16 ? md_.x : md_.y;                                 \
-        C0 = lr + (int)md_.z;                                                             \
-        C1 = C0 + 1;                                                                      \
+        C0 = p0 + (int)md_.z;                                                             \
+        C1 = p1 + (int)md_.z;                                                             \
         if (md_.x | md_.y) {                                                              \
             const unsigned two_ = (word_ >> sh) & 3u;                                     \
             if (two_) {                                                                   \
@@ -251,8 +256,8 @@ __device__ __forceinline__ void engine_band(const LayoutDev &L, const double *__
         {
             // the lane's own tile values again (not kept in registers across the slot loop)
             const volatile double *xv = xs, *yv = ys;
-            const double a0 = (Op::NVEC > 0) ? xv[lr] : 0, a1 = (Op::NVEC > 0) ? xv[lr + 1] : 0;
-            const double b0 = (Op::NVEC > 1) ? yv[lr] : 0, b1 = (Op::NVEC > 1) ? yv[lr + 1] : 0;
+            const double a0 = (Op::NVEC > 0) ? xv[p0] : 0, a1 = (Op::NVEC > 0) ? xv[p1] : 0;
+            const double b0 = (Op::NVEC > 1) ? yv[p0] : 0, b1 = (Op::NVEC > 1) ? yv[p1] : 0;
             op.finish(rowBase + lr, acc0, acc1, a0, b0, a1, b1, red);
         }
         __syncwarp(); // the buffer is overwritten by the copy issued in the next iteration
@@ -325,7 +330,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, ENGINE_MINB) engine_kernel(con
 
 inline size_t engine_smem_bytes(const LayoutDev &L, int nvec)
 {
-    return sizeof(double) * (size_t)((L.bandRows + L.maxHalo + 1) & ~1) * (size_t)nvec +
+    return sizeof(double) * (size_t)L.tileLen * (size_t)nvec +
            (size_t)(ENGINE_THREADS / 32) * 2 * (size_t)L.wbufBytes;
 }
 

@@ -125,6 +125,9 @@ struct LayoutDev {
     int wbufBytes;               // longest blob: size of one per-warp staging buffer
     const int *haloStart;        // [nBands+1]
     const int *haloIdx;          // banded extended index: < nPad local row, else nPad + recv slot
+    const uint16_t *haloPos;     // tile position of every halo column
+    const uint32_t *rowPos;      // tile positions of rows 2i, 2i+1 (two u16)
+    int tileLen;                 // tile length in doubles (even; >= bandRows + halo of any band)
     const int *perm;             // [nCells] caller cell -> banded row
     const int *iperm;            // [nPad]  banded row -> caller cell, -1 padding
     // peer-memory halo (null/0 when the exchange goes through NCCL into the vector's own tail)
@@ -156,6 +159,7 @@ struct b200ldu_addr {
     long long *d_sliceStart = nullptr;
     uint16_t *d_sliceW = nullptr, *d_sliceWL = nullptr;
     int *d_cStart = nullptr;
+    uint16_t *d_haloPos = nullptr, *d_rowPos = nullptr;
     uint16_t *d_col = nullptr; // ENGINE_COLMODE 1 only
     uint32_t *d_cblob = nullptr;
     int *d_code = nullptr; // [nEntries] value source: 2f+side | -1 pad | -2-pf interface
@@ -185,6 +189,7 @@ struct b200ldu_addr {
     std::vector<uint16_t> dbg_sliceW, dbg_sliceWL, dbg_col;
     std::vector<int> dbg_code, dbg_haloStart, dbg_haloIdx, dbg_cStart;
     std::vector<uint32_t> dbg_cblob;
+    std::vector<uint16_t> dbg_rowPos, dbg_haloPos;
     // workspace pool for caller-order entry points (banded vectors)
     std::vector<double *> pool;
     long long vecLen = 0; // nPad + nRecv (padded to even)

@@ -15,7 +15,7 @@
 
 #include <algorithm>
 
-#include "pcg_persistent.cuh"
+#include "pcg_fused2.cuh"
 #include "solver_steps.cuh"
 
 // initial residual, normFactor and the first convergence test, common to all solvers
@@ -208,15 +208,45 @@ int solve_pcg(Solve &S, int pk)
 }
 
 // ---------------------------------------------------------------------------
-// PCG as one persistent cooperative kernel (pcg_persistent.cuh): two matrix sweeps and two
-// device-wide barriers per iteration, global sums / cross-rank all-reduce / convergence
-// logic inside the barriers, one launch per solve.
+// PCG, fused form (pcg_fused2.cuh): two launches per iteration -- the AINV sweep and the Amul sweep -- each
+// with the scalar step of the PREVIOUS sweep (fixed-order sum of the per-CTA partials, peer-memory all-reduce,
+// alpha / beta / convergence test) in its prologue.  Same recurrences and per-row arithmetic as solve_pcg; the
+// psi/r update of body k is applied while body k+1 stages r.
 // ---------------------------------------------------------------------------
-int solve_pcg_persistent(Solve &S, int pk)
+__global__ void pcg2_init_kernel(PcgCarry *c, const SolverScalars *sc, const unsigned long long *seq)
+{
+    PcgCarry h;
+    h.wArA = GREAT_, h.wArAold = GREAT_, h.wApA = 0, h.alpha = 0, h.beta = 0; // PCG.C:88
+    h.finalResidual = sc->initialResidual;
+    h.rseq = seq ? *seq : 0;
+    h.nIterations = 0, h.bodies = 0, h.converged = sc->converged, h.singular = 0, h.stop = sc->stop, h.pad = 0;
+    c[0] = h;
+    c[1] = h;
+}
+
+template <class Op, int SWEEP>
+static int pcg2_launch(b200ldu_matrix *m, int G, const Op &op, const Pcg2Args &A)
+{
+    b200ldu_addr *a = m->a;
+    const size_t smem = engine_smem_bytes(a->L, 1);
+    static size_t configured[64] = {0};
+    const int dev = a->ctx->device & 63;
+    if (smem > 40 * 1024 && smem > configured[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(pcg2_kernel<Op, SWEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev] = smem;
+    }
+    pcg2_kernel<Op, SWEEP><<<G, ENGINE_THREADS, smem, a->ctx->stream>>>(a->L, m->d_val, op, A);
+    a->ctx->launches++;
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}
+
+int solve_pcg_fused(Solve &S, int pk)
 {
     b200ldu_matrix *m = S.m;
     b200ldu_addr *a = m->a;
     b200ldu_ctx *ctx = S.ctx;
+    const int *stop = &S.sc->stop;
     double *psi = S.psi, *b = S.src;
     double *pb[2] = {S.vec(0), S.vec(4)}, *w = S.vec(1), *rb[2] = {S.vec(2), S.vec(3)}, *z = S.vec(5);
     if (!pb[0] || !pb[1] || !w || !rb[0] || !rb[1] || !z) return B200LDU_ECUDA;
@@ -224,66 +254,56 @@ int solve_pcg_persistent(Solve &S, int pk)
     TRY(mat_amul(m, false, psi, w, 0, nullptr, nullptr, nullptr));
     TRY(init_residual(S, psi, b, w, rb[0], pb[0]));
 
+    // fixed grid: one CTA per SM slot (never more CTAs than bands)
     const size_t smem = engine_smem_bytes(a->L, 1);
-    static size_t configured[64] = {0};
-    static int coop[64] = {0}; // 0 unknown, 1 yes, -1 no
-    const int dev = ctx->device & 63;
-    if (!coop[dev]) {
-        int v = 0;
-        CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, ctx->device));
-        coop[dev] = v ? 1 : -1;
-    }
-    if (coop[dev] < 0) {
-        b200_set_error("PCG: the device does not support cooperative kernel launches");
-        return B200LDU_ECUDA;
-    }
-    if (smem > 40 * 1024 && smem > configured[dev]) {
-        CUDA_TRY(cudaFuncSetAttribute(pcg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[dev] = smem;
-    }
     int perSM = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, pcg_persistent_kernel, ENGINE_THREADS, smem));
-    if (perSM < 1) {
-        b200_set_error("PCG: the persistent kernel does not fit on an SM (%zu bytes of shared memory)", smem);
-        return B200LDU_ECUDA;
-    }
-    long long items = (long long)a->L.nBands + a->L.nPackChunks;
-    int G = (int)std::min<long long>((long long)perSM * ctx->smCount, items);
-    if (G < 1) G = 1;
-    if (m->cpartLen < (size_t)4 * G) {
+    if (smem > 40 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(pcg2_kernel<PAinvOp, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, pcg2_kernel<PAinvOp, 0>, ENGINE_THREADS, smem));
+    if (perSM < 1) perSM = 1;
+    const int G = (int)std::max<long long>(1, std::min<long long>((long long)perSM * ctx->smCount, a->L.nBands));
+    if (m->cpartLen < (size_t)4 * G + 64) {
         if (m->d_cpart) cudaFree(m->d_cpart);
         m->d_cpart = nullptr;
         m->cpartLen = 0;
-        CUDA_TRY(cudaMalloc((void **)&m->d_cpart, sizeof(double) * 4 * (size_t)G));
-        m->cpartLen = (size_t)4 * G;
+        CUDA_TRY(cudaMalloc((void **)&m->d_cpart, sizeof(double) * ((size_t)4 * G + 64)));
+        m->cpartLen = (size_t)4 * G + 64;
     }
-    if (!m->d_bar) {
-        CUDA_TRY(cudaMalloc((void **)&m->d_bar, 2 * sizeof(unsigned)));
-        CUDA_TRY(cudaMemsetAsync(m->d_bar, 0, 2 * sizeof(unsigned), ctx->stream));
-    }
-    PcgArgs A;
-    A.L = a->L;
-    A.val = m->d_val;
-    A.diag = m->d_diag;
-    A.rD = m->d_rD;
-    A.psi = psi;
-    A.rb[0] = rb[0], A.rb[1] = rb[1], A.pb[0] = pb[0], A.pb[1] = pb[1];
-    A.w = w;
-    A.z = z;
+    double *partA = m->d_cpart, *partB = m->d_cpart + 2 * (size_t)G;
+    PcgCarry *carry = reinterpret_cast<PcgCarry *>(m->d_cpart + 4 * (size_t)G); // 2 x 80 bytes
+    static_assert(2 * sizeof(PcgCarry) <= 64 * sizeof(double), "carry blocks fit behind the partials");
+    const bool multi = ctx->nRanks > 1 && ctx->p2p;
+    pcg2_init_kernel<<<1, 1, 0, ctx->stream>>>(carry, S.sc, multi ? ctx->d_seq : nullptr);
+    ctx->launches++;
+    KERNEL_CHECK();
+
+    Pcg2Args A;
     A.sc = S.sc;
     A.hist = S.hist;
-    A.cpart = m->d_cpart;
-    A.bar = m->d_bar;
-    A.p2p = (ctx->nRanks > 1 && ctx->p2p) ? comm_p2p_red(ctx) : P2PRed();
-    A.seqs = ctx->d_seq;
+    A.p2p = multi ? comm_p2p_red(ctx) : P2PRed();
+    A.err = ctx->d_seq ? ctx->d_seq + 7 : nullptr;
+    A.rD = m->d_rD;
     A.pk = pk;
-    const long long mb = (long long)S.c.maxIter + 1 > S.c.minIter ? (long long)S.c.maxIter + 1 : S.c.minIter;
-    A.maxBodies = mb + 1; // +1: the last body's update is applied (and its residual judged) by the next sweep A
-    void *args[] = {&A};
-    CUDA_TRY(cudaLaunchCooperativeKernel((const void *)pcg_persistent_kernel, dim3(G), dim3(ENGINE_THREADS), args, smem,
-                                         ctx->stream));
-    ctx->launches++;
-    return B200LDU_OK;
+    auto body = [&](long long k) -> int {
+        PAinvOp oa;
+        oa.stop = stop;
+        oa.rOld = rb[k & 1], oa.rNew = rb[(k + 1) & 1], oa.w = w, oa.p = pb[k & 1], oa.psi = psi, oa.z = z, oa.rD = m->d_rD;
+        oa.alpha = 0, oa.bodies = 0;
+        Pcg2Args aa = A;
+        aa.cin = carry, aa.cout = carry + 1, aa.pin = partB, aa.nIn = k > 0 ? G : 0, aa.pout = partA;
+        TRY((pcg2_launch<PAinvOp, 0>(m, G, oa, aa)));
+        PAmulOp ob;
+        ob.stop = stop;
+        ob.z = z, ob.pOld = pb[k & 1], ob.pNew = pb[(k + 1) & 1], ob.out = w, ob.diag = m->d_diag;
+        ob.beta = 0, ob.bodies = 0;
+        ob.waitHalo = a->L.nPackChunks > 0;
+        Pcg2Args ab = A;
+        ab.cin = carry + 1, ab.cout = carry, ab.pin = partA, ab.nIn = G, ab.pout = partB;
+        TRY((pcg2_launch<PAmulOp, 1>(m, G, ob, ab)));
+        return B200LDU_OK;
+    };
+    long long mb = (long long)S.c.maxIter + 1 > S.c.minIter ? (long long)S.c.maxIter + 1 : S.c.minIter;
+    return run_iterations(S, mb + 1, body); // +1: the last body's update is applied (and judged) by the next sweeps
 }
 
 // ---------------------------------------------------------------------------
@@ -668,12 +688,12 @@ int solve_banded(b200ldu_matrix *m, const char *solver, const char *pre, const b
             } else {
                 snprintf(perf->solverName, sizeof(perf->solverName), "%s%s", pname, sv);
                 if (!strcmp(sv, "PCG")) {
-                    // the persistent kernel needs every exchange inside the kernel: the peer-memory halo (or no
-                    // halo) and the peer-memory all-reduce (or one rank); otherwise -- cyclic patches, NCCL fall-back --
+                    // the fused form needs every exchange inside the kernels: the peer-memory halo (or no halo)
+                    // and the peer-memory all-reduce (or one rank); otherwise -- cyclic patches, NCCL fall-back --
                     // and with B200LDU_PCG_FUSED=0 the reference's op list runs kernel by kernel
                     const char *ev = getenv("B200LDU_PCG_FUSED");
                     bool fused = !(ev && atoi(ev) == 0) && (a->L.nRecv == 0 || a->p2pHalo) && (ctx->nRanks == 1 || ctx->p2p);
-                    rc = fused ? solve_pcg_persistent(S, pk) : solve_pcg(S, pk);
+                    rc = fused ? solve_pcg_fused(S, pk) : solve_pcg(S, pk);
                 } else if (!strcmp(sv, "PBiCG")) {
                     rc = solve_pbicg(S, pk);
                 } else {
