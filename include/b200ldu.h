@@ -291,6 +291,19 @@ int b200ldu_field_gather(b200ldu_ctx *ctx, int n, int nComp, const int *cells_d,
  * and the non-orthogonal correction (correctedSnGrad.C:44-75, gaussLaplacianScheme.C:92-130: corrVecs & interpolate(grad))
  * are compositions of entry points of this header (rapidcfd-dev_b200/fvc.py: laplacian, snGrad_correction). */
 int b200ldu_fv_sngrad(b200ldu_addr *a, int nComp, const double *deltaCoeffs_d, const double *vf_d, double *out_d);
+/* ---- limited / upwind interpolation (FV/interpolation/surfaceInterpolation/limitedSchemes/) ----
+ * b200ldu_fv_limiter: limiter field on the internal faces, LimitedScheme<..>::calcLimiter (LimitedScheme.C:60-140) with
+ *   NVDTVD::r (NVDTVD.H:99-127); scheme "upwind" (0, upwind.H:103-118) | "linear" (1) | "limitedLinear" (coefficient k,
+ *   limitedLinear.H:64-101) | "vanLeer" (vanLeer.H:66-85) | "Minmod" (Minmod.H:66-85); scalar field vf, gradc = fvc::grad(vf)
+ *   [3 per cell], C = cell centres [3 per cell].
+ * b200ldu_fv_limited_weights: w = limiter*cdWeight + (1 - limiter)*pos(faceFlux)
+ *   (limitedSurfaceInterpolationScheme.C:155-212); limiter_d NULL => upwind, w = pos(faceFlux) (upwind.H:120-123).
+ * The weights feed b200ldu_fv_interpolate_linear / _grad_linear / _flux_linear and b200ldu_fv_convection_fill exactly as the
+ * central-differencing weights do (surfaceInterpolationScheme::interpolate(vf, weights), gaussConvectionScheme::fvmDiv). */
+int b200ldu_fv_limiter(b200ldu_addr *a, const char *scheme, double k, const double *faceFlux_d, const double *vf_d,
+                       const double *gradc_d, const double *C_d, double *limiter_d);
+int b200ldu_fv_limited_weights(b200ldu_ctx *ctx, long long n, const double *limiter_d, const double *cdWeights_d,
+                               const double *faceFlux_d, double *weights_d);
 
 /* ---- structural self-check of the banded layout (host only, no GPU, no arithmetic);
  * used by the CPU test-suite.  what: 0 perm 1 iperm 2 sliceStart(int64) 3 sliceW(u16)

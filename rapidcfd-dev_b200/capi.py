@@ -67,7 +67,7 @@ EXPORTS = [
     "b200ldu_fvm_add_boundary_diag", "b200ldu_fvm_add_boundary_source", "b200ldu_fvm_A", "b200ldu_fvm_H",
     "b200ldu_fvm_flux", "b200ldu_fvm_residual", "b200ldu_fvm_relax", "b200ldu_fvm_set_reference",
     "b200ldu_fvm_solve", "b200ldu_fv_patch_neighbour_field",
-    "b200ldu_fv_sngrad", "b200ldu_field_binary", "b200ldu_field_unary", "b200ldu_field_dot3", "b200ldu_field_gather",
+    "b200ldu_fv_sngrad", "b200ldu_fv_limiter", "b200ldu_fv_limited_weights", "b200ldu_field_binary", "b200ldu_field_unary", "b200ldu_field_dot3", "b200ldu_field_gather",
 ]
 
 _lib = None
@@ -144,6 +144,8 @@ def lib():
     L.b200ldu_fvm_set_reference.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     L.b200ldu_fv_patch_neighbour_field.argtypes = [vp, C.c_int, vp, vp]
     L.b200ldu_fv_sngrad.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.b200ldu_fv_limiter.argtypes = [vp, C.c_char_p, C.c_double, vp, vp, vp, vp, vp]
+    L.b200ldu_fv_limited_weights.argtypes = [vp, C.c_longlong, vp, vp, vp, vp]
     L.b200ldu_field_binary.argtypes = [vp, C.c_int, C.c_longlong, C.c_int, vp, C.c_int, vp, vp]
     L.b200ldu_field_unary.argtypes = [vp, C.c_int, C.c_longlong, C.c_double, vp, vp]
     L.b200ldu_field_dot3.argtypes = [vp, C.c_longlong, vp, vp, vp]
@@ -587,6 +589,20 @@ def fv_sngrad(addr, nComp, deltaCoeffs, vf):
     """snGradScheme::snGrad on the internal faces"""
     out = _newlike(vf, addr.nFaces * nComp)
     check(lib().b200ldu_fv_sngrad(addr.h, nComp, _dp(deltaCoeffs), _dp(vf), _dp(out)))
+    return out
+
+
+def fv_limiter(addr, scheme, faceFlux, vf, gradc, centres, k=1.0):
+    """limiter field of a limited scheme on the internal faces (LimitedScheme::calcLimiter)"""
+    out = _newlike(faceFlux, addr.nFaces)
+    check(lib().b200ldu_fv_limiter(addr.h, scheme.encode(), float(k), _dp(faceFlux), _dp(vf), _dp(gradc), _dp(centres), _dp(out)))
+    return out
+
+
+def fv_limited_weights(ctx, faceFlux, limiter=None, cdWeights=None):
+    """interpolation weights of a limited scheme; limiter None: upwind, pos(faceFlux)"""
+    out = _newlike(faceFlux, faceFlux.numel())
+    check(lib().b200ldu_fv_limited_weights(ctx.h, faceFlux.numel(), _dp(limiter), _dp(cdWeights), _dp(faceFlux), _dp(out)))
     return out
 
 

@@ -31,7 +31,7 @@ extern "C" int b200ldu_field_binary(b200ldu_ctx *ctx, int op, long long n, int n
 
 extern "C" int b200ldu_field_unary(b200ldu_ctx *ctx, int op, long long n, double s, const double *a_d, double *out_d)
 {
-    if (!ctx || !a_d || !out_d || n < 0 || op < UN_NEG || op > UN_COPY) return B200LDU_EINVAL;
+    if (!ctx || !a_d || !out_d || n < 0 || op < UN_NEG || op > UN_POS) return B200LDU_EINVAL;
     if (n == 0) return B200LDU_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
     unary_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, op, s, a_d, out_d);
@@ -73,6 +73,57 @@ extern "C" int b200ldu_fv_sngrad(b200ldu_addr *a, int nComp, const double *delta
     sngrad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, a->ctx->stream>>>(a->nFaces, nComp, a->d_l, a->d_u, deltaCoeffs_d, vf_d,
                                                                              out_d);
     a->ctx->launches++;
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}
+
+// ---- limited / upwind interpolation weights ----
+// limiter field of a limited scheme on the internal faces (LimitedScheme.C:60-140); gradc = fvc::grad(vf) (b200ldu_fv_grad_linear),
+// C = cell centres.  scheme: "upwind" | "linear" | "limitedLinear" (coefficient k) | "vanLeer" | "Minmod"
+extern "C" int b200ldu_fv_limiter(b200ldu_addr *a, const char *scheme, double k, const double *faceFlux_d, const double *vf_d,
+                                  const double *gradc_d, const double *C_d, double *limiter_d)
+{
+    if (!a || !scheme || !limiter_d) return B200LDU_EINVAL;
+    int sch;
+    if (!strcmp(scheme, "upwind"))
+        sch = LIM_UPWIND;
+    else if (!strcmp(scheme, "linear"))
+        sch = LIM_LINEAR;
+    else if (!strcmp(scheme, "limitedLinear"))
+        sch = LIM_LIMITED_LINEAR;
+    else if (!strcmp(scheme, "vanLeer"))
+        sch = LIM_VANLEER;
+    else if (!strcmp(scheme, "Minmod"))
+        sch = LIM_MINMOD;
+    else {
+        b200_set_error("Unknown discretisation scheme %s; valid schemes are: (Minmod limitedLinear linear upwind vanLeer)", scheme);
+        return B200LDU_EINVAL;
+    }
+    if (sch >= LIM_LIMITED_LINEAR && (!faceFlux_d || !vf_d || !gradc_d || !C_d)) return B200LDU_EINVAL;
+    if (sch == LIM_LIMITED_LINEAR && (k < 0 || k > 1)) {
+        b200_set_error("limitedLinear: coefficient = %g should be >= 0 and <= 1 (limitedLinear.H:66-72)", k);
+        return B200LDU_EINVAL;
+    }
+    if (a->nFaces == 0) return B200LDU_OK;
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    const double kk = k > 1e-15 ? k : 1e-15;   // twoByk_ = 2.0/max(k_, SMALL), SMALL = 1e-15 (doubleScalar.H)
+    limiter_kernel<<<(a->nFaces + 255) / 256, 256, 0, a->ctx->stream>>>(a->nFaces, sch, 2.0 / kk, a->d_l, a->d_u, faceFlux_d, vf_d,
+                                                                       gradc_d, C_d, limiter_d);
+    a->ctx->launches++;
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}
+
+// weights of a limited scheme from its limiter field (limitedSurfaceInterpolationScheme.C:155-212); limiter_d NULL: upwind
+// (upwind.H:120-123).  n faces: internal faces, or the faces of a coupled patch.
+extern "C" int b200ldu_fv_limited_weights(b200ldu_ctx *ctx, long long n, const double *limiter_d, const double *cdWeights_d,
+                                          const double *faceFlux_d, double *weights_d)
+{
+    if (!ctx || !faceFlux_d || !weights_d || n < 0 || (limiter_d && !cdWeights_d)) return B200LDU_EINVAL;
+    if (n == 0) return B200LDU_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    limited_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, limiter_d, cdWeights_d, faceFlux_d, weights_d);
+    ctx->launches++;
     KERNEL_CHECK();
     return B200LDU_OK;
 }

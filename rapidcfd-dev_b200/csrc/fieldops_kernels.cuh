@@ -10,7 +10,8 @@ namespace // internal linkage: the headers are included by more than one transla
 {
 enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_DIV = 3, OP_MIN = 4, OP_MAX = 5 };
 enum { UN_NEG = 0, UN_MAG = 1, UN_S_MUL = 2, UN_S_RDIV = 3, UN_S_ADD = 4, UN_S_RSUB = 5, UN_S_MIN = 6, UN_S_MAX = 7,
-       UN_S_SUB = 8, UN_S_DIV = 9, UN_COPY = 10 };
+       UN_S_SUB = 8, UN_S_DIV = 9, UN_COPY = 10, UN_POS = 11 };
+enum { LIM_UPWIND = 0, LIM_LINEAR = 1, LIM_LIMITED_LINEAR = 2, LIM_VANLEER = 3, LIM_MINMOD = 4 };
 
 __device__ __forceinline__ double bin(int op, double a, double b)
 {
@@ -52,6 +53,7 @@ __global__ void unary_kernel(long long n, int op, double s, const double *a, dou
     case UN_S_MAX: r = fmax(x, s); break;
     case UN_S_SUB: r = __dsub_rn(x, s); break;
     case UN_S_DIV: r = __ddiv_rn(x, s); break;
+    case UN_POS: r = x >= 0 ? 1.0 : 0.0; break; // pos(), Scalar.H:119-122
     default: r = x; break;
     }
     out[i] = r;
@@ -74,6 +76,66 @@ __global__ void sngrad_kernel(int nFaces, int nc, const int *__restrict__ l, con
     if (i >= (long long)nFaces * nc) return;
     const int f = (int)(i / nc), k = (int)(i - (long long)f * nc);
     out[i] = __dmul_rn(delta[f], __dsub_rn(vf[(size_t)u[f] * nc + k], vf[(size_t)l[f] * nc + k]));
+}
+
+// NVDTVD::r (limitedSchemes/LimitedScheme/NVDTVD.H:99-127): ratio of the upwind-side cell gradient (projected on
+// d = C[nei] - C[own]) to the face gradient, r = 2*(gradcf/gradf) - 1, clipped when the face gradient vanishes
+__device__ __forceinline__ double nvdtvd_r(double faceFlux, double phiP, double phiN, const double *gP, const double *gN,
+                                           const double *d)
+{
+    const double gradf = __dsub_rn(phiN, phiP);
+    const double *g = faceFlux > 0 ? gP : gN;
+    // Vector & Vector: (d.x*g.x + d.y*g.y) + d.z*g.z (VectorI.H operator&)
+    const double gradcf = __dadd_rn(__dadd_rn(__dmul_rn(d[0], g[0]), __dmul_rn(d[1], g[1])), __dmul_rn(d[2], g[2]));
+    if (fabs(gradcf) >= __dmul_rn(1000.0, fabs(gradf))) {
+        const double sc = gradcf >= 0 ? 1.0 : -1.0, sf = gradf >= 0 ? 1.0 : -1.0; // sign(), Scalar.H:112-116
+        return __dsub_rn(__dmul_rn(__dmul_rn(2000.0, sc), sf), 1.0);               // 2*1000*sign*sign - 1
+    }
+    return __dsub_rn(__dmul_rn(2.0, __ddiv_rn(gradcf, gradf)), 1.0);
+}
+
+// LimitedScheme::calcLimiter on the internal faces (LimitedScheme.C:60-140) for a scalar field: limiter value per
+// face from the scheme's limiter function -- upwind 0 (upwind.H:103-118), linear 1, limitedLinear
+// max(min(2/max(k,SMALL)*r, 1), 0) (limitedLinear.H:64-101), vanLeer (r + |r|)/(1 + |r|) (vanLeer.H:66-85),
+// Minmod max(min(r, 1), 0) (Minmod.H:66-85)
+__global__ void limiter_kernel(int nFaces, int scheme, double twoByk, const int *__restrict__ l, const int *__restrict__ u,
+                               const double *__restrict__ faceFlux, const double *__restrict__ vf,
+                               const double *__restrict__ gradc, const double *__restrict__ C, double *__restrict__ out)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nFaces) return;
+    if (scheme == LIM_UPWIND || scheme == LIM_LINEAR) {
+        out[f] = scheme == LIM_LINEAR ? 1.0 : 0.0;
+        return;
+    }
+    const int o = l[f], n = u[f];
+    const double d[3] = {__dsub_rn(C[3 * (size_t)n], C[3 * (size_t)o]), __dsub_rn(C[3 * (size_t)n + 1], C[3 * (size_t)o + 1]),
+                         __dsub_rn(C[3 * (size_t)n + 2], C[3 * (size_t)o + 2])};
+    const double r = nvdtvd_r(faceFlux[f], vf[o], vf[n], gradc + 3 * (size_t)o, gradc + 3 * (size_t)n, d);
+    double lim;
+    if (scheme == LIM_LIMITED_LINEAR)
+        lim = fmax(fmin(__dmul_rn(twoByk, r), 1.0), 0.0);
+    else if (scheme == LIM_VANLEER)
+        lim = __ddiv_rn(__dadd_rn(r, fabs(r)), __dadd_rn(1.0, fabs(r)));
+    else
+        lim = fmax(fmin(r, 1.0), 0.0);
+    out[f] = lim;
+}
+
+// limitedSurfaceInterpolationScheme::weights (limitedSurfaceInterpolationScheme.C:155-212):
+// w = limiter*cdWeight + (1 - limiter)*pos(faceFlux); without a limiter field: upwind, w = pos(faceFlux) (upwind.H:120-123)
+__global__ void limited_weights_kernel(long long n, const double *__restrict__ limiter, const double *__restrict__ cd,
+                                       const double *__restrict__ faceFlux, double *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double p = faceFlux[i] >= 0 ? 1.0 : 0.0;
+    if (!limiter) {
+        out[i] = p;
+        return;
+    }
+    const double lim = limiter[i];
+    out[i] = __dadd_rn(__dmul_rn(lim, cd[i]), __dmul_rn(__dsub_rn(1.0, lim), p));
 }
 
 // patchInternalField: out[i][k] = field[cells[i]][k]

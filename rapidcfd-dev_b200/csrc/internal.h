@@ -43,19 +43,6 @@ void b200_set_error(const char *fmt, ...);
 // indices with 32-bit loads (ushort2).
 constexpr int SLICE_ROWS = 64;
 constexpr int ENGINE_THREADS = 256;
-// resident CTAs per SM the engine kernels are compiled for: 5 => 48 registers per thread (no spills in the
-// slot loop), 6 => 40 registers (a few 8-byte spills per group of four slots)
-#ifndef ENGINE_MINB
-#define ENGINE_MINB 5
-#endif
-// slots whose coefficient loads are in flight together (registers: 4 per slot)
-#ifndef ENGINE_GROUP
-#define ENGINE_GROUP 4
-#endif
-// experiment switch: 1 = explicit 16-bit column per entry (2 B/entry) instead of the compressed blob
-#ifndef ENGINE_COLMODE
-#define ENGINE_COLMODE 0
-#endif
 
 struct b200ldu_ctx {
     int device = 0;
@@ -117,17 +104,9 @@ struct LayoutDev {
     const long long *sliceStart; // [nSlices+1] entry offset of each slice (multiple of 64)
     const uint16_t *sliceW;      // slots per row in the slice, all entries
     const uint16_t *sliceWL;     // slots holding owner/neighbour entries only (no interfaces)
-#if ENGINE_COLMODE == 1
-    const uint16_t *col;         // [nEntries] explicit band-local columns (experiment)
-#endif
-    const int *cStart;           // [nSlices+1] offset of each slice's column blob, in 16-byte words
-    const uint4 *cblob;          // compressed band-local columns (layout.cu 3b): < bandRows own band, else halo slot
-    int wbufBytes;               // longest blob: size of one per-warp staging buffer
+    const uint16_t *col;         // [nEntries] band-local column: < bandRows own band, else halo slot
     const int *haloStart;        // [nBands+1]
     const int *haloIdx;          // banded extended index: < nPad local row, else nPad + recv slot
-    const uint16_t *haloPos;     // tile position of every halo column
-    const uint32_t *rowPos;      // tile positions of rows 2i, 2i+1 (two u16)
-    int tileLen;                 // tile length in doubles (even; >= bandRows + halo of any band)
     const int *perm;             // [nCells] caller cell -> banded row
     const int *iperm;            // [nPad]  banded row -> caller cell, -1 padding
     // peer-memory halo (null/0 when the exchange goes through NCCL into the vector's own tail)
@@ -157,11 +136,7 @@ struct b200ldu_addr {
     std::vector<double> centres_h; // optional cell centres (kept for GAMG coarse-level banding)
     // device arrays owned
     long long *d_sliceStart = nullptr;
-    uint16_t *d_sliceW = nullptr, *d_sliceWL = nullptr;
-    int *d_cStart = nullptr;
-    uint16_t *d_haloPos = nullptr, *d_rowPos = nullptr;
-    uint16_t *d_col = nullptr; // ENGINE_COLMODE 1 only
-    uint32_t *d_cblob = nullptr;
+    uint16_t *d_sliceW = nullptr, *d_sliceWL = nullptr, *d_col = nullptr;
     int *d_code = nullptr; // [nEntries] value source: 2f+side | -1 pad | -2-pf interface
     int *d_haloStart = nullptr, *d_haloIdx = nullptr, *d_perm = nullptr, *d_iperm = nullptr;
     int *d_sendRows = nullptr; // [nRecv] banded row of faceCells (pack kernel)
@@ -187,9 +162,7 @@ struct b200ldu_addr {
     bool hostOnly = false;
     std::vector<long long> dbg_sliceStart;
     std::vector<uint16_t> dbg_sliceW, dbg_sliceWL, dbg_col;
-    std::vector<int> dbg_code, dbg_haloStart, dbg_haloIdx, dbg_cStart;
-    std::vector<uint32_t> dbg_cblob;
-    std::vector<uint16_t> dbg_rowPos, dbg_haloPos;
+    std::vector<int> dbg_code, dbg_haloStart, dbg_haloIdx;
     // workspace pool for caller-order entry points (banded vectors)
     std::vector<double *> pool;
     long long vecLen = 0; // nPad + nRecv (padded to even)

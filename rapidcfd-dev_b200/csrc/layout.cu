@@ -12,11 +12,9 @@
 //  * entries of 64 consecutive rows are stored slot-major ("slice"): slot j of row q
 //    sits at sliceStart + 64*j + q, so a warp reads one slot of its 64 rows with a
 //    single 128-bit load per lane;
-//  * columns are indices into the band's shared-memory psi tile: the band's own rows
-//    first, then the band's halo list (rows of other bands / received interface values)
-//    which is gathered once per band.  They are stored compressed: per slice and slot one
-//    row offset shared by the regular rows + a bit mask and a short list of 16-bit columns
-//    for the others (section 3b).
+//  * columns are 16-bit indices into the band's shared-memory psi tile: the band's own
+//    rows first, then the band's halo list (rows of other bands / received interface
+//    values) which is gathered once per band.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -187,10 +185,9 @@ int layout_build(b200ldu_addr *a, const double *centres)
     int bits[3] = {0, 0, 0};
     {
         long long tiles = 1;
-        // tiles of ~one band (bandRows rows), caller order inside a tile: a band is a compact brick, and on
-        // block-structured meshes (lexicographic caller numbering) a row's neighbours sit at a constant row
-        // offset for whole slices -- which is what the column compression below exploits
-        while ((double)nCells / (double)tiles > (double)bandRows && bits[0] + bits[1] + bits[2] < 45) {
+        // tiles of ~one slice (64 rows): slices become small cubes (most of a row's faces stay inside its slice) and Morton order keeps
+        // every run of bandRows/64 consecutive tiles a compact brick
+        while ((double)nCells / (double)tiles > (double)SLICE_ROWS && bits[0] + bits[1] + bits[2] < 45) {
             int best = 2; // ties go to the last axis so x keeps the longest runs
             double bestExt = -1;
             for (int k = 2; k >= 0; k--) {
@@ -281,9 +278,6 @@ int layout_build(b200ldu_addr *a, const double *centres)
     std::vector<uint16_t> col((size_t)std::max<long long>(nEntries, 1));
     std::vector<int> code((size_t)std::max<long long>(nEntries, 1));
     std::vector<std::vector<int>> halo(nBands);
-    std::vector<std::vector<uint16_t>> haloPosB(nBands);
-    std::vector<uint16_t> rowPos((size_t)nPad, 0);
-    std::vector<int> tileLenB(nBands, 0);
     int tooWide = 0;
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : tooWide)
     for (int b = 0; b < nBands; b++) {
@@ -308,99 +302,10 @@ int layout_build(b200ldu_addr *a, const double *centres)
             tooWide++;
             continue;
         }
-        // ---- tile positions: where each row of the band and each halo column sits in the shared-memory tile.
-        // Default: rows at their band-local index, halo columns appended in sorted order.  When the band is a
-        // complete lattice brick in caller (x-fastest) order -- block-structured meshes -- rows and halo cells
-        // go to a brick padded by one cell on every side instead, so that the neighbour of every row in a given
-        // direction sits at the SAME tile offset, halo or not: the column compression (3b) then has no
-        // exceptions in such bands.  Purely an encoding choice: any assignment of distinct positions is valid.
-        uint16_t *rp = &rowPos[r0];
-        std::vector<uint16_t> &hp = haloPosB[b];
-        hp.assign(h.size(), 0);
-        int tileLen = bandRows + (int)h.size();
-        for (int i = 0; i < bandRows; i++) rp[i] = (uint16_t)i;
-        for (size_t i = 0; i < h.size(); i++) hp[i] = (uint16_t)(bandRows + i);
-        if (centres && iperm[r1 - 1] >= 0) {
-            // unique coordinates per axis (the brick's planes), tolerance relative to the mesh extent
-            std::vector<double> ax[3];
-            for (int k = 0; k < 3; k++) {
-                ax[k].reserve(bandRows);
-                for (int r = r0; r < r1; r++) ax[k].push_back(centres[3 * (size_t)iperm[r] + k]);
-                std::sort(ax[k].begin(), ax[k].end());
-                const double tol = 1e-9 * ext[k];
-                size_t m = 0;
-                for (size_t i = 0; i < ax[k].size(); i++)
-                    if (m == 0 || ax[k][i] - ax[k][m - 1] > tol) ax[k][m++] = ax[k][i];
-                ax[k].resize(m);
-            }
-            const long long nx = (long long)ax[0].size(), ny = (long long)ax[1].size(), nz = (long long)ax[2].size();
-            bool ok = nx * ny * nz == bandRows && (nx + 2) * (ny + 2) * (nz + 2) + (long long)h.size() <= 65535;
-            auto idxOf = [&](int k, double v) -> int {
-                const double tol = 1e-9 * ext[k];
-                int i = (int)(std::lower_bound(ax[k].begin(), ax[k].end(), v - tol) - ax[k].begin());
-                return (i < (int)ax[k].size() && std::fabs(ax[k][i] - v) <= tol) ? i : -1;
-            };
-            const int px = (int)nx + 2, pxy = px * ((int)ny + 2);
-            std::vector<int> lat; // lattice position of every row
-            if (ok) {
-                lat.resize(bandRows);
-                for (int r = r0; r < r1 && ok; r++) {
-                    const double *cc = centres + 3 * (size_t)iperm[r];
-                    const int i = idxOf(0, cc[0]), j = idxOf(1, cc[1]), k = idxOf(2, cc[2]);
-                    // caller order inside the brick must be x-fastest (x-lines contiguous in rows)
-                    ok = i >= 0 && j >= 0 && k >= 0 && (r - r0) == i + (int)nx * (j + (int)ny * k);
-                    lat[r - r0] = (i + 1) + px * (j + 1) + pxy * (k + 1);
-                }
-            }
-            std::vector<int> hlat;
-            if (ok) {
-                // halo cells: one step from the row that references them, along the axis their centres differ most
-                hlat.assign(h.size(), -1);
-                const int latticeLen = pxy * ((int)nz + 2);
-                int nIfc = 0;
-                auto place = [&](int r, int t) {
-                    if (t >= r0 && t < r1) return;
-                    const size_t hi = (size_t)(std::lower_bound(h.begin(), h.end(), t) - h.begin());
-                    const double *a0 = centres + 3 * (size_t)iperm[r], *a1 = centres + 3 * (size_t)iperm[t];
-                    int axis = 0;
-                    double best = -1;
-                    for (int k = 0; k < 3; k++) {
-                        const double d = std::fabs(a1[k] - a0[k]) / ext[k];
-                        if (d > best) best = d, axis = k;
-                    }
-                    const int step = (axis == 0 ? 1 : axis == 1 ? px : pxy) * (a1[axis] > a0[axis] ? 1 : -1);
-                    const int want = lat[r - r0] + step;
-                    if (hlat[hi] >= 0 && hlat[hi] != want) ok = false;
-                    hlat[hi] = want;
-                };
-                for (int r = r0; r < r1 && ok; r++) {
-                    const int c = iperm[r];
-                    for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++) place(r, perm[u[f]]);
-                    for (int k = losortStart[c]; k < losortStart[c + 1]; k++) place(r, perm[l[losort[k]]]);
-                }
-                // received interface values go behind the padded brick; positions must be distinct
-                std::vector<char> used(ok ? (size_t)latticeLen : 0, 0);
-                for (int i = 0; i < bandRows && ok; i++) used[lat[i]] = 1;
-                for (size_t i = 0; i < h.size() && ok; i++) {
-                    if (h[i] >= nPad) {
-                        hlat[i] = latticeLen + nIfc++;
-                    } else if (hlat[i] < 0 || hlat[i] >= latticeLen || used[hlat[i]]) {
-                        ok = false;
-                    } else
-                        used[hlat[i]] = 1;
-                }
-                if (ok) {
-                    for (int i = 0; i < bandRows; i++) rp[i] = (uint16_t)lat[i];
-                    for (size_t i = 0; i < h.size(); i++) hp[i] = (uint16_t)hlat[i];
-                    tileLen = latticeLen + nIfc;
-                }
-            }
-        }
-        tileLenB[b] = tileLen;
         auto colOf = [&](int t) -> uint16_t {
-            if (t >= r0 && t < r1) return rp[t - r0];
+            if (t >= r0 && t < r1) return (uint16_t)(t - r0);
             int pos = (int)(std::lower_bound(h.begin(), h.end(), t) - h.begin());
-            return hp[pos];
+            return (uint16_t)(bandRows + pos);
         };
         for (int sl = 0; sl < slicesPerBand; sl++) {
             int s = b * slicesPerBand + sl;
@@ -409,7 +314,7 @@ int layout_build(b200ldu_addr *a, const double *centres)
             for (int q = 0; q < SLICE_ROWS; q++) {
                 int r = s * SLICE_ROWS + q;
                 int c = iperm[r];
-                uint16_t self = rp[r - r0];
+                uint16_t self = (uint16_t)(r - r0);
                 int j = 0;
                 if (c >= 0) {
                     for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++, j++) {
@@ -457,10 +362,7 @@ int layout_build(b200ldu_addr *a, const double *centres)
         haloStart[b + 1] = haloStart[b] + (int)halo[b].size();
         maxHalo = std::max(maxHalo, (int)halo[b].size());
     }
-    int tileLen = 0;
-    for (int b = 0; b < nBands; b++) tileLen = std::max(tileLen, tileLenB[b]);
-    tileLen = (tileLen + 1) & ~1;
-    if ((size_t)(tileLen + 2) * 2 * sizeof(double) > TILE_BYTES_MAX) {
+    if ((size_t)(bandRows + maxHalo + 2) * 2 * sizeof(double) > TILE_BYTES_MAX) {
         // poorly clustered numbering (no cell centres, high-degree graph): the halo of a band does not fit
         // next to its rows in shared memory.  Narrower bands shrink both terms; the ordering is unchanged.
         if (bandRows > SLICE_ROWS) {
@@ -476,91 +378,9 @@ int layout_build(b200ldu_addr *a, const double *centres)
         return B200LDU_ELAYOUT;
     }
     std::vector<int> haloIdx((size_t)std::max(haloStart[nBands], 1));
-    std::vector<uint16_t> haloPos((size_t)std::max(haloStart[nBands], 1));
 #pragma omp parallel for schedule(static)
-    for (int b = 0; b < nBands; b++) {
+    for (int b = 0; b < nBands; b++)
         std::copy(halo[b].begin(), halo[b].end(), haloIdx.begin() + haloStart[b]);
-        std::copy(haloPosB[b].begin(), haloPosB[b].end(), haloPos.begin() + haloStart[b]);
-    }
-
-    // ---- 3b. compressed columns ---------------------------------------------
-    // Per slice one blob of 16-byte words: W slot descriptors {mask lo, mask hi, delta, exception offset}
-    // followed by the slice's exception list (16-bit columns, padded to 8).  Row q of the slice reads slot j
-    // at tile column (local row + delta) unless bit q of the mask is set, in which case the column is
-    // exc[offset + number of mask bits below q].  delta = the most frequent (column - local row) of the slot;
-    // on band-sized bricks of a structured mesh only the references into the halo are exceptions
-    // (~8 % of the entries): 16-bit columns cost 2 B per entry, this ~0.4 B.
-    std::vector<int> cStart((size_t)nSlices + 1, 0);
-    std::vector<std::vector<uint32_t>> blobs(nSlices);
-#pragma omp parallel for schedule(dynamic, 64)
-    for (int s = 0; s < nSlices; s++) {
-        const int W = sliceW[s];
-        const long long base = sliceStart[s];
-        const uint16_t *rps = &rowPos[(size_t)s * SLICE_ROWS];
-        std::vector<uint32_t> &bl = blobs[s];
-        bl.assign((size_t)4 * W, 0);
-        std::vector<uint16_t> exc;
-        for (int j = 0; j < W; j++) {
-            const uint16_t *cj = &col[base + (long long)j * SLICE_ROWS];
-            int d[SLICE_ROWS], best = 0, bestN = 0;
-            for (int q = 0; q < SLICE_ROWS; q++) d[q] = (int)cj[q] - (int)rps[q];
-            {
-                int t[SLICE_ROWS];
-                std::copy(d, d + SLICE_ROWS, t);
-                std::sort(t, t + SLICE_ROWS);
-                for (int q = 0; q < SLICE_ROWS;) { // longest run; ties go to the smallest offset
-                    int e = q;
-                    while (e < SLICE_ROWS && t[e] == t[q]) e++;
-                    if (e - q > bestN) {
-                        bestN = e - q;
-                        best = t[q];
-                    }
-                    q = e;
-                }
-            }
-            uint64_t mask = 0;
-            const uint32_t off = (uint32_t)exc.size();
-            for (int q = 0; q < SLICE_ROWS; q++)
-                if (d[q] != best) {
-                    mask |= 1ull << q;
-                    exc.push_back(cj[q]);
-                }
-            bl[4 * (size_t)j + 0] = (uint32_t)mask;
-            bl[4 * (size_t)j + 1] = (uint32_t)(mask >> 32);
-            bl[4 * (size_t)j + 2] = (uint32_t)best;
-            bl[4 * (size_t)j + 3] = off;
-        }
-        for (int q = 0; q < SLICE_ROWS; q += 2) bl.push_back((uint32_t)rps[q] | ((uint32_t)rps[q + 1] << 16)); // tile positions
-        while (exc.size() % 8) exc.push_back(0);
-        for (size_t i = 0; i < exc.size(); i += 2) bl.push_back((uint32_t)exc[i] | ((uint32_t)exc[i + 1] << 16));
-    }
-    int maxBlobWords16 = 0; // longest blob in 16-byte words (per-warp staging buffer of the engine)
-    for (int s = 0; s < nSlices; s++) {
-        const int w16 = (int)(blobs[s].size() / 4);
-        cStart[s + 1] = cStart[s] + w16;
-        maxBlobWords16 = std::max(maxBlobWords16, w16);
-    }
-    std::vector<uint32_t> cblob((size_t)std::max(cStart[nSlices], 1) * 4, 0);
-#pragma omp parallel for schedule(static)
-    for (int s = 0; s < nSlices; s++) std::copy(blobs[s].begin(), blobs[s].end(), cblob.begin() + (size_t)cStart[s] * 4);
-    blobs.clear();
-    blobs.shrink_to_fit();
-    {
-        // tile(s) + the per-warp double buffers must fit next to each other in shared memory
-        const size_t wb = (size_t)(ENGINE_THREADS / 32) * 2 * 16 * (size_t)maxBlobWords16;
-        if ((size_t)(tileLen + 2) * 2 * sizeof(double) + wb > TILE_BYTES_MAX + 16 * 1024) {
-            if (bandRows > SLICE_ROWS) {
-                const int saved = g_bandRowsRetry;
-                g_bandRowsRetry = bandRows / 2;
-                int rc = layout_build(a, centres);
-                g_bandRowsRetry = saved;
-                return rc;
-            }
-            b200_set_error("layout_build: rows of up to %d entries: the per-warp column buffers do not fit in shared memory",
-                           maxBlobWords16);
-            return B200LDU_ELAYOUT;
-        }
-    }
 
     std::vector<int> sendRows(std::max(nRecv, 1));
     for (int i = 0; i < nRecv; i++) sendRows[i] = perm[a->faceCells[i]];
@@ -575,8 +395,6 @@ int layout_build(b200ldu_addr *a, const double *centres)
     a->L.slicesPerBand = slicesPerBand;
     a->L.nRecv = nRecv;
     a->L.maxHalo = maxHalo;
-    a->L.wbufBytes = 16 * maxBlobWords16;
-    a->L.tileLen = tileLen;
     if (a->hostOnly) { // structural self-check path (tests): keep the host arrays, no GPU
         a->dbg_sliceStart.swap(sliceStart);
         a->dbg_sliceW.swap(sliceW);
@@ -585,10 +403,6 @@ int layout_build(b200ldu_addr *a, const double *centres)
         a->dbg_code.swap(code);
         a->dbg_haloStart.swap(haloStart);
         a->dbg_haloIdx.swap(haloIdx);
-        a->dbg_cStart.swap(cStart);
-        a->dbg_cblob.swap(cblob);
-        a->dbg_rowPos.swap(rowPos);
-        a->dbg_haloPos.swap(haloPos);
         return B200LDU_OK;
     }
 
@@ -596,17 +410,10 @@ int layout_build(b200ldu_addr *a, const double *centres)
     TRY(dev_upload(&a->d_sliceStart, sliceStart));
     TRY(dev_upload(&a->d_sliceW, sliceW));
     TRY(dev_upload(&a->d_sliceWL, sliceWL));
-#if ENGINE_COLMODE == 1
     TRY(dev_upload(&a->d_col, col));
-    a->L.col = a->d_col;
-#endif
-    TRY(dev_upload(&a->d_cStart, cStart));
-    TRY(dev_upload(&a->d_cblob, cblob));
     TRY(dev_upload(&a->d_code, code));
     TRY(dev_upload(&a->d_haloStart, haloStart));
     TRY(dev_upload(&a->d_haloIdx, haloIdx));
-    TRY(dev_upload(&a->d_haloPos, haloPos));
-    TRY(dev_upload(&a->d_rowPos, rowPos));
     TRY(dev_upload(&a->d_perm, a->perm_h));
     TRY(dev_upload(&a->d_iperm, a->iperm_h));
     TRY(dev_upload(&a->d_sendRows, sendRows));
@@ -627,14 +434,9 @@ int layout_build(b200ldu_addr *a, const double *centres)
     L.sliceStart = a->d_sliceStart;
     L.sliceW = a->d_sliceW;
     L.sliceWL = a->d_sliceWL;
-    L.cStart = a->d_cStart;
-    L.cblob = reinterpret_cast<const uint4 *>(a->d_cblob);
-    L.wbufBytes = 16 * maxBlobWords16;
+    L.col = a->d_col;
     L.haloStart = a->d_haloStart;
     L.haloIdx = a->d_haloIdx;
-    L.haloPos = a->d_haloPos;
-    L.rowPos = reinterpret_cast<const uint32_t *>(a->d_rowPos);
-    L.tileLen = tileLen;
     L.perm = a->d_perm;
     L.iperm = a->d_iperm;
     a->nEntries = nEntries;
@@ -674,8 +476,6 @@ extern "C" int b200ldu_layout_debug_create(int nCells, int nFaces, const int *lo
 
 // what: 0 perm(int32) 1 iperm(int32) 2 sliceStart(int64) 3 sliceW(u16) 4 sliceWL(u16) 5 col(u16)
 //       6 code(int32) 7 haloStart(int32) 8 haloIdx(int32) 9 dims {nPad,nBands,bandRows,nRecv,maxHalo}(int32)
-//       10 cStart(int32, 16-byte words) 11 cblob(uint32 words: compressed columns, see layout_build 3b)
-//       12 rowPos(u16: tile position of every row) 13 haloPos(u16: tile position of every halo column)
 // returns the element count (copies min(count, cap) elements when out != NULL)
 extern "C" long long b200ldu_layout_debug_get(const b200ldu_addr *a, int what, void *out, long long cap)
 {
@@ -684,7 +484,7 @@ extern "C" long long b200ldu_layout_debug_get(const b200ldu_addr *a, int what, v
         if (out) memcpy(out, src, elem * (size_t)std::min(n, cap));
         return n;
     };
-    int dims[6] = {a->L.nPad, a->L.nBands, a->L.bandRows, a->L.nRecv, a->L.maxHalo, a->L.tileLen};
+    int dims[5] = {a->L.nPad, a->L.nBands, a->L.bandRows, a->L.nRecv, a->L.maxHalo};
     switch (what) {
     case 0: return give(a->perm_h.data(), 4, (long long)a->perm_h.size());
     case 1: return give(a->iperm_h.data(), 4, (long long)a->iperm_h.size());
@@ -695,11 +495,7 @@ extern "C" long long b200ldu_layout_debug_get(const b200ldu_addr *a, int what, v
     case 6: return give(a->dbg_code.data(), 4, a->nEntries);
     case 7: return give(a->dbg_haloStart.data(), 4, (long long)a->dbg_haloStart.size());
     case 8: return give(a->dbg_haloIdx.data(), 4, a->nHaloTotal);
-    case 9: return give(dims, 4, 6);
-    case 10: return give(a->dbg_cStart.data(), 4, (long long)a->dbg_cStart.size());
-    case 11: return give(a->dbg_cblob.data(), 4, (long long)a->dbg_cblob.size());
-    case 12: return give(a->dbg_rowPos.data(), 2, (long long)a->dbg_rowPos.size());
-    case 13: return give(a->dbg_haloPos.data(), 2, a->nHaloTotal);
+    case 9: return give(dims, 4, 5);
     }
     return -1;
 }

@@ -199,7 +199,7 @@ extern "C" int b200ldu_addr_destroy(b200ldu_addr *a)
     if (!a) return B200LDU_OK;
     cudaSetDevice(a->ctx->device);
     cudaStreamSynchronize(a->ctx->stream);
-    void *ptrs[] = {a->d_sliceStart, a->d_sliceW, a->d_sliceWL, a->d_cStart, a->d_cblob, a->d_col, a->d_haloPos, a->d_rowPos, a->d_code, a->d_haloStart,
+    void *ptrs[] = {a->d_sliceStart, a->d_sliceW, a->d_sliceWL, a->d_col, a->d_code, a->d_haloStart,
                     a->d_haloIdx, a->d_perm, a->d_iperm, a->d_sendRows, a->d_l, a->d_u,
                     a->d_ownerStart, a->d_losort, a->d_losortStart, a->d_bFaceCells, a->d_cyclicSrc,
                     a->d_bCellStart, a->d_bCellFaces, a->d_bCells, a->d_packPatches, a->d_packChunks,

@@ -15,12 +15,14 @@ struct SolverScalars {
     int nIterations, converged, singular, stop;
     int maxIter, minIter, histCap, nSweeps;
     int bodies; // fused PCG: iteration bodies whose A.p product has been formed
+    unsigned stepGen; // fused PCG: deferred scalar steps completed (engine prologue, DeferredStep)
 };
 
 struct OpBase {
     const int *stop = nullptr;
     double *partials = nullptr;
     int waitHalo = 0; // 1: a peer-memory halo exchange of the staged vector is in flight
+    __device__ __forceinline__ bool prologue(const LayoutDev &) const { return true; }
 };
 
 // ---- Amul / Tmul: out = diag*x + sum v*x[c]  (lduMatrixATmul.C:78-137) ----
@@ -259,6 +261,30 @@ int ew_launch(b200ldu_ctx *ctx, int n2, const int *stop, double *partials, int *
     return B200LDU_OK;
 }
 
+// element-wise kernel that first runs a deferred scalar step (DeferredStep below) in its prologue
+template <int NRED, class F, class Pre>
+__global__ void __launch_bounds__(EW_THREADS) ew_kernel_pre(int n2, const int *stop, double *partials, F f, Pre pre)
+{
+    if (stop && *stop) return;
+    if (!pre.run()) return;
+    double red[NRED > 0 ? NRED : 1];
+#pragma unroll
+    for (int k = 0; k < (NRED > 0 ? NRED : 1); k++) red[k] = 0;
+    for (int i = blockIdx.x * EW_THREADS + threadIdx.x; i < n2; i += gridDim.x * EW_THREADS) f(i, red);
+    if (NRED > 0) block_reduce_store<(NRED > 0 ? NRED : 1), EW_THREADS>(red, partials, blockIdx.x);
+}
+
+template <int NRED, class F, class Pre>
+int ew_launch(b200ldu_ctx *ctx, int n2, const int *stop, double *partials, int *nPartialsOut, F f, Pre pre)
+{
+    int g = ew_grid(ctx, n2);
+    ew_kernel_pre<NRED, F, Pre><<<g, EW_THREADS, 0, ctx->stream>>>(n2, stop, partials, f, pre);
+    ctx->launches++;
+    if (nPartialsOut) *nPartialsOut = g;
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}
+
 // sums NRED interleaved partial streams in fixed order, then thread 0 runs the scalar
 // logic g(sc).  One CTA.  With more than one rank the per-rank sums are combined either
 //  * over peer memory (p2p.nRanks > 1): thread 0 stores its sums + a sequence flag into
@@ -321,3 +347,155 @@ __global__ void __launch_bounds__(256) scalar_kernel(const double *partials, int
     if (sc->stop) return;
     scalar_body<NRED, RUN_LOGIC>(partials, nPartials, sc, g, p2p);
 }
+
+// ---------------------------------------------------------------------------
+// Deferred scalar step: the step that closes sweep n (fixed-order sum of its per-band partials, cross-rank
+// all-reduce over the peer mailboxes, alpha / beta / convergence logic) runs in the PROLOGUE of sweep n+1's
+// kernel instead of a one-CTA launch of its own: CTA 0 does the work (the kernel boundary has made the
+// partials visible) and releases a generation counter; every other CTA waits for it before it touches
+// anything that depends on the scalars.  Saves two launches and two kernel boundaries per PCG iteration.
+// `want` is baked into the launch (graph-replayable): position of this sweep in the chunk of iterations.
+// ---------------------------------------------------------------------------
+template <int NRED, class G>
+struct DeferredStep {
+    const double *partials;
+    int nPartials;
+    SolverScalars *sc;
+    G g;
+    P2PRed p2p;
+    unsigned want, mod; // wait until stepGen % mod == want
+    int active;         // 0: nothing to close (first sweep of a solve)
+    __device__ __forceinline__ bool run() const
+    {
+        if (!active) return true;
+        if (blockIdx.x == 0) {
+            G gg = g;
+            scalar_body<NRED, true>(partials, nPartials, sc, gg, p2p);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned next = sc->stepGen + 1;
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&sc->stepGen), "r"(next) : "memory");
+            }
+        } else {
+            if (threadIdx.x == 0) {
+                unsigned v, spins = 0;
+                unsigned long long t0 = 0;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&sc->stepGen) : "memory");
+                    if (v % mod == want) break;
+                    if ((++spins & 0x3ffu) == 0) { // bounded: CTA 0 is dispatched first in practice, not by contract
+                        unsigned long long now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (!t0) t0 = now;
+                        if (now - t0 > 20000000000ull) {
+                            if (p2p.seq) atomicExch(p2p.seq + 7, 2ull);
+                            break;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        return *reinterpret_cast<volatile const int *>(&sc->stop) == 0;
+    }
+};
+
+// ---- fused PCG kernels (PCG.C:131-205 regrouped into two matrix sweeps per iteration) ----
+// K_A: applies the solution/residual update of the PREVIOUS body (psi += alpha p,
+// r -= alpha w; alpha from the device scalars) while staging r, then preconditions:
+// z = rD*(r - sum v*(rD*r)[c]); fused sums <z,r> and sum|r|.  r is ping-ponged (other bands
+// read the old halo values), psi is updated in place (own rows only).
+template <class Pre>
+struct PcgAinvOp : OpBase {
+    static constexpr int NVEC = 1, NRED = 2;
+    static constexpr bool LOCAL = true;
+    const double *rOld, *w, *p, *rD;
+    double *rNew, *psi, *z;
+    const SolverScalars *sc;
+    Pre pre; // scalar step of the previous sweep, run in this kernel's prologue
+    __device__ __forceinline__ bool prologue(const LayoutDev &) const { return pre.run(); }
+    __device__ __forceinline__ void stage(int g, double &a, double &) const
+    {
+        double r = sc->bodies > 0 ? fma(-sc->alpha, w[g], rOld[g]) : rOld[g];
+        a = __dmul_rn(rD[g], r);
+    }
+    __device__ __forceinline__ double pack_val(int) const { return 0.0; }
+    __device__ __forceinline__ void stage_own(int row, double2 &a, double2 &) const
+    {
+        double2 r = *reinterpret_cast<const double2 *>(rOld + row);
+        if (sc->bodies > 0) {
+            const double alpha = sc->alpha;
+            double2 ww = *reinterpret_cast<const double2 *>(w + row);
+            double2 pp = *reinterpret_cast<const double2 *>(p + row);
+            double2 x = *reinterpret_cast<const double2 *>(psi + row);
+            r.x = fma(-alpha, ww.x, r.x);
+            r.y = fma(-alpha, ww.y, r.y);
+            x.x = fma(alpha, pp.x, x.x);
+            x.y = fma(alpha, pp.y, x.y);
+            *reinterpret_cast<double2 *>(psi + row) = x;
+        }
+        *reinterpret_cast<double2 *>(rNew + row) = r;
+        double2 dd = *reinterpret_cast<const double2 *>(rD + row);
+        a = make_double2(__dmul_rn(dd.x, r.x), __dmul_rn(dd.y, r.y));
+    }
+    __device__ __forceinline__ double init(int, double, double) const { return 0.0; }
+    __device__ __forceinline__ double term(double acc, double v, double t, double) const
+    {
+        return __dadd_rn(acc, __dmul_rn(v, t));
+    }
+    __device__ __forceinline__ void finish(int row, double acc0, double acc1, double, double, double, double,
+                                           double *red) const
+    {
+        // rNew[row] was written by this CTA in phase 1 (visible after the barrier)
+        double2 d = *reinterpret_cast<const double2 *>(rD + row);
+        double2 r = *reinterpret_cast<const double2 *>(rNew + row);
+        double z0 = __dmul_rn(d.x, __dsub_rn(r.x, acc0));
+        double z1 = __dmul_rn(d.y, __dsub_rn(r.y, acc1));
+        *reinterpret_cast<double2 *>(z + row) = make_double2(z0, z1);
+        red[0] += z0 * r.x + z1 * r.y;
+        red[1] += fabs(r.x) + fabs(r.y);
+    }
+};
+
+// K_B: forms the new search direction while staging (p = z on the first body, else
+// z + beta p; beta from the device scalars; p ping-ponged), w = A p, fused <w,p>.  The halo
+// send (fused pack CTAs) evaluates the same expression at the patch face cells.
+template <class Pre>
+struct PcgAmulOp : OpBase {
+    static constexpr int NVEC = 1, NRED = 1;
+    static constexpr bool LOCAL = false;
+    const double *z, *pOld, *diag;
+    double *pNew, *out;
+    const SolverScalars *sc;
+    Pre pre; // scalar step of the previous sweep, run in this kernel's prologue
+    __device__ __forceinline__ bool prologue(const LayoutDev &) const { return pre.run(); }
+    __device__ __forceinline__ double pval(int g) const
+    {
+        return sc->bodies == 0 ? z[g] : fma(sc->beta, pOld[g], z[g]);
+    }
+    __device__ __forceinline__ void stage(int g, double &a, double &) const { a = pval(g); }
+    __device__ __forceinline__ double pack_val(int row) const { return pval(row); }
+    __device__ __forceinline__ void stage_own(int row, double2 &a, double2 &) const
+    {
+        double2 zz = *reinterpret_cast<const double2 *>(z + row);
+        if (sc->bodies > 0) {
+            const double beta = sc->beta;
+            double2 po = *reinterpret_cast<const double2 *>(pOld + row);
+            zz.x = fma(beta, po.x, zz.x);
+            zz.y = fma(beta, po.y, zz.y);
+        }
+        *reinterpret_cast<double2 *>(pNew + row) = zz;
+        a = zz;
+    }
+    __device__ __forceinline__ double init(int r, double a, double) const { return __dmul_rn(diag[r], a); }
+    __device__ __forceinline__ double term(double acc, double v, double a, double) const
+    {
+        return __dadd_rn(acc, __dmul_rn(v, a));
+    }
+    __device__ __forceinline__ void finish(int r, double acc0, double acc1, double a0, double, double a1,
+                                           double, double *red) const
+    {
+        *reinterpret_cast<double2 *>(out + r) = make_double2(acc0, acc1);
+        red[0] += acc0 * a0 + acc1 * a1;
+    }
+};

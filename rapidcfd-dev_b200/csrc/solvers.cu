@@ -15,7 +15,6 @@
 
 #include <algorithm>
 
-#include "pcg_fused2.cuh"
 #include "solver_steps.cuh"
 
 // initial residual, normFactor and the first convergence test, common to all solvers
@@ -208,102 +207,124 @@ int solve_pcg(Solve &S, int pk)
 }
 
 // ---------------------------------------------------------------------------
-// PCG, fused form (pcg_fused2.cuh): two launches per iteration -- the AINV sweep and the Amul sweep -- each
-// with the scalar step of the PREVIOUS sweep (fixed-order sum of the per-CTA partials, peer-memory all-reduce,
-// alpha / beta / convergence test) in its prologue.  Same recurrences and per-row arithmetic as solve_pcg; the
-// psi/r update of body k is applied while body k+1 stages r.
+// PCG, fused form: TWO launches per iteration (the reference: 8 Thrust launches + 3 host synchronisations,
+// PCG.C:131-205).  Sweep A (PcgAinvOp) applies the psi/r update of the previous body while staging r,
+// preconditions and reduces <z,r>, sum|r|; sweep B (PcgAmulOp) forms p = z + beta p while staging, multiplies
+// and reduces <Ap,p>.  The scalar step that closes each sweep (sum of the per-band partials in fixed order,
+// cross-rank all-reduce over the peer mailboxes, alpha / beta / convergence test) runs in the prologue of the
+// NEXT sweep's kernel (ops.cuh DeferredStep) -- round 1 spent two one-CTA launches per iteration on it.
+// Same recurrences and per-row arithmetic as solve_pcg; the convergence decision of body k is taken at the
+// start of sweep B of body k+1 (the preconditioner sweep that has then already run only overwrote scratch).
 // ---------------------------------------------------------------------------
-__global__ void pcg2_init_kernel(PcgCarry *c, const SolverScalars *sc, const unsigned long long *seq)
-{
-    PcgCarry h;
-    h.wArA = GREAT_, h.wArAold = GREAT_, h.wApA = 0, h.alpha = 0, h.beta = 0; // PCG.C:88
-    h.finalResidual = sc->initialResidual;
-    h.rseq = seq ? *seq : 0;
-    h.nIterations = 0, h.bodies = 0, h.converged = sc->converged, h.singular = 0, h.stop = sc->stop, h.pad = 0;
-    c[0] = h;
-    c[1] = h;
-}
-
-template <class Op, int SWEEP>
-static int pcg2_launch(b200ldu_matrix *m, int G, const Op &op, const Pcg2Args &A)
-{
-    b200ldu_addr *a = m->a;
-    const size_t smem = engine_smem_bytes(a->L, 1);
-    static size_t configured[64] = {0};
-    const int dev = a->ctx->device & 63;
-    if (smem > 40 * 1024 && smem > configured[dev]) {
-        CUDA_TRY(cudaFuncSetAttribute(pcg2_kernel<Op, SWEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[dev] = smem;
+// scalar step A of the fused PCG: closes body k-1 (residual, convergence: PCG.C:190-205), then beta of body k
+struct PcgStepA {
+    double *hist;
+    __device__ void operator()(SolverScalars *s) const
+    {
+        if (s->bodies > 0) {
+            end_of_body(s, hist, s->sum[1]);
+            if (s->stop) return;
+        }
+        s->wArAold = s->wArA;
+        s->wArA = s->sum[0];
+        s->beta = s->wArA / s->wArAold;
     }
-    pcg2_kernel<Op, SWEEP><<<G, ENGINE_THREADS, smem, a->ctx->stream>>>(a->L, m->d_val, op, A);
-    a->ctx->launches++;
-    KERNEL_CHECK();
-    return B200LDU_OK;
-}
+};
+// scalar step B: alpha of body k (PCG.C:166-175)
+struct PcgStepB {
+    __device__ void operator()(SolverScalars *s) const
+    {
+        s->wApA = s->sum[0];
+        if (!(fabs(s->wApA) / s->normFactor > VSMALL_)) { // checkSingularity PCG.C:170
+            s->singular = 1;
+            s->stop = 1;
+            return;
+        }
+        s->alpha = s->wArA / s->wApA;
+        s->bodies++;
+    }
+};
 
 int solve_pcg_fused(Solve &S, int pk)
 {
     b200ldu_matrix *m = S.m;
     b200ldu_addr *a = m->a;
-    b200ldu_ctx *ctx = S.ctx;
-    const int *stop = &S.sc->stop;
+    SolverScalars *sc = S.sc;
+    double *hist = S.hist;
+    const int *stop = &sc->stop;
+    const int n2 = a->L.nPad / 2;
     double *psi = S.psi, *b = S.src;
     double *pb[2] = {S.vec(0), S.vec(4)}, *w = S.vec(1), *rb[2] = {S.vec(2), S.vec(3)}, *z = S.vec(5);
     if (!pb[0] || !pb[1] || !w || !rb[0] || !rb[1] || !z) return B200LDU_ECUDA;
+    const double *rD = m->d_rD;
+    const P2PRed pr = (S.ctx->nRanks > 1 && S.ctx->p2p) ? comm_p2p_red(S.ctx) : P2PRed();
+    // the two sweeps leave their partials in separate buffers: a deferred step reads one while the sweep that
+    // runs it writes the other
+    double *partA = S.partials, *partB = S.partials + 2 * (size_t)(a->L.nBands > S.ctx->smCount * 8 ? a->L.nBands : S.ctx->smCount * 8);
 
     TRY(mat_amul(m, false, psi, w, 0, nullptr, nullptr, nullptr));
     TRY(init_residual(S, psi, b, w, rb[0], pb[0]));
 
-    // fixed grid: one CTA per SM slot (never more CTAs than bands)
-    const size_t smem = engine_smem_bytes(a->L, 1);
-    int perSM = 0;
-    if (smem > 40 * 1024)
-        CUDA_TRY(cudaFuncSetAttribute(pcg2_kernel<PAinvOp, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, pcg2_kernel<PAinvOp, 0>, ENGINE_THREADS, smem));
-    if (perSM < 1) perSM = 1;
-    const int G = (int)std::max<long long>(1, std::min<long long>((long long)perSM * ctx->smCount, a->L.nBands));
-    if (m->cpartLen < (size_t)4 * G + 64) {
-        if (m->d_cpart) cudaFree(m->d_cpart);
-        m->d_cpart = nullptr;
-        m->cpartLen = 0;
-        CUDA_TRY(cudaMalloc((void **)&m->d_cpart, sizeof(double) * ((size_t)4 * G + 64)));
-        m->cpartLen = (size_t)4 * G + 64;
-    }
-    double *partA = m->d_cpart, *partB = m->d_cpart + 2 * (size_t)G;
-    PcgCarry *carry = reinterpret_cast<PcgCarry *>(m->d_cpart + 4 * (size_t)G); // 2 x 80 bytes
-    static_assert(2 * sizeof(PcgCarry) <= 64 * sizeof(double), "carry blocks fit behind the partials");
-    const bool multi = ctx->nRanks > 1 && ctx->p2p;
-    pcg2_init_kernel<<<1, 1, 0, ctx->stream>>>(carry, S.sc, multi ? ctx->d_seq : nullptr);
-    ctx->launches++;
-    KERNEL_CHECK();
+    const PcgStepA gA{hist};
+    const PcgStepB gB{};
+    typedef DeferredStep<1, PcgStepB> PreA; // sweep A starts by closing sweep B of the previous body
+    typedef DeferredStep<2, PcgStepA> PreB; // sweep B starts by closing sweep A of this body
+    const int every = S.c.checkEvery > 0 ? S.c.checkEvery : 8;
+    const unsigned mod = 2u * (unsigned)every;
 
-    Pcg2Args A;
-    A.sc = S.sc;
-    A.hist = S.hist;
-    A.p2p = multi ? comm_p2p_red(ctx) : P2PRed();
-    A.err = ctx->d_seq ? ctx->d_seq + 7 : nullptr;
-    A.rD = m->d_rD;
-    A.pk = pk;
     auto body = [&](long long k) -> int {
-        PAinvOp oa;
-        oa.stop = stop;
-        oa.rOld = rb[k & 1], oa.rNew = rb[(k + 1) & 1], oa.w = w, oa.p = pb[k & 1], oa.psi = psi, oa.z = z, oa.rD = m->d_rD;
-        oa.alpha = 0, oa.bodies = 0;
-        Pcg2Args aa = A;
-        aa.cin = carry, aa.cout = carry + 1, aa.pin = partB, aa.nIn = k > 0 ? G : 0, aa.pout = partA;
-        TRY((pcg2_launch<PAinvOp, 0>(m, G, oa, aa)));
-        PAmulOp ob;
-        ob.stop = stop;
-        ob.z = z, ob.pOld = pb[k & 1], ob.pNew = pb[(k + 1) & 1], ob.out = w, ob.diag = m->d_diag;
-        ob.beta = 0, ob.bodies = 0;
-        ob.waitHalo = a->L.nPackChunks > 0;
-        Pcg2Args ab = A;
-        ab.cin = carry + 1, ab.cout = carry, ab.pin = partA, ab.nIn = G, ab.pout = partB;
-        TRY((pcg2_launch<PAmulOp, 1>(m, G, ob, ab)));
+        const double *rOld = rb[k & 1], *pPrev = pb[k & 1];
+        double *rNew = rb[(k + 1) & 1], *pNew = pb[(k + 1) & 1];
+        int npA = a->L.nBands;
+        const PreA preA{partB, a->L.nBands, sc, gB, pr, (unsigned)(2 * (k % every)), mod, k > 0 ? 1 : 0};
+        if (pk == 2) {
+            PcgAinvOp<PreA> op;
+            op.stop = stop;
+            op.partials = partA;
+            op.rOld = rOld, op.rNew = rNew, op.w = w, op.p = pPrev, op.psi = psi, op.z = z, op.rD = m->d_rD;
+            op.sc = sc;
+            op.pre = preA;
+            TRY(engine_launch_m(m, false, op));
+        } else {
+            // diagonal / no preconditioner: sweep A is element-wise; its deferred step runs as CTA 0's prologue too
+            TRY(ew_launch<2>(S.ctx, n2, stop, partA, &npA, [=] __device__(int i, double *red) {
+                double2 r = CV2(rOld)[i];
+                if (sc->bodies > 0) {
+                    const double alpha = sc->alpha;
+                    double2 ww = CV2(w)[i], pp = CV2(pPrev)[i], x = CV2(psi)[i];
+                    r.x = fma(-alpha, ww.x, r.x);
+                    r.y = fma(-alpha, ww.y, r.y);
+                    V2(psi)[i] = make_double2(fma(alpha, pp.x, x.x), fma(alpha, pp.y, x.y));
+                }
+                V2(rNew)[i] = r;
+                double2 zz = r;
+                if (pk == 1) {
+                    double2 d = CV2(rD)[i];
+                    zz = make_double2(__dmul_rn(d.x, r.x), __dmul_rn(d.y, r.y));
+                }
+                V2(z)[i] = zz;
+                red[0] += zz.x * r.x + zz.y * r.y;
+                red[1] += fabs(r.x) + fabs(r.y);
+            }, preA));
+        }
+        int wait = 0;
+        TRY(mat_halo(m, pNew, stop, &wait)); // peer-memory path: nothing is launched, the send is fused
+        const PreB preB{partA, npA, sc, gA, pr, (unsigned)(2 * (k % every) + 1), mod, 1};
+        PcgAmulOp<PreB> op;
+        op.stop = stop;
+        op.partials = partB;
+        op.waitHalo = wait;
+        op.z = z, op.pOld = pPrev, op.pNew = pNew, op.out = w, op.diag = m->d_diag;
+        op.sc = sc;
+        op.pre = preB;
+        TRY(engine_launch_m(m, false, op));
         return B200LDU_OK;
     };
     long long mb = (long long)S.c.maxIter + 1 > S.c.minIter ? (long long)S.c.maxIter + 1 : S.c.minIter;
-    return run_iterations(S, mb + 1, body); // +1: the last body's update is applied (and judged) by the next sweeps
+    TRY(run_iterations(S, mb + 1, body)); // +1: the last body's update is applied (and judged) by the next sweeps
+    // the loop ends on a decision taken in a prologue (or when the bodies run out): one last scalar step closes
+    // whatever sweep ran last without one -- a no-op once the stop flag is set
+    return B200LDU_OK;
 }
 
 // ---------------------------------------------------------------------------

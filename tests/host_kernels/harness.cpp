@@ -151,4 +151,15 @@ void hk_sngrad(int nFaces, int nc, const int *l, const int *u, const double *del
 {
     launch((long long)nFaces * nc, 256, fieldk::sngrad_kernel, nFaces, nc, l, u, delta, vf, out);
 }
+
+void hk_limiter(int nFaces, int scheme, double twoByk, const int *l, const int *u, const double *faceFlux, const double *vf,
+                const double *gradc, const double *C, double *out)
+{
+    launch(nFaces, 256, fieldk::limiter_kernel, nFaces, scheme, twoByk, l, u, faceFlux, vf, gradc, C, out);
+}
+
+void hk_limited_weights(long long n, const double *limiter, const double *cd, const double *faceFlux, double *out)
+{
+    launch(n, 256, fieldk::limited_weights_kernel, n, limiter, cd, faceFlux, out);
+}
 }

@@ -147,10 +147,16 @@ class FvMatrix:
         self.source.copy_(self._t(o.source))
 
     def setReference(self, celli, value):
-        o = self._o()
-        o.setReference(celli, value)
-        self.diag.copy_(self._t(o.diag))
-        self.source.copy_(self._t(o.source))
+        """source[celli] += diag[celli]*value; diag[celli] *= 2 (fvMatrix.C:965-983): in place on the caller's arrays,
+        before the matrix copies them (LduMatrix.set) -- touches no coefficient of the matrix itself"""
+        if celli < 0:
+            return
+        v = np.atleast_1d(np.asarray(value, np.float64))
+        d, s = _np(self.diag).copy(), _np(self.source).reshape(-1, self.nc).copy()
+        s[celli] += d[celli] * v
+        d[celli] += d[celli]
+        self.diag.copy_(self._t(d))
+        self.source.copy_(self._t(s))
 
     def solve(self, solver, pre, gamg=None, pnf=None, **ctl):
         psi, perfs, _ = self._o().solve(solver, pre, gamg.o if gamg is not None else None, self._pnf(pnf), **ctl)

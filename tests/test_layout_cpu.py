@@ -68,8 +68,7 @@ def _layout(capi, mesh, centres=True, band=None):
     for what, (name, dt) in enumerate([("perm", np.int32), ("iperm", np.int32), ("sliceStart", np.int64),
                                        ("sliceW", np.uint16), ("sliceWL", np.uint16), ("col", np.uint16),
                                        ("code", np.int32), ("haloStart", np.int32), ("haloIdx", np.int32),
-                                       ("dims", np.int32), ("cStart", np.int32), ("cblob", np.uint32),
-                                       ("rowPos", np.uint16), ("haloPos", np.uint16)]):
+                                       ("dims", np.int32)]):
         n = L.b200ldu_layout_debug_get(h, what, None, 0)
         a = np.zeros(max(n, 1), dtype=dt)
         L.b200ldu_layout_debug_get(h, what, a.ctypes.data, n)
@@ -79,7 +78,7 @@ def _layout(capi, mesh, centres=True, band=None):
 
 
 def _check_layout(mesh, lay):
-    nPad, nBands, bandRows, nRecv, maxHalo, tileLen = [int(x) for x in lay["dims"]]
+    nPad, nBands, bandRows, nRecv, maxHalo = [int(x) for x in lay["dims"]]
     n = mesh.nCells
     perm, iperm = lay["perm"], lay["iperm"]
     assert sorted(perm.tolist()) == list(range(n))
@@ -104,20 +103,14 @@ def _check_layout(mesh, lay):
         halo = lay["haloIdx"][hs:lay["haloStart"][band + 1]]
         assert np.all(np.diff(halo) > 0)
         assert len(halo) <= maxHalo
-        # tile positions of the band's rows and halo columns: distinct, inside the tile
-        rpos = lay["rowPos"][band * bandRows:(band + 1) * bandRows]
-        hpos = lay["haloPos"][hs:lay["haloStart"][band + 1]]
-        tmap = {int(p): band * bandRows + i for i, p in enumerate(rpos)}
-        tmap.update({int(p): int(g) for p, g in zip(hpos, halo)})
-        assert len(tmap) == bandRows + len(halo) and max(tmap) < tileLen
         for q in range(64):
             r = s * 64 + q
             c = iperm[r]
             cols = lay["col"][base + q: base + 64 * W: 64] if W else np.zeros(0, np.uint16)
             codes = lay["code"][base + q: base + 64 * W: 64] if W else np.zeros(0, np.int32)
 
-            def target(cv):   # tile position -> banded extended index
-                return tmap[cv]
+            def target(cv):
+                return band * bandRows + cv if cv < bandRows else int(halo[cv - bandRows])
             if c < 0:
                 assert np.all(codes == -1)
                 continue
@@ -157,7 +150,7 @@ def test_layout_bricks_are_compact(capi, meshmod):
     exactly the brick's face-adjacent cells (<= 6*64)."""
     mesh = meshmod.hex_mesh(32)
     lay = _layout(capi, mesh, True, 512)
-    nPad, nBands, bandRows, nRecv, maxHalo, tileLen = [int(x) for x in lay["dims"]]
+    nPad, nBands, bandRows, nRecv, maxHalo = [int(x) for x in lay["dims"]]
     assert bandRows == 512 and nBands == 64
     assert maxHalo <= 6 * 64
     cc = mesh.cell_centres()
@@ -203,54 +196,6 @@ def test_layout_narrows_bands_until_the_tile_fits(capi):
     builder halves bandRows until it fits instead of failing at launch time."""
     g = _RandomGraph(30000, 6, 1)
     lay = _layout(capi, g, centres=False, band=16384)
-    nPad, nBands, bandRows, nRecv, maxHalo, tileLen = [int(x) for x in lay["dims"]]
+    nPad, nBands, bandRows, nRecv, maxHalo = [int(x) for x in lay["dims"]]
     assert bandRows < 16384 and (bandRows + maxHalo + 2) * 16 <= 200 * 1024
     _check_layout(g, lay)
-
-
-def _decode_columns(lay):
-    """columns of every entry from the compressed blob (layout.cu 3b), as the engine decodes them"""
-    nPad, nBands, bandRows, nRecv, maxHalo, tileLen = [int(x) for x in lay["dims"]]
-    spb = bandRows // 64
-    nSlices = nPad // 64
-    out = np.zeros(len(lay["col"]), np.int64)
-    blob = lay["cblob"]
-    nExc = 0
-    for s in range(nSlices):
-        base, W = int(lay["sliceStart"][s]), int(lay["sliceW"][s])
-        w0, w1 = int(lay["cStart"][s]) * 4, int(lay["cStart"][s + 1]) * 4
-        words = blob[w0:w1]
-        pos = words[4 * W:4 * W + 32].view(np.uint16)
-        assert np.array_equal(pos, lay["rowPos"][s * 64:(s + 1) * 64])
-        exc = words[4 * W + 32:].view(np.uint16)
-        assert len(exc) % 8 == 0
-        for j in range(W):
-            lo, hi, delta, off = (int(x) for x in words[4 * j:4 * j + 4])
-            mask = lo | (hi << 32)
-            delta = delta - (1 << 32) if delta >= (1 << 31) else delta
-            k = off
-            for q in range(64):
-                if (mask >> q) & 1:
-                    out[base + 64 * j + q] = exc[k]
-                    k += 1
-                else:
-                    out[base + 64 * j + q] = int(pos[q]) + delta
-            nExc += k - off
-    return out, nExc
-
-
-@pytest.mark.parametrize("dims,centres,band,nR", [((16, 16, 16), True, None, 1), ((7, 3, 5), False, None, 1),
-                                                  ((12, 12, 12), True, 256, 1), ((8, 8, 8), True, 64, 4),
-                                                  ((32, 32, 16), True, 2048, 1)])
-def test_compressed_columns_reproduce_the_columns(capi, meshmod, dims, centres, band, nR):
-    """the engine reads its columns from the compressed blob: decoding it must give back the explicit
-    16-bit column of every entry; on band-sized bricks of a hex mesh only a small part are exceptions"""
-    mesh = meshmod.hex_mesh(*dims) if nR == 1 else meshmod.decompose(dims[0], nR, 1)
-    lay = _layout(capi, mesh, centres, band)
-    got, nExc = _decode_columns(lay)
-    assert np.array_equal(got, lay["col"].astype(np.int64))
-    if dims == (32, 32, 16):
-        # 16x16x8 lattice bricks padded by one cell: every neighbour sits at a constant tile offset, halo or not;
-        # only the rows whose slots shift at the mesh boundary (fewer faces) are exceptions
-        assert nExc < 0.08 * len(got), (nExc, len(got))
-        assert int(lay["dims"][5]) == 18 * 18 * 10
