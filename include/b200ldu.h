@@ -291,6 +291,17 @@ int b200ldu_field_gather(b200ldu_ctx *ctx, int n, int nComp, const int *cells_d,
  * and the non-orthogonal correction (correctedSnGrad.C:44-75, gaussLaplacianScheme.C:92-130: corrVecs & interpolate(grad))
  * are compositions of entry points of this header (rapidcfd-dev_b200/fvc.py: laplacian, snGrad_correction). */
 int b200ldu_fv_sngrad(b200ldu_addr *a, int nComp, const double *deltaCoeffs_d, const double *vf_d, double *out_d);
+/* ---- lduMatrix algebra on caller-order coefficient arrays (LDU/lduMatrix/lduMatrixOperations.C) ----
+ * row_sum: mode 0 sumDiag (:36-57), 1 negSumDiag (:59-80), 2 sumMagOffDiag (:83-104); lower_d NULL = symmetric; in place.
+ * add_assign: A += B / A -= B with the reference's rules for every combination of diagonal / symmetric / asymmetric
+ *   matrices (:235-397); has[3] = {diag, upper, lower} present; hasA is updated (symmetric += asymmetric becomes
+ *   asymmetric, diagonal += X takes X's triangles).  scale: A *= cell field (:400-441) or A *= s (sf_d NULL, :444-462). */
+int b200ldu_ldu_row_sum(b200ldu_addr *a, int mode, const double *upper_d, const double *lower_d, double *inout_d);
+int b200ldu_ldu_add_assign(b200ldu_addr *a, int subtract, double *diagA_d, double *upperA_d, double *lowerA_d, int *hasA,
+                           const double *diagB_d, const double *upperB_d, const double *lowerB_d, const int *hasB);
+int b200ldu_ldu_scale(b200ldu_addr *a, const double *sf_d, double s, double *diagA_d, double *upperA_d, double *lowerA_d,
+                      const int *hasA);
+
 /* ---- limited / upwind interpolation (FV/interpolation/surfaceInterpolation/limitedSchemes/) ----
  * b200ldu_fv_limiter: limiter field on the internal faces, LimitedScheme<..>::calcLimiter (LimitedScheme.C:60-140) with
  *   NVDTVD::r (NVDTVD.H:99-127); scheme "upwind" (0, upwind.H:103-118) | "linear" (1) | "limitedLinear" (coefficient k,

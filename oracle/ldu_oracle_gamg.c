@@ -186,8 +186,8 @@ static orc_addr *coarse_addressing(const orc_addr *fine, const int *rmap, int nC
     return ca;
 }
 
-/* processorGAMGInterface: coarse patch faces of every coupled patch
- * (interfaces/processorGAMGInterface/processorGAMGInterface.C:60-140).  nbrMap holds the
+/* processorGAMGInterface / cyclicGAMGInterface: coarse patch faces of every coupled patch
+ * (interfaces/processorGAMGInterface/processorGAMGInterface.C:60-140, cyclicGAMGInterface/cyclicGAMGInterface.C:70-150).  nbrMap holds the
  * neighbour side's restrict-map values per fine patch face (internalFieldTransfer). */
 static void coarse_interfaces(const orc_addr *fine, const int *rmap, const double *nbrMap, int myRank,
                               int **cPatchStartOut, int **cFaceCellsOut, int **pfRestrictOut)
@@ -208,7 +208,11 @@ static void coarse_interfaces(const orc_addr *fine, const int *rmap, const doubl
         int np = 0;
         for (int i = s0; i < s1; i++) {
             int mine = rmap[fine->faceCells[i]], theirs = (int)nbrMap[i];
-            int a = myRank < nb ? mine : theirs, b = myRank < nb ? theirs : mine;
+            /* master side first so that both sides enumerate the same pairs: the lower rank for a processor patch
+             * (processorGAMGInterface.C:93-118), the owner patch = lower patch index for a cyclic pair
+             * (cyclicGAMGInterface.C:104-127; nb = -(q+1), cyclicLduInterface::owner()) */
+            int master = nb >= 0 ? (myRank < nb) : (p < -nb - 1);
+            int a = master ? mine : theirs, b = master ? theirs : mine;
             int found = -1;
             for (int k = np - 1; k >= 0; k--) /* recent pairs first: patches are locally ordered */
                 if (pa[k] == a && pb[k] == b) {
@@ -596,14 +600,17 @@ static dense_lu *lu_factor(const orc_matrix *A, const orc_comm *comm)
         rows[(size_t)a->l[f] * N + offs[me] + a->u[f]] += A->upper[f];
         rows[(size_t)a->u[f] * N + offs[me] + a->l[f]] += A->lower[f];
     }
-    if (R > 1 && a->nPatches) {
+    if (a->nPatches && a->neighbRank) { /* coupled patches: processor (another rank's columns) or cyclic (this rank's) */
         double *ids = (double *)malloc(sizeof(double) * (size_t)nl);
         for (int c = 0; c < nl; c++) ids[c] = (double)c;
         double *nbrCell = orc_halo_exchange(a, ids, comm);
         free(ids);
-        for (int p = 0; p < a->nPatches; p++)
+        for (int p = 0; p < a->nPatches; p++) {
+            int nbRank = a->neighbRank[p] >= 0 ? a->neighbRank[p] : me;
+            if (nbRank != me && R == 1) continue;
             for (int i = a->patchStart[p]; i < a->patchStart[p + 1]; i++)
-                rows[(size_t)a->faceCells[i] * N + offs[a->neighbRank[p]] + (int)nbrCell[i]] -= A->bou[i];
+                rows[(size_t)a->faceCells[i] * N + offs[nbRank] + (int)nbrCell[i]] -= A->bou[i];
+        }
         free(nbrCell);
     }
     d->lu = (double *)calloc((size_t)N * N, sizeof(double));

@@ -67,7 +67,7 @@ EXPORTS = [
     "b200ldu_fvm_add_boundary_diag", "b200ldu_fvm_add_boundary_source", "b200ldu_fvm_A", "b200ldu_fvm_H",
     "b200ldu_fvm_flux", "b200ldu_fvm_residual", "b200ldu_fvm_relax", "b200ldu_fvm_set_reference",
     "b200ldu_fvm_solve", "b200ldu_fv_patch_neighbour_field",
-    "b200ldu_fv_sngrad", "b200ldu_fv_limiter", "b200ldu_fv_limited_weights", "b200ldu_field_binary", "b200ldu_field_unary", "b200ldu_field_dot3", "b200ldu_field_gather",
+    "b200ldu_ldu_row_sum", "b200ldu_ldu_add_assign", "b200ldu_ldu_scale", "b200ldu_fv_sngrad", "b200ldu_fv_limiter", "b200ldu_fv_limited_weights", "b200ldu_field_binary", "b200ldu_field_unary", "b200ldu_field_dot3", "b200ldu_field_gather",
 ]
 
 _lib = None
@@ -144,6 +144,9 @@ def lib():
     L.b200ldu_fvm_set_reference.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     L.b200ldu_fv_patch_neighbour_field.argtypes = [vp, C.c_int, vp, vp]
     L.b200ldu_fv_sngrad.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.b200ldu_ldu_row_sum.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.b200ldu_ldu_add_assign.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.b200ldu_ldu_scale.argtypes = [vp, vp, C.c_double, vp, vp, vp, vp]
     L.b200ldu_fv_limiter.argtypes = [vp, C.c_char_p, C.c_double, vp, vp, vp, vp, vp]
     L.b200ldu_fv_limited_weights.argtypes = [vp, C.c_longlong, vp, vp, vp, vp]
     L.b200ldu_field_binary.argtypes = [vp, C.c_int, C.c_longlong, C.c_int, vp, C.c_int, vp, vp]
@@ -590,6 +593,49 @@ def fv_sngrad(addr, nComp, deltaCoeffs, vf):
     out = _newlike(vf, addr.nFaces * nComp)
     check(lib().b200ldu_fv_sngrad(addr.h, nComp, _dp(deltaCoeffs), _dp(vf), _dp(out)))
     return out
+
+
+class LduCoeffs:
+    """diag / upper / lower device arrays with presence flags: the optional arrays of the reference's lduMatrix, for
+    the algebra of lduMatrixOperations.C (sumDiag ..., operator+= -= *=)"""
+
+    def __init__(self, addr, diag=None, upper=None, lower=None):
+        import torch
+        self.addr = addr
+        dev = addr.ctx.device
+        z = lambda n: torch.zeros(max(n, 1), dtype=torch.float64, device=dev)
+        self.has = (C.c_int * 3)(diag is not None, upper is not None, lower is not None)
+        self.diag = diag.clone() if diag is not None else z(addr.nCells)
+        self.upper = upper.clone() if upper is not None else z(addr.nFaces)
+        self.lower = lower.clone() if lower is not None else z(addr.nFaces)
+
+    def _combine(self, other, sub):
+        check(lib().b200ldu_ldu_add_assign(self.addr.h, sub, _dp(self.diag), _dp(self.upper), _dp(self.lower), self.has,
+                                           _dp(other.diag), _dp(other.upper), _dp(other.lower), other.has))
+        return self
+
+    def __iadd__(self, other):
+        return self._combine(other, 0)
+
+    def __isub__(self, other):
+        return self._combine(other, 1)
+
+    def scale(self, s):
+        """*= a cell field (tensor) or a scalar"""
+        sf = None if isinstance(s, (int, float)) else s
+        check(lib().b200ldu_ldu_scale(self.addr.h, _dp(sf), float(s) if sf is None else 0.0, _dp(self.diag), _dp(self.upper),
+                                      _dp(self.lower), self.has))
+        return self
+
+    def row_sum(self, mode, inout):
+        """0 sumDiag, 1 negSumDiag, 2 sumMagOffDiag; in place on `inout`"""
+        check(lib().b200ldu_ldu_row_sum(self.addr.h, mode, _dp(self.upper) if self.has[1] else _dp(self.lower),
+                                        _dp(self.lower) if self.has[2] else None, _dp(inout)))
+        return inout
+
+    def arrays(self):
+        return (self.diag[: self.addr.nCells] if self.has[0] else None, self.upper[: self.addr.nFaces] if self.has[1] else None,
+                self.lower[: self.addr.nFaces] if self.has[2] else None)
 
 
 def fv_limiter(addr, scheme, faceFlux, vf, gradc, centres, k=1.0):

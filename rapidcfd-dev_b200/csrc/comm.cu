@@ -349,6 +349,18 @@ int comm_exchange_patch_ints(b200ldu_ctx *ctx, int nPatches, const int *patchSta
 {
     int tot = nPatches ? patchStart[nPatches] : 0;
     if (tot == 0) return B200LDU_OK;
+    // cyclic pairs (neighbRank = -(q+1)): the neighbour values are this rank's own, at the partner patch
+    // (cyclicGAMGInterface::internalFieldTransfer, cyclicGAMGInterface.C:163-180)
+    bool remote = false;
+    for (int p = 0; p < nPatches; p++) {
+        if (neighbRank[p] >= 0) {
+            remote = true;
+            continue;
+        }
+        const int q = -neighbRank[p] - 1, n = patchStart[p + 1] - patchStart[p];
+        for (int i = 0; i < n; i++) recv[patchStart[p] + i] = send[patchStart[q] + i];
+    }
+    if (!remote) return B200LDU_OK;
     if (!ctx->nccl) {
         b200_set_error("processor patches present but no communicator (b200ldu_comm_init)");
         return B200LDU_ENCCL;
@@ -361,12 +373,17 @@ int comm_exchange_patch_ints(b200ldu_ctx *ctx, int nPatches, const int *patchSta
     NCCL_TRY(ncclGroupStart());
     for (int p = 0; p < nPatches; p++) {
         int s = patchStart[p], n = patchStart[p + 1] - s;
+        if (neighbRank[p] < 0) continue;
         NCCL_TRY(ncclSend(d_s + s, n, ncclInt, neighbRank[p], (ncclComm_t)ctx->nccl, st));
         NCCL_TRY(ncclRecv(d_r + s, n, ncclInt, neighbRank[p], (ncclComm_t)ctx->nccl, st));
     }
     NCCL_TRY(ncclGroupEnd());
-    CUDA_TRY(cudaMemcpyAsync(recv, d_r, sizeof(int) * (size_t)tot, cudaMemcpyDeviceToHost, st));
+    std::vector<int> got((size_t)tot);
+    CUDA_TRY(cudaMemcpyAsync(got.data(), d_r, sizeof(int) * (size_t)tot, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    for (int p = 0; p < nPatches; p++)
+        if (neighbRank[p] >= 0)
+            for (int i = patchStart[p]; i < patchStart[p + 1]; i++) recv[i] = got[i];
     cudaFree(d_s);
     cudaFree(d_r);
     return B200LDU_OK;

@@ -113,8 +113,7 @@ template <class Op>
 __global__ void __launch_bounds__(ENGINE_THREADS, 6) engine_kernel(const LayoutDev L, const double *__restrict__ val, Op op)
 {
     extern __shared__ double smem[];
-    if (op.stop && *op.stop) return;
-    if (!op.prologue(L)) return;
+    if (!op.prologue(L)) return; // stop flag (OpBase) or the deferred scalar step of the fused PCG (ops.cuh)
     // Fused halo send (peer-memory path): the first nPackChunks CTAs of the grid gather psi
     // at the processor-patch face cells, store it straight into the neighbours' receive
     // buffers over NVLink and release their arrival flags; all other CTAs are SpMV bands

@@ -222,8 +222,8 @@ extern "C" int b200ldu_gamg_create(b200ldu_addr *a, const double *faceWeights_h,
         return B200LDU_EINVAL;
     }
     for (int p = 0; p < a->nPatches; p++)
-        if (a->neighbRank[p] < 0 || a->neighbRank[p] == a->ctx->rank) {
-            b200_set_error("GAMG: cyclic interfaces are not supported (Krylov and smooth solvers are)");
+        if (a->neighbRank[p] == a->ctx->rank && a->ctx->nRanks > 1) {
+            b200_set_error("GAMG: patch %d names this rank as its neighbour; cyclic patches are declared with neighbRank = -(partnerPatch + 1)", p);
             return B200LDU_EINVAL;
         }
     CUDA_TRY(cudaSetDevice(a->ctx->device));
@@ -391,7 +391,8 @@ extern "C" int b200ldu_gamg_create(b200ldu_addr *a, const double *faceWeights_h,
             for (int C = 0; C < nCoarse; C++)
                 for (int k = 0; k < 3; k++) H.cc[3 * (size_t)C + k] /= cn[C];
         }
-        // processor interfaces of the coarse level (processorGAMGInterface.C:60-140): unique
+        // processor / cyclic interfaces of the coarse level (processorGAMGInterface.C:60-140,
+        // cyclicGAMGInterface.C:70-150): unique
         // (master cell, slave cell) pairs in order of first appearance along every fine patch
         H.nFinePF = nPatches ? fPatchStart[nPatches] : 0;
         H.pfRestrict.assign(std::max(H.nFinePF, 1), 0);
@@ -405,11 +406,14 @@ extern "C" int b200ldu_gamg_create(b200ldu_addr *a, const double *faceWeights_h,
             int nC = 0;
             for (int p = 0; p < nPatches; p++) {
                 const int nb = a->neighbRank[p], me = a->ctx->rank;
+                // master side first so that both sides enumerate the same pairs: the lower rank of a processor
+                // patch, the owner (= lower patch index) of a cyclic pair (cyclicGAMGInterface.C:104-127)
+                const bool master = nb >= 0 ? (me < nb) : (p < -nb - 1);
                 H.cPatchStart[p] = nC;
                 std::vector<std::pair<int, int>> pairs;
                 for (int i = fPatchStart[p]; i < fPatchStart[p + 1]; i++) {
-                    std::pair<int, int> pr = me < nb ? std::make_pair(sendMap[i], nbrMap[i])
-                                                     : std::make_pair(nbrMap[i], sendMap[i]);
+                    std::pair<int, int> pr = master ? std::make_pair(sendMap[i], nbrMap[i])
+                                                    : std::make_pair(nbrMap[i], sendMap[i]);
                     int found = -1;
                     for (int k = (int)pairs.size() - 1; k >= 0; k--)
                         if (pairs[k] == pr) {
@@ -460,7 +464,7 @@ extern "C" int b200ldu_gamg_create(b200ldu_addr *a, const double *faceWeights_h,
     g->nLevels = (int)g->lev.size();
     // coarsest level across the ranks: sizes, offsets and the neighbour-side cell of every
     // coarsest processor-patch face (columns of the global matrix, LUscalarMatrix.C:201-270)
-    if (g->nLevels > 0 && a->ctx->nRanks > 1) {
+    if (g->nLevels > 0 && (a->ctx->nRanks > 1 || nPatches)) {
         GamgLevel &LC = g->lev[g->nLevels - 1];
         const int R = a->ctx->nRanks;
         double mine = LC.nCoarse;
@@ -475,7 +479,7 @@ extern "C" int b200ldu_gamg_create(b200ldu_addr *a, const double *faceWeights_h,
                 g->coarsestOffs[r + 1] = g->coarsestOffs[r] + g->coarsestCounts[r];
                 g->nMaxCoarsest = std::max(g->nMaxCoarsest, g->coarsestCounts[r]);
             }
-            if (g->nMaxCoarsest > P2P_GMAX) {
+            if (R > 1 && g->nMaxCoarsest > P2P_GMAX) {
                 b200_set_error("GAMG: coarsest level has %d cells on one rank; the multi-rank direct solve "
                                "supports up to %d (lower nCellsInCoarsestLevel)", g->nMaxCoarsest, P2P_GMAX);
                 rc = B200LDU_EINVAL;
@@ -795,20 +799,25 @@ static int gamg_coarsest_inverse(Solve &S, b200ldu_gamg *g)
         rows[(size_t)nb * N + off + o] += l[f];
     }
     std::vector<double> A;
-    if (R > 1) {
-        // the neighbour's banded numbering is not known here: the neighbour-side cell index was
-        // exchanged in caller order, so all ranks also gather their perm to translate columns
-        std::vector<double> permD((size_t)nMax, -1.0), permAll((size_t)nMax * R);
+    if (L.addr->nPatches) {
+        // coupled patches: the coefficient sits at the neighbour cell's column -- another rank's block for a
+        // processor patch (LUscalarMatrix.C:201-270), this rank's own for a cyclic pair.  The neighbour's banded
+        // numbering is not known here: the neighbour-side cell index was exchanged in caller order, so all ranks
+        // also gather their perm to translate columns
+        std::vector<double> permD((size_t)std::max(nMax, 1), -1.0), permAll((size_t)std::max(nMax, 1) * R);
         for (int c = 0; c < n; c++) permD[c] = perm[c];
-        TRY(comm_allgather_host(ctx, permD.data(), nMax, permAll.data()));
+        TRY(comm_allgather_host(ctx, permD.data(), std::max(nMax, 1), permAll.data()));
         for (int p = 0; p < L.addr->nPatches; p++) {
-            int nbr = L.addr->neighbRank[p];
+            const int nbr = L.addr->neighbRank[p] >= 0 ? L.addr->neighbRank[p] : me;
+            const int nbrOff = R > 1 ? g->coarsestOffs[nbr] : 0;
             for (int i = L.cPatchStart[p]; i < L.cPatchStart[p + 1]; i++) {
                 int row = perm[L.cFaceCells[i]];
-                int col = g->coarsestOffs[nbr] + (int)permAll[(size_t)nbr * nMax + g->coarsestNbrCell[i]];
+                int col = nbrOff + (int)permAll[(size_t)nbr * std::max(nMax, 1) + g->coarsestNbrCell[i]];
                 rows[(size_t)row * N + col] -= bou[i];
             }
         }
+    }
+    if (R > 1) {
         std::vector<double> all((size_t)R * nMax * N);
         TRY(comm_allgather_host(ctx, rows.data(), nMax * N, all.data()));
         A.assign((size_t)N * N, 0.0);

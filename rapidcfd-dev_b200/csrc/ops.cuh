@@ -15,14 +15,19 @@ struct SolverScalars {
     int nIterations, converged, singular, stop;
     int maxIter, minIter, histCap, nSweeps;
     int bodies; // fused PCG: iteration bodies whose A.p product has been formed
-    unsigned stepGen; // fused PCG: deferred scalar steps completed (engine prologue, DeferredStep)
+    // fused PCG, deferred scalar steps (DeferredStep): steps completed (low 32 bits) | stop (bit 63), published by CTA 0 of
+    // each sweep with one release store and read by every other CTA with one acquire load.  On its own 128-byte line so
+    // that the waiting CTAs' polling does not slow down CTA 0's writes to the scalars above.
+    alignas(128) unsigned long long gate;
+    unsigned long long gatePad[15];
 };
 
 struct OpBase {
     const int *stop = nullptr;
     double *partials = nullptr;
     int waitHalo = 0; // 1: a peer-memory halo exchange of the staged vector is in flight
-    __device__ __forceinline__ bool prologue(const LayoutDev &) const { return true; }
+    // first thing every CTA of an engine kernel does; false => the CTA exits (the device has decided to stop)
+    __device__ __forceinline__ bool prologue(const LayoutDev &) const { return !(stop && *stop); }
 };
 
 // ---- Amul / Tmul: out = diag*x + sum v*x[c]  (lduMatrixATmul.C:78-137) ----
@@ -367,36 +372,50 @@ struct DeferredStep {
     int active;         // 0: nothing to close (first sweep of a solve)
     __device__ __forceinline__ bool run() const
     {
-        if (!active) return true;
+        if (!active) return *reinterpret_cast<volatile const int *>(&sc->stop) == 0;
+        __shared__ unsigned long long gateSeen;
         if (blockIdx.x == 0) {
+            if (*reinterpret_cast<volatile const int *>(&sc->stop)) {
+                // stopped before this sweep (e.g. converged at the initial residual): tell the waiting CTAs
+                if (threadIdx.x == 0) {
+                    const unsigned long long v = sc->gate | (1ull << 63);
+                    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&sc->gate), "l"(v) : "memory");
+                }
+                return false;
+            }
             G gg = g;
             scalar_body<NRED, true>(partials, nPartials, sc, gg, p2p);
             __syncthreads();
             if (threadIdx.x == 0) {
-                const unsigned next = sc->stepGen + 1;
-                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&sc->stepGen), "r"(next) : "memory");
+                const unsigned long long next = ((sc->gate & 0xffffffffull) + 1) | ((unsigned long long)(sc->stop != 0) << 63);
+                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&sc->gate), "l"(next) : "memory");
+                gateSeen = next;
             }
         } else {
             if (threadIdx.x == 0) {
-                unsigned v, spins = 0;
-                unsigned long long t0 = 0;
+                unsigned long long v, t0 = 0;
+                unsigned spins = 0;
                 for (;;) {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&sc->stepGen) : "memory");
-                    if (v % mod == want) break;
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(&sc->gate) : "memory");
+                    // this sweep's step is done, or an earlier sweep already stopped the solve (then nothing advances)
+                    if ((unsigned)(v & 0xffffffffull) % mod == want || (v >> 63)) break;
+                    __nanosleep(64);
                     if ((++spins & 0x3ffu) == 0) { // bounded: CTA 0 is dispatched first in practice, not by contract
                         unsigned long long now;
                         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
                         if (!t0) t0 = now;
                         if (now - t0 > 20000000000ull) {
                             if (p2p.seq) atomicExch(p2p.seq + 7, 2ull);
+                            v |= 1ull << 63;
                             break;
                         }
                     }
                 }
+                gateSeen = v;
             }
-            __syncthreads();
         }
-        return *reinterpret_cast<volatile const int *>(&sc->stop) == 0;
+        __syncthreads();
+        return (gateSeen >> 63) == 0;
     }
 };
 

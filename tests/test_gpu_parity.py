@@ -336,7 +336,7 @@ def test_fv_fused_interpolation_bit_exact(gpu, meshmod, orc):
 @pytest.mark.parametrize("kind", ["P", "U"])
 def test_cyclic_interfaces(gpu, meshmod, orc, kind):
     """Cyclic coupled patches (neighbRank = -(partner+1)): matrix operations bit-exact with the
-    oracle, Krylov and smooth solvers to the usual history tolerance, GAMG refuses them."""
+    oracle, Krylov and smooth solvers to the usual history tolerance, GAMG with cyclicGAMGInterface coarse levels."""
     from test_oracle_core import _cyclic_case
     capi, ctx, torch = gpu
     m, c, ps, fc, nr, lo, hi = _cyclic_case(meshmod, kind)
@@ -375,7 +375,20 @@ def test_cyclic_interfaces(gpu, meshmod, orc, kind):
         _cmp_hist(hist, href, first=10, rtol=1e-8)
         _cmp_hist(hist, href, first=30, rtol=1e-4, floor=1e-8)
         np.testing.assert_allclose(psi.cpu().numpy(), psi_ref, rtol=0, atol=1e-5)
-    with pytest.raises(Exception, match="cyclic"):
-        capi.GamgAgglomeration(addr, np.ones(m.nFaces), 4)
+    # GAMG over the cyclic pair (cyclicGAMGInterface): same agglomeration maps and cycle counts as the oracle
+    fw = meshmod.face_area_pair_weights(m)
+    og = orc.Gamg(oa, fw, 4, 1)
+    gg = capi.GamgAgglomeration(addr, fw, 4, 1)
+    assert gg.nLevels == og.nLevels
+    for lev in range(gg.nLevels):
+        assert np.array_equal(gg.restrict_addr(lev), og.restrict_addr(lev))
+    ctl = dict(tolerance=1e-9, maxIter=200)
+    psi_ref, pr, href = og.solve(om, "GaussSeidel", np.zeros(m.nCells), rhs, **ctl)
+    psi = torch.zeros(m.nCells, dtype=torch.float64, device=ctx.device)
+    perf, hist = mat.solve("GAMG", "GaussSeidel", psi, t(rhs), gamg=gg, histCap=512, **ctl)
+    assert perf.converged and perf.nIterations == pr.nIterations, (perf.nIterations, pr.nIterations)
+    np.testing.assert_allclose(hist[: len(href)], href, rtol=1e-8)
+    np.testing.assert_allclose(psi.cpu().numpy(), x, rtol=0, atol=1e-6)
+    gg.close()
     mat.close()
     addr.close()

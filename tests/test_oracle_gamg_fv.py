@@ -179,3 +179,35 @@ def test_fv_face_sums_vs_numpy(meshmod, orc):
     np.testing.assert_allclose(A2.sum(0), 0, atol=1e-12)   # conservative: column sums vanish
     vf = rng.uniform(-1, 1, m.nCells)
     np.testing.assert_allclose(orc.interpolate_linear(a, m.weights(), vf), 0.5 * (vf[m.lower] + vf[m.upper]))
+
+
+@pytest.mark.parametrize("kind", ["P", "U"])
+def test_gamg_over_cyclic_interfaces(meshmod, orc, kind):
+    """cyclicGAMGInterface (cyclicGAMGInterface.C:70-150): the coarse faces of a cyclic pair are the unique (owner-side
+    coarse cell, other-side coarse cell) pairs in order of appearance -- both patches of the pair enumerate the same
+    faces, face i of one facing face i of the other; the V-cycle converges to the periodic solution."""
+    from test_oracle_core import _cyclic_case
+    m, c, ps, fc, nr, lo, hi = _cyclic_case(meshmod, kind)
+    a = orc.Addr(m.nCells, m.lower, m.upper, ps, fc, neighbRank=nr)
+    M = orc.Matrix(a, c["diag"], c["upper"], c["lower"], c["bou"], c["int"])
+    g = orc.Gamg(a, meshmod.face_area_pair_weights(m), 4, 1)
+    assert g.nLevels >= 2
+    for lev in range(g.nLevels):
+        la = g.level_addr(lev)
+        pstart, cells = la.patch_start(), la.face_cells()
+        n0, n1 = pstart[1] - pstart[0], pstart[2] - pstart[1]
+        assert n0 == n1 > 0                                   # the two sides hold the same coarse faces
+        r = g.restrict_addr(lev)
+        pfr = g.patch_face_restrict(lev)
+        fine = a if lev == 0 else g.level_addr(lev - 1)
+        fps, ffc = fine.patch_start(), fine.face_cells()
+        nf = fps[1] - fps[0]
+        # fine face i of patch 0 and fine face i of patch 1 land on coarse faces with the same index in their patches
+        assert np.array_equal(pfr[:nf] - pstart[0], pfr[nf:2 * nf] - pstart[1])
+        # and a coarse patch face sits on the image of its fine faces' cells
+        assert np.array_equal(cells[pfr[: 2 * nf]], r[ffc[: 2 * nf]])
+    x = np.random.default_rng(2).standard_normal(m.nCells)
+    b = M.amul(x)
+    psi, perf, hist = g.solve(M, "GaussSeidel", np.zeros(m.nCells), b, tolerance=1e-10, maxIter=300)
+    assert perf.converged
+    np.testing.assert_allclose(psi, x, rtol=0, atol=1e-7)
