@@ -19,6 +19,22 @@
 
 using namespace b200;
 
+// A solver type added from OUTSIDE the facade, the way a user library registers one in the reference
+// (PCG.C:36-37: lduMatrix::solver::addsymMatrixConstructorToTable<PCG>): `solver loggedPCG;` in the dictionary
+// selects it through lduMatrix::solver::New.  It runs the library's PCG and reports under its own name.
+class loggedPCG : public lduMatrix::solver
+{
+public:
+    loggedPCG(const word &fieldName, const lduMatrix &m, const dictionary &d) : lduMatrix::solver(fieldName, m, d, "PCG") {}
+    virtual solverPerformance solve(scalargpuField &psi, const scalargpuField &source, const int cmpt = 0) const
+    {
+        solverPerformance sp = lduMatrix::solver::solve(psi, source, cmpt);
+        std::cout << "loggedPCG: " << sp.nIterations() << " iterations" << std::endl;
+        return sp;
+    }
+};
+static lduMatrix::solver::addsymMatrixConstructorToTable<loggedPCG> addloggedPCGSymMatrixConstructorToTable_("loggedPCG");
+
 static const char *defaultDict =
     "solvers\n{\n    p\n    {\n        solver          PCG;\n        preconditioner  DIC;\n"
     "        tolerance       1e-06;\n        relTol          0;\n    }\n}\n";

@@ -46,3 +46,16 @@ def test_app_unknown_solver_lists_table(tmp_path):
     p = subprocess.run([APP, "8", str(f)], capture_output=True, text=True, timeout=120)
     assert p.returncode == 2
     assert "Unknown symmetric matrix solver PBiCG" in p.stderr and "PCG" in p.stderr
+
+
+def test_app_solver_type_registered_from_outside_the_facade(tmp_path):
+    """run-time selection is a real registry: the application adds `loggedPCG` to the symmetric-matrix table with an
+    addsymMatrixConstructorToTable object (as PCG.C:36-37 does in the reference) and the dictionary selects it"""
+    f = tmp_path / "fvSolution"
+    f.write_text("solvers { p { solver loggedPCG; preconditioner DIC; tolerance 1e-07; relTol 0; } }")
+    p = subprocess.run([APP, "16", str(f)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert re.search(r"^loggedPCG: \d+ iterations", p.stdout, re.M) and "AINVPCG:  Solving for p" in p.stdout
+    f.write_text("solvers { p { solver nonsense; } }")
+    p = subprocess.run([APP, "8", str(f)], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 2 and "loggedPCG" in p.stderr   # the valid-solver list now shows the added word
