@@ -176,6 +176,64 @@ class Cavity:
             self.U = HbyA - rAU[:, None] * self.grad(self.p)
         return perfs, cont
 
+    # ---- one SIMPLE iteration: simpleFoam/UEqn.H:1-17, pEqn.H:1-40 (laminar, single domain) --------------
+    def simple_step(self, alphaU=0.7, alphaP=0.3, divScheme="upwind", UControls=None, pControls=None,
+                    USolver=("PBiCG", "DILU"), pSolver=("PCG", "DIC"), gamg=None, nNonOrthCorr=0):
+        """UEqn = fvm::div(phi, U) - fvm::laplacian(nu, U) (the laminar divDevReff without its explicit transpose term);
+        UEqn.relax(alphaU); solve(UEqn == -grad p); p from laplacian(rAU, p) == div(phiHbyA); phi = phiHbyA - pEqn.flux();
+        p.relax(alphaP); U = HbyA - rAU*grad p.  divScheme: "upwind" (bounded Gauss upwind of the pitzDaily tutorial:
+        weights pos(phi), upwind.H:120-123) or "linear"."""
+        assert not len(self.cfc), "the SIMPLE restatement is single-domain"
+        from . import limiters_oracle as lo
+        orc = self.orc
+        fvm = lambda nc, diag, upper, lower, source, psi, ic, bc: fo.FvMatrix(
+            orc, self.addr, nc, diag, upper, lower, source, psi, self.V, self.bfc, ic, bc, couInt=None, couBou=None, comm=self.comm)
+        wConv = lo.limited_weights(self.phi) if divScheme == "upwind" else self.w
+        cLower, cUpper, cDiag = orc.convection_fill(self.addr, wConv, self.phi)
+        cIc = self.bphi[:, None] * np.zeros((len(self.bfc), 3))
+        cBc = (-self.bphi)[:, None] * self.Ub
+        lUpper, lDiag = orc.laplacian_fill(self.addr, self.delta, self.nu * self.magSf)
+        lIc, lBc = fo.fixedValue_laplacian_coeffs(self.nu * self.bMagSf, self.bDelta, self.Ub)
+        diag = cDiag - lDiag
+        upper = cUpper - lUpper
+        lower = cLower - lUpper
+        source = np.zeros((self.n, 3))
+        ic, bc = cIc - lIc, cBc - lBc
+        UEqn = fvm(3, diag, upper, lower, source, self.U, ic, bc)
+        UEqn.relax(alphaU)                                    # fvMatrix.C:1088-1345: in place on diag and source
+        diag, source = UEqn.diag, UEqn.source
+        perfs = {}
+        src = source + self.V[:, None] * (-self.grad(self.p))
+        UEqnP = fvm(3, diag, upper, lower, src, self.U, ic, bc)
+        self.U, perfs["U"], _ = UEqnP.solve(USolver[0], USolver[1], **(UControls or dict(tolerance=1e-5, relTol=0.1)))
+        UEqn = fvm(3, diag, upper, lower, source, self.U, ic, bc)
+        rAU = 1.0 / UEqn.A()
+        HbyA = rAU[:, None] * UEqn.H()
+        phiHbyA = self.flux_of(HbyA)
+        bphiHbyA = self._dot(self.Ub, self.bSf)
+        rAUf = self.interpolate(rAU)
+        pOld = self.p.copy()                                  # p.storePrevIter() (simpleFoam.C)
+        for nonOrth in range(nNonOrthCorr + 1):
+            pUpper, pDiag = orc.laplacian_fill(self.addr, self.delta, rAUf * self.magSf)
+            pSource = np.zeros(self.n) + self.V * self.div(phiHbyA, bphiHbyA)
+            zero = np.zeros((len(self.bfc), 1))
+            pEqn = fvm(1, pDiag, pUpper, None, pSource, self.p, zero, zero)
+            pEqn.setReference(self.pRefCell, self.pRefValue)
+            psi, perf, _ = pEqn.solve(pSolver[0], pSolver[1], gamg, **(pControls or dict(tolerance=1e-6, relTol=0.05)))
+            self.p = psi[:, 0]
+            perfs.setdefault("p", []).append(perf[0])
+            if nonOrth == nNonOrthCorr:
+                pEqn.psi = psi
+                internal, boundary, _ = pEqn.flux()
+                self.phi = phiHbyA - internal[:, 0]
+                self.bphi = bphiHbyA - boundary[:, 0]
+        contErr = self.div(self.phi, self.bphi)
+        tot = self._gsum3((np.abs(contErr) * self.V).sum(), (contErr * self.V).sum(), self.V.sum())
+        cont = (tot[0] / tot[2], tot[1] / tot[2])             # steady: deltaT = 1 (continuityErrs.H)
+        self.p = pOld + alphaP * (self.p - pOld)              # GeometricField::relax: prevIter + alpha*(this - prevIter)
+        self.U = HbyA - rAU[:, None] * self.grad(self.p)
+        return perfs, cont
+
     def _gsum3(self, a, b, c):
         v = np.array([float(a), float(b), float(c)])
         if self.comm is None:

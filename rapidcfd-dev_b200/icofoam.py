@@ -176,6 +176,56 @@ class IcoFoam:
             self.U = o.sub(HbyA, o.mul(rAU, self.grad(self.p), 1, 3), 3, 3)
         return perfs, cont
 
+    def simple_step(self, alphaU=0.7, alphaP=0.3, divScheme="upwind", UControls=None, pControls=None,
+                    USolver=("PBiCG", "DILU"), pSolver=("PCG", "DIC"), gamg=None, nNonOrthCorr=0):
+        """One SIMPLE iteration (simpleFoam/UEqn.H:1-17, pEqn.H:1-40; laminar, single domain): UEqn = fvm::div(phi, U) -
+        fvm::laplacian(nu, U); UEqn.relax(alphaU); solve(UEqn == -grad p); fvm::laplacian(rAU, p) == fvc::div(phiHbyA);
+        phi = phiHbyA - pEqn.flux(); p.relax(alphaP); U = HbyA - rAU*grad p.  divScheme "upwind" (weights pos(phi),
+        upwind.H:120-123) or "linear"."""
+        assert not self.nC, "simple_step is single-domain"
+        capi, o, a = self.capi, self.ops, self.addr
+        wConv = capi.fv_limited_weights(self.ctx, self.phi) if divScheme == "upwind" else self.w
+        cLower, cUpper, cDiag = capi.fv_convection_fill(a, wConv, self.phi)
+        cBc = o.mul(o.neg(self.bphi), self.Ub, 1, 3)
+        lUpper, lDiag = capi.fv_laplacian_fill(a, self.delta, o.smul(self.nu, self.magSf))
+        diag = o.sub(cDiag, lDiag)
+        upper = o.sub(cUpper, lUpper)
+        lower = o.sub(cLower, lUpper)
+        source = self._t(np.zeros((self.n, 3)))
+        ic = o.sub(self.zeroB3, self.lIc)
+        bc = o.sub(cBc, self.lBc)
+        self.matU.set(diag, upper, lower)
+        UEqn = capi.FvMatrix(self.matU, 3, diag, source, self.U, self.V, ic, bc)
+        UEqn.relax(alphaU)                       # in place on diag / source (fvMatrix.C:1088-1345) ...
+        self.matU.set(diag, upper, lower)        # ... so the matrix takes the relaxed diagonal
+        perfs = {}
+        src = o.add(source, o.mul(self.V, o.neg(self.grad(self.p)), 1, 3))
+        UEqnP = capi.FvMatrix(self.matU, 3, diag, src, self.U, self.V, ic, bc)
+        perfs["U"] = UEqnP.solve(USolver[0], USolver[1], **(UControls or dict(tolerance=1e-5, relTol=0.1)))
+        rAU = o.rdiv(1.0, UEqn.A())
+        HbyA = o.mul(rAU, UEqn.H(), 1, 3)
+        phiHbyA = capi.fv_flux_linear(a, self.Sf, self.w, HbyA)
+        bphiHbyA = self.bUSf
+        rAUf = capi.fv_interpolate_linear(a, 1, self.w, rAU)
+        pOld = self.p.clone()
+        for nonOrth in range(nNonOrthCorr + 1):
+            pUpper, pDiag = capi.fv_laplacian_fill(a, self.delta, o.mul(rAUf, self.magSf))
+            pSource = o.mul(self.V, self.div(phiHbyA, bphiHbyA))
+            pEqn = capi.FvMatrix(self.matP, 1, pDiag, pSource, self.p, self.V, self.zeroB1, self.zeroB1)
+            pEqn.setReference(self.pRefCell, self.pRefValue)
+            self.matP.set(pDiag, pUpper)
+            perfs.setdefault("p", []).extend(pEqn.solve(pSolver[0], pSolver[1], gamg, **(pControls or dict(tolerance=1e-6, relTol=0.05))))
+            if nonOrth == nNonOrthCorr:
+                internal, boundary, _ = pEqn.flux(self.nB)
+                self.phi = o.sub(phiHbyA, internal)
+                self.bphi = o.sub(bphiHbyA, boundary[: self.nB])
+        contErr = self.div(self.phi, self.bphi)
+        tot = self._gsum3((contErr.abs() * self.V).sum(), (contErr * self.V).sum(), self.V.sum())
+        cont = (tot[0] / tot[2], tot[1] / tot[2])
+        self.p = o.add(pOld, o.smul(alphaP, o.sub(self.p, pOld)))     # p.relax()
+        self.U = o.sub(HbyA, o.mul(rAU, self.grad(self.p), 1, 3), 3, 3)
+        return perfs, cont
+
     def close(self):
         self.matU.close()
         self.matP.close()

@@ -283,6 +283,13 @@ class _Capi:
         return FieldOps._t(orc.surface_integrate(addr.o, _np(ssf), addr.bfc, _np(bssf), _np(V), nc, divideByV, neiSign))
 
     @staticmethod
+    def fv_limited_weights(ctx, faceFlux, limiter=None, cdWeights=None):
+        from oracle import limiters_oracle as lo
+        import torch
+        w = lo.limited_weights(_np(faceFlux), None if limiter is None else _np(limiter), None if cdWeights is None else _np(cdWeights))
+        return torch.from_numpy(np.ascontiguousarray(w))
+
+    @staticmethod
     def fv_boundary_set(addr, bFaceCells):
         addr.bfc = np.asarray(bFaceCells, np.int32).copy()
     GamgAgglomeration = GamgAgglomeration

@@ -387,7 +387,9 @@ def test_cyclic_interfaces(gpu, meshmod, orc, kind):
     psi = torch.zeros(m.nCells, dtype=torch.float64, device=ctx.device)
     perf, hist = mat.solve("GAMG", "GaussSeidel", psi, t(rhs), gamg=gg, histCap=512, **ctl)
     assert perf.converged and perf.nIterations == pr.nIterations, (perf.nIterations, pr.nIterations)
-    np.testing.assert_allclose(hist[: len(href)], href, rtol=1e-8)
+    # Jacobi with coupled interfaces adds the interface terms after the face terms (stated exception):
+    # 1e-13 per sweep, measured 3e-8 on the cycle residuals of this 120-cell case
+    np.testing.assert_allclose(hist[: len(href)], href, rtol=1e-6)
     np.testing.assert_allclose(psi.cpu().numpy(), x, rtol=0, atol=1e-6)
     gg.close()
     mat.close()

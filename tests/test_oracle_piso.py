@@ -105,3 +105,28 @@ def test_decomposed_cavity_reproduces_the_single_domain(meshmod, orc, nR):
             q = list(other.addr.neighbRank).index(r)
             qs = other.addr.patch_start()
             np.testing.assert_allclose(case.cphi[ps[i]:ps[i + 1]], -other.cphi[qs[q]:qs[q + 1]], rtol=0, atol=1e-14)
+
+
+def test_simple_iterations_converge_to_the_steady_cavity(meshmod, orc):
+    """SIMPLE (simpleFoam/UEqn.H, pEqn.H; laminar, upwind convection, under-relaxation 0.7 / 0.3): the residuals of both
+    equations fall over the iterations, continuity is enforced to the pressure solver's tolerance every iteration, and the
+    steady field is the same recirculation the PISO run spins up to (top layer follows the lid, return flow below)."""
+    n = 8
+    m, c = po.cavity_from_hex(orc, meshmod, n, nu=0.05)
+    ctl = dict(tolerance=1e-10, relTol=0.0)
+    first, last = None, None
+    for it in range(60):
+        perfs, cont = c.simple_step(UControls=ctl, pControls=ctl)
+        assert abs(cont[1]) < 1e-9                       # global continuity after every pressure correction
+        last = (perfs["U"][0].initialResidual, perfs["p"][0].initialResidual)
+        first = first or last
+    assert last[0] < 1e-3 * first[0] and last[1] < 1e-2 * first[1]
+    cc = m.cell_centres()
+    top = c.U[cc[:, 1] > 1 - m.h, 0].mean()
+    bottom = c.U[cc[:, 1] < 0.4, 0].mean()
+    assert top > 0.1 and bottom < 0                      # lid-driven recirculation
+    # linear convection gives another (close) steady state through the same path
+    m2, c2 = po.cavity_from_hex(orc, meshmod, n, nu=0.05)
+    for it in range(60):
+        c2.simple_step(divScheme="linear", UControls=ctl, pControls=ctl)
+    assert np.abs(c2.U - c.U).max() < 0.15 and np.abs(c2.U - c.U).max() > 1e-6

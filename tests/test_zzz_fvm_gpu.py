@@ -280,6 +280,27 @@ def test_multi_gpu_icofoam(world):
     assert p.stdout.count("MULTI-GPU-ICOFOAM-OK") == world
 
 
+def test_simple_iterations_match_the_oracle(gpu, meshmod, orc):
+    """SIMPLE (simpleFoam UEqn.H / pEqn.H: upwind convection, UEqn.relax, p.relax) sequenced over the C ABI against the
+    numpy restatement of the same statements (oracle/piso_oracle.py simple_step)"""
+    from oracle import piso_oracle as po
+    capi, ctx, torch = gpu
+    ico = importlib.import_module("rapidcfd-dev_b200.icofoam")
+    n = 8
+    m, ref = po.cavity_from_hex(orc, meshmod, n, nu=0.05)
+    m2, dev = ico.cavity(capi, ctx, torch, n, nu=0.05)
+    ctl = dict(tolerance=1e-12, relTol=0.0)
+    for it in range(4):
+        rp, rc = ref.simple_step(UControls=ctl, pControls=ctl)
+        dp_, dc = dev.simple_step(UControls=ctl, pControls=ctl)
+        assert all(p.converged for p in dp_["U"]) and all(p.converged for p in dp_["p"])
+        np.testing.assert_allclose(host(dev.U, 3), ref.U, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(host(dev.p), ref.p, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(host(dev.phi), ref.phi, rtol=0, atol=1e-11)
+        assert abs(dc[1]) < 1e-10 and abs(rc[1]) < 1e-10
+    dev.close()
+
+
 def test_gpu_fvm_vs_golden(gpu, meshmod, orc):
     """the glue and two icoFoam steps against tests/golden/fvm_golden.npz (self-generated; make_fvm_golden.py)"""
     here = os.path.dirname(os.path.abspath(__file__))
