@@ -63,6 +63,7 @@ __global__ void surface_integrate_kernel(int nCells, const int *__restrict__ own
     double acc[NC];
 #pragma unroll
     for (int k = 0; k < NC; k++) acc[k] = 0.0;
+    if constexpr (NC == 1) {
     // faces in batches of FV_BATCH: all loads of a batch (indices, then values) are issued before the first
     // add, so a thread keeps several independent loads in flight; the adds stay in face order
     const int o0 = ownerStart[c], o1 = ownerStart[c + 1];
@@ -96,6 +97,19 @@ __global__ void surface_integrate_kernel(int nCells, const int *__restrict__ own
             if (j0 + b < n1)
 #pragma unroll
                 for (int k = 0; k < NC; k++) acc[k] = neiSign < 0 ? __dsub_rn(acc[k], v[b][k]) : __dadd_rn(acc[k], v[b][k]);
+    }
+    } else { // vector fields: the batch arrays cost occupancy (measured slower), plain loops
+    for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++)
+#pragma unroll
+        for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], ssf[(size_t)f * NC + k]);
+    for (int j = losortStart[c]; j < losortStart[c + 1]; j++) {
+        int f = losort[j];
+#pragma unroll
+        for (int k = 0; k < NC; k++) {
+            double v = ssf[(size_t)f * NC + k];
+            acc[k] = neiSign < 0 ? __dsub_rn(acc[k], v) : __dadd_rn(acc[k], v);
+        }
+    }
     }
     if (bStart)
         for (int j = bStart[c]; j < bStart[c + 1]; j++) {
@@ -406,61 +420,27 @@ __global__ void grad_linear_kernel(int nCells, const int *__restrict__ ownerStar
     double acc[3 * NC];
 #pragma unroll
     for (int k = 0; k < 3 * NC; k++) acc[k] = 0.0;
-    // batches of FV_BATCH faces: indices, then weights / Sf / the cell values across the face, then the arithmetic
-    const int o0 = ownerStart[c], o1 = ownerStart[c + 1];
-    for (int f0 = o0; f0 < o1; f0 += FV_BATCH) {
-        int ni[FV_BATCH];
-        double ww[FV_BATCH], sv[FV_BATCH][3], ov[FV_BATCH][NC];
+    for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++) {
+        const int n = upper[f];
+        const double ww = w[f];
+        const double s[3] = {Sf[(size_t)f * 3], Sf[(size_t)f * 3 + 1], Sf[(size_t)f * 3 + 2]};
 #pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (f0 + b < o1) ni[b] = upper[f0 + b];
+        for (int j = 0; j < NC; j++) {
+            const double fv = lin_face(ww, mine[j], vf[(size_t)n * NC + j]);
 #pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (f0 + b < o1) {
-                const size_t f = (size_t)(f0 + b);
-                ww[b] = w[f];
-                sv[b][0] = Sf[f * 3], sv[b][1] = Sf[f * 3 + 1], sv[b][2] = Sf[f * 3 + 2];
-#pragma unroll
-                for (int j = 0; j < NC; j++) ov[b][j] = vf[(size_t)ni[b] * NC + j];
-            }
-#pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (f0 + b < o1)
-#pragma unroll
-                for (int j = 0; j < NC; j++) {
-                    const double fv = lin_face(ww[b], mine[j], ov[b][j]);
-#pragma unroll
-                    for (int i = 0; i < 3; i++) acc[i * NC + j] = __dadd_rn(acc[i * NC + j], __dmul_rn(sv[b][i], fv));
-                }
+            for (int i = 0; i < 3; i++) acc[i * NC + j] = __dadd_rn(acc[i * NC + j], __dmul_rn(s[i], fv));
+        }
     }
-    const int n0 = losortStart[c], n1 = losortStart[c + 1];
-    for (int q0 = n0; q0 < n1; q0 += FV_BATCH) {
-        int fi[FV_BATCH], oi[FV_BATCH];
-        double ww[FV_BATCH], sv[FV_BATCH][3], ov[FV_BATCH][NC];
+    for (int q = losortStart[c]; q < losortStart[c + 1]; q++) {
+        const int f = losort[q], o = lower[f];
+        const double ww = w[f];
+        const double s[3] = {Sf[(size_t)f * 3], Sf[(size_t)f * 3 + 1], Sf[(size_t)f * 3 + 2]};
 #pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (q0 + b < n1) fi[b] = losort[q0 + b];
+        for (int j = 0; j < NC; j++) {
+            const double fv = lin_face(ww, vf[(size_t)o * NC + j], mine[j]);
 #pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (q0 + b < n1) oi[b] = lower[fi[b]];
-#pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (q0 + b < n1) {
-                const size_t f = (size_t)fi[b];
-                ww[b] = w[f];
-                sv[b][0] = Sf[f * 3], sv[b][1] = Sf[f * 3 + 1], sv[b][2] = Sf[f * 3 + 2];
-#pragma unroll
-                for (int j = 0; j < NC; j++) ov[b][j] = vf[(size_t)oi[b] * NC + j];
-            }
-#pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (q0 + b < n1)
-#pragma unroll
-                for (int j = 0; j < NC; j++) {
-                    const double fv = lin_face(ww[b], ov[b][j], mine[j]);
-#pragma unroll
-                    for (int i = 0; i < 3; i++) acc[i * NC + j] = __dsub_rn(acc[i * NC + j], __dmul_rn(sv[b][i], fv));
-                }
+            for (int i = 0; i < 3; i++) acc[i * NC + j] = __dsub_rn(acc[i * NC + j], __dmul_rn(s[i], fv));
+        }
     }
     if (bStart)
         for (int q = bStart[c]; q < bStart[c + 1]; q++) {
