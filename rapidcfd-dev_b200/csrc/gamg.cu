@@ -135,8 +135,11 @@ static void coarse_addressing(const std::vector<int> &lo, const std::vector<int>
                               std::vector<int> &fr, std::vector<unsigned char> &flip)
 {
     const int nff = (int)lo.size();
-    std::vector<std::vector<int>> ccFaces(nCoarse); // per coarse owner: discovery-ordered coarse faces
-    std::vector<int> initNei;
+    // per coarse owner: its coarse faces in order of discovery, as singly linked lists in flat arrays (a vector per
+    // coarse cell cost seconds of allocator time on the first levels of a 16 M cell mesh)
+    std::vector<int> head(nCoarse, -1), tail(nCoarse, -1), nxt, initNei;
+    nxt.reserve(nff / 2 + 16);
+    initNei.reserve(nff / 2 + 16);
     fr.assign(nff, 0);
     for (int f = 0; f < nff; f++) {
         int ru = rmap[up[f]], rl = rmap[lo[f]];
@@ -146,15 +149,20 @@ static void coarse_addressing(const std::vector<int> &lo, const std::vector<int>
         }
         int cOwn = std::min(ru, rl), cNei = std::max(ru, rl);
         int found = -1;
-        for (int cfi : ccFaces[cOwn])
+        for (int cfi = head[cOwn]; cfi >= 0; cfi = nxt[cfi])
             if (initNei[cfi] == cNei) {
                 found = cfi;
                 break;
             }
         if (found < 0) {
             found = (int)initNei.size();
-            ccFaces[cOwn].push_back(found);
             initNei.push_back(cNei);
+            nxt.push_back(-1);
+            if (tail[cOwn] >= 0)
+                nxt[tail[cOwn]] = found;
+            else
+                head[cOwn] = found;
+            tail[cOwn] = found;
         }
         fr[f] = found;
     }
@@ -164,7 +172,7 @@ static void coarse_addressing(const std::vector<int> &lo, const std::vector<int>
     std::vector<int> cMap(nCF);
     int k = 0;
     for (int cc = 0; cc < nCoarse; cc++)
-        for (int cfi : ccFaces[cc]) {
+        for (int cfi = head[cc]; cfi >= 0; cfi = nxt[cfi]) {
             cOwner[k] = cc;
             cNeigh[k] = initNei[cfi];
             cMap[cfi] = k++;
@@ -632,11 +640,7 @@ __global__ void dense_apply_p2p_kernel(int nLocal, int nGlobal, const double *__
     if (threadIdx.x < G.nRanks) {
         unsigned long long *f = G.flag[threadIdx.x] + (par * P2P_MAXR + G.rank);
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(seq) : "memory");
-        const unsigned long long *w = G.flag[G.rank] + (par * P2P_MAXR + threadIdx.x);
-        unsigned long long v;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
-        } while (v < seq);
+        spin_until(G.flag[G.rank] + (par * P2P_MAXR + threadIdx.x), seq, G.seq + 5); // seqs[2] + 5 = the error word seqs[7]
     }
     __syncthreads();
     for (int r = 0; r < G.nRanks; r++)

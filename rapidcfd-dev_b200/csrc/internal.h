@@ -68,12 +68,13 @@ constexpr int P2P_MAXR = 8;
 constexpr size_t P2P_MAIL_OFF = 0;        // double mail[2][P2P_MAXR][8]
 constexpr size_t P2P_MAILFLAG_OFF = 2048; // u64 mailFlag[2][P2P_MAXR]
 constexpr size_t P2P_HALOFLAG_OFF = 4096; // u64 haloFlag[P2P_MAXR]   (indexed by source rank)
-constexpr int P2P_GMAX = 64;              // doubles per rank in the coarsest-level gather
+constexpr int P2P_GMAX = 256;             // doubles per rank in the coarsest-level gather
 constexpr size_t P2P_GATHER_OFF = 8192;   // double gather[2][P2P_MAXR][P2P_GMAX]
 constexpr size_t P2P_GFLAG_OFF = 8192 + 2 * P2P_MAXR * P2P_GMAX * sizeof(double); // u64 gflag[2][P2P_MAXR]
-constexpr size_t P2P_RECV_OFF = 32768;    // double recv[2][P2P_RECV_CAP]
+constexpr size_t P2P_RECV_OFF = 49152;    // double recv[2][P2P_RECV_CAP]
 constexpr size_t P2P_RECV_CAP = 1u << 20; // doubles per parity
 constexpr size_t P2P_REGION_BYTES = P2P_RECV_OFF + 2 * P2P_RECV_CAP * sizeof(double);
+static_assert(P2P_GFLAG_OFF + 2 * P2P_MAXR * sizeof(unsigned long long) <= P2P_RECV_OFF, "gather area overlaps the receive buffers");
 
 struct P2PRed { // passed by value to scalar_kernel
     int rank = 0, nRanks = 1;

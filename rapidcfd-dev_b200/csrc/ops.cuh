@@ -302,12 +302,25 @@ __device__ __forceinline__ void scalar_body(const double *partials, int nPartial
                                             G &g, const P2PRed &p2p)
 {
     if (NRED > 0) {
+        // thread t adds partials t, t+256, ... in that order (fixed => deterministic); the loads of eight of them are
+        // issued together, all NRED sums of a partial at once: the step is serial time for the whole GPU
         double red[NRED > 0 ? NRED : 1];
 #pragma unroll
-        for (int k = 0; k < (NRED > 0 ? NRED : 1); k++) {
-            double s = 0;
-            for (int i = threadIdx.x; i < nPartials; i += 256) s += __ldcg(partials + (size_t)i * NRED + k);
-            red[k] = s;
+        for (int k = 0; k < (NRED > 0 ? NRED : 1); k++) red[k] = 0;
+        for (int base = threadIdx.x; base < nPartials; base += 256 * 8) {
+            double v[8][NRED > 0 ? NRED : 1];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = base + u * 256;
+                if (i < nPartials)
+#pragma unroll
+                    for (int k = 0; k < NRED; k++) v[u][k] = __ldcg(partials + (size_t)i * NRED + k);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (base + u * 256 < nPartials)
+#pragma unroll
+                    for (int k = 0; k < NRED; k++) red[k] += v[u][k];
         }
         __shared__ double tot[NRED > 0 ? NRED : 1];
         block_reduce_store<(NRED > 0 ? NRED : 1), 256>(red, tot, 0);

@@ -271,16 +271,12 @@ int solve_pcg_fused(Solve &S, int pk)
     typedef DeferredStep<2, PcgStepA> PreB; // sweep B starts by closing sweep A of this body
     const int every = S.c.checkEvery > 0 ? S.c.checkEvery : 8;
     const unsigned mod = 2u * (unsigned)every;
-    // A/B switch for measurements: B200LDU_PCG_DEFERRED=0 runs the scalar steps as one-CTA launches of their own
-    // (round 1's structure: 4 launches per iteration)
-    const char *dv = getenv("B200LDU_PCG_DEFERRED");
-    const bool deferred = !(dv && atoi(dv) == 0);
 
     auto body = [&](long long k) -> int {
         const double *rOld = rb[k & 1], *pPrev = pb[k & 1];
         double *rNew = rb[(k + 1) & 1], *pNew = pb[(k + 1) & 1];
         int npA = a->L.nBands;
-        const PreA preA{partB, a->L.nBands, sc, gB, pr, (unsigned)(2 * (k % every)), mod, (deferred && k > 0) ? 1 : 0};
+        const PreA preA{partB, a->L.nBands, sc, gB, pr, (unsigned)(2 * (k % every)), mod, k > 0 ? 1 : 0};
         if (pk == 2) {
             PcgAinvOp<PreA> op;
             op.stop = stop;
@@ -313,8 +309,7 @@ int solve_pcg_fused(Solve &S, int pk)
         }
         int wait = 0;
         TRY(mat_halo(m, pNew, stop, &wait)); // peer-memory path: nothing is launched, the send is fused
-        if (!deferred) TRY(scalar_step_on<2>(S, partA, npA, gA));
-        const PreB preB{partA, npA, sc, gA, pr, (unsigned)(2 * (k % every) + 1), mod, deferred ? 1 : 0};
+        const PreB preB{partA, npA, sc, gA, pr, (unsigned)(2 * (k % every) + 1), mod, 1};
         PcgAmulOp<PreB> op;
         op.stop = stop;
         op.partials = partB;
@@ -323,7 +318,6 @@ int solve_pcg_fused(Solve &S, int pk)
         op.sc = sc;
         op.pre = preB;
         TRY(engine_launch_m(m, false, op));
-        if (!deferred) TRY(scalar_step_on<1>(S, partB, a->L.nBands, gB));
         return B200LDU_OK;
     };
     long long mb = (long long)S.c.maxIter + 1 > S.c.minIter ? (long long)S.c.maxIter + 1 : S.c.minIter;
