@@ -67,7 +67,7 @@ EXPORTS = [
     "b200ldu_fvm_add_boundary_diag", "b200ldu_fvm_add_boundary_source", "b200ldu_fvm_A", "b200ldu_fvm_H",
     "b200ldu_fvm_flux", "b200ldu_fvm_residual", "b200ldu_fvm_relax", "b200ldu_fvm_set_reference",
     "b200ldu_fvm_solve", "b200ldu_fv_patch_neighbour_field",
-    "b200ldu_ldu_row_sum", "b200ldu_ldu_add_assign", "b200ldu_ldu_scale", "b200ldu_fv_sngrad", "b200ldu_fv_limiter", "b200ldu_fv_limited_weights", "b200ldu_field_binary", "b200ldu_field_unary", "b200ldu_field_dot3", "b200ldu_field_gather",
+    "b200ldu_mules_limiter", "b200ldu_ldu_row_sum", "b200ldu_ldu_add_assign", "b200ldu_ldu_scale", "b200ldu_fv_sngrad", "b200ldu_fv_limiter", "b200ldu_fv_limited_weights", "b200ldu_field_binary", "b200ldu_field_unary", "b200ldu_field_dot3", "b200ldu_field_gather",
 ]
 
 _lib = None
@@ -144,6 +144,7 @@ def lib():
     L.b200ldu_fvm_set_reference.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     L.b200ldu_fv_patch_neighbour_field.argtypes = [vp, C.c_int, vp, vp]
     L.b200ldu_fv_sngrad.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.b200ldu_mules_limiter.argtypes = [vp, C.c_int, C.c_double] + [vp] * 12 + [C.c_double, C.c_double, vp, vp]
     L.b200ldu_ldu_row_sum.argtypes = [vp, C.c_int, vp, vp, vp]
     L.b200ldu_ldu_add_assign.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
     L.b200ldu_ldu_scale.argtypes = [vp, vp, C.c_double, vp, vp, vp, vp]
@@ -525,6 +526,9 @@ class FieldOps:
     def smin(self, a, s):            # min(a, s)
         return self.unary(6, a, s)
 
+    def sdiv(self, a, s):            # a/s
+        return self.unary(9, a, s)
+
     def dot3(self, a, b):
         out = self._new(a, a.numel() // 3)
         check(lib().b200ldu_field_dot3(self.ctx.h, a.numel() // 3, _dp(a), _dp(b), _dp(out)))
@@ -650,6 +654,18 @@ def fv_limited_weights(ctx, faceFlux, limiter=None, cdWeights=None):
     out = _newlike(faceFlux, faceFlux.numel())
     check(lib().b200ldu_fv_limited_weights(ctx.h, faceFlux.numel(), _dp(limiter), _dp(cdWeights), _dp(faceFlux), _dp(out)))
     return out
+
+
+def mules_limiter(addr, V, rDeltaT, psi, psi0, psiB, phiBD, phiBDB, phiCorr, phiCorrB, psiMax, psiMin, nLimiterIter=3,
+                  rho=None, rho0=None, Sp=None, Su=None):
+    """MULES::limiter: (lambda on the internal faces, lambda on the boundary faces of fv_boundary_set), starting from 1"""
+    import torch
+    lam = torch.ones(addr.nFaces, dtype=torch.float64, device=psi.device)
+    lamB = torch.ones(max(phiCorrB.numel(), 1), dtype=torch.float64, device=psi.device)
+    check(lib().b200ldu_mules_limiter(addr.h, int(nLimiterIter), float(rDeltaT), _dp(rho), _dp(rho0), _dp(psi), _dp(psi0), _dp(psiB),
+                                      _dp(phiBD), _dp(phiBDB), _dp(phiCorr), _dp(phiCorrB), _dp(Sp), _dp(Su), _dp(V), float(psiMax),
+                                      float(psiMin), _dp(lam), _dp(lamB)))
+    return lam, lamB[: phiCorrB.numel()]
 
 
 def fv_boundary_set(addr, bFaceCells):

@@ -157,6 +157,8 @@ struct b200ldu_addr {
     // grow-only scratch vectors
     int nCFaces = 0;
     int *d_cCellStart = nullptr, *d_cCellFaces = nullptr, *d_cFaceCells = nullptr;
+    double *d_mulesScratch = nullptr; // MULES limiter: six cell fields (mules.cu)
+    size_t mulesScratchLen = 0;
     double *d_fvmScratch[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t fvmScratchLen[4] = {0, 0, 0, 0};
     // host-only structural self-check (b200ldu_layout_debug_*): no GPU, no compute

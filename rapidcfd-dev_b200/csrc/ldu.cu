@@ -203,7 +203,7 @@ extern "C" int b200ldu_addr_destroy(b200ldu_addr *a)
                     a->d_haloIdx, a->d_perm, a->d_iperm, a->d_sendRows, a->d_l, a->d_u,
                     a->d_ownerStart, a->d_losort, a->d_losortStart, a->d_bFaceCells, a->d_cyclicSrc,
                     a->d_bCellStart, a->d_bCellFaces, a->d_bCells, a->d_packPatches, a->d_packChunks,
-                    a->d_cCellStart, a->d_cCellFaces, a->d_cFaceCells, a->d_fvmScratch[0],
+                    a->d_cCellStart, a->d_cCellFaces, a->d_cFaceCells, a->d_mulesScratch, a->d_fvmScratch[0],
                     a->d_fvmScratch[1], a->d_fvmScratch[2], a->d_fvmScratch[3]};
     for (void *p : ptrs)
         if (p) cudaFree(p);

@@ -1,0 +1,53 @@
+// mules.cu -- MULES: multidimensional universal limiter for explicit solution.
+// b200ldu_mules_limiter = MULES::limiter (FV/fvMatrices/solvers/MULES/MULESTemplates.C:381-745): the face limiters
+// lambda of the anti-diffusive flux phiCorr = phiPsi - phiBD such that psi stays within [psiMin, psiMax] and within
+// the extrema of its face neighbours.  MULES::limit (:748-813) and MULES::explicitSolve (:36-78) are compositions of
+// this entry with the upwind flux, the field operators and fvc::surfaceIntegrate (rapidcfd-dev_b200/mules.py).
+// Static mesh; boundary faces = the non-coupled faces given to b200ldu_fv_boundary_set.
+#include "internal.h"
+
+#include "mules_kernels.cuh"
+
+using namespace mulesk;
+
+extern "C" int b200ldu_mules_limiter(b200ldu_addr *a, int nLimiterIter, double rDeltaT, const double *rho_d, const double *rho0_d,
+                                     const double *psi_d, const double *psi0_d, const double *psiB_d, const double *phiBD_d,
+                                     const double *phiBDB_d, const double *phiCorr_d, const double *phiCorrB_d,
+                                     const double *Sp_d, const double *Su_d, const double *V_d, double psiMax, double psiMin,
+                                     double *lambda_d, double *lambdaB_d)
+{
+    if (!a || !psi_d || !psi0_d || !phiBD_d || !phiCorr_d || !V_d || !lambda_d || nLimiterIter < 0) return B200LDU_EINVAL;
+    if (a->nBFaces && (!psiB_d || !phiBDB_d || !phiCorrB_d || !lambdaB_d)) return B200LDU_EINVAL;
+    b200ldu_ctx *ctx = a->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int n = a->nCells, nF = a->nFaces, nB = a->nBFaces;
+    // scratch: psiMaxn, psiMinn, sumPhip, mSumPhim, lambdam, lambdap (six cell fields, kept across calls)
+    if (a->mulesScratchLen < (size_t)6 * n) {
+        if (a->d_mulesScratch) cudaFree(a->d_mulesScratch);
+        a->d_mulesScratch = nullptr;
+        a->mulesScratchLen = 0;
+        CUDA_TRY(cudaMalloc((void **)&a->d_mulesScratch, sizeof(double) * 6 * (size_t)n));
+        a->mulesScratchLen = (size_t)6 * n;
+    }
+    double *psiMaxn = a->d_mulesScratch, *psiMinn = psiMaxn + n, *sumPhip = psiMinn + n, *mSumPhim = sumPhip + n,
+           *lambdam = mSumPhim + n, *lambdap = lambdam + n;
+    const int *bs = nB ? a->d_bCellStart : nullptr;
+    // lambda_d / lambdaB_d come in holding the starting limiter (MULES::limit: allLambda(mesh.nFaces(), 1.0))
+    mules_bounds_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, a->d_ownerStart, a->d_u, a->d_losortStart, a->d_losort, a->d_l, bs,
+                                                         a->d_bCellFaces, psi_d, psiB_d, phiBD_d, phiBDB_d, phiCorr_d, phiCorrB_d,
+                                                         psi0_d, rho_d, rho0_d, Sp_d, Su_d, V_d, rDeltaT, psiMax, psiMin, psiMaxn,
+                                                         psiMinn, sumPhip, mSumPhim);
+    ctx->launches++;
+    for (int j = 0; j < nLimiterIter; j++) {
+        mules_cell_lambda_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, a->d_ownerStart, a->d_losortStart, a->d_losort, bs,
+                                                                  a->d_bCellFaces, lambda_d, lambdaB_d, phiCorr_d, phiCorrB_d,
+                                                                  psiMaxn, psiMinn, sumPhip, mSumPhim, lambdam, lambdap);
+        mules_face_lambda_kernel<<<(nF + nB + 255) / 256, 256, 0, st>>>(nF, nB, a->d_l, a->d_u, a->d_bFaceCells, phiCorr_d,
+                                                                        phiCorrB_d, phiBDB_d, lambdam, lambdap, lambda_d,
+                                                                        lambdaB_d);
+        ctx->launches += 2;
+    }
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}

@@ -26,6 +26,7 @@ using std::fmin;
 
 #include "fieldops_kernels.cuh"
 #include "fvmatrix_kernels.cuh"
+#include "mules_kernels.cuh"
 
 template <class K, class... A> static void launch(long long nThreads, int block, K k, A... args)
 {
@@ -161,5 +162,26 @@ void hk_limiter(int nFaces, int scheme, double twoByk, const int *l, const int *
 void hk_limited_weights(long long n, const double *limiter, const double *cd, const double *faceFlux, double *out)
 {
     launch(n, 256, fieldk::limited_weights_kernel, n, limiter, cd, faceFlux, out);
+}
+
+/* csrc/mules.cu: b200ldu_mules_limiter's three kernels in its launch order */
+void hk_mules_limiter(const HostCase *h, int nIter, double rDeltaT, const double *rho, const double *rho0, const double *psi,
+                      const double *psi0, const double *psiB, const double *phiBD, const double *phiBDB, const double *phiCorr,
+                      const double *phiCorrB, const double *Sp, const double *Su, const double *V, double psiMax, double psiMin,
+                      double *lambda, double *lambdaB, double *scratch /* 6*nCells */)
+{
+    using namespace mulesk;
+    const int n = h->nCells, nF = h->nFaces, nB = h->nB;
+    double *psiMaxn = scratch, *psiMinn = psiMaxn + n, *sumPhip = psiMinn + n, *mSumPhim = sumPhip + n, *lambdam = mSumPhim + n,
+           *lambdap = lambdam + n;
+    const int *bs = nB ? h->bStart : nullptr;
+    launch(n, 128, mules_bounds_kernel, n, h->ownerStart, h->u, h->losortStart, h->losort, h->l, bs, h->bFaces, psi, psiB, phiBD,
+           phiBDB, phiCorr, phiCorrB, psi0, rho, rho0, Sp, Su, V, rDeltaT, psiMax, psiMin, psiMaxn, psiMinn, sumPhip, mSumPhim);
+    for (int j = 0; j < nIter; j++) {
+        launch(n, 128, mules_cell_lambda_kernel, n, h->ownerStart, h->losortStart, h->losort, bs, h->bFaces, lambda, lambdaB,
+               phiCorr, phiCorrB, psiMaxn, psiMinn, sumPhip, mSumPhim, lambdam, lambdap);
+        launch((long long)nF + nB, 256, mules_face_lambda_kernel, nF, nB, h->l, h->u, h->bFaceCells, phiCorr, phiCorrB, phiBDB,
+               lambdam, lambdap, lambda, lambdaB);
+    }
 }
 }

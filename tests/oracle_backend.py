@@ -212,6 +212,9 @@ class FieldOps:
     def smin(self, a, s):
         return self._t(np.minimum(_np(a), s))
 
+    def sdiv(self, a, s):
+        return self._t(_np(a) / s)
+
     def dot3(self, a, b):
         A, B = _np(a).reshape(-1, 3), _np(b).reshape(-1, 3)
         return self._t((A[:, 0] * B[:, 0] + A[:, 1] * B[:, 1]) + A[:, 2] * B[:, 2])
@@ -288,6 +291,16 @@ class _Capi:
         import torch
         w = lo.limited_weights(_np(faceFlux), None if limiter is None else _np(limiter), None if cdWeights is None else _np(cdWeights))
         return torch.from_numpy(np.ascontiguousarray(w))
+
+    @staticmethod
+    def mules_limiter(addr, V, rDeltaT, psi, psi0, psiB, phiBD, phiBDB, phiCorr, phiCorrB, psiMax, psiMin, nLimiterIter=3,
+                      rho=None, rho0=None, Sp=None, Su=None):
+        from oracle import mules_oracle as mo
+        o = lambda x: None if x is None else _np(x)
+        lam, lamB = mo.limiter(addr.o.nCells, addr.o.lower(), addr.o.upper(), addr.bfc, _np(V), rDeltaT, _np(psi), _np(psi0), _np(psiB),
+                               _np(phiBD), _np(phiBDB), _np(phiCorr), _np(phiCorrB), psiMax, psiMin, nLimiterIter, o(rho), o(rho0),
+                               o(Sp), o(Su))
+        return FieldOps._t(lam), FieldOps._t(lamB)
 
     @staticmethod
     def fv_boundary_set(addr, bFaceCells):
