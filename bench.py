@@ -52,19 +52,19 @@ def ncu_traffic():
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r0*_ncu_full_engine_raw.csv")))
     if not files:
         return out
-    p = files[-1]
-    out["source"] = os.path.relpath(p, ROOT)
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    last, src = {}, {}
     try:
-        rows = list(csv.reader(open(p)))
-        hdr, units = rows[0], rows[1]
-        kn, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        last = {}
-        for r in rows[2:]:
-            byts = float(r[rd]) * mult[units[rd]] + float(r[wr]) * mult[units[wr]]
-            for key in ("AmulOp<0>", "PcgAinvOp", "PcgAmulOp", "pcg_persistent"):
-                if key in r[kn]:
-                    last[key] = byts
+        for p in files:                      # oldest first: the newest capture that holds a kernel wins
+            rows = list(csv.reader(open(p)))
+            hdr, units = rows[0], rows[1]
+            kn, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            for r in rows[2:]:
+                byts = float(r[rd]) * mult[units[rd]] + float(r[wr]) * mult[units[wr]]
+                for key in ("AmulOp<0>", "PcgAinvOp", "PcgAmulOp"):
+                    if key in r[kn]:
+                        last[key], src[key] = byts, os.path.relpath(p, ROOT)
+        out["source"] = sorted(set(src.values()))
         out["amul"] = last.get("AmulOp<0>")
         if "PcgAinvOp" in last and "PcgAmulOp" in last:
             out["pcg_iteration"] = last["PcgAinvOp"] + last["PcgAmulOp"]

@@ -116,13 +116,16 @@ int pick_band_rows(int nCells, int smCount)
         int v = atoi(e);
         if (v >= SLICE_ROWS && v % SLICE_ROWS == 0 && v <= 16384) return v;
     }
-    // Whole waves of CTAs: a sweep is one CTA per band, 6 resident per SM, and a last wave that is a quarter full
-    // costs as much as a full one.  Take the smallest number of waves whose bands stay within ~2400 rows (the tile
-    // of a band + its halo must leave room for 6 CTAs per SM) and size the bands to fill those waves exactly.
-    // Measured on B200, 128^3 (one rank of the 8-way 256^3 split), Mcell-iters/s of the fused PCG: 512 rows (4.6
-    // waves) 18.8 k, 1024 rows 19.2 k, 2368 rows (one wave of 886 CTAs) 20.3 k.
+    // A sweep is one CTA per band, 6 resident per SM.  Large meshes (>= 4 waves of 2048-row bands) take 2048 rows: with many
+    // waves the CTAs drift out of phase, staging and streaming overlap across CTAs, and a partly filled last wave is a small
+    // share.  Small meshes (one rank of a strong-scaling split) are quantised into whole waves: the smallest number of waves
+    // whose bands stay within ~2400 rows (the tile of a band + its halo must leave room for 6 CTAs per SM), bands sized to
+    // fill them exactly.  Measured on B200, fused PCG, Mcell-iters/s: 128^3 (2.1 M cells) 512 rows (4.6 waves) 18.8 k, 1024
+    // rows 19.2 k, 2368 rows (one wave of 886 CTAs) 19.9-20.3 k; 256^3 (16.8 M) 2048 rows (9.2 waves) 23.6 k, 2368 rows
+    // (8 whole waves) 23.1 k on the same box (profiles/r02_bench_n1*.json).
     const long long slots = (long long)(smCount > 0 ? smCount : 148) * 6;
     const long long maxRows = 2432;
+    if (nCells >= slots * 4 * 2048) return 2048;
     const long long waves = std::max<long long>(1, (nCells + slots * maxRows - 1) / (slots * maxRows));
     const long long perBand = (nCells + slots * waves - 1) / (slots * waves);
     long long rows = ((perBand + SLICE_ROWS - 1) / SLICE_ROWS) * SLICE_ROWS;
