@@ -123,6 +123,32 @@ def main():
            lambda: capi.check(L.b200ldu_fv_laplacian_fill(addr.h, dp(dc), dp(gm), dp(upp), dp(dgo))))
     timeit("fvm::div fill (+negSumDiag)", 32 * F + 8 * F + 8 * N,
            lambda: capi.check(L.b200ldu_fv_convection_fill(addr.h, dp(dc), dp(gm), dp(low), dp(upp), dp(dgo))))
+    # ---- explicit MULES: limiter (3 sweeps) and the whole limit + explicitSolve update ----
+    try:
+        mules = importlib.import_module("rapidcfd-dev_b200.mules")
+        ps_, bfc_ = mesh.patch_start_facecells(mesh.wall_patches())
+        capi.fv_boundary_set(addr, bfc_)
+        nBm = len(bfc_)
+        ops = capi.FieldOps(ctx)
+        Vm = tt(mesh.volumes())
+        psi_m = torch.rand(N, dtype=torch.float64, device=dev)
+        phi_m = (torch.rand(F, dtype=torch.float64, device=dev) - 0.5) * (mesh.h ** 2)
+        zB = torch.zeros(nBm, dtype=torch.float64, device=dev)
+        wl = torch.full((F,), 0.5, dtype=torch.float64, device=dev)
+        phiPsi = ops.mul(phi_m, capi.fv_interpolate_linear(addr, 1, wl, psi_m))
+        bd, bdB = mules.upwind_flux(capi, addr, ops, phi_m, zB, psi_m, zB)
+        corr = ops.sub(phiPsi, bd)
+        rdt = 4.0 / mesh.h
+        # bounds kernel: psi, psi0, V, 4 outputs (56N) + phiBD, phiCorr (16F); per sweep: lambda, phiCorr (16F) + 4 budgets in,
+        # 2 cell limiters out (48N), then phiCorr, lambda in, lambda out (24F) + the cell limiters gathered (counted once, 16N)
+        timeit("MULES::limiter, 3 sweeps (7 launches)", 56 * N + 16 * F + 3 * (64 * N + 40 * F),
+               lambda: capi.mules_limiter(addr, Vm, rdt, psi_m, psi_m, zB, bd, zB, corr, zB, 1.0, 0.0, 3))
+        timeit("MULES::limit + explicitSolve (ABI compositions)", 56 * N + 16 * F + 3 * (64 * N + 40 * F) + 80 * F + 56 * N,
+               lambda: mules.explicit_solve(capi, addr, ops, Vm, rdt, psi_m,
+                                            *mules.limit(capi, addr, ops, Vm, rdt, psi_m, psi_m, zB, phi_m, zB, phiPsi, zB, 1.0, 0.0, 3)))
+        del Vm, psi_m, phi_m, zB, wl, phiPsi, bd, bdB, corr
+    except Exception as e:  # noqa: BLE001 -- keep the table above
+        print("MULES rows:", repr(e), file=sys.stderr)
     # ---- time to solution: GAMG vs PCG on the pressure matrix (tolerance 1e-6, relTol 0) ----
     import time
     del dc, gm, upp, low, dgo

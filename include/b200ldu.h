@@ -295,13 +295,16 @@ int b200ldu_fv_sngrad(b200ldu_addr *a, int nComp, const double *deltaCoeffs_d, c
  * b200ldu_mules_limiter = MULES::limiter (:381-745): face limiters lambda (internal faces) / lambdaB (the non-coupled boundary
  * faces of b200ldu_fv_boundary_set) of the anti-diffusive flux phiCorr = phiPsi - phiBD, nLimiterIter sweeps, such that the
  * explicit update keeps psi within [psiMin, psiMax] and the extrema of its face neighbours.  lambda / lambdaB hold the starting
- * limiter on entry (1.0 in MULES::limit).  rho_d / rho0_d NULL = geometricOneField, Sp_d / Su_d NULL = zeroField.  Static mesh,
- * single domain.  MULES::limit (:748-813) and MULES::explicitSolve (:36-78) are compositions (rapidcfd-dev_b200/mules.py). */
+ * limiter on entry (1.0 in MULES::limit).  rho_d / rho0_d NULL = geometricOneField, Sp_d / Su_d NULL = zeroField.  Static mesh.
+ * nCoupledFaces: 0, or the number of coupled (processor / cyclic) patch faces of the addressing, which then are the LAST faces of the
+ * b200ldu_fv_boundary_set list in the patch order of b200ldu_addr_create; psiB_d holds patchNeighbourField() there (b200ldu_fv_patch_
+ * neighbour_field), they are limited by coupledPatchLambdaPfMULESFunctor and after every sweep take the minimum with the other side's
+ * limiter (syncTools::syncFaceList, :743; collective over the ranks).  MULES::limit (:748-813) and MULES::explicitSolve (:36-78) are compositions (rapidcfd-dev_b200/mules.py). */
 int b200ldu_mules_limiter(b200ldu_addr *a, int nLimiterIter, double rDeltaT, const double *rho_d, const double *rho0_d,
                           const double *psi_d, const double *psi0_d, const double *psiB_d, const double *phiBD_d,
                           const double *phiBDB_d, const double *phiCorr_d, const double *phiCorrB_d, const double *Sp_d,
                           const double *Su_d, const double *V_d, double psiMax, double psiMin, double *lambda_d,
-                          double *lambdaB_d);
+                          double *lambdaB_d, int nCoupledFaces);
 
 /* ---- lduMatrix algebra on caller-order coefficient arrays (LDU/lduMatrix/lduMatrixOperations.C) ----
  * row_sum: mode 0 sumDiag (:36-57), 1 negSumDiag (:59-80), 2 sumMagOffDiag (:83-104); lower_d NULL = symmetric; in place.

@@ -51,8 +51,11 @@ def _a(x):
     return None if x is None else np.asarray(x, np.float64)
 
 
-def limiter(nCells, lower, upper, bFaceCells, V, rDeltaT, psi, psi0, psiB, phiBD, phiBDB, phiCorr, phiCorrB, psiMax, psiMin,
-            nLimiterIter=3, rho=None, rho0=None, Sp=None, Su=None, lambda0=None, lambdaB0=None):
+def limiter_steps(nCells, lower, upper, bFaceCells, V, rDeltaT, psi, psi0, psiB, phiBD, phiBDB, phiCorr, phiCorrB, psiMax, psiMin,
+                  nLimiterIter=3, rho=None, rho0=None, Sp=None, Su=None, lambda0=None, lambdaB0=None, nCoupled=0):
+    """MULES::limiter as a generator: after every sweep it yields the limiters of the trailing nCoupled boundary faces (the coupled
+    patch faces, for which psiB holds patchNeighbourField()) and is sent the other side's values -- syncTools::syncFaceList with
+    minOp (MULESTemplates.C:743).  Returns (lambda, lambdaB) through StopIteration."""
     inc = Incidence(nCells, lower, upper, bFaceCells)
     psi, psi0, psiB, V = _a(psi), _a(psi0), _a(psiB), _a(V)
     bdAll, corrAll = np.concatenate([_a(phiBD), _a(phiBDB)]), np.concatenate([_a(phiCorr), _a(phiCorrB)])
@@ -106,8 +109,58 @@ def limiter(nCells, lower, upper, bFaceCells, V, rDeltaT, psi, psi0, psiB, phiBD
         if nB:
             pcB, c = corrAll[nF:], inc.bfc
             lim = np.where(pcB > 0, np.minimum(lamAll[nF:], lambdap[c]), np.minimum(lamAll[nF:], lambdam[c]))
-            lamAll[nF:] = np.where(bdAll[nF:] + pcB > SMALL * SMALL, lim, lamAll[nF:])
+            outflow = bdAll[nF:] + pcB > SMALL * SMALL                  # patchLambdaPfMULESFunctor: non-coupled faces
+            outflow[nB - nCoupled:] = True                              # coupledPatchLambdaPfMULESFunctor: every face
+            lamAll[nF:] = np.where(outflow, lim, lamAll[nF:])
+        if nCoupled:
+            theirs = yield lamAll[nF + nB - nCoupled:].copy()
+            lamAll[nF + nB - nCoupled:] = np.minimum(lamAll[nF + nB - nCoupled:], theirs)
     return lamAll[:nF].copy(), lamAll[nF:].copy()
+
+
+def limiter(*args, **kw):
+    """single domain (no coupled faces): MULES::limiter -> (lambda, lambdaB)"""
+    assert not kw.get("nCoupled")
+    g = limiter_steps(*args, **kw)
+    try:
+        next(g)
+    except StopIteration as e:
+        return e.value
+    raise AssertionError("unreachable: no coupled faces, nothing to synchronise")
+
+
+def limiter_ranks(cases, exchange):
+    """the ranks of a decomposed case in lockstep.  cases: one dict of limiter_steps keyword arguments per rank (nCoupled > 0, psiB
+    of the coupled faces = the neighbour cells' psi); exchange(list of per-rank coupled arrays) -> list of the arrays each rank
+    receives (the same faces seen from the other side).  Returns [(lambda, lambdaB)] per rank."""
+    gens = [limiter_steps(**c) for c in cases]
+    out = [None] * len(gens)
+    try:
+        mine = [next(g) for g in gens]
+    except StopIteration:                      # nLimiterIter = 0: every generator returns at once
+        return [limiter_steps_result(c) for c in cases]
+    while True:
+        theirs = exchange(mine)
+        nxt, done = [], 0
+        for r, g in enumerate(gens):
+            try:
+                nxt.append(g.send(theirs[r]))
+            except StopIteration as e:
+                out[r] = e.value
+                done += 1
+        if done:
+            assert done == len(gens)
+            return out
+        mine = nxt
+
+
+def limiter_steps_result(c):
+    g = limiter_steps(**c)
+    try:
+        next(g)
+    except StopIteration as e:
+        return e.value
+    raise AssertionError("expected no sweep")
 
 
 def upwind_flux(lower, upper, phi, phiB, psi, psiB):
@@ -158,8 +211,9 @@ def reference_available():
 
 
 def reference(mode, nCells, lower, upper, patchStart, bFaceCells, V, rDeltaT, psi, psi0, psiB, a, b, psiMax=1.0, psiMin=0.0,
-              nLimiterIter=3, rho=None, rho0=None, Sp=None, Su=None):
-    """mode 0: MULES::limiter(a = phiBD, b = phiCorr) -> allLambda; 1: MULES::limit(a = phi, b = phiPsi) -> phiPsi;
+              nLimiterIter=3, rho=None, rho0=None, Sp=None, Su=None, nCoupledPatches=0, lambda0=None):
+    """mode 0: MULES::limiter(a = phiBD, b = phiCorr) -> allLambda (lambda0: the starting limiter, default 1; the trailing
+    nCoupledPatches patches answer coupled() and psiB holds their patchNeighbourField(); syncFaceList is a no-op in the harness); 1: MULES::limit(a = phi, b = phiPsi) -> phiPsi;
     2: MULES::explicitSolve(a = phiPsi) -> psi.  a, b: internal faces followed by the boundary faces in patch order.
     The patch sort addressing comes from the reference's own lduAddressing.C (ref_ldu.ldu_addressing)."""
     global _lib
@@ -179,13 +233,31 @@ def reference(mode, nCells, lower, upper, patchStart, bFaceCells, V, rDeltaT, ps
     os_, ls, lo = i32(ad["ownerStart"]), i32(ad["losortStart"]), i32(ad["losort"])
     nF, nB = len(l), len(bfc)
     out = np.zeros(nCells if mode == 2 else nF + nB)
-    arrs = [f64(x) for x in (V, psi, psi0, psiB, rho, rho0, Sp, Su, a, b)]
-    Vv, psi_, psi0_, psiB_, rho_, rho0_, Sp_, Su_, a_, b_ = arrs
+    arrs = [f64(x) for x in (V, psi, psi0, psiB, rho, rho0, Sp, Su, a, b, lambda0)]
+    Vv, psi_, psi0_, psiB_, rho_, rho0_, Sp_, Su_, a_, b_, l0_ = arrs
     _lib.ref_mules.argtypes = ([C.c_int] * 3 + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 7 + [C.c_double] + [C.c_void_p] * 9 +
-                               [C.c_double, C.c_double, C.c_int, C.c_void_p])
+                               [C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p])
     rc = _lib.ref_mules(mode, int(nCells), nF, p(l), p(u), p(os_), p(ls), p(lo), nP, p(ps), p(bfc), p(scs), p(sc), p(sa), p(ss),
                         p(Vv), float(rDeltaT), p(psi_), p(psi0_), p(psiB_), p(rho_), p(rho0_), p(Sp_), p(Su_), p(a_), p(b_),
-                        float(psiMax), float(psiMin), int(nLimiterIter), p(out))
+                        float(psiMax), float(psiMin), int(nLimiterIter), p(out), int(nCoupledPatches), p(l0_))
     if rc != 0:
         raise RuntimeError("the reference code raised an error")
     return out
+
+
+def reference_ranks(cases, patchStarts, nCoupledPatches, exchange, nLimiterIter):
+    """MULES::limiter of a decomposed case through the reference's own code: one call with nLimiterIter = 1 per rank and sweep
+    (the flux budgets of the first part do not depend on lambda, so k calls of one sweep = one call of k sweeps), the minimum with
+    the other side's values in between -- what syncFaceList does.  cases: limiter_steps keyword dicts (nCoupled faces trailing)."""
+    lam = [np.ones(len(c["lower"]) + len(c["bFaceCells"])) for c in cases]
+    for _ in range(nLimiterIter):
+        for r, c in enumerate(cases):
+            lam[r] = reference(0, c["nCells"], c["lower"], c["upper"], patchStarts[r], c["bFaceCells"], c["V"], c["rDeltaT"], c["psi"],
+                               c["psi0"], c["psiB"], np.concatenate([c["phiBD"], c["phiBDB"]]),
+                               np.concatenate([c["phiCorr"], c["phiCorrB"]]), c["psiMax"], c["psiMin"], 1, c.get("rho"), c.get("rho0"),
+                               c.get("Sp"), c.get("Su"), nCoupledPatches[r], lam[r])
+        theirs = exchange([l[len(l) - c["nCoupled"]:] for l, c in zip(lam, cases)])
+        for r, c in enumerate(cases):
+            k = c["nCoupled"]
+            lam[r][len(lam[r]) - k:] = np.minimum(lam[r][len(lam[r]) - k:], theirs[r])
+    return [(l[: len(c["lower"])], l[len(c["lower"]):]) for l, c in zip(lam, cases)]

@@ -25,7 +25,7 @@ struct Case {
     Case(int n, int nF, const int *l, const int *u, const int *ownerStart, const int *losortStart, const int *losort, int nP,
          const int *patchStart, const int *bFaceCells, const int *sortCellsStart, const int *sortCells, const int *sortAddr,
          const int *sortStart, const double *V, double rDeltaT, const double *psi_, const double *psi0_, const double *psiB,
-         const double *rho_, const double *rho0_, const double *Sp_, const double *Su_)
+         const double *rho_, const double *rho0_, const double *Sp_, const double *Su_, int nCoupledPatches)
     {
         lduAddressing &a = mesh.addr_;
         a.nCells_ = n;
@@ -52,6 +52,7 @@ struct Case {
             a.patchSortV_[(size_t)p].view(sortAddr + s, e - s);
             a.patchSortStartV_[(size_t)p].view(sortStart + cs + p, nu + 1); /* nu + 1 entries per patch */
             psi.boundary_[(size_t)p].view(psiB + s, e - s);
+            psi.boundary_[(size_t)p].coupled_ = p >= nP - nCoupledPatches; /* the trailing patches (processor patches come last) */
         }
         psi.mesh_ = &mesh;
         psi.view(psi_, n);
@@ -88,13 +89,14 @@ struct Case {
 
 template <class Rho, class SpT, class SuT>
 void run(int mode, Case &c, double rDeltaT, const Rho &rho, const SpT &Sp, const SuT &Su, const double *a, const double *b,
-         double psiMax, double psiMin, int nIter, double *out)
+         double psiMax, double psiMin, int nIter, double *out, const double *lambda0)
 {
-    if (mode == 0) { /* limiter: a = phiBD, b = phiCorr -> out = allLambda */
+    if (mode == 0) { /* limiter: a = phiBD, b = phiCorr, lambda0 = the starting limiter (null: 1) -> out = allLambda */
         surfaceScalarField phiBD, phiCorr;
         c.surface(phiBD, a);
         c.surface(phiCorr, b);
         scalargpuField allLambda(c.mesh.nFaces(), 1.0);
+        if (lambda0) std::copy(lambda0, lambda0 + c.mesh.nFaces(), allLambda.data());
         MULES::limiter(allLambda, rDeltaT, rho, c.psi, phiBD, phiCorr, Sp, Su, psiMax, psiMin, nIter);
         std::copy(allLambda.data(), allLambda.data() + allLambda.size(), out);
     } else if (mode == 1) { /* limit: a = phi, b = phiPsi -> out = the limited phiPsi */
@@ -120,19 +122,22 @@ extern "C" int ref_mules(int mode, int n, int nF, const int *l, const int *u, co
                          const int *sortCells, const int *sortAddr, const int *sortStart, const double *V, double rDeltaT,
                          const double *psi, const double *psi0, const double *psiB, const double *rho, const double *rho0,
                          const double *Sp, const double *Su, const double *a, const double *b, double psiMax, double psiMin,
-                         int nIter, double *out)
+                         int nIter, double *out, int nCoupledPatches, const double *lambda0)
 {
+    /* nCoupledPatches: the trailing patches answer coupled() = true and psiB holds their patchNeighbourField(); the shim's
+     * syncFaceList is a no-op, so a multi-domain run calls this with nIter = 1 per sweep and takes the minimum with the other
+     * side's values in between (oracle/mules_oracle.py reference_ranks) */
     Case c(n, nF, l, u, ownerStart, losortStart, losort, nP, patchStart, bFaceCells, sortCellsStart, sortCells, sortAddr, sortStart,
-           V, rDeltaT, psi, psi0, psiB, rho, rho0, Sp, Su);
+           V, rDeltaT, psi, psi0, psiB, rho, rho0, Sp, Su, nCoupledPatches);
     try {
         if (rho && Sp)
-            run(mode, c, rDeltaT, c.rho, c.Sp, c.Su, a, b, psiMax, psiMin, nIter, out);
+            run(mode, c, rDeltaT, c.rho, c.Sp, c.Su, a, b, psiMax, psiMin, nIter, out, lambda0);
         else if (rho)
-            run(mode, c, rDeltaT, c.rho, zeroField(), zeroField(), a, b, psiMax, psiMin, nIter, out);
+            run(mode, c, rDeltaT, c.rho, zeroField(), zeroField(), a, b, psiMax, psiMin, nIter, out, lambda0);
         else if (Sp)
-            run(mode, c, rDeltaT, geometricOneField(), c.Sp, c.Su, a, b, psiMax, psiMin, nIter, out);
+            run(mode, c, rDeltaT, geometricOneField(), c.Sp, c.Su, a, b, psiMax, psiMin, nIter, out, lambda0);
         else
-            run(mode, c, rDeltaT, geometricOneField(), zeroField(), zeroField(), a, b, psiMax, psiMin, nIter, out);
+            run(mode, c, rDeltaT, geometricOneField(), zeroField(), zeroField(), a, b, psiMax, psiMin, nIter, out, lambda0);
     } catch (const std::runtime_error &) {
         return -1;
     }

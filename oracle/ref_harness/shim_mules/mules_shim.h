@@ -147,7 +147,8 @@ class fvPatchScalarField : public scalargpuField
 public:
     using scalargpuField::scalargpuField;
     using scalargpuField::operator=;
-    bool coupled() const { return false; }
+    bool coupled_ = false; /* processor / cyclic patch: the harness hands the neighbour values over as the patch values */
+    bool coupled() const { return coupled_; }
     tsf patchNeighbourField() const { return tsf(new scalargpuField(static_cast<const scalargpuField &>(*this))); }
 };
 class fvsPatchScalarField : public scalargpuField

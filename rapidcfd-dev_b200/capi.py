@@ -144,7 +144,7 @@ def lib():
     L.b200ldu_fvm_set_reference.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     L.b200ldu_fv_patch_neighbour_field.argtypes = [vp, C.c_int, vp, vp]
     L.b200ldu_fv_sngrad.argtypes = [vp, C.c_int, vp, vp, vp]
-    L.b200ldu_mules_limiter.argtypes = [vp, C.c_int, C.c_double] + [vp] * 12 + [C.c_double, C.c_double, vp, vp]
+    L.b200ldu_mules_limiter.argtypes = [vp, C.c_int, C.c_double] + [vp] * 12 + [C.c_double, C.c_double, vp, vp, C.c_int]
     L.b200ldu_ldu_row_sum.argtypes = [vp, C.c_int, vp, vp, vp]
     L.b200ldu_ldu_add_assign.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
     L.b200ldu_ldu_scale.argtypes = [vp, vp, C.c_double, vp, vp, vp, vp]
@@ -657,14 +657,15 @@ def fv_limited_weights(ctx, faceFlux, limiter=None, cdWeights=None):
 
 
 def mules_limiter(addr, V, rDeltaT, psi, psi0, psiB, phiBD, phiBDB, phiCorr, phiCorrB, psiMax, psiMin, nLimiterIter=3,
-                  rho=None, rho0=None, Sp=None, Su=None):
-    """MULES::limiter: (lambda on the internal faces, lambda on the boundary faces of fv_boundary_set), starting from 1"""
+                  rho=None, rho0=None, Sp=None, Su=None, nCoupled=0):
+    """MULES::limiter: (lambda on the internal faces, lambda on the boundary faces of fv_boundary_set), starting from 1.  nCoupled:
+    the trailing boundary faces that are coupled patch faces (psiB = patchNeighbourField there); collective over the ranks"""
     import torch
     lam = torch.ones(addr.nFaces, dtype=torch.float64, device=psi.device)
     lamB = torch.ones(max(phiCorrB.numel(), 1), dtype=torch.float64, device=psi.device)
     check(lib().b200ldu_mules_limiter(addr.h, int(nLimiterIter), float(rDeltaT), _dp(rho), _dp(rho0), _dp(psi), _dp(psi0), _dp(psiB),
                                       _dp(phiBD), _dp(phiBDB), _dp(phiCorr), _dp(phiCorrB), _dp(Sp), _dp(Su), _dp(V), float(psiMax),
-                                      float(psiMin), _dp(lam), _dp(lamB)))
+                                      float(psiMin), _dp(lam), _dp(lamB), int(nCoupled)))
     return lam, lamB[: phiCorrB.numel()]
 
 

@@ -116,21 +116,26 @@ int pick_band_rows(int nCells, int smCount)
         int v = atoi(e);
         if (v >= SLICE_ROWS && v % SLICE_ROWS == 0 && v <= 16384) return v;
     }
-    // A sweep is one CTA per band, 6 resident per SM.  Large meshes (>= 4 waves of 2048-row bands) take 2048 rows: with many
-    // waves the CTAs drift out of phase, staging and streaming overlap across CTAs, and a partly filled last wave is a small
-    // share.  Small meshes (one rank of a strong-scaling split) are quantised into whole waves: the smallest number of waves
-    // whose bands stay within ~2400 rows (the tile of a band + its halo must leave room for 6 CTAs per SM), bands sized to
-    // fill them exactly.  Measured on B200, fused PCG, Mcell-iters/s: 128^3 (2.1 M cells) 512 rows (4.6 waves) 18.8 k, 1024
-    // rows 19.2 k, 2368 rows (one wave of 886 CTAs) 19.9-20.3 k; 256^3 (16.8 M) 2048 rows (9.2 waves) 23.6 k, 2368 rows
-    // (8 whole waves) 23.1 k on the same box (profiles/r02_bench_n1*.json).
+    // A sweep is one CTA per band, 6 resident per SM (888 slots on B200).  Measured on B200, fused PCG, Mcell-iters/s
+    // (profiles/r02_band_rows.txt):
+    //   128^3 (2.1 M cells):  512 rows (4.6 waves) 18.8 k | 1024 rows (2.3 waves) 19.2 k | 2368 rows (ONE wave, 886 CTAs) 19.9-20.3 k
+    //   161^3 (4.2 M):       1024 rows (4.6 waves) 20.7 k | 2048 rows (2.3 waves) 19.8 k | 2368 rows (two whole waves) 17.7 k
+    //   256^3 (16.8 M):      2048 rows (9.2 waves) 23.6 k | 2368 rows (eight whole waves) 23.1 k
+    // A mesh that fits one wave is best served by exactly one (every CTA resident at once, 886 partial sums instead of 4096 for
+    // the scalar step).  Beyond that, whole waves are the WORST choice -- the CTAs of a wave stage and stream in lock-step, so the
+    // SM alternates between a latency-bound and a bandwidth-bound phase -- and 4+ waves of smaller bands, which drift out of
+    // phase, are best; the bands grow to 2048 rows as the mesh allows.
     const long long slots = (long long)(smCount > 0 ? smCount : 148) * 6;
-    const long long maxRows = 2432;
-    if (nCells >= slots * 4 * 2048) return 2048;
-    const long long waves = std::max<long long>(1, (nCells + slots * maxRows - 1) / (slots * maxRows));
-    const long long perBand = (nCells + slots * waves - 1) / (slots * waves);
-    long long rows = ((perBand + SLICE_ROWS - 1) / SLICE_ROWS) * SLICE_ROWS;
-    if (rows < SLICE_ROWS) rows = SLICE_ROWS;
-    return (int)rows;
+    const long long maxRows = 2432; // the tile of a band + its halo must leave room for 6 CTAs per SM
+    if (nCells <= slots * maxRows) {
+        const long long perBand = (nCells + slots - 1) / slots;
+        long long rows = ((perBand + SLICE_ROWS - 1) / SLICE_ROWS) * SLICE_ROWS;
+        return (int)std::max<long long>(rows, SLICE_ROWS);
+    }
+    const long long target = nCells / (slots * 4);
+    int b = SLICE_ROWS;
+    while (b * 2 <= target && b < 2048) b *= 2;
+    return b;
 }
 
 } // namespace

@@ -6,8 +6,8 @@
 // MULESFunctors.H: sumlPhiMULESFunctor, patchSumlPhiMULESFunctor, sumlPhipFinalMULESFunctor,
 // lambdaIfMULESFunctor).  The reference runs one functor over the cells and then one per patch over the
 // patch's cells; here one thread per cell walks its owner faces, its neighbour faces (losort) and its boundary
-// faces (flat list in patch order) in that same order, so every sum has the reference's order.  Static mesh,
-// non-coupled boundary patches (single domain).
+// faces (flat list in patch order) in that same order, so every sum has the reference's order.  Static mesh.  Coupled
+// (processor / cyclic) patch faces are the trailing faces of the boundary list, with psiB = patchNeighbourField().
 #ifndef B200LDU_MULES_KERNELS_CUH
 #define B200LDU_MULES_KERNELS_CUH
 #include <cstddef>
@@ -139,8 +139,9 @@ __global__ void mules_cell_lambda_kernel(int nCells, const int *__restrict__ own
 }
 
 // Step 3: face limiters from the cell limiters (lambdaIfMULESFunctor; boundary: patchLambdaPfMULESFunctor, outflow
-// faces only).  i < nFaces: internal face i; else boundary face i - nFaces.
-__global__ void mules_face_lambda_kernel(int nFaces, int nBFaces, const int *__restrict__ lower, const int *__restrict__ upper,
+// faces only; the trailing nCoupled boundary faces are coupled patch faces: coupledPatchLambdaPfMULESFunctor, every face).
+// i < nFaces: internal face i; else boundary face i - nFaces.
+__global__ void mules_face_lambda_kernel(int nFaces, int nBFaces, int nCoupled, const int *__restrict__ lower, const int *__restrict__ upper,
                                          const int *__restrict__ bFaceCells, const double *__restrict__ phiCorr,
                                          const double *__restrict__ phiCorrB, const double *__restrict__ phiBDB,
                                          const double *__restrict__ lambdam, const double *__restrict__ lambdap,
@@ -154,11 +155,18 @@ __global__ void mules_face_lambda_kernel(int nFaces, int nBFaces, const int *__r
     } else if (i < nFaces + nBFaces) {
         const int bf = i - nFaces;
         const double l = lambdaB[bf], pc = phiCorrB[bf];
-        if (__dadd_rn(phiBDB[bf], pc) > MULES_SMALL * MULES_SMALL) {
+        if (bf >= nBFaces - nCoupled || __dadd_rn(phiBDB[bf], pc) > MULES_SMALL * MULES_SMALL) {
             const int c = bFaceCells[bf];
             lambdaB[bf] = pc > 0.0 ? fmin(l, lambdap[c]) : fmin(l, lambdam[c]);
         }
     }
+}
+
+// syncTools::syncFaceList(mesh, allLambda, minOp<scalar>()) on the coupled faces (MULESTemplates.C:743): mine = min(mine, theirs)
+__global__ void mules_sync_min_kernel(int n, double *__restrict__ mine, const double *__restrict__ theirs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) mine[i] = fmin(mine[i], theirs[i]);
 }
 } // namespace
 } // namespace mulesk

@@ -6,22 +6,36 @@ its FieldOps.  Reference: FV/fvMatrices/solvers/MULES/MULESTemplates.C.
                    MULES::limiter (b200ldu_mules_limiter); phiPsi = phiBD + lambda*phiCorr
   explicit_solve   MULES::explicitSolve (:36-78): psi = (rho0*psi0*rDeltaT + Su - surfaceIntegrate(phiPsi))/(rho*rDeltaT - Sp)
 rho / rho0 None: geometricOneField; Sp / Su None: zeroField -- the operations the reference's one / zero algebra drops are not
-issued.  Static mesh; boundary faces = the non-coupled faces of fv_boundary_set, in patch order."""
+issued.  Static mesh; boundary faces = the faces of fv_boundary_set in patch order, coupled (processor / cyclic) patch faces last."""
 
 
-def upwind_flux(capi, addr, ops, phi, phiB, psi, psiB):
-    """upwind<scalar>::flux (upwind.H:86-103 weights pos(faceFlux); surfaceInterpolationScheme.C:176-184 faceFlux*interpolate)"""
+def _cat(a, b):
+    import torch
+    return torch.cat([a, b])
+
+
+def upwind_flux(capi, addr, ops, phi, phiB, psi, psiB, nCoupled=0, cfc=None):
+    """upwind<scalar>::flux (upwind.H:86-103 weights pos(faceFlux); surfaceInterpolationScheme.C:176-184 faceFlux*interpolate).
+    Coupled patch faces (the trailing nCoupled boundary faces, psiB = patchNeighbourField, cfc = their face cells):
+    w*patchInternalField + (1 - w)*patchNeighbourField (surfaceInterpolationScheme.C:300-312)"""
     w = capi.fv_limited_weights(addr.ctx, phi)
-    return ops.mul(phi, capi.fv_interpolate_linear(addr, 1, w, psi)), ops.mul(phiB, psiB)
+    bd = ops.mul(phi, capi.fv_interpolate_linear(addr, 1, w, psi))
+    if not nCoupled:
+        return bd, ops.mul(phiB, psiB)
+    nW = phiB.numel() - nCoupled
+    wc = capi.fv_limited_weights(addr.ctx, phiB[nW:])
+    sf = ops.add(ops.mul(wc, ops.gather(cfc, psi)), ops.mul(ops.rsub(1.0, wc), psiB[nW:]))
+    return bd, _cat(ops.mul(phiB[:nW], psiB[:nW]), ops.mul(phiB[nW:], sf))
 
 
 def limit(capi, addr, ops, V, rDeltaT, psi, psi0, psiB, phi, phiB, phiPsi, phiPsiB, psiMax, psiMin, nLimiterIter=3,
-          rho=None, rho0=None, Sp=None, Su=None):
-    """returns the limited (phiPsi, phiPsiB)"""
-    phiBD, phiBDB = upwind_flux(capi, addr, ops, phi, phiB, psi, psiB)
+          rho=None, rho0=None, Sp=None, Su=None, nCoupled=0, cfc=None):
+    """returns the limited (phiPsi, phiPsiB).  Decomposed meshes: the boundary faces of fv_boundary_set end with the nCoupled coupled
+    patch faces (face cells cfc), psiB there = fv_patch_neighbour_field(psi); collective over the ranks"""
+    phiBD, phiBDB = upwind_flux(capi, addr, ops, phi, phiB, psi, psiB, nCoupled, cfc)
     phiCorr, phiCorrB = ops.sub(phiPsi, phiBD), ops.sub(phiPsiB, phiBDB)
     lam, lamB = capi.mules_limiter(addr, V, rDeltaT, psi, psi0, psiB, phiBD, phiBDB, phiCorr, phiCorrB, psiMax, psiMin,
-                                   nLimiterIter, rho, rho0 if rho0 is not None else rho, Sp, Su)
+                                   nLimiterIter, rho, rho0 if rho0 is not None else rho, Sp, Su, nCoupled)
     return ops.add(phiBD, ops.mul(lam, phiCorr)), ops.add(phiBDB, ops.mul(lamB, phiCorrB))
 
 

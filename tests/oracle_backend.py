@@ -294,8 +294,9 @@ class _Capi:
 
     @staticmethod
     def mules_limiter(addr, V, rDeltaT, psi, psi0, psiB, phiBD, phiBDB, phiCorr, phiCorrB, psiMax, psiMin, nLimiterIter=3,
-                      rho=None, rho0=None, Sp=None, Su=None):
+                      rho=None, rho0=None, Sp=None, Su=None, nCoupled=0):
         from oracle import mules_oracle as mo
+        assert not nCoupled, "the stand-in runs single-domain MULES only (decomposed: oracle.mules_oracle.limiter_ranks)"
         o = lambda x: None if x is None else _np(x)
         lam, lamB = mo.limiter(addr.o.nCells, addr.o.lower(), addr.o.upper(), addr.bfc, _np(V), rDeltaT, _np(psi), _np(psi0), _np(psiB),
                                _np(phiBD), _np(phiBDB), _np(phiCorr), _np(phiCorrB), psiMax, psiMin, nLimiterIter, o(rho), o(rho0),

@@ -89,3 +89,21 @@ def test_mules_advection_64_cubed_is_bounded_and_conservative(gpu, meshmod):
     for v in out.values():
         assert abs(v.sum() - psi0.sum()) <= 1e-9 * psi0.sum()
     addr.close()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_multi_gpu_mules(world):
+    """MULES over processor patches, one rank per GPU (needs >= 2 GPUs; skipped otherwise)"""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29900 + world),
+           os.path.join(root, "tests", "multi_gpu_mules_worker.py")]
+    p = subprocess.run(cmd, cwd=root, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-4000:]
+    assert p.stdout.count("MULTI-GPU-MULES-OK") == 4 * world

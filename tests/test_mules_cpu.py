@@ -96,10 +96,10 @@ def test_device_mules_code_on_the_host(hk, meshmod, orc, combo):  # noqa: F811
                                      rho=kw.get("rho"), rho0=kw.get("rho0"), Sp=kw.get("Sp"), Su=kw.get("Su")).items()}
     for nIter in (0, 2, 3):
         lam, lamB, scratch = np.ones(nF), np.ones(nB), np.zeros(6 * n)
-        hk.hk_mules_limiter.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 12 + [C.c_double, C.c_double] + [C.c_void_p] * 3
+        hk.hk_mules_limiter.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 12 + [C.c_double, C.c_double] + [C.c_void_p] * 3 + [C.c_int]
         hk.hk_mules_limiter(H.p(), nIter, d["rDeltaT"], _d(arrs["rho"]), _d(arrs["rho0"]), _d(arrs["psi"]), _d(arrs["psi0"]),
                             _d(arrs["psiB"]), _d(arrs["bd"]), _d(arrs["bdB"]), _d(arrs["corr"]), _d(arrs["corrB"]), _d(arrs["Sp"]),
-                            _d(arrs["Su"]), _d(arrs["V"]), 1.0, 0.0, _d(lam), _d(lamB), _d(scratch))
+                            _d(arrs["Su"]), _d(arrs["V"]), 1.0, 0.0, _d(lam), _d(lamB), _d(scratch), 0)
         want, wantB = mo.limiter(n, m.lower, m.upper, d["bfc"], d["V"], d["rDeltaT"], d["psi"], d["psi0"], d["psiB"], bd, bdB, corr,
                                  corrB, 1.0, 0.0, nIter, **kw)
         assert np.array_equal(lam, want) and np.array_equal(lamB, wantB)
@@ -127,6 +127,147 @@ def test_mules_sequencing_over_the_oracle_backend(meshmod, orc, combo):
     new = mules.explicit_solve(capi, addr, ops, t(d["V"]), d["rDeltaT"], t(d["psi0"]), lp, lpB, **tk)
     assert np.array_equal(new.numpy(), mo.explicit_solve(d["n"], m.lower, m.upper, d["bfc"], d["V"], d["rDeltaT"], d["psi0"], want,
                                                          wantB, **kw))
+
+
+def _h01(meshmod, key, seed):
+    return meshmod._hash01(np.asarray(key, np.uint64) + meshmod._seedmix(seed))
+
+
+def decomposed(meshmod, dims, nRanks, seed=5, combo="one-zero", scale=1e-3):
+    """the ranks of a brick decomposition with fields that are functions of the GLOBAL cell / face: per rank a dict of
+    limiter_steps keyword arguments (walls first, then the processor patch faces with psiB = the neighbour cells' psi), the
+    patch starts, the number of coupled patches, and the exchange between the ranks"""
+    G = dims[0] * dims[1] * dims[2]
+    gpsi = _h01(meshmod, np.arange(G), seed)
+    gpsi[: G // 5], gpsi[G // 5: G // 3] = 1.0, 0.0
+    gV = (1.0 / dims[0]) ** 3 * (0.8 + 0.4 * _h01(meshmod, np.arange(G), seed + 1))
+    grho, grho0 = 0.9 + 0.2 * _h01(meshmod, np.arange(G), seed + 2), 0.9 + 0.2 * _h01(meshmod, np.arange(G), seed + 3)
+    gSp, gSu = -_h01(meshmod, np.arange(G), seed + 4), 0.1 * _h01(meshmod, np.arange(G), seed + 5)
+    gphi = lambda gOwner, axis: (2 * _h01(meshmod, np.asarray(gOwner, np.uint64) * np.uint64(3) + np.asarray(axis, np.uint64), seed + 6) - 1) * scale
+    cases, starts, nCP, meshes = [], [], [], []
+    for r in range(nRanks):
+        m = meshmod.decompose(None, nRanks, r, dims=dims) if nRanks > 1 else meshmod.hex_mesh(*dims)
+        if nRanks == 1:
+            m.cellGlobal = np.arange(m.nCells)
+        g = m.cellGlobal
+        walls, procs = m.wall_patches(), m.coupled_patches()
+        ps, bfc = m.patch_start_facecells(walls + procs)
+        psiB, phiB = [], []
+        for p in walls:
+            axis = int(np.nonzero(p.Sf[0])[0][0])
+            side = 2 * axis + int(p.Sf[0, axis] > 0)
+            key = g[p.faceCells].astype(np.uint64) * np.uint64(6) + np.uint64(side)
+            psiB.append(_h01(meshmod, key, seed + 7))
+            phiB.append(np.where(_h01(meshmod, key, seed + 8) < 0.3, 0.0, (2 * _h01(meshmod, key, seed + 9) - 1) * scale))
+        for p in procs:
+            axis = int(np.nonzero(p.Sf[0])[0][0])
+            out = p.Sf[0, axis] > 0                                    # this rank holds the global owner of the face
+            psiB.append(gpsi[p.nbrGlobalCells])
+            phiB.append(gphi(g[p.faceCells], axis) if out else -gphi(p.nbrGlobalCells, axis))
+        psiB, phiB = np.concatenate(psiB), np.concatenate(phiB)
+        phi = gphi(g[m.lower], m.faceDir)
+        psi = gpsi[g]
+        nC = sum(len(p.faceCells) for p in procs)
+        nW = len(bfc) - nC
+        cellB = psi[bfc]
+        phiPsi = phi * (0.5 * (psi[m.lower] + psi[m.upper]))
+        phiPsiB = np.where(np.arange(len(bfc)) < nW, phiB * psiB, phiB * (0.5 * (cellB + psiB)))
+        bd = mo.upwind_flux(m.lower, m.upper, phi, phiB, psi, psiB)[0]            # the reference's one-weight form, w*(P - N) + N
+        bdB = np.where(np.arange(len(bfc)) < nW, phiB * psiB, phiB * np.where(phiB >= 0, cellB, psiB))
+        c = dict(nCells=m.nCells, lower=m.lower, upper=m.upper, bFaceCells=bfc, V=gV[g], rDeltaT=50.0, psi=psi, psi0=psi.copy(), psiB=psiB,
+                 phiBD=bd, phiBDB=bdB, phiCorr=phiPsi - bd, phiCorrB=phiPsiB - bdB, psiMax=1.0, psiMin=0.0, nLimiterIter=3, nCoupled=nC)
+        if "rho" in combo:
+            c.update(rho=grho[g], rho0=grho0[g])
+        if "SpSu" in combo:
+            c.update(Sp=gSp[g], Su=gSu[g])
+        cases.append(c), starts.append(ps), nCP.append(len(procs)), meshes.append(m)
+        m.mules_fluxes = (phi, phiB)                                   # for the callers that go through MULES::limit
+
+    def exchange(mine):
+        """mine[r] = the values on rank r's coupled faces (patches in neighbour-rank order) -> what each rank receives"""
+        seg = {}
+        for r, m in enumerate(meshes):
+            o = 0
+            for p in m.coupled_patches():
+                seg[(r, p.neighbRank)] = mine[r][o: o + len(p.faceCells)]
+                o += len(p.faceCells)
+        return [np.concatenate([seg[(p.neighbRank, r)] for p in m.coupled_patches()]) if m.coupled_patches() else np.zeros(0)
+                for r, m in enumerate(meshes)]
+
+    return cases, starts, nCP, exchange, meshes
+
+
+def decomposed_fluxes(meshmod, dims, nRanks, rank, seed=5):
+    """(phi, phiB) of one rank of decomposed(): the face fluxes behind its phiBD / phiCorr"""
+    return decomposed(meshmod, dims, nRanks, seed)[4][rank].mules_fluxes
+
+
+@pytest.mark.skipif(not mo.reference_available(), reason="oracle/_ref/libref_mules.so not built")
+@pytest.mark.parametrize("nRanks,combo", [(2, "one-zero"), (4, "rho-SpSu"), (8, "SpSu")])
+def test_oracle_matches_the_reference_on_a_decomposed_case(meshmod, nRanks, combo):
+    """processor patches: psi of the neighbour cells in the extrema, the coupled face rule, the minimum with the other side"""
+    cases, starts, nCP, exchange, _ = decomposed(meshmod, (8, 6, 4), nRanks, combo=combo)
+    got = mo.limiter_ranks(cases, exchange)
+    ref = mo.reference_ranks(cases, starts, nCP, exchange, 3)
+    for (lam, lamB), (rl, rlB), c in zip(got, ref, cases):
+        assert np.array_equal(lam, rl) and np.array_equal(lamB, rlB)
+        assert (lamB[len(lamB) - c["nCoupled"]:] < 1).any()
+
+
+@pytest.mark.parametrize("nRanks,combo", [(2, "rho"), (8, "one-zero")])
+def test_device_mules_code_on_the_host_decomposed(hk, meshmod, orc, nRanks, combo):  # noqa: F811
+    """the coupled-face branch of the device code: one sweep per launch sequence and rank, the minimum with the other side between"""
+    cases, _, _, exchange, _ = decomposed(meshmod, (8, 6, 4), nRanks, seed=11, combo=combo)
+    want = mo.limiter_ranks(cases, exchange)
+    f = lambda x: None if x is None else np.ascontiguousarray(x, np.float64)
+    hk.hk_mules_limiter.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 12 + [C.c_double, C.c_double] + [C.c_void_p] * 3 + [C.c_int]
+    hosts, lam, lamB, arrs = [], [], [], []
+    for c in cases:
+        a = orc.Addr(c["nCells"], c["lower"], c["upper"])
+        hosts.append(Host(a, dict(bfc=c["bFaceCells"], diag=np.zeros(c["nCells"]), upper=np.zeros(len(c["lower"])), lower=None)))
+        lam.append(np.ones(len(c["lower"]))), lamB.append(np.ones(len(c["bFaceCells"])))
+        arrs.append({k: f(c.get(k)) for k in ("rho", "rho0", "psi", "psi0", "psiB", "phiBD", "phiBDB", "phiCorr", "phiCorrB", "Sp", "Su", "V")})
+    for _ in range(3):
+        for r, c in enumerate(cases):
+            A, scratch = arrs[r], np.zeros(6 * c["nCells"])
+            hk.hk_mules_limiter(hosts[r].p(), 1, c["rDeltaT"], _d(A["rho"]), _d(A["rho0"]), _d(A["psi"]), _d(A["psi0"]), _d(A["psiB"]),
+                                _d(A["phiBD"]), _d(A["phiBDB"]), _d(A["phiCorr"]), _d(A["phiCorrB"]), _d(A["Sp"]), _d(A["Su"]), _d(A["V"]),
+                                1.0, 0.0, _d(lam[r]), _d(lamB[r]), _d(scratch), c["nCoupled"])
+        theirs = exchange([lb[len(lb) - c["nCoupled"]:] for lb, c in zip(lamB, cases)])
+        for r, c in enumerate(cases):
+            k = len(lamB[r]) - c["nCoupled"]
+            lamB[r][k:] = np.minimum(lamB[r][k:], theirs[r])
+    for r in range(nRanks):
+        assert np.array_equal(lam[r], want[r][0]) and np.array_equal(lamB[r], want[r][1])
+
+
+@pytest.mark.parametrize("nRanks", [2, 8])
+def test_decomposed_limiter_is_the_single_domain_limiter(meshmod, nRanks):
+    """both sides of a processor face end with the same limiter, and every face's limiter is the single-domain one up to the
+    order of the per-cell sums (a face that became a patch face is added after the internal ones)"""
+    dims = (8, 6, 4)
+    cases, _, _, exchange, meshes = decomposed(meshmod, dims, nRanks)
+    got = mo.limiter_ranks(cases, exchange)
+    one, _, _, _, (m1,) = decomposed(meshmod, dims, 1)
+    lam1, lamB1 = mo.limiter(**{k: v for k, v in one[0].items() if k != "nCoupled"})
+    face1 = {(int(a), int(b)): i for i, (a, b) in enumerate(zip(m1.lower, m1.upper))}
+    mine = [l[1][len(l[1]) - c["nCoupled"]:] for l, c in zip(got, cases)]
+    theirs = exchange(mine)
+    nLive = 0
+    for r, (m, (lam, lamB), c) in enumerate(zip(meshes, got, cases)):
+        g = m.cellGlobal
+        idx = [face1[(int(g[a]), int(g[b]))] for a, b in zip(m.lower, m.upper)]
+        assert np.allclose(lam, lam1[idx], rtol=0, atol=1e-11)
+        assert np.array_equal(mine[r], theirs[r])
+        o = len(lamB) - c["nCoupled"]
+        for p in m.coupled_patches():
+            k = len(p.faceCells)
+            idx = [face1[tuple(sorted((int(g[a]), int(b))))] for a, b in zip(p.faceCells, p.nbrGlobalCells)]
+            live = c["phiCorrB"][o: o + k] != 0          # a face without anti-diffusive flux takes lambdam of both sides here,
+            nLive += int(live.sum())                     # lambdam / lambdap in the single domain: its limiter multiplies zero
+            assert np.allclose(lamB[o: o + k][live], lam1[idx][live], rtol=0, atol=1e-11)
+            o += k
+    assert nLive > 20
 
 
 def advect(meshmod, limited, steps=12):
