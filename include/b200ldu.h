@@ -305,6 +305,14 @@ int b200ldu_mules_limiter(b200ldu_addr *a, int nLimiterIter, double rDeltaT, con
                           const double *phiBDB_d, const double *phiCorr_d, const double *phiCorrB_d, const double *Sp_d,
                           const double *Su_d, const double *V_d, double psiMax, double psiMin, double *lambda_d,
                           double *lambdaB_d, int nCoupledFaces);
+/* b200ldu_mules_limiter_corr = MULES::limiterCorr (CMULESTemplates.C:375-704): the limiter of a flux correction phiCorr applied to an
+ * already bounded psi (MULES::correct, :35-75; MULES::limitCorr, :706-761: phiCorr *= lambda -- compositions in rapidcfd-dev_b200/
+ * mules.py).  phiB_d: the boundary values of the total flux phi (outflow test of the non-coupled faces); extremaCoeff: the solver
+ * dictionary's entry (default 0 in the reference).  Everything else as b200ldu_mules_limiter. */
+int b200ldu_mules_limiter_corr(b200ldu_addr *a, int nLimiterIter, double rDeltaT, const double *rho_d, const double *psi_d,
+                               const double *psiB_d, const double *phiB_d, const double *phiCorr_d, const double *phiCorrB_d,
+                               const double *Sp_d, const double *Su_d, const double *V_d, double psiMax, double psiMin,
+                               double extremaCoeff, double *lambda_d, double *lambdaB_d, int nCoupledFaces);
 
 /* ---- lduMatrix algebra on caller-order coefficient arrays (LDU/lduMatrix/lduMatrixOperations.C) ----
  * row_sum: mode 0 sumDiag (:36-57), 1 negSumDiag (:59-80), 2 sumMagOffDiag (:83-104); lower_d NULL = symmetric; in place.

@@ -52,8 +52,12 @@ def _a(x):
 
 
 def limiter_steps(nCells, lower, upper, bFaceCells, V, rDeltaT, psi, psi0, psiB, phiBD, phiBDB, phiCorr, phiCorrB, psiMax, psiMin,
-                  nLimiterIter=3, rho=None, rho0=None, Sp=None, Su=None, lambda0=None, lambdaB0=None, nCoupled=0):
-    """MULES::limiter as a generator: after every sweep it yields the limiters of the trailing nCoupled boundary faces (the coupled
+                  nLimiterIter=3, rho=None, rho0=None, Sp=None, Su=None, lambda0=None, lambdaB0=None, nCoupled=0, corr=False,
+                  extremaCoeff=0.0):
+    """corr=True: MULES::limiterCorr (CMULESTemplates.C:375-704) -- the same sweeps around other budgets: no bounded flux (phiBD is
+    ignored, phiBDB holds the boundary values of the TOTAL flux phi for the outflow test of patchLambdaPfCMULESFunctor), the extrema
+    widened by extremaCoeff*(psiMax - psiMin), the current psi and rho in place of the old-time ones (psi0, rho0 are ignored).
+    MULES::limiter as a generator: after every sweep it yields the limiters of the trailing nCoupled boundary faces (the coupled
     patch faces, for which psiB holds patchNeighbourField()) and is sent the other side's values -- syncTools::syncFaceList with
     minOp (MULESTemplates.C:743).  Returns (lambda, lambdaB) through StopIteration."""
     inc = Incidence(nCells, lower, upper, bFaceCells)
@@ -69,23 +73,33 @@ def limiter_steps(nCells, lower, upper, bFaceCells, V, rDeltaT, psi, psi0, psiB,
         psiMaxn = np.where(ok, np.maximum(psiMaxn, pn), psiMaxn)
         psiMinn = np.where(ok, np.minimum(psiMinn, pn), psiMinn)
         ownerLike = kind != 1
-        sumBD = np.where(ok, np.where(ownerLike, sumBD + bdAll[f], sumBD - bdAll[f]), sumBD)
+        if not corr:
+            sumBD = np.where(ok, np.where(ownerLike, sumBD + bdAll[f], sumBD - bdAll[f]), sumBD)
         pc = corrAll[f]
         toP = (pc > 0) == ownerLike            # owner & positive, or neighbour & not positive -> sumPhip
         sumPhip = np.where(ok & toP, np.where(ownerLike, sumPhip + pc, sumPhip - pc), sumPhip)
         mSumPhim = np.where(ok & ~toP, np.where(ownerLike, mSumPhim - pc, mSumPhim + pc), mSumPhim)
-    psiMaxn, psiMinn = np.minimum(psiMaxn, psiMax), np.maximum(psiMinn, psiMin)
+    if corr:
+        e = extremaCoeff * (psiMax - psiMin)
+        psiMaxn, psiMinn = np.minimum(psiMaxn + e, psiMax), np.maximum(psiMinn - e, psiMin)
+    else:
+        psiMaxn, psiMinn = np.minimum(psiMaxn, psiMax), np.maximum(psiMinn, psiMin)
     a = rDeltaT if rho is None else _a(rho) * rDeltaT
     if Sp is not None:
         a = a - _a(Sp)
-    r0 = rho0 if rho0 is not None else rho          # rho.oldTime()
-    b = (rDeltaT if r0 is None else _a(r0) * rDeltaT) * psi0
+    if corr:                                        # rho*psi*rDeltaT (CMULESTemplates.C:508, :517)
+        b = (psi if rho is None else _a(rho) * psi) * rDeltaT
+    else:
+        r0 = rho0 if rho0 is not None else rho      # rho.oldTime(): (rho0*rDeltaT)*psi0 (MULESTemplates.C:543, :552)
+        b = (rDeltaT if r0 is None else _a(r0) * rDeltaT) * psi0
     up = a * psiMaxn
     if Su is not None:
         up = up - _a(Su)
-    psiMaxn = V * (up - b) + sumBD
     lo = -(a * psiMinn) if Su is None else _a(Su) - a * psiMinn
-    psiMinn = V * (lo + b) - sumBD
+    if corr:
+        psiMaxn, psiMinn = V * (up - b), V * (lo + b)
+    else:
+        psiMaxn, psiMinn = V * (up - b) + sumBD, V * (lo + b) - sumBD
     lamAll = np.ones(nF + nB)
     if lambda0 is not None:
         lamAll[:nF] = lambda0
@@ -109,7 +123,8 @@ def limiter_steps(nCells, lower, upper, bFaceCells, V, rDeltaT, psi, psi0, psiB,
         if nB:
             pcB, c = corrAll[nF:], inc.bfc
             lim = np.where(pcB > 0, np.minimum(lamAll[nF:], lambdap[c]), np.minimum(lamAll[nF:], lambdam[c]))
-            outflow = bdAll[nF:] + pcB > SMALL * SMALL                  # patchLambdaPfMULESFunctor: non-coupled faces
+            # non-coupled faces, outflow only: patchLambdaPfMULESFunctor (phiBD + phiCorr), patchLambdaPfCMULESFunctor (phi)
+            outflow = (bdAll[nF:] if corr else bdAll[nF:] + pcB) > SMALL * SMALL
             outflow[nB - nCoupled:] = True                              # coupledPatchLambdaPfMULESFunctor: every face
             lamAll[nF:] = np.where(outflow, lim, lamAll[nF:])
         if nCoupled:
@@ -181,6 +196,27 @@ def limit(nCells, lower, upper, bFaceCells, V, rDeltaT, psi, psi0, psiB, phi, ph
     return phiBD + lam * phiCorr, phiBDB + lamB * phiCorrB
 
 
+def limit_corr(nCells, lower, upper, bFaceCells, V, rDeltaT, psi, psiB, phiB, phiCorr, phiCorrB, psiMax, psiMin, nLimiterIter=3,
+               rho=None, Sp=None, Su=None, extremaCoeff=0.0):
+    """MULES::limitCorr (CMULESTemplates.C:706-761): phiCorr *= lambda, lambda from limiterCorr"""
+    lam, lamB = limiter(nCells, lower, upper, bFaceCells, V, rDeltaT, psi, psi, psiB, np.zeros(len(lower)), phiB, phiCorr, phiCorrB,
+                        psiMax, psiMin, nLimiterIter, rho, None, Sp, Su, corr=True, extremaCoeff=extremaCoeff)
+    return _a(phiCorr) * lam, _a(phiCorrB) * lamB
+
+
+def correct(nCells, lower, upper, bFaceCells, V, rDeltaT, psi, phiCorr, phiCorrB, rho=None, Sp=None, Su=None):
+    """MULES::correct (CMULESTemplates.C:35-75): psi = (rho*psi*rDeltaT + Su - surfaceIntegrate(phiCorr))/(rho*rDeltaT - Sp)"""
+    sI = surface_integrate(nCells, lower, upper, bFaceCells, V, phiCorr, phiCorrB)
+    num = (_a(psi) if rho is None else _a(rho) * _a(psi)) * rDeltaT
+    if Su is not None:
+        num = num + _a(Su)
+    num = num - sI
+    den = rDeltaT if rho is None else _a(rho) * rDeltaT
+    if Sp is not None:
+        den = den - _a(Sp)
+    return num / den
+
+
 def surface_integrate(nCells, lower, upper, bFaceCells, V, ssf, bssf):
     inc = Incidence(nCells, lower, upper, bFaceCells)
     allf = np.concatenate([_a(ssf), _a(bssf)])
@@ -211,10 +247,11 @@ def reference_available():
 
 
 def reference(mode, nCells, lower, upper, patchStart, bFaceCells, V, rDeltaT, psi, psi0, psiB, a, b, psiMax=1.0, psiMin=0.0,
-              nLimiterIter=3, rho=None, rho0=None, Sp=None, Su=None, nCoupledPatches=0, lambda0=None):
+              nLimiterIter=3, rho=None, rho0=None, Sp=None, Su=None, nCoupledPatches=0, lambda0=None, extremaCoeff=0.0):
     """mode 0: MULES::limiter(a = phiBD, b = phiCorr) -> allLambda (lambda0: the starting limiter, default 1; the trailing
     nCoupledPatches patches answer coupled() and psiB holds their patchNeighbourField(); syncFaceList is a no-op in the harness); 1: MULES::limit(a = phi, b = phiPsi) -> phiPsi;
-    2: MULES::explicitSolve(a = phiPsi) -> psi.  a, b: internal faces followed by the boundary faces in patch order.
+    2: MULES::explicitSolve(a = phiPsi) -> psi; 3: MULES::limiterCorr(a = phi, b = phiCorr) -> allLambda; 4: MULES::limitCorr -> the
+    limited phiCorr; 5: MULES::correct(b = phiCorr) -> psi.  a, b: internal faces followed by the boundary faces in patch order.
     The patch sort addressing comes from the reference's own lduAddressing.C (ref_ldu.ldu_addressing)."""
     global _lib
     from oracle import ref_ldu
@@ -232,14 +269,14 @@ def reference(mode, nCells, lower, upper, patchStart, bFaceCells, V, rDeltaT, ps
     ss = i32(np.concatenate(ad["patchSortStart"])) if nP else i32([])
     os_, ls, lo = i32(ad["ownerStart"]), i32(ad["losortStart"]), i32(ad["losort"])
     nF, nB = len(l), len(bfc)
-    out = np.zeros(nCells if mode == 2 else nF + nB)
+    out = np.array(psi, np.float64).copy() if mode == 5 else np.zeros(nCells if mode == 2 else nF + nB)
     arrs = [f64(x) for x in (V, psi, psi0, psiB, rho, rho0, Sp, Su, a, b, lambda0)]
     Vv, psi_, psi0_, psiB_, rho_, rho0_, Sp_, Su_, a_, b_, l0_ = arrs
     _lib.ref_mules.argtypes = ([C.c_int] * 3 + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 7 + [C.c_double] + [C.c_void_p] * 9 +
-                               [C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p])
+                               [C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_double])
     rc = _lib.ref_mules(mode, int(nCells), nF, p(l), p(u), p(os_), p(ls), p(lo), nP, p(ps), p(bfc), p(scs), p(sc), p(sa), p(ss),
                         p(Vv), float(rDeltaT), p(psi_), p(psi0_), p(psiB_), p(rho_), p(rho0_), p(Sp_), p(Su_), p(a_), p(b_),
-                        float(psiMax), float(psiMin), int(nLimiterIter), p(out), int(nCoupledPatches), p(l0_))
+                        float(psiMax), float(psiMin), int(nLimiterIter), p(out), int(nCoupledPatches), p(l0_), float(extremaCoeff))
     if rc != 0:
         raise RuntimeError("the reference code raised an error")
     return out

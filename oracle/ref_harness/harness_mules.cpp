@@ -2,7 +2,7 @@
  * harness_mules.cpp -- runs the REFERENCE'S OWN explicit MULES on the CPU.  TEST INFRASTRUCTURE ONLY.
  * Included by path from /root/reference (symlinks in oracle/_ref/inc_mules/):
  *   FV/fvMatrices/solvers/MULES/MULES.H, MULESTemplates.C (explicitSolve :36-78, limiter :381-745 with its functors
- *   :143-377, limit :748-813), MULESFunctors.H
+ *   :143-377, limit :748-813), MULESFunctors.H, CMULES.H, CMULESTemplates.C (correct, limiterCorr, limitCorr)
  *   OpenFOAM/primitives/one/one.H, oneI.H, zero/zero.H, zeroI.H, fields/Fields/oneField/*, zeroField/*,
  *   fields/FieldFields/oneFieldField/*, fields/GeometricFields/geometricOneField/*
  * against oracle/ref_harness/shim_mules/ (+ shim/foam_shim.h).  What the shim restates instead of including is listed
@@ -13,6 +13,7 @@
 
 #include "geometricOneField.H"
 #include "MULES.H"
+#include "CMULES.H" /* CMULESTemplates.C: correct :35-75, limiterCorr :375-704 with its functors :156-372, limitCorr :706-761 */
 
 using namespace Foam;
 
@@ -105,6 +106,28 @@ void run(int mode, Case &c, double rDeltaT, const Rho &rho, const SpT &Sp, const
         c.surface(phiPsi, b);
         MULES::limit(rDeltaT, rho, c.psi, phi, phiPsi, Sp, Su, psiMax, psiMin, nIter, false);
         c.flat(phiPsi, out);
+    } else if (mode == 3) { /* limiterCorr: a = phi, b = phiCorr, lambda0 -> out = allLambda */
+        surfaceScalarField phi, phiCorr;
+        c.surface(phi, a);
+        c.surface(phiCorr, b);
+        scalargpuField allLambda(c.mesh.nFaces(), 1.0);
+        if (lambda0) std::copy(lambda0, lambda0 + c.mesh.nFaces(), allLambda.data());
+        MULES::limiterCorr(allLambda, rDeltaT, rho, c.psi, phi, phiCorr, Sp, Su, psiMax, psiMin, nIter);
+        std::copy(allLambda.data(), allLambda.data() + allLambda.size(), out);
+    } else if (mode == 4) { /* limitCorr: a = phi, b = phiCorr -> out = lambda*phiCorr */
+        surfaceScalarField phi, phiCorr;
+        c.surface(phi, a);
+        c.surface(phiCorr, b);
+        MULES::limitCorr(rDeltaT, rho, c.psi, phi, phiCorr, Sp, Su, psiMax, psiMin, nIter);
+        c.flat(phiCorr, out);
+    } else if (mode == 5) { /* correct: a = phi (unused by the reference), b = phiCorr; out holds psi on entry -> the corrected psi */
+        surfaceScalarField phi, phiCorr;
+        c.surface(phi, a);
+        c.surface(phiCorr, b);
+        volScalarField psi;
+        psi.mesh_ = &c.mesh;
+        psi.view(out, c.psi.size());
+        MULES::correct(rDeltaT, rho, psi, phi, phiCorr, Sp, Su);
     } else { /* explicitSolve: a = phiPsi -> out = psi */
         surfaceScalarField phiPsi;
         c.surface(phiPsi, a);
@@ -122,13 +145,14 @@ extern "C" int ref_mules(int mode, int n, int nF, const int *l, const int *u, co
                          const int *sortCells, const int *sortAddr, const int *sortStart, const double *V, double rDeltaT,
                          const double *psi, const double *psi0, const double *psiB, const double *rho, const double *rho0,
                          const double *Sp, const double *Su, const double *a, const double *b, double psiMax, double psiMin,
-                         int nIter, double *out, int nCoupledPatches, const double *lambda0)
+                         int nIter, double *out, int nCoupledPatches, const double *lambda0, double extremaCoeff)
 {
     /* nCoupledPatches: the trailing patches answer coupled() = true and psiB holds their patchNeighbourField(); the shim's
      * syncFaceList is a no-op, so a multi-domain run calls this with nIter = 1 per sweep and takes the minimum with the other
      * side's values in between (oracle/mules_oracle.py reference_ranks) */
     Case c(n, nF, l, u, ownerStart, losortStart, losort, nP, patchStart, bFaceCells, sortCellsStart, sortCells, sortAddr, sortStart,
            V, rDeltaT, psi, psi0, psiB, rho, rho0, Sp, Su, nCoupledPatches);
+    c.mesh.solverDict_.extremaCoeff_ = extremaCoeff; /* MULEScontrols.lookupOrDefault("extremaCoeff", 0.0), CMULESTemplates.C:398-401 */
     try {
         if (rho && Sp)
             run(mode, c, rDeltaT, c.rho, c.Sp, c.Su, a, b, psiMax, psiMin, nIter, out, lambda0);

@@ -119,7 +119,15 @@ template <class T, class U> inline bool isA(const U &u) { return dynamic_cast<co
 struct DimensionedInternalField { /* volScalarField::DimensionedInternalField: V, Sp, Su */
     scalargpuField f_;
     const scalargpuField &getField() const { return f_; }
+    operator const scalargpuField &() const { return f_; } /* CMULESTemplates.C:414: const scalargpuField& V = tVsc(); */
 };
+struct dictionary { /* mesh.solverDict(psi.name()): the two MULES controls CMULESTemplates.C reads */
+    scalar extremaCoeff_ = 0;
+    label nLimiterIter_ = 3;
+    template <class T> T lookupOrDefault(const word &, const T &) const { return (T)extremaCoeff_; }
+    label lookup(const word &) const { return nLimiterIter_; }
+};
+inline label readLabel(label l) { return l; }
 class fvMesh : public objectRegistry
 {
 public:
@@ -136,6 +144,8 @@ public:
     tmp<DimensionedInternalField> Vsc() const { return tmp<DimensionedInternalField>(V_); }
     tmp<DimensionedInternalField> Vsc0() const { return tmp<DimensionedInternalField>(V_); }
     const Time &time() const { return time_; }
+    dictionary solverDict_;
+    const dictionary &solverDict(const word &) const { return solverDict_; }
     label nFaces() const { return nFaces_; }
     label nInternalFaces() const { return nInternalFaces_; }
     const std::vector<fvPatch> &boundary() const { return patches_; }
@@ -177,6 +187,8 @@ public:
     const fvMesh &mesh() const { return *mesh_; }
     const scalargpuField &getField() const { return *this; }
     scalargpuField &getField() { return *this; }
+    const scalargpuField &internalField() const { return *this; }
+    scalargpuField &internalField() { return *this; }
     const volScalarField &oldTime() const { return *old_; }
     const GeometricBoundaryField &boundaryField() const { return boundary_; }
     word name() const { return word("psi"); }

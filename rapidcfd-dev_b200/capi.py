@@ -67,7 +67,7 @@ EXPORTS = [
     "b200ldu_fvm_add_boundary_diag", "b200ldu_fvm_add_boundary_source", "b200ldu_fvm_A", "b200ldu_fvm_H",
     "b200ldu_fvm_flux", "b200ldu_fvm_residual", "b200ldu_fvm_relax", "b200ldu_fvm_set_reference",
     "b200ldu_fvm_solve", "b200ldu_fv_patch_neighbour_field",
-    "b200ldu_mules_limiter", "b200ldu_ldu_row_sum", "b200ldu_ldu_add_assign", "b200ldu_ldu_scale", "b200ldu_fv_sngrad", "b200ldu_fv_limiter", "b200ldu_fv_limited_weights", "b200ldu_field_binary", "b200ldu_field_unary", "b200ldu_field_dot3", "b200ldu_field_gather",
+    "b200ldu_mules_limiter", "b200ldu_mules_limiter_corr", "b200ldu_ldu_row_sum", "b200ldu_ldu_add_assign", "b200ldu_ldu_scale", "b200ldu_fv_sngrad", "b200ldu_fv_limiter", "b200ldu_fv_limited_weights", "b200ldu_field_binary", "b200ldu_field_unary", "b200ldu_field_dot3", "b200ldu_field_gather",
 ]
 
 _lib = None
@@ -145,6 +145,7 @@ def lib():
     L.b200ldu_fv_patch_neighbour_field.argtypes = [vp, C.c_int, vp, vp]
     L.b200ldu_fv_sngrad.argtypes = [vp, C.c_int, vp, vp, vp]
     L.b200ldu_mules_limiter.argtypes = [vp, C.c_int, C.c_double] + [vp] * 12 + [C.c_double, C.c_double, vp, vp, C.c_int]
+    L.b200ldu_mules_limiter_corr.argtypes = [vp, C.c_int, C.c_double] + [vp] * 9 + [C.c_double] * 3 + [vp, vp, C.c_int]
     L.b200ldu_ldu_row_sum.argtypes = [vp, C.c_int, vp, vp, vp]
     L.b200ldu_ldu_add_assign.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
     L.b200ldu_ldu_scale.argtypes = [vp, vp, C.c_double, vp, vp, vp, vp]
@@ -666,6 +667,18 @@ def mules_limiter(addr, V, rDeltaT, psi, psi0, psiB, phiBD, phiBDB, phiCorr, phi
     check(lib().b200ldu_mules_limiter(addr.h, int(nLimiterIter), float(rDeltaT), _dp(rho), _dp(rho0), _dp(psi), _dp(psi0), _dp(psiB),
                                       _dp(phiBD), _dp(phiBDB), _dp(phiCorr), _dp(phiCorrB), _dp(Sp), _dp(Su), _dp(V), float(psiMax),
                                       float(psiMin), _dp(lam), _dp(lamB), int(nCoupled)))
+    return lam, lamB[: phiCorrB.numel()]
+
+
+def mules_limiter_corr(addr, V, rDeltaT, psi, psiB, phiB, phiCorr, phiCorrB, psiMax, psiMin, nLimiterIter=3, rho=None, Sp=None, Su=None,
+                       extremaCoeff=0.0, nCoupled=0):
+    """MULES::limiterCorr: the limiters of a flux correction, (internal faces, boundary faces of fv_boundary_set), starting from 1"""
+    import torch
+    lam = torch.ones(addr.nFaces, dtype=torch.float64, device=psi.device)
+    lamB = torch.ones(max(phiCorrB.numel(), 1), dtype=torch.float64, device=psi.device)
+    check(lib().b200ldu_mules_limiter_corr(addr.h, int(nLimiterIter), float(rDeltaT), _dp(rho), _dp(psi), _dp(psiB), _dp(phiB), _dp(phiCorr),
+                                           _dp(phiCorrB), _dp(Sp), _dp(Su), _dp(V), float(psiMax), float(psiMin), float(extremaCoeff),
+                                           _dp(lam), _dp(lamB), int(nCoupled)))
     return lam, lamB[: phiCorrB.numel()]
 
 

@@ -1,7 +1,8 @@
 // mules_kernels.cuh -- device code of csrc/mules.cu (explicit MULES limiter), free of launch syntax so that
 // tests/host_kernels/ can run it on the host against the oracle.
 //
-// Reference: FV/fvMatrices/solvers/MULES/MULESTemplates.C:381-745 (MULES::limiter) with its functors
+// Reference: FV/fvMatrices/solvers/MULES/CMULESTemplates.C:375-704 (MULES::limiterCorr, functors :156-372: `corr` below) and
+// FV/fvMatrices/solvers/MULES/MULESTemplates.C:381-745 (MULES::limiter) with its functors
 // (limiterMULESFunctor :143-258, patchMinMaxMULESFunctor :260-348, patchLambdaPfMULESFunctor :350-377,
 // MULESFunctors.H: sumlPhiMULESFunctor, patchSumlPhiMULESFunctor, sumlPhipFinalMULESFunctor,
 // lambdaIfMULESFunctor).  The reference runs one functor over the cells and then one per patch over the
@@ -36,7 +37,7 @@ __global__ void mules_bounds_kernel(int nCells, const int *__restrict__ ownerSta
                                     const double *__restrict__ Sp, const double *__restrict__ Su,
                                     const double *__restrict__ V, double rDeltaT, double psiMaxG, double psiMinG,
                                     double *__restrict__ psiMaxn, double *__restrict__ psiMinn,
-                                    double *__restrict__ sumPhip, double *__restrict__ mSumPhim)
+                                    double *__restrict__ sumPhip, double *__restrict__ mSumPhim, int corr, double extrema)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
@@ -46,7 +47,7 @@ __global__ void mules_bounds_kernel(int nCells, const int *__restrict__ ownerSta
         const double pn = psi[upper[f]];
         pMax = fmax(pMax, pn);
         pMin = fmin(pMin, pn);
-        sumBD = __dadd_rn(sumBD, phiBD[f]);
+        if (!corr) sumBD = __dadd_rn(sumBD, phiBD[f]);
         const double pc = phiCorr[f];
         if (pc > 0.0)
             sp = __dadd_rn(sp, pc);
@@ -58,7 +59,7 @@ __global__ void mules_bounds_kernel(int nCells, const int *__restrict__ ownerSta
         const double pn = psi[lower[f]];
         pMax = fmax(pMax, pn);
         pMin = fmin(pMin, pn);
-        sumBD = __dsub_rn(sumBD, phiBD[f]);
+        if (!corr) sumBD = __dsub_rn(sumBD, phiBD[f]);
         const double pc = phiCorr[f];
         if (pc > 0.0)
             sm = __dadd_rn(sm, pc);
@@ -70,27 +71,37 @@ __global__ void mules_bounds_kernel(int nCells, const int *__restrict__ ownerSta
             const int bf = bFaces[k];
             pMax = fmax(pMax, psiB[bf]);
             pMin = fmin(pMin, psiB[bf]);
-            sumBD = __dadd_rn(sumBD, phiBDB[bf]);
+            if (!corr) sumBD = __dadd_rn(sumBD, phiBDB[bf]);
             const double pc = phiCorrB[bf];
             if (pc > 0.0)
                 sp = __dadd_rn(sp, pc);
             else
                 sm = __dsub_rn(sm, pc);
         }
+    if (corr) { // limiterCorr: the extrema widened by extremaCoeff*(psiMax - psiMin) (CMULESTemplates.C:497-498)
+        pMax = __dadd_rn(pMax, extrema);
+        pMin = __dsub_rn(pMin, extrema);
+    }
     pMax = fmin(pMax, psiMaxG);
     pMin = fmax(pMin, psiMinG);
-    // (rho*rDeltaT - Sp), (rho0*rDeltaT)*psi0: one rounding per written operator
+    // (rho*rDeltaT - Sp); limiter: (rho0*rDeltaT)*psi0, limiterCorr: (rho*psi)*rDeltaT -- one rounding per written operator
     double a = rho ? __dmul_rn(rho[c], rDeltaT) : rDeltaT;
     if (Sp) a = __dsub_rn(a, Sp[c]);
-    const double b = __dmul_rn(rho0 ? __dmul_rn(rho0[c], rDeltaT) : rDeltaT, psi0[c]);
+    const double b = corr ? __dmul_rn(rho ? __dmul_rn(rho[c], psi[c]) : psi[c], rDeltaT)
+                          : __dmul_rn(rho0 ? __dmul_rn(rho0[c], rDeltaT) : rDeltaT, psi0[c]);
     const double v = V[c];
     double up = __dmul_rn(a, pMax);
     if (Su) up = __dsub_rn(up, Su[c]);
     up = __dsub_rn(up, b);
-    psiMaxn[c] = __dadd_rn(__dmul_rn(v, up), sumBD);
     double lo = __dsub_rn(Su ? Su[c] : 0.0, __dmul_rn(a, pMin));
     lo = __dadd_rn(lo, b);
-    psiMinn[c] = __dsub_rn(__dmul_rn(v, lo), sumBD);
+    if (corr) {
+        psiMaxn[c] = __dmul_rn(v, up);
+        psiMinn[c] = __dmul_rn(v, lo);
+    } else {
+        psiMaxn[c] = __dadd_rn(__dmul_rn(v, up), sumBD);
+        psiMinn[c] = __dsub_rn(__dmul_rn(v, lo), sumBD);
+    }
     sumPhip[c] = sp;
     mSumPhim[c] = sm;
 }
@@ -141,7 +152,7 @@ __global__ void mules_cell_lambda_kernel(int nCells, const int *__restrict__ own
 // Step 3: face limiters from the cell limiters (lambdaIfMULESFunctor; boundary: patchLambdaPfMULESFunctor, outflow
 // faces only; the trailing nCoupled boundary faces are coupled patch faces: coupledPatchLambdaPfMULESFunctor, every face).
 // i < nFaces: internal face i; else boundary face i - nFaces.
-__global__ void mules_face_lambda_kernel(int nFaces, int nBFaces, int nCoupled, const int *__restrict__ lower, const int *__restrict__ upper,
+__global__ void mules_face_lambda_kernel(int nFaces, int nBFaces, int nCoupled, int corr, const int *__restrict__ lower, const int *__restrict__ upper,
                                          const int *__restrict__ bFaceCells, const double *__restrict__ phiCorr,
                                          const double *__restrict__ phiCorrB, const double *__restrict__ phiBDB,
                                          const double *__restrict__ lambdam, const double *__restrict__ lambdap,
@@ -155,7 +166,8 @@ __global__ void mules_face_lambda_kernel(int nFaces, int nBFaces, int nCoupled, 
     } else if (i < nFaces + nBFaces) {
         const int bf = i - nFaces;
         const double l = lambdaB[bf], pc = phiCorrB[bf];
-        if (bf >= nBFaces - nCoupled || __dadd_rn(phiBDB[bf], pc) > MULES_SMALL * MULES_SMALL) {
+        // outflow faces only: limiter tests phiBD + phiCorr, limiterCorr the total flux (phiBDB then holds phi's boundary values)
+        if (bf >= nBFaces - nCoupled || (corr ? phiBDB[bf] : __dadd_rn(phiBDB[bf], pc)) > MULES_SMALL * MULES_SMALL) {
             const int c = bFaceCells[bf];
             lambdaB[bf] = pc > 0.0 ? fmin(l, lambdap[c]) : fmin(l, lambdam[c]);
         }

@@ -5,6 +5,9 @@ its FieldOps.  Reference: FV/fvMatrices/solvers/MULES/MULESTemplates.C.
   limit            MULES::limit (:748-813): phiBD = upwind<scalar>(mesh, phi).flux(psi); phiCorr = phiPsi - phiBD; lambda = 1;
                    MULES::limiter (b200ldu_mules_limiter); phiPsi = phiBD + lambda*phiCorr
   explicit_solve   MULES::explicitSolve (:36-78): psi = (rho0*psi0*rDeltaT + Su - surfaceIntegrate(phiPsi))/(rho*rDeltaT - Sp)
+  limit_corr       MULES::limitCorr (CMULESTemplates.C:706-761): phiCorr *= lambda, lambda from MULES::limiterCorr
+                   (b200ldu_mules_limiter_corr)
+  correct          MULES::correct (CMULESTemplates.C:35-75): psi = (rho*psi*rDeltaT + Su - surfaceIntegrate(phiCorr))/(rho*rDeltaT - Sp)
 rho / rho0 None: geometricOneField; Sp / Su None: zeroField -- the operations the reference's one / zero algebra drops are not
 issued.  Static mesh; boundary faces = the faces of fv_boundary_set in patch order, coupled (processor / cyclic) patch faces last."""
 
@@ -44,6 +47,29 @@ def explicit_solve(capi, addr, ops, V, rDeltaT, psi0, phiPsi, phiPsiB, rho=None,
     sI = capi.fv_surface_integrate(addr, 1, phiPsi, phiPsiB, V, True, -1)
     r0 = rho0 if rho0 is not None else rho
     num = ops.smul(rDeltaT, psi0 if r0 is None else ops.mul(r0, psi0))
+    if Su is not None:
+        num = ops.add(num, Su)
+    num = ops.sub(num, sI)
+    if rho is None and Sp is None:
+        return ops.sdiv(num, rDeltaT)
+    den = ops.smul(rDeltaT, rho) if rho is not None else None
+    if Sp is not None:
+        den = ops.sub(den, Sp) if den is not None else ops.rsub(rDeltaT, Sp)
+    return ops.div(num, den)
+
+
+def limit_corr(capi, addr, ops, V, rDeltaT, psi, psiB, phiB, phiCorr, phiCorrB, psiMax, psiMin, nLimiterIter=3, rho=None, Sp=None,
+               Su=None, extremaCoeff=0.0, nCoupled=0):
+    """returns the limited correction (lambda*phiCorr, lambdaB*phiCorrB); phiB: boundary values of the total flux"""
+    lam, lamB = capi.mules_limiter_corr(addr, V, rDeltaT, psi, psiB, phiB, phiCorr, phiCorrB, psiMax, psiMin, nLimiterIter, rho, Sp, Su,
+                                        extremaCoeff, nCoupled)
+    return ops.mul(phiCorr, lam), ops.mul(phiCorrB, lamB)
+
+
+def correct(capi, addr, ops, V, rDeltaT, psi, phiCorr, phiCorrB, rho=None, Sp=None, Su=None):
+    """returns the corrected psi"""
+    sI = capi.fv_surface_integrate(addr, 1, phiCorr, phiCorrB, V, True, -1)
+    num = ops.smul(rDeltaT, psi if rho is None else ops.mul(rho, psi))
     if Su is not None:
         num = ops.add(num, Su)
     num = ops.sub(num, sI)

@@ -168,7 +168,7 @@ void hk_limited_weights(long long n, const double *limiter, const double *cd, co
 void hk_mules_limiter(const HostCase *h, int nIter, double rDeltaT, const double *rho, const double *rho0, const double *psi,
                       const double *psi0, const double *psiB, const double *phiBD, const double *phiBDB, const double *phiCorr,
                       const double *phiCorrB, const double *Sp, const double *Su, const double *V, double psiMax, double psiMin,
-                      double *lambda, double *lambdaB, double *scratch /* 6*nCells */, int nCoupled)
+                      double *lambda, double *lambdaB, double *scratch /* 6*nCells */, int nCoupled, int corr, double extrema)
 {
     using namespace mulesk;
     const int n = h->nCells, nF = h->nFaces, nB = h->nB;
@@ -176,11 +176,11 @@ void hk_mules_limiter(const HostCase *h, int nIter, double rDeltaT, const double
            *lambdap = lambdam + n;
     const int *bs = nB ? h->bStart : nullptr;
     launch(n, 128, mules_bounds_kernel, n, h->ownerStart, h->u, h->losortStart, h->losort, h->l, bs, h->bFaces, psi, psiB, phiBD,
-           phiBDB, phiCorr, phiCorrB, psi0, rho, rho0, Sp, Su, V, rDeltaT, psiMax, psiMin, psiMaxn, psiMinn, sumPhip, mSumPhim);
+           phiBDB, phiCorr, phiCorrB, psi0, rho, rho0, Sp, Su, V, rDeltaT, psiMax, psiMin, psiMaxn, psiMinn, sumPhip, mSumPhim, corr, extrema);
     for (int j = 0; j < nIter; j++) {
         launch(n, 128, mules_cell_lambda_kernel, n, h->ownerStart, h->losortStart, h->losort, bs, h->bFaces, lambda, lambdaB,
                phiCorr, phiCorrB, psiMaxn, psiMinn, sumPhip, mSumPhim, lambdam, lambdap);
-        launch((long long)nF + nB, 256, mules_face_lambda_kernel, nF, nB, nCoupled, h->l, h->u, h->bFaceCells, phiCorr, phiCorrB, phiBDB,
+        launch((long long)nF + nB, 256, mules_face_lambda_kernel, nF, nB, nCoupled, corr, h->l, h->u, h->bFaceCells, phiCorr, phiCorrB, phiBDB,
                lambdam, lambdap, lambda, lambdaB);
     }
 }

@@ -304,6 +304,17 @@ class _Capi:
         return FieldOps._t(lam), FieldOps._t(lamB)
 
     @staticmethod
+    def mules_limiter_corr(addr, V, rDeltaT, psi, psiB, phiB, phiCorr, phiCorrB, psiMax, psiMin, nLimiterIter=3, rho=None, Sp=None,
+                           Su=None, extremaCoeff=0.0, nCoupled=0):
+        from oracle import mules_oracle as mo
+        assert not nCoupled, "the stand-in runs single-domain MULES only"
+        o = lambda x: None if x is None else _np(x)
+        lam, lamB = mo.limiter(addr.o.nCells, addr.o.lower(), addr.o.upper(), addr.bfc, _np(V), rDeltaT, _np(psi), _np(psi), _np(psiB),
+                               np.zeros(addr.nFaces), _np(phiB), _np(phiCorr), _np(phiCorrB), psiMax, psiMin, nLimiterIter, o(rho), None,
+                               o(Sp), o(Su), corr=True, extremaCoeff=extremaCoeff)
+        return FieldOps._t(lam), FieldOps._t(lamB)
+
+    @staticmethod
     def fv_boundary_set(addr, bFaceCells):
         addr.bfc = np.asarray(bFaceCells, np.int32).copy()
     GamgAgglomeration = GamgAgglomeration

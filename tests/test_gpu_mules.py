@@ -50,6 +50,36 @@ def test_mules_on_the_device(gpu, meshmod, combo):
     addr.close()
 
 
+@pytest.mark.parametrize("combo", COMBOS)
+def test_cmules_on_the_device(gpu, meshmod, combo):
+    """b200ldu_mules_limiter_corr, limit_corr and correct against the oracle, bit for bit"""
+    from test_mules_cpu import corr_case
+    capi, ctx, torch = gpu
+    mules = importlib.import_module("rapidcfd-dev_b200.mules")
+    d = corr_case(meshmod, (11, 9, 8), 13, combo)
+    m, kw = d["m"], d["kw"]
+    t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a, np.float64)).to(ctx.device)
+    addr = capi.mesh_to_device(ctx, m)
+    capi.fv_boundary_set(addr, d["bfc"])
+    ops = capi.FieldOps(ctx)
+    tk = {k: t(v) for k, v in kw.items()}
+    for ex in (0.0, 0.2):
+        lam, lamB = capi.mules_limiter_corr(addr, t(d["V"]), d["rDeltaT"], t(d["psi"]), t(d["psiB"]), t(d["phiB"]), t(d["corr"]), t(d["corrB"]),
+                                            1.0, 0.0, 3, tk.get("rho"), tk.get("Sp"), tk.get("Su"), ex)
+        want, wantB = mo.limiter(d["n"], m.lower, m.upper, d["bfc"], d["V"], d["rDeltaT"], d["psi"], d["psi"], d["psiB"], np.zeros(d["nF"]),
+                                 d["phiB"], d["corr"], d["corrB"], 1.0, 0.0, 3, kw.get("rho"), None, kw.get("Sp"), kw.get("Su"), corr=True,
+                                 extremaCoeff=ex)
+        assert np.array_equal(lam.cpu().numpy(), want) and np.array_equal(lamB.cpu().numpy(), wantB)
+    lc, lcB = mules.limit_corr(capi, addr, ops, t(d["V"]), d["rDeltaT"], t(d["psi"]), t(d["psiB"]), t(d["phiB"]), t(d["corr"]), t(d["corrB"]),
+                               1.0, 0.0, 3, **tk)
+    want, wantB = mo.limit_corr(d["n"], m.lower, m.upper, d["bfc"], d["V"], d["rDeltaT"], d["psi"], d["psiB"], d["phiB"], d["corr"],
+                                d["corrB"], 1.0, 0.0, 3, **kw)
+    assert np.array_equal(lc.cpu().numpy(), want) and np.array_equal(lcB.cpu().numpy(), wantB)
+    new = mules.correct(capi, addr, ops, t(d["V"]), d["rDeltaT"], t(d["psi"]), lc, lcB, **tk)
+    assert np.array_equal(new.cpu().numpy(), mo.correct(d["n"], m.lower, m.upper, d["bfc"], d["V"], d["rDeltaT"], d["psi"], want, wantB, **kw))
+    addr.close()
+
+
 def test_mules_advection_64_cubed_is_bounded_and_conservative(gpu, meshmod):
     """a disc of psi = 1 carried round by a discretely solenoidal flux (differences of a stream function that vanishes on the
     walls): central face values limited by MULES stay within [0, 1] to rounding and the total is conserved; without the limiter

@@ -96,10 +96,10 @@ def test_device_mules_code_on_the_host(hk, meshmod, orc, combo):  # noqa: F811
                                      rho=kw.get("rho"), rho0=kw.get("rho0"), Sp=kw.get("Sp"), Su=kw.get("Su")).items()}
     for nIter in (0, 2, 3):
         lam, lamB, scratch = np.ones(nF), np.ones(nB), np.zeros(6 * n)
-        hk.hk_mules_limiter.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 12 + [C.c_double, C.c_double] + [C.c_void_p] * 3 + [C.c_int]
+        hk.hk_mules_limiter.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 12 + [C.c_double, C.c_double] + [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_double]
         hk.hk_mules_limiter(H.p(), nIter, d["rDeltaT"], _d(arrs["rho"]), _d(arrs["rho0"]), _d(arrs["psi"]), _d(arrs["psi0"]),
                             _d(arrs["psiB"]), _d(arrs["bd"]), _d(arrs["bdB"]), _d(arrs["corr"]), _d(arrs["corrB"]), _d(arrs["Sp"]),
-                            _d(arrs["Su"]), _d(arrs["V"]), 1.0, 0.0, _d(lam), _d(lamB), _d(scratch), 0)
+                            _d(arrs["Su"]), _d(arrs["V"]), 1.0, 0.0, _d(lam), _d(lamB), _d(scratch), 0, 0, 0.0)
         want, wantB = mo.limiter(n, m.lower, m.upper, d["bfc"], d["V"], d["rDeltaT"], d["psi"], d["psi0"], d["psiB"], bd, bdB, corr,
                                  corrB, 1.0, 0.0, nIter, **kw)
         assert np.array_equal(lam, want) and np.array_equal(lamB, wantB)
@@ -220,7 +220,7 @@ def test_device_mules_code_on_the_host_decomposed(hk, meshmod, orc, nRanks, comb
     cases, _, _, exchange, _ = decomposed(meshmod, (8, 6, 4), nRanks, seed=11, combo=combo)
     want = mo.limiter_ranks(cases, exchange)
     f = lambda x: None if x is None else np.ascontiguousarray(x, np.float64)
-    hk.hk_mules_limiter.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 12 + [C.c_double, C.c_double] + [C.c_void_p] * 3 + [C.c_int]
+    hk.hk_mules_limiter.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 12 + [C.c_double, C.c_double] + [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_double]
     hosts, lam, lamB, arrs = [], [], [], []
     for c in cases:
         a = orc.Addr(c["nCells"], c["lower"], c["upper"])
@@ -232,7 +232,7 @@ def test_device_mules_code_on_the_host_decomposed(hk, meshmod, orc, nRanks, comb
             A, scratch = arrs[r], np.zeros(6 * c["nCells"])
             hk.hk_mules_limiter(hosts[r].p(), 1, c["rDeltaT"], _d(A["rho"]), _d(A["rho0"]), _d(A["psi"]), _d(A["psi0"]), _d(A["psiB"]),
                                 _d(A["phiBD"]), _d(A["phiBDB"]), _d(A["phiCorr"]), _d(A["phiCorrB"]), _d(A["Sp"]), _d(A["Su"]), _d(A["V"]),
-                                1.0, 0.0, _d(lam[r]), _d(lamB[r]), _d(scratch), c["nCoupled"])
+                                1.0, 0.0, _d(lam[r]), _d(lamB[r]), _d(scratch), c["nCoupled"], 0, 0.0)
         theirs = exchange([lb[len(lb) - c["nCoupled"]:] for lb, c in zip(lamB, cases)])
         for r, c in enumerate(cases):
             k = len(lamB[r]) - c["nCoupled"]
@@ -268,6 +268,72 @@ def test_decomposed_limiter_is_the_single_domain_limiter(meshmod, nRanks):
             assert np.allclose(lamB[o: o + k][live], lam1[idx][live], rtol=0, atol=1e-11)
             o += k
     assert nLive > 20
+
+
+def corr_case(meshmod, dims, seed, combo):
+    """a flux correction on top of the case: high-order minus upwind, perturbed on the boundary so that its faces take part"""
+    d = case(meshmod, dims, seed=seed, combo=combo)
+    m = d["m"]
+    bd, bdB = mo.upwind_flux(m.lower, m.upper, d["phi"], d["phiB"], d["psi"], d["psiB"])
+    d["corr"], d["corrB"] = d["phiPsi"] - bd, d["phiPsiB"] - bdB + 1e-5 * np.sin(np.arange(d["nB"]))
+    d["kw"].pop("rho0", None)
+    return d
+
+
+@pytest.mark.skipif(not mo.reference_available(), reason="oracle/_ref/libref_mules.so not built")
+@pytest.mark.parametrize("combo", COMBOS)
+@pytest.mark.parametrize("extremaCoeff", [0.0, 0.1])
+def test_oracle_matches_the_reference_cmules(meshmod, combo, extremaCoeff):
+    d = corr_case(meshmod, (7, 5, 4), 3, combo)
+    m, kw = d["m"], d["kw"]
+    args = (d["n"], m.lower, m.upper, d["ps"], d["bfc"], d["V"], d["rDeltaT"], d["psi"], d["psi0"], d["psiB"])
+    phiAll, corrAll = _cat(d["phi"], d["phiB"]), _cat(d["corr"], d["corrB"])
+    lam, lamB = mo.limiter(d["n"], m.lower, m.upper, d["bfc"], d["V"], d["rDeltaT"], d["psi"], d["psi"], d["psiB"], np.zeros(d["nF"]),
+                           d["phiB"], d["corr"], d["corrB"], 1.0, 0.0, 3, kw.get("rho"), None, kw.get("Sp"), kw.get("Su"), corr=True,
+                           extremaCoeff=extremaCoeff)
+    assert np.array_equal(_cat(lam, lamB), mo.reference(3, *args, phiAll, corrAll, 1.0, 0.0, 3, extremaCoeff=extremaCoeff, **kw))
+    assert (lam < 1).sum() > d["nF"] // 5 and (lamB < 1).any()
+    lc, lcB = mo.limit_corr(d["n"], m.lower, m.upper, d["bfc"], d["V"], d["rDeltaT"], d["psi"], d["psiB"], d["phiB"], d["corr"], d["corrB"],
+                            1.0, 0.0, 3, extremaCoeff=extremaCoeff, **kw)
+    assert np.array_equal(_cat(lc, lcB), mo.reference(4, *args, phiAll, corrAll, 1.0, 0.0, 3, extremaCoeff=extremaCoeff, **kw))
+    new = mo.correct(d["n"], m.lower, m.upper, d["bfc"], d["V"], d["rDeltaT"], d["psi"], lc, lcB, **kw)
+    assert np.array_equal(new, mo.reference(5, *args, phiAll, _cat(lc, lcB), **kw))
+
+
+@pytest.mark.parametrize("combo", COMBOS)
+def test_device_cmules_code_on_the_host_and_sequencing(hk, meshmod, orc, combo):  # noqa: F811
+    import torch
+    import oracle_backend as ob
+    d = corr_case(meshmod, (6, 7, 5), 4, combo)
+    m, kw, n, nF, nB = d["m"], d["kw"], d["n"], d["nF"], d["nB"]
+    H = Host(orc.Addr(n, m.lower, m.upper), dict(bfc=d["bfc"], diag=np.zeros(n), upper=np.zeros(nF), lower=None))
+    f = lambda x: None if x is None else np.ascontiguousarray(x, np.float64)
+    A = {k: f(v) for k, v in dict(psi=d["psi"], psiB=d["psiB"], phiB=d["phiB"], corr=d["corr"], corrB=d["corrB"], V=d["V"],
+                                  rho=kw.get("rho"), Sp=kw.get("Sp"), Su=kw.get("Su")).items()}
+    hk.hk_mules_limiter.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 12 + [C.c_double, C.c_double] + [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_double]
+    for ex in (0.0, 0.25):
+        lam, lamB, scratch = np.ones(nF), np.ones(nB), np.zeros(6 * n)
+        hk.hk_mules_limiter(H.p(), 3, d["rDeltaT"], _d(A["rho"]), None, _d(A["psi"]), _d(A["psi"]), _d(A["psiB"]), None, _d(A["phiB"]),
+                            _d(A["corr"]), _d(A["corrB"]), _d(A["Sp"]), _d(A["Su"]), _d(A["V"]), 1.0, 0.0, _d(lam), _d(lamB), _d(scratch),
+                            0, 1, ex * (1.0 - 0.0))
+        want, wantB = mo.limiter(n, m.lower, m.upper, d["bfc"], d["V"], d["rDeltaT"], d["psi"], d["psi"], d["psiB"], np.zeros(nF), d["phiB"],
+                                 d["corr"], d["corrB"], 1.0, 0.0, 3, kw.get("rho"), None, kw.get("Sp"), kw.get("Su"), corr=True, extremaCoeff=ex)
+        assert np.array_equal(lam, want) and np.array_equal(lamB, wantB)
+    # rapidcfd-dev_b200/mules.py limit_corr + correct over the stand-in
+    mules = importlib.import_module("rapidcfd-dev_b200.mules")
+    capi, ctx, _ = ob.fixture()
+    addr = capi.mesh_to_device(ctx, m)
+    capi.fv_boundary_set(addr, d["bfc"])
+    ops = capi.FieldOps(ctx)
+    t = lambda x: None if x is None else torch.from_numpy(np.ascontiguousarray(x, np.float64))
+    tk = {k: t(v) for k, v in kw.items()}
+    lc, lcB = mules.limit_corr(capi, addr, ops, t(d["V"]), d["rDeltaT"], t(d["psi"]), t(d["psiB"]), t(d["phiB"]), t(d["corr"]), t(d["corrB"]),
+                               1.0, 0.0, 3, **tk)
+    want, wantB = mo.limit_corr(n, m.lower, m.upper, d["bfc"], d["V"], d["rDeltaT"], d["psi"], d["psiB"], d["phiB"], d["corr"], d["corrB"],
+                                1.0, 0.0, 3, **kw)
+    assert np.array_equal(lc.numpy(), want) and np.array_equal(lcB.numpy(), wantB)
+    new = mules.correct(capi, addr, ops, t(d["V"]), d["rDeltaT"], t(d["psi"]), lc, lcB, **tk)
+    assert np.array_equal(new.numpy(), mo.correct(n, m.lower, m.upper, d["bfc"], d["V"], d["rDeltaT"], d["psi"], want, wantB, **kw))
 
 
 def advect(meshmod, limited, steps=12):
