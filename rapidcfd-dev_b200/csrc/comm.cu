@@ -37,7 +37,7 @@
         }                                                                                   \
     } while (0)
 
-constexpr int PACK_CHUNK = 4096;
+// PACK_CHUNK (faces per packing CTA of the fused halo send): internal.h
 
 extern "C" int b200ldu_comm_unique_id(void *out128)
 {

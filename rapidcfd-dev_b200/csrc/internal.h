@@ -68,6 +68,7 @@ constexpr int P2P_MAXR = 8;
 constexpr size_t P2P_MAIL_OFF = 0;        // double mail[2][P2P_MAXR][8]
 constexpr size_t P2P_MAILFLAG_OFF = 2048; // u64 mailFlag[2][P2P_MAXR]
 constexpr size_t P2P_HALOFLAG_OFF = 4096; // u64 haloFlag[P2P_MAXR]   (indexed by source rank)
+constexpr int PACK_CHUNK = 4096; // faces per packing CTA of the fused halo send (comm.cu); layout.cu reserves their CTA slots
 constexpr int P2P_GMAX = 256;             // doubles per rank in the coarsest-level gather
 constexpr size_t P2P_GATHER_OFF = 8192;   // double gather[2][P2P_MAXR][P2P_GMAX]
 constexpr size_t P2P_GFLAG_OFF = 8192 + 2 * P2P_MAXR * P2P_GMAX * sizeof(double); // u64 gflag[2][P2P_MAXR]

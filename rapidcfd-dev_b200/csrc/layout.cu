@@ -109,7 +109,7 @@ thread_local int g_bandRowsRetry = 0;
 // B200 gives a CTA 227 KB, the kernel keeps a little static scratch
 constexpr size_t TILE_BYTES_MAX = 200 * 1024;
 
-int pick_band_rows(int nCells, int smCount)
+int pick_band_rows(int nCells, int smCount, int packCtas)
 {
     if (g_bandRowsRetry) return g_bandRowsRetry;
     if (const char *e = getenv("B200LDU_BAND_ROWS")) {
@@ -125,7 +125,8 @@ int pick_band_rows(int nCells, int smCount)
     // the scalar step).  Beyond that, whole waves are the WORST choice -- the CTAs of a wave stage and stream in lock-step, so the
     // SM alternates between a latency-bound and a bandwidth-bound phase -- and 4+ waves of smaller bands, which drift out of
     // phase, are best; the bands grow to 2048 rows as the mesh allows.
-    const long long slots = (long long)(smCount > 0 ? smCount : 148) * 6;
+    // the packing CTAs of the fused halo send share the grid with the bands: keep bands + packers within the one wave
+    const long long slots = (long long)(smCount > 0 ? smCount : 148) * 6 - packCtas;
     const long long maxRows = 2432; // the tile of a band + its halo must leave room for 6 CTAs per SM
     if (nCells <= slots * maxRows) {
         const long long perBand = (nCells + slots - 1) / slots;
@@ -158,7 +159,10 @@ int layout_build(b200ldu_addr *a, const double *centres)
     build_owner_start(nCells, l, ownerStart);
     build_losort(nCells, u, losortStart, losort);
 
-    const int bandRows = pick_band_rows(nCells, a->ctx ? a->ctx->smCount : 148);
+    int packCtas = 0;
+    for (int p = 0; p < a->nPatches; p++)
+        if (p < (int)a->neighbRank.size() && a->neighbRank[p] >= 0) packCtas += (a->patchStart[p + 1] - a->patchStart[p] + PACK_CHUNK - 1) / PACK_CHUNK;
+    const int bandRows = pick_band_rows(nCells, a->ctx ? a->ctx->smCount : 148, packCtas);
     const int nBands = (nCells + bandRows - 1) / bandRows;
     const int nPad = nBands * bandRows;
     const int slicesPerBand = bandRows / SLICE_ROWS;
