@@ -17,6 +17,10 @@
 
 #include "internal.h"
 
+#include "fv_kernels.cuh"
+
+using namespace fvk;
+
 extern "C" int b200ldu_fv_boundary_set(b200ldu_addr *a, int nBFaces, const int *bFaceCells_h)
 {
     if (!a || nBFaces < 0 || (nBFaces && !bFaceCells_h)) return B200LDU_EINVAL;
@@ -47,81 +51,6 @@ extern "C" int b200ldu_fv_boundary_set(b200ldu_addr *a, int nBFaces, const int *
     return B200LDU_OK;
 }
 
-// faces whose loads are in flight together per thread (face-sum kernels)
-constexpr int FV_BATCH = 3;
-
-template <int NC>
-__global__ void surface_integrate_kernel(int nCells, const int *__restrict__ ownerStart,
-                                         const int *__restrict__ losortStart, const int *__restrict__ losort,
-                                         const int *__restrict__ bStart, const int *__restrict__ bFaces,
-                                         const double *__restrict__ ssf, const double *__restrict__ bssf,
-                                         const double *__restrict__ V, double *__restrict__ out, int divideByV,
-                                         int neiSign)
-{
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nCells) return;
-    double acc[NC];
-#pragma unroll
-    for (int k = 0; k < NC; k++) acc[k] = 0.0;
-    if constexpr (NC == 1) {
-    // faces in batches of FV_BATCH: all loads of a batch (indices, then values) are issued before the first
-    // add, so a thread keeps several independent loads in flight; the adds stay in face order
-    const int o0 = ownerStart[c], o1 = ownerStart[c + 1];
-    for (int f0 = o0; f0 < o1; f0 += FV_BATCH) {
-        double v[FV_BATCH][NC];
-#pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (f0 + b < o1)
-#pragma unroll
-                for (int k = 0; k < NC; k++) v[b][k] = ssf[(size_t)(f0 + b) * NC + k];
-#pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (f0 + b < o1)
-#pragma unroll
-                for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], v[b][k]);
-    }
-    const int n0 = losortStart[c], n1 = losortStart[c + 1];
-    for (int j0 = n0; j0 < n1; j0 += FV_BATCH) {
-        int fi[FV_BATCH];
-        double v[FV_BATCH][NC];
-#pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (j0 + b < n1) fi[b] = losort[j0 + b];
-#pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (j0 + b < n1)
-#pragma unroll
-                for (int k = 0; k < NC; k++) v[b][k] = ssf[(size_t)fi[b] * NC + k];
-#pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (j0 + b < n1)
-#pragma unroll
-                for (int k = 0; k < NC; k++) acc[k] = neiSign < 0 ? __dsub_rn(acc[k], v[b][k]) : __dadd_rn(acc[k], v[b][k]);
-    }
-    } else { // vector fields: the batch arrays cost occupancy (measured slower), plain loops
-    for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++)
-#pragma unroll
-        for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], ssf[(size_t)f * NC + k]);
-    for (int j = losortStart[c]; j < losortStart[c + 1]; j++) {
-        int f = losort[j];
-#pragma unroll
-        for (int k = 0; k < NC; k++) {
-            double v = ssf[(size_t)f * NC + k];
-            acc[k] = neiSign < 0 ? __dsub_rn(acc[k], v) : __dadd_rn(acc[k], v);
-        }
-    }
-    }
-    if (bStart)
-        for (int j = bStart[c]; j < bStart[c + 1]; j++) {
-            int bf = bFaces[j];
-#pragma unroll
-            for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], bssf[(size_t)bf * NC + k]);
-        }
-    double v = divideByV ? V[c] : 1.0;
-#pragma unroll
-    for (int k = 0; k < NC; k++) out[(size_t)c * NC + k] = divideByV ? __ddiv_rn(acc[k], v) : acc[k];
-}
-
 extern "C" int b200ldu_fv_surface_integrate(b200ldu_addr *a, int nComp, const double *ssf_d,
                                             const double *bssf_d, const double *V_d, double *out_d,
                                             int divideByV, int neiSign)
@@ -142,78 +71,6 @@ extern "C" int b200ldu_fv_surface_integrate(b200ldu_addr *a, int nComp, const do
     a->ctx->launches++;
     KERNEL_CHECK();
     return B200LDU_OK;
-}
-
-// NC = 1: vector result; NC = 3: tensor result T[i][j] = Sf[i]*ssf[j]
-template <int NC>
-__global__ void gauss_grad_kernel(int nCells, const int *__restrict__ ownerStart,
-                                  const int *__restrict__ losortStart, const int *__restrict__ losort,
-                                  const int *__restrict__ bStart, const int *__restrict__ bFaces,
-                                  const double *__restrict__ Sf, const double *__restrict__ ssf,
-                                  const double *__restrict__ bSf, const double *__restrict__ bssf,
-                                  const double *__restrict__ V, double *__restrict__ out)
-{
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nCells) return;
-    double acc[3 * NC];
-#pragma unroll
-    for (int k = 0; k < 3 * NC; k++) acc[k] = 0.0;
-    // batches of FV_BATCH faces: loads first (indices, Sf, face values), then the products and adds in face order
-    const int o0 = ownerStart[c], o1 = ownerStart[c + 1];
-    for (int f0 = o0; f0 < o1; f0 += FV_BATCH) {
-        double sv[FV_BATCH][3], fv[FV_BATCH][NC];
-#pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (f0 + b < o1) {
-                const size_t f = (size_t)(f0 + b);
-                sv[b][0] = Sf[f * 3], sv[b][1] = Sf[f * 3 + 1], sv[b][2] = Sf[f * 3 + 2];
-#pragma unroll
-                for (int j = 0; j < NC; j++) fv[b][j] = ssf[f * NC + j];
-            }
-#pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (f0 + b < o1)
-#pragma unroll
-                for (int i = 0; i < 3; i++)
-#pragma unroll
-                    for (int j = 0; j < NC; j++) acc[i * NC + j] = __dadd_rn(acc[i * NC + j], __dmul_rn(sv[b][i], fv[b][j]));
-    }
-    const int n0 = losortStart[c], n1 = losortStart[c + 1];
-    for (int q0 = n0; q0 < n1; q0 += FV_BATCH) {
-        int fi[FV_BATCH];
-        double sv[FV_BATCH][3], fv[FV_BATCH][NC];
-#pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (q0 + b < n1) fi[b] = losort[q0 + b];
-#pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (q0 + b < n1) {
-                const size_t f = (size_t)fi[b];
-                sv[b][0] = Sf[f * 3], sv[b][1] = Sf[f * 3 + 1], sv[b][2] = Sf[f * 3 + 2];
-#pragma unroll
-                for (int j = 0; j < NC; j++) fv[b][j] = ssf[f * NC + j];
-            }
-#pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (q0 + b < n1)
-#pragma unroll
-                for (int i = 0; i < 3; i++)
-#pragma unroll
-                    for (int j = 0; j < NC; j++) acc[i * NC + j] = __dsub_rn(acc[i * NC + j], __dmul_rn(sv[b][i], fv[b][j]));
-    }
-    if (bStart)
-        for (int q = bStart[c]; q < bStart[c + 1]; q++) {
-            int bf = bFaces[q];
-            double s[3] = {bSf[(size_t)bf * 3], bSf[(size_t)bf * 3 + 1], bSf[(size_t)bf * 3 + 2]};
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-                for (int j = 0; j < NC; j++)
-                    acc[i * NC + j] = __dadd_rn(acc[i * NC + j], __dmul_rn(s[i], bssf[(size_t)bf * NC + j]));
-        }
-    double v = V[c];
-#pragma unroll
-    for (int k = 0; k < 3 * NC; k++) out[(size_t)c * 3 * NC + k] = __ddiv_rn(acc[k], v);
 }
 
 extern "C" int b200ldu_fv_gauss_grad(b200ldu_addr *a, int nComp, const double *Sf_d, const double *ssf_d,
@@ -259,42 +116,6 @@ __global__ void convection_faces_kernel(int nFaces, const double *__restrict__ w
     }
 }
 
-// diag[c] = 0 - sum_{own} lower[f] - sum_{nei} upper[f]
-__global__ void neg_sum_diag_kernel(int nCells, const int *__restrict__ ownerStart,
-                                    const int *__restrict__ losortStart, const int *__restrict__ losort,
-                                    const double *__restrict__ upper, const double *__restrict__ lower,
-                                    double *__restrict__ diag)
-{
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nCells) return;
-    double acc = 0.0;
-    const int o0 = ownerStart[c], o1 = ownerStart[c + 1];
-    for (int f0 = o0; f0 < o1; f0 += FV_BATCH) {
-        double v[FV_BATCH];
-#pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (f0 + b < o1) v[b] = lower[f0 + b];
-#pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (f0 + b < o1) acc = __dsub_rn(acc, v[b]);
-    }
-    const int n0 = losortStart[c], n1 = losortStart[c + 1];
-    for (int j0 = n0; j0 < n1; j0 += FV_BATCH) {
-        int fi[FV_BATCH];
-        double v[FV_BATCH];
-#pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (j0 + b < n1) fi[b] = losort[j0 + b];
-#pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (j0 + b < n1) v[b] = upper[fi[b]];
-#pragma unroll
-        for (int b = 0; b < FV_BATCH; b++)
-            if (j0 + b < n1) acc = __dsub_rn(acc, v[b]);
-    }
-    diag[c] = acc;
-}
-
 extern "C" int b200ldu_fv_laplacian_fill(b200ldu_addr *a, const double *deltaCoeffs_d,
                                          const double *gammaMagSf_d, double *upper_d, double *diag_d)
 {
@@ -321,140 +142,6 @@ extern "C" int b200ldu_fv_convection_fill(b200ldu_addr *a, const double *weights
     a->ctx->launches += 2;
     KERNEL_CHECK();
     return B200LDU_OK;
-}
-
-// linear face value as interpolate(vf) forms it: w*(own - nei) + nei (surfaceInterpolationScheme.C:272-351), each operation
-// rounded on its own
-__device__ __forceinline__ double lin_face(double w, double own, double nei)
-{
-    return __dadd_rn(__dmul_rn(w, __dsub_rn(own, nei)), nei);
-}
-
-template <int NC>
-__global__ void interpolate_linear_kernel(int nFaces, const int *__restrict__ l, const int *__restrict__ u,
-                                          const double *__restrict__ w, const double *__restrict__ vf,
-                                          double *__restrict__ sf)
-{
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nFaces) return;
-    double ww = w[f];
-    int o = l[f], n = u[f];
-#pragma unroll
-    for (int k = 0; k < NC; k++)
-        sf[(size_t)f * NC + k] = lin_face(ww, vf[(size_t)o * NC + k], vf[(size_t)n * NC + k]);
-}
-
-extern "C" int b200ldu_fv_interpolate_linear(b200ldu_addr *a, int nComp, const double *w_d,
-                                             const double *vf_d, double *sf_d)
-{
-    if (!a || !w_d || !vf_d || !sf_d || (nComp != 1 && nComp != 3)) return B200LDU_EINVAL;
-    CUDA_TRY(cudaSetDevice(a->ctx->device));
-    if (a->nFaces == 0) return B200LDU_OK;
-    dim3 g((a->nFaces + 255) / 256), b(256);
-    if (nComp == 1)
-        interpolate_linear_kernel<1><<<g, b, 0, a->ctx->stream>>>(a->nFaces, a->d_l, a->d_u, w_d, vf_d, sf_d);
-    else
-        interpolate_linear_kernel<3><<<g, b, 0, a->ctx->stream>>>(a->nFaces, a->d_l, a->d_u, w_d, vf_d, sf_d);
-    a->ctx->launches++;
-    KERNEL_CHECK();
-    return B200LDU_OK;
-}
-
-// x[cell] += sum of coeffs over the cell's boundary faces (ascending boundary face)
-__global__ void add_boundary_kernel(int nCells, const int *__restrict__ bStart, const int *__restrict__ bFaces,
-                                    const double *__restrict__ coeffs, double *__restrict__ x)
-{
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nCells) return;
-    int s = bStart[c], e = bStart[c + 1];
-    if (s == e) return;
-    double acc = x[c];
-    for (int j = s; j < e; j++) acc = __dadd_rn(acc, coeffs[bFaces[j]]);
-    x[c] = acc;
-}
-
-static int add_boundary(b200ldu_addr *a, const double *coeffs, double *x)
-{
-    if (!a || !coeffs || !x) return B200LDU_EINVAL;
-    if (!a->nBFaces) return B200LDU_OK;
-    CUDA_TRY(cudaSetDevice(a->ctx->device));
-    add_boundary_kernel<<<(a->nCells + 255) / 256, 256, 0, a->ctx->stream>>>(a->nCells, a->d_bCellStart,
-                                                                             a->d_bCellFaces, coeffs, x);
-    a->ctx->launches++;
-    KERNEL_CHECK();
-    return B200LDU_OK;
-}
-
-extern "C" int b200ldu_fv_add_boundary_diag(b200ldu_addr *a, const double *internalCoeffs_d, double *diag_d)
-{
-    return add_boundary(a, internalCoeffs_d, diag_d);
-}
-
-extern "C" int b200ldu_fv_add_boundary_source(b200ldu_addr *a, const double *boundaryCoeffs_d, double *source_d)
-{
-    return add_boundary(a, boundaryCoeffs_d, source_d);
-}
-
-// ---------------------------------------------------------------------------
-// surface interpolation fused into the face sums, so the
-// F-sized interpolated face field (401 MB - 1.2 GB at 256^3) is never written or re-read.
-// gaussGrad::calcGrad = gradf(interpolate(vsf)) (gaussGrad.C:256-271 with the linear scheme,
-// surfaceInterpolationScheme.C:272-351): the face value w*(psi[own] - psi[nei]) + psi[nei] is
-// formed on the fly with the same rounded subtract, product and add as the unfused pipeline,
-// so the result equals b200ldu_fv_gauss_grad(b200ldu_fv_interpolate_linear(...)) bit for bit.
-// ---------------------------------------------------------------------------
-template <int NC>
-__global__ void grad_linear_kernel(int nCells, const int *__restrict__ ownerStart, const int *__restrict__ upper,
-                                   const int *__restrict__ losortStart, const int *__restrict__ losort,
-                                   const int *__restrict__ lower, const int *__restrict__ bStart,
-                                   const int *__restrict__ bFaces, const double *__restrict__ Sf,
-                                   const double *__restrict__ w, const double *__restrict__ vf,
-                                   const double *__restrict__ bSf, const double *__restrict__ bvf,
-                                   const double *__restrict__ V, double *__restrict__ out)
-{
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nCells) return;
-    double mine[NC];
-#pragma unroll
-    for (int j = 0; j < NC; j++) mine[j] = vf[(size_t)c * NC + j];
-    double acc[3 * NC];
-#pragma unroll
-    for (int k = 0; k < 3 * NC; k++) acc[k] = 0.0;
-    for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++) {
-        const int n = upper[f];
-        const double ww = w[f];
-        const double s[3] = {Sf[(size_t)f * 3], Sf[(size_t)f * 3 + 1], Sf[(size_t)f * 3 + 2]};
-#pragma unroll
-        for (int j = 0; j < NC; j++) {
-            const double fv = lin_face(ww, mine[j], vf[(size_t)n * NC + j]);
-#pragma unroll
-            for (int i = 0; i < 3; i++) acc[i * NC + j] = __dadd_rn(acc[i * NC + j], __dmul_rn(s[i], fv));
-        }
-    }
-    for (int q = losortStart[c]; q < losortStart[c + 1]; q++) {
-        const int f = losort[q], o = lower[f];
-        const double ww = w[f];
-        const double s[3] = {Sf[(size_t)f * 3], Sf[(size_t)f * 3 + 1], Sf[(size_t)f * 3 + 2]};
-#pragma unroll
-        for (int j = 0; j < NC; j++) {
-            const double fv = lin_face(ww, vf[(size_t)o * NC + j], mine[j]);
-#pragma unroll
-            for (int i = 0; i < 3; i++) acc[i * NC + j] = __dsub_rn(acc[i * NC + j], __dmul_rn(s[i], fv));
-        }
-    }
-    if (bStart)
-        for (int q = bStart[c]; q < bStart[c + 1]; q++) {
-            const int bf = bFaces[q];
-            const double s[3] = {bSf[(size_t)bf * 3], bSf[(size_t)bf * 3 + 1], bSf[(size_t)bf * 3 + 2]};
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-                for (int j = 0; j < NC; j++)
-                    acc[i * NC + j] = __dadd_rn(acc[i * NC + j], __dmul_rn(s[i], bvf[(size_t)bf * NC + j]));
-        }
-    const double v = V[c];
-#pragma unroll
-    for (int k = 0; k < 3 * NC; k++) out[(size_t)c * 3 * NC + k] = __ddiv_rn(acc[k], v);
 }
 
 extern "C" int b200ldu_fv_grad_linear(b200ldu_addr *a, int nComp, const double *Sf_d, const double *w_d,

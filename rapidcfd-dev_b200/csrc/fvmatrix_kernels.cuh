@@ -125,16 +125,50 @@ __global__ void H_kernel(int nCells, const int *__restrict__ ownerStart, const i
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
+    // load scheduling as in fv_kernels.cuh: everything known up front first, then the first batch of coefficients and indices
+    // together, then what the indices point at -- the sums keep the reference's order
+    constexpr int B = 3;
+    const int o0 = ownerStart[c], o1 = ownerStart[c + 1], n0 = losortStart[c], n1 = losortStart[c + 1];
+    int b0 = 0, b1 = 0, c0 = 0, c1 = 0;
+    if (L.bStart) b0 = L.bStart[c], b1 = L.bStart[c + 1];
+    if (L.cStart && pnf) c0 = L.cStart[c], c1 = L.cStart[c + 1];
+    const double v = V[c];
+    double src[NC];
+#pragma unroll
+    for (int k = 0; k < NC; k++) src[k] = source[(size_t)c * NC + k];
+    double oa[B], na[B];
+    int on[B], fi[B], no[B], bf0 = 0, pf0 = 0;
+#pragma unroll
+    for (int b = 0; b < B; b++)
+        if (o0 + b < o1) oa[b] = upper[o0 + b], on[b] = u[o0 + b];
+#pragma unroll
+    for (int b = 0; b < B; b++)
+        if (n0 + b < n1) fi[b] = losort[n0 + b];
+    if (b0 < b1) bf0 = L.bFaces[b0];
+    if (c0 < c1) pf0 = L.cFaces[c0];
+#pragma unroll
+    for (int b = 0; b < B; b++)
+        if (n0 + b < n1) na[b] = lower[fi[b]], no[b] = l[fi[b]];
     double acc[NC];
 #pragma unroll
     for (int k = 0; k < NC; k++) acc[k] = 0.0;
-    for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++) {
+#pragma unroll
+    for (int b = 0; b < B; b++)
+        if (o0 + b < o1)
+#pragma unroll
+            for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], -__dmul_rn(oa[b], psi[(size_t)on[b] * NC + k]));
+    for (int f = o0 + B; f < o1; f++) {
         const double a = upper[f];
         const int n = u[f];
 #pragma unroll
         for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], -__dmul_rn(a, psi[(size_t)n * NC + k]));
     }
-    for (int q = losortStart[c]; q < losortStart[c + 1]; q++) {
+#pragma unroll
+    for (int b = 0; b < B; b++)
+        if (n0 + b < n1)
+#pragma unroll
+            for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], -__dmul_rn(na[b], psi[(size_t)no[b] * NC + k]));
+    for (int q = n0 + B; q < n1; q++) {
         const int f = losort[q];
         const double a = lower[f];
         const int o = l[f];
@@ -142,21 +176,18 @@ __global__ void H_kernel(int nCells, const int *__restrict__ ownerStart, const i
         for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], -__dmul_rn(a, psi[(size_t)o * NC + k]));
     }
 #pragma unroll
-    for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], source[(size_t)c * NC + k]);
-    if (L.bStart)
-        for (int j = L.bStart[c]; j < L.bStart[c + 1]; j++) {
-            const int bf = L.bFaces[j];
+    for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], src[k]);
+    for (int j = b0; j < b1; j++) {
+        const int bf = j == b0 ? bf0 : L.bFaces[j];
 #pragma unroll
-            for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], bc[(size_t)bf * NC + k]);
-        }
-    if (L.cStart && pnf)
-        for (int j = L.cStart[c]; j < L.cStart[c + 1]; j++) {
-            const int pf = L.cFaces[j];
-            const double b = couBou[pf];
+        for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], bc[(size_t)bf * NC + k]);
+    }
+    for (int j = c0; j < c1; j++) {
+        const int pf = j == c0 ? pf0 : L.cFaces[j];
+        const double b = couBou[pf];
 #pragma unroll
-            for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], __dmul_rn(b, pnf[(size_t)pf * NC + k]));
-        }
-    const double v = V[c];
+        for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], __dmul_rn(b, pnf[(size_t)pf * NC + k]));
+    }
 #pragma unroll
     for (int k = 0; k < NC; k++) out[(size_t)c * NC + k] = __ddiv_rn(acc[k], v);
 }
@@ -222,10 +253,34 @@ __global__ void relax_kernel(int nCells, const int *__restrict__ ownerStart, con
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
+    // load scheduling as in fv_kernels.cuh: ranges, diagonal, psi and source first; then the owner coefficients with the losort
+    // indices; then the neighbour coefficients
+    constexpr int B = 3;
+    const int o0 = ownerStart[c], o1 = ownerStart[c + 1], n0 = losortStart[c], n1 = losortStart[c + 1];
     const double D0 = diag[c];
+    double ps[NC], src[NC];
+#pragma unroll
+    for (int k = 0; k < NC; k++) ps[k] = psi[(size_t)c * NC + k], src[k] = source[(size_t)c * NC + k];
+    double ou[B], nl[B];
+    int fi[B];
+#pragma unroll
+    for (int b = 0; b < B; b++)
+        if (o0 + b < o1) ou[b] = upper[o0 + b];
+#pragma unroll
+    for (int b = 0; b < B; b++)
+        if (n0 + b < n1) fi[b] = losort[n0 + b];
+#pragma unroll
+    for (int b = 0; b < B; b++)
+        if (n0 + b < n1) nl[b] = lower[fi[b]];
     double sumOff = 0.0;
-    for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++) sumOff = __dadd_rn(sumOff, fabs(upper[f]));
-    for (int q = losortStart[c]; q < losortStart[c + 1]; q++) sumOff = __dadd_rn(sumOff, fabs(lower[losort[q]]));
+#pragma unroll
+    for (int b = 0; b < B; b++)
+        if (o0 + b < o1) sumOff = __dadd_rn(sumOff, fabs(ou[b]));
+    for (int f = o0 + B; f < o1; f++) sumOff = __dadd_rn(sumOff, fabs(upper[f]));
+#pragma unroll
+    for (int b = 0; b < B; b++)
+        if (n0 + b < n1) sumOff = __dadd_rn(sumOff, fabs(nl[b]));
+    for (int q = n0 + B; q < n1; q++) sumOff = __dadd_rn(sumOff, fabs(lower[losort[q]]));
     double D = D0;
     if (L.bStart)
         for (int j = L.bStart[c]; j < L.bStart[c + 1]; j++) {
@@ -256,8 +311,7 @@ __global__ void relax_kernel(int nCells, const int *__restrict__ ownerStart, con
     diag[c] = D;
     const double dD = __dsub_rn(D, D0);
 #pragma unroll
-    for (int k = 0; k < NC; k++)
-        source[(size_t)c * NC + k] = __dadd_rn(source[(size_t)c * NC + k], __dmul_rn(dD, psi[(size_t)c * NC + k]));
+    for (int k = 0; k < NC; k++) source[(size_t)c * NC + k] = __dadd_rn(src[k], __dmul_rn(dD, ps[k]));
 }
 
 __global__ void set_reference_kernel(int cell, int nc, double v0, double v1, double v2, double *diag, double *source)

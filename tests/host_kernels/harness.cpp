@@ -27,6 +27,7 @@ using std::fmin;
 #include "fieldops_kernels.cuh"
 #include "fvmatrix_kernels.cuh"
 #include "mules_kernels.cuh"
+#include "fv_kernels.cuh"
 
 template <class K, class... A> static void launch(long long nThreads, int block, K k, A... args)
 {
@@ -183,5 +184,44 @@ void hk_mules_limiter(const HostCase *h, int nIter, double rDeltaT, const double
         launch((long long)nF + nB, 256, mules_face_lambda_kernel, nF, nB, nCoupled, corr, h->l, h->u, h->bFaceCells, phiCorr, phiCorrB, phiBDB,
                lambdam, lambdap, lambda, lambdaB);
     }
+}
+
+/* csrc/fv.cu: the cell-parallel face sums (fv_kernels.cuh) */
+void hk_surface_integrate(const HostCase *h, int nc, const double *ssf, const double *bssf, const double *V, double *out, int divideByV,
+                          int neiSign)
+{
+    const int *bs = h->nB ? h->bStart : nullptr;
+    if (nc == 1)
+        launch(h->nCells, 128, fvk::surface_integrate_kernel<1>, h->nCells, h->ownerStart, h->losortStart, h->losort, bs, h->bFaces, ssf,
+               bssf, V, out, divideByV, neiSign);
+    else
+        launch(h->nCells, 128, fvk::surface_integrate_kernel<3>, h->nCells, h->ownerStart, h->losortStart, h->losort, bs, h->bFaces, ssf,
+               bssf, V, out, divideByV, neiSign);
+}
+void hk_gauss_grad(const HostCase *h, int nc, const double *Sf, const double *ssf, const double *bSf, const double *bssf, const double *V,
+                   double *out)
+{
+    const int *bs = h->nB ? h->bStart : nullptr;
+    if (nc == 1)
+        launch(h->nCells, 128, fvk::gauss_grad_kernel<1>, h->nCells, h->ownerStart, h->losortStart, h->losort, bs, h->bFaces, Sf, ssf, bSf,
+               bssf, V, out);
+    else
+        launch(h->nCells, 128, fvk::gauss_grad_kernel<3>, h->nCells, h->ownerStart, h->losortStart, h->losort, bs, h->bFaces, Sf, ssf, bSf,
+               bssf, V, out);
+}
+void hk_grad_linear(const HostCase *h, int nc, const double *Sf, const double *w, const double *vf, const double *bSf, const double *bvf,
+                    const double *V, double *out)
+{
+    const int *bs = h->nB ? h->bStart : nullptr;
+    if (nc == 1)
+        launch(h->nCells, 128, fvk::grad_linear_kernel<1>, h->nCells, h->ownerStart, h->u, h->losortStart, h->losort, h->l, bs, h->bFaces,
+               Sf, w, vf, bSf, bvf, V, out);
+    else
+        launch(h->nCells, 128, fvk::grad_linear_kernel<3>, h->nCells, h->ownerStart, h->u, h->losortStart, h->losort, h->l, bs, h->bFaces,
+               Sf, w, vf, bSf, bvf, V, out);
+}
+void hk_neg_sum_diag(const HostCase *h, const double *upper, const double *lower, double *diag)
+{
+    launch(h->nCells, 128, fvk::neg_sum_diag_kernel, h->nCells, h->ownerStart, h->losortStart, h->losort, upper, lower, diag);
 }
 }

@@ -27,7 +27,7 @@ class HostCase(C.Structure):
 
 @pytest.fixture(scope="module")
 def hk():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("fvmatrix_kernels.cuh", "fieldops_kernels.cuh", "mules_kernels.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("fvmatrix_kernels.cuh", "fieldops_kernels.cuh", "mules_kernels.cuh", "fv_kernels.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-Wall",
