@@ -144,6 +144,76 @@ extern "C" int b200ldu_fv_convection_fill(b200ldu_addr *a, const double *weights
     return B200LDU_OK;
 }
 
+template <int NC>
+__global__ void interpolate_linear_kernel(int nFaces, const int *__restrict__ l, const int *__restrict__ u,
+                                          const double *__restrict__ w, const double *__restrict__ vf,
+                                          double *__restrict__ sf)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nFaces) return;
+    double ww = w[f];
+    int o = l[f], n = u[f];
+#pragma unroll
+    for (int k = 0; k < NC; k++)
+        sf[(size_t)f * NC + k] = lin_face(ww, vf[(size_t)o * NC + k], vf[(size_t)n * NC + k]);
+}
+
+extern "C" int b200ldu_fv_interpolate_linear(b200ldu_addr *a, int nComp, const double *w_d,
+                                             const double *vf_d, double *sf_d)
+{
+    if (!a || !w_d || !vf_d || !sf_d || (nComp != 1 && nComp != 3)) return B200LDU_EINVAL;
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    if (a->nFaces == 0) return B200LDU_OK;
+    dim3 g((a->nFaces + 255) / 256), b(256);
+    if (nComp == 1)
+        interpolate_linear_kernel<1><<<g, b, 0, a->ctx->stream>>>(a->nFaces, a->d_l, a->d_u, w_d, vf_d, sf_d);
+    else
+        interpolate_linear_kernel<3><<<g, b, 0, a->ctx->stream>>>(a->nFaces, a->d_l, a->d_u, w_d, vf_d, sf_d);
+    a->ctx->launches++;
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}
+
+// x[cell] += sum of coeffs over the cell's boundary faces (ascending boundary face)
+__global__ void add_boundary_kernel(int nCells, const int *__restrict__ bStart, const int *__restrict__ bFaces,
+                                    const double *__restrict__ coeffs, double *__restrict__ x)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    int s = bStart[c], e = bStart[c + 1];
+    if (s == e) return;
+    double acc = x[c];
+    for (int j = s; j < e; j++) acc = __dadd_rn(acc, coeffs[bFaces[j]]);
+    x[c] = acc;
+}
+
+static int add_boundary(b200ldu_addr *a, const double *coeffs, double *x)
+{
+    if (!a || !coeffs || !x) return B200LDU_EINVAL;
+    if (!a->nBFaces) return B200LDU_OK;
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    add_boundary_kernel<<<(a->nCells + 255) / 256, 256, 0, a->ctx->stream>>>(a->nCells, a->d_bCellStart,
+                                                                             a->d_bCellFaces, coeffs, x);
+    a->ctx->launches++;
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}
+
+extern "C" int b200ldu_fv_add_boundary_diag(b200ldu_addr *a, const double *internalCoeffs_d, double *diag_d)
+{
+    return add_boundary(a, internalCoeffs_d, diag_d);
+}
+
+extern "C" int b200ldu_fv_add_boundary_source(b200ldu_addr *a, const double *boundaryCoeffs_d, double *source_d)
+{
+    return add_boundary(a, boundaryCoeffs_d, source_d);
+}
+
+
+// ---------------------------------------------------------------------------
+// surface interpolation fused into the face sums (grad_linear_kernel, fv_kernels.cuh), so the
+// F-sized interpolated face field (401 MB - 1.2 GB at 256^3) is never written or re-read.
+// ---------------------------------------------------------------------------
 extern "C" int b200ldu_fv_grad_linear(b200ldu_addr *a, int nComp, const double *Sf_d, const double *w_d,
                                       const double *vf_d, const double *bSf_d, const double *bvf_d,
                                       const double *V_d, double *out_d)
