@@ -11,6 +11,10 @@
 // thread can know up front is loaded first (the three row ranges, V, the cell's own value), then the first batch of owner
 // values TOGETHER with the first batch of losort indices and the first boundary face index, then the values those indices
 // point at: three levels.  Cells with more than FV_BATCH faces on a side continue with plain loops, in the same order.
+// Measured at 256^3 (profiles/r02_kernel_table_n256.txt against ..._before_hoisting.txt): surfaceIntegrate scalar 258 -> 231 us,
+// gaussGrad scalar 562 -> 533 us, negSumDiag fills 385 -> 355 / 468 -> 443 us, fvMatrix::H 422 -> 359 / 617 -> 518 us, relax
+// 406 -> 379 / 445 -> 427 us.  Where the scheme needs ~64 registers it loses more occupancy than the shorter chain gains
+// (surfaceIntegrate of a vector field, the fused interpolate + gradient, the MULES sweeps): those keep their plain loops.
 #ifndef B200LDU_FV_KERNELS_CUH
 #define B200LDU_FV_KERNELS_CUH
 #include <cstddef>
@@ -36,6 +40,10 @@ __global__ void surface_integrate_kernel(int nCells, const int *__restrict__ own
     int b0 = 0, b1 = 0;
     if (bStart) b0 = bStart[c], b1 = bStart[c + 1];
     const double vol = divideByV ? V[c] : 1.0;
+    double acc[NC];
+#pragma unroll
+    for (int k = 0; k < NC; k++) acc[k] = 0.0;
+    if constexpr (NC == 1) {
     // level 2: first batch of owner values, of losort indices, the first boundary face
     double ov[FV_BATCH][NC];
     int fi[FV_BATCH], bf0 = 0;
@@ -59,9 +67,6 @@ __global__ void surface_integrate_kernel(int nCells, const int *__restrict__ own
 #pragma unroll
         for (int k = 0; k < NC; k++) bv0[k] = bssf[(size_t)bf0 * NC + k];
     // sums in face order
-    double acc[NC];
-#pragma unroll
-    for (int k = 0; k < NC; k++) acc[k] = 0.0;
 #pragma unroll
     for (int b = 0; b < FV_BATCH; b++)
         if (o0 + b < o1)
@@ -87,6 +92,26 @@ __global__ void surface_integrate_kernel(int nCells, const int *__restrict__ own
 #pragma unroll
         for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], bv0[k]);
         for (int j = b0 + 1; j < b1; j++) {
+            const int bf = bFaces[j];
+#pragma unroll
+            for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], bssf[(size_t)bf * NC + k]);
+        }
+    }
+    } else {
+        // vector fields: holding two batches of three-component values costs the occupancy more than the shorter chain gains
+        // (measured: 484 us against 453 us at 256^3), so only the row ranges are loaded ahead
+        for (int f = o0; f < o1; f++)
+#pragma unroll
+            for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], ssf[(size_t)f * NC + k]);
+        for (int j = n0; j < n1; j++) {
+            const int f = losort[j];
+#pragma unroll
+            for (int k = 0; k < NC; k++) {
+                const double v = ssf[(size_t)f * NC + k];
+                acc[k] = neiSign < 0 ? __dsub_rn(acc[k], v) : __dadd_rn(acc[k], v);
+            }
+        }
+        for (int j = b0; j < b1; j++) {
             const int bf = bFaces[j];
 #pragma unroll
             for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], bssf[(size_t)bf * NC + k]);
@@ -236,31 +261,16 @@ __global__ void grad_linear_kernel(int nCells, const int *__restrict__ ownerStar
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
-    // level 1
-    const int o0 = ownerStart[c], o1 = ownerStart[c + 1], n0 = losortStart[c], n1 = losortStart[c + 1];
-    int b0 = 0, b1 = 0;
-    if (bStart) b0 = bStart[c], b1 = bStart[c + 1];
-    const double vol = V[c];
+    // plain loops: prefetching the first batch of indices (the scheme of the kernels above) raised this kernel to 64 registers
+    // and made it slower (791 us against 664 us at 256^3, scalar field)
     double mine[NC];
 #pragma unroll
     for (int j = 0; j < NC; j++) mine[j] = vf[(size_t)c * NC + j];
-    // level 2: the cells across the first owner faces, the first neighbour faces, the first boundary face
-    int on[FV_BATCH], fi[FV_BATCH], no[FV_BATCH], bf0 = 0;
-#pragma unroll
-    for (int b = 0; b < FV_BATCH; b++)
-        if (o0 + b < o1) on[b] = upper[o0 + b];
-#pragma unroll
-    for (int b = 0; b < FV_BATCH; b++)
-        if (n0 + b < n1) fi[b] = losort[n0 + b];
-    if (b0 < b1) bf0 = bFaces[b0];
-    // level 3: the owners of the first neighbour faces
-#pragma unroll
-    for (int b = 0; b < FV_BATCH; b++)
-        if (n0 + b < n1) no[b] = lower[fi[b]];
     double acc[3 * NC];
 #pragma unroll
     for (int k = 0; k < 3 * NC; k++) acc[k] = 0.0;
-    auto ownerFace = [&](int f, int n) {
+    for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++) {
+        const int n = upper[f];
         const double ww = w[f];
         const double s[3] = {Sf[(size_t)f * 3], Sf[(size_t)f * 3 + 1], Sf[(size_t)f * 3 + 2]};
 #pragma unroll
@@ -269,8 +279,9 @@ __global__ void grad_linear_kernel(int nCells, const int *__restrict__ ownerStar
 #pragma unroll
             for (int i = 0; i < 3; i++) acc[i * NC + j] = __dadd_rn(acc[i * NC + j], __dmul_rn(s[i], fv));
         }
-    };
-    auto neighbourFace = [&](int f, int o) {
+    }
+    for (int q = losortStart[c]; q < losortStart[c + 1]; q++) {
+        const int f = losort[q], o = lower[f];
         const double ww = w[f];
         const double s[3] = {Sf[(size_t)f * 3], Sf[(size_t)f * 3 + 1], Sf[(size_t)f * 3 + 2]};
 #pragma unroll
@@ -279,29 +290,20 @@ __global__ void grad_linear_kernel(int nCells, const int *__restrict__ ownerStar
 #pragma unroll
             for (int i = 0; i < 3; i++) acc[i * NC + j] = __dsub_rn(acc[i * NC + j], __dmul_rn(s[i], fv));
         }
-    };
-#pragma unroll
-    for (int b = 0; b < FV_BATCH; b++)
-        if (o0 + b < o1) ownerFace(o0 + b, on[b]);
-    for (int f = o0 + FV_BATCH; f < o1; f++) ownerFace(f, upper[f]);
-#pragma unroll
-    for (int b = 0; b < FV_BATCH; b++)
-        if (n0 + b < n1) neighbourFace(fi[b], no[b]);
-    for (int q = n0 + FV_BATCH; q < n1; q++) {
-        const int f = losort[q];
-        neighbourFace(f, lower[f]);
     }
-    for (int q = b0; q < b1; q++) {
-        const int bf = q == b0 ? bf0 : bFaces[q];
-        const double s[3] = {bSf[(size_t)bf * 3], bSf[(size_t)bf * 3 + 1], bSf[(size_t)bf * 3 + 2]};
+    if (bStart)
+        for (int q = bStart[c]; q < bStart[c + 1]; q++) {
+            const int bf = bFaces[q];
+            const double s[3] = {bSf[(size_t)bf * 3], bSf[(size_t)bf * 3 + 1], bSf[(size_t)bf * 3 + 2]};
 #pragma unroll
-        for (int i = 0; i < 3; i++)
+            for (int i = 0; i < 3; i++)
 #pragma unroll
-            for (int j = 0; j < NC; j++)
-                acc[i * NC + j] = __dadd_rn(acc[i * NC + j], __dmul_rn(s[i], bvf[(size_t)bf * NC + j]));
-    }
+                for (int j = 0; j < NC; j++)
+                    acc[i * NC + j] = __dadd_rn(acc[i * NC + j], __dmul_rn(s[i], bvf[(size_t)bf * NC + j]));
+        }
+    const double v = V[c];
 #pragma unroll
-    for (int k = 0; k < 3 * NC; k++) out[(size_t)c * 3 * NC + k] = __ddiv_rn(acc[k], vol);
+    for (int k = 0; k < 3 * NC; k++) out[(size_t)c * 3 * NC + k] = __ddiv_rn(acc[k], v);
 }
 } // namespace
 } // namespace fvk

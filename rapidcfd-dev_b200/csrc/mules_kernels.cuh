@@ -41,28 +41,10 @@ __global__ void mules_bounds_kernel(int nCells, const int *__restrict__ ownerSta
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
-    // load scheduling as in fv_kernels.cuh: the row ranges and the cell's own scalars first, then the first batch of face indices,
-    // then what they point at; the sums keep the reference's order
-    constexpr int B = 3;
-    const int o0 = ownerStart[c], o1 = ownerStart[c + 1], n0 = losortStart[c], n1 = losortStart[c + 1];
-    int b0 = 0, b1 = 0;
-    if (bStart) b0 = bStart[c], b1 = bStart[c + 1];
-    const double v = V[c], psiC = psi[c], psi0C = psi0[c];
-    const double rhoC = rho ? rho[c] : 1.0, rho0C = rho0 ? rho0[c] : 1.0, SpC = Sp ? Sp[c] : 0.0, SuC = Su ? Su[c] : 0.0;
-    int on[B], fi[B], no[B];
-#pragma unroll
-    for (int b = 0; b < B; b++)
-        if (o0 + b < o1) on[b] = upper[o0 + b];
-#pragma unroll
-    for (int b = 0; b < B; b++)
-        if (n0 + b < n1) fi[b] = losort[n0 + b];
-#pragma unroll
-    for (int b = 0; b < B; b++)
-        if (n0 + b < n1) no[b] = lower[fi[b]];
     double pMax = psiMinG, pMin = psiMaxG; // the search for the maximum starts from the global minimum (:445-446)
     double sumBD = 0, sp = MULES_VSMALL, sm = MULES_VSMALL;
-    auto ownerFace = [&](int f, int n) {
-        const double pn = psi[n];
+    for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++) {
+        const double pn = psi[upper[f]];
         pMax = fmax(pMax, pn);
         pMin = fmin(pMin, pn);
         if (!corr) sumBD = __dadd_rn(sumBD, phiBD[f]);
@@ -71,9 +53,10 @@ __global__ void mules_bounds_kernel(int nCells, const int *__restrict__ ownerSta
             sp = __dadd_rn(sp, pc);
         else
             sm = __dsub_rn(sm, pc);
-    };
-    auto neighbourFace = [&](int f, int o) {
-        const double pn = psi[o];
+    }
+    for (int k = losortStart[c]; k < losortStart[c + 1]; k++) {
+        const int f = losort[k];
+        const double pn = psi[lower[f]];
         pMax = fmax(pMax, pn);
         pMin = fmin(pMin, pn);
         if (!corr) sumBD = __dsub_rn(sumBD, phiBD[f]);
@@ -82,29 +65,19 @@ __global__ void mules_bounds_kernel(int nCells, const int *__restrict__ ownerSta
             sm = __dadd_rn(sm, pc);
         else
             sp = __dsub_rn(sp, pc);
-    };
-#pragma unroll
-    for (int b = 0; b < B; b++)
-        if (o0 + b < o1) ownerFace(o0 + b, on[b]);
-    for (int f = o0 + B; f < o1; f++) ownerFace(f, upper[f]);
-#pragma unroll
-    for (int b = 0; b < B; b++)
-        if (n0 + b < n1) neighbourFace(fi[b], no[b]);
-    for (int k = n0 + B; k < n1; k++) {
-        const int f = losort[k];
-        neighbourFace(f, lower[f]);
     }
-    for (int k = b0; k < b1; k++) {
-        const int bf = bFaces[k];
-        pMax = fmax(pMax, psiB[bf]);
-        pMin = fmin(pMin, psiB[bf]);
-        if (!corr) sumBD = __dadd_rn(sumBD, phiBDB[bf]);
-        const double pc = phiCorrB[bf];
-        if (pc > 0.0)
-            sp = __dadd_rn(sp, pc);
-        else
-            sm = __dsub_rn(sm, pc);
-    }
+    if (bStart)
+        for (int k = bStart[c]; k < bStart[c + 1]; k++) {
+            const int bf = bFaces[k];
+            pMax = fmax(pMax, psiB[bf]);
+            pMin = fmin(pMin, psiB[bf]);
+            if (!corr) sumBD = __dadd_rn(sumBD, phiBDB[bf]);
+            const double pc = phiCorrB[bf];
+            if (pc > 0.0)
+                sp = __dadd_rn(sp, pc);
+            else
+                sm = __dsub_rn(sm, pc);
+        }
     if (corr) { // limiterCorr: the extrema widened by extremaCoeff*(psiMax - psiMin) (CMULESTemplates.C:497-498)
         pMax = __dadd_rn(pMax, extrema);
         pMin = __dsub_rn(pMin, extrema);
@@ -112,14 +85,15 @@ __global__ void mules_bounds_kernel(int nCells, const int *__restrict__ ownerSta
     pMax = fmin(pMax, psiMaxG);
     pMin = fmax(pMin, psiMinG);
     // (rho*rDeltaT - Sp); limiter: (rho0*rDeltaT)*psi0, limiterCorr: (rho*psi)*rDeltaT -- one rounding per written operator
-    double a = rho ? __dmul_rn(rhoC, rDeltaT) : rDeltaT;
-    if (Sp) a = __dsub_rn(a, SpC);
-    const double b = corr ? __dmul_rn(rho ? __dmul_rn(rhoC, psiC) : psiC, rDeltaT)
-                          : __dmul_rn(rho0 ? __dmul_rn(rho0C, rDeltaT) : rDeltaT, psi0C);
+    double a = rho ? __dmul_rn(rho[c], rDeltaT) : rDeltaT;
+    if (Sp) a = __dsub_rn(a, Sp[c]);
+    const double b = corr ? __dmul_rn(rho ? __dmul_rn(rho[c], psi[c]) : psi[c], rDeltaT)
+                          : __dmul_rn(rho0 ? __dmul_rn(rho0[c], rDeltaT) : rDeltaT, psi0[c]);
+    const double v = V[c];
     double up = __dmul_rn(a, pMax);
-    if (Su) up = __dsub_rn(up, SuC);
+    if (Su) up = __dsub_rn(up, Su[c]);
     up = __dsub_rn(up, b);
-    double lo = __dsub_rn(Su ? SuC : 0.0, __dmul_rn(a, pMin));
+    double lo = __dsub_rn(Su ? Su[c] : 0.0, __dmul_rn(a, pMin));
     lo = __dadd_rn(lo, b);
     if (corr) {
         psiMaxn[c] = __dmul_rn(v, up);
@@ -146,54 +120,33 @@ __global__ void mules_cell_lambda_kernel(int nCells, const int *__restrict__ own
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
-    constexpr int B = 3;
-    const int o0 = ownerStart[c], o1 = ownerStart[c + 1], n0 = losortStart[c], n1 = losortStart[c + 1];
-    int b0 = 0, b1 = 0;
-    if (bStart) b0 = bStart[c], b1 = bStart[c + 1];
-    const double maxn = psiMaxn[c], minn = psiMinn[c], sPp = sumPhip[c], sPm = mSumPhim[c];
-    double ol[B], oc[B], nl[B], nc_[B];
-    int fi[B];
-#pragma unroll
-    for (int b = 0; b < B; b++)
-        if (o0 + b < o1) ol[b] = lambda[o0 + b], oc[b] = phiCorr[o0 + b];
-#pragma unroll
-    for (int b = 0; b < B; b++)
-        if (n0 + b < n1) fi[b] = losort[n0 + b];
-#pragma unroll
-    for (int b = 0; b < B; b++)
-        if (n0 + b < n1) nl[b] = lambda[fi[b]], nc_[b] = phiCorr[fi[b]];
     double slp = 0.0, mslm = 0.0;
-    auto ownerLike = [&](double l, double pc) {
-        const double lp = __dmul_rn(l, pc);
+    for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++) {
+        const double lp = __dmul_rn(lambda[f], phiCorr[f]);
         if (lp > 0.0)
             slp = __dadd_rn(slp, lp);
         else
             mslm = __dsub_rn(mslm, lp);
-    };
-    auto neighbourLike = [&](double l, double pc) {
-        const double lp = __dmul_rn(l, pc);
+    }
+    for (int k = losortStart[c]; k < losortStart[c + 1]; k++) {
+        const int f = losort[k];
+        const double lp = __dmul_rn(lambda[f], phiCorr[f]);
         if (lp > 0.0)
             mslm = __dadd_rn(mslm, lp);
         else
             slp = __dsub_rn(slp, lp);
-    };
-#pragma unroll
-    for (int b = 0; b < B; b++)
-        if (o0 + b < o1) ownerLike(ol[b], oc[b]);
-    for (int f = o0 + B; f < o1; f++) ownerLike(lambda[f], phiCorr[f]);
-#pragma unroll
-    for (int b = 0; b < B; b++)
-        if (n0 + b < n1) neighbourLike(nl[b], nc_[b]);
-    for (int k = n0 + B; k < n1; k++) {
-        const int f = losort[k];
-        neighbourLike(lambda[f], phiCorr[f]);
     }
-    for (int k = b0; k < b1; k++) {
-        const int bf = bFaces[k];
-        ownerLike(lambdaB[bf], phiCorrB[bf]);
-    }
-    lambdam[c] = fmax(fmin(__ddiv_rn(__dadd_rn(slp, maxn), __dsub_rn(sPm, MULES_SMALL)), 1.0), 0.0);
-    lambdap[c] = fmax(fmin(__ddiv_rn(__dadd_rn(mslm, minn), __dadd_rn(sPp, MULES_SMALL)), 1.0), 0.0);
+    if (bStart)
+        for (int k = bStart[c]; k < bStart[c + 1]; k++) {
+            const int bf = bFaces[k];
+            const double lp = __dmul_rn(lambdaB[bf], phiCorrB[bf]);
+            if (lp > 0.0)
+                slp = __dadd_rn(slp, lp);
+            else
+                mslm = __dsub_rn(mslm, lp);
+        }
+    lambdam[c] = fmax(fmin(__ddiv_rn(__dadd_rn(slp, psiMaxn[c]), __dsub_rn(mSumPhim[c], MULES_SMALL)), 1.0), 0.0);
+    lambdap[c] = fmax(fmin(__ddiv_rn(__dadd_rn(mslm, psiMinn[c]), __dadd_rn(sumPhip[c], MULES_SMALL)), 1.0), 0.0);
 }
 
 // Step 3: face limiters from the cell limiters (lambdaIfMULESFunctor; boundary: patchLambdaPfMULESFunctor, outflow
