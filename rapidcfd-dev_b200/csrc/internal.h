@@ -191,9 +191,6 @@ struct b200ldu_matrix {
     // solver workspace (allocated once, reused across solves -- PCGCache.H:9-58)
     std::vector<double *> work;
     double *d_partials = nullptr; // reduction partials
-    double *d_cpart = nullptr;    // persistent PCG: per-CTA partial sums [2][grid][2]
-    size_t cpartLen = 0;
-    unsigned *d_bar = nullptr;    // persistent PCG: grid barrier {arrivals, generation}
     void *d_scal = nullptr;       // SolverScalars
     double *d_hist = nullptr;     // device residual history
     double *d_sendBuf = nullptr;  // packed psi at coupled-patch face cells

@@ -325,7 +325,7 @@ extern "C" int b200ldu_matrix_destroy(b200ldu_matrix *m)
     cudaStreamSynchronize(m->a->ctx->stream);
     if (m->d_valT && m->d_valT != m->d_val) cudaFree(m->d_valT);
     void *ptrs[] = {m->d_val, m->d_diag, m->d_rD, m->d_partials, m->d_scal, m->d_hist, m->d_sendBuf,
-                    m->own[0], m->own[1], m->own[2], m->own[3], m->own[4], m->d_cpart, m->d_bar};
+                    m->own[0], m->own[1], m->own[2], m->own[3], m->own[4]};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (double *p : m->work)
