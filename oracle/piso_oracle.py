@@ -91,9 +91,10 @@ class Cavity:
 
     # ---- one time step: icoFoam.C:55-103 --------------------------------------------------------------
     def step(self, nCorr=2, nNonOrthCorr=0, UControls=None, pControls=None, momentumPredictor=True,
-             USolver=("PBiCG", "DILU"), pSolver=("PCG", "DIC"), gamg=None):
+             USolver=("PBiCG", "DILU"), pSolver=("PCG", "DIC"), gamg=None, divScheme="linear"):
         """USolver / pSolver: (solver, preconditioner or smoother) as fvSolution names them; gamg: the cached
-        agglomeration (orc.Gamg) when pSolver is GAMG"""
+        agglomeration (orc.Gamg) when pSolver is GAMG; divScheme "linear" | "upwind": the weights of fvm::div(phi, U)
+        (upwind.H:120-123 pos(faceFlux), on the coupled patches too)"""
         orc = self.orc
         fvm = lambda nc, diag, upper, lower, source, psi, ic, bc, ci, cb: fo.FvMatrix(
             orc, self.addr, nc, diag, upper, lower, source, psi, self.V, self.bfc, ic, bc,
@@ -106,11 +107,13 @@ class Cavity:
         # fvm::div(phi, U): gaussConvectionScheme.C:76-115 (lower = -w*phi, upper = lower + phi, negSumDiag; fixedValue
         # patches: internalCoeffs = 0, boundaryCoeffs = -patchFlux*U_b; coupled: patchFlux*w and -patchFlux*(1 - w),
         # coupledFvPatchField.C:162-179)
-        cLower, cUpper, cDiag = orc.convection_fill(self.addr, self.w, self.phi)
+        wConv = np.where(self.phi >= 0, 1.0, 0.0) if divScheme == "upwind" else self.w
+        cwConv = np.where(self.cphi >= 0, 1.0, 0.0) if divScheme == "upwind" else self.cw
+        cLower, cUpper, cDiag = orc.convection_fill(self.addr, wConv, self.phi)
         cIc = self.bphi[:, None] * np.zeros((len(self.bfc), 3))
         cBc = (-self.bphi)[:, None] * self.Ub
-        cCi = self.cphi * self.cw
-        cCb = (-self.cphi) * (1.0 - self.cw)
+        cCi = self.cphi * cwConv
+        cCb = (-self.cphi) * (1.0 - cwConv)
         # fvm::laplacian(nu, U): gaussLaplacianSchemes.C:39-93, gaussLaplacianScheme.C:46-89 (coupled: pGamma*(-delta) and
         # -pGamma*delta, coupledFvPatchField.C:184-209)
         gammaMagSf = self.nu * self.magSf

@@ -25,7 +25,8 @@ import numpy as np
 # ---------------------------------------------------------------------------
 # tokenizer + dictionary
 # ---------------------------------------------------------------------------
-_TOKEN = re.compile(r'"(?:[^"\\]|\\.)*"|[{}()\[\];]|[^\s{}()\[\];"]+')
+_NUMBER = re.compile(r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eE][-+]?\d+)?")
+_ENDS = set(" \t\r\n\f\v{}()[];\"")
 
 
 def _strip_comments(text):
@@ -34,7 +35,45 @@ def _strip_comments(text):
 
 
 def tokenize(text):
-    return _TOKEN.findall(_strip_comments(text))
+    """Tokens as ISstream::read(token&) forms them (ISstream.C:140-420): punctuation, quoted strings, numbers, and words -- a word
+    runs to the next white space, quote, `;`, `{`, `}` or bracket and may CONTAIN balanced parentheses (`div(phi,U)`,
+    `div((nuEff*dev(T(grad(U)))))` are single keywords, ISstream::read(word&) :425-470); an unbalanced `)` ends it."""
+    s = _strip_comments(text)
+    out, i, n = [], 0, len(s)
+    while i < n:
+        c = s[i]
+        if c.isspace():
+            i += 1
+        elif c == '"':
+            j = i + 1
+            while j < n and s[j] != '"':
+                j += 2 if s[j] == "\\" else 1
+            out.append(s[i:j + 1])
+            i = j + 1
+        elif c in "{}()[];":
+            out.append(c)
+            i += 1
+        else:
+            m = _NUMBER.match(s, i)
+            if m and (m.end() == n or s[m.end()] in _ENDS):
+                out.append(m.group())
+                i = m.end()
+                continue
+            j, depth = i, 0
+            while j < n:
+                ch = s[j]
+                if ch == "(":
+                    depth += 1
+                elif ch == ")":
+                    if not depth:
+                        break
+                    depth -= 1
+                elif ch.isspace() or ch in '{}[];"':
+                    break
+                j += 1
+            out.append(s[i:j])
+            i = j
+    return out
 
 
 _INT = re.compile(r"[-+]?\d+")
@@ -248,6 +287,88 @@ def solver_controls(fvSolution, fieldName):
             v = sd.lookup(key)
             controls[fld] = _switch(v) if typ == "bool" else typ(v)
     return str(solver), str(second), controls
+
+
+class FvSchemes:
+    """system/fvSchemes as fvSchemes::read and the scheme look-ups interpret it (FV/finiteVolume/fvSchemes/fvSchemes.C:36-256,
+    :425-580): per kind a sub-dictionary with an optional `default`; a look-up returns the entry for the name (exact keyword, then
+    the quoted regular expressions, most recent first -- dictionary rules) and otherwise the default; `default none` means no
+    default, and a name without an entry is then the reference's FatalIOError "keyword ... is undefined in dictionary".
+    interpolationSchemes defaults to `linear` and snGradSchemes to `corrected` when the section is missing (:163-170, :207-214).
+    Schemes come back as token lists, e.g. ["Gauss", "limitedLinear", 1]."""
+    KINDS = ("ddtSchemes", "d2dt2Schemes", "interpolationSchemes", "divSchemes", "gradSchemes", "snGradSchemes", "laplacianSchemes")
+
+    def __init__(self, d):
+        self.sections, self.defaults = {}, {}
+        for kind in self.KINDS:
+            sec = d.subDict(kind) if d.found(kind) and isinstance(d.lookup(kind), FoamDict) else FoamDict(d, kind)
+            if kind in ("ddtSchemes", "d2dt2Schemes") and not d.found(kind):
+                sec.add("default", d.lookup("timeScheme") if d.found("timeScheme") else "none")   # the pre-1.6 keyword (:64-103)
+            if kind == "interpolationSchemes" and not d.found(kind) and not sec.found("default"):
+                sec.add("default", "linear")
+            if kind == "snGradSchemes" and not d.found(kind) and not sec.found("default"):
+                sec.add("default", "corrected")
+            self.sections[kind] = sec
+            dflt = self._tokens(sec.lookup("default")) if sec.found("default") else []
+            self.defaults[kind] = [] if dflt[:1] == ["none"] else dflt
+        self.flux = d.subDict("fluxRequired") if d.found("fluxRequired") else FoamDict(d, "fluxRequired")
+        self.defaultFlux = False
+        if self.flux.found("default") and self.flux.lookup("default") not in (None, "none"):
+            self.defaultFlux = bool(_switch(self.flux.lookup("default")))
+
+    @staticmethod
+    def _tokens(v):
+        return list(v) if isinstance(v, (list, tuple)) else [v]
+
+    def _scheme(self, kind, name):
+        sec, dflt = self.sections[kind], self.defaults[kind]
+        if sec.found(name) or not dflt:
+            if not sec.found(name):
+                raise KeyError(f"keyword {name} is undefined in dictionary \"{sec.path()}\"")
+            return self._tokens(sec.lookup(name))
+        return list(dflt)
+
+    def ddt(self, name):
+        return self._scheme("ddtSchemes", name)
+
+    def d2dt2(self, name):
+        return self._scheme("d2dt2Schemes", name)
+
+    def interpolation(self, name):
+        return self._scheme("interpolationSchemes", name)
+
+    def div(self, name):
+        return self._scheme("divSchemes", name)
+
+    def grad(self, name):
+        return self._scheme("gradSchemes", name)
+
+    def snGrad(self, name):
+        return self._scheme("snGradSchemes", name)
+
+    def laplacian(self, name):
+        return self._scheme("laplacianSchemes", name)
+
+    def fluxRequired(self, name):
+        return True if self.flux.found(name) else self.defaultFlux
+
+
+def convection_scheme(tokens):
+    """`Gauss <interpolation scheme> [k]` of a divSchemes entry -> (scheme word for b200ldu_fv_limiter, k); `bounded Gauss ...` keeps
+    the flag.  Unknown words answer like convectionScheme::New / surfaceInterpolationScheme::New: "Unknown ... scheme"."""
+    t = list(tokens)
+    bounded = t[:1] == ["bounded"]
+    if bounded:
+        t = t[1:]
+    if t[:1] != ["Gauss"]:
+        raise ValueError(f"Unknown convection type {t[0] if t else ''}\n\nValid convection types are :\n(Gauss bounded)")
+    if len(t) < 2:
+        raise ValueError("Discretisation scheme not specified")
+    name = str(t[1])
+    if name not in ("linear", "upwind", "limitedLinear", "vanLeer", "Minmod"):
+        raise ValueError(f"Unknown discretisation scheme {name}\n\nValid schemes are :\n(Minmod limitedLinear linear upwind vanLeer)")
+    k = float(t[2]) if name == "limitedLinear" and len(t) > 2 else 1.0
+    return name, k, bounded
 
 
 # ---------------------------------------------------------------------------

@@ -93,8 +93,10 @@ class IcoFoam:
         return v if self.allsum is None else [float(x) for x in self.allsum(np.array(v))]
 
     def step(self, nCorr=2, nNonOrthCorr=0, UControls=None, pControls=None, momentumPredictor=True,
-             USolver=("PBiCG", "DILU"), pSolver=("PCG", "DIC"), gamg=None):
-        """icoFoam.C:55-103; returns ({"U": [Perf x3], "p": [Perf per pressure solve]}, continuity errors).
+             USolver=("PBiCG", "DILU"), pSolver=("PCG", "DIC"), gamg=None, divScheme="linear"):
+        """divScheme: the interpolation scheme of `div(phi,U) Gauss <scheme>` in system/fvSchemes: "linear" or "upwind" (weights
+        pos(phi) on the internal and the processor faces, upwind.H:120-123).
+        icoFoam.C:55-103; returns ({"U": [Perf x3], "p": [Perf per pressure solve]}, continuity errors).
         USolver / pSolver: (solver, preconditioner or smoother) as system/fvSolution names them; gamg: the cached
         agglomeration (capi.GamgAgglomeration over self.addr) when pSolver is GAMG."""
         capi, o, a, cat, nC = self.capi, self.ops, self.addr, self.torch.cat, self.nC
@@ -104,7 +106,11 @@ class IcoFoam:
         ddtDiag = o.smul(rDeltaT, self.V)
         ddtSource = o.mul(o.smul(rDeltaT, U0), self.V, 3, 1)
         # fvm::div(phi, U)
-        cLower, cUpper, cDiag = capi.fv_convection_fill(a, self.w, self.phi)
+        if divScheme not in ("linear", "upwind"):
+            raise ValueError(f"Unknown discretisation scheme {divScheme}\n\nValid schemes are :\n(linear upwind)")
+        upwind = divScheme == "upwind"
+        wConv = capi.fv_limited_weights(self.ctx, self.phi) if upwind else self.w
+        cLower, cUpper, cDiag = capi.fv_convection_fill(a, wConv, self.phi)
         cBc = o.mul(o.neg(self.bphi), self.Ub, 1, 3)
         # fvm::laplacian(nu, U)
         lUpper, lDiag = capi.fv_laplacian_fill(a, self.delta, o.smul(self.nu, self.magSf))
@@ -120,8 +126,9 @@ class IcoFoam:
             # processor patches (coupledFvPatchField.C:162-209): convection patchFlux*w / -patchFlux*(1 - w), diffusion
             # pGamma*(-delta) / -pGamma*delta; the glue's boundary list carries zeros for these faces
             cGamma = o.smul(self.nu, self.cMagSf)
-            ci = o.sub(o.mul(self.cphi, self.cw), o.mul(cGamma, o.neg(self.cDelta)))
-            cb = o.sub(o.mul(o.neg(self.cphi), o.rsub(1.0, self.cw)), o.mul(o.neg(cGamma), self.cDelta))
+            cwConv = capi.fv_limited_weights(self.ctx, self.cphi) if upwind else self.cw
+            ci = o.sub(o.mul(self.cphi, cwConv), o.mul(cGamma, o.neg(self.cDelta)))
+            cb = o.sub(o.mul(o.neg(self.cphi), o.rsub(1.0, cwConv)), o.mul(o.neg(cGamma), self.cDelta))
             ic, bc = cat([ic, self.zeroC3]), cat([bc, self.zeroC3])
         self.matU.set(diag, upper, lower, cb, ci)
         pnfU = (lambda f: capi.fv_patch_neighbour_field(a, 3, f)) if nC else (lambda f: None)
@@ -386,8 +393,39 @@ def load_case(capi, ctx, torch, caseDir, rank=None, allsum=None):
                nNonOrthCorr=int(piso.lookupOrDefault("nNonOrthogonalCorrectors", 0)),
                momentumPredictor=bool(ff._switch(piso.lookupOrDefault("momentumPredictor", "yes"))),
                USolver=(us, up_), UControls=uc, pSolver=(ps_, pp), pControls=pc, patches=pm.patches, nInternalFaces=nI,
-               Ufile=Ufile, pfile=pfile, polyMesh=pm, geometry=geo, base=base)
+               Ufile=Ufile, pfile=pfile, polyMesh=pm, geometry=geo, base=base, divScheme=_schemes_of_the_step(ff, j))
     return case, run
+
+
+def _schemes_of_the_step(ff, j):
+    """system/fvSchemes against what this step discretises with (icoFoam.C:55-103): every look-up the application makes is made
+    here with the reference's rules (FvSchemes), and a scheme the step does not implement is refused by name instead of being
+    silently replaced.  Returns the interpolation scheme of div(phi,U).  A case without system/fvSchemes (the reference would not
+    start) runs with the cavity tutorial's schemes."""
+    import os
+    path = j("system", "fvSchemes")
+    if not (os.path.exists(path) or os.path.exists(path + ".gz")):
+        return "linear"
+    fs = ff.FvSchemes(ff.read_dict(path))
+
+    def need(what, got, allowed):
+        if [str(t) for t in got] not in allowed:
+            raise NotImplementedError(f"fvSchemes: {what} {' '.join(str(t) for t in got)} -- this step implements "
+                                      + " | ".join(" ".join(a) for a in allowed))
+
+    need("ddt(U)", fs.ddt("ddt(U)"), [["Euler"]])
+    for g in ("grad(p)", "grad(U)"):
+        need(g, fs.grad(g), [["Gauss", "linear"]])
+    for lap in ("laplacian(nu,U)", "laplacian((1|A(U)),p)"):
+        need(lap, fs.laplacian(lap), [["Gauss", "linear", c] for c in ("corrected", "uncorrected", "orthogonal")])
+    need("interpolate(HbyA)", fs.interpolation("interpolate(HbyA)"), [["linear"]])
+    if not fs.fluxRequired("p"):
+        raise ValueError("fvSchemes: fluxRequired has no entry for p (fvMatrix::flux() of the pressure equation needs it, fvMatrix.C:857-866)")
+    name, _, _ = ff.convection_scheme(fs.div("div(phi,U)"))
+    if name not in ("linear", "upwind"):
+        raise NotImplementedError(f"fvSchemes: div(phi,U) Gauss {name} -- limited schemes are built for scalar fields only "
+                                  "(b200ldu_fv_limiter); this step implements Gauss linear | Gauss upwind")
+    return name
 
 
 def run_case(capi, ctx, torch, caseDir, log=print, write=True, maxSteps=None, rank=None, allsum=None):
@@ -414,7 +452,7 @@ def run_case(capi, ctx, torch, caseDir, log=print, write=True, maxSteps=None, ra
         t += run["deltaT"]
         log(f"Time = {_time_name(t)}\n")
         perfs, cont = case.step(run["nCorr"], run["nNonOrthCorr"], run["UControls"] or None, run["pControls"] or None,
-                                run["momentumPredictor"], run["USolver"], run["pSolver"], gamg)
+                                run["momentumPredictor"], run["USolver"], run["pSolver"], gamg, run["divScheme"])
         for k, pf in enumerate(perfs.get("U", [])):
             log(perf_line(pf, "U" + "xyz"[k]))
         per = len(perfs["p"]) // max(run["nCorr"], 1)

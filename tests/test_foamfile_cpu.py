@@ -482,3 +482,34 @@ def test_field_files_roundtrip(ff, tmp_path, binary):
     assert np.array_equal(p1["internalField"], pv) and np.array_equal(U1["internalField"], Uv)
     assert np.array_equal(U1["boundaryField"]["movingWall"]["value"], lid)
     assert np.array_equal(U1["boundaryField"]["fixedWalls"]["value"], [0.0, 0.0, 0.0])
+
+
+def test_fvSchemes_lookups_follow_the_reference():
+    """fvSchemes.C:36-256, :425-580: per-kind default, `default none`, regular-expression keywords, the sections that default when
+    missing, fluxRequired; keywords with balanced parentheses are single words (ISstream::read(word&))"""
+    ff = importlib.import_module("rapidcfd-dev_b200.foamfile")
+    d = ff.parse_dict("""
+ddtSchemes { default Euler; }
+gradSchemes { default Gauss linear; grad(p) leastSquares; }
+divSchemes { default none; div(phi,U) Gauss limitedLinearV 1; div((nuEff*dev(T(grad(U))))) Gauss linear;
+             "div\\(phi,(k|epsilon)\\)" bounded Gauss upwind; div(phi,alpha) Gauss vanLeer; }
+laplacianSchemes { default Gauss linear corrected; }
+fluxRequired { default no; p; }
+""")
+    assert ff.tokenize("div((nuEff*dev(T(grad(U))))) Gauss linear; f (1 2 3); g 2(4 5);") == [
+        "div((nuEff*dev(T(grad(U)))))", "Gauss", "linear", ";", "f", "(", "1", "2", "3", ")", ";", "g", "2", "(", "4", "5", ")", ";"]
+    s = ff.FvSchemes(d)
+    assert s.ddt("ddt(U)") == ["Euler"] and s.grad("grad(U)") == ["Gauss", "linear"] and s.grad("grad(p)") == ["leastSquares"]
+    assert s.div("div(phi,U)") == ["Gauss", "limitedLinearV", 1] and s.div("div((nuEff*dev(T(grad(U)))))") == ["Gauss", "linear"]
+    assert s.div("div(phi,epsilon)") == ["bounded", "Gauss", "upwind"]
+    assert s.laplacian("laplacian(nu,U)") == ["Gauss", "linear", "corrected"]
+    assert s.interpolation("interpolate(U)") == ["linear"] and s.snGrad("snGrad(p)") == ["corrected"]     # missing sections
+    assert s.fluxRequired("p") and not s.fluxRequired("U")
+    with pytest.raises(KeyError, match="keyword div\\(phi,T\\) is undefined"):
+        s.div("div(phi,T)")
+    assert ff.convection_scheme(s.div("div(phi,k)")) == ("upwind", 1.0, True)
+    assert ff.convection_scheme(["Gauss", "limitedLinear", 0.33]) == ("limitedLinear", 0.33, False)
+    with pytest.raises(ValueError, match="Unknown discretisation scheme QUICK"):
+        ff.convection_scheme(["Gauss", "QUICK"])
+    with pytest.raises(ValueError, match="Unknown convection type"):
+        ff.convection_scheme(["linear"])

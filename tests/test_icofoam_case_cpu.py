@@ -191,3 +191,50 @@ def test_run_case_on_processor_directories(meshmod, orc, tmp_path):
         assert text.count("time step continuity errors") == 4
         tdir = os.path.join(root, f"processor{r}", ico._time_name(2 * dt))
         np.testing.assert_allclose(ff.read_field(os.path.join(tdir, "p"))["internalField"], p, rtol=1e-15)
+
+
+FVSCHEMES = """FoamFile { version 2.0; format ascii; class dictionary; object fvSchemes; }
+ddtSchemes { default Euler; }
+gradSchemes { default Gauss linear; grad(p) Gauss linear; }
+divSchemes { default none; div(phi,U) Gauss %s; }
+laplacianSchemes { default none; laplacian(nu,U) Gauss linear orthogonal; laplacian((1|A(U)),p) Gauss linear orthogonal; }
+interpolationSchemes { default linear; interpolate(HbyA) linear; }
+snGradSchemes { default orthogonal; }
+fluxRequired { default no; p; }
+"""
+
+
+def test_run_case_honours_fvSchemes(meshmod, orc, tmp_path):
+    """div(phi,U) Gauss upwind from system/fvSchemes reaches the momentum matrix (keywords with parentheses are single words,
+    as ISstream reads them); a scheme the step does not implement, or a missing entry under `default none`, is refused"""
+    ff = importlib.import_module("rapidcfd-dev_b200.foamfile")
+    ico = importlib.import_module("rapidcfd-dev_b200.icofoam")
+    n = 6
+    root = str(tmp_path / "cavity")
+    m, dt = write_cavity(ff, meshmod, root, n)
+    schemes = os.path.join(root, "system", "fvSchemes")
+    open(schemes, "w").write(FVSCHEMES % "upwind")
+    capi, ctx, torch = oracle_backend.fixture()
+    case, hist = ico.run_case(capi, ctx, torch, root, log=lambda *_: None, write=False)
+    ctl = dict(tolerance=1e-12, relTol=0.0)
+    refs = {}
+    for scheme in ("upwind", "linear"):
+        _, ref = po.cavity_from_hex(orc, meshmod, n, nu=0.01, deltaT=dt)
+        for _ in range(2):
+            ref.step(UControls=ctl, pControls=ctl, divScheme=scheme)
+        refs[scheme] = ref.U.copy()
+    U = case.U.numpy().reshape(-1, 3)
+    np.testing.assert_allclose(U, refs["upwind"], rtol=0, atol=1e-8)
+    assert np.abs(refs["upwind"] - refs["linear"]).max() > 1e-4          # the scheme is visible in the result
+    open(schemes, "w").write(FVSCHEMES % "limitedLinearV 1")
+    with pytest.raises(ValueError, match="Unknown discretisation scheme limitedLinearV"):
+        ico.run_case(capi, ctx, torch, root, log=lambda *_: None, write=False)
+    open(schemes, "w").write(FVSCHEMES % "vanLeer")
+    with pytest.raises(NotImplementedError, match="scalar fields only"):
+        ico.run_case(capi, ctx, torch, root, log=lambda *_: None, write=False)
+    open(schemes, "w").write((FVSCHEMES % "linear").replace("div(phi,U) Gauss linear;", ""))
+    with pytest.raises(KeyError, match=r"keyword div\(phi,U\) is undefined in dictionary"):
+        ico.run_case(capi, ctx, torch, root, log=lambda *_: None, write=False)
+    open(schemes, "w").write((FVSCHEMES % "linear").replace("default Euler", "default CrankNicolson 0.9"))
+    with pytest.raises(NotImplementedError, match="ddt"):
+        ico.run_case(capi, ctx, torch, root, log=lambda *_: None, write=False)
