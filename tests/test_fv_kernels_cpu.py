@@ -7,7 +7,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from test_host_kernels_cpu import Host, _d, hk  # noqa: F401  (fixture: the host build of the kernels)
+from test_host_kernels_cpu import Host, _d, hk, run_all  # noqa: F401  (hk: fixture, the host build of the kernels)
 
 
 class _Graph:
@@ -74,3 +74,20 @@ def test_neg_sum_diag_on_the_host(hk, meshmod, orc):  # noqa: F811
         lo, up2, dg2 = (np.ascontiguousarray(x) for x in orc.convection_fill(a, wts, phi - 0.5))
         hk.hk_neg_sum_diag(H.p(), _d(up2), _d(lo), _d(out))
         assert np.array_equal(out, dg2), name
+
+
+@pytest.mark.parametrize("nc", [1, 3])
+def test_fvmatrix_kernels_on_a_random_graph(hk, orc, nc):  # noqa: F811
+    """A, H, flux, boundary folding, relax, setReference (csrc/fvmatrix_kernels.cuh) on rows with up to a dozen faces per side and
+    several boundary faces per cell: the loops behind the prefetched first batch of H and relax"""
+    g = _Graph(260, 4, 11)
+    rng = np.random.default_rng(12)
+    n, nF = g.nCells, g.nFaces
+    bfc = rng.integers(0, n, 140).astype(np.int32)
+    a = orc.Addr(n, g.lower, g.upper)
+    upper, lower = rng.uniform(-1, 1, nF), rng.uniform(-1, 1, nF)
+    d = dict(diag=rng.uniform(8, 12, n), upper=upper, lower=None if nc == 1 else lower, source=rng.uniform(-1, 1, (n, nc)) if nc > 1 else
+             rng.uniform(-1, 1, n), bfc=bfc, ic=rng.uniform(0, 1, (len(bfc), nc)), bc=rng.uniform(-1, 1, (len(bfc), nc)),
+             V=rng.uniform(0.5, 2, n))
+    assert np.bincount(g.lower, minlength=n).max() > 3 and np.bincount(g.upper, minlength=n).max() > 3
+    run_all(hk, orc, a, d, nc, rng.uniform(-1, 1, (n, nc)))

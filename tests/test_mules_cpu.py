@@ -365,3 +365,28 @@ def test_limited_update_is_bounded_and_conservative(meshmod):
     lo, hi, massL = advect(meshmod, True)
     assert lo.min() >= -1e-12 and hi.max() <= 1 + 1e-12        # MULES keeps psi within [psiMin, psiMax]
     assert np.allclose(massL, massL[0], rtol=1e-13) and np.allclose(mass, massL[0], rtol=1e-13)   # fluxes only: conservative
+
+
+@pytest.mark.parametrize("corr", [0, 1])
+def test_device_mules_code_on_a_random_graph(hk, orc, corr):  # noqa: F811
+    """rows with up to a dozen faces per side, several boundary faces per cell, cells without owner or neighbour faces"""
+    from test_fv_kernels_cpu import _Graph
+    g = _Graph(240, 4, 21)
+    rng = np.random.default_rng(22)
+    n, nF = g.nCells, g.nFaces
+    bfc = rng.integers(0, n, 130).astype(np.int32)
+    nB = len(bfc)
+    H = Host(orc.Addr(n, g.lower, g.upper), dict(bfc=bfc, diag=np.zeros(n), upper=np.zeros(nF), lower=None))
+    f = lambda x: np.ascontiguousarray(x, np.float64)
+    psi, psiB, V = f(rng.uniform(0, 1, n)), f(rng.uniform(0, 1, nB)), f(rng.uniform(0.5, 2, n))
+    bd, bdB = f(rng.uniform(-1, 1, nF) * 1e-2), f(rng.uniform(-1, 1, nB) * 1e-2)
+    pc, pcB = f(rng.uniform(-1, 1, nF) * 1e-2), f(rng.uniform(-1, 1, nB) * 1e-2)
+    rho, Sp, Su = f(rng.uniform(0.9, 1.1, n)), f(-rng.uniform(0, 1, n)), f(rng.uniform(0, 0.1, n))
+    hk.hk_mules_limiter.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 12 + [C.c_double, C.c_double] + [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_double]
+    lam, lamB, scratch = np.ones(nF), np.ones(nB), np.zeros(6 * n)
+    hk.hk_mules_limiter(H.p(), 3, 20.0, _d(rho), _d(rho), _d(psi), _d(psi), _d(psiB), None if corr else _d(bd), _d(bdB), _d(pc), _d(pcB),
+                        _d(Sp), _d(Su), _d(V), 1.0, 0.0, _d(lam), _d(lamB), _d(scratch), 0, corr, 0.1 if corr else 0.0)
+    want, wantB = mo.limiter(n, g.lower, g.upper, bfc, V, 20.0, psi, psi, psiB, bd, bdB, pc, pcB, 1.0, 0.0, 3, rho, rho, Sp, Su,
+                             corr=bool(corr), extremaCoeff=0.1 if corr else 0.0)
+    assert np.array_equal(lam, want) and np.array_equal(lamB, wantB)
+    assert (lam < 1).sum() > 20                       # the limiter is active on this case
