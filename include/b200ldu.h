@@ -285,6 +285,9 @@ int b200ldu_field_binary(b200ldu_ctx *ctx, int op, long long n, int nCompA, cons
                          const double *b_d, double *out_d);
 int b200ldu_field_unary(b200ldu_ctx *ctx, int op, long long n, double s, const double *a_d, double *out_d);
 int b200ldu_field_dot3(b200ldu_ctx *ctx, long long n, const double *a_d, const double *b_d, double *out_d);
+/* magSqr(symm(T)) per element of a tensor field [n*9] (TensorI.H:483-491, SymmTensorI.H:276-284): the k-epsilon production term
+ * G = nut*2*magSqr(symm(fvc::grad(U))) (kEpsilon.C:235) takes its tensor from b200ldu_fv_grad_linear(nComp = 3) */
+int b200ldu_field_symm_magsqr(b200ldu_ctx *ctx, long long n, const double *tensor_d, double *out_d);
 int b200ldu_field_gather(b200ldu_ctx *ctx, int n, int nComp, const int *cells_d, const double *field_d, double *out_d);
 /* snGradScheme::snGrad on the internal faces (FV/finiteVolume/snGradSchemes/snGradScheme/snGradScheme.C:101-160):
  * out[f] = deltaCoeffs[f]*(vf[nei] - vf[own]).  With it fvc::laplacian (gaussLaplacianSchemes.C:95-112: div(gamma*snGrad*magSf))

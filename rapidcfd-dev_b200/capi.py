@@ -67,7 +67,7 @@ EXPORTS = [
     "b200ldu_fvm_add_boundary_diag", "b200ldu_fvm_add_boundary_source", "b200ldu_fvm_A", "b200ldu_fvm_H",
     "b200ldu_fvm_flux", "b200ldu_fvm_residual", "b200ldu_fvm_relax", "b200ldu_fvm_set_reference",
     "b200ldu_fvm_solve", "b200ldu_fv_patch_neighbour_field",
-    "b200ldu_mules_limiter", "b200ldu_mules_limiter_corr", "b200ldu_ldu_row_sum", "b200ldu_ldu_add_assign", "b200ldu_ldu_scale", "b200ldu_fv_sngrad", "b200ldu_fv_limiter", "b200ldu_fv_limited_weights", "b200ldu_field_binary", "b200ldu_field_unary", "b200ldu_field_dot3", "b200ldu_field_gather",
+    "b200ldu_mules_limiter", "b200ldu_mules_limiter_corr", "b200ldu_ldu_row_sum", "b200ldu_ldu_add_assign", "b200ldu_ldu_scale", "b200ldu_fv_sngrad", "b200ldu_fv_limiter", "b200ldu_fv_limited_weights", "b200ldu_field_binary", "b200ldu_field_unary", "b200ldu_field_dot3", "b200ldu_field_symm_magsqr", "b200ldu_field_gather",
 ]
 
 _lib = None
@@ -154,6 +154,7 @@ def lib():
     L.b200ldu_field_binary.argtypes = [vp, C.c_int, C.c_longlong, C.c_int, vp, C.c_int, vp, vp]
     L.b200ldu_field_unary.argtypes = [vp, C.c_int, C.c_longlong, C.c_double, vp, vp]
     L.b200ldu_field_dot3.argtypes = [vp, C.c_longlong, vp, vp, vp]
+    L.b200ldu_field_symm_magsqr.argtypes = [vp, C.c_longlong, vp, vp]
     L.b200ldu_field_gather.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     L.b200ldu_fvm_solve.argtypes = [vp, C.c_int, C.c_char_p, C.c_char_p, C.POINTER(Controls), vp, vp, vp, vp, vp, vp,
                                     C.POINTER(Perf)]
@@ -529,6 +530,20 @@ class FieldOps:
 
     def sdiv(self, a, s):            # a/s
         return self.unary(9, a, s)
+
+    def smax(self, a, s):            # max(a, s)
+        return self.unary(7, a, s)
+
+    def pos(self, a):                # pos(a): 1 where a >= 0, else 0
+        return self.unary(11, a)
+
+    def bmax(self, a, b):            # max(a, b) per element
+        return self.binary(self.MAX, a, b)
+
+    def symm_magsqr(self, T):        # magSqr(symm(T)), T [n*9]
+        out = self._new(T, T.numel() // 9)
+        check(lib().b200ldu_field_symm_magsqr(self.ctx.h, T.numel() // 9, _dp(T), _dp(out)))
+        return out
 
     def dot3(self, a, b):
         out = self._new(a, a.numel() // 3)

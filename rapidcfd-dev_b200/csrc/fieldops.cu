@@ -51,6 +51,17 @@ extern "C" int b200ldu_field_dot3(b200ldu_ctx *ctx, long long n, const double *a
     return B200LDU_OK;
 }
 
+extern "C" int b200ldu_field_symm_magsqr(b200ldu_ctx *ctx, long long n, const double *tensor_d, double *out_d)
+{
+    if (!ctx || !tensor_d || !out_d || n < 0) return B200LDU_EINVAL;
+    if (n == 0) return B200LDU_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    symm_magsqr_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, tensor_d, out_d);
+    ctx->launches++;
+    KERNEL_CHECK();
+    return B200LDU_OK;
+}
+
 extern "C" int b200ldu_field_gather(b200ldu_ctx *ctx, int n, int nComp, const int *cells_d, const double *field_d,
                                     double *out_d)
 {

@@ -68,6 +68,26 @@ __global__ void dot3_kernel(long long n, const double *__restrict__ a, const dou
     out[i] = __dadd_rn(s, __dmul_rn(a[3 * i + 2], b[3 * i + 2]));
 }
 
+// magSqr(symm(T)) per element of a tensor field (9 components, row-major T[i][j] as gauss_grad / grad_linear write it): the
+// production term of the k-epsilon model, G = nut*2*magSqr(symm(fvc::grad(U))) (kEpsilon.C:235).  symm (TensorI.H:483-491):
+// (xx, 0.5*(xy + yx), 0.5*(xz + zx), yy, 0.5*(yz + zy), zz); magSqr of a SymmTensor (SymmTensorI.H:276-284):
+// magSqr(xx) + 2*magSqr(xy) + 2*magSqr(xz) + magSqr(yy) + 2*magSqr(yz) + magSqr(zz), added left to right
+__global__ void symm_magsqr_kernel(long long n, const double *__restrict__ T, double *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *t = T + 9 * i;
+    const double xx = t[0], yy = t[4], zz = t[8];
+    const double xy = __dmul_rn(0.5, __dadd_rn(t[1], t[3])), xz = __dmul_rn(0.5, __dadd_rn(t[2], t[6])),
+                 yz = __dmul_rn(0.5, __dadd_rn(t[5], t[7]));
+    double s = __dmul_rn(xx, xx);
+    s = __dadd_rn(s, __dmul_rn(2.0, __dmul_rn(xy, xy)));
+    s = __dadd_rn(s, __dmul_rn(2.0, __dmul_rn(xz, xz)));
+    s = __dadd_rn(s, __dmul_rn(yy, yy));
+    s = __dadd_rn(s, __dmul_rn(2.0, __dmul_rn(yz, yz)));
+    out[i] = __dadd_rn(s, __dmul_rn(zz, zz));
+}
+
 // snGradScheme::snGrad on the internal faces (snGradScheme.C:101-160): d*(vf[nei] - vf[own])
 __global__ void sngrad_kernel(int nFaces, int nc, const int *__restrict__ l, const int *__restrict__ u,
                               const double *__restrict__ delta, const double *__restrict__ vf, double *__restrict__ out)

@@ -143,6 +143,7 @@ void hk_field_unary(int op, long long n, double s, const double *a, double *out)
 }
 
 void hk_field_dot3(long long n, const double *a, const double *b, double *out) { launch(n, 256, fieldk::dot3_kernel, n, a, b, out); }
+void hk_field_symm_magsqr(long long n, const double *T, double *out) { launch(n, 256, fieldk::symm_magsqr_kernel, n, T, out); }
 
 void hk_field_gather(int n, int nc, const int *cells, const double *f, double *out)
 {

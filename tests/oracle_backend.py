@@ -215,6 +215,19 @@ class FieldOps:
     def sdiv(self, a, s):
         return self._t(_np(a) / s)
 
+    def smax(self, a, s):
+        return self._t(np.maximum(_np(a), s))
+
+    def pos(self, a):
+        return self._t(np.where(_np(a) >= 0, 1.0, 0.0))
+
+    def bmax(self, a, b):
+        return self._t(np.maximum(_np(a), _np(b)))
+
+    def symm_magsqr(self, T):
+        from oracle import kepsilon_oracle as ko
+        return self._t(ko.symm_magsqr(_np(T).reshape(-1, 9)))
+
     def dot3(self, a, b):
         A, B = _np(a).reshape(-1, 3), _np(b).reshape(-1, 3)
         return self._t((A[:, 0] * B[:, 0] + A[:, 1] * B[:, 1]) + A[:, 2] * B[:, 2])
