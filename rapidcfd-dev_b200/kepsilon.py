@@ -66,7 +66,8 @@ class KEpsilon:
         new = psi.clone()
         eqn = capi.FvMatrix(self.mat, 1, diag, source, new, c.V, ic, bc)
         if alpha is not None:
-            eqn.relax(alpha)
+            eqn.relax(alpha)                     # in place on diag / source (fvMatrix.C:1088-1345) ...
+            self.mat.set(diag, upper, lower)     # ... and the matrix holds copies: it takes the relaxed diagonal here
         perf = eqn.solve("PBiCG", "DILU", **ctl)[0]
         return new, perf
 

@@ -46,7 +46,9 @@ class LduMatrix:
 
     def set(self, diag, upper, lower=None, bou=None, intc=None):
         self.m = orc.Matrix(self.addr.o, _np(diag), _np(upper), _np(lower), _np(bou), _np(intc))
-        self.coeffs = (diag, upper, lower, bou, intc)
+        # the library copies the coefficients (b200ldu_matrix_set): a later change of the caller's arrays -- fvMatrix::relax,
+        # setReference -- does not reach A / H / flux / residual / solve until the matrix is set again
+        self.coeffs = tuple(None if x is None else x.clone() for x in (diag, upper, lower, bou, intc))
         return self
 
     def _t(self, a):
@@ -100,9 +102,9 @@ class FvMatrix:
         self.diag, self.source, self.psi, self.V, self.ic, self.bc = diag, source, psi, V, internalCoeffs, boundaryCoeffs
 
     def _o(self, diag=None, source=None):
-        _, upper, lower, bou, intc = self.m.coeffs
+        own, upper, lower, bou, intc = self.m.coeffs
         a = self.m.addr
-        return fo.FvMatrix(orc, a.o, self.nc, _np(self.diag if diag is None else diag), _np(upper), _np(lower),
+        return fo.FvMatrix(orc, a.o, self.nc, _np(own if diag is None else diag), _np(upper), _np(lower),
                            _np(self.source if source is None else source), _np(self.psi), _np(self.V), a.bfc,
                            _np(self.ic), _np(self.bc), couInt=_np(intc), couBou=_np(bou), comm=a.ctx.comm)
 
@@ -141,7 +143,7 @@ class FvMatrix:
         return self._t(self._o().residual(self._pnf(pnf)))
 
     def relax(self, alpha):
-        o = self._o()
+        o = self._o(diag=self.diag)            # b200ldu_fvm_relax works on the caller's diag / source
         o.relax(alpha)
         self.diag.copy_(self._t(o.diag))
         self.source.copy_(self._t(o.source))
